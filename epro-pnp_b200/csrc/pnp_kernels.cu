@@ -1,0 +1,943 @@
+// pnp_kernels.cu -- sm_100a kernels of the EPro-PnP hot path and their C ABI (include/epropnp_b200.h).
+//
+// Execution model (all solve kernels):
+//   * persistent grid: one 128-thread CTA works on one object at a time and strides over the batch;
+//   * the object's correspondence set {x3d, x2d, w2d} is pulled from HBM exactly once by TMA bulk
+//     copies (cp.async.bulk -> mbarrier complete_tx) into a 2-slot staging ring, re-packed into a
+//     32-byte-per-point record in shared memory, and every later pass (K+1 LM evaluations, I AMIS
+//     cost sweeps over S samples) reads shared memory only; the next object's chunks are already in
+//     flight while the current object is being solved;
+//   * LM: threads stride over points, 28 partial sums (21 J^T J + 6 J^T r + cost) are reduced with
+//     a transposed butterfly (31 shuffles per warp instead of 140) and one cross-warp pass; the 6x6
+//     damped Cholesky solve, SE(3) retraction and trust-region logic run on one thread out of
+//     shared memory;
+//   * AMIS: one thread owns one sample of the iteration: draws it (injected noise or Philox), sweeps
+//     all N points with the pre-multiplied projection K[R|t] (points are smem broadcasts), evaluates
+//     the proposal densities it needs; the proposal refit is a handful of block reductions.
+// No tensor cores: the only contraction is 6-deep, the work is FP32-pipe + MUFU bound.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "pnp_math.cuh"
+
+namespace {
+using namespace pnp;
+
+constexpr int NT = 128;                 // threads per CTA
+constexpr int NW = NT / 32;
+constexpr int CH = 128;                 // correspondences per TMA chunk (2 slots x 3.5 KB)
+constexpr int STAGE_FLOATS = CH * 7;    // x3d (3) + x2d (2) + w2d (2)
+constexpr int MAX_ITER = 8;             // AMIS iterations supported (reference default 4)
+constexpr int PROP_FLOATS = 19;         // proposals dump: mu3, Lt6, Lr10
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+thread_local int g_last_cuda_error = 0;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + 1-D TMA bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct FastRcp {
+    __device__ __forceinline__ float operator()(float x) const { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+};
+struct FastSqrt {
+    __device__ __forceinline__ float operator()(float x) const { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct KArgs {
+    const float *x3d, *x2d, *w2d, *cam, *lb, *ub, *delta;
+    const float *pose_init;                 // LM entry
+    const float *pose_opt_in, *pose_cov_in; // AMIS-only entry
+    const float *noise_n3, *noise_chi2, *noise_rot;
+    const float *poses;                     // cost-only entry: (S, B, D)
+    float *pose_opt, *pose_cov, *cost, *pose_plus, *cost_init;
+    float *pose_samples, *logw, *proposals;
+    float *cost_out;                        // cost-only entry: (S, B)
+    int B, N, S_eval, use_tma;
+    uint32_t obj_offset;
+    uint64_t seed;
+    Params p;
+};
+
+// Static part of the shared-memory image (the dynamic arrays follow it).
+template <int DOF> struct SmemHead {
+    uint64_t bar[2];
+    float red[NW * 32];
+    float ev[32];                           // reduced evaluation: NV floats
+    LMState<DOF> lm;
+    float cov[DOF * DOF];
+    Proposal6 prop[MAX_ITER];
+};
+
+struct SmemPlan {        // offsets in floats from the start of dynamic smem
+    int stage, pts, smp, cost, logp, lw, total_bytes;
+};
+
+template <int DOF>
+__host__ __device__ inline SmemPlan plan_smem(int N, int M, int I, bool amis) {
+    SmemPlan s;
+    int off = (int)((sizeof(SmemHead<DOF>) + 127) / 128 * 128 / 4);
+    s.stage = off; off += 2 * STAGE_FLOATS;
+    s.pts = off; off += 8 * ((N + 3) / 4 * 4);
+    s.smp = off; if (amis) off += Dim<DOF>::POSE * M;
+    s.cost = off; if (amis) off += M;
+    s.logp = off; if (amis) off += I * M;
+    s.lw = off; if (amis) off += M;
+    s.total_bytes = off * 4;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Correspondence loader: TMA ring (or plain loads when pointers / N break the 16-byte rules).
+struct Loader {
+    const KArgs& a;
+    uint64_t* bar;
+    float* stage;
+    int nch, n_my, total;
+
+    __device__ Loader(const KArgs& a_, uint64_t* bar_, float* stage_) : a(a_), bar(bar_), stage(stage_) {
+        nch = (a.N + CH - 1) / CH;
+        n_my = ((int)blockIdx.x < a.B) ? (a.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        total = n_my * nch;
+    }
+    __device__ void issue(int c) {          // one thread
+        const int obj = (int)blockIdx.x + (c / nch) * (int)gridDim.x;
+        const int k = c % nch;
+        const int npts = min(CH, a.N - k * CH);
+        const size_t first = (size_t)obj * a.N + (size_t)k * CH;
+        float* dst = stage + (c & 1) * STAGE_FLOATS;
+        uint64_t* b = bar + (c & 1);
+        mbar_expect_tx(b, (uint32_t)npts * 28u);
+        tma_load_1d(dst, a.x3d + first * 3, (uint32_t)npts * 12u, b);
+        tma_load_1d(dst + CH * 3, a.x2d + first * 2, (uint32_t)npts * 8u, b);
+        tma_load_1d(dst + CH * 5, a.w2d + first * 2, (uint32_t)npts * 8u, b);
+    }
+    __device__ void prologue() {
+        if (a.use_tma && threadIdx.x == 0) {
+            mbar_init(bar + 0, 1);
+            mbar_init(bar + 1, 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        if (a.use_tma && threadIdx.x == 0) {
+            if (total > 0) issue(0);
+            if (total > 1) issue(1);
+        }
+    }
+    // Bring object number `it` of this CTA into the packed point array. Ends with a __syncthreads.
+    __device__ void load_object(int it, int obj, float4* pts4) {
+        const int tid = threadIdx.x;
+        if (a.use_tma) {
+            for (int k = 0; k < nch; ++k) {
+                const int c = it * nch + k;
+                const float* st = stage + (c & 1) * STAGE_FLOATS;
+                mbar_wait(bar + (c & 1), (uint32_t)((c >> 1) & 1));
+                const int npts = min(CH, a.N - k * CH);
+                for (int n = tid; n < npts; n += NT) {
+                    const float X = st[3 * n], Y = st[3 * n + 1], Z = st[3 * n + 2];
+                    const float2 uv = reinterpret_cast<const float2*>(st + CH * 3)[n];
+                    const float2 w = reinterpret_cast<const float2*>(st + CH * 5)[n];
+                    pts4[2 * (k * CH + n)] = make_float4(X, Y, Z, uv.x);
+                    pts4[2 * (k * CH + n) + 1] = make_float4(uv.y, w.x, w.y, 0.f);
+                }
+                __syncthreads();            // slot drained (and, after the last chunk, pts complete)
+                if (tid == 0 && c + 2 < total) { fence_proxy_async(); issue(c + 2); }
+            }
+        } else {
+            const float* g3 = a.x3d + (size_t)obj * a.N * 3;
+            const float* g2 = a.x2d + (size_t)obj * a.N * 2;
+            const float* gw = a.w2d + (size_t)obj * a.N * 2;
+            for (int n = tid; n < a.N; n += NT) {
+                pts4[2 * n] = make_float4(__ldg(g3 + 3 * n), __ldg(g3 + 3 * n + 1), __ldg(g3 + 3 * n + 2), __ldg(g2 + 2 * n));
+                pts4[2 * n + 1] = make_float4(__ldg(g2 + 2 * n + 1), __ldg(gw + 2 * n), __ldg(gw + 2 * n + 1), 0.f);
+            }
+            __syncthreads();
+        }
+    }
+};
+
+__device__ __forceinline__ Cam load_cam(const KArgs& a, int obj) {
+    Cam c;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) c.k[i] = __ldg(a.cam + (size_t)obj * 9 + i);
+    c.z_min = a.p.z_min;
+    c.bounded = (a.lb != nullptr && a.ub != nullptr) ? 1 : 0;
+    if (c.bounded) {
+        c.lbx = __ldg(a.lb + 2 * obj); c.lby = __ldg(a.lb + 2 * obj + 1);
+        c.ubx = __ldg(a.ub + 2 * obj); c.uby = __ldg(a.ub + 2 * obj + 1);
+    } else {
+        c.lbx = c.lby = -CUDART_INF_F; c.ubx = c.uby = CUDART_INF_F;
+    }
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reductions
+// 32 values per lane -> lane j holds the warp total of v[j]   (31 shuffles)
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const float keep = up ? v[k + half] : v[k];
+            const float send = up ? v[k] : v[k + half];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+template <int K> __device__ __forceinline__ void block_sum(float (&v)[K], float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) red[warp * 32 + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = (red[k] + red[32 + k]) + (red[64 + k] + red[96 + k]);
+    __syncthreads();
+}
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) red[warp * 32] = v;
+    __syncthreads();
+    v = fmaxf(fmaxf(red[0], red[32]), fmaxf(red[64], red[96]));
+    __syncthreads();
+    return v;
+}
+
+// Evaluate the normal equations at `pose` (shared memory) over all points; result in ev[0..NV).
+template <int DOF, bool CLIP>
+__device__ void eval_normal_eq(const float4* pts4, int N, const float* pose, const Cam& cam, float delta,
+                               float huber_eps, float* red, float* ev) {
+    constexpr int NV = Dim<DOF>::NV;
+    float R[9], t[3];
+    {
+        float ps[Dim<DOF>::POSE];
+#pragma unroll
+        for (int i = 0; i < Dim<DOF>::POSE; ++i) ps[i] = pose[i];
+        pose_to_rot<DOF>(ps, R);
+        t[0] = ps[0]; t[1] = ps[1]; t[2] = ps[2];
+    }
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int n = threadIdx.x; n < N; n += NT) {
+        const float4 p0 = pts4[2 * n], p1 = pts4[2 * n + 1];
+        point_normal_eq<DOF, CLIP>(R, t, cam, delta, huber_eps, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, acc);
+    }
+    const float tot = warp_transpose_sum(acc);
+    red[(threadIdx.x >> 5) * 32 + (threadIdx.x & 31)] = tot;
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        const int j = threadIdx.x;
+        ev[j] = (red[j] + red[32 + j]) + (red[64 + j] + red[96 + j]);
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// LM / GN solve of the object resident in pts4.  Leaves the solution in sh.lm.pose, the covariance
+// in sh.cov (when want_cov) and writes the requested outputs.
+template <int DOF>
+__device__ void lm_phase(const KArgs& a, SmemHead<DOF>& sh, const float4* pts4, const Cam& cam, float delta,
+                         int obj, bool want_cov) {
+    constexpr int PD = Dim<DOF>::POSE;
+    const Params& p = a.p;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < PD; ++i) sh.lm.pose[i] = __ldg(a.pose_init + (size_t)obj * PD + i);
+        sh.lm.radius = p.initial_radius;
+        sh.lm.shrink = 2.0f;
+    }
+    __syncthreads();
+    if (!p.fast_mode) {
+        eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);
+        if (tid == 0) {
+            lm_adopt<DOF>(sh.lm, sh.ev);
+            if (a.cost_init) a.cost_init[obj] = sh.lm.cost;
+            if (p.lm_iter > 0) lm_propose<DOF>(sh.lm, p);
+        }
+        __syncthreads();
+        for (int it = 0; it < p.lm_iter; ++it) {
+            eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose_new, cam, delta, p.huber_eps, sh.red, sh.ev);
+            if (tid == 0) {
+                lm_update<DOF>(sh.lm, sh.ev, p);
+                if (it + 1 < p.lm_iter) lm_propose<DOF>(sh.lm, p);
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int it = 0; it < p.lm_iter; ++it) {
+            eval_normal_eq<DOF, false>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);
+            if (tid == 0) {
+                lm_adopt<DOF>(sh.lm, sh.ev);                 // kept for covariance / cost (pre-step)
+                if (it == 0 && a.cost_init) a.cost_init[obj] = sh.lm.cost;
+                gn_advance<DOF>(sh.lm.pose, sh.ev, p.eps, sh.lm.pose);
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < PD; ++i) a.pose_opt[(size_t)obj * PD + i] = sh.lm.pose[i];
+        if (a.cost) a.cost[obj] = sh.lm.cost;
+        if (want_cov) {
+            pose_covariance<DOF>(sh.lm.a, p.eps, sh.cov);
+            if (a.pose_cov) {
+#pragma unroll
+                for (int i = 0; i < DOF * DOF; ++i) a.pose_cov[(size_t)obj * DOF * DOF + i] = sh.cov[i];
+            }
+        }
+    }
+    if (a.pose_plus) {      // y* (+) one undamped GN step, clip_jac always on (gn_step default)
+        eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);
+        if (tid == 0) {
+            float plus[PD];
+            gn_advance<DOF>(sh.lm.pose, sh.ev, p.eps, plus);
+#pragma unroll
+            for (int i = 0; i < PD; ++i) a.pose_plus[(size_t)obj * PD + i] = plus[i];
+        }
+    }
+    __syncthreads();
+}
+
+// Huber cost of one pose over every resident point (thread-private sweep, points are broadcasts).
+template <bool BOUNDED>
+__device__ __forceinline__ float sweep_cost(const float4* pts4, int N, const float* P, const Cam& cam, float delta) {
+    const float half_d2 = 0.5f * delta * delta;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    int n = 0;
+    for (; n + 4 <= N; n += 4) {
+        const float4 a0 = pts4[2 * n], b0 = pts4[2 * n + 1];
+        const float4 a1 = pts4[2 * n + 2], b1 = pts4[2 * n + 3];
+        const float4 a2 = pts4[2 * n + 4], b2 = pts4[2 * n + 5];
+        const float4 a3 = pts4[2 * n + 6], b3 = pts4[2 * n + 7];
+        c0 += point_cost<BOUNDED>(P, cam, delta, half_d2, a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, FastRcp(), FastSqrt());
+        c1 += point_cost<BOUNDED>(P, cam, delta, half_d2, a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, FastRcp(), FastSqrt());
+        c2 += point_cost<BOUNDED>(P, cam, delta, half_d2, a2.x, a2.y, a2.z, a2.w, b2.x, b2.y, b2.z, FastRcp(), FastSqrt());
+        c3 += point_cost<BOUNDED>(P, cam, delta, half_d2, a3.x, a3.y, a3.z, a3.w, b3.x, b3.y, b3.z, FastRcp(), FastSqrt());
+    }
+    for (; n < N; ++n) {
+        const float4 a0 = pts4[2 * n], b0 = pts4[2 * n + 1];
+        c0 += point_cost<BOUNDED>(P, cam, delta, half_d2, a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, FastRcp(), FastSqrt());
+    }
+    return (c0 + c1) + (c2 + c3);
+}
+
+template <int DOF>
+__device__ __forceinline__ float pose_cost(const float4* pts4, int N, const float* pose, const Cam& cam, float delta) {
+    float R[9], P[12];
+    pose_to_rot<DOF>(pose, R);
+    make_proj(cam.k, R, pose, P);
+    return cam.bounded ? sweep_cost<true>(pts4, N, P, cam, delta) : sweep_cost<false>(pts4, N, P, cam, delta);
+}
+
+// ------------------------------------------------------------------------------------------------
+// AMIS loop for the resident object (6DoF).  sh.prop[0] must not be set yet; pose / cov are read from
+// pose_opt[7] / cov[36] (shared or registers of thread 0 -- passed as shared pointers).
+__device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float4* pts4, float* smp, float* cst,
+                            float* logp, float* lw, const Cam& cam, float delta, int obj,
+                            const float* pose_opt, const float* cov) {
+    const Params& p = a.p;
+    const int tid = threadIdx.x;
+    const int M = p.mc_samples, I = p.mc_iter, S = M / I;
+    const bool injected = a.noise_n3 != nullptr;
+
+    if (tid == 0) initial_fit6(pose_opt, cov, p.acg_dispersion, sh.prop[0]);
+    __syncthreads();
+
+    for (int i = 0; i < I; ++i) {
+        // ---- draw, cost, densities of the new samples (one sample per thread and pass)
+        for (int s = tid; s < S; s += NT) {
+            const int m = i * S + s;
+            float n3[3], n4[4], chi2;
+            if (injected) {
+                const size_t g = (size_t)obj * M + m;
+                n3[0] = __ldg(a.noise_n3 + g * 3); n3[1] = __ldg(a.noise_n3 + g * 3 + 1); n3[2] = __ldg(a.noise_n3 + g * 3 + 2);
+                chi2 = __ldg(a.noise_chi2 + g);
+                n4[0] = __ldg(a.noise_rot + g * 4); n4[1] = __ldg(a.noise_rot + g * 4 + 1);
+                n4[2] = __ldg(a.noise_rot + g * 4 + 2); n4[3] = __ldg(a.noise_rot + g * 4 + 3);
+            } else {
+                draw_base_noise(a.seed, a.obj_offset + (uint32_t)obj, (uint32_t)m, n3, chi2, n4);
+            }
+            float q[7];
+            proposal_draw6(sh.prop[i], n3, chi2, n4, q);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) smp[m * 7 + k] = q[k];
+            float* out = a.pose_samples + ((size_t)obj * M + m) * 7;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) out[k] = q[k];
+            cst[m] = pose_cost<6>(pts4, a.N, q, cam, delta);
+            for (int j = 0; j <= i; ++j) logp[j * M + m] = proposal_logpdf6(sh.prop[j], q);
+        }
+        // ---- the new proposal on all earlier samples
+        for (int m = tid; m < i * S; m += NT) {
+            float q[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) q[k] = smp[m * 7 + k];
+            logp[i * M + m] = proposal_logpdf6(sh.prop[i], q);
+        }
+        __syncthreads();
+        // ---- mixture density and log-weights of all samples so far
+        const int n = (i + 1) * S;
+        const float log_cnt = logf((float)(i + 1));
+        float mx = -CUDART_INF_F;
+        for (int m = tid; m < n; m += NT) {
+            float top = logp[m];
+            for (int j = 1; j <= i; ++j) top = fmaxf(top, logp[j * M + m]);
+            float acc = 0.f;
+            for (int j = 0; j <= i; ++j) acc += expf(logp[j * M + m] - top);
+            const float v = -cst[m] - ((top + logf(acc)) - log_cnt);
+            lw[m] = v;
+            mx = fmaxf(mx, v);
+        }
+        if (i == I - 1) {
+            for (int m = tid; m < M; m += NT) a.logw[(size_t)obj * M + m] = lw[m];
+            break;
+        }
+        // ---- refit proposal i+1 to the weighted samples (estimate_params)
+        mx = block_max(mx, sh.red);
+        float v1[1] = {0.f};
+        for (int m = tid; m < n; m += NT) { const float e = expf(lw[m] - mx); lw[m] = e; v1[0] += e; }
+        block_sum<1>(v1, sh.red);
+        const float inv_sum = 1.0f / v1[0];
+        float mean[3] = {0.f, 0.f, 0.f};
+        for (int m = tid; m < n; m += NT) {
+            const float w = lw[m] * inv_sum;
+            lw[m] = w;                                   // normalised softmax weight
+            mean[0] = fmaf(w, smp[m * 7], mean[0]); mean[1] = fmaf(w, smp[m * 7 + 1], mean[1]); mean[2] = fmaf(w, smp[m * 7 + 2], mean[2]);
+        }
+        block_sum<3>(mean, sh.red);
+        // translation covariance + ACG fixed-point iterations (Lambda_0 = I)
+        float lam_inv[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) lam_inv[r] = (r % 5 == 0) ? 1.f : 0.f;
+        float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float lam10[10];
+        for (int itr = 0; itr < p.acg_mle_iter; ++itr) {
+            float acc[17];
+#pragma unroll
+            for (int r = 0; r < 17; ++r) acc[r] = 0.f;
+            for (int m = tid; m < n; m += NT) {
+                const float w = lw[m];
+                const float* q = smp + m * 7 + 3;
+                const float mq = fmaxf(quad4(lam_inv, q), p.amis_eps);
+                const float wm = w / mq;
+                acc[0] += wm;
+                int idx = 1;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
+                if (itr == 0) {
+                    const float d0 = smp[m * 7] - mean[0], d1 = smp[m * 7 + 1] - mean[1], d2 = smp[m * 7 + 2] - mean[2];
+                    acc[11] = fmaf(w * d0, d0, acc[11]); acc[12] = fmaf(w * d0, d1, acc[12]); acc[13] = fmaf(w * d0, d2, acc[13]);
+                    acc[14] = fmaf(w * d1, d1, acc[14]); acc[15] = fmaf(w * d1, d2, acc[15]); acc[16] = fmaf(w * d2, d2, acc[16]);
+                }
+            }
+            block_sum<17>(acc, sh.red);
+            if (itr == 0) {
+#pragma unroll
+                for (int r = 0; r < 6; ++r) tc[r] = acc[11 + r];
+            }
+            const float inv0 = 1.0f / acc[0];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) lam10[r] = acc[1 + r] * inv0;
+            lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
+            if (itr + 1 < p.acg_mle_iter) acg_scatter_inverse(lam10, lam_inv);
+        }
+        if (p.acg_mle_iter == 0) {      // degenerate configuration: Lambda stays the identity
+#pragma unroll
+            for (int r = 0; r < 10; ++r) lam10[r] = 0.f;
+            lam10[0] = lam10[4] = lam10[7] = lam10[9] = 1.f;
+            float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int m = tid; m < n; m += NT) {
+                const float w = lw[m];
+                const float d0 = smp[m * 7] - mean[0], d1 = smp[m * 7 + 1] - mean[1], d2 = smp[m * 7 + 2] - mean[2];
+                acc[0] = fmaf(w * d0, d0, acc[0]); acc[1] = fmaf(w * d0, d1, acc[1]); acc[2] = fmaf(w * d0, d2, acc[2]);
+                acc[3] = fmaf(w * d1, d1, acc[3]); acc[4] = fmaf(w * d1, d2, acc[4]); acc[5] = fmaf(w * d2, d2, acc[5]);
+            }
+            block_sum<6>(acc, sh.red);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) tc[r] = acc[r];
+        }
+        if (tid == 0) {
+            refit_finish6(mean, tc, lam10, p.acg_dispersion, sh.prop[i + 1]);
+        }
+        __syncthreads();
+    }
+    if (a.proposals && tid < I) {
+        float* o = a.proposals + ((size_t)obj * I + tid) * PROP_FLOATS;
+        const Proposal6& pr = sh.prop[tid];
+        o[0] = pr.mu[0]; o[1] = pr.mu[1]; o[2] = pr.mu[2];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) o[3 + r] = pr.lt[r];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) o[9 + r] = pr.lr[r];
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernels
+template <int DOF, bool DO_LM, bool DO_AMIS>
+__global__ void __launch_bounds__(NT, 4) solve_kernel(const KArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
+    float* dyn = reinterpret_cast<float*>(smem_raw);
+    const SmemPlan pl = plan_smem<DOF>(a.N, a.p.mc_samples, a.p.mc_iter, DO_AMIS);
+    float4* pts4 = reinterpret_cast<float4*>(dyn + pl.pts);
+
+    Loader ld(a, sh.bar, dyn + pl.stage);
+    ld.prologue();
+    for (int it = 0; it < ld.n_my; ++it) {
+        const int obj = (int)blockIdx.x + it * (int)gridDim.x;
+        ld.load_object(it, obj, pts4);
+        const Cam cam = load_cam(a, obj);
+        const float delta = __ldg(a.delta + obj);
+        if constexpr (DO_LM) {
+            lm_phase<DOF>(a, sh, pts4, cam, delta, obj, DO_AMIS || a.pose_cov != nullptr);
+        }
+        if constexpr (DO_AMIS && DOF == 6) {
+            if constexpr (!DO_LM) {
+                if (threadIdx.x < Dim<DOF>::POSE) sh.lm.pose[threadIdx.x] = __ldg(a.pose_opt_in + (size_t)obj * Dim<DOF>::POSE + threadIdx.x);
+                if (threadIdx.x < DOF * DOF) sh.cov[threadIdx.x] = __ldg(a.pose_cov_in + (size_t)obj * DOF * DOF + threadIdx.x);
+                __syncthreads();
+            }
+            amis_phase6(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.lw, cam, delta, obj,
+                        sh.lm.pose, sh.cov);
+        }
+    }
+}
+
+// cost of S poses per object: poses (S, B, D) -> cost (S, B)
+template <int DOF>
+__global__ void __launch_bounds__(NT, 4) cost_kernel(const KArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
+    float* dyn = reinterpret_cast<float*>(smem_raw);
+    const SmemPlan pl = plan_smem<DOF>(a.N, 0, 0, false);
+    float4* pts4 = reinterpret_cast<float4*>(dyn + pl.pts);
+    constexpr int PD = Dim<DOF>::POSE;
+    Loader ld(a, sh.bar, dyn + pl.stage);
+    ld.prologue();
+    for (int it = 0; it < ld.n_my; ++it) {
+        const int obj = (int)blockIdx.x + it * (int)gridDim.x;
+        ld.load_object(it, obj, pts4);
+        const Cam cam = load_cam(a, obj);
+        const float delta = __ldg(a.delta + obj);
+        for (int s = threadIdx.x; s < a.S_eval; s += NT) {
+            float pose[PD];
+#pragma unroll
+            for (int k = 0; k < PD; ++k) pose[k] = __ldg(a.poses + ((size_t)s * a.B + obj) * PD + k);
+            a.cost_out[(size_t)s * a.B + obj] = pose_cost<DOF>(pts4, a.N, pose, cam, delta);
+        }
+        __syncthreads();        // pts4 is overwritten by the next object
+    }
+}
+
+// residual / Jacobian / cost written out per point (API parity with evaluate_pnp's out_* tensors)
+template <int DOF>
+__global__ void __launch_bounds__(NT) evaluate_full_kernel(const KArgs a, float* residual, float* jac, float* cost,
+                                                         int clip, float huber_eps) {
+    __shared__ float red[NW];
+    const int obj = blockIdx.x;
+    constexpr int PD = Dim<DOF>::POSE;
+    const Cam cam = load_cam(a, obj);
+    const float delta = __ldg(a.delta + obj);
+    float pose[PD], R[9];
+#pragma unroll
+    for (int k = 0; k < PD; ++k) pose[k] = __ldg(a.poses + (size_t)obj * PD + k);
+    pose_to_rot<DOF>(pose, R);
+    float csum = 0.f;
+    for (int n = threadIdx.x; n < a.N; n += NT) {
+        const size_t g = (size_t)obj * a.N + n;
+        float r[2], j[2 * DOF];
+        csum += point_residual_jac<DOF>(R, pose, cam, delta, huber_eps, clip != 0,
+                                        a.x3d[g * 3], a.x3d[g * 3 + 1], a.x3d[g * 3 + 2],
+                                        a.x2d[g * 2], a.x2d[g * 2 + 1], a.w2d[g * 2], a.w2d[g * 2 + 1], r, j);
+        if (residual) { residual[g * 2] = r[0]; residual[g * 2 + 1] = r[1]; }
+        if (jac) {
+#pragma unroll
+            for (int k = 0; k < 2 * DOF; ++k) jac[g * 2 * DOF + k] = j[k];
+        }
+    }
+    if (cost) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = csum;
+        __syncthreads();
+        if (threadIdx.x == 0) cost[obj] = (red[0] + red[1]) + (red[2] + red[3]);
+    }
+}
+
+// AdaptiveHuberPnPCost.set_param: delta = mean(w2d) * sqrt(var_x + var_y) * relative_delta
+__global__ void __launch_bounds__(NT) adaptive_delta_kernel(const float* x2d, const float* w2d, float rel,
+                                                          float* delta, int N) {
+    __shared__ float red[NW * 32];
+    const int obj = blockIdx.x;
+    const float2* x = reinterpret_cast<const float2*>(x2d) + (size_t)obj * N;
+    const float2* w = reinterpret_cast<const float2*>(w2d) + (size_t)obj * N;
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int n = threadIdx.x; n < N; n += NT) {
+        const float2 a = x[n], b = w[n];
+        s[0] += a.x; s[1] += a.y; s[2] += b.x + b.y;
+    }
+    block_sum<3>(s, red);
+    const float mx = s[0] / N, my = s[1] / N, mw = s[2] / (2.f * N);
+    float v[2] = {0.f, 0.f};
+    for (int n = threadIdx.x; n < N; n += NT) {
+        const float2 a = x[n];
+        v[0] = fmaf(a.x - mx, a.x - mx, v[0]); v[1] = fmaf(a.y - my, a.y - my, v[1]);
+    }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0) delta[obj] = mw * sqrtf((v[0] + v[1]) / (float)(N - 1)) * rel;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return EPNP_ERR_CUDA; }
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_common(const KArgs& a) {
+    if (!a.x3d || !a.x2d || !a.w2d || !a.cam || !a.delta) return EPNP_ERR_BAD_ARG;
+    if ((a.lb == nullptr) != (a.ub == nullptr)) return EPNP_ERR_BAD_ARG;
+    if (a.B < 0 || a.N <= 0) return EPNP_ERR_BAD_ARG;
+    if (a.p.dof != 4 && a.p.dof != 6) return EPNP_ERR_BAD_ARG;
+    return EPNP_OK;
+}
+
+template <class Kern>
+int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream) {
+    if (a.B == 0) return EPNP_OK;
+    if ((size_t)smem_bytes > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
+    a.use_tma = (a.N % 4 == 0) && aligned16(a.x3d) && aligned16(a.x2d) && aligned16(a.w2d);
+    int dev = 0, sms = 0, occ = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem_bytes);
+    if (e != cudaSuccess) return cuda_fail(e);
+    if (occ < 1) return EPNP_ERR_TOO_MANY_POINTS;
+    // persistent grid, balanced: every CTA gets the same number of objects (+-1)
+    const int slots = sms * occ;
+    const int rounds = (a.B + slots - 1) / slots;
+    const int grid = (a.B + rounds - 1) / rounds;
+    kern<<<grid, NT, smem_bytes, stream>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    return EPNP_OK;
+}
+
+int check_amis_params(const Params& p) {
+    if (p.mc_iter <= 0 || p.mc_iter > MAX_ITER || p.mc_samples <= 0 || p.mc_samples % p.mc_iter != 0) return EPNP_ERR_BAD_ARG;
+    if (p.dof != 6) return EPNP_ERR_UNSUPPORTED;
+    if (p.acg_mle_iter < 0) return EPNP_ERR_BAD_ARG;
+    return EPNP_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int epnp_abi_version(void) { return EPNP_ABI_VERSION; }
+
+int epnp_last_cuda_error(void) { return g_last_cuda_error; }
+
+const char* epnp_error_string(int code) {
+    switch (code) {
+        case EPNP_OK: return "ok";
+        case EPNP_ERR_BAD_ARG: return "bad argument";
+        case EPNP_ERR_TOO_MANY_POINTS: return "correspondence set (and sample buffers) exceed 227 KB of shared memory";
+        case EPNP_ERR_UNSUPPORTED: return "combination not supported by this build";
+        case EPNP_ERR_CUDA: return "CUDA runtime error (see epnp_last_cuda_error)";
+        case EPNP_ERR_NO_DEVICE: return "no CUDA device";
+        default: return "unknown error";
+    }
+}
+
+void epnp_default_params(EpnpParams* p, int dof) {
+    p->dof = dof; p->lm_iter = 10; p->fast_mode = 0; p->z_min = 0.1f;
+    p->min_lm_diagonal = 1e-6f; p->max_lm_diagonal = 1e32f; p->min_relative_decrease = 1e-3f;
+    p->initial_radius = 30.0f; p->max_radius = 1e16f; p->eps = 1e-5f; p->huber_eps = 1e-10f;
+    p->mc_samples = 512; p->mc_iter = 4; p->amis_eps = 1e-5f; p->acg_mle_iter = 3; p->acg_dispersion = 1e-3f;
+}
+
+int epnp_max_points(int dof, int mc_samples, int mc_iter) {
+    const bool amis = mc_samples > 0;
+    int lo = 0, hi = 1 << 16;
+    while (lo + 4 <= hi) {                   // largest multiple of 4 that fits
+        const int mid = ((lo + hi) / 2) / 4 * 4;
+        if (mid == lo) break;
+        const int bytes = (dof == 6) ? plan_smem<6>(mid, mc_samples, mc_iter, amis).total_bytes
+                                     : plan_smem<4>(mid, mc_samples, mc_iter, amis).total_bytes;
+        if ((size_t)bytes <= SMEM_LIMIT) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+int epnp_adaptive_delta_f32(const float* x2d, const float* w2d, float relative_delta, float* delta, int B, int N,
+                            void* stream) {
+    if (!x2d || !w2d || !delta || B < 0 || N <= 0) return EPNP_ERR_BAD_ARG;
+    if (B == 0) return EPNP_OK;
+    adaptive_delta_kernel<<<B, NT, 0, (cudaStream_t)stream>>>(x2d, w2d, relative_delta, delta, N);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
+}
+
+int epnp_evaluate_cost_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                           const float* lb, const float* ub, const float* delta, const float* poses, float* cost,
+                           int S, int B, int N, int dof, float z_min, void* stream) {
+    KArgs a{};
+    a.x3d = x3d; a.x2d = x2d; a.w2d = w2d; a.cam = cam_mats; a.lb = lb; a.ub = ub; a.delta = delta;
+    a.poses = poses; a.cost_out = cost; a.S_eval = S; a.B = B; a.N = N;
+    epnp_default_params(&a.p, dof);
+    a.p.z_min = z_min;
+    int rc = check_common(a);
+    if (rc != EPNP_OK) return rc;
+    if (!poses || !cost || S < 0) return EPNP_ERR_BAD_ARG;
+    if (S == 0) return EPNP_OK;
+    if (dof == 6) return launch_persistent(cost_kernel<6>, a, plan_smem<6>(N, 0, 0, false).total_bytes, (cudaStream_t)stream);
+    return launch_persistent(cost_kernel<4>, a, plan_smem<4>(N, 0, 0, false).total_bytes, (cudaStream_t)stream);
+}
+
+int epnp_evaluate_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                      const float* lb, const float* ub, const float* delta, const float* pose,
+                      float* residual, float* jac, float* cost, int clip_jac,
+                      int B, int N, int dof, float z_min, float huber_eps, void* stream) {
+    KArgs a{};
+    a.x3d = x3d; a.x2d = x2d; a.w2d = w2d; a.cam = cam_mats; a.lb = lb; a.ub = ub; a.delta = delta;
+    a.poses = pose; a.B = B; a.N = N;
+    epnp_default_params(&a.p, dof);
+    a.p.z_min = z_min;
+    int rc = check_common(a);
+    if (rc != EPNP_OK) return rc;
+    if (!pose) return EPNP_ERR_BAD_ARG;
+    if (B == 0) return EPNP_OK;
+    if (dof == 6) evaluate_full_kernel<6><<<B, NT, 0, (cudaStream_t)stream>>>(a, residual, jac, cost, clip_jac, huber_eps);
+    else evaluate_full_kernel<4><<<B, NT, 0, (cudaStream_t)stream>>>(a, residual, jac, cost, clip_jac, huber_eps);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
+}
+
+int epnp_lm_solve_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                      const float* lb, const float* ub, const float* delta, const float* pose_init,
+                      float* pose_opt, float* pose_cov, float* cost, float* pose_opt_plus, float* cost_init,
+                      int B, int N, const EpnpParams* p, void* stream) {
+    if (!p) return EPNP_ERR_BAD_ARG;
+    KArgs a{};
+    a.x3d = x3d; a.x2d = x2d; a.w2d = w2d; a.cam = cam_mats; a.lb = lb; a.ub = ub; a.delta = delta;
+    a.pose_init = pose_init; a.pose_opt = pose_opt; a.pose_cov = pose_cov; a.cost = cost;
+    a.pose_plus = pose_opt_plus; a.cost_init = cost_init; a.B = B; a.N = N; a.p = *p;
+    int rc = check_common(a);
+    if (rc != EPNP_OK) return rc;
+    if (!pose_init || !pose_opt || p->lm_iter < 0) return EPNP_ERR_BAD_ARG;
+    if (p->dof == 6) return launch_persistent(solve_kernel<6, true, false>, a, plan_smem<6>(N, 0, 0, false).total_bytes, (cudaStream_t)stream);
+    return launch_persistent(solve_kernel<4, true, false>, a, plan_smem<4>(N, 0, 0, false).total_bytes, (cudaStream_t)stream);
+}
+
+int epnp_amis_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                  const float* lb, const float* ub, const float* delta, const float* pose_opt, const float* pose_cov,
+                  const float* noise_normal, const float* noise_chi2, const float* noise_rot,
+                  uint64_t seed, uint32_t obj_offset, float* pose_samples, float* logw, float* proposals,
+                  int B, int N, const EpnpParams* p, void* stream) {
+    if (!p) return EPNP_ERR_BAD_ARG;
+    KArgs a{};
+    a.x3d = x3d; a.x2d = x2d; a.w2d = w2d; a.cam = cam_mats; a.lb = lb; a.ub = ub; a.delta = delta;
+    a.pose_opt_in = pose_opt; a.pose_cov_in = pose_cov;
+    a.noise_n3 = noise_normal; a.noise_chi2 = noise_chi2; a.noise_rot = noise_rot;
+    a.seed = seed; a.obj_offset = obj_offset;
+    a.pose_samples = pose_samples; a.logw = logw; a.proposals = proposals; a.B = B; a.N = N; a.p = *p;
+    int rc = check_common(a);
+    if (rc != EPNP_OK) return rc;
+    rc = check_amis_params(*p);
+    if (rc != EPNP_OK) return rc;
+    if (!pose_opt || !pose_cov || !pose_samples || !logw) return EPNP_ERR_BAD_ARG;
+    const bool any = noise_normal || noise_chi2 || noise_rot, all = noise_normal && noise_chi2 && noise_rot;
+    if (any && !all) return EPNP_ERR_BAD_ARG;
+    return launch_persistent(solve_kernel<6, false, true>, a, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes,
+                             (cudaStream_t)stream);
+}
+
+int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                           const float* lb, const float* ub, const float* delta, const float* pose_init,
+                           const float* noise_normal, const float* noise_chi2, const float* noise_rot,
+                           uint64_t seed, uint32_t obj_offset,
+                           float* pose_opt, float* pose_cov, float* cost, float* pose_opt_plus, float* cost_init,
+                           float* pose_samples, float* logw, float* proposals,
+                           int B, int N, const EpnpParams* p, void* stream) {
+    if (!p) return EPNP_ERR_BAD_ARG;
+    KArgs a{};
+    a.x3d = x3d; a.x2d = x2d; a.w2d = w2d; a.cam = cam_mats; a.lb = lb; a.ub = ub; a.delta = delta;
+    a.pose_init = pose_init;
+    a.noise_n3 = noise_normal; a.noise_chi2 = noise_chi2; a.noise_rot = noise_rot;
+    a.seed = seed; a.obj_offset = obj_offset;
+    a.pose_opt = pose_opt; a.pose_cov = pose_cov; a.cost = cost; a.pose_plus = pose_opt_plus; a.cost_init = cost_init;
+    a.pose_samples = pose_samples; a.logw = logw; a.proposals = proposals; a.B = B; a.N = N; a.p = *p;
+    int rc = check_common(a);
+    if (rc != EPNP_OK) return rc;
+    rc = check_amis_params(*p);
+    if (rc != EPNP_OK) return rc;
+    if (!pose_init || !pose_opt || !pose_samples || !logw || p->lm_iter < 0) return EPNP_ERR_BAD_ARG;
+    const bool any = noise_normal || noise_chi2 || noise_rot, all = noise_normal && noise_chi2 && noise_rot;
+    if (any && !all) return EPNP_ERR_BAD_ARG;
+    return launch_persistent(solve_kernel<6, true, true>, a, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes,
+                             (cudaStream_t)stream);
+}
+
+// ---- host-buffer entry point: chunked H2D -> fused kernel -> D2H on two internal streams
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct WsLayout {
+    size_t x3d, x2d, w2d, cam, lb, ub, delta, pose_init, pose_opt, pose_cov, cost, samples, logw, total;
+};
+
+static WsLayout ws_layout(int B, int N, const EpnpParams* p) {
+    const size_t D = (p->dof == 6) ? 7 : 4, dof = p->dof, M = p->mc_samples;
+    WsLayout w; size_t o = 0;
+    w.x3d = o; o += align256((size_t)B * N * 3 * 4);
+    w.x2d = o; o += align256((size_t)B * N * 2 * 4);
+    w.w2d = o; o += align256((size_t)B * N * 2 * 4);
+    w.cam = o; o += align256((size_t)B * 9 * 4);
+    w.lb = o; o += align256((size_t)B * 2 * 4);
+    w.ub = o; o += align256((size_t)B * 2 * 4);
+    w.delta = o; o += align256((size_t)B * 4);
+    w.pose_init = o; o += align256((size_t)B * D * 4);
+    w.pose_opt = o; o += align256((size_t)B * D * 4);
+    w.pose_cov = o; o += align256((size_t)B * dof * dof * 4);
+    w.cost = o; o += align256((size_t)B * 4);
+    w.samples = o; o += align256((size_t)B * M * D * 4);
+    w.logw = o; o += align256((size_t)B * M * 4);
+    w.total = o;
+    return w;
+}
+
+size_t epnp_fused_workspace_bytes(int B, int N, const EpnpParams* p) {
+    if (!p || B < 0 || N <= 0) return 0;
+    return ws_layout(B, N, p).total;
+}
+
+int epnp_lm_amis_fused_host_f32(const float* x3d_host, const float* x2d_host, const float* w2d_host,
+                                const float* cam_mats_host, const float* lb_host, const float* ub_host,
+                                const float* delta_host, const float* pose_init_host,
+                                uint64_t seed, uint32_t obj_offset,
+                                float* pose_opt_host, float* pose_cov_host, float* cost_host,
+                                float* pose_samples_host, float* logw_host,
+                                void* workspace, size_t workspace_bytes, int n_chunks,
+                                int B, int N, const EpnpParams* p, void* stream_) {
+    if (!p || !workspace || !x3d_host || !x2d_host || !w2d_host || !cam_mats_host || !delta_host || !pose_init_host ||
+        !pose_opt_host || !logw_host)
+        return EPNP_ERR_BAD_ARG;
+    if ((lb_host == nullptr) != (ub_host == nullptr)) return EPNP_ERR_BAD_ARG;
+    if (B < 0 || N <= 0) return EPNP_ERR_BAD_ARG;
+    if (B == 0) return EPNP_OK;
+    const WsLayout w = ws_layout(B, N, p);
+    if (workspace_bytes < w.total) return EPNP_ERR_BAD_ARG;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > B) n_chunks = B;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    char* ws = (char*)workspace;
+    const size_t D = (p->dof == 6) ? 7 : 4, dof = p->dof, M = p->mc_samples;
+    // Two helper streams forked from / joined to `stream` with events: chunk c runs on helper c&1, so the
+    // H2D of chunk c+1 overlaps the kernel of chunk c and the D2H of chunk c-1.
+    cudaStream_t hs[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    int rc = EPNP_OK;
+#define EPNP_TRY(x) do { e = (x); if (e != cudaSuccess) { rc = cuda_fail(e); goto done; } } while (0)
+    EPNP_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    EPNP_TRY(cudaEventRecord(fork, stream));
+    for (int i = 0; i < 2; ++i) {
+        EPNP_TRY(cudaStreamCreateWithFlags(&hs[i], cudaStreamNonBlocking));
+        EPNP_TRY(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+        EPNP_TRY(cudaStreamWaitEvent(hs[i], fork, 0));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b0 = (int)((long long)B * c / n_chunks), b1 = (int)((long long)B * (c + 1) / n_chunks);
+        const int nb = b1 - b0;
+        if (nb <= 0) continue;
+        cudaStream_t s = hs[c & 1];
+#define H2D(field, host, per) EPNP_TRY(cudaMemcpyAsync(ws + w.field + (size_t)b0 * (per) * 4, (host) + (size_t)b0 * (per), (size_t)nb * (per) * 4, cudaMemcpyHostToDevice, s))
+#define D2H(field, host, per) EPNP_TRY(cudaMemcpyAsync((host) + (size_t)b0 * (per), ws + w.field + (size_t)b0 * (per) * 4, (size_t)nb * (per) * 4, cudaMemcpyDeviceToHost, s))
+        H2D(x3d, x3d_host, (size_t)N * 3); H2D(x2d, x2d_host, (size_t)N * 2); H2D(w2d, w2d_host, (size_t)N * 2);
+        H2D(cam, cam_mats_host, 9); H2D(delta, delta_host, 1); H2D(pose_init, pose_init_host, D);
+        if (lb_host) { H2D(lb, lb_host, 2); H2D(ub, ub_host, 2); }
+        rc = epnp_lm_amis_fused_f32(
+            (float*)(ws + w.x3d) + (size_t)b0 * N * 3, (float*)(ws + w.x2d) + (size_t)b0 * N * 2,
+            (float*)(ws + w.w2d) + (size_t)b0 * N * 2, (float*)(ws + w.cam) + (size_t)b0 * 9,
+            lb_host ? (float*)(ws + w.lb) + (size_t)b0 * 2 : nullptr, lb_host ? (float*)(ws + w.ub) + (size_t)b0 * 2 : nullptr,
+            (float*)(ws + w.delta) + b0, (float*)(ws + w.pose_init) + (size_t)b0 * D,
+            nullptr, nullptr, nullptr, seed, obj_offset + (uint32_t)b0,
+            (float*)(ws + w.pose_opt) + (size_t)b0 * D, (float*)(ws + w.pose_cov) + (size_t)b0 * dof * dof,
+            (float*)(ws + w.cost) + b0, nullptr, nullptr,
+            (float*)(ws + w.samples) + (size_t)b0 * M * D, (float*)(ws + w.logw) + (size_t)b0 * M, nullptr,
+            nb, N, p, s);
+        if (rc != EPNP_OK) goto done;
+        D2H(pose_opt, pose_opt_host, D); D2H(logw, logw_host, M);
+        if (pose_cov_host) D2H(pose_cov, pose_cov_host, dof * dof);
+        if (cost_host) D2H(cost, cost_host, 1);
+        if (pose_samples_host) D2H(samples, pose_samples_host, M * D);
+#undef H2D
+#undef D2H
+    }
+    for (int i = 0; i < 2; ++i) {
+        EPNP_TRY(cudaEventRecord(join[i], hs[i]));
+        EPNP_TRY(cudaStreamWaitEvent(stream, join[i], 0));
+    }
+done:
+#undef EPNP_TRY
+    // helper streams/events are released once their work is done (cudaStreamDestroy defers)
+    for (int i = 0; i < 2; ++i) {
+        if (hs[i]) cudaStreamDestroy(hs[i]);
+        if (join[i]) cudaEventDestroy(join[i]);
+    }
+    if (fork) cudaEventDestroy(fork);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,634 @@
+// pnp_math.cuh -- scalar building blocks of the EPro-PnP hot path, shared by the sm_100a kernels
+// (pnp_kernels.cu) and by a host-side build of the same functions that the CPU tests drive
+// (tests/host_emul.cpp) so formulas can be checked against the golden vectors without a GPU.
+//
+// Everything is fp32 and allocation-free; matrices are tiny fixed-size arrays with static indexing
+// so they live in registers.  Reference behaviour (file:line under /root/reference/epropnp/) is
+// cited per function; the code itself is written from the math, not translated.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "epropnp_b200.h"
+
+#if defined(__CUDACC__)
+#define PNP_HD __host__ __device__ __forceinline__
+// once-per-object fp64 routines: kept out of line so they do not inflate the register allocation of
+// the per-point loops they are called next to
+#define PNP_HD_COLD __host__ __device__ __noinline__
+#else
+#define PNP_HD inline
+#define PNP_HD_COLD inline
+#endif
+
+namespace pnp {
+
+// ------------------------------------------------------------------------------------------------
+// Solver hyper-parameters: the C ABI's POD (include/epropnp_b200.h), passed by value to the kernels.
+using Params = ::EpnpParams;
+
+struct Cam {
+    float k[9];                 // row-major 3x3
+    float lbx, lby, ubx, uby;
+    float z_min;
+    int   bounded;
+};
+
+template <int DOF> struct Dim {
+    static constexpr int POSE = (DOF == 6) ? 7 : 4;
+    static constexpr int NA = DOF * (DOF + 1) / 2;     // packed upper triangle of J^T J
+    static constexpr int NV = NA + DOF + 1;            // + J^T r + cost
+};
+
+// packed upper-triangular index, row-major: (i, j>=i)
+PNP_HD constexpr int tri(int i, int j, int n) { return i * n - i * (i - 1) / 2 + (j - i); }
+
+// ------------------------------------------------------------------------------------------------
+// rotations  (common.py:22-64)
+PNP_HD void quat_to_rot(const float* q, float* R) {
+    const float w = q[0], x = q[1], y = q[2], z = q[3];
+    const float ww = w * w, xx = x * x, yy = y * y, zz = z * z;
+    R[0] = ww + xx - yy - zz; R[1] = 2.f * (x * y - w * z); R[2] = 2.f * (x * z + w * y);
+    R[3] = 2.f * (x * y + w * z); R[4] = ww - xx + yy - zz; R[5] = 2.f * (y * z - w * x);
+    R[6] = 2.f * (x * z - w * y); R[7] = 2.f * (y * z + w * x); R[8] = ww - xx - yy + zz;
+}
+
+PNP_HD void yaw_to_rot(float yaw, float* R) {
+    float s, c;
+#if defined(__CUDA_ARCH__)
+    sincosf(yaw, &s, &c);
+#else
+    s = sinf(yaw); c = cosf(yaw);
+#endif
+    R[0] = c;  R[1] = 0.f; R[2] = s;
+    R[3] = 0.f; R[4] = 1.f; R[5] = 0.f;
+    R[6] = -s; R[7] = 0.f; R[8] = c;
+}
+
+template <int DOF> PNP_HD void pose_to_rot(const float* pose, float* R) {
+    if (DOF == 6) quat_to_rot(pose + 3, R); else yaw_to_rot(pose[3], R);
+}
+
+// P = K [R | t] as 3 rows of 4  (the pre-multiplied form of camera.py:21-30 `project_b`)
+PNP_HD void make_proj(const float* K, const float* R, const float* t, float* P) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            P[r * 4 + c] = K[r * 3 + 0] * R[0 + c] + K[r * 3 + 1] * R[3 + c] + K[r * 3 + 2] * R[6 + c];
+        P[r * 4 + 3] = K[r * 3 + 0] * t[0] + K[r * 3 + 1] * t[1] + K[r * 3 + 2] * t[2];
+    }
+}
+
+// pose (+) step  (levenberg_marquardt.py:255-265, camera.py:145-165): translation adds; the
+// rotation increment d lives in the tangent space, q <- normalize(q + T(q) d).
+template <int DOF> PNP_HD void pose_add(const float* pose, const float* step, float* out) {
+    out[0] = pose[0] + step[0]; out[1] = pose[1] + step[1]; out[2] = pose[2] + step[2];
+    if (DOF == 4) { out[3] = pose[3] + step[3]; return; }
+    const float w = pose[3], x = pose[4], y = pose[5], z = pose[6];
+    const float a = step[3], b = step[4], c = step[5];
+    float qw = w + (x * a + y * b + z * c);
+    float qx = x + (-w * a - z * b + y * c);
+    float qy = y + (z * a - w * b - x * c);
+    float qz = z + (-y * a + x * b - w * c);
+    float n = sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
+    n = fmaxf(n, 1e-12f);
+    out[3] = qw / n; out[4] = qx / n; out[5] = qy / n; out[6] = qz / n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cost of one correspondence under a pre-multiplied projection (AMIS inner loop; cost-only
+// evaluate_pnp).  camera.py:21-30 + :81-93 clamp, cost_fun.py:8-12,52-59.
+// `rcp`: 1/x functor so the device build can use the approximate MUFU reciprocal.
+struct ExactRcp { PNP_HD float operator()(float x) const { return 1.0f / x; } };
+struct ExactSqrt { PNP_HD float operator()(float x) const { return sqrtf(x); } };
+
+template <bool BOUNDED, class Rcp, class Sqrt>
+PNP_HD float point_cost(const float* P, const Cam& c, float delta, float half_d2,
+                        float X, float Y, float Z, float u, float v, float wu, float wv,
+                        Rcp rcp, Sqrt sq) {
+    float xh = fmaf(P[0], X, fmaf(P[1], Y, fmaf(P[2], Z, P[3])));
+    float yh = fmaf(P[4], X, fmaf(P[5], Y, fmaf(P[6], Z, P[7])));
+    float zh = fmaf(P[8], X, fmaf(P[9], Y, fmaf(P[10], Z, P[11])));
+    float iz = rcp(fmaxf(zh, c.z_min));
+    float px = xh * iz, py = yh * iz;
+    if (BOUNDED) {
+        px = fminf(fmaxf(px, c.lbx), c.ubx);
+        py = fminf(fmaxf(py, c.lby), c.uby);
+    }
+    float rx = (px - u) * wu, ry = (py - v) * wv;
+    float s2 = fmaf(rx, rx, ry * ry);
+    float s = sq(s2);
+    return (s <= delta) ? 0.5f * s2 : fmaf(delta, s, -half_d2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One correspondence's contribution to the Gauss-Newton normal equations:
+//   acc[0..NA)       upper triangle of J~^T J~
+//   acc[NA..NA+DOF)  J~^T r~
+//   acc[NA+DOF]      sum of Huber costs
+// camera.py:10-18 (project_a), :81-105 (clamp + clip mask), :111-143 (2xDOF Jacobian);
+// cost_fun.py:52-84 (weighted residual, Huber, robust rescale of residual and Jacobian).
+template <int DOF, bool CLIP>
+PNP_HD void point_normal_eq(const float* R, const float* t, const Cam& c, float delta, float huber_eps,
+                            float X, float Y, float Z, float u, float v, float wu, float wv,
+                            float* acc) {
+    constexpr int NA = Dim<DOF>::NA;
+    const float xr = fmaf(R[0], X, fmaf(R[1], Y, R[2] * Z));
+    const float yr = fmaf(R[3], X, fmaf(R[4], Y, R[5] * Z));
+    const float zr = fmaf(R[6], X, fmaf(R[7], Y, R[8] * Z));
+    const float xc = xr + t[0], yc = yr + t[1], zc = zr + t[2];
+    const float* K = c.k;
+    const float xh = fmaf(K[0], xc, fmaf(K[1], yc, K[2] * zc));
+    const float yh = fmaf(K[3], xc, fmaf(K[4], yc, K[5] * zc));
+    const float zh = fmaf(K[6], xc, fmaf(K[7], yc, K[8] * zc));
+    const float z = fmaxf(zh, c.z_min);
+    const float iz = 1.0f / z;
+    float px = xh * iz, py = yh * iz;
+    if (c.bounded) {
+        px = fminf(fmaxf(px, c.lbx), c.ubx);
+        py = fminf(fmaxf(py, c.lby), c.uby);
+    }
+    float rx = (px - u) * wu, ry = (py - v) * wv;
+    const float s2 = fmaf(rx, rx, ry * ry);
+    const float s = sqrtf(s2);
+    acc[NA + DOF] += (s <= delta) ? 0.5f * s2 : fmaf(delta, s, -0.5f * delta * delta);
+    const float sc = sqrtf(fminf(delta / fmaxf(s, huber_eps), 1.0f));      // sqrt(rho')
+    rx *= sc; ry *= sc;
+
+    float jx[DOF], jy[DOF];
+    jx[0] = K[0] * iz; jx[1] = K[1] * iz; jx[2] = (K[2] - px) * iz;
+    jy[0] = K[3] * iz; jy[1] = K[4] * iz; jy[2] = (K[5] - py) * iz;
+    if (DOF == 6) {
+        const float ax = 2.f * xr, ay = 2.f * yr, az = 2.f * zr;          // J3 * skew(2 x_rot)
+        jx[3] = jx[1] * az - jx[2] * ay; jx[4] = jx[2] * ax - jx[0] * az; jx[5] = jx[0] * ay - jx[1] * ax;
+        jy[3] = jy[1] * az - jy[2] * ay; jy[4] = jy[2] * ax - jy[0] * az; jy[5] = jy[0] * ay - jy[1] * ax;
+    } else {
+        jx[3] = jx[0] * zr - jx[2] * xr;                                   // d/d yaw
+        jy[3] = jy[0] * zr - jy[2] * xr;
+    }
+    float sx = wu * sc, sy = wv * sc;
+    if (CLIP) {           // rows whose projection sits on a clamp carry no gradient
+        const bool cz = (z == c.z_min);
+        const bool cx = cz || (c.bounded && (px == c.lbx || px == c.ubx));
+        const bool cy = cz || (c.bounded && (py == c.lby || py == c.uby));
+        sx = cx ? 0.f : sx;
+        sy = cy ? 0.f : sy;
+    }
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) { jx[i] *= sx; jy[i] *= sy; }
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) {
+#pragma unroll
+        for (int j = i; j < DOF; ++j) { acc[idx] = fmaf(jx[i], jx[j], fmaf(jy[i], jy[j], acc[idx])); ++idx; }
+    }
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) acc[NA + i] = fmaf(jx[i], rx, fmaf(jy[i], ry, acc[NA + i]));
+}
+
+// The same per-point quantities written out instead of reduced (evaluate_pnp with out_residual /
+// out_jacobian, common.py:67-100): res[2], jac[2*DOF] (row x then row y), returns the Huber cost.
+template <int DOF>
+PNP_HD float point_residual_jac(const float* R, const float* t, const Cam& c, float delta, float huber_eps,
+                                bool clip, float X, float Y, float Z, float u, float v, float wu, float wv,
+                                float* res, float* jac) {
+    const float xr = fmaf(R[0], X, fmaf(R[1], Y, R[2] * Z));
+    const float yr = fmaf(R[3], X, fmaf(R[4], Y, R[5] * Z));
+    const float zr = fmaf(R[6], X, fmaf(R[7], Y, R[8] * Z));
+    const float xc = xr + t[0], yc = yr + t[1], zc = zr + t[2];
+    const float* K = c.k;
+    const float xh = fmaf(K[0], xc, fmaf(K[1], yc, K[2] * zc));
+    const float yh = fmaf(K[3], xc, fmaf(K[4], yc, K[5] * zc));
+    const float zh = fmaf(K[6], xc, fmaf(K[7], yc, K[8] * zc));
+    const float z = fmaxf(zh, c.z_min);
+    const float iz = 1.0f / z;
+    float px = xh * iz, py = yh * iz;
+    if (c.bounded) {
+        px = fminf(fmaxf(px, c.lbx), c.ubx);
+        py = fminf(fmaxf(py, c.lby), c.uby);
+    }
+    float rx = (px - u) * wu, ry = (py - v) * wv;
+    const float s2 = fmaf(rx, rx, ry * ry);
+    const float s = sqrtf(s2);
+    const float cost = (s <= delta) ? 0.5f * s2 : fmaf(delta, s, -0.5f * delta * delta);
+    const float sc = sqrtf(fminf(delta / fmaxf(s, huber_eps), 1.0f));
+    res[0] = rx * sc; res[1] = ry * sc;
+    float* jx = jac; float* jy = jac + DOF;
+    jx[0] = K[0] * iz; jx[1] = K[1] * iz; jx[2] = (K[2] - px) * iz;
+    jy[0] = K[3] * iz; jy[1] = K[4] * iz; jy[2] = (K[5] - py) * iz;
+    if (DOF == 6) {
+        const float ax = 2.f * xr, ay = 2.f * yr, az = 2.f * zr;
+        jx[3] = jx[1] * az - jx[2] * ay; jx[4] = jx[2] * ax - jx[0] * az; jx[5] = jx[0] * ay - jx[1] * ax;
+        jy[3] = jy[1] * az - jy[2] * ay; jy[4] = jy[2] * ax - jy[0] * az; jy[5] = jy[0] * ay - jy[1] * ax;
+    } else {
+        jx[3] = jx[0] * zr - jx[2] * xr;
+        jy[3] = jy[0] * zr - jy[2] * xr;
+    }
+    float sx = wu * sc, sy = wv * sc;
+    if (clip) {
+        const bool cz = (z == c.z_min);
+        if (cz || (c.bounded && (px == c.lbx || px == c.ubx))) sx = 0.f;
+        if (cz || (c.bounded && (py == c.lby || py == c.uby))) sy = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) { jx[i] *= sx; jy[i] *= sy; }
+    return cost;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small symmetric-positive-definite linear algebra, N <= 6, static indexing only, templated on the
+// working precision.  The per-point loops are fp32; these once-per-object factorizations run in fp64
+// (`Hi`): the matrices are ill-conditioned by construction (information ~1e5 next to an identity
+// block, epropnp.py:297-298) and fp64 here costs nothing measurable while it removes the largest
+// rounding term of the fp32 reference from our side of the parity budget.
+typedef double Hi;
+
+// a: packed upper triangle (row-major).  L: full n*n row-major lower factor.  Returns false when a
+// pivot is not positive (LAPACK potrf's failure test: pivot <= 0 or NaN).
+template <int N, class T> PNP_HD bool chol_packed(const T* a, T* L) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        T d = a[tri(j, j, N)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= L[j * N + k] * L[j * N + k];
+        ok = ok && (d > T(0));
+        const T ljj = sqrt(d);
+        L[j * N + j] = ljj;
+        const T inv = T(1) / ljj;
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            T v = a[tri(j, i, N)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v -= L[i * N + k] * L[j * N + k];
+            L[i * N + j] = v * inv;
+        }
+#pragma unroll
+        for (int i = 0; i < j; ++i) L[i * N + j] = T(0);
+    }
+    return ok;
+}
+
+// x = A^-1 b through the Cholesky factor (A SPD).  NaN when A is not PD.
+template <int N, class T> PNP_HD void chol_solve(const T* L, const T* b, T* x) {
+    T y[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        T v = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) v -= L[i * N + k] * y[k];
+        y[i] = v / L[i * N + i];
+    }
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+        T v = y[i];
+#pragma unroll
+        for (int k = i + 1; k < N; ++k) v -= L[k * N + i] * x[k];
+        x[i] = v / L[i * N + i];
+    }
+}
+
+// inverse of the lower factor (lower triangular, full storage)
+template <int N, class T> PNP_HD void tri_inverse(const T* L, T* Li) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (i < j) { Li[i * N + j] = T(0); continue; }
+            if (i == j) { Li[i * N + j] = T(1) / L[i * N + i]; continue; }
+            T v = T(0);
+#pragma unroll
+            for (int k = j; k < i; ++k) v -= L[i * N + k] * Li[k * N + j];
+            Li[i * N + j] = v / L[i * N + i];
+        }
+    }
+}
+
+// A^-1 (full, symmetric) = Li^T Li.  Replaces torch.inverse on the SPD matrices of the path.
+template <int N, class T> PNP_HD bool spd_inverse(const T* a_packed, T* inv_full) {
+    T L[N * N], Li[N * N];
+    const bool ok = chol_packed<N, T>(a_packed, L);
+    tri_inverse<N, T>(L, Li);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = i; j < N; ++j) {
+            T v = T(0);
+#pragma unroll
+            for (int k = j; k < N; ++k) v += Li[k * N + i] * Li[k * N + j];
+            inv_full[i * N + j] = v;
+            inv_full[j * N + i] = v;
+        }
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Levenberg-Marquardt state machine for ONE object (levenberg_marquardt.py:154-179, 192-241).
+// The Jacobian is never stored: "current" and "candidate" are the reduced normal equations.
+template <int DOF> struct LMState {
+    float pose[Dim<DOF>::POSE];
+    float pose_new[Dim<DOF>::POSE];
+    float a[Dim<DOF>::NA];      // J^T J at pose (upper triangle)
+    float g[DOF];               // J^T r at pose
+    float cost;
+    float radius, shrink;
+    float model_change;         // predicted decrease of the pending step
+};
+
+// Adopt a freshly reduced evaluation (acc layout of point_normal_eq) as the current linearisation.
+template <int DOF> PNP_HD void lm_adopt(LMState<DOF>& s, const float* acc) {
+    constexpr int NA = Dim<DOF>::NA;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) s.a[i] = acc[i];
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) s.g[i] = acc[NA + i];
+    s.cost = acc[NA + DOF];
+}
+
+// step = -(A + diag(add))^-1 g, in fp64; returns step in fp32 and the model cost change
+// -step^T (A step / 2 + g)   (levenberg_marquardt.py:205-216, 225)
+template <int DOF> PNP_HD_COLD float damped_step(const float* a, const float* g, const float* add, float* step) {
+    constexpr int NA = Dim<DOF>::NA;
+    Hi al[NA], gh[DOF], L[DOF * DOF], st[DOF];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) al[i] = (Hi)a[i];
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) { al[tri(i, i, DOF)] += (Hi)add[i]; gh[i] = (Hi)g[i]; }
+    chol_packed<DOF, Hi>(al, L);
+    chol_solve<DOF, Hi>(L, gh, st);
+    Hi m = 0;
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) {
+        Hi v = 0;
+#pragma unroll
+        for (int j = 0; j < DOF; ++j) v += (Hi)a[(i <= j) ? tri(i, j, DOF) : tri(j, i, DOF)] * (-st[j]);
+        m += (-st[i]) * (v * 0.5 + gh[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) step[i] = (float)(-st[i]);
+    return (float)(-m);
+}
+
+// Damped step from the current linearisation -> s.pose_new, s.model_change  (:205-225)
+template <int DOF> PNP_HD void lm_propose(LMState<DOF>& s, const Params& p) {
+    float add[DOF], step[DOF];
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) {
+        const float d = s.a[tri(i, i, DOF)];
+        add[i] = fminf(fmaxf(d, p.min_lm_diagonal), p.max_lm_diagonal) / s.radius + p.eps;
+    }
+    s.model_change = damped_step<DOF>(s.a, s.g, add, step);
+    pose_add<DOF>(s.pose, step, s.pose_new);
+}
+
+// Accept / reject the pending step given the candidate evaluation `acc`  (:227-240)
+template <int DOF> PNP_HD bool lm_update(LMState<DOF>& s, const float* acc, const Params& p) {
+    constexpr int NA = Dim<DOF>::NA;
+    const float cost_new = acc[NA + DOF];
+    const float rho = (s.cost - cost_new) / s.model_change;
+    const bool ok = (rho >= p.min_relative_decrease) && (s.model_change > 0.0f);
+    if (ok) {
+#pragma unroll
+        for (int i = 0; i < Dim<DOF>::POSE; ++i) s.pose[i] = s.pose_new[i];
+        const float q = 2.0f * rho - 1.0f;
+        s.radius = s.radius / fmaxf(1.0f - q * q * q, 1.0f / 3.0f);
+    }
+    s.radius = fmaxf(fminf(s.radius, p.max_radius), p.eps);
+    if (ok) {
+        s.shrink = 2.0f;
+        lm_adopt<DOF>(s, acc);
+    } else {
+        s.radius = s.radius / s.shrink;
+        s.shrink *= 2.0f;
+    }
+    return ok;
+}
+
+// Gauss-Newton step (fast mode :136-152 and gn_step :243-253): pose_out = pose (+) -(A+eps I)^-1 g
+template <int DOF> PNP_HD void gn_advance(const float* pose, const float* acc, float eps, float* pose_out) {
+    float add[DOF], step[DOF];
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) add[i] = eps;
+    damped_step<DOF>(acc, acc + Dim<DOF>::NA, add, step);
+    pose_add<DOF>(pose, step, pose_out);
+}
+
+// pose covariance = (J^T J + eps I)^-1  (:170-179)
+template <int DOF> PNP_HD_COLD void pose_covariance(const float* a_packed, float eps, float* cov_full) {
+    constexpr int NA = Dim<DOF>::NA;
+    Hi al[NA], inv[DOF * DOF];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) al[i] = (Hi)a_packed[i];
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) al[tri(i, i, DOF)] += (Hi)eps;
+    spd_inverse<DOF, Hi>(al, inv);
+#pragma unroll
+    for (int i = 0; i < DOF * DOF; ++i) cov_full[i] = (float)inv[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// AMIS proposal for 6DoF: translation ~ multivariate t (df=3), rotation ~ angular central Gaussian.
+// Stored with everything log_prob needs pre-computed.
+struct Proposal6 {
+    float mu[3];
+    float lt[6];     // L_t lower: l00 l10 l11 l20 l21 l22
+    float lr[10];    // L_r lower: l00 l10 l11 l20 l21 l22 l30 l31 l32 l33
+    float ct, cr;    // additive log-normalisers (already negated)
+};
+
+// lgamma(1.5) - lgamma(3) + 1.5 log(3 pi):  log-normaliser of the df=3, n=3 Student-t
+#define PNP_MVT3_LOGNORM 2.5510838435810745f
+// log(2 pi^2): area of S^3
+#define PNP_LOG_S3_AREA 2.9826069522587457f
+
+PNP_HD void proposal_finish(Proposal6& p) {
+    p.ct = -(logf(p.lt[0]) + logf(p.lt[2]) + logf(p.lt[5]) + PNP_MVT3_LOGNORM);
+    p.cr = -(logf(p.lr[0]) + logf(p.lr[2]) + logf(p.lr[5]) + logf(p.lr[9]) + PNP_LOG_S3_AREA);
+}
+
+// chol of a symmetric 3x3 given by its packed upper triangle, with the reference's fallback:
+// not PD -> identity (cholesky_wrapper, epropnp.py:16-33; default_diag is None on the 6DoF path)
+PNP_HD void chol3_or_identity(const Hi* a6, float* l) {
+    Hi L[9];
+    if (chol_packed<3, Hi>(a6, L)) {
+        l[0] = (float)L[0]; l[1] = (float)L[3]; l[2] = (float)L[4]; l[3] = (float)L[6]; l[4] = (float)L[7]; l[5] = (float)L[8];
+    } else { l[0] = 1.f; l[1] = 0.f; l[2] = 1.f; l[3] = 0.f; l[4] = 0.f; l[5] = 1.f; }
+}
+
+// L_r = chol(C + det(C)^(1/4) * dispersion * I), identity when not PD  (epropnp.py:301-302, 341-342)
+PNP_HD void acg_dispersed_chol(const Hi* c10, float dispersion, float* lr) {
+    Hi L[16], a[10];
+    chol_packed<4, Hi>(c10, L);
+    const Hi d = L[0] * L[5] * L[10] * L[15];            // sqrt(det C); NaN if C is not PD
+    const Hi add = sqrt(d) * (Hi)dispersion;              // det^(1/4) * dispersion
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = c10[i];
+    a[0] += add; a[4] += add; a[7] += add; a[9] += add;
+    if (chol_packed<4, Hi>(a, L)) {
+        lr[0] = (float)L[0]; lr[1] = (float)L[4]; lr[2] = (float)L[5]; lr[3] = (float)L[8]; lr[4] = (float)L[9];
+        lr[5] = (float)L[10]; lr[6] = (float)L[12]; lr[7] = (float)L[13]; lr[8] = (float)L[14]; lr[9] = (float)L[15];
+    } else {
+        lr[0] = 1.f; lr[1] = 0.f; lr[2] = 1.f; lr[3] = 0.f; lr[4] = 0.f; lr[5] = 1.f;
+        lr[6] = 0.f; lr[7] = 0.f; lr[8] = 0.f; lr[9] = 1.f;
+    }
+}
+
+// First proposal from the LM solution and its covariance (EProPnP6DoF.initial_fit, epropnp.py:288-302)
+PNP_HD_COLD void initial_fit6(const float* pose, const float* cov /*6x6 full*/, float dispersion, Proposal6& p) {
+    p.mu[0] = pose[0]; p.mu[1] = pose[1]; p.mu[2] = pose[2];
+    const Hi ctt[6] = {(Hi)cov[0], (Hi)cov[1], (Hi)cov[2], (Hi)cov[7], (Hi)cov[8], (Hi)cov[14]};
+    chol3_or_identity(ctt, p.lt);
+    // information of the rotation block, lifted to R^4 through the tangent map T(q)
+    const Hi crr[6] = {(Hi)cov[21], (Hi)cov[22], (Hi)cov[23], (Hi)cov[28], (Hi)cov[29], (Hi)cov[35]};
+    Hi info[9];
+    spd_inverse<3, Hi>(crr, info);
+    const Hi w = pose[3], x = pose[4], y = pose[5], z = pose[6];
+    const Hi T[12] = {x, y, z, -w, -z, y, z, -w, -x, -y, x, -w};    // 4x3
+    Hi TI[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            TI[i * 3 + j] = T[i * 3 + 0] * info[0 + j] + T[i * 3 + 1] * info[3 + j] + T[i * 3 + 2] * info[6 + j];
+    Hi m[10];
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = i; j < 4; ++j) {
+            m[idx] = TI[i * 3 + 0] * T[j * 3 + 0] + TI[i * 3 + 1] * T[j * 3 + 1] + TI[i * 3 + 2] * T[j * 3 + 2]
+                     + ((i == j) ? 1.0 : 0.0);
+            ++idx;
+        }
+    Hi rc[16];
+    spd_inverse<4, Hi>(m, rc);
+    const Hi tr = rc[0] + rc[5] + rc[10] + rc[15];
+    const Hi c10[10] = {rc[0] / tr, rc[1] / tr, rc[2] / tr, rc[3] / tr, rc[5] / tr, rc[6] / tr, rc[7] / tr,
+                        rc[10] / tr, rc[11] / tr, rc[15] / tr};
+    acg_dispersed_chol(c10, dispersion, p.lr);
+    proposal_finish(p);
+}
+
+// Lambda^-1 (fp32 out) of the ACG scatter matrix given as packed fp32 upper triangle
+PNP_HD_COLD void acg_scatter_inverse(const float* lam10, float* inv16) {
+    Hi a[10], inv[16];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = (Hi)lam10[i];
+    spd_inverse<4, Hi>(a, inv);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) inv16[i] = (float)inv[i];
+}
+
+// Next proposal from the refit statistics (EProPnP6DoF.estimate_params tail, epropnp.py:325, 341-342)
+PNP_HD_COLD void refit_finish6(const float* mean, const float* tc6, const float* lam10, float dispersion, Proposal6& np) {
+    np.mu[0] = mean[0]; np.mu[1] = mean[1]; np.mu[2] = mean[2];
+    Hi a6[6], c10[10];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a6[i] = (Hi)tc6[i];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) c10[i] = (Hi)lam10[i];
+    chol3_or_identity(a6, np.lt);
+    acg_dispersed_chol(c10, dispersion, np.lr);
+    proposal_finish(np);
+}
+
+// one sample from the proposal given base noise  (pyro MultivariateStudentT.rsample;
+// distributions.py:42-52 AngularCentralGaussian.rsample)
+PNP_HD void proposal_draw6(const Proposal6& p, const float* n3, float chi2, const float* n4, float* smp) {
+    const float sc = 1.0f / sqrtf(chi2 / 3.0f);
+    const float y0 = n3[0] * sc, y1 = n3[1] * sc, y2 = n3[2] * sc;
+    smp[0] = p.mu[0] + p.lt[0] * y0;
+    smp[1] = p.mu[1] + (p.lt[1] * y0 + p.lt[2] * y1);
+    smp[2] = p.mu[2] + (p.lt[3] * y0 + p.lt[4] * y1 + p.lt[5] * y2);
+    const float g0 = p.lr[0] * n4[0];
+    const float g1 = p.lr[1] * n4[0] + p.lr[2] * n4[1];
+    const float g2 = p.lr[3] * n4[0] + p.lr[4] * n4[1] + p.lr[5] * n4[2];
+    const float g3 = p.lr[6] * n4[0] + p.lr[7] * n4[1] + p.lr[8] * n4[2] + p.lr[9] * n4[3];
+    const float n = sqrtf(g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3);
+    if (n < 1e-6f) { smp[3] = 1.f; smp[4] = 0.f; smp[5] = 0.f; smp[6] = 0.f; }
+    else { smp[3] = g0 / n; smp[4] = g1 / n; smp[5] = g2 / n; smp[6] = g3 / n; }
+}
+
+// log q(sample) under one proposal  (pyro MultivariateStudentT.log_prob + distributions.py:32-40)
+PNP_HD float proposal_logpdf6(const Proposal6& p, const float* smp) {
+    const float d0 = smp[0] - p.mu[0], d1 = smp[1] - p.mu[1], d2 = smp[2] - p.mu[2];
+    const float y0 = d0 / p.lt[0];
+    const float y1 = (d1 - p.lt[1] * y0) / p.lt[2];
+    const float y2 = (d2 - p.lt[3] * y0 - p.lt[4] * y1) / p.lt[5];
+    const float mt = y0 * y0 + y1 * y1 + y2 * y2;
+    const float z0 = smp[3] / p.lr[0];
+    const float z1 = (smp[4] - p.lr[1] * z0) / p.lr[2];
+    const float z2 = (smp[5] - p.lr[3] * z0 - p.lr[4] * z1) / p.lr[5];
+    const float z3 = (smp[6] - p.lr[6] * z0 - p.lr[7] * z1 - p.lr[8] * z2) / p.lr[9];
+    const float mr = z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3;
+    return (-3.0f * log1pf(mt / 3.0f) + p.ct) + (-2.0f * logf(mr) + p.cr);
+}
+
+// q^T Lambda^-1 q for the ACG fixed-point iteration (epropnp.py:335-337)
+PNP_HD float quad4(const float* inv16, const float* q) {
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v = fmaf(inv16[i * 4 + j], q[j], v);
+        r = fmaf(q[i], v, r);
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Counter-based RNG for the production (non-injected) AMIS draws: Philox-4x32-10.
+struct Philox {
+    uint32_t k0, k1;
+    PNP_HD static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+        const uint64_t p = (uint64_t)a * b;
+        hi = (uint32_t)(p >> 32); lo = (uint32_t)p;
+    }
+    PNP_HD void operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out) const {
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t h0, l0, h1, l1;
+            mulhilo(0xD2511F53u, c0, h0, l0);
+            mulhilo(0xCD9E8D57u, c2, h1, l1);
+            const uint32_t n0 = h1 ^ c1 ^ a, n2 = h0 ^ c3 ^ b;
+            c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+};
+
+// two uniforms -> two standard normals (Box-Muller)
+PNP_HD void box_muller(uint32_t u0, uint32_t u1, float& n0, float& n1) {
+    const float a = ((float)(u0 >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0,1)
+    const float b = ((float)(u1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(a));
+    float s, c;
+#if defined(__CUDA_ARCH__)
+    sincospif(2.0f * b, &s, &c);
+#else
+    s = sinf(6.283185307179586f * b); c = cosf(6.283185307179586f * b);
+#endif
+    n0 = r * c; n1 = r * s;
+}
+
+// base noise of sample `m` of global object `obj`: n3[3], chi2 (3 dof), n4[4]
+PNP_HD void draw_base_noise(uint64_t seed, uint32_t obj, uint32_t m, float* n3, float& chi2, float* n4) {
+    Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t r[12];
+    ph(obj, m, 0u, 0x45505250u, r);
+    ph(obj, m, 1u, 0x45505250u, r + 4);
+    ph(obj, m, 2u, 0x45505250u, r + 8);
+    float g[12];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) box_muller(r[2 * i], r[2 * i + 1], g[2 * i], g[2 * i + 1]);
+    n3[0] = g[0]; n3[1] = g[1]; n3[2] = g[2];
+    chi2 = g[3] * g[3] + g[4] * g[4] + g[5] * g[5];
+    n4[0] = g[6]; n4[1] = g[7]; n4[2] = g[8]; n4[3] = g[9];
+}
+
+}  // namespace pnp

@@ -1,0 +1,150 @@
+/* epropnp_b200.h -- C ABI of libepropnp_b200.so: the EPro-PnP hot path (batched LM / GN pose solve
+ * and the AMIS Monte-Carlo loop) as hand-written sm_100a CUDA.
+ *
+ * The reference (tjiiv-cprg/EPro-PnP) has NO native interface for this path: it is ~10^3 PyTorch
+ * op launches behind Python classes.  This header is therefore the FFI a maintainer would bind
+ * underneath those classes; each entry point names the reference code it replaces (file:line under
+ * epropnp/ of the reference).  The Python mirror of the reference surface that calls it lives in
+ * epro-pnp_b200/epropnp/ ; INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous row-major fp32 unless the name ends in _host;
+ *   - the caller owns and allocates every buffer; the library keeps no state, allocates nothing,
+ *     is re-entrant, and only enqueues work on `stream` (a cudaStream_t passed as void*);
+ *   - return value: EPNP_OK or a negative EPNP_ERR_* code (never throws, never aborts);
+ *     CUDA launch errors come back as EPNP_ERR_CUDA (epnp_last_cuda_error() has the cudaError_t);
+ *   - B = objects, N = correspondences per object, D = 7 (dof 6: x y z w i j k) or 4 (dof 4:
+ *     x y z yaw), M = mc_samples, I = mc_iter, S = M / I;
+ *   - nullable arguments are marked [opt];
+ *   - AMIS outputs are OBJECT-MAJOR: pose_samples (B, M, D), logw (B, M).  The reference returns
+ *     (M, B, D) / (M, B); the Python layer hands out transposed views.
+ */
+#ifndef EPROPNP_B200_H
+#define EPROPNP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPNP_ABI_VERSION 1
+
+enum {
+    EPNP_OK = 0,
+    EPNP_ERR_BAD_ARG = -1,       /* null pointer, non-positive size, dof not in {4,6}, M % I != 0 ...  */
+    EPNP_ERR_TOO_MANY_POINTS = -2, /* N (and M) do not fit the 227 KB shared memory of one SM       */
+    EPNP_ERR_UNSUPPORTED = -3,   /* combination not built yet (4-DoF AMIS)                             */
+    EPNP_ERR_CUDA = -4,          /* a CUDA runtime call failed, see epnp_last_cuda_error()             */
+    EPNP_ERR_NO_DEVICE = -5      /* no sm_100 device is current                                        */
+};
+
+/* Hyper-parameters of the solve.  Defaults (epnp_default_params) are the reference's constructor
+ * defaults: LMSolver.__init__ levenberg_marquardt.py:31-53, HuberPnPCost.__init__ cost_fun.py:25-28,
+ * PerspectiveCamera.__init__ camera.py:35-43, EProPnPBase/6DoF.__init__ epropnp.py:47-62,273-280. */
+typedef struct EpnpParams {
+    int32_t dof;                    /* 4 or 6                                                   */
+    int32_t lm_iter;                /* LMSolver.num_iter                                        */
+    int32_t fast_mode;              /* 1: Gauss-Newton, no trust region, no clip_jac            */
+    float   z_min;                  /* PerspectiveCamera.z_min                                  */
+    float   min_lm_diagonal;
+    float   max_lm_diagonal;
+    float   min_relative_decrease;
+    float   initial_radius;         /* initial_trust_region_radius                              */
+    float   max_radius;             /* max_trust_region_radius                                  */
+    float   eps;                    /* LMSolver.eps                                             */
+    float   huber_eps;              /* HuberPnPCost.eps                                         */
+    int32_t mc_samples;             /* EProPnPBase.mc_samples  (M)                              */
+    int32_t mc_iter;                /* EProPnPBase.num_iter    (I)                              */
+    float   amis_eps;               /* EProPnPBase.eps                                          */
+    int32_t acg_mle_iter;           /* EProPnP6DoF.acg_mle_iter                                 */
+    float   acg_dispersion;         /* EProPnP6DoF.acg_dispersion                               */
+} EpnpParams;
+
+int         epnp_abi_version(void);
+const char* epnp_error_string(int code);
+int         epnp_last_cuda_error(void);             /* cudaError_t of the last EPNP_ERR_CUDA    */
+void        epnp_default_params(EpnpParams* p, int dof);
+/* Largest N one object may have (correspondences are resident in shared memory); mc_samples = 0
+ * for the LM-only entry points. */
+int         epnp_max_points(int dof, int mc_samples, int mc_iter);
+
+/* AdaptiveHuberPnPCost.set_param (cost_fun.py:123-126):
+ *   delta[b] = mean(w2d[b]) * sqrt(sum_xy var_unbiased(x2d[b])) * relative_delta               */
+int epnp_adaptive_delta_f32(const float* x2d, const float* w2d, float relative_delta,
+                            float* delta /*(B)*/, int B, int N, void* stream);
+
+/* evaluate_pnp(..., out_cost=True) for a stack of poses (common.py:67-100 through camera.py:21-30
+ * `project_b` and cost_fun.py:52-59): poses (S, B, D) -> cost (S, B).  S may be 1.
+ * lb/ub: [opt] (B, 2) clamp bounds of the projection (both or neither).                        */
+int epnp_evaluate_cost_f32(const float* x3d /*(B,N,3)*/, const float* x2d /*(B,N,2)*/,
+                           const float* w2d /*(B,N,2)*/, const float* cam_mats /*(B,3,3)*/,
+                           const float* lb, const float* ub, const float* delta /*(B)*/,
+                           const float* poses, float* cost,
+                           int S, int B, int N, int dof, float z_min, void* stream);
+
+/* evaluate_pnp(..., out_jacobian, out_residual, out_cost) at one pose per object (common.py:67-100,
+ * camera.py:10-18,64-143, cost_fun.py:33-89): pose (B, D) ->
+ * residual [opt] (B, 2N), jac [opt] (B, 2N, dof), cost [opt] (B).                              */
+int epnp_evaluate_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                      const float* lb, const float* ub, const float* delta, const float* pose,
+                      float* residual, float* jac, float* cost, int clip_jac,
+                      int B, int N, int dof, float z_min, float huber_eps, void* stream);
+
+/* LMSolver.solve with a given pose_init (levenberg_marquardt.py:80-190, _lm_iter :192-241, GN
+ * fast mode :136-152) plus, when pose_opt_plus != NULL, the extra Gauss-Newton step of
+ * LMSolver.forward (:66-68, gn_step :243-253, pose_add :255-265).
+ *   pose_opt (B, D); pose_cov [opt] (B, dof, dof) = inverse(J^T J + eps I); cost [opt] (B);
+ *   cost_init [opt] (B) = cost at pose_init (what monte_carlo_forward returns, epropnp.py:121-124) */
+int epnp_lm_solve_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                      const float* lb, const float* ub, const float* delta, const float* pose_init,
+                      float* pose_opt, float* pose_cov, float* cost, float* pose_opt_plus,
+                      float* cost_init, int B, int N, const EpnpParams* p, void* stream);
+
+/* The AMIS loop of EProPnPBase.monte_carlo_forward (epropnp.py:132-182) for EProPnP6DoF
+ * (initial_fit :288-302, gen_new/old_distr :304-315, estimate_params :317-342; proposals from
+ * distributions.py:15-52 and pyro MultivariateStudentT), starting from a given local solution.
+ *   noise_*: [opt] injected base noise, object-major, m = iteration * S + s:
+ *            noise_normal (B, M, 3), noise_chi2 (B, M), noise_rot (B, M, 4).  All three or none;
+ *            when NULL the kernel draws Philox-4x32-10 noise keyed by (seed, obj_offset + b, m),
+ *            so a sharded batch reproduces the unsharded one.
+ *   proposals [opt] (B, I, 19): mode[3], L_t[6] (row-major lower), L_r[10] per AMIS iteration.  */
+int epnp_amis_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                  const float* lb, const float* ub, const float* delta,
+                  const float* pose_opt, const float* pose_cov,
+                  const float* noise_normal, const float* noise_chi2, const float* noise_rot,
+                  uint64_t seed, uint32_t obj_offset,
+                  float* pose_samples /*(B,M,D)*/, float* logw /*(B,M)*/, float* proposals,
+                  int B, int N, const EpnpParams* p, void* stream);
+
+/* monte_carlo_forward with pose_init given and no init solver (epropnp.py:87-196 with
+ * force_init_solve=False): LM solve + covariance + AMIS in ONE launch, one CTA per object, the
+ * correspondence set staged once into shared memory (TMA bulk copies) and never re-read from HBM. */
+int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                           const float* lb, const float* ub, const float* delta, const float* pose_init,
+                           const float* noise_normal, const float* noise_chi2, const float* noise_rot,
+                           uint64_t seed, uint32_t obj_offset,
+                           float* pose_opt, float* pose_cov, float* cost, float* pose_opt_plus,
+                           float* cost_init, float* pose_samples, float* logw, float* proposals,
+                           int B, int N, const EpnpParams* p, void* stream);
+
+/* Same as epnp_lm_amis_fused_f32 with HOST buffers (pinned for full speed): copies the inputs to
+ * the caller-provided device workspace, runs the fused kernel and copies the results back, all on
+ * `stream`, in `n_chunks` object chunks so the copies of one chunk overlap the solve of another.
+ * workspace: device memory of at least epnp_fused_workspace_bytes(B, N, p) bytes.
+ * Outputs [opt] as above (pose_samples_host may be NULL to skip the largest copy).              */
+size_t epnp_fused_workspace_bytes(int B, int N, const EpnpParams* p);
+int epnp_lm_amis_fused_host_f32(const float* x3d_host, const float* x2d_host, const float* w2d_host,
+                                const float* cam_mats_host, const float* lb_host, const float* ub_host,
+                                const float* delta_host, const float* pose_init_host,
+                                uint64_t seed, uint32_t obj_offset,
+                                float* pose_opt_host, float* pose_cov_host, float* cost_host,
+                                float* pose_samples_host, float* logw_host,
+                                void* workspace, size_t workspace_bytes, int n_chunks,
+                                int B, int N, const EpnpParams* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPROPNP_B200_H */

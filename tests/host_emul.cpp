@@ -1,0 +1,272 @@
+// host_emul.cpp -- TEST-ONLY serial driver around epro-pnp_b200/csrc/pnp_math.cuh compiled with g++.
+// It lets the CPU test-suite (-m "not gpu") exercise the exact scalar code the sm_100a kernels inline
+// (per-point math, LM state machine, small Cholesky algebra, proposal draw/density, refit formulas)
+// against the golden vectors, without a GPU.  It is NOT a product path and is not shipped in the
+// library: the library has no CPU fallback.  The loops here mirror pnp_kernels.cu's control flow with
+// the parallel reductions replaced by plain sums.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../epro-pnp_b200/csrc/pnp_math.cuh"
+
+using namespace pnp;
+
+namespace {
+
+Cam make_cam(const float* cam, const float* lb, const float* ub, int b, float z_min) {
+    Cam c;
+    for (int i = 0; i < 9; ++i) c.k[i] = cam[b * 9 + i];
+    c.z_min = z_min;
+    c.bounded = (lb && ub) ? 1 : 0;
+    if (c.bounded) { c.lbx = lb[2 * b]; c.lby = lb[2 * b + 1]; c.ubx = ub[2 * b]; c.uby = ub[2 * b + 1]; }
+    else { c.lbx = c.lby = -INFINITY; c.ubx = c.uby = INFINITY; }
+    return c;
+}
+
+template <int DOF>
+void eval_ne(const float* x3d, const float* x2d, const float* w2d, int N, const float* pose, const Cam& cam,
+             float delta, float heps, bool clip, float* ev) {
+    float R[9];
+    pose_to_rot<DOF>(pose, R);
+    float acc[32];
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int n = 0; n < N; ++n) {
+        if (clip) point_normal_eq<DOF, true>(R, pose, cam, delta, heps, x3d[3 * n], x3d[3 * n + 1], x3d[3 * n + 2],
+                                              x2d[2 * n], x2d[2 * n + 1], w2d[2 * n], w2d[2 * n + 1], acc);
+        else point_normal_eq<DOF, false>(R, pose, cam, delta, heps, x3d[3 * n], x3d[3 * n + 1], x3d[3 * n + 2],
+                                          x2d[2 * n], x2d[2 * n + 1], w2d[2 * n], w2d[2 * n + 1], acc);
+    }
+    for (int i = 0; i < Dim<DOF>::NV; ++i) ev[i] = acc[i];
+}
+
+template <int DOF>
+float pose_cost_host(const float* x3d, const float* x2d, const float* w2d, int N, const float* pose, const Cam& cam,
+                     float delta) {
+    float R[9], P[12];
+    pose_to_rot<DOF>(pose, R);
+    make_proj(cam.k, R, pose, P);
+    const float half_d2 = 0.5f * delta * delta;
+    float c = 0.f;
+    for (int n = 0; n < N; ++n) {
+        if (cam.bounded)
+            c += point_cost<true>(P, cam, delta, half_d2, x3d[3 * n], x3d[3 * n + 1], x3d[3 * n + 2], x2d[2 * n],
+                                  x2d[2 * n + 1], w2d[2 * n], w2d[2 * n + 1], ExactRcp(), ExactSqrt());
+        else
+            c += point_cost<false>(P, cam, delta, half_d2, x3d[3 * n], x3d[3 * n + 1], x3d[3 * n + 2], x2d[2 * n],
+                                   x2d[2 * n + 1], w2d[2 * n], w2d[2 * n + 1], ExactRcp(), ExactSqrt());
+    }
+    return c;
+}
+
+template <int DOF>
+void lm_object(const float* x3d, const float* x2d, const float* w2d, int N, const Cam& cam, float delta,
+               const float* pose_init, const EpnpParams& p, float* pose_opt, float* cov, float* cost,
+               float* pose_plus, float* cost_init) {
+    constexpr int PD = Dim<DOF>::POSE;
+    LMState<DOF> s;
+    float ev[32];
+    for (int i = 0; i < PD; ++i) s.pose[i] = pose_init[i];
+    s.radius = p.initial_radius;
+    s.shrink = 2.0f;
+    if (!p.fast_mode) {
+        eval_ne<DOF>(x3d, x2d, w2d, N, s.pose, cam, delta, p.huber_eps, true, ev);
+        lm_adopt<DOF>(s, ev);
+        if (cost_init) *cost_init = s.cost;
+        if (p.lm_iter > 0) lm_propose<DOF>(s, p);
+        for (int it = 0; it < p.lm_iter; ++it) {
+            eval_ne<DOF>(x3d, x2d, w2d, N, s.pose_new, cam, delta, p.huber_eps, true, ev);
+            lm_update<DOF>(s, ev, p);
+            if (it + 1 < p.lm_iter) lm_propose<DOF>(s, p);
+        }
+    } else {
+        for (int it = 0; it < p.lm_iter; ++it) {
+            eval_ne<DOF>(x3d, x2d, w2d, N, s.pose, cam, delta, p.huber_eps, false, ev);
+            lm_adopt<DOF>(s, ev);
+            if (it == 0 && cost_init) *cost_init = s.cost;
+            gn_advance<DOF>(s.pose, ev, p.eps, s.pose);
+        }
+    }
+    for (int i = 0; i < PD; ++i) pose_opt[i] = s.pose[i];
+    if (cost) *cost = s.cost;
+    if (cov) pose_covariance<DOF>(s.a, p.eps, cov);
+    if (pose_plus) {
+        eval_ne<DOF>(x3d, x2d, w2d, N, s.pose, cam, delta, p.huber_eps, true, ev);
+        gn_advance<DOF>(s.pose, ev, p.eps, pose_plus);
+    }
+}
+
+void amis_object6(const float* x3d, const float* x2d, const float* w2d, int N, const Cam& cam, float delta,
+                  const float* pose_opt, const float* cov, const float* n3, const float* c2, const float* n4,
+                  uint64_t seed, uint32_t obj, const EpnpParams& p, float* samples, float* logw, float* props) {
+    const int M = p.mc_samples, I = p.mc_iter, S = M / I;
+    std::vector<Proposal6> prop(I);
+    std::vector<float> cst(M), logp((size_t)I * M), lw(M);
+    initial_fit6(pose_opt, cov, p.acg_dispersion, prop[0]);
+    for (int i = 0; i < I; ++i) {
+        for (int s = 0; s < S; ++s) {
+            const int m = i * S + s;
+            float a3[3], a4[4], chi2;
+            if (n3) { memcpy(a3, n3 + 3 * m, 12); chi2 = c2[m]; memcpy(a4, n4 + 4 * m, 16); }
+            else draw_base_noise(seed, obj, (uint32_t)m, a3, chi2, a4);
+            float* q = samples + 7 * m;
+            proposal_draw6(prop[i], a3, chi2, a4, q);
+            cst[m] = pose_cost_host<6>(x3d, x2d, w2d, N, q, cam, delta);
+            for (int j = 0; j <= i; ++j) logp[(size_t)j * M + m] = proposal_logpdf6(prop[j], q);
+        }
+        for (int m = 0; m < i * S; ++m) logp[(size_t)i * M + m] = proposal_logpdf6(prop[i], samples + 7 * m);
+        const int n = (i + 1) * S;
+        const float log_cnt = logf((float)(i + 1));
+        float mx = -INFINITY;
+        for (int m = 0; m < n; ++m) {
+            float top = logp[m];
+            for (int j = 1; j <= i; ++j) top = fmaxf(top, logp[(size_t)j * M + m]);
+            float acc = 0.f;
+            for (int j = 0; j <= i; ++j) acc += expf(logp[(size_t)j * M + m] - top);
+            lw[m] = -cst[m] - ((top + logf(acc)) - log_cnt);
+            mx = fmaxf(mx, lw[m]);
+        }
+        if (i == I - 1) { for (int m = 0; m < M; ++m) logw[m] = lw[m]; break; }
+        float sum = 0.f;
+        for (int m = 0; m < n; ++m) { lw[m] = expf(lw[m] - mx); sum += lw[m]; }
+        const float inv_sum = 1.0f / sum;
+        float mean[3] = {0, 0, 0};
+        for (int m = 0; m < n; ++m) {
+            lw[m] *= inv_sum;
+            for (int k = 0; k < 3; ++k) mean[k] = fmaf(lw[m], samples[7 * m + k], mean[k]);
+        }
+        float lam_inv[16];
+        for (int r = 0; r < 16; ++r) lam_inv[r] = (r % 5 == 0) ? 1.f : 0.f;
+        float tc[6] = {0, 0, 0, 0, 0, 0}, lam10[10];
+        for (int itr = 0; itr < p.acg_mle_iter; ++itr) {
+            float acc[17];
+            for (int r = 0; r < 17; ++r) acc[r] = 0.f;
+            for (int m = 0; m < n; ++m) {
+                const float w = lw[m];
+                const float* q = samples + 7 * m + 3;
+                const float mq = fmaxf(quad4(lam_inv, q), p.amis_eps);
+                const float wm = w / mq;
+                acc[0] += wm;
+                int idx = 1;
+                for (int r = 0; r < 4; ++r)
+                    for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
+                if (itr == 0) {
+                    const float d0 = samples[7 * m] - mean[0], d1 = samples[7 * m + 1] - mean[1], d2 = samples[7 * m + 2] - mean[2];
+                    acc[11] = fmaf(w * d0, d0, acc[11]); acc[12] = fmaf(w * d0, d1, acc[12]); acc[13] = fmaf(w * d0, d2, acc[13]);
+                    acc[14] = fmaf(w * d1, d1, acc[14]); acc[15] = fmaf(w * d1, d2, acc[15]); acc[16] = fmaf(w * d2, d2, acc[16]);
+                }
+            }
+            if (itr == 0) for (int r = 0; r < 6; ++r) tc[r] = acc[11 + r];
+            const float inv0 = 1.0f / acc[0];
+            for (int r = 0; r < 10; ++r) lam10[r] = acc[1 + r] * inv0;
+            lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
+            if (itr + 1 < p.acg_mle_iter) acg_scatter_inverse(lam10, lam_inv);
+        }
+        refit_finish6(mean, tc, lam10, p.acg_dispersion, prop[i + 1]);
+    }
+    if (props) {
+        for (int i = 0; i < I; ++i) {
+            float* o = props + i * 19;
+            for (int r = 0; r < 3; ++r) o[r] = prop[i].mu[r];
+            for (int r = 0; r < 6; ++r) o[3 + r] = prop[i].lt[r];
+            for (int r = 0; r < 10; ++r) o[9 + r] = prop[i].lr[r];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// normal equations (NV floats per object) at one pose per object
+int emul_normal_eq(const float* x3d, const float* x2d, const float* w2d, const float* cam, const float* lb,
+                   const float* ub, const float* delta, const float* pose, float* out, int clip, int B, int N,
+                   int dof, float z_min, float heps) {
+    for (int b = 0; b < B; ++b) {
+        const Cam c = make_cam(cam, lb, ub, b, z_min);
+        const float *p3 = x3d + (size_t)b * N * 3, *p2 = x2d + (size_t)b * N * 2, *pw = w2d + (size_t)b * N * 2;
+        if (dof == 6) eval_ne<6>(p3, p2, pw, N, pose + b * 7, c, delta[b], heps, clip != 0, out + b * Dim<6>::NV);
+        else eval_ne<4>(p3, p2, pw, N, pose + b * 4, c, delta[b], heps, clip != 0, out + b * Dim<4>::NV);
+    }
+    return 0;
+}
+
+int emul_residual_jac(const float* x3d, const float* x2d, const float* w2d, const float* cam, const float* lb,
+                      const float* ub, const float* delta, const float* pose, float* res, float* jac, float* cost,
+                      int clip, int B, int N, int dof, float z_min, float heps) {
+    for (int b = 0; b < B; ++b) {
+        const Cam c = make_cam(cam, lb, ub, b, z_min);
+        float R[9];
+        const int PD = dof == 6 ? 7 : 4;
+        if (dof == 6) pose_to_rot<6>(pose + b * PD, R); else pose_to_rot<4>(pose + b * PD, R);
+        float cs = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const size_t g = (size_t)b * N + n;
+            if (dof == 6)
+                cs += point_residual_jac<6>(R, pose + b * PD, c, delta[b], heps, clip != 0, x3d[g * 3], x3d[g * 3 + 1],
+                                            x3d[g * 3 + 2], x2d[g * 2], x2d[g * 2 + 1], w2d[g * 2], w2d[g * 2 + 1],
+                                            res + g * 2, jac + g * 12);
+            else
+                cs += point_residual_jac<4>(R, pose + b * PD, c, delta[b], heps, clip != 0, x3d[g * 3], x3d[g * 3 + 1],
+                                            x3d[g * 3 + 2], x2d[g * 2], x2d[g * 2 + 1], w2d[g * 2], w2d[g * 2 + 1],
+                                            res + g * 2, jac + g * 8);
+        }
+        cost[b] = cs;
+    }
+    return 0;
+}
+
+int emul_cost(const float* x3d, const float* x2d, const float* w2d, const float* cam, const float* lb, const float* ub,
+              const float* delta, const float* poses, float* cost, int S, int B, int N, int dof, float z_min) {
+    const int PD = dof == 6 ? 7 : 4;
+    for (int s = 0; s < S; ++s)
+        for (int b = 0; b < B; ++b) {
+            const Cam c = make_cam(cam, lb, ub, b, z_min);
+            const float *p3 = x3d + (size_t)b * N * 3, *p2 = x2d + (size_t)b * N * 2, *pw = w2d + (size_t)b * N * 2;
+            const float* pose = poses + ((size_t)s * B + b) * PD;
+            cost[(size_t)s * B + b] = dof == 6 ? pose_cost_host<6>(p3, p2, pw, N, pose, c, delta[b])
+                                               : pose_cost_host<4>(p3, p2, pw, N, pose, c, delta[b]);
+        }
+    return 0;
+}
+
+int emul_lm(const float* x3d, const float* x2d, const float* w2d, const float* cam, const float* lb, const float* ub,
+            const float* delta, const float* pose_init, float* pose_opt, float* cov, float* cost, float* pose_plus,
+            float* cost_init, int B, int N, const EpnpParams* p) {
+    const int dof = p->dof, PD = dof == 6 ? 7 : 4;
+    for (int b = 0; b < B; ++b) {
+        const Cam c = make_cam(cam, lb, ub, b, p->z_min);
+        const float *p3 = x3d + (size_t)b * N * 3, *p2 = x2d + (size_t)b * N * 2, *pw = w2d + (size_t)b * N * 2;
+        if (dof == 6)
+            lm_object<6>(p3, p2, pw, N, c, delta[b], pose_init + b * PD, *p, pose_opt + b * PD, cov ? cov + b * 36 : nullptr,
+                         cost ? cost + b : nullptr, pose_plus ? pose_plus + b * PD : nullptr, cost_init ? cost_init + b : nullptr);
+        else
+            lm_object<4>(p3, p2, pw, N, c, delta[b], pose_init + b * PD, *p, pose_opt + b * PD, cov ? cov + b * 16 : nullptr,
+                         cost ? cost + b : nullptr, pose_plus ? pose_plus + b * PD : nullptr, cost_init ? cost_init + b : nullptr);
+    }
+    return 0;
+}
+
+// noise object-major: n3 (B,M,3), c2 (B,M), n4 (B,M,4) or all NULL (Philox)
+int emul_amis6(const float* x3d, const float* x2d, const float* w2d, const float* cam, const float* lb, const float* ub,
+               const float* delta, const float* pose_opt, const float* cov, const float* n3, const float* c2,
+               const float* n4, uint64_t seed, uint32_t obj_offset, float* samples, float* logw, float* props, int B,
+               int N, const EpnpParams* p) {
+    const int M = p->mc_samples, I = p->mc_iter;
+    for (int b = 0; b < B; ++b) {
+        const Cam c = make_cam(cam, lb, ub, b, p->z_min);
+        const float *p3 = x3d + (size_t)b * N * 3, *p2 = x2d + (size_t)b * N * 2, *pw = w2d + (size_t)b * N * 2;
+        amis_object6(p3, p2, pw, N, c, delta[b], pose_opt + b * 7, cov + b * 36, n3 ? n3 + (size_t)b * M * 3 : nullptr,
+                     c2 ? c2 + (size_t)b * M : nullptr, n4 ? n4 + (size_t)b * M * 4 : nullptr, seed, obj_offset + b, *p,
+                     samples + (size_t)b * M * 7, logw + (size_t)b * M, props ? props + (size_t)b * I * 19 : nullptr);
+    }
+    return 0;
+}
+
+// base noise of the production RNG, for statistical tests: out (count, 8) = n3, chi2, n4
+int emul_base_noise(uint64_t seed, uint32_t obj, int count, float* out) {
+    for (int m = 0; m < count; ++m) draw_base_noise(seed, obj, (uint32_t)m, out + 8 * m, out[8 * m + 3], out + 8 * m + 4);
+    return 0;
+}
+
+}  // extern "C"

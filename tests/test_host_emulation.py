@@ -1,0 +1,185 @@
+"""CPU check of the scalar code the kernels inline (epro-pnp_b200/csrc/pnp_math.cuh), compiled with
+g++ and driven serially by tests/host_emul.cpp, against the reference's golden vectors.
+This is host-logic coverage for `-m "not gpu"`; the CUDA path itself is tested in test_gpu_parity.py."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import err_vs, golden_names, load_golden
+from epropnp_b200 import build
+from epropnp_b200.capi import EpnpParams
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return ctypes.CDLL(build.build_host_emul())
+
+
+def fptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def params_for(g, **kw):
+    p = EpnpParams(dof=int(g["dof"]), lm_iter=int(g["lm_iter"]), fast_mode=int(g["fast_mode"]),
+                   z_min=float(g["z_min"]), min_lm_diagonal=1e-6, max_lm_diagonal=1e32,
+                   min_relative_decrease=1e-3, initial_radius=30.0, max_radius=1e16, eps=1e-5,
+                   huber_eps=1e-10, mc_samples=512, mc_iter=4, amis_eps=1e-5, acg_mle_iter=3,
+                   acg_dispersion=1e-3)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def inputs(g):
+    B, N = int(g["B"]), int(g["N"])
+    f = lambda k: np.ascontiguousarray(g[k], dtype=np.float32)
+    kind = int(g["bounds"])
+    if kind == 0:
+        lb = ub = None
+    elif kind == 1:
+        lb = np.full((B, 2), float(g["lb"]), np.float32)
+        ub = np.full((B, 2), float(g["ub"]), np.float32)
+    else:
+        lb, ub = f("lb"), f("ub")
+    return B, N, f("x3d"), f("x2d"), f("w2d"), f("cam_mats"), lb, ub, f("delta"), f("pose_init")
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_point_math(emul, name):
+    g = load_golden(name)
+    B, N, x3d, x2d, w2d, cam, lb, ub, delta, pose = inputs(g)
+    dof = int(g["dof"])
+    clip = 0 if int(g["fast_mode"]) else 1
+    res = np.zeros((B, 2 * N), np.float32)
+    jac = np.zeros((B, 2 * N, dof), np.float32)
+    cost = np.zeros(B, np.float32)
+    emul.emul_residual_jac(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(pose),
+                           fptr(res), fptr(jac), fptr(cost), clip, B, N, dof, ctypes.c_float(float(g["z_min"])),
+                           ctypes.c_float(1e-10))
+    # scale-relative against the fp64 run of the reference: fp32 rounding only
+    assert err_vs(res, g["ref64_eval_residual"]) < 2e-4
+    assert err_vs(jac, g["ref64_eval_jac"]) < 2e-5
+    assert err_vs(cost, g["ref64_eval_cost"]) < 2e-5
+    # normal equations = J^T J, J^T r, cost of the golden Jacobian
+    NV = dof * (dof + 1) // 2 + dof + 1
+    ne = np.zeros((B, NV), np.float32)
+    emul.emul_normal_eq(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(pose),
+                        fptr(ne), clip, B, N, dof, ctypes.c_float(float(g["z_min"])), ctypes.c_float(1e-10))
+    J, r = g["ref64_eval_jac"], g["ref64_eval_residual"]
+    JtJ = np.einsum("bnd,bne->bde", J, J)
+    iu = np.triu_indices(dof)
+    want = np.concatenate([JtJ[:, iu[0], iu[1]], np.einsum("bnd,bn->bd", J, r), g["ref64_eval_cost"][:, None]], 1)
+    for b in range(B):
+        assert err_vs(ne[b, :-dof - 1], want[b, :-dof - 1]) < 5e-5
+        assert err_vs(ne[b, -dof - 1:-1], want[b, -dof - 1:-1]) < 5e-4    # J^T r: cancellation near the optimum
+    # cost of stacked poses (pre-multiplied projection path)
+    poses = np.ascontiguousarray(g["eval_poses"], np.float32)
+    S = poses.shape[0]
+    cm = np.zeros((S, B), np.float32)
+    emul.emul_cost(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(poses), fptr(cm),
+                   S, B, N, dof, ctypes.c_float(float(g["z_min"])))
+    assert err_vs(cm, g["ref64_eval_cost_multi"]) < 2e-5
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_lm_state_machine(emul, name):
+    g = load_golden(name)
+    B, N, x3d, x2d, w2d, cam, lb, ub, delta, pose0 = inputs(g)
+    dof = int(g["dof"])
+    PD = 7 if dof == 6 else 4
+    p = params_for(g)
+    pose = np.zeros((B, PD), np.float32)
+    cov = np.zeros((B, dof, dof), np.float32)
+    cost = np.zeros(B, np.float32)
+    plus = np.zeros((B, PD), np.float32)
+    cinit = np.zeros(B, np.float32)
+    emul.emul_lm(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(pose0), fptr(pose),
+                 fptr(cov), fptr(cost), fptr(plus), fptr(cinit), B, N, ctypes.byref(p))
+    floor = err_vs(g["ref32_lm_pose"], g["ref64_lm_pose"])
+    tol = max(1e-4, 3 * floor)
+    assert err_vs(pose, g["ref64_lm_pose"]) < tol
+    assert err_vs(pose, g["ref32_lm_pose"]) < tol
+    assert err_vs(cost, g["ref64_lm_cost"]) < max(1e-4, 3 * err_vs(g["ref32_lm_cost"], g["ref64_lm_cost"]))
+    assert err_vs(cov, g["ref64_lm_cov"]) < max(2e-3, 3 * err_vs(g["ref32_lm_cov"], g["ref64_lm_cov"]))
+    assert err_vs(plus, g["ref64_lm_pose_plus"]) < tol
+    assert err_vs(cinit, g["ref64_eval_cost"]) < 2e-5
+
+
+def _noise_object_major(g):
+    n3 = np.ascontiguousarray(np.transpose(g["noise_normal"], (2, 0, 1, 3)).reshape(int(g["B"]), -1, 3), np.float32)
+    c2 = np.ascontiguousarray(np.transpose(g["noise_chi2"], (2, 0, 1)).reshape(int(g["B"]), -1), np.float32)
+    n4 = np.ascontiguousarray(np.transpose(g["noise_rot"], (2, 0, 1, 3)).reshape(int(g["B"]), -1, 4), np.float32)
+    return n3, c2, n4
+
+
+@pytest.mark.parametrize("name", golden_names("mc6"))
+@pytest.mark.parametrize("start", ["golden_lm", "own_lm"])
+def test_amis_formulas(emul, name, start):
+    g = load_golden(name)
+    B, N, x3d, x2d, w2d, cam, lb, ub, delta, pose0 = inputs(g)
+    M, I = int(g["mc_samples_total"]), int(g["mc_iters"])
+    p = params_for(g, mc_samples=M, mc_iter=I)
+    if start == "golden_lm":
+        pose = np.ascontiguousarray(g["ref32_lm_pose"], np.float32)
+        cov = np.ascontiguousarray(g["ref32_lm_cov"], np.float32)
+    else:
+        pose = np.zeros((B, 7), np.float32)
+        cov = np.zeros((B, 6, 6), np.float32)
+        emul.emul_lm(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(pose0), fptr(pose),
+                     fptr(cov), None, None, None, B, N, ctypes.byref(p))
+    n3, c2, n4 = _noise_object_major(g)
+    smp = np.zeros((B, M, 7), np.float32)
+    logw = np.zeros((B, M), np.float32)
+    props = np.zeros((B, I, 19), np.float32)
+    emul.emul_amis6(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(pose), fptr(cov),
+                    fptr(n3), fptr(c2), fptr(n4), ctypes.c_uint64(0), ctypes.c_uint32(0), fptr(smp), fptr(logw),
+                    fptr(props), B, N, ctypes.byref(p))
+    smp_r = np.transpose(smp, (1, 0, 2))
+    logw_r = logw.T
+    floor_s = err_vs(g["ref32_mc_samples"], g["ref64_mc_samples"])
+    floor_w = err_vs(g["ref32_mc_logw"], g["ref64_mc_logw"])
+    # max-norm (dominated by a few heavy-tail samples) within 5x of the reference's own fp32 floor,
+    # bulk of the distribution (median, 99th percentile) within 3x
+    assert err_vs(smp_r, g["ref64_mc_samples"]) < max(1e-4, 5 * floor_s)
+    assert err_vs(logw_r, g["ref64_mc_logw"]) < max(1e-4, 5 * floor_w)
+    mine = np.abs(logw_r - g["ref64_mc_logw"])
+    ref = np.abs(g["ref32_mc_logw"] - g["ref64_mc_logw"])
+    for q in (50, 99):
+        assert np.percentile(mine, q) < 3 * np.percentile(ref, q) + 1e-5
+    # proposals of every AMIS iteration
+    mode = np.transpose(props[:, :, :3], (1, 0, 2))
+    assert err_vs(mode, g["ref64_mc_trans_mode"]) < 1e-4
+    lt = props[:, :, 3:9]
+    ref_lt = g["ref64_mc_trans_cov_tril"]
+    lt_full = np.stack([lt[..., 0], lt[..., 1], lt[..., 2], lt[..., 3], lt[..., 4], lt[..., 5]], -1)
+    ref_pack = np.stack([ref_lt[..., 0, 0], ref_lt[..., 1, 0], ref_lt[..., 1, 1], ref_lt[..., 2, 0],
+                         ref_lt[..., 2, 1], ref_lt[..., 2, 2]], -1)
+    fl = err_vs(g["ref32_mc_trans_cov_tril"], ref_lt)
+    assert err_vs(np.transpose(lt_full, (1, 0, 2)), ref_pack) < max(1e-3, 3 * fl)
+    ref_lr = g["ref64_mc_rot_cov_tril"]
+    rp = np.stack([ref_lr[..., i, j] for i in range(4) for j in range(i + 1)], -1)
+    fr = err_vs(g["ref32_mc_rot_cov_tril"], ref_lr)
+    assert err_vs(np.transpose(props[:, :, 9:], (1, 0, 2)), rp) < max(1e-3, 3 * fr)
+
+
+def test_production_rng_statistics(emul):
+    """Philox + Box-Muller base noise: moments of the three noise families."""
+    n = 200000
+    out = np.zeros((n, 8), np.float32)
+    emul.emul_base_noise(ctypes.c_uint64(1234), ctypes.c_uint32(7), n, fptr(out))
+    z = np.concatenate([out[:, :3], out[:, 4:]], 1).astype(np.float64)
+    assert np.abs(z.mean(0)).max() < 0.01
+    assert np.abs(z.var(0) - 1).max() < 0.02
+    assert np.abs(np.corrcoef(z.T) - np.eye(7)).max() < 0.01
+    assert abs((z ** 4).mean() - 3.0) < 0.1
+    chi = out[:, 3].astype(np.float64)
+    assert abs(chi.mean() - 3.0) < 0.03 and abs(chi.var() - 6.0) < 0.15
+    # different objects / seeds decorrelate, same key reproduces
+    out2 = np.zeros((1000, 8), np.float32)
+    emul.emul_base_noise(ctypes.c_uint64(1234), ctypes.c_uint32(8), 1000, fptr(out2))
+    assert abs(np.corrcoef(out[:1000, 0], out2[:, 0])[0, 1]) < 0.12
+    out3 = np.zeros((1000, 8), np.float32)
+    emul.emul_base_noise(ctypes.c_uint64(1234), ctypes.c_uint32(7), 1000, fptr(out3))
+    assert np.array_equal(out3, out[:1000])
