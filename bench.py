@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- EPro-PnP hot path on B200: PnP objects/sec at (B=4096 per GPU, N=512, M=512).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]           # our arm  (N>1: launched by torchrun)
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU arm: the reference's algorithm
+                                                                   # (oracle port) on the host cores
+
+One "step" = one pass of the hot path over one batch of synthetic correspondence sets: the fused
+LM(10) + covariance + AMIS(4 x 128) kernel on 4096 objects per GPU (BASELINE.json config #3/#5 shape,
+EProPnP6DoF.monte_carlo_forward with pose_init given), followed, for N > 1, by the single NCCL gather
+of poses + log-weights.  Prints ONE JSON line (rank 0).
+
+  value      objects/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same through the C-ABI call with HOST (pinned) buffers: H2D of all inputs and D2H of
+             pose / covariance / cost / log-weights / samples inside the timed region
+  roofline   algorithmic HBM bytes per launch / launch time vs the measured copy bandwidth
+             (MEASURED_PEAKS.json).  The kernel is FP32-pipe bound, not HBM bound:
+             `fp32` reports the lane-instruction estimate against 148 SM x 128 lanes x clock.
+  cpu_baseline   oracle/pnp_oracle.py (same algorithm as the reference's PyTorch layer, batched torch ops,
+             all host threads) on a bounded sample of the same workload; rank 0, N = 1 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "epro-pnp_b200"))
+
+import torch  # noqa: E402
+
+B_PER_GPU, N_PTS, MC_SAMPLES, MC_ITER, LM_ITER = 4096, 512, 512, 4, 10
+ROTATING_SETS = 4                         # 4 x 58.7 MB of inputs > 126 MB L2
+METRIC = "PnP objects/sec (B=4096,N=512,M=512)"
+
+
+def algorithmic_bytes_per_object(n=N_PTS, m=MC_SAMPLES):
+    """read 28 N + 36 (K) + 4 (delta) + 28 (pose_init); write 28 (pose) + 144 (cov) + 4 (cost)
+    + 28 M (samples) + 4 M (log-weights)."""
+    return 28 * n + 36 + 4 + 28 + 28 + 144 + 4 + 28 * m + 4 * m
+
+
+def fp32_lane_instr_per_object(n=N_PTS, m=MC_SAMPLES, k=LM_ITER):
+    """~26 issue slots per (sample, point) pair in the AMIS sweep, ~150 per point per LM
+    evaluation (K + 1 evaluations)."""
+    return 26 * n * m + 150 * n * (k + 1)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def measured_traffic():
+    """dram bytes per launch of the fused kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("fused_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
+            sm = [float(r[0]) for r in rows]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = sorted({names[i] for r in rows for i in range(4) if len(r) >= 7 and "Active" in r[3 + i] and "Not" not in r[3 + i]})
+            if sm:
+                busy = sorted(sm)[len(sm) // 2:]
+                out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                       "samples": len(sm), "power_w_max": max(float(r[2]) for r in rows)}
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+def cpu_oracle_rate(target_seconds, n_pts=N_PTS, m=MC_SAMPLES, batch=64):
+    """objects/s of the oracle port (LM + AMIS, fp32, all host threads) on a bounded sample."""
+    from oracle import pnp_oracle as orc
+    from epropnp_b200.synth import make_noise, make_problem
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pc = make_problem(batch, n_pts, seed=5)
+    n3, c2, n4 = make_noise(batch, m, seed=6)
+    S = m // MC_ITER
+    noise = (n3.reshape(batch, MC_ITER, S, 3).permute(1, 2, 0, 3).contiguous(),
+             c2.reshape(batch, MC_ITER, S).permute(1, 2, 0).contiguous(),
+             n4.reshape(batch, MC_ITER, S, 4).permute(1, 2, 0, 3).contiguous())
+    cam = orc.Camera(pc["cam_mats"], 0.1)
+
+    def run():
+        with torch.no_grad():
+            delta = orc.adaptive_delta(pc["x2d"], pc["w2d"], 0.5)
+            return orc.monte_carlo_forward_6dof(pc["x3d"], pc["x2d"], pc["w2d"], cam, delta, pc["pose_init"], noise, m,
+                                                MC_ITER, orc.LMParams(num_iter=LM_ITER))
+    run()
+    t0 = time.perf_counter()
+    runs = 0
+    while True:
+        run()
+        runs += 1
+        el = time.perf_counter() - t0
+        if el >= target_seconds or runs >= 200:
+            break
+    return batch * runs / el, cores, f"{runs} runs x {batch} objects (N={n_pts}, M={m}, LM {LM_ITER} + AMIS {MC_ITER}x{S}), fp32, {torch.get_num_threads()} threads, {el:.1f} s"
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_oracle_rate(min(per_step, 3.0))
+    rates, sample, cores = [], "", 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, cores, sample = cpu_oracle_rate(per_step)
+        rates.append(r)
+    el = time.perf_counter() - t0
+    value = statistics.mean(rates)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"EProPnP6DoF LM({LM_ITER})+AMIS({MC_ITER}x{MC_SAMPLES // MC_ITER}), N={N_PTS}, "
+                                   f"M={MC_SAMPLES}; CPU arm on a bounded sample per step"},
+            "cpu_baseline": {"value": value, "unit": "objects/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="objects per GPU (default: the metric's 4096)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from epropnp_b200 import native
+    from epropnp_b200.sharded import gather_results
+    from epropnp_b200.synth import make_problem
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    Bg = args.batch
+    B_total = Bg * world
+
+    # ---- synthetic inputs of this rank's shard (global object index keys the RNG, rank keys the data seed)
+    pc = make_problem(Bg, N_PTS, seed=1000 + rank)
+    sets = []
+    for r in range(ROTATING_SETS):
+        shift = (r * Bg) // ROTATING_SETS
+        d = {k: torch.roll(v, shifts=shift, dims=0).to(dev).contiguous() for k, v in pc.items()}
+        d["delta"] = native.adaptive_delta(d["x2d"], d["w2d"], 0.5)
+        d["prob"] = native.Problem(d["x3d"], d["x2d"], d["w2d"], d["cam_mats"], None, None, d["delta"])
+        sets.append(d)
+    params = native.default_params(6, lm_iter=LM_ITER, mc_samples=MC_SAMPLES, mc_iter=MC_ITER)
+
+    def step(i):
+        s = sets[i % ROTATING_SETS]
+        out = native.lm_amis_fused(s["prob"], s["pose_init"], params, seed=1234 + i, obj_offset=rank * Bg,
+                                   want_cost=True, want_cost_init=False)
+        if world > 1:
+            gather_results(out, B_total, keys=("pose_opt", "logw"))
+        return out
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    fence()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region: exactly K steps, one event pair around all of them + one pair per kernel launch
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    t_begin.record()
+    for i in range(args.steps):
+        k_ev[i][0].record()
+        s = sets[i % ROTATING_SETS]
+        out = native.lm_amis_fused(s["prob"], s["pose_init"], params, seed=1234 + i, obj_offset=rank * Bg,
+                                   want_cost=True, want_cost_init=False)
+        k_ev[i][1].record()
+        if world > 1:
+            gather_results(out, B_total, keys=("pose_opt", "logw"))
+    t_end.record()
+    fence()
+    total_ms = t_begin.elapsed_time(t_end)
+    kern_ms = statistics.mean(a.elapsed_time(b) for a, b in k_ev)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms, kern_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms = t.tolist()
+
+    # ---- end to end: HOST (pinned) buffers through the C ABI, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        host = {k: pc[k].contiguous().pin_memory() for k in ("x3d", "x2d", "w2d", "cam_mats", "pose_init")}
+        host["delta"] = sets[0]["delta"].cpu().pin_memory()
+        shift0 = {k: v for k, v in host.items()}
+        ws = torch.empty(native.fused_workspace_bytes(Bg, N_PTS, params), dtype=torch.uint8, device=dev)
+        res = None
+        e_steps = max(3, min(args.steps, 10))
+        for i in range(2):
+            res = native.lm_amis_fused_host(shift0, params, ws, n_chunks=8, seed=77 + i, obj_offset=rank * Bg, out=res)
+        fence()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(e_steps):
+            res = native.lm_amis_fused_host(shift0, params, ws, n_chunks=8, seed=99 + i, obj_offset=rank * Bg, out=res)
+        e1.record()
+        fence()
+        te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = sum(host[k].numel() * 4 for k in host)
+        d2h = sum(v.numel() * 4 for v in res.values() if v is not None)
+        e2e = {"value": B_total * e_steps / (te.item() * 1e-3), "unit": "objects/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e_steps, "chunks": 8,
+               "path": "epnp_lm_amis_fused_host_f32 (pinned host buffers, chunked copy/solve overlap)"}
+
+    if rank == 0:
+        peak, peak_src, sm_max = load_peaks()
+        value = B_total * args.steps / (total_ms * 1e-3)
+        per_launch_bytes = algorithmic_bytes_per_object() * Bg
+        achieved = per_launch_bytes / (kern_ms * 1e-3) / 1e9
+        clk = (clocks or {}).get("sm_mhz") or sm_max
+        fp32_peak = 148 * 128 * clk * 1e6
+        fp32_rate = fp32_lane_instr_per_object() * Bg / (kern_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"fused EProPnP6DoF.monte_carlo_forward: LM({LM_ITER}) + cov + AMIS({MC_ITER}x"
+                                   f"{MC_SAMPLES // MC_ITER}), B={Bg}/GPU, N={N_PTS}, M={MC_SAMPLES}, in-kernel Philox",
+                       "global_batch": B_total, "parallelism": f"batch-split x{world}, gather(pose,logw) only",
+                       "l2": f"rotating {ROTATING_SETS} input sets ({ROTATING_SETS * 28 * N_PTS * Bg / 1e6:.0f} MB > 126 MB L2)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": measured_traffic(), "peak_source": peak_src,
+                         "bytes_per_object": algorithmic_bytes_per_object(), "kernel_ms": kern_ms,
+                         "note": "FP32-pipe bound, not HBM bound: see fp32"},
+            "fp32": {"lane_instr_per_object_est": fp32_lane_instr_per_object(), "achieved_lane_instr_per_s": fp32_rate,
+                     "peak_lane_instr_per_s": fp32_peak, "frac": fp32_rate / fp32_peak, "sm_mhz_used": clk},
+            "clocks": clocks, "gpu_launches": args.steps * world,
+            "kernel": "solve_kernel<6,true,true> (libepropnp_b200.so)",
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_oracle_rate(12.0)
+            line["cpu_baseline"] = {"value": v, "unit": "objects/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,163 @@
+"""EProPnP6DoF / EProPnP4DoF with the reference's constructor and call signatures
+(reference epropnp/epropnp.py), executing on the native sm_100a kernels.
+
+`monte_carlo_forward` = one fused launch (epnp_lm_amis_fused_f32): the LM solve, its covariance, the
+first proposal, and all AMIS iterations (draw -> cost of every sample over all points -> mixture
+densities -> log-weights -> proposal refit) run per object inside one CTA with the correspondences
+resident in shared memory.  The reference's materialised (S, B, N, 3) intermediates, its per-iteration
+host Cholesky round trips and its ~10^3 op launches do not exist here.
+
+Layout note: the kernel writes object-major (B, M, D) / (B, M) buffers; the tuples returned below
+hold (M, B, D) / (M, B) *views* of them so reference call sites (softmax(dim=0), logsumexp(dim=0),
+[..., [0, 2]] ...) work unchanged.
+
+Extra keyword-only arguments (not in the reference): `amis_noise` = (normal3 (B,M,3), chi2 (B,M),
+rot (B,M,4)) injects the proposals' base noise (parity tests); `amis_seed` fixes the Philox stream.
+Without them a seed is drawn from torch's default CPU generator, so torch.manual_seed() governs it.
+"""
+from abc import ABCMeta, abstractmethod
+
+import torch
+
+from epropnp_b200 import native
+from .common import evaluate_pnp, pnp_normalize, pnp_denormalize
+
+
+def cholesky_wrapper(mat, default_diag=None, force_cpu=True):
+    """Batched lower Cholesky; matrices that are not positive definite fall back to diag(default_diag)
+    (or the identity).  Device-side (`cholesky_ex`), no host round trip; `force_cpu` is accepted for
+    signature compatibility and ignored (reference epropnp.py:16-33)."""
+    n = mat.size(-1)
+    L, info = torch.linalg.cholesky_ex(mat)
+    bad = info != 0
+    fallback = torch.diag(mat.new_tensor(default_diag)) if default_diag is not None else \
+        torch.eye(n, dtype=mat.dtype, device=mat.device)
+    return torch.where(bad[..., None, None], fallback, L)
+
+
+class EProPnPBase(torch.nn.Module, metaclass=ABCMeta):
+    """End-to-End Probabilistic Perspective-n-Points.
+
+    Args:
+        mc_samples (int): total number of Monte Carlo samples
+        num_iter (int): number of AMIS iterations
+        normalize (bool): centre the 3D points before solving
+        eps (float)
+        solver: PnP solver module (LMSolver)
+    """
+
+    def __init__(self, mc_samples=512, num_iter=4, normalize=False, eps=1e-5, solver=None):
+        super(EProPnPBase, self).__init__()
+        assert num_iter > 0
+        assert mc_samples % num_iter == 0
+        self.mc_samples = mc_samples
+        self.num_iter = num_iter
+        self.iter_samples = self.mc_samples // self.num_iter
+        self.eps = eps
+        self.normalize = normalize
+        self.solver = solver
+
+    @property
+    @abstractmethod
+    def dof(self):
+        pass
+
+    def _amis_params(self, camera, cost_fun, fast_mode):
+        return self.solver.native_params(camera, cost_fun, fast_mode, mc_samples=int(self.mc_samples),
+                                         mc_iter=int(self.num_iter), amis_eps=float(self.eps),
+                                         **self._extra_native_params())
+
+    def _extra_native_params(self):
+        return {}
+
+    def forward(self, *args, **kwargs):
+        return self.solver(*args, **kwargs)
+
+    def monte_carlo_forward(self, x3d, x2d, w2d, camera, cost_fun, pose_init=None, force_init_solve=True,
+                            amis_noise=None, amis_seed=None, **kwargs):
+        """Weighted pose samples from the pose distribution defined by {x3d, x2d, w2d}.
+
+        Args / returns as the reference (epropnp.py:87-113):
+            pose_opt (B, 4|7), cost (B) | None, pose_opt_plus (B, 4|7) | None,
+            pose_samples (mc_samples, B, 4|7), pose_sample_logweights (mc_samples, B), cost_init (B) | None
+        kwargs forwarded to the solver: with_pose_opt_plus, fast_mode, with_cost.
+        """
+        with_plus = kwargs.pop("with_pose_opt_plus", False)
+        fast_mode = kwargs.pop("fast_mode", False)
+        with_cost = kwargs.pop("with_cost", False)
+        if kwargs:
+            raise TypeError(f"unexpected arguments {sorted(kwargs)}")
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (x3d, x2d, w2d)):
+            from .autograd import evaluate_cost_autograd
+            evaluate_cost_autograd(x3d, x2d, w2d, pose_init, camera, cost_fun)   # raises: backward not built yet
+        if self.normalize:
+            transform, x3d, pose_init = pnp_normalize(x3d, pose_init, detach_transformation=True)
+        assert x3d.dim() == x2d.dim() == w2d.dim() == 3
+        num_obj = x3d.size(0)
+        pd = 4 if self.dof == 4 else 7
+        kw = dict(dtype=x3d.dtype, device=x3d.device)
+
+        with torch.no_grad():
+            if num_obj == 0:
+                pose_opt = torch.empty((0, pd), **kw)
+                cost = torch.empty((0,), **kw) if with_cost else None
+                pose_opt_plus = torch.empty((0, pd), **kw) if with_plus else None
+                pose_samples = torch.zeros((self.mc_samples, 0, pd), **kw)
+                logw = torch.zeros((self.mc_samples, 0), **kw)
+                cost_init = torch.empty((0,), **kw) if pose_init is not None else None
+            else:
+                needs_init_solver = pose_init is None or force_init_solve
+                cost_init = None
+                if needs_init_solver:
+                    if pose_init is not None:
+                        cost_init = evaluate_pnp(x3d, x2d, w2d, pose_init, camera, cost_fun, out_cost=True)[1]
+                    start = self.solver._starting_pose(x3d, x2d, w2d, camera, cost_fun, pose_init, cost_init,
+                                                       force_init_solve, fast_mode)
+                else:
+                    start = pose_init
+                prob = native.Problem(x3d, x2d, w2d, camera.cam_mats, camera.lb, camera.ub, cost_fun.delta)
+                seed = int(amis_seed) if amis_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+                out = native.lm_amis_fused(prob, start, self._amis_params(camera, cost_fun, fast_mode),
+                                           noise=amis_noise, seed=seed, want_cost=with_cost, want_plus=with_plus,
+                                           want_cost_init=(pose_init is not None and not needs_init_solver),
+                                           want_cov=False)
+                cast = lambda t: None if t is None else t.to(x3d.dtype)
+                pose_opt, cost, pose_opt_plus = cast(out["pose_opt"]), cast(out["cost"]), cast(out["pose_opt_plus"])
+                if cost_init is None:
+                    cost_init = cast(out["cost_init"])
+                pose_samples = cast(out["pose_samples"]).transpose(0, 1)      # (M, B, D) view
+                logw = cast(out["logw"]).transpose(0, 1)                      # (M, B) view
+
+        if self.normalize:
+            pose_opt = pnp_denormalize(transform, pose_opt)
+            pose_samples = pnp_denormalize(transform, pose_samples)
+            if pose_opt_plus is not None:
+                pose_opt_plus = pnp_denormalize(transform, pose_opt_plus)
+        return pose_opt, cost, pose_opt_plus, pose_samples, logw, cost_init
+
+
+class EProPnP4DoF(EProPnPBase):
+    """4DoF pose [x, y, z, yaw]; proposals: translation ~ multivariate t (df 3), yaw ~ 0.75 von Mises +
+    0.25 uniform (reference epropnp.py:199-260).  The LM / GN solve (`forward`) runs natively; the 4DoF
+    AMIS kernel is not built yet and `monte_carlo_forward` says so."""
+
+    dof = 4
+
+    def monte_carlo_forward(self, *args, **kwargs):
+        raise NotImplementedError("4DoF AMIS (von Mises / uniform yaw proposal) is not built yet; "
+                                  "EProPnP4DoF.forward (LM / GN solve) is available")
+
+
+class EProPnP6DoF(EProPnPBase):
+    """6DoF pose [x, y, z, w, i, j, k]; proposals: translation ~ multivariate t (df 3), orientation ~
+    angular central Gaussian (reference epropnp.py:263-342)."""
+
+    dof = 6
+
+    def __init__(self, *args, acg_mle_iter=3, acg_dispersion=0.001, **kwargs):
+        super(EProPnP6DoF, self).__init__(*args, **kwargs)
+        self.acg_mle_iter = acg_mle_iter
+        self.acg_dispersion = acg_dispersion
+
+    def _extra_native_params(self):
+        return dict(acg_mle_iter=int(self.acg_mle_iter), acg_dispersion=float(self.acg_dispersion))

@@ -1,0 +1,190 @@
+"""LMSolver / RSLMSolver with the reference's constructor and call signatures
+(reference epropnp/levenberg_marquardt.py), executing on the native sm_100a kernels.
+
+What runs where:
+  * the K-iteration Levenberg-Marquardt (or Gauss-Newton `fast_mode`) loop, the pose covariance and
+    the optional extra GN step are ONE kernel launch (epnp_lm_solve_f32): no per-iteration launches,
+    no host round trips, no materialised (B, 2N, 6) Jacobian;
+  * RSLMSolver draws its random subsets / start rotations with torch (index bookkeeping), then solves
+    all P*B mini-problems in one launch and scores the P hypotheses per object in one more.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from epropnp_b200 import native
+from .common import evaluate_pnp, pnp_normalize, pnp_denormalize
+
+
+def solve_wrapper(b, A):
+    """A^-1 b with the reference's empty-batch convention (levenberg_marquardt.py:15-19)."""
+    if A.numel() > 0:
+        return torch.linalg.solve(A, b)
+    return b + A.reshape_as(b)
+
+
+class LMSolver(nn.Module):
+    """Levenberg-Marquardt solver with a fixed number of iterations.
+
+    4DoF pose = [x, y, z, yaw] (yaw about the Y axis); 6DoF pose = [x, y, z, w, i, j, k]."""
+
+    def __init__(self, dof=4, num_iter=10, min_lm_diagonal=1e-6, max_lm_diagonal=1e32,
+                 min_relative_decrease=1e-3, initial_trust_region_radius=30.0,
+                 max_trust_region_radius=1e16, eps=1e-5, normalize=False, init_solver=None):
+        super(LMSolver, self).__init__()
+        self.dof = dof
+        self.num_iter = num_iter
+        self.min_lm_diagonal = min_lm_diagonal
+        self.max_lm_diagonal = max_lm_diagonal
+        self.min_relative_decrease = min_relative_decrease
+        self.initial_trust_region_radius = initial_trust_region_radius
+        self.max_trust_region_radius = max_trust_region_radius
+        self.eps = eps
+        self.normalize = normalize
+        self.init_solver = init_solver
+
+    # ------------------------------------------------------------------ native parameter block
+    def native_params(self, camera, cost_fun, fast_mode=False, **extra):
+        return native.default_params(
+            self.dof, lm_iter=int(self.num_iter), fast_mode=int(bool(fast_mode)), z_min=float(camera.z_min),
+            min_lm_diagonal=float(self.min_lm_diagonal), max_lm_diagonal=float(self.max_lm_diagonal),
+            min_relative_decrease=float(self.min_relative_decrease),
+            initial_radius=float(self.initial_trust_region_radius),
+            max_radius=float(self.max_trust_region_radius), eps=float(self.eps),
+            huber_eps=float(getattr(cost_fun, "eps", 1e-10)), **extra)
+
+    def _pose_dim(self):
+        return 4 if self.dof == 4 else 7
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x3d, x2d, w2d, camera, cost_fun, with_pose_opt_plus=False, pose_init=None,
+                normalize_override=None, **kwargs):
+        normalize = normalize_override if isinstance(normalize_override, bool) else self.normalize
+        if normalize:
+            transform, x3d, pose_init = pnp_normalize(x3d, pose_init, detach_transformation=True)
+        pose_opt, pose_cov, cost, pose_opt_plus = self._solve_impl(
+            x3d, x2d, w2d, camera, cost_fun, pose_init=pose_init, with_pose_opt_plus=with_pose_opt_plus, **kwargs)
+        if normalize:
+            pose_opt = pnp_denormalize(transform, pose_opt)
+            if pose_cov is not None:
+                raise NotImplementedError('Normalized covariance unsupported')
+            if pose_opt_plus is not None:
+                pose_opt_plus = pnp_denormalize(transform, pose_opt_plus)
+        return pose_opt, pose_cov, cost, pose_opt_plus
+
+    def solve(self, x3d, x2d, w2d, camera, cost_fun, pose_init=None, cost_init=None,
+              with_pose_cov=False, with_cost=False, force_init_solve=False, fast_mode=False):
+        """-> pose_opt (B, 4|7), pose_cov (B, dof, dof) | None, cost (B) | None."""
+        return self._solve_impl(x3d, x2d, w2d, camera, cost_fun, pose_init=pose_init, cost_init=cost_init,
+                                with_pose_cov=with_pose_cov, with_cost=with_cost,
+                                force_init_solve=force_init_solve, fast_mode=fast_mode)[:3]
+
+    def _starting_pose(self, x3d, x2d, w2d, camera, cost_fun, pose_init, cost_init, force_init_solve, fast_mode):
+        """pose the LM iterations start from (levenberg_marquardt.py:115-130)."""
+        if pose_init is not None and not force_init_solve:
+            return pose_init.detach()
+        assert self.init_solver is not None
+        if pose_init is None:
+            return self.init_solver.solve(x3d, x2d, w2d, camera, cost_fun, fast_mode=fast_mode)[0]
+        if cost_init is None:
+            cost_init = evaluate_pnp(x3d.detach(), x2d.detach(), w2d.detach(), pose_init.detach(), camera, cost_fun,
+                                     out_cost=True)[1]
+        pose_rs, _, cost_rs = self.init_solver.solve(x3d, x2d, w2d, camera, cost_fun, with_cost=True,
+                                                     fast_mode=fast_mode)
+        keep = (cost_init.detach() < cost_rs)[:, None]
+        return torch.where(keep, pose_init.detach().to(pose_rs.dtype), pose_rs)
+
+    @torch.no_grad()
+    def _solve_impl(self, x3d, x2d, w2d, camera, cost_fun, pose_init=None, cost_init=None, with_pose_cov=False,
+                    with_cost=False, force_init_solve=False, fast_mode=False, with_pose_opt_plus=False):
+        num_obj = x2d.size(0)
+        kw = dict(dtype=x2d.dtype, device=x2d.device)
+        if num_obj == 0:
+            return (torch.empty((0, self._pose_dim()), **kw),
+                    torch.empty((0, self.dof, self.dof), **kw) if with_pose_cov else None,
+                    torch.empty((0,), **kw) if with_cost else None,
+                    torch.empty((0, self._pose_dim()), **kw) if with_pose_opt_plus else None)
+        start = self._starting_pose(x3d, x2d, w2d, camera, cost_fun, pose_init, cost_init, force_init_solve, fast_mode)
+        prob = native.Problem(x3d, x2d, w2d, camera.cam_mats, camera.lb, camera.ub, cost_fun.delta)
+        out = native.lm_solve(prob, start, self.native_params(camera, cost_fun, fast_mode), want_cov=with_pose_cov,
+                              want_cost=with_cost, want_plus=with_pose_opt_plus)
+        cast = lambda t: None if t is None else t.to(x2d.dtype)
+        return cast(out["pose_opt"]), cast(out["pose_cov"]), cast(out["cost"]), cast(out["pose_opt_plus"])
+
+    def gn_step(self, x3d, x2d, w2d, pose, camera, cost_fun):
+        """Undamped Gauss-Newton increment -(J^T J + eps I)^-1 J^T r at `pose` (levenberg_marquardt.py:243-253)."""
+        residual, _, jac = evaluate_pnp(x3d, x2d, w2d, pose, camera, cost_fun, out_jacobian=True, out_residual=True)
+        jac_t = jac.transpose(-1, -2)
+        jtj = jac_t @ jac + torch.eye(self.dof, device=jac.device, dtype=jac.dtype) * self.eps
+        return -solve_wrapper(jac_t @ residual.unsqueeze(-1), jtj).squeeze(-1)
+
+    def pose_add(self, pose_opt, step, camera):
+        """pose (+) step; rotations are updated on the unit-quaternion manifold (levenberg_marquardt.py:255-265)."""
+        if self.dof == 4:
+            return pose_opt + step
+        q = pose_opt[..., 3:]
+        dq = (camera.get_quaternion_transfrom_mat(q) @ step[..., 3:, None]).squeeze(-1)
+        return torch.cat((pose_opt[..., :3] + step[..., :3], F.normalize(q + dq, dim=-1)), dim=-1)
+
+
+class RSLMSolver(LMSolver):
+    """Random-sample LM: a RANSAC-like initialiser for ambiguous problems (levenberg_marquardt.py:268-353)."""
+
+    def __init__(self, num_points=16, num_proposals=64, num_iter=3, **kwargs):
+        super(RSLMSolver, self).__init__(num_iter=num_iter, **kwargs)
+        self.num_points = num_points
+        self.num_proposals = num_proposals
+
+    def center_based_init(self, x2d, x3d, camera, eps=1e-6):
+        """Translation guess from the spread of the 2D points vs the 3D points (:283-298)."""
+        homo = F.pad(x2d, [0, 1], mode='constant', value=1.)
+        rays = torch.linalg.solve(camera.cam_mats, homo.transpose(-1, -2)).transpose(-1, -2)
+        rays = rays[..., :2] / rays[..., 2:].clamp(min=eps)
+        ray_std, ray_mean = torch.std_mean(rays, dim=-2)
+        obj_std = torch.std(x3d, dim=-2)
+        direction = F.pad(ray_mean, [0, 1], mode='constant', value=1.)
+        if self.dof == 4:
+            depth = obj_std[..., 1] / ray_std[..., 1].clamp(min=eps)
+        else:
+            depth = math.sqrt(2 / 3) * obj_std.norm(dim=-1) / ray_std.norm(dim=-1).clamp(min=eps)
+        return direction * depth.unsqueeze(-1)
+
+    @torch.no_grad()
+    def solve(self, x3d, x2d, w2d, camera, cost_fun, **kwargs):
+        """-> pose (B, 4|7), None, min_cost (B)."""
+        bs, pn, _ = x2d.size()
+        pd = self._pose_dim()
+        if bs == 0:
+            return x2d.new_empty((0, pd)), None, x2d.new_empty((0,))
+        P, n = self.num_proposals, self.num_points
+        x3d, x2d, w2d = x3d.detach(), x2d.detach(), w2d.detach()
+        # weighted subsets without replacement, one row per (proposal, object)
+        prob_rows = w2d.mean(dim=-1).unsqueeze(0).expand(P, bs, pn).reshape(P * bs, pn)
+        inds = torch.multinomial(prob_rows, n).reshape(P, bs, n)
+        inds = inds + (torch.arange(bs, device=inds.device) * pn)[:, None]
+        sub3 = x3d.reshape(-1, 3)[inds].reshape(P * bs, n, 3)
+        sub2 = x2d.reshape(-1, 2)[inds].reshape(P * bs, n, 2)
+        subw = w2d.reshape(-1, 2)[inds].reshape(P * bs, n, 2)
+        start = x2d.new_empty((P, bs, pd))
+        start[..., :3] = self.center_based_init(x2d, x3d, camera)
+        if self.dof == 4:
+            start[..., 3] = torch.rand((P, bs), dtype=x2d.dtype, device=x2d.device) * (2 * math.pi)
+        else:
+            q = torch.randn((P, bs, 4), dtype=x2d.dtype, device=x2d.device)
+            qn = q.norm(dim=-1, keepdim=True)
+            unit = q.new_tensor([1., 0., 0., 0.])
+            start[..., 3:] = torch.where(qn < self.eps, unit, q / qn)
+        cam_p = camera.shallow_copy().repeat_(P)
+        cost_p = cost_fun.shallow_copy().repeat_(P)
+        fast_mode = kwargs.get("fast_mode", False)
+        mini = native.Problem(sub3, sub2, subw, cam_p.cam_mats, cam_p.lb, cam_p.ub,
+                              cost_p.delta if not torch.is_tensor(cost_p.delta) or cost_p.delta.numel() == P * bs
+                              else cost_p.delta.reshape(-1))
+        sol = native.lm_solve(mini, start.reshape(P * bs, pd), self.native_params(camera, cost_fun, fast_mode))
+        pose = sol["pose_opt"].reshape(P, bs, pd).to(x2d.dtype)
+        # score every hypothesis on the full correspondence set, keep the best per object
+        cost = evaluate_pnp(x3d, x2d, w2d, pose, camera, cost_fun, out_cost=True)[1]
+        min_cost, best = cost.min(dim=0)
+        return pose[best, torch.arange(bs, device=pose.device)], None, min_cost

@@ -1,0 +1,202 @@
+"""Tensor-level entry points of the native library (one function per C-ABI call).
+
+Inputs are torch CUDA tensors; every function validates / normalises them (float32, contiguous,
+broadcast scalars), allocates the outputs with torch (the library never allocates) and enqueues
+the kernel on the current CUDA stream.  CPU tensors are rejected: there is no fallback path.
+"""
+import ctypes
+
+import torch
+
+from . import capi
+from .capi import NativeError, check, default_params, lib, ptr, stream_ptr
+
+
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise NativeError(f"{what}: tensor is on {t.device}; the EPro-PnP hot path runs on CUDA only "
+                          "(no CPU / PyTorch fallback). Move the inputs to a B200 device.")
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _bounds(lb, ub, B, device):
+    """None | float | (B,2)/(2,) tensor -> (B,2) float32 contiguous (or None, None)."""
+    if lb is None or ub is None:
+        return None, None
+
+    def one(b):
+        if torch.is_tensor(b):
+            return b.detach().to(device=device, dtype=torch.float32).expand(B, 2).contiguous()
+        return torch.full((B, 2), float(b), dtype=torch.float32, device=device)
+    return one(lb), one(ub)
+
+
+def _delta(delta, B, device):
+    if torch.is_tensor(delta):
+        return delta.detach().to(device=device, dtype=torch.float32).expand(B).contiguous()
+    return torch.full((B,), float(delta), dtype=torch.float32, device=device)
+
+
+def _cam(cam_mats, B, device):
+    return cam_mats.detach().to(device=device, dtype=torch.float32).expand(B, 3, 3).contiguous()
+
+
+class Problem:
+    """Validated, contiguous fp32 view of one batch of correspondence sets + camera + Huber delta."""
+
+    def __init__(self, x3d, x2d, w2d, cam_mats, lb, ub, delta):
+        _need_cuda(x3d, "x3d")
+        if x3d.dim() != 3 or x2d.dim() != 3 or w2d.dim() != 3:
+            raise ValueError("x3d/x2d/w2d must be (num_obj, num_pts, 3|2|2)")
+        self.B, self.N = x3d.shape[0], x3d.shape[1]
+        self.device = x3d.device
+        self.x3d, self.x2d, self.w2d = _f32c(x3d), _f32c(x2d), _f32c(w2d)
+        self.cam = _cam(cam_mats, self.B, self.device)
+        self.lb, self.ub = _bounds(lb, ub, self.B, self.device)
+        self.delta = _delta(delta, self.B, self.device)
+
+    def common_ptrs(self):
+        return (ptr(self.x3d), ptr(self.x2d), ptr(self.w2d), ptr(self.cam), ptr(self.lb), ptr(self.ub),
+                ptr(self.delta))
+
+    def empty(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+
+def adaptive_delta(x2d, w2d, relative_delta):
+    _need_cuda(x2d, "x2d")
+    B, N = x2d.shape[0], x2d.shape[1]
+    x2d, w2d = _f32c(x2d), _f32c(w2d)
+    out = torch.empty(B, dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        check(lib().epnp_adaptive_delta_f32(ptr(x2d), ptr(w2d), ctypes.c_float(relative_delta), ptr(out), B, N,
+                                            stream_ptr(x2d.device)), "epnp_adaptive_delta_f32")
+    return out
+
+
+def evaluate_cost(prob: Problem, poses, dof, z_min):
+    """poses (S, B, D) -> cost (S, B)."""
+    S = poses.shape[0]
+    poses = _f32c(poses)
+    out = prob.empty(S, prob.B)
+    with torch.cuda.device(prob.device):
+        check(lib().epnp_evaluate_cost_f32(*prob.common_ptrs(), ptr(poses), ptr(out), S, prob.B, prob.N, dof,
+                                           ctypes.c_float(z_min), stream_ptr(prob.device)), "epnp_evaluate_cost_f32")
+    return out
+
+
+def evaluate_full(prob: Problem, pose, dof, z_min, huber_eps, clip_jac, want_residual, want_jac, want_cost):
+    pose = _f32c(pose)
+    B, N = prob.B, prob.N
+    res = prob.empty(B, 2 * N) if want_residual else None
+    jac = prob.empty(B, 2 * N, dof) if want_jac else None
+    cost = prob.empty(B) if want_cost else None
+    with torch.cuda.device(prob.device):
+        check(lib().epnp_evaluate_f32(*prob.common_ptrs(), ptr(pose), ptr(res), ptr(jac), ptr(cost), int(clip_jac),
+                                      B, N, dof, ctypes.c_float(z_min), ctypes.c_float(huber_eps),
+                                      stream_ptr(prob.device)), "epnp_evaluate_f32")
+    return res, cost, jac
+
+
+def lm_solve(prob: Problem, pose_init, params, want_cov=False, want_cost=False, want_plus=False,
+             want_cost_init=False):
+    D = 7 if params.dof == 6 else 4
+    B = prob.B
+    pose_init = _f32c(pose_init)
+    out = dict(pose_opt=prob.empty(B, D),
+               pose_cov=prob.empty(B, params.dof, params.dof) if want_cov else None,
+               cost=prob.empty(B) if want_cost else None,
+               pose_opt_plus=prob.empty(B, D) if want_plus else None,
+               cost_init=prob.empty(B) if want_cost_init else None)
+    with torch.cuda.device(prob.device):
+        check(lib().epnp_lm_solve_f32(*prob.common_ptrs(), ptr(pose_init), ptr(out["pose_opt"]), ptr(out["pose_cov"]),
+                                      ptr(out["cost"]), ptr(out["pose_opt_plus"]), ptr(out["cost_init"]), B, prob.N,
+                                      ctypes.byref(params), stream_ptr(prob.device)), "epnp_lm_solve_f32")
+    return out
+
+
+def _noise_ptrs(noise):
+    if noise is None:
+        return None, None, None, ()
+    n3, c2, n4 = (_f32c(t) for t in noise)
+    return ptr(n3), ptr(c2), ptr(n4), (n3, c2, n4)
+
+
+def amis(prob: Problem, pose_opt, pose_cov, params, noise=None, seed=0, obj_offset=0, want_proposals=False):
+    """-> pose_samples (B, M, D), logw (B, M) [object-major], proposals (B, I, 19) | None."""
+    D = 7 if params.dof == 6 else 4
+    B, M, I = prob.B, params.mc_samples, params.mc_iter
+    pose_opt, pose_cov = _f32c(pose_opt), _f32c(pose_cov)
+    samples, logw = prob.empty(B, M, D), prob.empty(B, M)
+    props = prob.empty(B, I, 19) if want_proposals else None
+    p3, p2, p4, keep = _noise_ptrs(noise)
+    with torch.cuda.device(prob.device):
+        check(lib().epnp_amis_f32(*prob.common_ptrs(), ptr(pose_opt), ptr(pose_cov), p3, p2, p4,
+                                  ctypes.c_uint64(seed), ctypes.c_uint32(obj_offset), ptr(samples), ptr(logw),
+                                  ptr(props), B, prob.N, ctypes.byref(params), stream_ptr(prob.device)),
+              "epnp_amis_f32")
+    del keep
+    return samples, logw, props
+
+
+def lm_amis_fused(prob: Problem, pose_init, params, noise=None, seed=0, obj_offset=0, want_cost=False,
+                  want_plus=False, want_cost_init=True, want_proposals=False, want_cov=True):
+    D = 7 if params.dof == 6 else 4
+    B, M, I = prob.B, params.mc_samples, params.mc_iter
+    pose_init = _f32c(pose_init)
+    out = dict(pose_opt=prob.empty(B, D), pose_cov=prob.empty(B, params.dof, params.dof) if want_cov else None,
+               cost=prob.empty(B) if want_cost else None,
+               pose_opt_plus=prob.empty(B, D) if want_plus else None,
+               cost_init=prob.empty(B) if want_cost_init else None,
+               pose_samples=prob.empty(B, M, D), logw=prob.empty(B, M),
+               proposals=prob.empty(B, I, 19) if want_proposals else None)
+    p3, p2, p4, keep = _noise_ptrs(noise)
+    with torch.cuda.device(prob.device):
+        check(lib().epnp_lm_amis_fused_f32(*prob.common_ptrs(), ptr(pose_init), p3, p2, p4,
+                                           ctypes.c_uint64(seed), ctypes.c_uint32(obj_offset),
+                                           ptr(out["pose_opt"]), ptr(out["pose_cov"]), ptr(out["cost"]),
+                                           ptr(out["pose_opt_plus"]), ptr(out["cost_init"]),
+                                           ptr(out["pose_samples"]), ptr(out["logw"]), ptr(out["proposals"]),
+                                           B, prob.N, ctypes.byref(params), stream_ptr(prob.device)),
+              "epnp_lm_amis_fused_f32")
+    del keep
+    return out
+
+
+def fused_workspace_bytes(B, N, params):
+    return int(lib().epnp_fused_workspace_bytes(B, N, ctypes.byref(params)))
+
+
+def lm_amis_fused_host(host, params, workspace, n_chunks=8, seed=0, obj_offset=0, out=None, want_samples=True):
+    """End-to-end call with HOST (pinned) tensors: host = dict(x3d, x2d, w2d, cam_mats, lb, ub, delta,
+    pose_init) of CPU float32 tensors; `workspace` a CUDA uint8 tensor of fused_workspace_bytes().
+    Results land in `out` (pinned CPU tensors, allocated when None).  Work is enqueued on the current
+    stream of the workspace's device; synchronise that stream before reading `out`."""
+    B, N = host["x3d"].shape[0], host["x3d"].shape[1]
+    D = 7 if params.dof == 6 else 4
+    M = params.mc_samples
+    if out is None:
+        pin = dict(dtype=torch.float32, pin_memory=True)
+        out = dict(pose_opt=torch.empty(B, D, **pin), pose_cov=torch.empty(B, params.dof, params.dof, **pin),
+                   cost=torch.empty(B, **pin), logw=torch.empty(B, M, **pin),
+                   pose_samples=torch.empty(B, M, D, **pin) if want_samples else None)
+    for k in ("x3d", "x2d", "w2d", "cam_mats", "delta", "pose_init"):
+        t = host[k]
+        assert (not t.is_cuda) and t.dtype == torch.float32 and t.is_contiguous(), k
+    dev = workspace.device
+    with torch.cuda.device(dev):
+        check(lib().epnp_lm_amis_fused_host_f32(
+            ptr(host["x3d"]), ptr(host["x2d"]), ptr(host["w2d"]), ptr(host["cam_mats"]), ptr(host.get("lb")),
+            ptr(host.get("ub")), ptr(host["delta"]), ptr(host["pose_init"]), ctypes.c_uint64(seed),
+            ctypes.c_uint32(obj_offset), ptr(out["pose_opt"]), ptr(out["pose_cov"]), ptr(out["cost"]),
+            ptr(out.get("pose_samples")), ptr(out["logw"]), ctypes.c_void_p(workspace.data_ptr()),
+            ctypes.c_size_t(workspace.numel()), int(n_chunks), B, N, ctypes.byref(params), stream_ptr(dev)),
+            "epnp_lm_amis_fused_host_f32")
+    return out
+
+
+__all__ = ["Problem", "adaptive_delta", "evaluate_cost", "evaluate_full", "lm_solve", "amis", "lm_amis_fused",
+           "lm_amis_fused_host", "fused_workspace_bytes", "default_params", "NativeError", "capi"]

@@ -1,0 +1,122 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/epropnp_b200.h
+declares; argument validation that needs no device works; the product path refuses CPU tensors."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+from epropnp_b200 import build, capi, native
+
+
+@pytest.fixture(scope="module")
+def handle():
+    build.build_library()
+    return capi.lib()
+
+
+def test_header_symbols_are_exported(handle):
+    header = open(os.path.join(ROOT, "include", "epropnp_b200.h")).read()
+    declared = set(re.findall(r"\b(epnp_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(capi.exported_symbols()), declared ^ set(capi.exported_symbols())
+    for name in declared:
+        assert hasattr(handle, name), name
+
+
+def test_abi_basics(handle):
+    assert handle.epnp_abi_version() == 1
+    assert handle.epnp_error_string(0) == b"ok"
+    assert b"shared memory" in handle.epnp_error_string(-2)
+    p = capi.default_params(6)
+    assert (p.dof, p.lm_iter, p.mc_samples, p.mc_iter, p.acg_mle_iter) == (6, 10, 512, 4, 3)
+    assert abs(p.initial_radius - 30.0) < 1e-6 and abs(p.eps - 1e-5) < 1e-12 and abs(p.z_min - 0.1) < 1e-7
+    assert ctypes.sizeof(capi.EpnpParams) == 64
+    # resident-point capacity: the bench / dense configs must fit
+    assert handle.epnp_max_points(6, 512, 4) >= 4096
+    assert handle.epnp_max_points(6, 0, 0) >= 4096
+    assert handle.epnp_max_points(6, 512, 4) % 4 == 0
+
+
+def test_bad_arguments_are_rejected_without_a_device(handle):
+    p = capi.default_params(6)
+    null = None
+    assert handle.epnp_lm_solve_f32(null, null, null, null, null, null, null, null, null, null, null, null, null,
+                                    4, 64, ctypes.byref(p), None) == -1
+    p.mc_samples, p.mc_iter = 510, 4       # M % I != 0
+    one = ctypes.c_void_p(16)
+    assert handle.epnp_amis_f32(one, one, one, one, null, null, one, one, one, null, null, null, 0, 0, one, one, null,
+                                4, 64, ctypes.byref(p), None) == -1
+    p4 = capi.default_params(4)
+    assert handle.epnp_amis_f32(one, one, one, one, null, null, one, one, one, null, null, null, 0, 0, one, one, null,
+                                4, 64, ctypes.byref(p4), None) == -3
+    assert handle.epnp_fused_workspace_bytes(4096, 512, ctypes.byref(capi.default_params(6))) > 4096 * 512 * 28
+
+
+def test_product_path_refuses_cpu_tensors():
+    from epropnp.camera import PerspectiveCamera
+    from epropnp.cost_fun import HuberPnPCost
+    from epropnp.levenberg_marquardt import LMSolver
+    x3d, x2d, w2d = torch.rand(2, 8, 3), torch.rand(2, 8, 2), torch.rand(2, 8, 2)
+    cam = PerspectiveCamera(cam_mats=torch.eye(3).expand(2, 3, 3))
+    pose = torch.tensor([[0, 0, 5, 1, 0, 0, 0.]]).repeat(2, 1)
+    with pytest.raises(native.NativeError, match="no CPU"):
+        LMSolver(dof=6)(x3d, x2d, w2d, cam, HuberPnPCost(), pose_init=pose)
+
+
+def test_reference_surface_is_importable():
+    import epropnp.camera as c, epropnp.common as m, epropnp.cost_fun as f          # noqa: E401
+    import epropnp.distributions as d, epropnp.epropnp as e, epropnp.levenberg_marquardt as l   # noqa: E401
+    assert "epro-pnp_b200" in os.path.abspath(e.__file__)
+    for mod, names in ((e, "EProPnP6DoF EProPnP4DoF EProPnPBase cholesky_wrapper"),
+                       (l, "LMSolver RSLMSolver solve_wrapper"), (c, "PerspectiveCamera"),
+                       (f, "HuberPnPCost AdaptiveHuberPnPCost huber_kernel huber_d_kernel"),
+                       (m, "evaluate_pnp pnp_normalize pnp_denormalize quaternion_to_rot_mat yaw_to_rot_mat skew"),
+                       (d, "AngularCentralGaussian VonMisesUniformMix")):
+        for n in names.split():
+            assert hasattr(mod, n), n
+    layer = e.EProPnP6DoF(mc_samples=512, num_iter=4, solver=l.LMSolver(dof=6, num_iter=10))
+    assert len(layer.state_dict()) == 0 and layer.iter_samples == 128
+    with pytest.raises(AssertionError):
+        e.EProPnP6DoF(mc_samples=510, num_iter=4)
+    # empty batch keeps the reference's shapes without touching the device
+    cam = c.PerspectiveCamera(cam_mats=torch.zeros(0, 3, 3))
+    r = layer.monte_carlo_forward(torch.zeros(0, 8, 3), torch.zeros(0, 8, 2), torch.zeros(0, 8, 2), cam,
+                                  f.HuberPnPCost(), pose_init=torch.zeros(0, 7), force_init_solve=False)
+    assert r[0].shape == (0, 7) and r[3].shape == (512, 0, 7) and r[4].shape == (512, 0) and r[5].shape == (0,)
+    s = l.LMSolver(dof=6).solve(torch.zeros(0, 8, 3), torch.zeros(0, 8, 2), torch.zeros(0, 8, 2), cam,
+                                f.HuberPnPCost(), pose_init=torch.zeros(0, 7), with_pose_cov=True, with_cost=True)
+    assert s[0].shape == (0, 7) and s[1].shape == (0, 6, 6) and s[2].shape == (0,)
+
+
+def test_torch_side_helpers_match_oracle():
+    from oracle import pnp_oracle as orc
+    from epropnp.common import pnp_denormalize, pnp_normalize, quaternion_to_rot_mat, skew, yaw_to_rot_mat
+    from epropnp.camera import PerspectiveCamera
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(5, 4, generator=g, dtype=torch.float64)
+    q = q / q.norm(dim=-1, keepdim=True)
+    assert torch.allclose(quaternion_to_rot_mat(q), orc.quat_to_rotmat(q))
+    yaw = torch.randn(5, generator=g, dtype=torch.float64)
+    assert torch.allclose(yaw_to_rot_mat(yaw), orc.yaw_to_rotmat(yaw))
+    v = torch.randn(5, 3, generator=g, dtype=torch.float64)
+    w = torch.randn(5, 3, generator=g, dtype=torch.float64)
+    assert torch.allclose((skew(v) @ w[..., None]).squeeze(-1), torch.linalg.cross(v, w))
+    assert torch.allclose(PerspectiveCamera.get_quaternion_transfrom_mat(q), orc.quat_tangent_map(q))
+    x3d = torch.randn(5, 9, 3, generator=g, dtype=torch.float64)
+    pose = torch.cat((torch.randn(5, 3, generator=g, dtype=torch.float64), q), -1)
+    off, xn, pn = pnp_normalize(x3d, pose)
+    off_o, xn_o, pn_o = orc.normalize_points(x3d, pose)
+    assert torch.allclose(xn, xn_o) and torch.allclose(pn, pn_o)
+    assert torch.allclose(pnp_denormalize(off, pn), pose)
+    # standalone projection utility against the oracle's evaluate (camera Jacobian * weights)
+    cam_mats = torch.tensor([[800., 0, 320], [0, 800, 240], [0, 0, 1]], dtype=torch.float64).expand(5, 3, 3)
+    pose[:, 2] += 6
+    cam = PerspectiveCamera(cam_mats=cam_mats, z_min=0.1)
+    u, jac = cam.project(x3d, pose, out_jac=True)
+    x2d = u + 0.5
+    w2d = torch.ones_like(x2d)
+    e = orc.evaluate(x3d, x2d, w2d, pose, orc.Camera(cam_mats, 0.1), 1e9, want_jac=True)
+    assert torch.allclose(jac.flatten(-3, -2), e["jac"], rtol=1e-9, atol=1e-9)

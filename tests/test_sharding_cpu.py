@@ -1,0 +1,58 @@
+"""World-size-2 (and 3, ragged) gloo test of the batch sharding + gather logic -- no GPU needed."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from epropnp_b200.sharded import gather_objects, gather_results, shard_range, shard_sizes
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 8, 4096, 32768, 1001):
+        for w in (1, 2, 3, 4, 8):
+            edges = [shard_range(n, r, w) for r in range(w)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
+            sizes = shard_sizes(n, w)
+            assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, num_obj, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full_pose = torch.arange(num_obj * 7, dtype=torch.float32).reshape(num_obj, 7)
+        full_logw = torch.arange(num_obj * 16, dtype=torch.float32).reshape(num_obj, 16) * 0.5
+        b, e = shard_range(num_obj, rank, world)
+        local = dict(pose_opt=full_pose[b:e].clone(), logw=full_logw[b:e].clone(), pose_cov=None, cost=None)
+        got = gather_results(local, num_obj)
+        ok = torch.equal(got["pose_opt"], full_pose) and torch.equal(got["logw"], full_logw) and "cost" not in got
+        ok = ok and torch.equal(gather_objects(full_pose[b:e].clone(), num_obj), full_pose)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,num_obj", [(2, 8), (2, 9), (3, 10)])
+def test_gather_gloo(world, num_obj):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, num_obj, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(r, True) for r in range(world)]
