@@ -244,9 +244,25 @@ PNP_HD float point_residual_jac(const float* R, const float* t, const Cam& c, fl
 // rounding term of the fp32 reference from our side of the parity budget.
 typedef double Hi;
 
-// a: packed upper triangle (row-major).  L: full n*n row-major lower factor.  Returns false when a
-// pivot is not positive (LAPACK potrf's failure test: pivot <= 0 or NaN).
-template <int N, class T> PNP_HD bool chol_packed(const T* a, T* L) {
+PNP_HD float inv_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+PNP_HD double inv_sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// a: packed upper triangle (row-major).  L: full n*n row-major lower factor with the RECIPROCAL of the
+// diagonal stored in Dinv (so the substitutions below multiply instead of divide).  Returns false when
+// a pivot is not positive (LAPACK potrf's failure test: pivot <= 0 or NaN).
+template <int N, class T> PNP_HD bool chol_packed(const T* a, T* L, T* Dinv) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
@@ -254,9 +270,9 @@ template <int N, class T> PNP_HD bool chol_packed(const T* a, T* L) {
 #pragma unroll
         for (int k = 0; k < j; ++k) d -= L[j * N + k] * L[j * N + k];
         ok = ok && (d > T(0));
-        const T ljj = sqrt(d);
-        L[j * N + j] = ljj;
-        const T inv = T(1) / ljj;
+        const T inv = inv_sqrt(d);
+        Dinv[j] = inv;
+        L[j * N + j] = d * inv;
 #pragma unroll
         for (int i = j + 1; i < N; ++i) {
             T v = a[tri(j, i, N)];
@@ -271,45 +287,45 @@ template <int N, class T> PNP_HD bool chol_packed(const T* a, T* L) {
 }
 
 // x = A^-1 b through the Cholesky factor (A SPD).  NaN when A is not PD.
-template <int N, class T> PNP_HD void chol_solve(const T* L, const T* b, T* x) {
+template <int N, class T> PNP_HD void chol_solve(const T* L, const T* Dinv, const T* b, T* x) {
     T y[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         T v = b[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) v -= L[i * N + k] * y[k];
-        y[i] = v / L[i * N + i];
+        y[i] = v * Dinv[i];
     }
 #pragma unroll
     for (int i = N - 1; i >= 0; --i) {
         T v = y[i];
 #pragma unroll
         for (int k = i + 1; k < N; ++k) v -= L[k * N + i] * x[k];
-        x[i] = v / L[i * N + i];
+        x[i] = v * Dinv[i];
     }
 }
 
 // inverse of the lower factor (lower triangular, full storage)
-template <int N, class T> PNP_HD void tri_inverse(const T* L, T* Li) {
+template <int N, class T> PNP_HD void tri_inverse(const T* L, const T* Dinv, T* Li) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             if (i < j) { Li[i * N + j] = T(0); continue; }
-            if (i == j) { Li[i * N + j] = T(1) / L[i * N + i]; continue; }
+            if (i == j) { Li[i * N + j] = Dinv[i]; continue; }
             T v = T(0);
 #pragma unroll
             for (int k = j; k < i; ++k) v -= L[i * N + k] * Li[k * N + j];
-            Li[i * N + j] = v / L[i * N + i];
+            Li[i * N + j] = v * Dinv[i];
         }
     }
 }
 
 // A^-1 (full, symmetric) = Li^T Li.  Replaces torch.inverse on the SPD matrices of the path.
 template <int N, class T> PNP_HD bool spd_inverse(const T* a_packed, T* inv_full) {
-    T L[N * N], Li[N * N];
-    const bool ok = chol_packed<N, T>(a_packed, L);
-    tri_inverse<N, T>(L, Li);
+    T L[N * N], Li[N * N], Dinv[N];
+    const bool ok = chol_packed<N, T>(a_packed, L, Dinv);
+    tri_inverse<N, T>(L, Dinv, Li);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
 #pragma unroll
@@ -347,27 +363,66 @@ template <int DOF> PNP_HD void lm_adopt(LMState<DOF>& s, const float* acc) {
     s.cost = acc[NA + DOF];
 }
 
-// step = -(A + diag(add))^-1 g, in fp64; returns step in fp32 and the model cost change
-// -step^T (A step / 2 + g)   (levenberg_marquardt.py:205-216, 225)
-template <int DOF> PNP_HD_COLD float damped_step(const float* a, const float* g, const float* add, float* step) {
+// step = -(A + diag(add))^-1 g and the model cost change -step^T (A step / 2 + g)
+// (levenberg_marquardt.py:205-216, 225).  T = float inside the LM / GN iterations (a step only has to
+// decrease the cost; the iteration corrects its rounding), so the per-iteration serial section is a
+// short fp32 chain with MUFU rsqrt and no divisions.
+template <int DOF, class T> PNP_HD float damped_step(const float* a, const float* g, const float* add, float* step) {
     constexpr int NA = Dim<DOF>::NA;
-    Hi al[NA], gh[DOF], L[DOF * DOF], st[DOF];
+    T al[NA], gh[DOF], L[DOF * DOF], Dinv[DOF], st[DOF];
 #pragma unroll
-    for (int i = 0; i < NA; ++i) al[i] = (Hi)a[i];
+    for (int i = 0; i < NA; ++i) al[i] = (T)a[i];
 #pragma unroll
-    for (int i = 0; i < DOF; ++i) { al[tri(i, i, DOF)] += (Hi)add[i]; gh[i] = (Hi)g[i]; }
-    chol_packed<DOF, Hi>(al, L);
-    chol_solve<DOF, Hi>(L, gh, st);
+    for (int i = 0; i < DOF; ++i) { al[tri(i, i, DOF)] += (T)add[i]; gh[i] = (T)g[i]; }
+    chol_packed<DOF, T>(al, L, Dinv);
+    chol_solve<DOF, T>(L, Dinv, gh, st);
+    T m = 0;
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) {
+        T v = 0;
+#pragma unroll
+        for (int j = 0; j < DOF; ++j) v += (T)a[(i <= j) ? tri(i, j, DOF) : tri(j, i, DOF)] * (-st[j]);
+        m += (-st[i]) * (v * T(0.5) + gh[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) step[i] = (float)(-st[i]);
+    return (float)(-m);
+}
+
+// Same result to ~fp64 accuracy at fp32 latency: fp32 Cholesky solve, then ONE step of iterative
+// refinement whose residual g - (A + D) x is formed in fp64 (6 independent length-DOF dot products, no
+// fp64 sqrt / divide chain) and solved again with the fp32 factor.
+template <int DOF> PNP_HD float damped_step_refined(const float* a, const float* g, const float* add, float* step) {
+    constexpr int NA = Dim<DOF>::NA;
+    float al[NA], L[DOF * DOF], Dinv[DOF], x[DOF], r[DOF], dx[DOF];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) al[i] = a[i];
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) al[tri(i, i, DOF)] += add[i];
+    chol_packed<DOF, float>(al, L, Dinv);
+    chol_solve<DOF, float>(L, Dinv, g, x);
+    Hi xh[DOF];
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) {
+        Hi v = (Hi)g[i];
+#pragma unroll
+        for (int j = 0; j < DOF; ++j) {
+            const Hi aij = (Hi)a[(i <= j) ? tri(i, j, DOF) : tri(j, i, DOF)] + ((i == j) ? (Hi)add[i] : Hi(0));
+            v -= aij * (Hi)x[j];
+        }
+        r[i] = (float)v;
+    }
+    chol_solve<DOF, float>(L, Dinv, r, dx);
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) { xh[i] = (Hi)x[i] + (Hi)dx[i]; step[i] = (float)(-xh[i]); }
     Hi m = 0;
 #pragma unroll
     for (int i = 0; i < DOF; ++i) {
         Hi v = 0;
 #pragma unroll
-        for (int j = 0; j < DOF; ++j) v += (Hi)a[(i <= j) ? tri(i, j, DOF) : tri(j, i, DOF)] * (-st[j]);
-        m += (-st[i]) * (v * 0.5 + gh[i]);
+        for (int j = 0; j < DOF; ++j) v += (Hi)a[(i <= j) ? tri(i, j, DOF) : tri(j, i, DOF)] * (-xh[j]);
+        m += (-xh[i]) * (v * 0.5 + (Hi)g[i]);
     }
-#pragma unroll
-    for (int i = 0; i < DOF; ++i) step[i] = (float)(-st[i]);
     return (float)(-m);
 }
 
@@ -379,7 +434,7 @@ template <int DOF> PNP_HD void lm_propose(LMState<DOF>& s, const Params& p) {
         const float d = s.a[tri(i, i, DOF)];
         add[i] = fminf(fmaxf(d, p.min_lm_diagonal), p.max_lm_diagonal) / s.radius + p.eps;
     }
-    s.model_change = damped_step<DOF>(s.a, s.g, add, step);
+    s.model_change = damped_step_refined<DOF>(s.a, s.g, add, step);
     pose_add<DOF>(s.pose, step, s.pose_new);
 }
 
@@ -411,7 +466,7 @@ template <int DOF> PNP_HD void gn_advance(const float* pose, const float* acc, f
     float add[DOF], step[DOF];
 #pragma unroll
     for (int i = 0; i < DOF; ++i) add[i] = eps;
-    damped_step<DOF>(acc, acc + Dim<DOF>::NA, add, step);
+    damped_step_refined<DOF>(acc, acc + Dim<DOF>::NA, add, step);
     pose_add<DOF>(pose, step, pose_out);
 }
 
@@ -451,22 +506,22 @@ PNP_HD void proposal_finish(Proposal6& p) {
 // chol of a symmetric 3x3 given by its packed upper triangle, with the reference's fallback:
 // not PD -> identity (cholesky_wrapper, epropnp.py:16-33; default_diag is None on the 6DoF path)
 PNP_HD void chol3_or_identity(const Hi* a6, float* l) {
-    Hi L[9];
-    if (chol_packed<3, Hi>(a6, L)) {
+    Hi L[9], Dinv[3];
+    if (chol_packed<3, Hi>(a6, L, Dinv)) {
         l[0] = (float)L[0]; l[1] = (float)L[3]; l[2] = (float)L[4]; l[3] = (float)L[6]; l[4] = (float)L[7]; l[5] = (float)L[8];
     } else { l[0] = 1.f; l[1] = 0.f; l[2] = 1.f; l[3] = 0.f; l[4] = 0.f; l[5] = 1.f; }
 }
 
 // L_r = chol(C + det(C)^(1/4) * dispersion * I), identity when not PD  (epropnp.py:301-302, 341-342)
 PNP_HD void acg_dispersed_chol(const Hi* c10, float dispersion, float* lr) {
-    Hi L[16], a[10];
-    chol_packed<4, Hi>(c10, L);
+    Hi L[16], a[10], Dinv[4];
+    chol_packed<4, Hi>(c10, L, Dinv);
     const Hi d = L[0] * L[5] * L[10] * L[15];            // sqrt(det C); NaN if C is not PD
     const Hi add = sqrt(d) * (Hi)dispersion;              // det^(1/4) * dispersion
 #pragma unroll
     for (int i = 0; i < 10; ++i) a[i] = c10[i];
     a[0] += add; a[4] += add; a[7] += add; a[9] += add;
-    if (chol_packed<4, Hi>(a, L)) {
+    if (chol_packed<4, Hi>(a, L, Dinv)) {
         lr[0] = (float)L[0]; lr[1] = (float)L[4]; lr[2] = (float)L[5]; lr[3] = (float)L[8]; lr[4] = (float)L[9];
         lr[5] = (float)L[10]; lr[6] = (float)L[12]; lr[7] = (float)L[13]; lr[8] = (float)L[14]; lr[9] = (float)L[15];
     } else {

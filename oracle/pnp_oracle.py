@@ -107,9 +107,11 @@ def evaluate(x3d, x2d, w2d, pose, cam: Camera, delta, want_jac=False, clip_jac=T
     dof = 4 if pose.shape[-1] == 4 else 6
     K = cam.cam_mats
     R = pose_rotmat(pose)                                   # (*, B, 3, 3)
-    x_rot = x3d @ R.transpose(-1, -2)                       # (*, B, N, 3)
-    x_cam = x_rot + pose[..., None, :3]
-    xh = x_cam @ K.transpose(-1, -2)
+    if want_jac:                                            # camera.py:10-18 (rotate, translate, then K)
+        x_rot = x3d @ R.transpose(-1, -2)                   # (*, B, N, 3)
+        xh = (x_rot + pose[..., None, :3]) @ K.transpose(-1, -2)
+    else:                                                   # camera.py:21-30 (K R and K t folded once per pose)
+        xh = x3d @ (K @ R).transpose(-1, -2) + (K @ pose[..., :3, None]).squeeze(-1).unsqueeze(-2)
     z = xh[..., 2:3].clamp(min=cam.z_min)
     u = xh[..., :2] / z
     lb, ub = _bound(cam.lb, u), _bound(cam.ub, u)

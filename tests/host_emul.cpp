@@ -5,6 +5,7 @@
 // library: the library has no CPU fallback.  The loops here mirror pnp_kernels.cu's control flow with
 // the parallel reductions replaced by plain sums.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
