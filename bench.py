@@ -246,8 +246,13 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on stdout at communicator creation; keep stdout = the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     Bg = args.batch
     B_total = Bg * world
@@ -280,6 +285,10 @@ def main():
     for i in range(args.warmup):
         step(i)
     fence()
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

@@ -4,7 +4,8 @@
 //   * persistent grid: one 128-thread CTA works on one object at a time and strides over the batch;
 //   * the object's correspondence set {x3d, x2d, w2d} is pulled from HBM exactly once by TMA bulk
 //     copies (cp.async.bulk -> mbarrier complete_tx) into a 2-slot staging ring, re-packed into a
-//     32-byte-per-point record in shared memory, and every later pass (K+1 LM evaluations, I AMIS
+//     64-byte record per PAIR of points {X0 X1 Y0 Y1 | Z0 Z1 -u0 -u1 | -v0 -v1 wu0 wu1 | wv0 wv1 . .}
+//     in shared memory (operands of the packed fp32x2 FFMA2 the AMIS sweep runs on), and every later pass (K+1 LM evaluations, I AMIS
 //     cost sweeps over S samples) reads shared memory only; the next object's chunks are already in
 //     flight while the current object is being solved;
 //   * LM: threads stride over points, 28 partial sums (21 J^T J + 6 J^T r + cost) are reduced with
@@ -105,13 +106,32 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int M, int I, bool amis) {
     SmemPlan s;
     int off = (int)((sizeof(SmemHead<DOF>) + 127) / 128 * 128 / 4);
     s.stage = off; off += 2 * STAGE_FLOATS;
-    s.pts = off; off += 8 * ((N + 3) / 4 * 4);
+    s.pts = off; off += 16 * ((N + 1) / 2);        // 64 B per pair of points
     s.smp = off; if (amis) off += Dim<DOF>::POSE * M;
     s.cost = off; if (amis) off += M;
     s.logp = off; if (amis) off += I * M;
     s.lw = off; if (amis) off += M;
     s.total_bytes = off * 4;
     return s;
+}
+
+// Packed point store.  Pair j = points (2j, 2j+1) occupies 16 floats:
+//   [0..3] X0 X1 Y0 Y1   [4..7] Z0 Z1 -u0 -u1   [8..11] -v0 -v1 wu0 wu1   [12..15] wv0 wv1 0 0
+__device__ __forceinline__ void store_point(float* pts, int n, float X, float Y, float Z, float u, float v, float wu, float wv) {
+    float* p = pts + (n >> 1) * 16 + (n & 1);
+    p[0] = X; p[2] = Y; p[4] = Z; p[6] = -u; p[8] = -v; p[10] = wu; p[12] = wv;
+}
+// odd N: the second half of the last pair is a zero-weight copy of the first (contributes exactly 0)
+__device__ __forceinline__ void pad_last_pair(float* pts, int N) {
+    float* p = pts + (N >> 1) * 16;
+    p[1] = p[0]; p[3] = p[2]; p[5] = p[4]; p[7] = p[6]; p[9] = p[8]; p[11] = 0.f; p[13] = 0.f;
+}
+struct PointRec { float X, Y, Z, u, v, wu, wv; };
+__device__ __forceinline__ PointRec load_point(const float* pts, int n) {
+    const float* p = pts + (n >> 1) * 16 + (n & 1);
+    PointRec r;
+    r.X = p[0]; r.Y = p[2]; r.Z = p[4]; r.u = -p[6]; r.v = -p[8]; r.wu = p[10]; r.wv = p[12];
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -152,7 +172,7 @@ struct Loader {
         }
     }
     // Bring object number `it` of this CTA into the packed point array. Ends with a __syncthreads.
-    __device__ void load_object(int it, int obj, float4* pts4) {
+    __device__ void load_object(int it, int obj, float* pts) {
         const int tid = threadIdx.x;
         if (a.use_tma) {
             for (int k = 0; k < nch; ++k) {
@@ -161,12 +181,11 @@ struct Loader {
                 mbar_wait(bar + (c & 1), (uint32_t)((c >> 1) & 1));
                 const int npts = min(CH, a.N - k * CH);
                 for (int n = tid; n < npts; n += NT) {
-                    const float X = st[3 * n], Y = st[3 * n + 1], Z = st[3 * n + 2];
                     const float2 uv = reinterpret_cast<const float2*>(st + CH * 3)[n];
                     const float2 w = reinterpret_cast<const float2*>(st + CH * 5)[n];
-                    pts4[2 * (k * CH + n)] = make_float4(X, Y, Z, uv.x);
-                    pts4[2 * (k * CH + n) + 1] = make_float4(uv.y, w.x, w.y, 0.f);
+                    store_point(pts, k * CH + n, st[3 * n], st[3 * n + 1], st[3 * n + 2], uv.x, uv.y, w.x, w.y);
                 }
+                if (k == nch - 1 && (a.N & 1) && tid == 0) pad_last_pair(pts, a.N);
                 __syncthreads();            // slot drained (and, after the last chunk, pts complete)
                 if (tid == 0 && c + 2 < total) { fence_proxy_async(); issue(c + 2); }
             }
@@ -174,10 +193,10 @@ struct Loader {
             const float* g3 = a.x3d + (size_t)obj * a.N * 3;
             const float* g2 = a.x2d + (size_t)obj * a.N * 2;
             const float* gw = a.w2d + (size_t)obj * a.N * 2;
-            for (int n = tid; n < a.N; n += NT) {
-                pts4[2 * n] = make_float4(__ldg(g3 + 3 * n), __ldg(g3 + 3 * n + 1), __ldg(g3 + 3 * n + 2), __ldg(g2 + 2 * n));
-                pts4[2 * n + 1] = make_float4(__ldg(g2 + 2 * n + 1), __ldg(gw + 2 * n), __ldg(gw + 2 * n + 1), 0.f);
-            }
+            for (int n = tid; n < a.N; n += NT)
+                store_point(pts, n, __ldg(g3 + 3 * n), __ldg(g3 + 3 * n + 1), __ldg(g3 + 3 * n + 2), __ldg(g2 + 2 * n),
+                            __ldg(g2 + 2 * n + 1), __ldg(gw + 2 * n), __ldg(gw + 2 * n + 1));
+            if ((a.N & 1) && tid == 0) pad_last_pair(pts, a.N);
             __syncthreads();
         }
     }
@@ -246,7 +265,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 
 // Evaluate the normal equations at `pose` (shared memory) over all points; result in ev[0..NV).
 template <int DOF, bool CLIP>
-__device__ void eval_normal_eq(const float4* pts4, int N, const float* pose, const Cam& cam, float delta,
+__device__ void eval_normal_eq(const float* pts, int N, const float* pose, const Cam& cam, float delta,
                                float huber_eps, float* red, float* ev) {
     constexpr int NV = Dim<DOF>::NV;
     float R[9], t[3];
@@ -261,8 +280,8 @@ __device__ void eval_normal_eq(const float4* pts4, int N, const float* pose, con
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
     for (int n = threadIdx.x; n < N; n += NT) {
-        const float4 p0 = pts4[2 * n], p1 = pts4[2 * n + 1];
-        point_normal_eq<DOF, CLIP>(R, t, cam, delta, huber_eps, p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, acc);
+        const PointRec q = load_point(pts, n);
+        point_normal_eq<DOF, CLIP>(R, t, cam, delta, huber_eps, q.X, q.Y, q.Z, q.u, q.v, q.wu, q.wv, acc);
     }
     const float tot = warp_transpose_sum(acc);
     red[(threadIdx.x >> 5) * 32 + (threadIdx.x & 31)] = tot;
@@ -278,7 +297,7 @@ __device__ void eval_normal_eq(const float4* pts4, int N, const float* pose, con
 // LM / GN solve of the object resident in pts4.  Leaves the solution in sh.lm.pose, the covariance
 // in sh.cov (when want_cov) and writes the requested outputs.
 template <int DOF>
-__device__ void lm_phase(const KArgs& a, SmemHead<DOF>& sh, const float4* pts4, const Cam& cam, float delta,
+__device__ void lm_phase(const KArgs& a, SmemHead<DOF>& sh, const float* pts4, const Cam& cam, float delta,
                          int obj, bool want_cov) {
     constexpr int PD = Dim<DOF>::POSE;
     const Params& p = a.p;
@@ -317,17 +336,17 @@ __device__ void lm_phase(const KArgs& a, SmemHead<DOF>& sh, const float4* pts4, 
             __syncthreads();
         }
     }
-    if (tid == 0) {
+    if (tid < PD) a.pose_opt[(size_t)obj * PD + tid] = sh.lm.pose[tid];
+    if (tid == 32 && a.cost) a.cost[obj] = sh.lm.cost;
+    if (want_cov) {
+        if (tid < DOF) {                    // one covariance column per lane (fp64 Cholesky + one solve)
+            float col[DOF];
+            pose_covariance_column<DOF>(sh.lm.a, p.eps, tid, col);
 #pragma unroll
-        for (int i = 0; i < PD; ++i) a.pose_opt[(size_t)obj * PD + i] = sh.lm.pose[i];
-        if (a.cost) a.cost[obj] = sh.lm.cost;
-        if (want_cov) {
-            pose_covariance<DOF>(sh.lm.a, p.eps, sh.cov);
-            if (a.pose_cov) {
-#pragma unroll
-                for (int i = 0; i < DOF * DOF; ++i) a.pose_cov[(size_t)obj * DOF * DOF + i] = sh.cov[i];
-            }
+            for (int i = 0; i < DOF; ++i) sh.cov[i * DOF + tid] = col[i];
         }
+        __syncthreads();
+        if (a.pose_cov && tid < DOF * DOF) a.pose_cov[(size_t)obj * DOF * DOF + tid] = sh.cov[tid];
     }
     if (a.pose_plus) {      // y* (+) one undamped GN step, clip_jac always on (gn_step default)
         eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);
@@ -341,41 +360,74 @@ __device__ void lm_phase(const KArgs& a, SmemHead<DOF>& sh, const float4* pts4, 
     __syncthreads();
 }
 
-// Huber cost of one pose over every resident point (thread-private sweep, points are broadcasts).
+// Huber cost of one pose over every resident point: thread-private sweep, every lane reads the same pair
+// record (shared-memory broadcast, 4 x LDS.128 per 2 points) and evaluates two points per instruction with
+// packed fp32x2 arithmetic (SASS FFMA2 / FMUL2 / FADD2).  P2[k] = (P[k], P[k]) is the pre-multiplied
+// projection K[R|t] duplicated into both halves.  Same arithmetic per half as pnp::point_cost.
+__device__ __forceinline__ float2 splat(float x) { return make_float2(x, x); }
+
+template <bool BOUNDED>
+__device__ __forceinline__ float2 pair_cost(const float2 (&P2)[12], const Cam& cam, float2 d2, float2 nhd2,
+                                            const float4 q0, const float4 q1, const float4 q2, const float4 q3) {
+    const float2 X = make_float2(q0.x, q0.y), Y = make_float2(q0.z, q0.w), Z = make_float2(q1.x, q1.y);
+    const float2 nu = make_float2(q1.z, q1.w), nv = make_float2(q2.x, q2.y);
+    const float2 wu = make_float2(q2.z, q2.w), wv = make_float2(q3.x, q3.y);
+    const float2 xh = __ffma2_rn(P2[0], X, __ffma2_rn(P2[1], Y, __ffma2_rn(P2[2], Z, P2[3])));
+    const float2 yh = __ffma2_rn(P2[4], X, __ffma2_rn(P2[5], Y, __ffma2_rn(P2[6], Z, P2[7])));
+    const float2 zh = __ffma2_rn(P2[8], X, __ffma2_rn(P2[9], Y, __ffma2_rn(P2[10], Z, P2[11])));
+    const float2 iz = make_float2(FastRcp()(fmaxf(zh.x, cam.z_min)), FastRcp()(fmaxf(zh.y, cam.z_min)));
+    float2 tx, ty;
+    if (BOUNDED) {
+        float2 px = __fmul2_rn(xh, iz), py = __fmul2_rn(yh, iz);
+        px.x = fminf(fmaxf(px.x, cam.lbx), cam.ubx); px.y = fminf(fmaxf(px.y, cam.lbx), cam.ubx);
+        py.x = fminf(fmaxf(py.x, cam.lby), cam.uby); py.y = fminf(fmaxf(py.y, cam.lby), cam.uby);
+        tx = __fadd2_rn(px, nu); ty = __fadd2_rn(py, nv);
+    } else {
+        tx = __ffma2_rn(xh, iz, nu); ty = __ffma2_rn(yh, iz, nv);
+    }
+    const float2 rx = __fmul2_rn(tx, wu), ry = __fmul2_rn(ty, wv);
+    const float2 s2 = __ffma2_rn(rx, rx, __fmul2_rn(ry, ry));
+    const float2 s = make_float2(FastSqrt()(s2.x), FastSqrt()(s2.y));
+    const float2 inl = __fmul2_rn(s2, splat(0.5f));
+    const float2 outl = __ffma2_rn(s, d2, nhd2);
+    return make_float2(s.x <= d2.x ? inl.x : outl.x, s.y <= d2.x ? inl.y : outl.y);
+}
+
 template <bool BOUNDED>
 __device__ __forceinline__ float sweep_cost(const float4* pts4, int N, const float* P, const Cam& cam, float delta) {
-    const float half_d2 = 0.5f * delta * delta;
-    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-    int n = 0;
-    for (; n + 4 <= N; n += 4) {
-        const float4 a0 = pts4[2 * n], b0 = pts4[2 * n + 1];
-        const float4 a1 = pts4[2 * n + 2], b1 = pts4[2 * n + 3];
-        const float4 a2 = pts4[2 * n + 4], b2 = pts4[2 * n + 5];
-        const float4 a3 = pts4[2 * n + 6], b3 = pts4[2 * n + 7];
-        c0 += point_cost<BOUNDED>(P, cam, delta, half_d2, a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, FastRcp(), FastSqrt());
-        c1 += point_cost<BOUNDED>(P, cam, delta, half_d2, a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, FastRcp(), FastSqrt());
-        c2 += point_cost<BOUNDED>(P, cam, delta, half_d2, a2.x, a2.y, a2.z, a2.w, b2.x, b2.y, b2.z, FastRcp(), FastSqrt());
-        c3 += point_cost<BOUNDED>(P, cam, delta, half_d2, a3.x, a3.y, a3.z, a3.w, b3.x, b3.y, b3.z, FastRcp(), FastSqrt());
+    float2 P2[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) P2[k] = splat(P[k]);
+    const float2 d2 = splat(delta), nhd2 = splat(-0.5f * delta * delta);
+    float2 c0 = splat(0.f), c1 = splat(0.f);
+    const int npair = (N + 1) >> 1;
+    int j = 0;
+    for (; j + 2 <= npair; j += 2) {
+        const float4 a0 = pts4[4 * j], a1 = pts4[4 * j + 1], a2 = pts4[4 * j + 2], a3 = pts4[4 * j + 3];
+        const float4 b0 = pts4[4 * j + 4], b1 = pts4[4 * j + 5], b2 = pts4[4 * j + 6], b3 = pts4[4 * j + 7];
+        c0 = __fadd2_rn(c0, pair_cost<BOUNDED>(P2, cam, d2, nhd2, a0, a1, a2, a3));
+        c1 = __fadd2_rn(c1, pair_cost<BOUNDED>(P2, cam, d2, nhd2, b0, b1, b2, b3));
     }
-    for (; n < N; ++n) {
-        const float4 a0 = pts4[2 * n], b0 = pts4[2 * n + 1];
-        c0 += point_cost<BOUNDED>(P, cam, delta, half_d2, a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, b0.z, FastRcp(), FastSqrt());
+    if (j < npair) {
+        const float4 a0 = pts4[4 * j], a1 = pts4[4 * j + 1], a2 = pts4[4 * j + 2], a3 = pts4[4 * j + 3];
+        c0 = __fadd2_rn(c0, pair_cost<BOUNDED>(P2, cam, d2, nhd2, a0, a1, a2, a3));
     }
-    return (c0 + c1) + (c2 + c3);
+    return (c0.x + c0.y) + (c1.x + c1.y);
 }
 
 template <int DOF>
-__device__ __forceinline__ float pose_cost(const float4* pts4, int N, const float* pose, const Cam& cam, float delta) {
+__device__ __forceinline__ float pose_cost(const float* pts, int N, const float* pose, const Cam& cam, float delta) {
     float R[9], P[12];
     pose_to_rot<DOF>(pose, R);
     make_proj(cam.k, R, pose, P);
+    const float4* pts4 = reinterpret_cast<const float4*>(pts);
     return cam.bounded ? sweep_cost<true>(pts4, N, P, cam, delta) : sweep_cost<false>(pts4, N, P, cam, delta);
 }
 
 // ------------------------------------------------------------------------------------------------
 // AMIS loop for the resident object (6DoF).  sh.prop[0] must not be set yet; pose / cov are read from
 // pose_opt[7] / cov[36] (shared or registers of thread 0 -- passed as shared pointers).
-__device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float4* pts4, float* smp, float* cst,
+__device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, float* smp, float* cst,
                             float* logp, float* lw, const Cam& cam, float delta, int obj,
                             const float* pose_opt, const float* cov) {
     const Params& p = a.p;
@@ -526,7 +578,7 @@ __global__ void __launch_bounds__(NT, 4) solve_kernel(const KArgs a) {
     SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
     float* dyn = reinterpret_cast<float*>(smem_raw);
     const SmemPlan pl = plan_smem<DOF>(a.N, a.p.mc_samples, a.p.mc_iter, DO_AMIS);
-    float4* pts4 = reinterpret_cast<float4*>(dyn + pl.pts);
+    float* pts4 = dyn + pl.pts;
 
     Loader ld(a, sh.bar, dyn + pl.stage);
     ld.prologue();
@@ -557,7 +609,7 @@ __global__ void __launch_bounds__(NT, 4) cost_kernel(const KArgs a) {
     SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
     float* dyn = reinterpret_cast<float*>(smem_raw);
     const SmemPlan pl = plan_smem<DOF>(a.N, 0, 0, false);
-    float4* pts4 = reinterpret_cast<float4*>(dyn + pl.pts);
+    float* pts4 = dyn + pl.pts;
     constexpr int PD = Dim<DOF>::POSE;
     Loader ld(a, sh.bar, dyn + pl.stage);
     ld.prologue();

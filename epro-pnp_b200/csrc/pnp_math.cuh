@@ -470,17 +470,28 @@ template <int DOF> PNP_HD void gn_advance(const float* pose, const float* acc, f
     pose_add<DOF>(pose, step, pose_out);
 }
 
-// pose covariance = (J^T J + eps I)^-1  (:170-179)
-template <int DOF> PNP_HD_COLD void pose_covariance(const float* a_packed, float eps, float* cov_full) {
+// pose covariance = (J^T J + eps I)^-1  (:170-179), one COLUMN per caller: the kernel spreads the DOF
+// columns over DOF lanes (each repeats the cheap Cholesky and does one pair of substitutions) instead of
+// inverting on a single thread.  fp64.
+template <int DOF> PNP_HD void pose_covariance_column(const float* a_packed, float eps, int col, float* out) {
     constexpr int NA = Dim<DOF>::NA;
-    Hi al[NA], inv[DOF * DOF];
+    Hi al[NA], L[DOF * DOF], Dinv[DOF], e[DOF], x[DOF];
 #pragma unroll
     for (int i = 0; i < NA; ++i) al[i] = (Hi)a_packed[i];
 #pragma unroll
-    for (int i = 0; i < DOF; ++i) al[tri(i, i, DOF)] += (Hi)eps;
-    spd_inverse<DOF, Hi>(al, inv);
+    for (int i = 0; i < DOF; ++i) { al[tri(i, i, DOF)] += (Hi)eps; e[i] = (i == col) ? Hi(1) : Hi(0); }
+    chol_packed<DOF, Hi>(al, L, Dinv);
+    chol_solve<DOF, Hi>(L, Dinv, e, x);
 #pragma unroll
-    for (int i = 0; i < DOF * DOF; ++i) cov_full[i] = (float)inv[i];
+    for (int i = 0; i < DOF; ++i) out[i] = (float)x[i];
+}
+
+template <int DOF> PNP_HD void pose_covariance(const float* a_packed, float eps, float* cov_full) {
+    float c[DOF];
+    for (int j = 0; j < DOF; ++j) {
+        pose_covariance_column<DOF>(a_packed, eps, j, c);
+        for (int i = 0; i < DOF; ++i) cov_full[i * DOF + j] = c[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -530,39 +541,51 @@ PNP_HD void acg_dispersed_chol(const Hi* c10, float dispersion, float* lr) {
     }
 }
 
-// First proposal from the LM solution and its covariance (EProPnP6DoF.initial_fit, epropnp.py:288-302)
+// First proposal from the LM solution and its covariance (EProPnP6DoF.initial_fit, epropnp.py:288-302).
+// The reference forms (T S^-1 T^T + I_4)^-1 with S = cov[3:,3:] and T = T(q) the 4x3 tangent map.  For a
+// unit quaternion [T | q] is orthogonal (columns of T are orthonormal and orthogonal to q), hence
+//     (T S^-1 T^T + I)^-1 = T (S^-1 + I)^-1 T^T + q q^T = T [S (I + S)^-1] T^T + q q^T
+// which needs one WELL-conditioned 3x3 SPD solve instead of two ill-conditioned inverses, and
+// det of that matrix = det(S (I+S)^-1).  Same quantity, evaluated stably; fp64.
 PNP_HD_COLD void initial_fit6(const float* pose, const float* cov /*6x6 full*/, float dispersion, Proposal6& p) {
     p.mu[0] = pose[0]; p.mu[1] = pose[1]; p.mu[2] = pose[2];
     const Hi ctt[6] = {(Hi)cov[0], (Hi)cov[1], (Hi)cov[2], (Hi)cov[7], (Hi)cov[8], (Hi)cov[14]};
     chol3_or_identity(ctt, p.lt);
-    // information of the rotation block, lifted to R^4 through the tangent map T(q)
-    const Hi crr[6] = {(Hi)cov[21], (Hi)cov[22], (Hi)cov[23], (Hi)cov[28], (Hi)cov[29], (Hi)cov[35]};
-    Hi info[9];
-    spd_inverse<3, Hi>(crr, info);
+    const Hi S[9] = {(Hi)cov[21], (Hi)cov[22], (Hi)cov[23], (Hi)cov[22], (Hi)cov[28], (Hi)cov[29],
+                     (Hi)cov[23], (Hi)cov[29], (Hi)cov[35]};
+    const Hi ips[6] = {S[0] + 1.0, S[1], S[2], S[4] + 1.0, S[5], S[8] + 1.0};        // I + S (packed upper)
+    Hi L[9], Dinv[3], C[9];
+    chol_packed<3, Hi>(ips, L, Dinv);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {              // C[:, c] = (I + S)^-1 S[:, c]   (C = S (I+S)^-1 is symmetric)
+        const Hi b[3] = {S[c], S[3 + c], S[6 + c]};
+        Hi x[3];
+        chol_solve<3, Hi>(L, Dinv, b, x);
+        C[c] = x[0]; C[3 + c] = x[1]; C[6 + c] = x[2];
+    }
     const Hi w = pose[3], x = pose[4], y = pose[5], z = pose[6];
     const Hi T[12] = {x, y, z, -w, -z, y, z, -w, -x, -y, x, -w};    // 4x3
-    Hi TI[12];
+    const Hi q[4] = {w, x, y, z};
+    Hi TC[12];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-            TI[i * 3 + j] = T[i * 3 + 0] * info[0 + j] + T[i * 3 + 1] * info[3 + j] + T[i * 3 + 2] * info[6 + j];
-    Hi m[10];
+            TC[i * 3 + j] = T[i * 3 + 0] * C[0 + j] + T[i * 3 + 1] * C[3 + j] + T[i * 3 + 2] * C[6 + j];
+    Hi rc[10], tr = 0;
     int idx = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = i; j < 4; ++j) {
-            m[idx] = TI[i * 3 + 0] * T[j * 3 + 0] + TI[i * 3 + 1] * T[j * 3 + 1] + TI[i * 3 + 2] * T[j * 3 + 2]
-                     + ((i == j) ? 1.0 : 0.0);
+            rc[idx] = TC[i * 3 + 0] * T[j * 3 + 0] + TC[i * 3 + 1] * T[j * 3 + 1] + TC[i * 3 + 2] * T[j * 3 + 2] + q[i] * q[j];
+            if (i == j) tr += rc[idx];
             ++idx;
         }
-    Hi rc[16];
-    spd_inverse<4, Hi>(m, rc);
-    const Hi tr = rc[0] + rc[5] + rc[10] + rc[15];
-    const Hi c10[10] = {rc[0] / tr, rc[1] / tr, rc[2] / tr, rc[3] / tr, rc[5] / tr, rc[6] / tr, rc[7] / tr,
-                        rc[10] / tr, rc[11] / tr, rc[15] / tr};
-    acg_dispersed_chol(c10, dispersion, p.lr);
+    const Hi itr = 1.0 / tr;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) rc[i] *= itr;
+    acg_dispersed_chol(rc, dispersion, p.lr);
     proposal_finish(p);
 }
 
