@@ -399,19 +399,21 @@ __device__ __forceinline__ float sweep_cost(const float4* pts4, int N, const flo
 #pragma unroll
     for (int k = 0; k < 12; ++k) P2[k] = splat(P[k]);
     const float2 d2 = splat(delta), nhd2 = splat(-0.5f * delta * delta);
-    float2 c0 = splat(0.f), c1 = splat(0.f);
+    float2 c0 = splat(0.f), c1 = splat(0.f), c2 = splat(0.f), c3 = splat(0.f);
     const int npair = (N + 1) >> 1;
     int j = 0;
-    for (; j + 2 <= npair; j += 2) {
-        const float4 a0 = pts4[4 * j], a1 = pts4[4 * j + 1], a2 = pts4[4 * j + 2], a3 = pts4[4 * j + 3];
-        const float4 b0 = pts4[4 * j + 4], b1 = pts4[4 * j + 5], b2 = pts4[4 * j + 6], b3 = pts4[4 * j + 7];
-        c0 = __fadd2_rn(c0, pair_cost<BOUNDED>(P2, cam, d2, nhd2, a0, a1, a2, a3));
-        c1 = __fadd2_rn(c1, pair_cost<BOUNDED>(P2, cam, d2, nhd2, b0, b1, b2, b3));
+    for (; j + 4 <= npair; j += 4) {            // 8 points in flight per thread
+        const float4* q = pts4 + 4 * j;
+        c0 = __fadd2_rn(c0, pair_cost<BOUNDED>(P2, cam, d2, nhd2, q[0], q[1], q[2], q[3]));
+        c1 = __fadd2_rn(c1, pair_cost<BOUNDED>(P2, cam, d2, nhd2, q[4], q[5], q[6], q[7]));
+        c2 = __fadd2_rn(c2, pair_cost<BOUNDED>(P2, cam, d2, nhd2, q[8], q[9], q[10], q[11]));
+        c3 = __fadd2_rn(c3, pair_cost<BOUNDED>(P2, cam, d2, nhd2, q[12], q[13], q[14], q[15]));
     }
-    if (j < npair) {
-        const float4 a0 = pts4[4 * j], a1 = pts4[4 * j + 1], a2 = pts4[4 * j + 2], a3 = pts4[4 * j + 3];
-        c0 = __fadd2_rn(c0, pair_cost<BOUNDED>(P2, cam, d2, nhd2, a0, a1, a2, a3));
+    for (; j < npair; ++j) {
+        const float4* q = pts4 + 4 * j;
+        c0 = __fadd2_rn(c0, pair_cost<BOUNDED>(P2, cam, d2, nhd2, q[0], q[1], q[2], q[3]));
     }
+    c0 = __fadd2_rn(c0, c2); c1 = __fadd2_rn(c1, c3);
     return (c0.x + c0.y) + (c1.x + c1.y);
 }
 

@@ -516,23 +516,23 @@ PNP_HD void proposal_finish(Proposal6& p) {
 
 // chol of a symmetric 3x3 given by its packed upper triangle, with the reference's fallback:
 // not PD -> identity (cholesky_wrapper, epropnp.py:16-33; default_diag is None on the 6DoF path)
-PNP_HD void chol3_or_identity(const Hi* a6, float* l) {
-    Hi L[9], Dinv[3];
-    if (chol_packed<3, Hi>(a6, L, Dinv)) {
+template <class T> PNP_HD void chol3_or_identity(const T* a6, float* l) {
+    T L[9], Dinv[3];
+    if (chol_packed<3, T>(a6, L, Dinv)) {
         l[0] = (float)L[0]; l[1] = (float)L[3]; l[2] = (float)L[4]; l[3] = (float)L[6]; l[4] = (float)L[7]; l[5] = (float)L[8];
     } else { l[0] = 1.f; l[1] = 0.f; l[2] = 1.f; l[3] = 0.f; l[4] = 0.f; l[5] = 1.f; }
 }
 
 // L_r = chol(C + det(C)^(1/4) * dispersion * I), identity when not PD  (epropnp.py:301-302, 341-342)
-PNP_HD void acg_dispersed_chol(const Hi* c10, float dispersion, float* lr) {
-    Hi L[16], a[10], Dinv[4];
-    chol_packed<4, Hi>(c10, L, Dinv);
-    const Hi d = L[0] * L[5] * L[10] * L[15];            // sqrt(det C); NaN if C is not PD
-    const Hi add = sqrt(d) * (Hi)dispersion;              // det^(1/4) * dispersion
+template <class T> PNP_HD void acg_dispersed_chol(const T* c10, float dispersion, float* lr) {
+    T L[16], a[10], Dinv[4];
+    chol_packed<4, T>(c10, L, Dinv);
+    const T d = L[0] * L[5] * L[10] * L[15];              // sqrt(det C); NaN if C is not PD
+    const T add = sqrt(d) * (T)dispersion;                // det^(1/4) * dispersion
 #pragma unroll
     for (int i = 0; i < 10; ++i) a[i] = c10[i];
     a[0] += add; a[4] += add; a[7] += add; a[9] += add;
-    if (chol_packed<4, Hi>(a, L, Dinv)) {
+    if (chol_packed<4, T>(a, L, Dinv)) {
         lr[0] = (float)L[0]; lr[1] = (float)L[4]; lr[2] = (float)L[5]; lr[3] = (float)L[8]; lr[4] = (float)L[9];
         lr[5] = (float)L[10]; lr[6] = (float)L[12]; lr[7] = (float)L[13]; lr[8] = (float)L[14]; lr[9] = (float)L[15];
     } else {
@@ -550,7 +550,7 @@ PNP_HD void acg_dispersed_chol(const Hi* c10, float dispersion, float* lr) {
 PNP_HD_COLD void initial_fit6(const float* pose, const float* cov /*6x6 full*/, float dispersion, Proposal6& p) {
     p.mu[0] = pose[0]; p.mu[1] = pose[1]; p.mu[2] = pose[2];
     const Hi ctt[6] = {(Hi)cov[0], (Hi)cov[1], (Hi)cov[2], (Hi)cov[7], (Hi)cov[8], (Hi)cov[14]};
-    chol3_or_identity(ctt, p.lt);
+    chol3_or_identity<Hi>(ctt, p.lt);
     const Hi S[9] = {(Hi)cov[21], (Hi)cov[22], (Hi)cov[23], (Hi)cov[22], (Hi)cov[28], (Hi)cov[29],
                      (Hi)cov[23], (Hi)cov[29], (Hi)cov[35]};
     const Hi ips[6] = {S[0] + 1.0, S[1], S[2], S[4] + 1.0, S[5], S[8] + 1.0};        // I + S (packed upper)
@@ -585,30 +585,39 @@ PNP_HD_COLD void initial_fit6(const float* pose, const float* cov /*6x6 full*/, 
     const Hi itr = 1.0 / tr;
 #pragma unroll
     for (int i = 0; i < 10; ++i) rc[i] *= itr;
-    acg_dispersed_chol(rc, dispersion, p.lr);
+    acg_dispersed_chol<Hi>(rc, dispersion, p.lr);
     proposal_finish(p);
 }
 
+// The refits in the middle of the AMIS loop work from statistics that were accumulated in fp32 over
+// softmax weights carrying ~1e-4 of cost noise, exactly like the reference's fp32
+// tensors.  Measured on the golden cases: the thread-0 factorization that closes a refit (`Refit`, on
+// the serial critical path between two AMIS iterations) is as accurate in fp32 as in fp64, so it is a
+// short MUFU.RSQ chain; the scatter-matrix inverse inside the ACG fixed point (`RefitInv`, evaluated by
+// all threads in parallel, not serial-critical) does lose accuracy in fp32 and stays fp64.
+typedef float Refit;
+typedef double RefitInv;
+
 // Lambda^-1 (fp32 out) of the ACG scatter matrix given as packed fp32 upper triangle
-PNP_HD_COLD void acg_scatter_inverse(const float* lam10, float* inv16) {
-    Hi a[10], inv[16];
+PNP_HD void acg_scatter_inverse(const float* lam10, float* inv16) {
+    RefitInv a[10], inv[16];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) a[i] = (Hi)lam10[i];
-    spd_inverse<4, Hi>(a, inv);
+    for (int i = 0; i < 10; ++i) a[i] = (RefitInv)lam10[i];
+    spd_inverse<4, RefitInv>(a, inv);
 #pragma unroll
     for (int i = 0; i < 16; ++i) inv16[i] = (float)inv[i];
 }
 
 // Next proposal from the refit statistics (EProPnP6DoF.estimate_params tail, epropnp.py:325, 341-342)
-PNP_HD_COLD void refit_finish6(const float* mean, const float* tc6, const float* lam10, float dispersion, Proposal6& np) {
+PNP_HD void refit_finish6(const float* mean, const float* tc6, const float* lam10, float dispersion, Proposal6& np) {
     np.mu[0] = mean[0]; np.mu[1] = mean[1]; np.mu[2] = mean[2];
-    Hi a6[6], c10[10];
+    Refit a6[6], c10[10];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) a6[i] = (Hi)tc6[i];
+    for (int i = 0; i < 6; ++i) a6[i] = (Refit)tc6[i];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) c10[i] = (Hi)lam10[i];
-    chol3_or_identity(a6, np.lt);
-    acg_dispersed_chol(c10, dispersion, np.lr);
+    for (int i = 0; i < 10; ++i) c10[i] = (Refit)lam10[i];
+    chol3_or_identity<Refit>(a6, np.lt);
+    acg_dispersed_chol<Refit>(c10, dispersion, np.lr);
     proposal_finish(np);
 }
 
