@@ -34,6 +34,25 @@ constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 thread_local int g_last_cuda_error = 0;
 
+// Phase timers (profiling build: -DEPNP_PHASE_TIMERS; tools/phase_profile.py).  Thread 0 of every CTA adds
+// the clock64() cycles it spent in each phase; the production build compiles them away.
+enum Phase { PH_LOAD = 0, PH_LM_EVAL, PH_LM_SERIAL, PH_COV, PH_INIT_FIT, PH_DRAW_SWEEP, PH_LOGP_OLD, PH_WEIGHTS,
+             PH_REFIT_SUMS, PH_REFIT_FINISH, PH_OUTPUT, PH_COUNT };
+#ifdef EPNP_PHASE_TIMERS
+#define PH_DECL long long ph_t = clock64()
+#define PH_MARK(a_, which)                                                                     \
+    do {                                                                                       \
+        if ((int)threadIdx.x == serial_thread(a_) && (a_).prof) {                                                \
+            const long long now_ = clock64();                                                  \
+            atomicAdd((a_).prof + (which), (unsigned long long)(now_ - ph_t));                 \
+            ph_t = now_;                                                                       \
+        }                                                                                      \
+    } while (0)
+#else
+#define PH_DECL
+#define PH_MARK(a_, which)
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier + 1-D TMA bulk copy
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,16 +100,17 @@ struct KArgs {
     float *pose_opt, *pose_cov, *cost, *pose_plus, *cost_init;
     float *pose_samples, *logw, *proposals;
     float *cost_out;                        // cost-only entry: (S, B)
-    int B, N, S_eval, use_tma;
+    int B, N, S_eval, use_tma, num_sms;
     uint32_t obj_offset;
     uint64_t seed;
+    unsigned long long* prof;               // phase timers (profiling build only), else unused
     Params p;
 };
 
 // Static part of the shared-memory image (the dynamic arrays follow it).
 template <int DOF> struct SmemHead {
     uint64_t bar[2];
-    float red[NW * 32];
+    float red[2 * NW * 32];                 // two halves: consecutive reductions alternate, one barrier each
     float ev[32];                           // reduced evaluation: NV floats
     LMState<DOF> lm;
     float cov[DOF * DOF];
@@ -217,6 +237,14 @@ __device__ __forceinline__ Cam load_cam(const KArgs& a, int obj) {
     return c;
 }
 
+// The once-per-iteration serial work of a CTA (LM step solve, refit finish, first proposal) runs on lane 0
+// of ONE warp.  Co-resident CTAs of an SM are typically blockIdx, blockIdx + #SM, ...; rotating the serial
+// warp with blockIdx / #SM puts their serial chains on different SM sub-partitions (warp w -> SMSP w % 4)
+// instead of all of them competing for the scheduler of warp 0.
+__device__ __forceinline__ int serial_thread(const KArgs& a) {
+    return 32 * (int)((blockIdx.x / (unsigned)max(a.num_sms, 1)) & (NW - 1));
+}
+
 // ------------------------------------------------------------------------------------------------
 // Reductions
 // 32 values per lane -> lane j holds the warp total of v[j]   (31 shuffles)
@@ -235,8 +263,12 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32]) {
     return v[0];
 }
 
-template <int K> __device__ __forceinline__ void block_sum(float (&v)[K], float* red) {
+// Block-wide sums of K values per thread; every thread gets the totals.  `red` holds two halves of
+// NW*32 floats: call sites alternate `half` so one __syncthreads per reduction is enough (a thread can be
+// at most one reduction ahead of the slowest reader, and then it writes the other half).
+template <int K> __device__ __forceinline__ void block_sum(float (&v)[K], float* red, int half) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* r = red + half * (NW * 32);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
@@ -244,23 +276,21 @@ template <int K> __device__ __forceinline__ void block_sum(float (&v)[K], float*
     }
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) red[warp * 32 + k] = v[k];
+        for (int k = 0; k < K; ++k) r[warp * 32 + k] = v[k];
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = (red[k] + red[32 + k]) + (red[64 + k] + red[96 + k]);
-    __syncthreads();
+    for (int k = 0; k < K; ++k) v[k] = (r[k] + r[32 + k]) + (r[64 + k] + r[96 + k]);
 }
 
-__device__ __forceinline__ float block_max(float v, float* red) {
+__device__ __forceinline__ float block_max(float v, float* red, int half) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* r = red + half * (NW * 32);
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (lane == 0) red[warp * 32] = v;
+    if (lane == 0) r[warp * 32] = v;
     __syncthreads();
-    v = fmaxf(fmaxf(red[0], red[32]), fmaxf(red[64], red[96]));
-    __syncthreads();
-    return v;
+    return fmaxf(fmaxf(r[0], r[32]), fmaxf(r[64], r[96]));
 }
 
 // Evaluate the normal equations at `pose` (shared memory) over all points; result in ev[0..NV).
@@ -302,7 +332,9 @@ __device__ void lm_phase(const KArgs& a, SmemHead<DOF>& sh, const float* pts4, c
     constexpr int PD = Dim<DOF>::POSE;
     const Params& p = a.p;
     const int tid = threadIdx.x;
-    if (tid == 0) {
+    const int st = serial_thread(a);
+    PH_DECL;
+    if (tid == st) {
 #pragma unroll
         for (int i = 0; i < PD; ++i) sh.lm.pose[i] = __ldg(a.pose_init + (size_t)obj * PD + i);
         sh.lm.radius = p.initial_radius;
@@ -311,24 +343,28 @@ __device__ void lm_phase(const KArgs& a, SmemHead<DOF>& sh, const float* pts4, c
     __syncthreads();
     if (!p.fast_mode) {
         eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);
-        if (tid == 0) {
+        PH_MARK(a, PH_LM_EVAL);
+        if (tid == st) {
             lm_adopt<DOF>(sh.lm, sh.ev);
             if (a.cost_init) a.cost_init[obj] = sh.lm.cost;
             if (p.lm_iter > 0) lm_propose<DOF>(sh.lm, p);
         }
+        PH_MARK(a, PH_LM_SERIAL);
         __syncthreads();
         for (int it = 0; it < p.lm_iter; ++it) {
             eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose_new, cam, delta, p.huber_eps, sh.red, sh.ev);
-            if (tid == 0) {
+            PH_MARK(a, PH_LM_EVAL);
+            if (tid == st) {
                 lm_update<DOF>(sh.lm, sh.ev, p);
                 if (it + 1 < p.lm_iter) lm_propose<DOF>(sh.lm, p);
             }
+            PH_MARK(a, PH_LM_SERIAL);
             __syncthreads();
         }
     } else {
         for (int it = 0; it < p.lm_iter; ++it) {
             eval_normal_eq<DOF, false>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);
-            if (tid == 0) {
+            if (tid == st) {
                 lm_adopt<DOF>(sh.lm, sh.ev);                 // kept for covariance / cost (pre-step)
                 if (it == 0 && a.cost_init) a.cost_init[obj] = sh.lm.cost;
                 gn_advance<DOF>(sh.lm.pose, sh.ev, p.eps, sh.lm.pose);
@@ -348,9 +384,10 @@ __device__ void lm_phase(const KArgs& a, SmemHead<DOF>& sh, const float* pts4, c
         __syncthreads();
         if (a.pose_cov && tid < DOF * DOF) a.pose_cov[(size_t)obj * DOF * DOF + tid] = sh.cov[tid];
     }
+    PH_MARK(a, PH_COV);
     if (a.pose_plus) {      // y* (+) one undamped GN step, clip_jac always on (gn_step default)
         eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);
-        if (tid == 0) {
+        if (tid == st) {
             float plus[PD];
             gn_advance<DOF>(sh.lm.pose, sh.ev, p.eps, plus);
 #pragma unroll
@@ -436,8 +473,11 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
     const int tid = threadIdx.x;
     const int M = p.mc_samples, I = p.mc_iter, S = M / I;
     const bool injected = a.noise_n3 != nullptr;
+    const int st = serial_thread(a);
+    PH_DECL;
 
-    if (tid == 0) initial_fit6(pose_opt, cov, p.acg_dispersion, sh.prop[0]);
+    if (tid == st) initial_fit6(pose_opt, cov, p.acg_dispersion, sh.prop[0]);
+    PH_MARK(a, PH_INIT_FIT);
     __syncthreads();
 
     for (int i = 0; i < I; ++i) {
@@ -464,6 +504,7 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
             cst[m] = pose_cost<6>(pts4, a.N, q, cam, delta);
             for (int j = 0; j <= i; ++j) logp[j * M + m] = proposal_logpdf6(sh.prop[j], q);
         }
+        PH_MARK(a, PH_DRAW_SWEEP);
         // ---- the new proposal on all earlier samples
         for (int m = tid; m < i * S; m += NT) {
             float q[7];
@@ -472,6 +513,7 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
             logp[i * M + m] = proposal_logpdf6(sh.prop[i], q);
         }
         __syncthreads();
+        PH_MARK(a, PH_LOGP_OLD);
         // ---- mixture density and log-weights of all samples so far
         const int n = (i + 1) * S;
         const float log_cnt = logf((float)(i + 1));
@@ -485,79 +527,118 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
             lw[m] = v;
             mx = fmaxf(mx, v);
         }
+        PH_MARK(a, PH_WEIGHTS);
         if (i == I - 1) {
             for (int m = tid; m < M; m += NT) a.logw[(size_t)obj * M + m] = lw[m];
+            PH_MARK(a, PH_OUTPUT);
             break;
         }
-        // ---- refit proposal i+1 to the weighted samples (estimate_params)
-        mx = block_max(mx, sh.red);
-        float v1[1] = {0.f};
-        for (int m = tid; m < n; m += NT) { const float e = expf(lw[m] - mx); lw[m] = e; v1[0] += e; }
-        block_sum<1>(v1, sh.red);
-        const float inv_sum = 1.0f / v1[0];
-        float mean[3] = {0.f, 0.f, 0.f};
-        for (int m = tid; m < n; m += NT) {
-            const float w = lw[m] * inv_sum;
-            lw[m] = w;                                   // normalised softmax weight
-            mean[0] = fmaf(w, smp[m * 7], mean[0]); mean[1] = fmaf(w, smp[m * 7 + 1], mean[1]); mean[2] = fmaf(w, smp[m * 7 + 2], mean[2]);
-        }
-        block_sum<3>(mean, sh.red);
-        // translation covariance + ACG fixed-point iterations (Lambda_0 = I)
-        float lam_inv[16];
-#pragma unroll
-        for (int r = 0; r < 16; ++r) lam_inv[r] = (r % 5 == 0) ? 1.f : 0.f;
-        float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // ---- refit proposal i+1 to the weighted samples (estimate_params, epropnp.py:317-342).
+        // Four block reductions, one barrier each:
+        //   A  max of the log-weights
+        //   B  e = exp(lw - max): sum e, sum e t, and ACG fixed-point iteration 1 (Lambda_0 = I, so
+        //      M = q.q) -- the normalisation of the weights cancels in Lambda
+        //   C  translation covariance about the mean (+ ACG iteration 2)
+        //   D+ remaining ACG iterations
+        mx = block_max(mx, sh.red, 0);
         float lam10[10];
-        for (int itr = 0; itr < p.acg_mle_iter; ++itr) {
+        float mean[3], inv_sum;
+        {
+            float acc[15];
+#pragma unroll
+            for (int r = 0; r < 15; ++r) acc[r] = 0.f;
+            for (int m = tid; m < n; m += NT) {
+                const float e = expf(lw[m] - mx);
+                lw[m] = e;
+                const float* s7 = smp + m * 7;
+                acc[0] += e;
+                acc[1] = fmaf(e, s7[0], acc[1]); acc[2] = fmaf(e, s7[1], acc[2]); acc[3] = fmaf(e, s7[2], acc[3]);
+                const float* q = s7 + 3;
+                const float mq = fmaxf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3], p.amis_eps);
+                const float wm = e / mq;
+                acc[4] += wm;
+                int idx = 5;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
+            }
+            block_sum<15>(acc, sh.red, 1);
+            inv_sum = 1.0f / acc[0];
+            mean[0] = acc[1] * inv_sum; mean[1] = acc[2] * inv_sum; mean[2] = acc[3] * inv_sum;
+            const float inv0 = 1.0f / acc[4];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) lam10[r] = acc[5 + r] * inv0;
+            lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
+        }
+        if (p.acg_mle_iter == 0) {          // degenerate configuration: Lambda stays the identity
+#pragma unroll
+            for (int r = 0; r < 10; ++r) lam10[r] = 0.f;
+            lam10[0] = lam10[4] = lam10[7] = lam10[9] = 1.f;
+        }
+        float tc[6];
+        {
+            const bool more = p.acg_mle_iter >= 2;
+            float lam_inv[16];
+            if (more) acg_scatter_inverse(lam10, lam_inv);
             float acc[17];
 #pragma unroll
             for (int r = 0; r < 17; ++r) acc[r] = 0.f;
             for (int m = tid; m < n; m += NT) {
-                const float w = lw[m];
+                const float w = lw[m] * inv_sum;                         // normalised softmax weight
+                lw[m] = w;
+                const float* s7 = smp + m * 7;
+                const float d0 = s7[0] - mean[0], d1 = s7[1] - mean[1], d2 = s7[2] - mean[2];
+                acc[11] = fmaf(w * d0, d0, acc[11]); acc[12] = fmaf(w * d0, d1, acc[12]); acc[13] = fmaf(w * d0, d2, acc[13]);
+                acc[14] = fmaf(w * d1, d1, acc[14]); acc[15] = fmaf(w * d1, d2, acc[15]); acc[16] = fmaf(w * d2, d2, acc[16]);
+                if (more) {
+                    const float* q = s7 + 3;
+                    const float wm = w / fmaxf(quad4(lam_inv, q), p.amis_eps);
+                    acc[0] += wm;
+                    int idx = 1;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
+                }
+            }
+            block_sum<17>(acc, sh.red, 0);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) tc[r] = acc[11 + r];
+            if (more) {
+                const float inv0 = 1.0f / acc[0];
+#pragma unroll
+                for (int r = 0; r < 10; ++r) lam10[r] = acc[1 + r] * inv0;
+                lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
+            }
+        }
+        for (int itr = 2; itr < p.acg_mle_iter; ++itr) {
+            float lam_inv[16];
+            acg_scatter_inverse(lam10, lam_inv);
+            float acc[11];
+#pragma unroll
+            for (int r = 0; r < 11; ++r) acc[r] = 0.f;
+            for (int m = tid; m < n; m += NT) {
                 const float* q = smp + m * 7 + 3;
-                const float mq = fmaxf(quad4(lam_inv, q), p.amis_eps);
-                const float wm = w / mq;
+                const float wm = lw[m] / fmaxf(quad4(lam_inv, q), p.amis_eps);
                 acc[0] += wm;
                 int idx = 1;
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
 #pragma unroll
                     for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
-                if (itr == 0) {
-                    const float d0 = smp[m * 7] - mean[0], d1 = smp[m * 7 + 1] - mean[1], d2 = smp[m * 7 + 2] - mean[2];
-                    acc[11] = fmaf(w * d0, d0, acc[11]); acc[12] = fmaf(w * d0, d1, acc[12]); acc[13] = fmaf(w * d0, d2, acc[13]);
-                    acc[14] = fmaf(w * d1, d1, acc[14]); acc[15] = fmaf(w * d1, d2, acc[15]); acc[16] = fmaf(w * d2, d2, acc[16]);
-                }
             }
-            block_sum<17>(acc, sh.red);
-            if (itr == 0) {
-#pragma unroll
-                for (int r = 0; r < 6; ++r) tc[r] = acc[11 + r];
-            }
+            block_sum<11>(acc, sh.red, (itr + 1) & 1);
             const float inv0 = 1.0f / acc[0];
 #pragma unroll
             for (int r = 0; r < 10; ++r) lam10[r] = acc[1 + r] * inv0;
             lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
-            if (itr + 1 < p.acg_mle_iter) acg_scatter_inverse(lam10, lam_inv);
         }
-        if (p.acg_mle_iter == 0) {      // degenerate configuration: Lambda stays the identity
-#pragma unroll
-            for (int r = 0; r < 10; ++r) lam10[r] = 0.f;
-            lam10[0] = lam10[4] = lam10[7] = lam10[9] = 1.f;
-            float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int m = tid; m < n; m += NT) {
-                const float w = lw[m];
-                const float d0 = smp[m * 7] - mean[0], d1 = smp[m * 7 + 1] - mean[1], d2 = smp[m * 7 + 2] - mean[2];
-                acc[0] = fmaf(w * d0, d0, acc[0]); acc[1] = fmaf(w * d0, d1, acc[1]); acc[2] = fmaf(w * d0, d2, acc[2]);
-                acc[3] = fmaf(w * d1, d1, acc[3]); acc[4] = fmaf(w * d1, d2, acc[4]); acc[5] = fmaf(w * d2, d2, acc[5]);
-            }
-            block_sum<6>(acc, sh.red);
-#pragma unroll
-            for (int r = 0; r < 6; ++r) tc[r] = acc[r];
-        }
-        if (tid == 0) {
+        PH_MARK(a, PH_REFIT_SUMS);
+        if (tid == st) {
             refit_finish6(mean, tc, lam10, p.acg_dispersion, sh.prop[i + 1]);
         }
+        PH_MARK(a, PH_REFIT_FINISH);
         __syncthreads();
     }
     if (a.proposals && tid < I) {
@@ -586,9 +667,11 @@ __global__ void __launch_bounds__(NT, 4) solve_kernel(const KArgs a) {
     ld.prologue();
     for (int it = 0; it < ld.n_my; ++it) {
         const int obj = (int)blockIdx.x + it * (int)gridDim.x;
+        PH_DECL;
         ld.load_object(it, obj, pts4);
         const Cam cam = load_cam(a, obj);
         const float delta = __ldg(a.delta + obj);
+        PH_MARK(a, PH_LOAD);
         if constexpr (DO_LM) {
             lm_phase<DOF>(a, sh, pts4, cam, delta, obj, DO_AMIS || a.pose_cov != nullptr);
         }
@@ -668,7 +751,7 @@ __global__ void __launch_bounds__(NT) evaluate_full_kernel(const KArgs a, float*
 // AdaptiveHuberPnPCost.set_param: delta = mean(w2d) * sqrt(var_x + var_y) * relative_delta
 __global__ void __launch_bounds__(NT) adaptive_delta_kernel(const float* x2d, const float* w2d, float rel,
                                                           float* delta, int N) {
-    __shared__ float red[NW * 32];
+    __shared__ float red[2 * NW * 32];
     const int obj = blockIdx.x;
     const float2* x = reinterpret_cast<const float2*>(x2d) + (size_t)obj * N;
     const float2* w = reinterpret_cast<const float2*>(w2d) + (size_t)obj * N;
@@ -677,14 +760,14 @@ __global__ void __launch_bounds__(NT) adaptive_delta_kernel(const float* x2d, co
         const float2 a = x[n], b = w[n];
         s[0] += a.x; s[1] += a.y; s[2] += b.x + b.y;
     }
-    block_sum<3>(s, red);
+    block_sum<3>(s, red, 0);
     const float mx = s[0] / N, my = s[1] / N, mw = s[2] / (2.f * N);
     float v[2] = {0.f, 0.f};
     for (int n = threadIdx.x; n < N; n += NT) {
         const float2 a = x[n];
         v[0] = fmaf(a.x - mx, a.x - mx, v[0]); v[1] = fmaf(a.y - my, a.y - my, v[1]);
     }
-    block_sum<2>(v, red);
+    block_sum<2>(v, red, 1);
     if (threadIdx.x == 0) delta[obj] = mw * sqrtf((v[0] + v[1]) / (float)(N - 1)) * rel;
 }
 
@@ -718,6 +801,7 @@ int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream) 
     if (e != cudaSuccess) return cuda_fail(e);
     if (occ < 1) return EPNP_ERR_TOO_MANY_POINTS;
     // persistent grid, balanced: every CTA gets the same number of objects (+-1)
+    a.num_sms = sms;
     const int slots = sms * occ;
     const int rounds = (a.B + slots - 1) / slots;
     const int grid = (a.B + rounds - 1) / rounds;
@@ -726,6 +810,8 @@ int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream) 
     if (e != cudaSuccess) return cuda_fail(e);
     return EPNP_OK;
 }
+
+unsigned long long* g_prof_buffer = nullptr;     // set by epnp_debug_set_phase_buffer (profiling build)
 
 int check_amis_params(const Params& p) {
     if (p.mc_iter <= 0 || p.mc_iter > MAX_ITER || p.mc_samples <= 0 || p.mc_samples % p.mc_iter != 0) return EPNP_ERR_BAD_ARG;
@@ -738,6 +824,11 @@ int check_amis_params(const Params& p) {
 
 // ================================================================================================
 extern "C" {
+
+#ifdef EPNP_PHASE_TIMERS
+// profiling build only (not declared in the public header): device buffer of PH_COUNT uint64 counters
+void epnp_debug_set_phase_buffer(unsigned long long* dev_buf) { g_prof_buffer = dev_buf; }
+#endif
 
 int epnp_abi_version(void) { return EPNP_ABI_VERSION; }
 
@@ -873,6 +964,7 @@ int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d,
     a.seed = seed; a.obj_offset = obj_offset;
     a.pose_opt = pose_opt; a.pose_cov = pose_cov; a.cost = cost; a.pose_plus = pose_opt_plus; a.cost_init = cost_init;
     a.pose_samples = pose_samples; a.logw = logw; a.proposals = proposals; a.B = B; a.N = N; a.p = *p;
+    a.prof = g_prof_buffer;
     int rc = check_common(a);
     if (rc != EPNP_OK) return rc;
     rc = check_amis_params(*p);

@@ -91,9 +91,9 @@ template <int DOF> PNP_HD void pose_add(const float* pose, const float* step, fl
     float qx = x + (-w * a - z * b + y * c);
     float qy = y + (z * a - w * b - x * c);
     float qz = z + (-y * a + x * b - w * c);
-    float n = sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
-    n = fmaxf(n, 1e-12f);
-    out[3] = qw / n; out[4] = qx / n; out[5] = qy / n; out[6] = qz / n;
+    const float n = fmaxf(sqrtf(qw * qw + qx * qx + qy * qy + qz * qz), 1e-12f);
+    const float inv = 1.0f / n;
+    out[3] = qw * inv; out[4] = qx * inv; out[5] = qy * inv; out[6] = qz * inv;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -429,10 +429,11 @@ template <int DOF> PNP_HD float damped_step_refined(const float* a, const float*
 // Damped step from the current linearisation -> s.pose_new, s.model_change  (:205-225)
 template <int DOF> PNP_HD void lm_propose(LMState<DOF>& s, const Params& p) {
     float add[DOF], step[DOF];
+    const float inv_radius = 1.0f / s.radius;
 #pragma unroll
     for (int i = 0; i < DOF; ++i) {
         const float d = s.a[tri(i, i, DOF)];
-        add[i] = fminf(fmaxf(d, p.min_lm_diagonal), p.max_lm_diagonal) / s.radius + p.eps;
+        add[i] = fmaf(fminf(fmaxf(d, p.min_lm_diagonal), p.max_lm_diagonal), inv_radius, p.eps);
     }
     s.model_change = damped_step_refined<DOF>(s.a, s.g, add, step);
     pose_add<DOF>(s.pose, step, s.pose_new);
@@ -502,6 +503,7 @@ struct Proposal6 {
     float lt[6];     // L_t lower: l00 l10 l11 l20 l21 l22
     float lr[10];    // L_r lower: l00 l10 l11 l20 l21 l22 l30 l31 l32 l33
     float ct, cr;    // additive log-normalisers (already negated)
+    float ilt[3], ilr[4];   // reciprocals of the diagonals of L_t / L_r (densities multiply, never divide)
 };
 
 // lgamma(1.5) - lgamma(3) + 1.5 log(3 pi):  log-normaliser of the df=3, n=3 Student-t
@@ -512,6 +514,8 @@ struct Proposal6 {
 PNP_HD void proposal_finish(Proposal6& p) {
     p.ct = -(logf(p.lt[0]) + logf(p.lt[2]) + logf(p.lt[5]) + PNP_MVT3_LOGNORM);
     p.cr = -(logf(p.lr[0]) + logf(p.lr[2]) + logf(p.lr[5]) + logf(p.lr[9]) + PNP_LOG_S3_AREA);
+    p.ilt[0] = 1.0f / p.lt[0]; p.ilt[1] = 1.0f / p.lt[2]; p.ilt[2] = 1.0f / p.lt[5];
+    p.ilr[0] = 1.0f / p.lr[0]; p.ilr[1] = 1.0f / p.lr[2]; p.ilr[2] = 1.0f / p.lr[5]; p.ilr[3] = 1.0f / p.lr[9];
 }
 
 // chol of a symmetric 3x3 given by its packed upper triangle, with the reference's fallback:
@@ -641,16 +645,16 @@ PNP_HD void proposal_draw6(const Proposal6& p, const float* n3, float chi2, cons
 // log q(sample) under one proposal  (pyro MultivariateStudentT.log_prob + distributions.py:32-40)
 PNP_HD float proposal_logpdf6(const Proposal6& p, const float* smp) {
     const float d0 = smp[0] - p.mu[0], d1 = smp[1] - p.mu[1], d2 = smp[2] - p.mu[2];
-    const float y0 = d0 / p.lt[0];
-    const float y1 = (d1 - p.lt[1] * y0) / p.lt[2];
-    const float y2 = (d2 - p.lt[3] * y0 - p.lt[4] * y1) / p.lt[5];
+    const float y0 = d0 * p.ilt[0];
+    const float y1 = (d1 - p.lt[1] * y0) * p.ilt[1];
+    const float y2 = (d2 - p.lt[3] * y0 - p.lt[4] * y1) * p.ilt[2];
     const float mt = y0 * y0 + y1 * y1 + y2 * y2;
-    const float z0 = smp[3] / p.lr[0];
-    const float z1 = (smp[4] - p.lr[1] * z0) / p.lr[2];
-    const float z2 = (smp[5] - p.lr[3] * z0 - p.lr[4] * z1) / p.lr[5];
-    const float z3 = (smp[6] - p.lr[6] * z0 - p.lr[7] * z1 - p.lr[8] * z2) / p.lr[9];
+    const float z0 = smp[3] * p.ilr[0];
+    const float z1 = (smp[4] - p.lr[1] * z0) * p.ilr[1];
+    const float z2 = (smp[5] - p.lr[3] * z0 - p.lr[4] * z1) * p.ilr[2];
+    const float z3 = (smp[6] - p.lr[6] * z0 - p.lr[7] * z1 - p.lr[8] * z2) * p.ilr[3];
     const float mr = z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3;
-    return (-3.0f * log1pf(mt / 3.0f) + p.ct) + (-2.0f * logf(mr) + p.cr);
+    return (-3.0f * log1pf(mt * (1.0f / 3.0f)) + p.ct) + (-2.0f * logf(mr) + p.cr);
 }
 
 // q^T Lambda^-1 q for the ACG fixed-point iteration (epropnp.py:335-337)

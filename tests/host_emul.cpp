@@ -128,40 +128,76 @@ void amis_object6(const float* x3d, const float* x2d, const float* w2d, int N, c
             mx = fmaxf(mx, lw[m]);
         }
         if (i == I - 1) { for (int m = 0; m < M; ++m) logw[m] = lw[m]; break; }
-        float sum = 0.f;
-        for (int m = 0; m < n; ++m) { lw[m] = expf(lw[m] - mx); sum += lw[m]; }
-        const float inv_sum = 1.0f / sum;
-        float mean[3] = {0, 0, 0};
+        // pass B: e = exp(lw - max); sum e, sum e t, ACG iteration 1 (Lambda_0 = I)
+        float accB[15];
+        for (int r = 0; r < 15; ++r) accB[r] = 0.f;
         for (int m = 0; m < n; ++m) {
-            lw[m] *= inv_sum;
-            for (int k = 0; k < 3; ++k) mean[k] = fmaf(lw[m], samples[7 * m + k], mean[k]);
+            const float e = expf(lw[m] - mx);
+            lw[m] = e;
+            const float* s7 = samples + 7 * m;
+            accB[0] += e;
+            for (int k = 0; k < 3; ++k) accB[1 + k] = fmaf(e, s7[k], accB[1 + k]);
+            const float* q = s7 + 3;
+            const float mq = fmaxf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3], p.amis_eps);
+            const float wm = e / mq;
+            accB[4] += wm;
+            int idx = 5;
+            for (int r = 0; r < 4; ++r)
+                for (int c = r; c < 4; ++c) { accB[idx] = fmaf(wm * q[r], q[c], accB[idx]); ++idx; }
         }
-        float lam_inv[16];
-        for (int r = 0; r < 16; ++r) lam_inv[r] = (r % 5 == 0) ? 1.f : 0.f;
-        float tc[6] = {0, 0, 0, 0, 0, 0}, lam10[10];
-        for (int itr = 0; itr < p.acg_mle_iter; ++itr) {
+        const float inv_sum = 1.0f / accB[0];
+        float mean[3] = {accB[1] * inv_sum, accB[2] * inv_sum, accB[3] * inv_sum};
+        float lam10[10], tc[6], lam_inv[16];
+        {
+            const float inv0 = 1.0f / accB[4];
+            for (int r = 0; r < 10; ++r) lam10[r] = accB[5 + r] * inv0;
+            lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
+        }
+        if (p.acg_mle_iter == 0) { for (int r = 0; r < 10; ++r) lam10[r] = 0.f; lam10[0] = lam10[4] = lam10[7] = lam10[9] = 1.f; }
+        // pass C: covariance about the mean (+ ACG iteration 2)
+        {
+            const bool more = p.acg_mle_iter >= 2;
+            if (more) acg_scatter_inverse(lam10, lam_inv);
             float acc[17];
             for (int r = 0; r < 17; ++r) acc[r] = 0.f;
             for (int m = 0; m < n; ++m) {
-                const float w = lw[m];
+                const float w = lw[m] * inv_sum;
+                lw[m] = w;
+                const float* s7 = samples + 7 * m;
+                const float d0 = s7[0] - mean[0], d1 = s7[1] - mean[1], d2 = s7[2] - mean[2];
+                acc[11] = fmaf(w * d0, d0, acc[11]); acc[12] = fmaf(w * d0, d1, acc[12]); acc[13] = fmaf(w * d0, d2, acc[13]);
+                acc[14] = fmaf(w * d1, d1, acc[14]); acc[15] = fmaf(w * d1, d2, acc[15]); acc[16] = fmaf(w * d2, d2, acc[16]);
+                if (more) {
+                    const float* q = s7 + 3;
+                    const float wm = w / fmaxf(quad4(lam_inv, q), p.amis_eps);
+                    acc[0] += wm;
+                    int idx = 1;
+                    for (int r = 0; r < 4; ++r)
+                        for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
+                }
+            }
+            for (int r = 0; r < 6; ++r) tc[r] = acc[11 + r];
+            if (more) {
+                const float inv0 = 1.0f / acc[0];
+                for (int r = 0; r < 10; ++r) lam10[r] = acc[1 + r] * inv0;
+                lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
+            }
+        }
+        for (int itr = 2; itr < p.acg_mle_iter; ++itr) {
+            acg_scatter_inverse(lam10, lam_inv);
+            float acc[11];
+            for (int r = 0; r < 11; ++r) acc[r] = 0.f;
+            for (int m = 0; m < n; ++m) {
                 const float* q = samples + 7 * m + 3;
-                const float mq = fmaxf(quad4(lam_inv, q), p.amis_eps);
-                const float wm = w / mq;
+                const float wm = lw[m] / fmaxf(quad4(lam_inv, q), p.amis_eps);
                 acc[0] += wm;
                 int idx = 1;
                 for (int r = 0; r < 4; ++r)
                     for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
-                if (itr == 0) {
-                    const float d0 = samples[7 * m] - mean[0], d1 = samples[7 * m + 1] - mean[1], d2 = samples[7 * m + 2] - mean[2];
-                    acc[11] = fmaf(w * d0, d0, acc[11]); acc[12] = fmaf(w * d0, d1, acc[12]); acc[13] = fmaf(w * d0, d2, acc[13]);
-                    acc[14] = fmaf(w * d1, d1, acc[14]); acc[15] = fmaf(w * d1, d2, acc[15]); acc[16] = fmaf(w * d2, d2, acc[16]);
-                }
             }
-            if (itr == 0) for (int r = 0; r < 6; ++r) tc[r] = acc[11 + r];
             const float inv0 = 1.0f / acc[0];
             for (int r = 0; r < 10; ++r) lam10[r] = acc[1 + r] * inv0;
             lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
-            if (itr + 1 < p.acg_mle_iter) acg_scatter_inverse(lam10, lam_inv);
         }
         refit_finish6(mean, tc, lam10, p.acg_dispersion, prop[i + 1]);
     }

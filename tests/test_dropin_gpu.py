@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import err_vs, golden_bounds, golden_names, load_golden
+from conftest import assert_lm_parity, err_vs, golden_bounds, golden_names, load_golden
 from epropnp.camera import PerspectiveCamera
 from epropnp.common import evaluate_pnp
 from epropnp.cost_fun import AdaptiveHuberPnPCost, HuberPnPCost
@@ -38,8 +38,8 @@ def test_lmsolver_forward(cuda_device, name):
     pose, cov, cost, plus = solver(x3d, x2d, w2d, camera, cost_fun, pose_init=pose_init, with_pose_cov=True,
                                    with_cost=True, with_pose_opt_plus=True, fast_mode=bool(g["fast_mode"]))
     tol = max(1e-4, 3 * err_vs(g["ref32_lm_pose"], g["ref64_lm_pose"]))
-    assert err_vs(pose.cpu().numpy(), g["ref32_lm_pose"]) < tol
-    assert err_vs(plus.cpu().numpy(), g["ref32_lm_pose_plus"]) < tol
+    assert_lm_parity(pose.cpu().numpy(), cost.cpu().numpy(), g["ref32_lm_pose"], g["ref64_lm_cost"], tol, what=name)
+    assert_lm_parity(plus.cpu().numpy(), cost.cpu().numpy(), g["ref32_lm_pose_plus"], g["ref64_lm_cost"], tol, what=name)
     assert cov.shape == g["ref32_lm_cov"].shape and cost.shape == g["ref32_lm_cost"].shape
     pose2, cov2, cost2 = solver.solve(x3d, x2d, w2d, camera, cost_fun, pose_init=pose_init,
                                       fast_mode=bool(g["fast_mode"]))
@@ -47,7 +47,7 @@ def test_lmsolver_forward(cuda_device, name):
     if int(g["normalize"]):
         sn = LMSolver(dof=int(g["dof"]), num_iter=int(g["lm_iter"]), normalize=True)
         pn = sn(x3d, x2d, w2d, camera, cost_fun, pose_init=pose_init, with_cost=True)
-        assert err_vs(pn[0].cpu().numpy(), g["ref32_lmnorm_pose"]) < tol
+        assert_lm_parity(pn[0].cpu().numpy(), pn[2].cpu().numpy(), g["ref32_lmnorm_pose"], g["ref64_lm_cost"], tol, what=name)
         with pytest.raises(NotImplementedError):
             sn(x3d, x2d, w2d, camera, cost_fun, pose_init=pose_init, with_pose_cov=True)
 

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import err_vs, golden_bounds, golden_names, load_golden
+from conftest import assert_lm_parity, err_vs, golden_bounds, golden_names, load_golden
 from epropnp_b200 import native
 from epropnp_b200.synth import make_noise, make_problem
 
@@ -66,10 +66,11 @@ def test_golden_lm_solve(cuda_device, name):
     out = native.lm_solve(prob, pose0, _params(g), want_cov=True, want_cost=True, want_plus=True, want_cost_init=True)
     floor = err_vs(g["ref32_lm_pose"], g["ref64_lm_pose"])
     tol = max(1e-4, 3 * floor)                                             # k = 3
-    pose = out["pose_opt"].cpu().numpy()
-    assert err_vs(pose, g["ref32_lm_pose"]) < tol
-    assert err_vs(pose, g["ref64_lm_pose"]) < tol
-    assert err_vs(out["pose_opt_plus"].cpu().numpy(), g["ref64_lm_pose_plus"]) < tol
+    pose, cst = out["pose_opt"].cpu().numpy(), out["cost"].cpu().numpy()
+    assert_lm_parity(pose, cst, g["ref32_lm_pose"], g["ref64_lm_cost"], tol, what=name + " vs ref32")
+    assert_lm_parity(pose, cst, g["ref64_lm_pose"], g["ref64_lm_cost"], tol, what=name + " vs ref64")
+    assert_lm_parity(out["pose_opt_plus"].cpu().numpy(), cst, g["ref64_lm_pose_plus"], g["ref64_lm_cost"], tol,
+                     what=name + " pose_plus")
     assert err_vs(out["cost"].cpu().numpy(), g["ref64_lm_cost"]) < max(1e-4, 3 * err_vs(g["ref32_lm_cost"], g["ref64_lm_cost"]))
     assert err_vs(out["pose_cov"].cpu().numpy(), g["ref64_lm_cov"]) < max(2e-3, 3 * err_vs(g["ref32_lm_cov"], g["ref64_lm_cov"]))
     assert err_vs(out["cost_init"].cpu().numpy(), g["ref64_eval_cost"]) < 2e-5
@@ -162,7 +163,9 @@ def test_fused_against_oracle_north_star_shape(cuda_device, B, N, M, I):
     floor_p = err_vs(r32["pose_opt"], r64["pose_opt"])
     floor_w = err_vs(r32["logw"], r64["logw"])
     floor_s = err_vs(r32["samples"], r64["samples"])
-    assert err_vs(pose, r64["pose_opt"]) < max(1e-4, 3 * floor_p)
+    flips = assert_lm_parity(pose, out["cost"].cpu().numpy(), r64["pose_opt"].numpy(), r64["lm_cost"].numpy(),
+                             max(1e-4, 3 * floor_p), max_flip_frac=0.05, what="oracle shape")
+    assert flips == 0.0 or N < 512
     assert err_vs(smp, r64["samples"]) < max(1e-4, 5 * floor_s)
     assert err_vs(lw, r64["logw"]) < max(1e-4, 5 * floor_w)
     if N >= 512 and M == 512:
@@ -225,6 +228,21 @@ def test_full_size_deterministic_and_shard_invariant(big):
     other = native.lm_amis_fused(prob, big["pose_init"], p, seed=99)
     assert not torch.equal(other["logw"], big["out"]["logw"])
     assert torch.equal(other["pose_opt"], big["out"]["pose_opt"])          # the LM part does not see the seed
+
+
+def test_lm_flip_rate_at_north_star_shape(big):
+    """LM poses of 1024 objects (N = 512) against the fp64 oracle: <= 1e-4 for (almost) all, the rest must
+    be cost-equivalent accept/reject flips; the flip rate is printed for the record."""
+    from oracle import pnp_oracle as orc
+    n = 1024
+    d = torch.float64
+    cam = orc.Camera(big["cam_mats"][:n].cpu().to(d), 0.1)
+    x3d, x2d, w2d = (big[k][:n].cpu().to(d) for k in ("x3d", "x2d", "w2d"))
+    delta = orc.adaptive_delta(x2d, w2d, 0.5)
+    pose64, _, cost64 = orc.lm_solve(x3d, x2d, w2d, cam, delta, big["pose_init"][:n].cpu().to(d), orc.LMParams())
+    flips = assert_lm_parity(big["out"]["pose_opt"][:n].cpu().numpy(), big["out"]["cost"][:n].cpu().numpy(),
+                             pose64.numpy(), cost64.numpy(), 1e-4, max_flip_frac=0.01, what="north-star LM")
+    print(f"LM flip rate at N=512: {flips:.4%} of {n} objects")
 
 
 def test_tma_and_plain_loader_agree(big):

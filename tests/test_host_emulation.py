@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import err_vs, golden_names, load_golden
+from conftest import assert_lm_parity, err_vs, golden_names, load_golden
 from epropnp_b200 import build
 from epropnp_b200.capi import EpnpParams
 
@@ -99,11 +99,11 @@ def test_lm_state_machine(emul, name):
                  fptr(cov), fptr(cost), fptr(plus), fptr(cinit), B, N, ctypes.byref(p))
     floor = err_vs(g["ref32_lm_pose"], g["ref64_lm_pose"])
     tol = max(1e-4, 3 * floor)
-    assert err_vs(pose, g["ref64_lm_pose"]) < tol
-    assert err_vs(pose, g["ref32_lm_pose"]) < tol
+    assert_lm_parity(pose, cost, g["ref64_lm_pose"], g["ref64_lm_cost"], tol, what=name + " vs ref64")
+    assert_lm_parity(pose, cost, g["ref32_lm_pose"], g["ref64_lm_cost"], tol, what=name + " vs ref32")
     assert err_vs(cost, g["ref64_lm_cost"]) < max(1e-4, 3 * err_vs(g["ref32_lm_cost"], g["ref64_lm_cost"]))
     assert err_vs(cov, g["ref64_lm_cov"]) < max(2e-3, 3 * err_vs(g["ref32_lm_cov"], g["ref64_lm_cov"]))
-    assert err_vs(plus, g["ref64_lm_pose_plus"]) < tol
+    assert_lm_parity(plus, cost, g["ref64_lm_pose_plus"], g["ref64_lm_cost"], tol, what=name + " pose_plus")
     assert err_vs(cinit, g["ref64_eval_cost"]) < 2e-5
 
 
