@@ -153,7 +153,9 @@ PNP_HD void point_normal_eq(const float* R, const float* t, const Cam& c, float 
     const float s2 = fmaf(rx, rx, ry * ry);
     const float s = sqrtf(s2);
     acc[NA + DOF] += (s <= delta) ? 0.5f * s2 : fmaf(delta, s, -0.5f * delta * delta);
-    const float sc = sqrtf(fminf(delta / fmaxf(s, huber_eps), 1.0f));      // sqrt(rho')
+    // sqrt(rho') = sqrt(min(delta / max(s, eps), 1)): exactly 1 for inliers (s <= delta), which is most points
+    // near the optimum -- skip the divide + sqrt there (warp-uniform most of the time)
+    const float sc = (s <= delta && delta >= huber_eps) ? 1.0f : sqrtf(fminf(delta / fmaxf(s, huber_eps), 1.0f));
     rx *= sc; ry *= sc;
 
     float jx[DOF], jy[DOF];
@@ -212,7 +214,7 @@ PNP_HD float point_residual_jac(const float* R, const float* t, const Cam& c, fl
     const float s2 = fmaf(rx, rx, ry * ry);
     const float s = sqrtf(s2);
     const float cost = (s <= delta) ? 0.5f * s2 : fmaf(delta, s, -0.5f * delta * delta);
-    const float sc = sqrtf(fminf(delta / fmaxf(s, huber_eps), 1.0f));
+    const float sc = (s <= delta && delta >= huber_eps) ? 1.0f : sqrtf(fminf(delta / fmaxf(s, huber_eps), 1.0f));
     res[0] = rx * sc; res[1] = ry * sc;
     float* jx = jac; float* jy = jac + DOF;
     jx[0] = K[0] * iz; jx[1] = K[1] * iz; jx[2] = (K[2] - px) * iz;
@@ -253,11 +255,30 @@ PNP_HD float inv_sqrt(float x) {
 }
 PNP_HD double inv_sqrt(double x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrt(x);
+    // MUFU.RSQ seed (2 ulp in fp32) + two Newton steps in fp64: relative error ~1e-16 with six DP
+    // multiply-adds instead of the ~40-instruction IEEE rsqrt(double) sequence.  Arguments here are
+    // Cholesky pivots (1e-12 .. 1e8), well inside fp32 range; <= 0 / NaN still yield NaN / inf.
+    const double y0 = (double)rsqrtf((float)x);
+    const double hx = 0.5 * x;
+    double y = y0 * (1.5 - hx * y0 * y0);
+    y = y * (1.5 - hx * y * y);
+    return y;
 #else
     return 1.0 / sqrt(x);
 #endif
 }
+PNP_HD double fast_recip(double x) {
+#if defined(__CUDA_ARCH__)
+    // same idea for 1/x: MUFU.RCP seed + two Newton steps
+    const double y0 = (double)(1.0f / (float)x);
+    double y = y0 * (2.0 - x * y0);
+    y = y * (2.0 - x * y);
+    return y;
+#else
+    return 1.0 / x;
+#endif
+}
+PNP_HD float fast_recip(float x) { return 1.0f / x; }
 
 // a: packed upper triangle (row-major).  L: full n*n row-major lower factor with the RECIPROCAL of the
 // diagonal stored in Dinv (so the substitutions below multiply instead of divide).  Returns false when
@@ -532,7 +553,7 @@ template <class T> PNP_HD void acg_dispersed_chol(const T* c10, float dispersion
     T L[16], a[10], Dinv[4];
     chol_packed<4, T>(c10, L, Dinv);
     const T d = L[0] * L[5] * L[10] * L[15];              // sqrt(det C); NaN if C is not PD
-    const T add = sqrt(d) * (T)dispersion;                // det^(1/4) * dispersion
+    const T add = (d * inv_sqrt(d)) * (T)dispersion;      // det^(1/4) * dispersion  (sqrt(d) = d * rsqrt(d))
 #pragma unroll
     for (int i = 0; i < 10; ++i) a[i] = c10[i];
     a[0] += add; a[4] += add; a[7] += add; a[9] += add;
@@ -586,7 +607,7 @@ PNP_HD_COLD void initial_fit6(const float* pose, const float* cov /*6x6 full*/, 
             if (i == j) tr += rc[idx];
             ++idx;
         }
-    const Hi itr = 1.0 / tr;
+    const Hi itr = fast_recip(tr);
 #pragma unroll
     for (int i = 0; i < 10; ++i) rc[i] *= itr;
     acg_dispersed_chol<Hi>(rc, dispersion, p.lr);
@@ -697,12 +718,14 @@ struct Philox {
 PNP_HD void box_muller(uint32_t u0, uint32_t u1, float& n0, float& n1) {
     const float a = ((float)(u0 >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0,1)
     const float b = ((float)(u1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float r = sqrtf(-2.0f * logf(a));
-    float s, c;
+    float r, s, c;
 #if defined(__CUDA_ARCH__)
-    sincospif(2.0f * b, &s, &c);
+    // MUFU-based log / sin / cos: ~1e-6 relative error, irrelevant for random draws, ~4x fewer instructions
+    r = sqrtf(-2.0f * __logf(a));
+    __sincosf(6.283185307179586f * b - 3.14159265358979f, &s, &c);
 #else
-    s = sinf(6.283185307179586f * b); c = cosf(6.283185307179586f * b);
+    r = sqrtf(-2.0f * logf(a));
+    s = sinf(6.283185307179586f * b - 3.14159265358979f); c = cosf(6.283185307179586f * b - 3.14159265358979f);
 #endif
     n0 = r * c; n1 = r * s;
 }
