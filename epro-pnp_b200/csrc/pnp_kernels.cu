@@ -309,9 +309,15 @@ __device__ void eval_normal_eq(const float* pts, int N, const float* pose, const
     float acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    for (int n = threadIdx.x; n < N; n += NT) {
-        const PointRec q = load_point(pts, n);
-        point_normal_eq<DOF, CLIP>(R, t, cam, delta, huber_eps, q.X, q.Y, q.Z, q.u, q.v, q.wu, q.wv, acc);
+    // one PAIR record (4 x LDS.128) per thread and step: 4-way bank conflicts instead of the 16-way a
+    // per-point scalar walk over the 64-byte records would cause
+    const float4* p4 = reinterpret_cast<const float4*>(pts);
+    const int npair = (N + 1) >> 1;
+    for (int j = threadIdx.x; j < npair; j += NT) {
+        const float4 q0 = p4[4 * j], q1 = p4[4 * j + 1], q2 = p4[4 * j + 2], q3 = p4[4 * j + 3];
+        point_normal_eq<DOF, CLIP>(R, t, cam, delta, huber_eps, q0.x, q0.z, q1.x, -q1.z, -q2.x, q2.z, q3.x, acc);
+        if (2 * j + 1 < N)
+            point_normal_eq<DOF, CLIP>(R, t, cam, delta, huber_eps, q0.y, q0.w, q1.y, -q1.w, -q2.y, q2.w, q3.y, acc);
     }
     const float tot = warp_transpose_sum(acc);
     red[(threadIdx.x >> 5) * 32 + (threadIdx.x & 31)] = tot;

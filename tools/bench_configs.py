@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Device-timed throughput of the BASELINE.json configs that are not the headline bench line
+(parity-test shapes, measured for the record):  #2 LM-only, #3 LM+AMIS at B=1024, #4 dense N=4096."""
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "epro-pnp_b200"))
+import torch  # noqa: E402
+from epropnp_b200 import native  # noqa: E402
+from epropnp_b200.synth import make_problem  # noqa: E402
+
+
+def timed(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return statistics.median(a.elapsed_time(b) for a, b in ev)
+
+
+def main():
+    dev = torch.device("cuda:0")
+    out = []
+
+    def setup(B, N, rel, **kw):
+        pc = make_problem(B, N, seed=11, **kw)
+        d = {k: v.to(dev) for k, v in pc.items()}
+        delta = native.adaptive_delta(d["x2d"], d["w2d"], rel)
+        return native.Problem(d["x3d"], d["x2d"], d["w2d"], d["cam_mats"], None, None, delta), d["pose_init"]
+
+    for B in (1024, 4096, 16384):
+        prob, p0 = setup(B, 512, 0.5)
+        p = native.default_params(6, lm_iter=10)
+        ms = timed(lambda: native.lm_solve(prob, p0, p, want_cov=True, want_cost=True))
+        out.append(dict(config="#2 LM(10) only, N=512", B=B, ms=ms, objects_per_s=B / ms * 1e3,
+                        hbm_gbs=B * 14580 / ms / 1e6))
+    for B in (1024, 4096):
+        prob, p0 = setup(B, 512, 0.5)
+        p = native.default_params(6, lm_iter=10, mc_samples=512, mc_iter=4)
+        ms = timed(lambda: native.lm_amis_fused(prob, p0, p, seed=1))
+        out.append(dict(config="#3 LM(10)+AMIS(4x128), N=512", B=B, ms=ms, objects_per_s=B / ms * 1e3,
+                        hbm_gbs=B * 30964 / ms / 1e6))
+    for B in (256, 1024):
+        prob, p0 = setup(B, 4096, 0.1, grid2d=True)
+        p = native.default_params(6, lm_iter=3, fast_mode=1, z_min=0.01, mc_samples=512, mc_iter=4)
+        ms = timed(lambda: native.lm_amis_fused(prob, p0, p, seed=1), iters=10)
+        out.append(dict(config="#4 dense GN(3)+AMIS(4x128), N=4096", B=B, ms=ms, objects_per_s=B / ms * 1e3,
+                        hbm_gbs=B * 131316 / ms / 1e6))
+        ms = timed(lambda: native.lm_solve(prob, p0, p, want_cov=True), iters=10)
+        out.append(dict(config="#4 dense GN(3) only (test-time path, lib/test.py:209-211), N=4096", B=B, ms=ms,
+                        objects_per_s=B / ms * 1e3, hbm_gbs=B * 114932 / ms / 1e6))
+    S = 128
+    prob, p0 = setup(4096, 512, 0.5)
+    poses = p0[None].repeat(S, 1, 1).contiguous()
+    ms = timed(lambda: native.evaluate_cost(prob, poses, 6, 0.1))
+    out.append(dict(config="evaluate_pnp cost, 128 poses x 4096 objects x 512 pts", B=4096, ms=ms,
+                    pose_point_pairs_per_s=S * 4096 * 512 / ms * 1e3))
+    for r in out:
+        print(json.dumps(r))
+
+
+if __name__ == "__main__":
+    main()
