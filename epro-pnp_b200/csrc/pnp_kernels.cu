@@ -115,6 +115,7 @@ template <int DOF> struct SmemHead {
     LMState<DOF> lm;
     float cov[DOF * DOF];
     Proposal6 prop[MAX_ITER];
+    Proposal4 prop4[MAX_ITER];
 };
 
 struct SmemPlan {        // offsets in floats from the start of dynamic smem
@@ -660,6 +661,110 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// AMIS loop for the resident object, 4DoF (EProPnP4DoF, epropnp.py:199-260): same skeleton as amis_phase6
+// with the yaw proposal 0.75 von Mises + 0.25 uniform.  Injected noise: noise_rot (B, M) holds the yaw
+// draws themselves (the reference samples them with numpy on the host, distributions.py:61-72, so there
+// is no base noise to replay).
+__device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, float* smp, float* cst,
+                            float* logp, float* lw, const Cam& cam, float delta, int obj,
+                            const float* pose_opt, const float* cov) {
+    const Params& p = a.p;
+    const int tid = threadIdx.x;
+    const int M = p.mc_samples, I = p.mc_iter, S = M / I;
+    const bool injected = a.noise_n3 != nullptr;
+    const int st = serial_thread(a);
+    PH_DECL;
+
+    if (tid == st) initial_fit4(pose_opt, cov, p.amis_eps, sh.prop4[0]);
+    PH_MARK(a, PH_INIT_FIT);
+    __syncthreads();
+
+    for (int i = 0; i < I; ++i) {
+        for (int s = tid; s < S; s += NT) {
+            const int m = i * S + s;
+            float n3[3], chi2, q[4];
+            if (injected) {
+                const size_t g = (size_t)obj * M + m;
+                n3[0] = __ldg(a.noise_n3 + g * 3); n3[1] = __ldg(a.noise_n3 + g * 3 + 1); n3[2] = __ldg(a.noise_n3 + g * 3 + 2);
+                chi2 = __ldg(a.noise_chi2 + g);
+                q[3] = __ldg(a.noise_rot + g);
+            } else {
+                draw_base_noise_t(a.seed, a.obj_offset + (uint32_t)obj, (uint32_t)m, n3, chi2);
+                q[3] = draw_yaw(a.seed, a.obj_offset + (uint32_t)obj, (uint32_t)m, s, S, sh.prop4[i].mode, sh.prop4[i].kappa);
+            }
+            draw_translation(sh.prop4[i].mu, sh.prop4[i].lt, n3, chi2, q);
+            float* out = a.pose_samples + ((size_t)obj * M + m) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { smp[m * 4 + k] = q[k]; out[k] = q[k]; }
+            cst[m] = pose_cost<4>(pts4, a.N, q, cam, delta);
+            for (int j = 0; j <= i; ++j) logp[j * M + m] = proposal_logpdf4(sh.prop4[j], q);
+        }
+        PH_MARK(a, PH_DRAW_SWEEP);
+        for (int m = tid; m < i * S; m += NT) logp[i * M + m] = proposal_logpdf4(sh.prop4[i], smp + m * 4);
+        __syncthreads();
+        PH_MARK(a, PH_LOGP_OLD);
+        const int n = (i + 1) * S;
+        const float log_cnt = logf((float)(i + 1));
+        float mx = -CUDART_INF_F;
+        for (int m = tid; m < n; m += NT) {
+            float top = logp[m];
+            for (int j = 1; j <= i; ++j) top = fmaxf(top, logp[j * M + m]);
+            float acc = 0.f;
+            for (int j = 0; j <= i; ++j) acc += expf(logp[j * M + m] - top);
+            const float v = -cst[m] - ((top + logf(acc)) - log_cnt);
+            lw[m] = v;
+            mx = fmaxf(mx, v);
+        }
+        PH_MARK(a, PH_WEIGHTS);
+        if (i == I - 1) {
+            for (int m = tid; m < M; m += NT) a.logw[(size_t)obj * M + m] = lw[m];
+            PH_MARK(a, PH_OUTPUT);
+            break;
+        }
+        // ---- refit (estimate_params, epropnp.py:232-260): A max, B sums of e, e t, e sin, e cos, C covariance
+        mx = block_max(mx, sh.red, 0);
+        float accB[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int m = tid; m < n; m += NT) {
+            const float e = expf(lw[m] - mx);
+            lw[m] = e;
+            const float* s4 = smp + m * 4;
+            float sn, cs;
+            sincosf(s4[3], &sn, &cs);
+            accB[0] += e;
+            accB[1] = fmaf(e, s4[0], accB[1]); accB[2] = fmaf(e, s4[1], accB[2]); accB[3] = fmaf(e, s4[2], accB[3]);
+            accB[4] = fmaf(e, sn, accB[4]); accB[5] = fmaf(e, cs, accB[5]);
+        }
+        block_sum<6>(accB, sh.red, 1);
+        const float inv_sum = 1.0f / accB[0];
+        const float mean[3] = {accB[1] * inv_sum, accB[2] * inv_sum, accB[3] * inv_sum};
+        float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int m = tid; m < n; m += NT) {
+            const float w = lw[m] * inv_sum;
+            const float* s4 = smp + m * 4;
+            const float d0 = s4[0] - mean[0], d1 = s4[1] - mean[1], d2 = s4[2] - mean[2];
+            tc[0] = fmaf(w * d0, d0, tc[0]); tc[1] = fmaf(w * d0, d1, tc[1]); tc[2] = fmaf(w * d0, d2, tc[2]);
+            tc[3] = fmaf(w * d1, d1, tc[3]); tc[4] = fmaf(w * d1, d2, tc[4]); tc[5] = fmaf(w * d2, d2, tc[5]);
+        }
+        block_sum<6>(tc, sh.red, 0);
+        PH_MARK(a, PH_REFIT_SUMS);
+        if (tid == st) refit_finish4(mean, tc, accB[4] * inv_sum, accB[5] * inv_sum, p.amis_eps, sh.prop4[i + 1]);
+        PH_MARK(a, PH_REFIT_FINISH);
+        __syncthreads();
+    }
+    if (a.proposals && tid < I) {       // (B, I, 19): mu3, Lt6, mode, kappa, 0...
+        float* o = a.proposals + ((size_t)obj * I + tid) * PROP_FLOATS;
+        const Proposal4& pr = sh.prop4[tid];
+        o[0] = pr.mu[0]; o[1] = pr.mu[1]; o[2] = pr.mu[2];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) o[3 + r] = pr.lt[r];
+        o[9] = pr.mode; o[10] = pr.kappa;
+#pragma unroll
+        for (int r = 11; r < PROP_FLOATS; ++r) o[r] = 0.f;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Kernels
 template <int DOF, bool DO_LM, bool DO_AMIS>
 __global__ void __launch_bounds__(NT, 4) solve_kernel(const KArgs a) {
@@ -681,14 +786,18 @@ __global__ void __launch_bounds__(NT, 4) solve_kernel(const KArgs a) {
         if constexpr (DO_LM) {
             lm_phase<DOF>(a, sh, pts4, cam, delta, obj, DO_AMIS || a.pose_cov != nullptr);
         }
-        if constexpr (DO_AMIS && DOF == 6) {
+        if constexpr (DO_AMIS) {
             if constexpr (!DO_LM) {
                 if (threadIdx.x < Dim<DOF>::POSE) sh.lm.pose[threadIdx.x] = __ldg(a.pose_opt_in + (size_t)obj * Dim<DOF>::POSE + threadIdx.x);
                 if (threadIdx.x < DOF * DOF) sh.cov[threadIdx.x] = __ldg(a.pose_cov_in + (size_t)obj * DOF * DOF + threadIdx.x);
                 __syncthreads();
             }
-            amis_phase6(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.lw, cam, delta, obj,
-                        sh.lm.pose, sh.cov);
+            if constexpr (DOF == 6)
+                amis_phase6(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.lw, cam, delta, obj,
+                            sh.lm.pose, sh.cov);
+            else
+                amis_phase4(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.lw, cam, delta, obj,
+                            sh.lm.pose, sh.cov);
         }
     }
 }
@@ -821,7 +930,6 @@ unsigned long long* g_prof_buffer = nullptr;     // set by epnp_debug_set_phase_
 
 int check_amis_params(const Params& p) {
     if (p.mc_iter <= 0 || p.mc_iter > MAX_ITER || p.mc_samples <= 0 || p.mc_samples % p.mc_iter != 0) return EPNP_ERR_BAD_ARG;
-    if (p.dof != 6) return EPNP_ERR_UNSUPPORTED;
     if (p.acg_mle_iter < 0) return EPNP_ERR_BAD_ARG;
     return EPNP_OK;
 }
@@ -951,7 +1059,10 @@ int epnp_amis_f32(const float* x3d, const float* x2d, const float* w2d, const fl
     if (!pose_opt || !pose_cov || !pose_samples || !logw) return EPNP_ERR_BAD_ARG;
     const bool any = noise_normal || noise_chi2 || noise_rot, all = noise_normal && noise_chi2 && noise_rot;
     if (any && !all) return EPNP_ERR_BAD_ARG;
-    return launch_persistent(solve_kernel<6, false, true>, a, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes,
+    if (p->dof == 6)
+        return launch_persistent(solve_kernel<6, false, true>, a, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes,
+                                 (cudaStream_t)stream);
+    return launch_persistent(solve_kernel<4, false, true>, a, plan_smem<4>(N, p->mc_samples, p->mc_iter, true).total_bytes,
                              (cudaStream_t)stream);
 }
 
@@ -978,7 +1089,10 @@ int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d,
     if (!pose_init || !pose_opt || !pose_samples || !logw || p->lm_iter < 0) return EPNP_ERR_BAD_ARG;
     const bool any = noise_normal || noise_chi2 || noise_rot, all = noise_normal && noise_chi2 && noise_rot;
     if (any && !all) return EPNP_ERR_BAD_ARG;
-    return launch_persistent(solve_kernel<6, true, true>, a, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes,
+    if (p->dof == 6)
+        return launch_persistent(solve_kernel<6, true, true>, a, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes,
+                                 (cudaStream_t)stream);
+    return launch_persistent(solve_kernel<4, true, true>, a, plan_smem<4>(N, p->mc_samples, p->mc_iter, true).total_bytes,
                              (cudaStream_t)stream);
 }
 

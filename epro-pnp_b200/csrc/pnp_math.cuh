@@ -692,6 +692,105 @@ PNP_HD float quad4(const float* inv16, const float* q) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// AMIS proposal for 4DoF (EProPnP4DoF, epropnp.py:199-260): translation ~ multivariate t (df=3), yaw ~
+// 0.75 von Mises(mode, kappa) + 0.25 uniform on the circle (distributions.py:55-79).
+struct Proposal4 {
+    float mu[3];
+    float lt[6];        // L_t lower: l00 l10 l11 l20 l21 l22
+    float ilt[3];       // reciprocal diagonal
+    float ct;           // -(sum log diag L_t + Student-t log-normaliser)
+    float mode, kappa;  // von Mises location / concentration
+    float cvm;          // log(0.75) - log(2 pi) - log I0(kappa)
+};
+
+#define PNP_LOG_UNIFORM_MIX (-3.2241714810970856f)      // log(0.25 / (2 pi))
+#define PNP_LOG_VM_MIX (-0.2876820724517809f)           // log(0.75)
+#define PNP_LOG_2PI 1.8378770664093453f
+
+// log I0(x) with the polynomial approximations torch.distributions.von_mises uses
+// (_log_modified_bessel_fn, order 0: Abramowitz-Stegun 9.8.1 / 9.8.2), so densities match the reference's.
+PNP_HD float log_bessel_i0(float x) {
+    if (x < 3.75f) {
+        float y = x / 3.75f;
+        y = y * y;
+        float r = 0.45813e-2f;
+        r = 0.360768e-1f + y * r; r = 0.2659732f + y * r; r = 1.2067492f + y * r;
+        r = 3.0899424f + y * r; r = 3.5156229f + y * r; r = 1.0f + y * r;
+        return logf(r);
+    }
+    const float y = 3.75f / x;
+    float r = 0.392377e-2f;
+    r = -0.1647633e-1f + y * r; r = 0.2635537e-1f + y * r; r = -0.2057706e-1f + y * r; r = 0.916281e-2f + y * r;
+    r = -0.157565e-2f + y * r; r = 0.225319e-2f + y * r; r = 0.1328592e-1f + y * r; r = 0.39894228f + y * r;
+    return x - 0.5f * logf(x) + logf(r);
+}
+
+PNP_HD void proposal4_finish(Proposal4& p) {
+    p.ct = -(logf(p.lt[0]) + logf(p.lt[2]) + logf(p.lt[5]) + PNP_MVT3_LOGNORM);
+    p.ilt[0] = 1.0f / p.lt[0]; p.ilt[1] = 1.0f / p.lt[2]; p.ilt[2] = 1.0f / p.lt[5];
+    p.cvm = PNP_LOG_VM_MIX - PNP_LOG_2PI - log_bessel_i0(p.kappa);
+}
+
+// chol of a symmetric 3x3 (packed upper), not PD -> diag(1, 1, 4): cholesky_wrapper(..., [1.0, 1.0, 4.0])
+template <class T> PNP_HD void chol3_or_default4(const T* a6, float* l) {
+    T L[9], Dinv[3];
+    if (chol_packed<3, T>(a6, L, Dinv)) {
+        l[0] = (float)L[0]; l[1] = (float)L[3]; l[2] = (float)L[4]; l[3] = (float)L[6]; l[4] = (float)L[7]; l[5] = (float)L[8];
+    } else { l[0] = 1.f; l[1] = 0.f; l[2] = 1.f; l[3] = 0.f; l[4] = 0.f; l[5] = 4.f; }
+}
+
+// EProPnP4DoF.initial_fit (epropnp.py:216-220): kappa_0 = 0.33 / max(var(yaw), eps)
+PNP_HD_COLD void initial_fit4(const float* pose, const float* cov /*4x4 full*/, float eps, Proposal4& p) {
+    p.mu[0] = pose[0]; p.mu[1] = pose[1]; p.mu[2] = pose[2];
+    const Hi ctt[6] = {(Hi)cov[0], (Hi)cov[1], (Hi)cov[2], (Hi)cov[5], (Hi)cov[6], (Hi)cov[10]};
+    chol3_or_default4<Hi>(ctt, p.lt);
+    p.mode = pose[3];
+    p.kappa = 0.33f / fmaxf(cov[15], eps);
+    proposal4_finish(p);
+}
+
+// EProPnP4DoF.estimate_params tail (epropnp.py:246-260) from the weighted statistics
+PNP_HD void refit_finish4(const float* mean, const float* tc6, float sum_sin, float sum_cos, float eps, Proposal4& np) {
+    np.mu[0] = mean[0]; np.mu[1] = mean[1]; np.mu[2] = mean[2];
+    Refit a6[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a6[i] = (Refit)tc6[i];
+    chol3_or_default4<Refit>(a6, np.lt);
+    np.mode = atan2f(sum_sin, sum_cos);
+    const float r_sq = sum_sin * sum_sin + sum_cos * sum_cos;
+    np.kappa = 0.33f * fmaxf(sqrtf(r_sq), eps) * (2.0f - r_sq) / fmaxf(1.0f - r_sq, eps);
+    proposal4_finish(np);
+}
+
+PNP_HD float wrap_pi(float a) {
+    const float two_pi = 6.283185307179586f;
+    a = a - two_pi * floorf((a + 3.14159265358979f) / two_pi);
+    return a;
+}
+
+// translation part of a draw (shared with 6DoF): t = mu + L (n3 * sqrt(3 / chi2))
+PNP_HD void draw_translation(const float* mu, const float* lt, const float* n3, float chi2, float* t) {
+    const float sc = 1.0f / sqrtf(chi2 / 3.0f);
+    const float y0 = n3[0] * sc, y1 = n3[1] * sc, y2 = n3[2] * sc;
+    t[0] = mu[0] + lt[0] * y0;
+    t[1] = mu[1] + (lt[1] * y0 + lt[2] * y1);
+    t[2] = mu[2] + (lt[3] * y0 + lt[4] * y1 + lt[5] * y2);
+}
+
+// log q(sample) under one 4DoF proposal: Student-t + logaddexp(von Mises part, uniform part)
+PNP_HD float proposal_logpdf4(const Proposal4& p, const float* smp) {
+    const float d0 = smp[0] - p.mu[0], d1 = smp[1] - p.mu[1], d2 = smp[2] - p.mu[2];
+    const float y0 = d0 * p.ilt[0];
+    const float y1 = (d1 - p.lt[1] * y0) * p.ilt[1];
+    const float y2 = (d2 - p.lt[3] * y0 - p.lt[4] * y1) * p.ilt[2];
+    const float mt = y0 * y0 + y1 * y1 + y2 * y2;
+    const float vm = p.kappa * cosf(smp[3] - p.mode) + p.cvm;
+    const float hi = fmaxf(vm, PNP_LOG_UNIFORM_MIX), lo = fminf(vm, PNP_LOG_UNIFORM_MIX);
+    const float rot = hi + log1pf(expf(lo - hi));
+    return (-3.0f * log1pf(mt * (1.0f / 3.0f)) + p.ct) + rot;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Counter-based RNG for the production (non-injected) AMIS draws: Philox-4x32-10.
 struct Philox {
     uint32_t k0, k1;
@@ -743,6 +842,51 @@ PNP_HD void draw_base_noise(uint64_t seed, uint32_t obj, uint32_t m, float* n3, 
     n3[0] = g[0]; n3[1] = g[1]; n3[2] = g[2];
     chi2 = g[3] * g[3] + g[4] * g[4] + g[5] * g[5];
     n4[0] = g[6]; n4[1] = g[7]; n4[2] = g[8]; n4[3] = g[9];
+}
+
+// translation-only base noise (4DoF): n3[3], chi2 -- the same Philox blocks 0 and 1 as draw_base_noise
+PNP_HD void draw_base_noise_t(uint64_t seed, uint32_t obj, uint32_t m, float* n3, float& chi2) {
+    Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t r[8];
+    ph(obj, m, 0u, 0x45505250u, r);
+    ph(obj, m, 1u, 0x45505250u, r + 4);
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) box_muller(r[2 * i], r[2 * i + 1], g[2 * i], g[2 * i + 1]);
+    n3[0] = g[0]; n3[1] = g[1]; n3[2] = g[2];
+    chi2 = g[3] * g[3] + g[4] * g[4] + g[5] * g[5];
+}
+
+// uniform in (0, 1) from 24 random bits
+PNP_HD float u01(uint32_t r) { return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// Production 4DoF draw of sample `m` (index `s_in_iter` within its AMIS iteration of `S` samples):
+// n3 / chi2 as in the 6DoF case; yaw: the first round(0.25 S) samples of an iteration are uniform on
+// [-pi, pi), the rest von Mises(mode, kappa) by Best-Fisher rejection (distributions.py:61-72 uses numpy's
+// sampler of the same family).  Returns the yaw.
+PNP_HD float draw_yaw(uint64_t seed, uint32_t obj, uint32_t m, int s_in_iter, int S, float mode, float kappa) {
+    Philox ph{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t r[4];
+    const int n_uniform = (int)floorf(0.25f * (float)S + 0.5f);
+    ph(obj, m, 2u, 0x45505250u, r);
+    if (s_in_iter < n_uniform) return (2.0f * u01(r[3]) - 1.0f) * 3.14159265358979f;
+    if (!(kappa > 1e-6f)) return (2.0f * u01(r[3]) - 1.0f) * 3.14159265358979f;     // flat (or NaN) concentration
+    const float tau = 1.0f + sqrtf(1.0f + 4.0f * kappa * kappa);
+    const float rho = (tau - sqrtf(2.0f * tau)) / (2.0f * kappa);
+    const float rr = (1.0f + rho * rho) / (2.0f * rho);
+    float f = 1.0f;
+    for (uint32_t attempt = 0; attempt < 64u; ++attempt) {
+        ph(obj, m, 3u + attempt, 0x45505250u, r);
+        const float z = cosf(3.14159265358979f * u01(r[0]));
+        f = (1.0f + rr * z) / (rr + z);
+        const float c = kappa * (rr - f);
+        const float u2 = u01(r[1]);
+        if (c * (2.0f - c) - u2 > 0.0f || logf(c / u2) + 1.0f - c >= 0.0f) {
+            const float a = acosf(fminf(fmaxf(f, -1.0f), 1.0f));
+            return wrap_pi(mode + ((u01(r[2]) < 0.5f) ? -a : a));
+        }
+    }
+    return wrap_pi(mode);
 }
 
 }  // namespace pnp

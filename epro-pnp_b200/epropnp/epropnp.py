@@ -138,14 +138,11 @@ class EProPnPBase(torch.nn.Module, metaclass=ABCMeta):
 
 class EProPnP4DoF(EProPnPBase):
     """4DoF pose [x, y, z, yaw]; proposals: translation ~ multivariate t (df 3), yaw ~ 0.75 von Mises +
-    0.25 uniform (reference epropnp.py:199-260).  The LM / GN solve (`forward`) runs natively; the 4DoF
-    AMIS kernel is not built yet and `monte_carlo_forward` says so."""
+    0.25 uniform (reference epropnp.py:199-260).  `amis_noise` = (normal3 (B,M,3), chi2 (B,M), yaw (B,M)):
+    for 4DoF the third tensor holds the yaw draws themselves (the reference draws them with numpy on the
+    host, distributions.py:61-72); without it the kernel samples yaw with Philox + Best-Fisher rejection."""
 
     dof = 4
-
-    def monte_carlo_forward(self, *args, **kwargs):
-        raise NotImplementedError("4DoF AMIS (von Mises / uniform yaw proposal) is not built yet; "
-                                  "EProPnP4DoF.forward (LM / GN solve) is available")
 
 
 class EProPnP6DoF(EProPnPBase):

@@ -35,7 +35,7 @@ enum {
     EPNP_OK = 0,
     EPNP_ERR_BAD_ARG = -1,       /* null pointer, non-positive size, dof not in {4,6}, M % I != 0 ...  */
     EPNP_ERR_TOO_MANY_POINTS = -2, /* N (and M) do not fit the 227 KB shared memory of one SM       */
-    EPNP_ERR_UNSUPPORTED = -3,   /* combination not built yet (4-DoF AMIS)                             */
+    EPNP_ERR_UNSUPPORTED = -3,   /* combination not supported by this build                            */
     EPNP_ERR_CUDA = -4,          /* a CUDA runtime call failed, see epnp_last_cuda_error()             */
     EPNP_ERR_NO_DEVICE = -5      /* no sm_100 device is current                                        */
 };
@@ -106,10 +106,13 @@ int epnp_lm_solve_f32(const float* x3d, const float* x2d, const float* w2d, cons
  * (initial_fit :288-302, gen_new/old_distr :304-315, estimate_params :317-342; proposals from
  * distributions.py:15-52 and pyro MultivariateStudentT), starting from a given local solution.
  *   noise_*: [opt] injected base noise, object-major, m = iteration * S + s:
- *            noise_normal (B, M, 3), noise_chi2 (B, M), noise_rot (B, M, 4).  All three or none;
+ *            noise_normal (B, M, 3), noise_chi2 (B, M), noise_rot (B, M, 4) for dof 6; for dof 4
+ *            (EProPnP4DoF, epropnp.py:199-260, distributions.py:55-79) noise_rot is (B, M) and holds the
+ *            YAW DRAWS themselves (the reference samples yaw with numpy on the host).  All three or none;
  *            when NULL the kernel draws Philox-4x32-10 noise keyed by (seed, obj_offset + b, m),
  *            so a sharded batch reproduces the unsharded one.
- *   proposals [opt] (B, I, 19): mode[3], L_t[6] (row-major lower), L_r[10] per AMIS iteration.  */
+ *   proposals [opt] (B, I, 19): mode[3], L_t[6] (row-major lower), L_r[10] per AMIS iteration
+ *            (dof 4: mode[3], L_t[6], yaw mode, kappa, 0...).                                     */
 int epnp_amis_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
                   const float* lb, const float* ub, const float* delta,
                   const float* pose_opt, const float* pose_cov,

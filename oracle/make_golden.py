@@ -24,7 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(HERE, "pyro_shim"))
 sys.path.insert(0, "/root/reference")
-sys.path.insert(0, os.path.join(ROOT, "epro-pnp_b200"))
+sys.path.append(os.path.join(ROOT, "epro-pnp_b200"))     # after the reference: `epropnp` must resolve to /root/reference
 warnings.filterwarnings("ignore")
 
 import pyro.distributions as shim                      # noqa: E402  (the shim)
@@ -199,6 +199,10 @@ def run_case(name, B, N, dof=6, seed=0, lm_iter=10, fast_mode=False, mc=None, z_
                     ("trans_mode", "trans_cov_tril", "rot_mode", "rot_kappa")
             for nm, bf in zip(names, stash["bufs"]):
                 out[f"{tag}_mc_{nm}"] = to_np(bf)
+            if dof == 4:
+                # 4DoF draws yaw on the host with numpy (distributions.py:61-72): no base noise to replay, so
+                # keep the drawn yaw samples of EACH run (they depend on that run's mode / kappa)
+                out["yaw_samples" if tag == "ref32" else "yaw_samples64"] = to_np(samples[..., 3].reshape(I, M // I, B))
             if tag == "ref32":
                 out["mc_samples_total"], out["mc_iters"] = M, I
                 S = M // I
@@ -207,9 +211,6 @@ def run_case(name, B, N, dof=6, seed=0, lm_iter=10, fast_mode=False, mc=None, z_
                 out["noise_chi2"] = to_np(torch.stack(tape.chi2).reshape(I, S, B))
                 if dof == 6:
                     out["noise_rot"] = to_np(torch.stack(tape.rot).reshape(I, S, B, 4))
-                else:
-                    # 4DoF draws yaw on the host with numpy: keep the drawn yaw samples themselves
-                    out["yaw_samples"] = to_np(samples[..., 3].reshape(I, S, B))
 
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **{k: v for k, v in out.items() if v is not None})

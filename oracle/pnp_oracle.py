@@ -23,6 +23,7 @@ Reference map (file:line under /root/reference/epropnp/):
     normalize / denormalize                common.py:103-136
     robust_cholesky                        epropnp.py:16-33
     amis_6dof (initial fit, mixture, refit) epropnp.py:87-196, 282-342
+    amis_4dof (von Mises / uniform yaw)     epropnp.py:199-260; distributions.py:55-79; torch VonMises
     acg_logpdf / acg sample                distributions.py:32-52
     mvt_logpdf / mvt sample                pyro.distributions.MultivariateStudentT (see pyro_shim)
 """
@@ -358,3 +359,76 @@ def monte_carlo_forward_6dof(x3d, x2d, w2d, cam: Camera, delta, pose_init, noise
     r = amis_6dof(x3d, x2d, w2d, cam, delta, pose_opt, pose_cov, noise, mc_samples, num_iter, prm.eps)
     r.update(pose_opt=pose_opt, pose_cov=pose_cov, lm_cost=cost, cost_init=cost_init)
     return r
+
+
+# ----------------------------------------------------------------------------- AMIS (4DoF)
+_I0_SMALL = [1.0, 3.5156229, 3.0899424, 1.2067492, 0.2659732, 0.360768e-1, 0.45813e-2]
+_I0_LARGE = [0.39894228, 0.1328592e-1, 0.225319e-2, -0.157565e-2, 0.916281e-2, -0.2057706e-1, 0.2635537e-1,
+             -0.1647633e-1, 0.392377e-2]
+
+
+def _poly(y, coef):
+    r = torch.full_like(y, coef[-1])
+    for c in reversed(coef[:-1]):
+        r = c + y * r
+    return r
+
+
+def log_bessel_i0(x):
+    """log I0(x) exactly as torch.distributions.von_mises._log_modified_bessel_fn(order=0) evaluates it
+    (Abramowitz-Stegun polynomials) -- this is what VonMises.log_prob, hence the reference, uses."""
+    small = _poly((x / 3.75) ** 2, _I0_SMALL).log()
+    large = x - 0.5 * x.log() + _poly(3.75 / x, _I0_LARGE).log()
+    return torch.where(x < 3.75, small, large)
+
+
+def vm_mix_logpdf(yaw, loc, kappa, uniform_mix=0.25):
+    vm = kappa * torch.cos(yaw - loc) - math.log(2 * math.pi) - log_bessel_i0(kappa) + math.log(1 - uniform_mix)
+    return torch.logaddexp(vm, torch.full_like(vm, math.log(uniform_mix / (2 * math.pi))))
+
+
+def amis_4dof(x3d, x2d, w2d, cam: Camera, delta, pose_opt, pose_cov, noise, mc_samples=512, num_iter=4, eps=1e-5):
+    """noise = (normal3 (I,S,B,3), chi2 (I,S,B), yaw draws (I,S,B)) -- the reference draws yaw with numpy on
+    the host, so the draws themselves are the injected quantity.  Returns samples (M,B,4), logw (M,B), ..."""
+    n3, c2, yaw = noise
+    I, S = num_iter, mc_samples // num_iter
+    B, dt = x3d.shape[0], x3d.dtype
+    mode = torch.zeros(I, B, 3, dtype=dt)
+    Lt = torch.zeros(I, B, 3, 3, dtype=dt)
+    rmode = torch.zeros(I, B, dtype=dt)
+    kappa = torch.zeros(I, B, dtype=dt)
+    dd = [1.0, 1.0, 4.0]
+    mode[0] = pose_opt[:, :3]
+    rmode[0] = pose_opt[:, 3]
+    Lt[0] = robust_cholesky(pose_cov[:, :3, :3], dd)
+    kappa[0] = 0.33 / pose_cov[:, 3, 3].clamp(min=eps)
+    samples = torch.zeros(I, S, B, 4, dtype=dt)
+    cost = torch.zeros(I, S, B, dtype=dt)
+    logp = torch.zeros(I, I, S, B, dtype=dt)
+    logw = None
+    for i in range(I):
+        samples[i, ..., :3] = mvt_draw(n3[i], c2[i], mode[i], Lt[i])
+        samples[i, ..., 3] = yaw[i]
+        cost[i] = evaluate(x3d, x2d, w2d, samples[i], cam, delta)["cost"]
+        logp[i, :i + 1] = mvt_logpdf(samples[:i + 1, ..., :3], mode[i], Lt[i]) \
+            + vm_mix_logpdf(samples[:i + 1, ..., 3], rmode[i], kappa[i])
+        if i > 0:
+            logp[:i, i] = mvt_logpdf(samples[i, ..., :3], mode[:i, None], Lt[:i, None]) \
+                + vm_mix_logpdf(samples[i, ..., 3], rmode[:i, None], kappa[:i, None])
+        mix = torch.logsumexp(logp[:i + 1, :i + 1], dim=0) - math.log(i + 1)
+        logw = -cost[:i + 1] - mix
+        if i == I - 1:
+            break
+        w = torch.softmax(logw.reshape(-1, B), dim=0)
+        smp = samples[:i + 1].reshape(-1, B, 4)
+        t = smp[..., :3]
+        mode[i + 1] = (w[..., None] * t).sum(0)
+        dev = t - mode[i + 1]
+        Lt[i + 1] = robust_cholesky((w[..., None, None] * dev[..., :, None] * dev[..., None, :]).sum(0), dd)
+        s_sum = (w * smp[..., 3].sin()).sum(0)
+        c_sum = (w * smp[..., 3].cos()).sum(0)
+        rmode[i + 1] = torch.atan2(s_sum, c_sum)
+        r_sq = s_sum ** 2 + c_sum ** 2
+        kappa[i + 1] = 0.33 * r_sq.sqrt().clamp(min=eps) * (2 - r_sq) / (1 - r_sq).clamp(min=eps)
+    return dict(samples=samples.reshape(I * S, B, 4), logw=logw.reshape(I * S, B), trans_mode=mode, trans_tril=Lt,
+                rot_mode=rmode, rot_kappa=kappa, cost=cost)

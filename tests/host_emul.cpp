@@ -211,6 +211,69 @@ void amis_object6(const float* x3d, const float* x2d, const float* w2d, int N, c
     }
 }
 
+void amis_object4(const float* x3d, const float* x2d, const float* w2d, int N, const Cam& cam, float delta,
+                  const float* pose_opt, const float* cov, const float* n3, const float* c2, const float* yaw,
+                  uint64_t seed, uint32_t obj, const EpnpParams& p, float* samples, float* logw, float* props) {
+    const int M = p.mc_samples, I = p.mc_iter, S = M / I;
+    std::vector<Proposal4> prop(I);
+    std::vector<float> cst(M), logp((size_t)I * M), lw(M);
+    initial_fit4(pose_opt, cov, p.amis_eps, prop[0]);
+    for (int i = 0; i < I; ++i) {
+        for (int s = 0; s < S; ++s) {
+            const int m = i * S + s;
+            float a3[3], chi2;
+            float* q = samples + 4 * m;
+            if (n3) { memcpy(a3, n3 + 3 * m, 12); chi2 = c2[m]; q[3] = yaw[m]; }
+            else { draw_base_noise_t(seed, obj, (uint32_t)m, a3, chi2); q[3] = draw_yaw(seed, obj, (uint32_t)m, s, S, prop[i].mode, prop[i].kappa); }
+            draw_translation(prop[i].mu, prop[i].lt, a3, chi2, q);
+            cst[m] = pose_cost_host<4>(x3d, x2d, w2d, N, q, cam, delta);
+            for (int j = 0; j <= i; ++j) logp[(size_t)j * M + m] = proposal_logpdf4(prop[j], q);
+        }
+        for (int m = 0; m < i * S; ++m) logp[(size_t)i * M + m] = proposal_logpdf4(prop[i], samples + 4 * m);
+        const int n = (i + 1) * S;
+        const float log_cnt = logf((float)(i + 1));
+        float mx = -INFINITY;
+        for (int m = 0; m < n; ++m) {
+            float top = logp[m];
+            for (int j = 1; j <= i; ++j) top = fmaxf(top, logp[(size_t)j * M + m]);
+            float acc = 0.f;
+            for (int j = 0; j <= i; ++j) acc += expf(logp[(size_t)j * M + m] - top);
+            lw[m] = -cst[m] - ((top + logf(acc)) - log_cnt);
+            mx = fmaxf(mx, lw[m]);
+        }
+        if (i == I - 1) { for (int m = 0; m < M; ++m) logw[m] = lw[m]; break; }
+        float accB[6] = {0, 0, 0, 0, 0, 0};
+        for (int m = 0; m < n; ++m) {
+            const float e = expf(lw[m] - mx);
+            lw[m] = e;
+            const float* s4 = samples + 4 * m;
+            accB[0] += e;
+            for (int k = 0; k < 3; ++k) accB[1 + k] = fmaf(e, s4[k], accB[1 + k]);
+            accB[4] = fmaf(e, sinf(s4[3]), accB[4]); accB[5] = fmaf(e, cosf(s4[3]), accB[5]);
+        }
+        const float inv_sum = 1.0f / accB[0];
+        const float mean[3] = {accB[1] * inv_sum, accB[2] * inv_sum, accB[3] * inv_sum};
+        float tc[6] = {0, 0, 0, 0, 0, 0};
+        for (int m = 0; m < n; ++m) {
+            const float w = lw[m] * inv_sum;
+            const float* s4 = samples + 4 * m;
+            const float d0 = s4[0] - mean[0], d1 = s4[1] - mean[1], d2 = s4[2] - mean[2];
+            tc[0] = fmaf(w * d0, d0, tc[0]); tc[1] = fmaf(w * d0, d1, tc[1]); tc[2] = fmaf(w * d0, d2, tc[2]);
+            tc[3] = fmaf(w * d1, d1, tc[3]); tc[4] = fmaf(w * d1, d2, tc[4]); tc[5] = fmaf(w * d2, d2, tc[5]);
+        }
+        refit_finish4(mean, tc, accB[4] * inv_sum, accB[5] * inv_sum, p.amis_eps, prop[i + 1]);
+    }
+    if (props) {
+        for (int i = 0; i < I; ++i) {
+            float* o = props + i * 19;
+            for (int r = 0; r < 19; ++r) o[r] = 0.f;
+            for (int r = 0; r < 3; ++r) o[r] = prop[i].mu[r];
+            for (int r = 0; r < 6; ++r) o[3 + r] = prop[i].lt[r];
+            o[9] = prop[i].mode; o[10] = prop[i].kappa;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -297,6 +360,28 @@ int emul_amis6(const float* x3d, const float* x2d, const float* w2d, const float
                      c2 ? c2 + (size_t)b * M : nullptr, n4 ? n4 + (size_t)b * M * 4 : nullptr, seed, obj_offset + b, *p,
                      samples + (size_t)b * M * 7, logw + (size_t)b * M, props ? props + (size_t)b * I * 19 : nullptr);
     }
+    return 0;
+}
+
+// 4DoF: n3 (B,M,3), c2 (B,M), yaw draws (B,M) or all NULL (Philox + Best-Fisher)
+int emul_amis4(const float* x3d, const float* x2d, const float* w2d, const float* cam, const float* lb, const float* ub,
+               const float* delta, const float* pose_opt, const float* cov, const float* n3, const float* c2,
+               const float* yaw, uint64_t seed, uint32_t obj_offset, float* samples, float* logw, float* props, int B,
+               int N, const EpnpParams* p) {
+    const int M = p->mc_samples, I = p->mc_iter;
+    for (int b = 0; b < B; ++b) {
+        const Cam c = make_cam(cam, lb, ub, b, p->z_min);
+        const float *p3 = x3d + (size_t)b * N * 3, *p2 = x2d + (size_t)b * N * 2, *pw = w2d + (size_t)b * N * 2;
+        amis_object4(p3, p2, pw, N, c, delta[b], pose_opt + b * 4, cov + b * 16, n3 ? n3 + (size_t)b * M * 3 : nullptr,
+                     c2 ? c2 + (size_t)b * M : nullptr, yaw ? yaw + (size_t)b * M : nullptr, seed, obj_offset + b, *p,
+                     samples + (size_t)b * M * 4, logw + (size_t)b * M, props ? props + (size_t)b * I * 19 : nullptr);
+    }
+    return 0;
+}
+
+// yaw draws of the production sampler, for statistical tests
+int emul_yaw(uint64_t seed, uint32_t obj, int count, int S, float mode, float kappa, float* out) {
+    for (int m = 0; m < count; ++m) out[m] = draw_yaw(seed, obj, (uint32_t)m, m % S, S, mode, kappa);
     return 0;
 }
 

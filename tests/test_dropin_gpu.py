@@ -109,8 +109,10 @@ def test_layer_forward_and_4dof(cuda_device):
     pose, cov, cost, plus = layer(x3d, x2d, w2d, camera, cost_fun, pose_init=pose_init, with_pose_cov=True)
     tol = max(1e-4, 3 * err_vs(g["ref32_lm_pose"], g["ref64_lm_pose"]))
     assert err_vs(pose.cpu().numpy(), g["ref32_lm_pose"]) < tol and cov.shape == (int(g["B"]), 4, 4)
-    with pytest.raises(NotImplementedError):
-        layer.monte_carlo_forward(x3d, x2d, w2d, camera, cost_fun, pose_init=pose_init)
+    r = layer.monte_carlo_forward(x3d, x2d, w2d, camera, cost_fun, pose_init=pose_init, force_init_solve=False,
+                                  with_cost=True, amis_seed=11)
+    assert r[3].shape == (512, int(g["B"]), 4) and r[4].shape == (512, int(g["B"])) and torch.isfinite(r[4]).all()
+    assert torch.equal(r[0], pose)
 
 
 def test_rslm_init_and_force_init_solve(cuda_device):

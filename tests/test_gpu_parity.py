@@ -130,6 +130,40 @@ def test_golden_fused_lm_amis(cuda_device, name):
     assert torch.equal(s2, out["pose_samples"]) and torch.equal(w2, out["logw"])
 
 
+def test_golden_fused_lm_amis_4dof(cuda_device):
+    """EProPnP4DoF path: LM + AMIS with the von Mises / uniform yaw proposal, the reference's own yaw draws and
+    Student-t base noise injected (golden from the unmodified reference, fp32 run)."""
+    g = load_golden("mc4_basic")
+    prob, pose0 = _problem(g, cuda_device)
+    B, M, I = int(g["B"]), int(g["mc_samples_total"]), int(g["mc_iters"])
+    p = _params(g, mc_samples=M, mc_iter=I)
+    dev = cuda_device
+    noise = (torch.from_numpy(np.transpose(g["noise_normal"], (2, 0, 1, 3)).reshape(B, -1, 3).copy()).to(dev),
+             torch.from_numpy(np.transpose(g["noise_chi2"], (2, 0, 1)).reshape(B, -1).copy()).to(dev),
+             torch.from_numpy(np.transpose(g["yaw_samples"], (2, 0, 1)).reshape(B, -1).copy()).to(dev))
+    out = native.lm_amis_fused(prob, pose0, p, noise=noise, want_cost=True, want_proposals=True)
+    floor_w = err_vs(g["ref32_mc_logw"], g["ref64_mc_logw"])
+    lw = out["logw"].transpose(0, 1).cpu().numpy()
+    smp = out["pose_samples"].transpose(0, 1).cpu().numpy()
+    assert smp.shape == (M, B, 4) and np.isfinite(lw).all()
+    assert_lm_parity(out["pose_opt"].cpu().numpy(), out["cost"].cpu().numpy(), g["ref32_mc_pose"], g["ref64_mc_cost"],
+                     max(1e-4, 3 * err_vs(g["ref32_mc_pose"], g["ref64_mc_pose"])), what="mc4 pose")
+    assert err_vs(smp, g["ref32_mc_samples"]) < 1e-4
+    assert err_vs(lw, g["ref32_mc_logw"]) < max(1e-4, 5 * floor_w)
+    pr = out["proposals"].cpu().numpy()
+    assert err_vs(pr[:, :, 9].T, g["ref32_mc_rot_mode"][..., 0]) < 1e-4
+    assert err_vs(pr[:, :, 10].T, g["ref32_mc_rot_kappa"][..., 0]) < 2e-3
+    # production sampler (Philox + Best-Fisher): deterministic per seed, healthy weights, yaw on the circle
+    a = native.lm_amis_fused(prob, pose0, p, seed=3)
+    b = native.lm_amis_fused(prob, pose0, p, seed=3)
+    assert torch.equal(a["logw"], b["logw"]) and torch.isfinite(a["logw"]).all()
+    assert a["pose_samples"][..., 3].abs().max() <= np.pi + 1e-5
+    ess = 1.0 / (torch.softmax(a["logw"], 1) ** 2).sum(1)
+    assert ess.min() > 8
+    ev = lambda r: torch.logsumexp(r["logw"], dim=1) - np.log(M)
+    assert (ev(a) - ev(out)).abs().max() < 0.5           # same evidence estimate within Monte-Carlo error
+
+
 # ------------------------------------------------------------------------------------------------ oracle
 def _oracle_run(prob_cpu, noise_cpu, M, I, dtype, lm_iter=10):
     from oracle import pnp_oracle as orc

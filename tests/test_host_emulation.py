@@ -164,6 +164,47 @@ def test_amis_formulas(emul, name, start):
     assert err_vs(np.transpose(props[:, :, 9:], (1, 0, 2)), rp) < max(1e-3, 3 * fr)
 
 
+def test_amis4_formulas(emul):
+    g = load_golden("mc4_basic")
+    B, N, x3d, x2d, w2d, cam, lb, ub, delta, pose0 = inputs(g)
+    M, I = int(g["mc_samples_total"]), int(g["mc_iters"])
+    p = params_for(g, mc_samples=M, mc_iter=I)
+    pose = np.ascontiguousarray(g["ref32_lm_pose"], np.float32)
+    cov = np.ascontiguousarray(g["ref32_lm_cov"], np.float32)
+    n3 = np.ascontiguousarray(np.transpose(g["noise_normal"], (2, 0, 1, 3)).reshape(B, -1, 3), np.float32)
+    c2 = np.ascontiguousarray(np.transpose(g["noise_chi2"], (2, 0, 1)).reshape(B, -1), np.float32)
+    yaw = np.ascontiguousarray(np.transpose(g["yaw_samples"], (2, 0, 1)).reshape(B, -1), np.float32)
+    smp = np.zeros((B, M, 4), np.float32)
+    logw = np.zeros((B, M), np.float32)
+    props = np.zeros((B, I, 19), np.float32)
+    emul.emul_amis4(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(pose), fptr(cov),
+                    fptr(n3), fptr(c2), fptr(yaw), ctypes.c_uint64(0), ctypes.c_uint32(0), fptr(smp), fptr(logw),
+                    fptr(props), B, N, ctypes.byref(p))
+    floor_w = err_vs(g["ref32_mc_logw"], g["ref64_mc_logw"])
+    # compare with the fp32 reference run (the injected yaw draws are that run's)
+    assert err_vs(logw.T, g["ref32_mc_logw"]) < max(1e-4, 5 * floor_w)
+    assert err_vs(np.transpose(smp, (1, 0, 2)), g["ref32_mc_samples"]) < 1e-4
+    assert err_vs(np.transpose(props[:, :, :3], (1, 0, 2)), g["ref32_mc_trans_mode"]) < 1e-4
+    assert err_vs(props[:, :, 9].T, g["ref32_mc_rot_mode"][..., 0]) < 1e-4
+    assert err_vs(props[:, :, 10].T, g["ref32_mc_rot_kappa"][..., 0]) < 2e-3
+
+
+def test_production_yaw_sampler(emul):
+    """Best-Fisher von Mises + 25 % uniform mixture: circular moments of the draws."""
+    n, S = 200000, 128
+    for kappa in (0.5, 4.0, 50.0, 2000.0):
+        out = np.zeros(n, np.float32)
+        emul.emul_yaw(ctypes.c_uint64(9), ctypes.c_uint32(3), n, S, ctypes.c_float(0.7), ctypes.c_float(kappa), fptr(out))
+        assert np.abs(out).max() <= np.pi + 1e-5
+        is_uniform = (np.arange(n) % S) < 32
+        u, v = out[is_uniform].astype(np.float64), out[~is_uniform].astype(np.float64)
+        assert abs(np.cos(u).mean()) < 0.02 and abs(np.sin(u).mean()) < 0.02          # flat on the circle
+        from scipy.special import i0e, i1e
+        a1 = i1e(kappa) / i0e(kappa)                                                  # mean resultant length
+        assert abs(np.cos(v - 0.7).mean() - a1) < 0.01
+        assert abs(np.sin(v - 0.7).mean()) < 0.01
+
+
 def test_production_rng_statistics(emul):
     """Philox + Box-Muller base noise: moments of the three noise families."""
     n = 200000

@@ -81,6 +81,37 @@ def test_amis_6dof(name, prec):
         assert err_vs(r["logw"], g["ref32_mc_logw"]) < max(1e-4, 3 * floor_w)
 
 
+@pytest.mark.parametrize("prec", ["ref64", "ref32"])
+def test_amis_4dof(prec):
+    g = load_golden("mc4_basic")
+    dtype = torch.float64 if prec == "ref64" else torch.float32
+    x3d, x2d, w2d, cam, delta, pose_init = _setup(g, dtype)
+    M, I = int(g["mc_samples_total"]), int(g["mc_iters"])
+    yaw_key = "yaw_samples64" if prec == "ref64" else "yaw_samples"
+    noise = tuple(torch.from_numpy(g[k]).to(dtype) for k in ("noise_normal", "noise_chi2", yaw_key))
+    pose, cov, _ = orc.lm_solve(x3d, x2d, w2d, cam, delta, pose_init, orc.LMParams(num_iter=int(g["lm_iter"])))
+    r = orc.amis_4dof(x3d, x2d, w2d, cam, delta, pose, cov, noise, M, I)
+    if prec == "ref64":
+        assert err_vs(pose, g["ref64_mc_pose"]) < 1e-8
+        assert err_vs(r["trans_mode"], g["ref64_mc_trans_mode"]) < 1e-7
+        assert err_vs(r["trans_tril"], g["ref64_mc_trans_cov_tril"]) < 1e-6
+        assert err_vs(r["rot_mode"], g["ref64_mc_rot_mode"][..., 0]) < 1e-7
+        assert err_vs(r["rot_kappa"], g["ref64_mc_rot_kappa"][..., 0]) < 1e-6
+        assert err_vs(r["samples"], g["ref64_mc_samples"]) < 1e-7
+        assert err_vs(r["logw"], g["ref64_mc_logw"]) < 1e-7
+    else:
+        floor_w = err_vs(g["ref32_mc_logw"], g["ref64_mc_logw"])
+        assert err_vs(r["logw"], g["ref32_mc_logw"]) < max(1e-4, 3 * floor_w)
+
+
+def test_bessel_polynomial_matches_torch():
+    from torch.distributions.von_mises import _log_modified_bessel_fn
+    x = torch.logspace(-3, 3, 200, dtype=torch.float64)
+    assert (orc.log_bessel_i0(x) - _log_modified_bessel_fn(x, order=0)).abs().max() < 1e-12
+    exact = torch.special.i0e(x).log() + x
+    assert (orc.log_bessel_i0(x) - exact).abs().max() < 5e-7      # the polynomial's own accuracy
+
+
 def test_student_t_density_against_scipy():
     """The un-vendored pyro piece: multivariate Student-t log density (df=3, n=3)."""
     from scipy.stats import multivariate_t
