@@ -282,8 +282,15 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
+    # warm-up: at least W steps AND at least ~0.5 s of back-to-back launches -- the first ~100 ms after an idle
+    # period run measurably slower (power-state ramp), which W = 3 steps of 1.5 ms do not cover
+    t_warm = time.time()
+    n_warm = 0
+    while n_warm < args.warmup or time.time() - t_warm < 0.5:
+        step(n_warm)
+        n_warm += 1
+        if n_warm % 16 == 0:
+            torch.cuda.synchronize()
     fence()
     if saved_stdout is not None:
         sys.stdout.flush()
@@ -358,7 +365,7 @@ def main():
         fp32_rate = fp32_lane_instr_per_object() * Bg / (kern_ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "warmup_steps_run": n_warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"fused EProPnP6DoF.monte_carlo_forward: LM({LM_ITER}) + cov + AMIS({MC_ITER}x"
                                    f"{MC_SAMPLES // MC_ITER}), B={Bg}/GPU, N={N_PTS}, M={MC_SAMPLES}, in-kernel Philox",
