@@ -863,6 +863,103 @@ __global__ void __launch_bounds__(NT) evaluate_full_kernel(const KArgs a, float*
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of the Monte-Carlo cost: for every object, sum over its poses p (pose_init and all AMIS samples)
+// of g[p] * d cost(pose p; x3d, x2d, w2d, delta) / d(x3d, x2d, w2d, delta).
+// One CTA per object; thread <-> correspondence (up to BW_PPT per thread, accumulators in registers); the
+// poses' pre-multiplied projections K[R|t] and upstream gradients are staged once in shared memory and read
+// as broadcasts, so the (pose, point) loop touches no global memory.
+constexpr int BW_PPT = 4;               // correspondences per thread and tile
+constexpr int BW_POSE_TILE = 1024;      // poses staged per tile (13 floats each)
+
+struct BwArgs {
+    const float *x3d, *x2d, *w2d, *cam, *lb, *ub, *delta;
+    const float *poses_a, *grad_a;      // (B, PA, D), (B, PA)
+    const float *poses_b, *grad_b;      // [opt] (B, PB, D), (B, PB)
+    float *gx3d, *gx2d, *gw2d, *gdelta;
+    int B, N, PA, PB;
+    float z_min;
+};
+
+template <int DOF>
+__global__ void __launch_bounds__(NT, 4) cost_backward_kernel(const BwArgs a) {
+    extern __shared__ __align__(16) float bw_smem[];
+    float* Pm = bw_smem;                                 // [tile][12]
+    float* gs = bw_smem + BW_POSE_TILE * 12;             // [tile]
+    float* red = gs + BW_POSE_TILE;                      // 2 * NW * 32
+    constexpr int PD = Dim<DOF>::POSE;
+    const int tid = threadIdx.x;
+    const int P_total = a.PA + a.PB;
+    for (int obj = blockIdx.x; obj < a.B; obj += gridDim.x) {
+        KArgs ka{};
+        ka.cam = a.cam; ka.lb = a.lb; ka.ub = a.ub; ka.p.z_min = a.z_min;
+        const Cam cam = load_cam(ka, obj);
+        const float delta = __ldg(a.delta + obj);
+        float gdelta = 0.f;
+        for (int base = 0; base < a.N; base += NT * BW_PPT) {
+            float X[BW_PPT], Y[BW_PPT], Z[BW_PPT], u[BW_PPT], v[BW_PPT], wu[BW_PPT], wv[BW_PPT], g[BW_PPT][7];
+#pragma unroll
+            for (int k = 0; k < BW_PPT; ++k) {
+                const int n = base + k * NT + tid;
+                const bool ok = n < a.N;
+                const size_t q = (size_t)obj * a.N + (ok ? n : 0);
+                X[k] = __ldg(a.x3d + q * 3); Y[k] = __ldg(a.x3d + q * 3 + 1); Z[k] = __ldg(a.x3d + q * 3 + 2);
+                u[k] = __ldg(a.x2d + q * 2); v[k] = __ldg(a.x2d + q * 2 + 1);
+                wu[k] = ok ? __ldg(a.w2d + q * 2) : 0.f; wv[k] = ok ? __ldg(a.w2d + q * 2 + 1) : 0.f;
+#pragma unroll
+                for (int c = 0; c < 7; ++c) g[k][c] = 0.f;
+            }
+            for (int p0 = 0; p0 < P_total; p0 += BW_POSE_TILE) {
+                const int np = min(BW_POSE_TILE, P_total - p0);
+                __syncthreads();                          // previous tile fully consumed
+                for (int j = tid; j < np; j += NT) {
+                    const int pi = p0 + j;
+                    const bool in_a = pi < a.PA;
+                    const float* src = in_a ? a.poses_a + ((size_t)obj * a.PA + pi) * PD
+                                            : a.poses_b + ((size_t)obj * a.PB + (pi - a.PA)) * PD;
+                    float pose[PD], R[9], Pj[12];
+#pragma unroll
+                    for (int c = 0; c < PD; ++c) pose[c] = __ldg(src + c);
+                    pose_to_rot<DOF>(pose, R);
+                    make_proj(cam.k, R, pose, Pj);
+#pragma unroll
+                    for (int c = 0; c < 12; ++c) Pm[j * 12 + c] = Pj[c];
+                    gs[j] = in_a ? __ldg(a.grad_a + (size_t)obj * a.PA + pi) : __ldg(a.grad_b + (size_t)obj * a.PB + (pi - a.PA));
+                }
+                __syncthreads();
+                for (int j = 0; j < np; ++j) {
+                    const float4 r0 = reinterpret_cast<const float4*>(Pm)[3 * j];
+                    const float4 r1 = reinterpret_cast<const float4*>(Pm)[3 * j + 1];
+                    const float4 r2 = reinterpret_cast<const float4*>(Pm)[3 * j + 2];
+                    const float Pj[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                    const float gj = gs[j];
+#pragma unroll
+                    for (int k = 0; k < BW_PPT; ++k) {
+                        gdelta += cam.bounded
+                            ? point_cost_backward<true>(Pj, cam, delta, gj, X[k], Y[k], Z[k], u[k], v[k], wu[k], wv[k], g[k], FastRcp())
+                            : point_cost_backward<false>(Pj, cam, delta, gj, X[k], Y[k], Z[k], u[k], v[k], wu[k], wv[k], g[k], FastRcp());
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < BW_PPT; ++k) {
+                const int n = base + k * NT + tid;
+                if (n < a.N) {
+                    const size_t q = (size_t)obj * a.N + n;
+                    if (a.gx3d) { a.gx3d[q * 3] = g[k][0]; a.gx3d[q * 3 + 1] = g[k][1]; a.gx3d[q * 3 + 2] = g[k][2]; }
+                    if (a.gx2d) { a.gx2d[q * 2] = g[k][3]; a.gx2d[q * 2 + 1] = g[k][4]; }
+                    if (a.gw2d) { a.gw2d[q * 2] = g[k][5]; a.gw2d[q * 2 + 1] = g[k][6]; }
+                }
+            }
+        }
+        // padded (n >= N) lanes carry zero weights: their residual is 0 -> inlier -> no delta contribution
+        float gd[1] = {gdelta};
+        __syncthreads();
+        block_sum<1>(gd, red, 0);
+        if (tid == 0 && a.gdelta) a.gdelta[obj] = gd[0];
+    }
+}
+
 // AdaptiveHuberPnPCost.set_param: delta = mean(w2d) * sqrt(var_x + var_y) * relative_delta
 __global__ void __launch_bounds__(NT) adaptive_delta_kernel(const float* x2d, const float* w2d, float rel,
                                                           float* delta, int N) {
@@ -1094,6 +1191,39 @@ int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d,
                                  (cudaStream_t)stream);
     return launch_persistent(solve_kernel<4, true, true>, a, plan_smem<4>(N, p->mc_samples, p->mc_iter, true).total_bytes,
                              (cudaStream_t)stream);
+}
+
+int epnp_cost_backward_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                           const float* lb, const float* ub, const float* delta,
+                           const float* poses_a, const float* grad_a, int PA,
+                           const float* poses_b, const float* grad_b, int PB,
+                           float* grad_x3d, float* grad_x2d, float* grad_w2d, float* grad_delta,
+                           int B, int N, int dof, float z_min, void* stream) {
+    if (!x3d || !x2d || !w2d || !cam_mats || !delta) return EPNP_ERR_BAD_ARG;
+    if ((lb == nullptr) != (ub == nullptr)) return EPNP_ERR_BAD_ARG;
+    if (B < 0 || N <= 0 || PA < 0 || PB < 0 || (dof != 4 && dof != 6)) return EPNP_ERR_BAD_ARG;
+    if ((PA > 0 && (!poses_a || !grad_a)) || (PB > 0 && (!poses_b || !grad_b))) return EPNP_ERR_BAD_ARG;
+    if (B == 0) return EPNP_OK;
+    BwArgs a{};
+    a.x3d = x3d; a.x2d = x2d; a.w2d = w2d; a.cam = cam_mats; a.lb = lb; a.ub = ub; a.delta = delta;
+    a.poses_a = poses_a; a.grad_a = grad_a; a.poses_b = poses_b; a.grad_b = grad_b; a.PA = PA; a.PB = PB;
+    a.gx3d = grad_x3d; a.gx2d = grad_x2d; a.gw2d = grad_w2d; a.gdelta = grad_delta;
+    a.B = B; a.N = N; a.z_min = z_min;
+    const int smem = (BW_POSE_TILE * 13 + 2 * NW * 32) * 4;
+    cudaError_t e;
+    int dev = 0, sms = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return cuda_fail(e);
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return cuda_fail(e);
+    const int grid = B < sms * 4 ? B : sms * 4;
+    if (dof == 6) {
+        if ((e = cudaFuncSetAttribute(cost_backward_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return cuda_fail(e);
+        cost_backward_kernel<6><<<grid, NT, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        if ((e = cudaFuncSetAttribute(cost_backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return cuda_fail(e);
+        cost_backward_kernel<4><<<grid, NT, smem, (cudaStream_t)stream>>>(a);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
 }
 
 // ---- host-buffer entry point: chunked H2D -> fused kernel -> D2H on two internal streams

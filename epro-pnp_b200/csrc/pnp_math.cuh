@@ -123,6 +123,49 @@ PNP_HD float point_cost(const float* P, const Cam& c, float delta, float half_d2
 }
 
 // ------------------------------------------------------------------------------------------------
+// Reverse mode of point_cost: given g = dL/d(cost of this pose), accumulate dL/d(X,Y,Z,u,v,wu,wv) of one
+// correspondence and dL/d(delta).  Differentiates exactly what the reference's autograd sees on the cost
+// path (camera.py:21-30 project_b, :81-93 clamps -> zero gradient where clamped, z.clamp(min) -> zero where
+// zh < z_min; cost_fun.py:8-12 Huber):
+//   d cost / d r = r * min(1, delta / s)          d cost / d delta = (s - delta) for outliers, 0 for inliers
+// grad[0..2] += dL/dX, grad[3..4] += dL/d(u,v), grad[5..6] += dL/d(wu,wv); returns dL/d delta contribution.
+template <bool BOUNDED, class Rcp>
+PNP_HD float point_cost_backward(const float* P, const Cam& c, float delta, float g,
+                                 float X, float Y, float Z, float u, float v, float wu, float wv,
+                                 float* grad, Rcp rcp) {
+    const float xh = fmaf(P[0], X, fmaf(P[1], Y, fmaf(P[2], Z, P[3])));
+    const float yh = fmaf(P[4], X, fmaf(P[5], Y, fmaf(P[6], Z, P[7])));
+    const float zh = fmaf(P[8], X, fmaf(P[9], Y, fmaf(P[10], Z, P[11])));
+    const float iz = rcp(fmaxf(zh, c.z_min));
+    const float px = xh * iz, py = yh * iz;
+    float pxc = px, pyc = py;
+    if (BOUNDED) {
+        pxc = fminf(fmaxf(px, c.lbx), c.ubx);
+        pyc = fminf(fmaxf(py, c.lby), c.uby);
+    }
+    const float ex = pxc - u, ey = pyc - v;
+    const float rx = ex * wu, ry = ey * wv;
+    const float s2 = fmaf(rx, rx, ry * ry);
+    const float s = sqrtf(s2);
+    const bool inlier = (s <= delta);
+    const float k = inlier ? g : g * (delta / s);
+    const float grx = k * rx, gry = k * ry;
+    grad[5] = fmaf(grx, ex, grad[5]);
+    grad[6] = fmaf(gry, ey, grad[6]);
+    const float gex = grx * wu, gey = gry * wv;          // dL/d(pxc - u), dL/d(pyc - v)
+    grad[3] -= gex;
+    grad[4] -= gey;
+    const float gpx = (!BOUNDED || pxc == px) ? gex : 0.f;
+    const float gpy = (!BOUNDED || pyc == py) ? gey : 0.f;
+    const float gxh = gpx * iz, gyh = gpy * iz;
+    const float gzh = (zh >= c.z_min) ? -(gxh * px + gyh * py) : 0.f;
+    grad[0] = fmaf(P[0], gxh, fmaf(P[4], gyh, fmaf(P[8], gzh, grad[0])));
+    grad[1] = fmaf(P[1], gxh, fmaf(P[5], gyh, fmaf(P[9], gzh, grad[1])));
+    grad[2] = fmaf(P[2], gxh, fmaf(P[6], gyh, fmaf(P[10], gzh, grad[2])));
+    return inlier ? 0.f : g * (s - delta);
+}
+
+// ------------------------------------------------------------------------------------------------
 // One correspondence's contribution to the Gauss-Newton normal equations:
 //   acc[0..NA)       upper triangle of J~^T J~
 //   acc[NA..NA+DOF)  J~^T r~

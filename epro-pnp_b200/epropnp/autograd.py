@@ -1,9 +1,136 @@
-"""Autograd bridge for the differentiable outputs of the layer (cost_init, Monte-Carlo cost of the
-samples -> log-weights).  SURVEY.md section 8(f1): the backward kernel is the next row after the forward
-path; until it lands, asking for gradients fails loudly instead of silently running a PyTorch path."""
+"""Autograd bridge for the differentiable outputs of the layer (reference epropnp.py:108-113):
+
+    cost_init                       d/d(x3d, x2d, w2d, delta)   native kernel (epnp_cost_backward_f32)
+    pose_sample_logweights          = -cost(samples) - mixture density; only the cost term carries gradient
+                                    (samples and proposals are built under no_grad, epropnp.py:139-140,172-179)
+                                    -> same native kernel, upstream gradient -dL/dlogw
+    evaluate_pnp(out_cost=True)     same kernel
+    pose_opt_plus                   one un-damped Gauss-Newton step at the (detached) solution; differentiated
+                                    by torch autograd through `PerspectiveCamera.project` + `HuberPnPCost.compute`
+                                    (a single evaluation, levenberg_marquardt.py:243-253 -- not the iterated path)
+
+Gradients w.r.t. poses (pose_init / stacked hypotheses) are not provided: the reference's losses never use
+them (pose_init is the ground truth, lib/train.py:178-180), and asking for them raises.
+"""
+import torch
+
+from epropnp_b200 import native
+
+
+def _delta_tensor(delta, ref):
+    if torch.is_tensor(delta):
+        return delta
+    return ref.new_tensor(float(delta))
+
+
+def _grads_to(like_list, grads):
+    """Native gradients (B,N,3) / (B,N,2) / (B,N,2) / (B) -> dtype and shape of the inputs they belong to
+    (a scalar / 1-element delta tensor receives the sum over objects)."""
+    out = []
+    for like, g in zip(like_list, grads):
+        if like is None or g is None:
+            out.append(None)
+            continue
+        g = g.to(like.dtype)
+        out.append(g.sum().reshape(like.shape) if like.numel() == 1 and g.numel() != 1 else g.reshape(like.shape))
+    return out
+
+
+class _MonteCarloForward(torch.autograd.Function):
+    """Fused LM + AMIS forward; backward = native Monte-Carlo cost gradient."""
+
+    @staticmethod
+    def forward(ctx, x3d, x2d, w2d, delta, cam_mats, lb, ub, pose_start, cost_init_pose, params, noise, seed,
+                want_cost, z_min):
+        prob = native.Problem(x3d, x2d, w2d, cam_mats, lb, ub, delta)
+        out = native.lm_amis_fused(prob, pose_start, params, noise=noise, seed=seed, want_cost=want_cost,
+                                   want_cost_init=False, want_cov=False)
+        dof = params.dof
+        cost_init = None
+        if cost_init_pose is not None:
+            cost_init = native.evaluate_cost(prob, cost_init_pose.detach().unsqueeze(0), dof, z_min)[0]
+        ctx.prob, ctx.dof, ctx.z_min = prob, dof, z_min
+        ctx.samples = out["pose_samples"]
+        ctx.cost_init_pose = None if cost_init_pose is None else cost_init_pose.detach()
+        ctx.in_like = (x3d, x2d, w2d, delta if torch.is_tensor(delta) else None)
+        ctx.needs = (x3d.requires_grad, x2d.requires_grad, w2d.requires_grad,
+                     torch.is_tensor(delta) and delta.requires_grad)
+        cost = out["cost"] if want_cost else x3d.new_zeros(0)
+        ci = cost_init if cost_init is not None else x3d.new_zeros(0)
+        dt = x3d.dtype
+        ctx.mark_non_differentiable(out["pose_opt"], cost, out["pose_samples"])
+        return out["pose_opt"].to(dt), cost.to(dt), out["pose_samples"].to(dt), out["logw"].to(dt), ci.to(dt)
+
+    @staticmethod
+    def backward(ctx, g_pose, g_cost, g_samples, g_logw, g_cost_init):
+        prob = ctx.prob
+        B = prob.B
+        if g_logw is None:
+            g_logw = torch.zeros(B, ctx.samples.shape[1], device=prob.device)
+        poses_b = grad_b = None
+        if ctx.cost_init_pose is not None and g_cost_init is not None and g_cost_init.numel() == B:
+            poses_b = ctx.cost_init_pose.reshape(B, 1, -1)
+            grad_b = g_cost_init.reshape(B, 1)
+        grads = native.cost_backward(prob, ctx.dof, ctx.z_min, ctx.samples, -g_logw.contiguous(), poses_b, grad_b,
+                                     want=ctx.needs)
+        gx3d, gx2d, gw2d, gdel = _grads_to(ctx.in_like, grads)
+        return gx3d, gx2d, gw2d, gdel, None, None, None, None, None, None, None, None, None, None
+
+
+class _CostOnly(torch.autograd.Function):
+    """evaluate_pnp(out_cost=True) with gradients w.r.t. the correspondences / delta."""
+
+    @staticmethod
+    def forward(ctx, x3d, x2d, w2d, delta, cam_mats, lb, ub, poses, dof, z_min):
+        prob = native.Problem(x3d, x2d, w2d, cam_mats, lb, ub, delta)
+        S = poses.shape[0]
+        cost = native.evaluate_cost(prob, poses, dof, z_min)                    # (S, B)
+        ctx.prob, ctx.dof, ctx.z_min = prob, dof, z_min
+        ctx.poses = poses.detach().transpose(0, 1).contiguous()                 # object-major (B, S, D)
+        ctx.in_like = (x3d, x2d, w2d, delta if torch.is_tensor(delta) else None)
+        ctx.needs = (x3d.requires_grad, x2d.requires_grad, w2d.requires_grad,
+                     torch.is_tensor(delta) and delta.requires_grad)
+        return cost.to(x3d.dtype)
+
+    @staticmethod
+    def backward(ctx, g_cost):
+        grads = native.cost_backward(ctx.prob, ctx.dof, ctx.z_min, ctx.poses, g_cost.transpose(0, 1).contiguous(),
+                                     want=ctx.needs)
+        gx3d, gx2d, gw2d, gdel = _grads_to(ctx.in_like, grads)
+        return gx3d, gx2d, gw2d, gdel, None, None, None, None, None, None
+
+
+def _no_pose_grad(pose):
+    if torch.is_tensor(pose) and pose.requires_grad:
+        raise NotImplementedError("gradients with respect to poses are not provided by the native EPro-PnP path "
+                                  "(detach the pose; the reference's losses never differentiate through it)")
 
 
 def evaluate_cost_autograd(x3d, x2d, w2d, pose, camera, cost_fun):
-    raise NotImplementedError(
-        "gradients through the native EPro-PnP cost are not built yet (forward/inference only in this "
-        "release); call under torch.no_grad() or detach the inputs")
+    """cost (*, B) of pose hypotheses with autograd w.r.t. x3d / x2d / w2d / cost_fun.delta."""
+    _no_pose_grad(pose)
+    dof = 4 if pose.size(-1) == 4 else 6
+    lead = pose.shape[:-1]
+    B = x3d.shape[0]
+    cost = _CostOnly.apply(x3d, x2d, w2d, _delta_tensor(cost_fun.delta, x2d), camera.cam_mats, camera.lb, camera.ub,
+                           pose.detach().reshape(-1, B, pose.size(-1)), dof, float(camera.z_min))
+    return cost.reshape(lead)
+
+
+def monte_carlo_autograd(x3d, x2d, w2d, camera, cost_fun, pose_start, pose_init, params, noise, seed, want_cost):
+    """-> pose_opt, cost | None, pose_samples (B,M,D), logw (B,M) [differentiable], cost_init | None [differentiable]."""
+    _no_pose_grad(pose_init)
+    pose_opt, cost, samples, logw, cost_init = _MonteCarloForward.apply(
+        x3d, x2d, w2d, _delta_tensor(cost_fun.delta, x2d), camera.cam_mats, camera.lb, camera.ub, pose_start.detach(),
+        None if pose_init is None else pose_init.detach(), params, noise, seed, bool(want_cost), float(camera.z_min))
+    return pose_opt, (cost if want_cost else None), samples, logw, (cost_init if pose_init is not None else None)
+
+
+def gn_step_autograd(solver, x3d, x2d, w2d, pose, camera, cost_fun):
+    """Differentiable un-damped Gauss-Newton increment at a detached pose (levenberg_marquardt.py:243-253)."""
+    pose = pose.detach()
+    x2d_proj, jac_cam = camera.project(x3d, pose, out_jac=True, clip_jac=True)
+    residual, _, jac = cost_fun.compute(x2d_proj, x2d, w2d, jac_cam=jac_cam, out_residual=True, out_jacobian=True)
+    jac_t = jac.transpose(-1, -2)
+    jtj = jac_t @ jac + torch.eye(solver.dof, device=jac.device, dtype=jac.dtype) * solver.eps
+    return -torch.linalg.solve(jtj, jac_t @ residual.unsqueeze(-1)).squeeze(-1)

@@ -87,9 +87,9 @@ class EProPnPBase(torch.nn.Module, metaclass=ABCMeta):
         with_cost = kwargs.pop("with_cost", False)
         if kwargs:
             raise TypeError(f"unexpected arguments {sorted(kwargs)}")
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (x3d, x2d, w2d)):
-            from .autograd import evaluate_cost_autograd
-            evaluate_cost_autograd(x3d, x2d, w2d, pose_init, camera, cost_fun)   # raises: backward not built yet
+        delta = cost_fun.delta
+        differentiable = torch.is_grad_enabled() and (any(t.requires_grad for t in (x3d, x2d, w2d)) or
+                                                      (torch.is_tensor(delta) and delta.requires_grad))
         if self.normalize:
             transform, x3d, pose_init = pnp_normalize(x3d, pose_init, detach_transformation=True)
         assert x3d.dim() == x2d.dim() == w2d.dim() == 3
@@ -115,18 +115,31 @@ class EProPnPBase(torch.nn.Module, metaclass=ABCMeta):
                                                        force_init_solve, fast_mode)
                 else:
                     start = pose_init
-                prob = native.Problem(x3d, x2d, w2d, camera.cam_mats, camera.lb, camera.ub, cost_fun.delta)
                 seed = int(amis_seed) if amis_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
-                out = native.lm_amis_fused(prob, start, self._amis_params(camera, cost_fun, fast_mode),
-                                           noise=amis_noise, seed=seed, want_cost=with_cost, want_plus=with_plus,
-                                           want_cost_init=(pose_init is not None and not needs_init_solver),
-                                           want_cov=False)
-                cast = lambda t: None if t is None else t.to(x3d.dtype)
-                pose_opt, cost, pose_opt_plus = cast(out["pose_opt"]), cast(out["cost"]), cast(out["pose_opt_plus"])
-                if cost_init is None:
-                    cost_init = cast(out["cost_init"])
-                pose_samples = cast(out["pose_samples"]).transpose(0, 1)      # (M, B, D) view
-                logw = cast(out["logw"]).transpose(0, 1)                      # (M, B) view
+                params = self._amis_params(camera, cost_fun, fast_mode)
+                if not differentiable:
+                    prob = native.Problem(x3d, x2d, w2d, camera.cam_mats, camera.lb, camera.ub, cost_fun.delta)
+                    out = native.lm_amis_fused(prob, start, params, noise=amis_noise, seed=seed, want_cost=with_cost,
+                                               want_plus=with_plus,
+                                               want_cost_init=(pose_init is not None and not needs_init_solver),
+                                               want_cov=False)
+                    cast = lambda t: None if t is None else t.to(x3d.dtype)
+                    pose_opt, cost, pose_opt_plus = cast(out["pose_opt"]), cast(out["cost"]), cast(out["pose_opt_plus"])
+                    if cost_init is None:
+                        cost_init = cast(out["cost_init"])
+                    pose_samples = cast(out["pose_samples"]).transpose(0, 1)      # (M, B, D) view
+                    logw = cast(out["logw"]).transpose(0, 1)                      # (M, B) view
+
+        if num_obj > 0 and differentiable:
+            # training path: forward = the same fused kernel, backward = native Monte-Carlo cost gradient
+            from .autograd import gn_step_autograd, monte_carlo_autograd
+            pose_opt, cost, samples_bm, logw_bm, cost_init = monte_carlo_autograd(
+                x3d, x2d, w2d, camera, cost_fun, start, pose_init, params, amis_noise, seed, with_cost)
+            pose_samples, logw = samples_bm.transpose(0, 1), logw_bm.transpose(0, 1)
+            pose_opt_plus = None
+            if with_plus:
+                step = gn_step_autograd(self.solver, x3d, x2d, w2d, pose_opt, camera, cost_fun)
+                pose_opt_plus = self.solver.pose_add(pose_opt, step, camera)
 
         if self.normalize:
             pose_opt = pnp_denormalize(transform, pose_opt)

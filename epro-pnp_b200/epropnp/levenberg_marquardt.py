@@ -64,8 +64,15 @@ class LMSolver(nn.Module):
         normalize = normalize_override if isinstance(normalize_override, bool) else self.normalize
         if normalize:
             transform, x3d, pose_init = pnp_normalize(x3d, pose_init, detach_transformation=True)
+        delta = getattr(cost_fun, "delta", None)
+        differentiable = with_pose_opt_plus and torch.is_grad_enabled() and (
+            any(t.requires_grad for t in (x3d, x2d, w2d)) or (torch.is_tensor(delta) and delta.requires_grad))
         pose_opt, pose_cov, cost, pose_opt_plus = self._solve_impl(
-            x3d, x2d, w2d, camera, cost_fun, pose_init=pose_init, with_pose_opt_plus=with_pose_opt_plus, **kwargs)
+            x3d, x2d, w2d, camera, cost_fun, pose_init=pose_init,
+            with_pose_opt_plus=with_pose_opt_plus and not differentiable, **kwargs)
+        if differentiable:       # y* (+) GN step, differentiable w.r.t. the correspondences (:66-68)
+            from .autograd import gn_step_autograd
+            pose_opt_plus = self.pose_add(pose_opt, gn_step_autograd(self, x3d, x2d, w2d, pose_opt, camera, cost_fun), camera)
         if normalize:
             pose_opt = pnp_denormalize(transform, pose_opt)
             if pose_cov is not None:

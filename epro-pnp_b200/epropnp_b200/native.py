@@ -166,6 +166,29 @@ def lm_amis_fused(prob: Problem, pose_init, params, noise=None, seed=0, obj_offs
     return out
 
 
+def cost_backward(prob: Problem, dof, z_min, poses_a, grad_a, poses_b=None, grad_b=None,
+                  want=(True, True, True, True)):
+    """sum_p grad[p] * d cost(pose p) / d (x3d, x2d, w2d, delta) for object-major pose sets
+    a: (B, PA, D) / (B, PA) and optional b: (B, PB, D) / (B, PB).  Returns (gx3d, gx2d, gw2d, gdelta), None
+    where `want` is False."""
+    B, N = prob.B, prob.N
+    poses_a, grad_a = _f32c(poses_a), _f32c(grad_a)
+    PA = poses_a.shape[1]
+    PB = 0
+    if poses_b is not None:
+        poses_b, grad_b = _f32c(poses_b), _f32c(grad_b)
+        PB = poses_b.shape[1]
+    gx3d = prob.empty(B, N, 3) if want[0] else None
+    gx2d = prob.empty(B, N, 2) if want[1] else None
+    gw2d = prob.empty(B, N, 2) if want[2] else None
+    gdel = prob.empty(B) if want[3] else None
+    with torch.cuda.device(prob.device):
+        check(lib().epnp_cost_backward_f32(*prob.common_ptrs(), ptr(poses_a), ptr(grad_a), PA, ptr(poses_b), ptr(grad_b), PB,
+                                           ptr(gx3d), ptr(gx2d), ptr(gw2d), ptr(gdel), B, N, int(dof),
+                                           ctypes.c_float(z_min), stream_ptr(prob.device)), "epnp_cost_backward_f32")
+    return gx3d, gx2d, gw2d, gdel
+
+
 def fused_workspace_bytes(B, N, params):
     return int(lib().epnp_fused_workspace_bytes(B, N, ctypes.byref(params)))
 
@@ -198,5 +221,5 @@ def lm_amis_fused_host(host, params, workspace, n_chunks=8, seed=0, obj_offset=0
     return out
 
 
-__all__ = ["Problem", "adaptive_delta", "evaluate_cost", "evaluate_full", "lm_solve", "amis", "lm_amis_fused",
+__all__ = ["Problem", "adaptive_delta", "cost_backward", "evaluate_cost", "evaluate_full", "lm_solve", "amis", "lm_amis_fused",
            "lm_amis_fused_host", "fused_workspace_bytes", "default_params", "NativeError", "capi"]

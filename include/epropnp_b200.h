@@ -132,6 +132,21 @@ int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d,
                            float* cost_init, float* pose_samples, float* logw, float* proposals,
                            int B, int N, const EpnpParams* p, void* stream);
 
+/* Backward of the differentiable outputs of monte_carlo_forward (epropnp.py:108-113: cost_init and the
+ * Monte-Carlo costs inside pose_sample_logweights; proposal densities and samples carry no gradient,
+ * epropnp.py:139-140,172-179) and of evaluate_pnp(out_cost=True) (common.py:67-100): for every object
+ *   grad_x3d/x2d/w2d/delta = sum_p grad[p] * d cost(pose p) / d (x3d, x2d, w2d, delta)
+ * over two pose sets given object-major: set a (B, PA, D) with grad_a (B, PA) -- e.g. the AMIS samples and
+ * -dL/dlogw -- and [opt] set b (B, PB, D), grad_b (B, PB) -- e.g. pose_init and dL/dcost_init.
+ * Differentiates what the reference's autograd sees: project_b (camera.py:21-30), the z / bound clamps
+ * (zero gradient where clamped, :81-93), Huber (cost_fun.py:8-12).  Outputs [opt]: (B,N,3), (B,N,2), (B,N,2), (B). */
+int epnp_cost_backward_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                           const float* lb, const float* ub, const float* delta,
+                           const float* poses_a, const float* grad_a, int PA,
+                           const float* poses_b, const float* grad_b, int PB,
+                           float* grad_x3d, float* grad_x2d, float* grad_w2d, float* grad_delta,
+                           int B, int N, int dof, float z_min, void* stream);
+
 /* Same as epnp_lm_amis_fused_f32 with HOST buffers (pinned for full speed): copies the inputs to
  * the caller-provided device workspace, runs the fused kernel and copies the results back, all on
  * `stream`, in `n_chunks` object chunks so the copies of one chunk overlap the solve of another.

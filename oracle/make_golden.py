@@ -108,7 +108,7 @@ def to_np(x):
 
 def run_case(name, B, N, dof=6, seed=0, lm_iter=10, fast_mode=False, mc=None, z_min=0.1,
              bounds=None, relative_delta=0.5, fixed_delta=None, outlier_frac=0.0, grid2d=False,
-             behind=False, normalize=False, init_noise=(0.05, 3.0), eval_samples=5):
+             behind=False, normalize=False, init_noise=(0.05, 3.0), eval_samples=5, grads=False):
     p = make_problem(B, N, seed=seed, dof=dof, outlier_frac=outlier_frac, grid2d=grid2d,
                      init_trans_noise=init_noise[0], init_rot_noise_deg=init_noise[1])
     if behind:
@@ -212,6 +212,38 @@ def run_case(name, B, N, dof=6, seed=0, lm_iter=10, fast_mode=False, mc=None, z_
                 if dof == 6:
                     out["noise_rot"] = to_np(torch.stack(tape.rot).reshape(I, S, B, 4))
 
+    if grads and mc is not None:
+        # Gradients of the reference's differentiable outputs (epropnp.py:108-113), float64, recorded noise played
+        # back: L1 = <c1, logweights> + <c2, cost_init>, L2 = <c3, pose_opt_plus>; delta depends on w2d exactly
+        # as the reference's training loop sets it (EPro-PnP-6DoF/lib/train.py:175-177).
+        tape.start_playback()
+        d = torch.float64
+        x3d = p["x3d"].to(d).requires_grad_(True)
+        x2d = p["x2d"].to(d).requires_grad_(True)
+        w2d = p["w2d"].to(d).requires_grad_(True)
+        camera, _, _, _ = build_camera_cost(p, d, z_min, bounds, relative_delta, fixed_delta)
+        cost_fun = AdaptiveHuberPnPCost(relative_delta=relative_delta)
+        cost_fun.set_param(x2d.detach(), w2d)
+        M, I = mc
+        cls = EProPnP6DoF if dof == 6 else EProPnP4DoF
+        layer = cls(mc_samples=M, num_iter=I, solver=LMSolver(dof=dof, num_iter=lm_iter))
+        if dof == 4:
+            np.random.seed(seed + 5)
+        pose_opt, _, pose_plus, samples, logw, cost_init = layer.monte_carlo_forward(
+            x3d, x2d, w2d, camera, cost_fun, pose_init=p["pose_init"].to(d), force_init_solve=False,
+            with_pose_opt_plus=True)
+        g = torch.Generator().manual_seed(seed + 99)
+        c1 = 0.01 * torch.randn(logw.shape, generator=g, dtype=d)
+        c2 = torch.randn(cost_init.shape, generator=g, dtype=d)
+        c3 = torch.randn(pose_plus.shape, generator=g, dtype=d)
+        g1 = torch.autograd.grad((c1 * logw).sum() + (c2 * cost_init).sum(), [x3d, x2d, w2d], retain_graph=True)
+        g2 = torch.autograd.grad((c3 * pose_plus).sum(), [x3d, x2d, w2d])
+        out["grad_c1"], out["grad_c2"], out["grad_c3"] = to_np(c1), to_np(c2), to_np(c3)
+        for nm, a, b in zip(("x3d", "x2d", "w2d"), g1, g2):
+            out[f"ref64_gradL1_{nm}"], out[f"ref64_gradL2_{nm}"] = to_np(a), to_np(b)
+        out["ref64_grad_pose_opt"], out["ref64_grad_pose_plus"] = to_np(pose_opt), to_np(pose_plus)
+        out["ref64_grad_logw"], out["ref64_grad_cost_init"] = to_np(logw), to_np(cost_init)
+
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **{k: v for k, v in out.items() if v is not None})
     d32, d64 = out["ref32_lm_pose"], out["ref64_lm_pose"]
@@ -236,14 +268,14 @@ def main():
              relative_delta=0.1, z_min=0.01)
     run_case("lm6_normalize", B=4, N=64, seed=16, normalize=True)
     # 6DoF AMIS
-    run_case("mc6_basic", B=4, N=64, seed=21, mc=(512, 4))
+    run_case("mc6_basic", B=4, N=64, seed=21, mc=(512, 4), grads=True)
     run_case("mc6_small", B=3, N=52, seed=22, mc=(64, 4), outlier_frac=0.05)
-    run_case("mc6_bounds", B=3, N=100, seed=23, mc=(256, 2), bounds="tensor")
+    run_case("mc6_bounds", B=3, N=100, seed=23, mc=(256, 2), bounds="tensor", grads=True)
     run_case("mc6_n512", B=2, N=512, seed=24, mc=(512, 4))
     # 4DoF
     run_case("lm4_basic", B=6, N=64, seed=31, dof=4)
     run_case("gn4_fast", B=4, N=128, seed=32, dof=4, lm_iter=5, fast_mode=True)
-    run_case("mc4_basic", B=4, N=64, seed=33, dof=4, mc=(512, 4))
+    run_case("mc4_basic", B=4, N=64, seed=33, dof=4, mc=(512, 4), grads=True)
 
 
 if __name__ == "__main__":

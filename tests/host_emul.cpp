@@ -379,6 +379,37 @@ int emul_amis4(const float* x3d, const float* x2d, const float* w2d, const float
     return 0;
 }
 
+// reverse mode of the cost: poses (B, P, D), grads (B, P) -> gx3d (B,N,3), gx2d (B,N,2), gw2d (B,N,2), gdelta (B)
+int emul_cost_backward(const float* x3d, const float* x2d, const float* w2d, const float* cam, const float* lb,
+                       const float* ub, const float* delta, const float* poses, const float* grads, float* gx3d,
+                       float* gx2d, float* gw2d, float* gdelta, int P, int B, int N, int dof, float z_min) {
+    const int PD = dof == 6 ? 7 : 4;
+    for (int b = 0; b < B; ++b) {
+        const Cam c = make_cam(cam, lb, ub, b, z_min);
+        float gd = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const size_t q = (size_t)b * N + n;
+            float g[7] = {0, 0, 0, 0, 0, 0, 0};
+            for (int p = 0; p < P; ++p) {
+                const float* pose = poses + ((size_t)b * P + p) * PD;
+                float R[9], Pj[12];
+                if (dof == 6) pose_to_rot<6>(pose, R); else pose_to_rot<4>(pose, R);
+                make_proj(c.k, R, pose, Pj);
+                const float gj = grads[(size_t)b * P + p];
+                gd += c.bounded
+                    ? point_cost_backward<true>(Pj, c, delta[b], gj, x3d[q * 3], x3d[q * 3 + 1], x3d[q * 3 + 2], x2d[q * 2],
+                                                x2d[q * 2 + 1], w2d[q * 2], w2d[q * 2 + 1], g, ExactRcp())
+                    : point_cost_backward<false>(Pj, c, delta[b], gj, x3d[q * 3], x3d[q * 3 + 1], x3d[q * 3 + 2], x2d[q * 2],
+                                                 x2d[q * 2 + 1], w2d[q * 2], w2d[q * 2 + 1], g, ExactRcp());
+            }
+            gx3d[q * 3] = g[0]; gx3d[q * 3 + 1] = g[1]; gx3d[q * 3 + 2] = g[2];
+            gx2d[q * 2] = g[3]; gx2d[q * 2 + 1] = g[4]; gw2d[q * 2] = g[5]; gw2d[q * 2 + 1] = g[6];
+        }
+        gdelta[b] = gd;
+    }
+    return 0;
+}
+
 // yaw draws of the production sampler, for statistical tests
 int emul_yaw(uint64_t seed, uint32_t obj, int count, int S, float mode, float kappa, float* out) {
     for (int m = 0; m < count; ++m) out[m] = draw_yaw(seed, obj, (uint32_t)m, m % S, S, mode, kappa);

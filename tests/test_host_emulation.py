@@ -189,6 +189,37 @@ def test_amis4_formulas(emul):
     assert err_vs(props[:, :, 10].T, g["ref32_mc_rot_kappa"][..., 0]) < 2e-3
 
 
+@pytest.mark.parametrize("name", ["lm6_basic", "lm6_bounds", "lm6_scalar_bounds_fixed_delta", "lm4_basic"])
+def test_cost_backward_math(emul, name):
+    """Reverse mode of the cost (what the native backward kernel inlines) against torch autograd of the
+    pinned oracle in float64: d sum_p g_p cost(pose_p) / d(x3d, x2d, w2d, delta)."""
+    from oracle import pnp_oracle as orc
+    from conftest import golden_bounds
+    g = load_golden(name)
+    B, N, x3d, x2d, w2d, cam, lb, ub, delta, pose0 = inputs(g)
+    dof = int(g["dof"])
+    poses = np.ascontiguousarray(np.transpose(g["eval_poses"], (1, 0, 2)), np.float32)       # (B, P, D)
+    P = poses.shape[1]
+    rng = np.random.default_rng(5)
+    up = rng.standard_normal((B, P)).astype(np.float32)
+    gx3d = np.zeros((B, N, 3), np.float32); gx2d = np.zeros((B, N, 2), np.float32)
+    gw2d = np.zeros((B, N, 2), np.float32); gdel = np.zeros(B, np.float32)
+    emul.emul_cost_backward(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(poses),
+                            fptr(up), fptr(gx3d), fptr(gx2d), fptr(gw2d), fptr(gdel), P, B, N, dof,
+                            ctypes.c_float(float(g["z_min"])))
+    d = torch.float64
+    t3, t2, tw = (torch.from_numpy(a).to(d).requires_grad_(True) for a in (x3d, x2d, w2d))
+    td = torch.from_numpy(delta).to(d).requires_grad_(True)
+    lb_o, ub_o = golden_bounds(g, d)
+    ocam = orc.Camera(torch.from_numpy(cam).to(d), float(g["z_min"]), lb_o, ub_o)
+    cost = orc.evaluate(t3, t2, tw, torch.from_numpy(g["eval_poses"]).to(d), ocam, td)["cost"]        # (P, B)
+    (cost * torch.from_numpy(up.T.copy()).to(d)).sum().backward()
+    assert err_vs(gx3d, t3.grad.numpy()) < 2e-4
+    assert err_vs(gx2d, t2.grad.numpy()) < 2e-4
+    assert err_vs(gw2d, tw.grad.numpy()) < 2e-4
+    assert err_vs(gdel, td.grad.numpy()) < 2e-4
+
+
 def test_production_yaw_sampler(emul):
     """Best-Fisher von Mises + 25 % uniform mixture: circular moments of the draws."""
     n, S = 200000, 128

@@ -57,6 +57,18 @@ def main():
         ms = timed(lambda: native.lm_solve(prob, p0, p, want_cov=True), iters=10)
         out.append(dict(config="#4 dense GN(3) only (test-time path, lib/test.py:209-211), N=4096", B=B, ms=ms,
                         objects_per_s=B / ms * 1e3, hbm_gbs=B * 114932 / ms / 1e6))
+    # training step: fused forward + native Monte-Carlo cost backward (513 poses per object)
+    for B in (1024, 4096):
+        prob, p0 = setup(B, 512, 0.5)
+        p = native.default_params(6, lm_iter=10, mc_samples=512, mc_iter=4)
+        fw = native.lm_amis_fused(prob, p0, p, seed=1, want_cov=False)
+        gl = torch.randn(B, 512, device=dev)
+        gc = torch.randn(B, 1, device=dev)
+        ms_b = timed(lambda: native.cost_backward(prob, 6, 0.1, fw["pose_samples"], gl, p0.reshape(B, 1, 7), gc))
+        ms_f = timed(lambda: native.lm_amis_fused(prob, p0, p, seed=1, want_cov=False))
+        out.append(dict(config="training step: fused forward + MC-cost backward, N=512, M=512", B=B, ms_forward=ms_f,
+                        ms_backward=ms_b, objects_per_s=B / (ms_f + ms_b) * 1e3,
+                        backward_pose_point_pairs_per_s=B * 513 * 512 / ms_b * 1e3))
     S = 128
     prob, p0 = setup(4096, 512, 0.5)
     poses = p0[None].repeat(S, 1, 1).contiguous()
