@@ -142,10 +142,12 @@ __device__ __forceinline__ void store_point(float* pts, int n, float X, float Y,
     float* p = pts + (n >> 1) * 16 + (n & 1);
     p[0] = X; p[2] = Y; p[4] = Z; p[6] = -u; p[8] = -v; p[10] = wu; p[12] = wv;
 }
-// odd N: the second half of the last pair is a zero-weight copy of the first (contributes exactly 0)
-__device__ __forceinline__ void pad_last_pair(float* pts, int N) {
-    float* p = pts + (N >> 1) * 16;
-    p[1] = p[0]; p[3] = p[2]; p[5] = p[4]; p[7] = p[6]; p[9] = p[8]; p[11] = 0.f; p[13] = 0.f;
+// odd N: the second half of the last pair is a zero-weight copy of the last point (contributes exactly 0);
+// written by the SAME thread that stores point N-1, so no other thread's data is read
+__device__ __forceinline__ void store_point_padded(float* pts, int n, int N, float X, float Y, float Z, float u, float v,
+                                                   float wu, float wv) {
+    store_point(pts, n, X, Y, Z, u, v, wu, wv);
+    if ((N & 1) && n == N - 1) store_point(pts, n + 1, X, Y, Z, u, v, 0.f, 0.f);
 }
 struct PointRec { float X, Y, Z, u, v, wu, wv; };
 __device__ __forceinline__ PointRec load_point(const float* pts, int n) {
@@ -204,9 +206,8 @@ struct Loader {
                 for (int n = tid; n < npts; n += NT) {
                     const float2 uv = reinterpret_cast<const float2*>(st + CH * 3)[n];
                     const float2 w = reinterpret_cast<const float2*>(st + CH * 5)[n];
-                    store_point(pts, k * CH + n, st[3 * n], st[3 * n + 1], st[3 * n + 2], uv.x, uv.y, w.x, w.y);
+                    store_point_padded(pts, k * CH + n, a.N, st[3 * n], st[3 * n + 1], st[3 * n + 2], uv.x, uv.y, w.x, w.y);
                 }
-                if (k == nch - 1 && (a.N & 1) && tid == 0) pad_last_pair(pts, a.N);
                 __syncthreads();            // slot drained (and, after the last chunk, pts complete)
                 if (tid == 0 && c + 2 < total) { fence_proxy_async(); issue(c + 2); }
             }
@@ -215,9 +216,8 @@ struct Loader {
             const float* g2 = a.x2d + (size_t)obj * a.N * 2;
             const float* gw = a.w2d + (size_t)obj * a.N * 2;
             for (int n = tid; n < a.N; n += NT)
-                store_point(pts, n, __ldg(g3 + 3 * n), __ldg(g3 + 3 * n + 1), __ldg(g3 + 3 * n + 2), __ldg(g2 + 2 * n),
-                            __ldg(g2 + 2 * n + 1), __ldg(gw + 2 * n), __ldg(gw + 2 * n + 1));
-            if ((a.N & 1) && tid == 0) pad_last_pair(pts, a.N);
+                store_point_padded(pts, n, a.N, __ldg(g3 + 3 * n), __ldg(g3 + 3 * n + 1), __ldg(g3 + 3 * n + 2),
+                                   __ldg(g2 + 2 * n), __ldg(g2 + 2 * n + 1), __ldg(gw + 2 * n), __ldg(gw + 2 * n + 1));
             __syncthreads();
         }
     }

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Small driver for compute-sanitizer: one call of every kernel family on tiny problems (6DoF / 4DoF,
+TMA and plain loaders, bounded / unbounded, AMIS-only, fused, cost, full evaluate, backward)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "epro-pnp_b200"))
+import torch  # noqa: E402
+from epropnp_b200 import native  # noqa: E402
+from epropnp_b200.synth import make_problem  # noqa: E402
+
+dev = torch.device("cuda:0")
+for dof, N, B, bounded in ((6, 64, 5, False), (6, 130, 3, True), (6, 51, 4, False), (4, 64, 4, True)):
+    pc = make_problem(B, N, seed=dof + N, dof=dof)
+    d = {k: v.to(dev) for k, v in pc.items()}
+    delta = native.adaptive_delta(d["x2d"], d["w2d"], 0.5)
+    lb = ub = None
+    if bounded:
+        lb = d["x2d"].min(1).values + 5
+        ub = d["x2d"].max(1).values - 5
+    prob = native.Problem(d["x3d"], d["x2d"], d["w2d"], d["cam_mats"], lb, ub, delta)
+    D = 7 if dof == 6 else 4
+    p = native.default_params(dof, mc_samples=128, mc_iter=4)
+    lm = native.lm_solve(prob, d["pose_init"], p, want_cov=True, want_cost=True, want_plus=True, want_cost_init=True)
+    s, w, _ = native.amis(prob, lm["pose_opt"], lm["pose_cov"], p, seed=1, want_proposals=True)
+    out = native.lm_amis_fused(prob, d["pose_init"], p, seed=1, want_cost=True)
+    c = native.evaluate_cost(prob, out["pose_samples"].transpose(0, 1).contiguous()[:9], dof, 0.1)
+    native.evaluate_full(prob, d["pose_init"], dof, 0.1, 1e-10, True, True, True, True)
+    g = native.cost_backward(prob, dof, 0.1, out["pose_samples"], torch.randn(B, 128, device=dev),
+                             d["pose_init"].reshape(B, 1, D), torch.randn(B, 1, device=dev))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out["logw"]).all() and all(torch.isfinite(t).all() for t in g)
+print("sanitize driver finished")
