@@ -1258,6 +1258,28 @@ size_t epnp_fused_workspace_bytes(int B, int N, const EpnpParams* p) {
     return ws_layout(B, N, p).total;
 }
 
+// Helper streams of the host-buffer entry point: one copy-in, two compute, one copy-out stream per host
+// thread, created on first use and kept for the life of the thread (the only resource the library owns;
+// creating and destroying four streams per call costs more than a whole chunk of work).
+struct HostPipe {
+    cudaStream_t in = nullptr, k[2] = {nullptr, nullptr}, out = nullptr;
+    int device = -1;
+    cudaError_t ensure() {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev == device && in) return cudaSuccess;
+        if (in) { cudaStreamDestroy(in); cudaStreamDestroy(k[0]); cudaStreamDestroy(k[1]); cudaStreamDestroy(out); in = nullptr; }
+        if ((e = cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&k[0], cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&k[1], cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if ((e = cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        device = dev;
+        return cudaSuccess;
+    }
+};
+static thread_local HostPipe g_pipe;
+
 int epnp_lm_amis_fused_host_f32(const float* x3d_host, const float* x2d_host, const float* w2d_host,
                                 const float* cam_mats_host, const float* lb_host, const float* ub_host,
                                 const float* delta_host, const float* pose_init_host,
@@ -1276,33 +1298,38 @@ int epnp_lm_amis_fused_host_f32(const float* x3d_host, const float* x2d_host, co
     if (workspace_bytes < w.total) return EPNP_ERR_BAD_ARG;
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > B) n_chunks = B;
+    if (n_chunks > 64) n_chunks = 64;
     cudaStream_t stream = (cudaStream_t)stream_;
     char* ws = (char*)workspace;
     const size_t D = (p->dof == 6) ? 7 : 4, dof = p->dof, M = p->mc_samples;
-    // Two helper streams forked from / joined to `stream` with events: chunk c runs on helper c&1, so the
-    // H2D of chunk c+1 overlaps the kernel of chunk c and the D2H of chunk c-1.
-    cudaStream_t hs[2] = {nullptr, nullptr};
-    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    // Three-stage pipeline over object chunks: copy-in stream -> {compute 0, compute 1} -> copy-out stream, chained
+    // by per-chunk events, so all H2D copies run back to back on one DMA engine, all D2H copies on the other, and
+    // the solve of chunk c overlaps both (and the tail of chunk c-1 on the other compute stream).
     cudaError_t e = cudaSuccess;
     int rc = EPNP_OK;
+    cudaEvent_t fork = nullptr, ev_in[64], ev_k[64], done[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < 64; ++i) { ev_in[i] = nullptr; ev_k[i] = nullptr; }
 #define EPNP_TRY(x) do { e = (x); if (e != cudaSuccess) { rc = cuda_fail(e); goto done; } } while (0)
+    EPNP_TRY(g_pipe.ensure());
     EPNP_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
     EPNP_TRY(cudaEventRecord(fork, stream));
-    for (int i = 0; i < 2; ++i) {
-        EPNP_TRY(cudaStreamCreateWithFlags(&hs[i], cudaStreamNonBlocking));
-        EPNP_TRY(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
-        EPNP_TRY(cudaStreamWaitEvent(hs[i], fork, 0));
-    }
+    EPNP_TRY(cudaStreamWaitEvent(g_pipe.in, fork, 0));
+    EPNP_TRY(cudaStreamWaitEvent(g_pipe.k[0], fork, 0));
+    EPNP_TRY(cudaStreamWaitEvent(g_pipe.k[1], fork, 0));
+    EPNP_TRY(cudaStreamWaitEvent(g_pipe.out, fork, 0));
     for (int c = 0; c < n_chunks; ++c) {
         const int b0 = (int)((long long)B * c / n_chunks), b1 = (int)((long long)B * (c + 1) / n_chunks);
         const int nb = b1 - b0;
         if (nb <= 0) continue;
-        cudaStream_t s = hs[c & 1];
-#define H2D(field, host, per) EPNP_TRY(cudaMemcpyAsync(ws + w.field + (size_t)b0 * (per) * 4, (host) + (size_t)b0 * (per), (size_t)nb * (per) * 4, cudaMemcpyHostToDevice, s))
-#define D2H(field, host, per) EPNP_TRY(cudaMemcpyAsync((host) + (size_t)b0 * (per), ws + w.field + (size_t)b0 * (per) * 4, (size_t)nb * (per) * 4, cudaMemcpyDeviceToHost, s))
+        cudaStream_t sk = g_pipe.k[c & 1];
+#define H2D(field, host, per) EPNP_TRY(cudaMemcpyAsync(ws + w.field + (size_t)b0 * (per) * 4, (host) + (size_t)b0 * (per), (size_t)nb * (per) * 4, cudaMemcpyHostToDevice, g_pipe.in))
+#define D2H(field, host, per) EPNP_TRY(cudaMemcpyAsync((host) + (size_t)b0 * (per), ws + w.field + (size_t)b0 * (per) * 4, (size_t)nb * (per) * 4, cudaMemcpyDeviceToHost, g_pipe.out))
         H2D(x3d, x3d_host, (size_t)N * 3); H2D(x2d, x2d_host, (size_t)N * 2); H2D(w2d, w2d_host, (size_t)N * 2);
         H2D(cam, cam_mats_host, 9); H2D(delta, delta_host, 1); H2D(pose_init, pose_init_host, D);
         if (lb_host) { H2D(lb, lb_host, 2); H2D(ub, ub_host, 2); }
+        EPNP_TRY(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+        EPNP_TRY(cudaEventRecord(ev_in[c], g_pipe.in));
+        EPNP_TRY(cudaStreamWaitEvent(sk, ev_in[c], 0));
         rc = epnp_lm_amis_fused_f32(
             (float*)(ws + w.x3d) + (size_t)b0 * N * 3, (float*)(ws + w.x2d) + (size_t)b0 * N * 2,
             (float*)(ws + w.w2d) + (size_t)b0 * N * 2, (float*)(ws + w.cam) + (size_t)b0 * 9,
@@ -1312,8 +1339,11 @@ int epnp_lm_amis_fused_host_f32(const float* x3d_host, const float* x2d_host, co
             (float*)(ws + w.pose_opt) + (size_t)b0 * D, (float*)(ws + w.pose_cov) + (size_t)b0 * dof * dof,
             (float*)(ws + w.cost) + b0, nullptr, nullptr,
             (float*)(ws + w.samples) + (size_t)b0 * M * D, (float*)(ws + w.logw) + (size_t)b0 * M, nullptr,
-            nb, N, p, s);
+            nb, N, p, sk);
         if (rc != EPNP_OK) goto done;
+        EPNP_TRY(cudaEventCreateWithFlags(&ev_k[c], cudaEventDisableTiming));
+        EPNP_TRY(cudaEventRecord(ev_k[c], sk));
+        EPNP_TRY(cudaStreamWaitEvent(g_pipe.out, ev_k[c], 0));
         D2H(pose_opt, pose_opt_host, D); D2H(logw, logw_host, M);
         if (pose_cov_host) D2H(pose_cov, pose_cov_host, dof * dof);
         if (cost_host) D2H(cost, cost_host, 1);
@@ -1321,17 +1351,19 @@ int epnp_lm_amis_fused_host_f32(const float* x3d_host, const float* x2d_host, co
 #undef H2D
 #undef D2H
     }
-    for (int i = 0; i < 2; ++i) {
-        EPNP_TRY(cudaEventRecord(join[i], hs[i]));
-        EPNP_TRY(cudaStreamWaitEvent(stream, join[i], 0));
+    {   // join: the caller's stream waits for everything the helpers were given
+        cudaStream_t all[3] = {g_pipe.out, g_pipe.k[0], g_pipe.k[1]};
+        for (int i = 0; i < 3; ++i) {
+            EPNP_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+            EPNP_TRY(cudaEventRecord(done[i], all[i]));
+            EPNP_TRY(cudaStreamWaitEvent(stream, done[i], 0));
+        }
     }
 done:
 #undef EPNP_TRY
-    // helper streams/events are released once their work is done (cudaStreamDestroy defers)
-    for (int i = 0; i < 2; ++i) {
-        if (hs[i]) cudaStreamDestroy(hs[i]);
-        if (join[i]) cudaEventDestroy(join[i]);
-    }
+    // events are released once recorded work has drained (cudaEventDestroy defers)
+    for (int i = 0; i < 64; ++i) { if (ev_in[i]) cudaEventDestroy(ev_in[i]); if (ev_k[i]) cudaEventDestroy(ev_k[i]); }
+    for (int i = 0; i < 3; ++i) if (done[i]) cudaEventDestroy(done[i]);
     if (fork) cudaEventDestroy(fork);
     return rc;
 }

@@ -149,7 +149,9 @@ int epnp_cost_backward_f32(const float* x3d, const float* x2d, const float* w2d,
 
 /* Same as epnp_lm_amis_fused_f32 with HOST buffers (pinned for full speed): copies the inputs to
  * the caller-provided device workspace, runs the fused kernel and copies the results back, all on
- * `stream`, in `n_chunks` object chunks so the copies of one chunk overlap the solve of another.
+ * `stream`, in `n_chunks` object chunks through a copy-in / solve / copy-out pipeline (helper streams owned by
+ * the calling host thread, created on first use -- the only resource the library keeps).  Choose n_chunks so a
+ * chunk still holds >= ~1000 objects (two waves of the persistent grid); 4 for B = 4096.
  * workspace: device memory of at least epnp_fused_workspace_bytes(B, N, p) bytes.
  * Outputs [opt] as above (pose_samples_host may be NULL to skip the largest copy).              */
 size_t epnp_fused_workspace_bytes(int B, int N, const EpnpParams* p);
