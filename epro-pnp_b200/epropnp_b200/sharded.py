@@ -47,3 +47,36 @@ def gather_objects(local, num_obj, group=None):
 def gather_results(result, num_obj, keys=("pose_opt", "logw", "pose_cov", "cost"), group=None):
     """result: dict of local object-major tensors (as returned by native.lm_amis_fused)."""
     return {k: gather_objects(result[k], num_obj, group) for k in keys if result.get(k) is not None}
+
+
+class PendingGather:
+    """Handle of an asynchronous gather: `.wait()` makes the current stream wait for it and returns the dict."""
+
+    def __init__(self, tensors, works):
+        self.tensors, self.works = tensors, works
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+        return self.tensors
+
+
+def gather_results_async(result, num_obj, keys=("pose_opt", "logw"), group=None):
+    """Same gather, issued asynchronously (equal shards only): NCCL runs it on its own stream after the work
+    already enqueued on the current stream, so the NEXT batch's solve overlaps this batch's exchange.  Objects of
+    different batches are independent; nothing inside a solve ever waits for a collective."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return PendingGather({k: result[k] for k in keys if result.get(k) is not None}, [])
+    world = dist.get_world_size(group)
+    if len(set(shard_sizes(num_obj, world))) != 1:
+        return PendingGather(gather_results(result, num_obj, keys, group), [])
+    outs, works = {}, []
+    for k in keys:
+        local = result.get(k)
+        if local is None:
+            continue
+        out = local.new_empty((num_obj,) + tuple(local.shape[1:]))
+        works.append(dist.all_gather_into_tensor(out, local.contiguous(), group=group, async_op=True))
+        outs[k] = out
+    return PendingGather(outs, works)

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from epropnp_b200.sharded import gather_objects, gather_results, shard_range, shard_sizes
+from epropnp_b200.sharded import gather_objects, gather_results, gather_results_async, shard_range, shard_sizes
 
 
 def test_shard_range_partitions():
@@ -39,6 +39,9 @@ def _worker(rank, world, port, num_obj, q):
         got = gather_results(local, num_obj)
         ok = torch.equal(got["pose_opt"], full_pose) and torch.equal(got["logw"], full_logw) and "cost" not in got
         ok = ok and torch.equal(gather_objects(full_pose[b:e].clone(), num_obj), full_pose)
+        pend = gather_results_async(local, num_obj)
+        got2 = pend.wait()
+        ok = ok and torch.equal(got2["pose_opt"], full_pose) and torch.equal(got2["logw"], full_logw)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
