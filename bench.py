@@ -325,11 +325,18 @@ def main():
     t_warm = time.time()
     n_warm = 0
     out = None
-    while n_warm < args.warmup or time.time() - t_warm < 0.5:
+    while True:
         out = step(n_warm)       # same liveness pattern as the timed loop (previous outputs alive while the next are
         n_warm += 1              # allocated), so torch's caching allocator is primed and never calls cudaMalloc later
         if n_warm % 16 == 0:
             torch.cuda.synchronize()
+            # the stop decision must be COLLECTIVE: every rank has to run the same number of steps (= the same number
+            # of gathers); ranks deciding on their own wall clocks deadlock the next collective
+            flag = torch.tensor([1.0 if (n_warm >= args.warmup and time.time() - t_warm >= 0.5) else 0.0], device=dev)
+            if world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if flag.item() > 0.5:
+                break
     drain()
     fence()
     if saved_stdout is not None:
