@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "pnp_math.cuh"
 
 namespace {
@@ -1015,7 +1017,16 @@ int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream) 
     // persistent grid, balanced: every CTA gets the same number of objects (+-1)
     a.num_sms = sms;
     const int slots = sms * occ;
-    const int rounds = (a.B + slots - 1) / slots;
+    int rounds = (a.B + slots - 1) / slots;
+    // Launch-policy knob (environment, read per call): EPNP_MAX_OBJECTS_PER_CTA = k caps how many objects one CTA
+    // works through.  Default: fully persistent (grid = resident slots).  k = 1 gives one CTA per object: SM slots
+    // free up continuously, so a concurrently enqueued kernel of another stream (the NCCL gather of the previous
+    // batch in the multi-GPU pipeline) can start at once instead of waiting for the whole grid to drain; the price
+    // is that the next object's TMA prefetch no longer overlaps the current solve (~1.5 %).
+    if (const char* env = std::getenv("EPNP_MAX_OBJECTS_PER_CTA")) {
+        const int k = std::atoi(env);
+        if (k >= 1 && k < rounds) rounds = k;
+    }
     const int grid = (a.B + rounds - 1) / rounds;
     kern<<<grid, NT, smem_bytes, stream>>>(a);
     e = cudaGetLastError();
