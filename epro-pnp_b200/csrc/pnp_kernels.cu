@@ -1015,7 +1015,6 @@ int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream) 
     if (e != cudaSuccess) return cuda_fail(e);
     if (occ < 1) return EPNP_ERR_TOO_MANY_POINTS;
     a.num_sms = sms;
-    const int slots = sms * occ;
     // Work distribution.  Default: ONE object per CTA (grid = B) and the hardware scheduler hands CTAs to SMs as
     // slots free up -- measured 5 % faster than a persistent grid at B = 4096 (2.93 vs 2.79 M objects/s): the CTAs'
     // serial and parallel phases de-synchronise and there is no lock-step tail, which outweighs losing the
