@@ -15,7 +15,7 @@ of poses + log-weights.  Prints ONE JSON line (rank 0).
              pose / covariance / cost / log-weights / samples inside the timed region
   roofline   algorithmic HBM bytes per launch / launch time vs the measured copy bandwidth
              (MEASURED_PEAKS.json).  The kernel is FP32-pipe bound, not HBM bound:
-             `fp32` reports the lane-instruction estimate against 148 SM x 128 lanes x clock.
+             `issue` reports executed warp-instructions (ncu) per second against 148 SM x 4 schedulers x clock.
   cpu_baseline   oracle/pnp_oracle.py (same algorithm as the reference's PyTorch layer, batched torch ops,
              all host threads) on a bounded sample of the same workload; rank 0, N = 1 only.
 """
@@ -46,10 +46,9 @@ def algorithmic_bytes_per_object(n=N_PTS, m=MC_SAMPLES):
     return 28 * n + 36 + 4 + 28 + 28 + 144 + 4 + 28 * m + 4 * m
 
 
-def fp32_lane_instr_per_object(n=N_PTS, m=MC_SAMPLES, k=LM_ITER):
-    """~26 issue slots per (sample, point) pair in the AMIS sweep, ~150 per point per LM
-    evaluation (K + 1 evaluations)."""
-    return 26 * n * m + 150 * n * (k + 1)
+# Executed warp-instructions per object of the fused kernel at (N, M, K) = (512, 512, 10), from the committed
+# `ncu --set full` capture (profiles/r1_final_fused_ncu_raw_metrics.json: smsp__inst_executed.sum / 4096 objects).
+WARP_INSTR_PER_OBJECT = 954271847 / 4096.0
 
 
 def load_peaks():
@@ -404,8 +403,8 @@ def main():
         per_launch_bytes = algorithmic_bytes_per_object() * Bg
         achieved = per_launch_bytes / (kern_ms * 1e-3) / 1e9
         clk = (clocks or {}).get("sm_mhz") or sm_max
-        fp32_peak = 148 * 128 * clk * 1e6
-        fp32_rate = fp32_lane_instr_per_object() * Bg / (kern_ms * 1e-3)
+        issue_peak = 148 * 4 * clk * 1e6                      # one warp-instruction per SM sub-partition per cycle
+        issue_rate = WARP_INSTR_PER_OBJECT * Bg / (kern_ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "warmup_steps_run": n_warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -417,9 +416,11 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(), "peak_source": peak_src,
                          "bytes_per_object": algorithmic_bytes_per_object(), "kernel_ms": kern_ms,
-                         "note": "FP32-pipe bound, not HBM bound: see fp32"},
-            "fp32": {"lane_instr_per_object_est": fp32_lane_instr_per_object(), "achieved_lane_instr_per_s": fp32_rate,
-                     "peak_lane_instr_per_s": fp32_peak, "frac": fp32_rate / fp32_peak, "sm_mhz_used": clk},
+                         "note": "issue / FP32-pipe bound, not HBM bound: see the issue block"},
+            "issue": {"bound": "warp-instruction issue / FP32 pipe (the binding resource, see DESIGN.md section 4)",
+                      "warp_instr_per_object": WARP_INSTR_PER_OBJECT, "achieved_warp_instr_per_s": issue_rate,
+                      "peak_warp_instr_per_s": issue_peak, "frac": issue_rate / issue_peak, "sm_mhz_used": clk,
+                      "source": "instruction count from the committed ncu capture, time from this run"},
             "clocks": clocks, "gpu_launches": args.steps * world,
             "kernel": "solve_kernel<6,true,true> (libepropnp_b200.so)",
         }

@@ -151,14 +151,6 @@ __device__ __forceinline__ void store_point_padded(float* pts, int n, int N, flo
     store_point(pts, n, X, Y, Z, u, v, wu, wv);
     if ((N & 1) && n == N - 1) store_point(pts, n + 1, X, Y, Z, u, v, 0.f, 0.f);
 }
-struct PointRec { float X, Y, Z, u, v, wu, wv; };
-__device__ __forceinline__ PointRec load_point(const float* pts, int n) {
-    const float* p = pts + (n >> 1) * 16 + (n & 1);
-    PointRec r;
-    r.X = p[0]; r.Y = p[2]; r.Z = p[4]; r.u = -p[6]; r.v = -p[8]; r.wu = p[10]; r.wv = p[12];
-    return r;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Correspondence loader: TMA ring (or plain loads when pointers / N break the 16-byte rules).
 struct Loader {
