@@ -866,6 +866,56 @@ __global__ void __launch_bounds__(NT) evaluate_full_kernel(const KArgs a, float*
 constexpr int BW_PPT = 4;               // correspondences per thread and tile
 constexpr int BW_POSE_TILE = 1024;      // poses staged per tile (13 floats each)
 
+struct FastRsqrt {
+    __device__ __forceinline__ float operator()(float x) const { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+};
+
+// Reverse mode of the cost for TWO correspondences at once (packed fp32x2; same math per half as
+// pnp::point_cost_backward, with s = s2 * rsqrt(s2) and delta / s = delta * rsqrt(s2) from one MUFU.RSQ).
+// g[0..2] += dL/d(X,Y,Z), g[3..4] += dL/d(u,v), g[5..6] += dL/d(wu,wv); gd += dL/d delta (both halves).
+template <bool BOUNDED>
+__device__ __forceinline__ void pair_cost_backward(const float (&P)[12], const Cam& cam, float delta, float gj,
+                                                   float2 X, float2 Y, float2 Z, float2 nu, float2 nv, float2 wu,
+                                                   float2 wv, float2 (&g)[7], float2& gd) {
+    const float2 xh = __ffma2_rn(splat(P[0]), X, __ffma2_rn(splat(P[1]), Y, __ffma2_rn(splat(P[2]), Z, splat(P[3]))));
+    const float2 yh = __ffma2_rn(splat(P[4]), X, __ffma2_rn(splat(P[5]), Y, __ffma2_rn(splat(P[6]), Z, splat(P[7]))));
+    const float2 zh = __ffma2_rn(splat(P[8]), X, __ffma2_rn(splat(P[9]), Y, __ffma2_rn(splat(P[10]), Z, splat(P[11]))));
+    const float2 iz = make_float2(FastRcp()(fmaxf(zh.x, cam.z_min)), FastRcp()(fmaxf(zh.y, cam.z_min)));
+    const float2 px = __fmul2_rn(xh, iz), py = __fmul2_rn(yh, iz);
+    float2 pxc = px, pyc = py;
+    if (BOUNDED) {
+        pxc.x = fminf(fmaxf(px.x, cam.lbx), cam.ubx); pxc.y = fminf(fmaxf(px.y, cam.lbx), cam.ubx);
+        pyc.x = fminf(fmaxf(py.x, cam.lby), cam.uby); pyc.y = fminf(fmaxf(py.y, cam.lby), cam.uby);
+    }
+    const float2 ex = __fadd2_rn(pxc, nu), ey = __fadd2_rn(pyc, nv);
+    const float2 rx = __fmul2_rn(ex, wu), ry = __fmul2_rn(ey, wv);
+    const float2 s2 = __ffma2_rn(rx, rx, __fmul2_rn(ry, ry));
+    const float2 rs = make_float2(FastRsqrt()(fmaxf(s2.x, 1e-30f)), FastRsqrt()(fmaxf(s2.y, 1e-30f)));
+    const float2 s = __fmul2_rn(s2, rs);
+    const bool in0 = s.x <= delta, in1 = s.y <= delta;
+    const float2 ko = __fmul2_rn(splat(gj * delta), rs);                 // outlier: g * delta / s
+    const float2 k = make_float2(in0 ? gj : ko.x, in1 ? gj : ko.y);
+    const float2 grx = __fmul2_rn(k, rx), gry = __fmul2_rn(k, ry);
+    g[5] = __ffma2_rn(grx, ex, g[5]);
+    g[6] = __ffma2_rn(gry, ey, g[6]);
+    const float2 gex = __fmul2_rn(grx, wu), gey = __fmul2_rn(gry, wv);
+    g[3] = __ffma2_rn(gex, splat(-1.0f), g[3]);
+    g[4] = __ffma2_rn(gey, splat(-1.0f), g[4]);
+    float2 gpx = gex, gpy = gey;
+    if (BOUNDED) {
+        gpx.x = (pxc.x == px.x) ? gex.x : 0.f; gpx.y = (pxc.y == px.y) ? gex.y : 0.f;
+        gpy.x = (pyc.x == py.x) ? gey.x : 0.f; gpy.y = (pyc.y == py.y) ? gey.y : 0.f;
+    }
+    const float2 gxh = __fmul2_rn(gpx, iz), gyh = __fmul2_rn(gpy, iz);
+    const float2 tz = __ffma2_rn(gxh, px, __fmul2_rn(gyh, py));
+    const float2 gzh = make_float2(zh.x >= cam.z_min ? -tz.x : 0.f, zh.y >= cam.z_min ? -tz.y : 0.f);
+    g[0] = __ffma2_rn(splat(P[0]), gxh, __ffma2_rn(splat(P[4]), gyh, __ffma2_rn(splat(P[8]), gzh, g[0])));
+    g[1] = __ffma2_rn(splat(P[1]), gxh, __ffma2_rn(splat(P[5]), gyh, __ffma2_rn(splat(P[9]), gzh, g[1])));
+    g[2] = __ffma2_rn(splat(P[2]), gxh, __ffma2_rn(splat(P[6]), gyh, __ffma2_rn(splat(P[10]), gzh, g[2])));
+    const float2 over = __fadd2_rn(s, splat(-delta));
+    gd = __ffma2_rn(make_float2(in0 ? 0.f : over.x, in1 ? 0.f : over.y), splat(gj), gd);
+}
+
 struct BwArgs {
     const float *x3d, *x2d, *w2d, *cam, *lb, *ub, *delta;
     const float *poses_a, *grad_a;      // (B, PA, D), (B, PA)
@@ -889,19 +939,29 @@ __global__ void __launch_bounds__(NT, 4) cost_backward_kernel(const BwArgs a) {
         ka.cam = a.cam; ka.lb = a.lb; ka.ub = a.ub; ka.p.z_min = a.z_min;
         const Cam cam = load_cam(ka, obj);
         const float delta = __ldg(a.delta + obj);
-        float gdelta = 0.f;
+        float2 gd2 = make_float2(0.f, 0.f);
         for (int base = 0; base < a.N; base += NT * BW_PPT) {
-            float X[BW_PPT], Y[BW_PPT], Z[BW_PPT], u[BW_PPT], v[BW_PPT], wu[BW_PPT], wv[BW_PPT], g[BW_PPT][7];
+            // BW_PPT = 4 correspondences per thread = 2 packed pairs: pair p holds points base + (2p)*NT + tid (.x)
+            // and base + (2p+1)*NT + tid (.y); out-of-range slots get zero weights (exactly zero contribution)
+            constexpr int NP = BW_PPT / 2;
+            float2 X[NP], Y[NP], Z[NP], nu[NP], nv[NP], wu[NP], wv[NP], g[NP][7];
 #pragma unroll
-            for (int k = 0; k < BW_PPT; ++k) {
-                const int n = base + k * NT + tid;
-                const bool ok = n < a.N;
-                const size_t q = (size_t)obj * a.N + (ok ? n : 0);
-                X[k] = __ldg(a.x3d + q * 3); Y[k] = __ldg(a.x3d + q * 3 + 1); Z[k] = __ldg(a.x3d + q * 3 + 2);
-                u[k] = __ldg(a.x2d + q * 2); v[k] = __ldg(a.x2d + q * 2 + 1);
-                wu[k] = ok ? __ldg(a.w2d + q * 2) : 0.f; wv[k] = ok ? __ldg(a.w2d + q * 2 + 1) : 0.f;
+            for (int k = 0; k < NP; ++k) {
+                float v7[2][7];
 #pragma unroll
-                for (int c = 0; c < 7; ++c) g[k][c] = 0.f;
+                for (int h = 0; h < 2; ++h) {
+                    const int n = base + (2 * k + h) * NT + tid;
+                    const bool ok = n < a.N;
+                    const size_t q = (size_t)obj * a.N + (ok ? n : 0);
+                    v7[h][0] = __ldg(a.x3d + q * 3); v7[h][1] = __ldg(a.x3d + q * 3 + 1); v7[h][2] = __ldg(a.x3d + q * 3 + 2);
+                    v7[h][3] = -__ldg(a.x2d + q * 2); v7[h][4] = -__ldg(a.x2d + q * 2 + 1);
+                    v7[h][5] = ok ? __ldg(a.w2d + q * 2) : 0.f; v7[h][6] = ok ? __ldg(a.w2d + q * 2 + 1) : 0.f;
+                }
+                X[k] = make_float2(v7[0][0], v7[1][0]); Y[k] = make_float2(v7[0][1], v7[1][1]); Z[k] = make_float2(v7[0][2], v7[1][2]);
+                nu[k] = make_float2(v7[0][3], v7[1][3]); nv[k] = make_float2(v7[0][4], v7[1][4]);
+                wu[k] = make_float2(v7[0][5], v7[1][5]); wv[k] = make_float2(v7[0][6], v7[1][6]);
+#pragma unroll
+                for (int c = 0; c < 7; ++c) g[k][c] = make_float2(0.f, 0.f);
             }
             for (int p0 = 0; p0 < P_total; p0 += BW_POSE_TILE) {
                 const int np = min(BW_POSE_TILE, P_total - p0);
@@ -928,24 +988,28 @@ __global__ void __launch_bounds__(NT, 4) cost_backward_kernel(const BwArgs a) {
                     const float Pj[12] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
                     const float gj = gs[j];
 #pragma unroll
-                    for (int k = 0; k < BW_PPT; ++k) {
-                        gdelta += cam.bounded
-                            ? point_cost_backward<true>(Pj, cam, delta, gj, X[k], Y[k], Z[k], u[k], v[k], wu[k], wv[k], g[k], FastRcp())
-                            : point_cost_backward<false>(Pj, cam, delta, gj, X[k], Y[k], Z[k], u[k], v[k], wu[k], wv[k], g[k], FastRcp());
+                    for (int k = 0; k < NP; ++k) {
+                        if (cam.bounded) pair_cost_backward<true>(Pj, cam, delta, gj, X[k], Y[k], Z[k], nu[k], nv[k], wu[k], wv[k], g[k], gd2);
+                        else pair_cost_backward<false>(Pj, cam, delta, gj, X[k], Y[k], Z[k], nu[k], nv[k], wu[k], wv[k], g[k], gd2);
                     }
                 }
             }
 #pragma unroll
-            for (int k = 0; k < BW_PPT; ++k) {
-                const int n = base + k * NT + tid;
-                if (n < a.N) {
-                    const size_t q = (size_t)obj * a.N + n;
-                    if (a.gx3d) { a.gx3d[q * 3] = g[k][0]; a.gx3d[q * 3 + 1] = g[k][1]; a.gx3d[q * 3 + 2] = g[k][2]; }
-                    if (a.gx2d) { a.gx2d[q * 2] = g[k][3]; a.gx2d[q * 2 + 1] = g[k][4]; }
-                    if (a.gw2d) { a.gw2d[q * 2] = g[k][5]; a.gw2d[q * 2 + 1] = g[k][6]; }
+            for (int k = 0; k < NP; ++k) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n = base + (2 * k + h) * NT + tid;
+                    if (n < a.N) {
+                        const size_t q = (size_t)obj * a.N + n;
+                        auto pick = [&](int c) { return h == 0 ? g[k][c].x : g[k][c].y; };
+                        if (a.gx3d) { a.gx3d[q * 3] = pick(0); a.gx3d[q * 3 + 1] = pick(1); a.gx3d[q * 3 + 2] = pick(2); }
+                        if (a.gx2d) { a.gx2d[q * 2] = pick(3); a.gx2d[q * 2 + 1] = pick(4); }
+                        if (a.gw2d) { a.gw2d[q * 2] = pick(5); a.gw2d[q * 2 + 1] = pick(6); }
+                    }
                 }
             }
         }
+        const float gdelta = gd2.x + gd2.y;
         // padded (n >= N) lanes carry zero weights: their residual is 0 -> inlier -> no delta contribution
         float gd[1] = {gdelta};
         __syncthreads();
