@@ -1,64 +1,75 @@
-"""Proposal distributions of the AMIS loop as standalone torch distributions (reference
-epropnp/distributions.py).  The native kernels carry their own fused sampler / density; these classes
-keep the public names importable and serve callers (and tests) that want the densities on their own.
-No pyro dependency: they derive from torch.distributions directly."""
+"""Stand-alone versions of the two orientation proposals of the AMIS loop (reference epropnp/distributions.py).
+
+The kernels carry their own fused sampler / density for these (pnp_math.cuh: proposal_draw6 / proposal_logpdf6,
+draw_yaw / proposal_logpdf4); the classes here keep the public names importable and let callers and tests use the
+densities on their own.  Plain torch.distributions subclasses -- pyro is not needed.
+"""
 import math
 
 import torch
 from torch.distributions import Distribution, VonMises, constraints
 
 
+def _forward_substitute(tril, rhs):
+    """Solve tril @ y = rhs for batches that broadcast against each other."""
+    lead = torch.broadcast_shapes(rhs.shape[:-1], tril.shape[:-2])
+    q = tril.size(-1)
+    y = torch.linalg.solve_triangular(tril.expand(lead + (q, q)), rhs.expand(lead + (q,)).unsqueeze(-1), upper=False)
+    return y.squeeze(-1)
+
+
 class AngularCentralGaussian(Distribution):
-    """ACG on S^(q-1): x = L z / |L z|, z ~ N(0, I_q)."""
+    """Direction of a zero-mean Gaussian: x = L z / |L z| with z ~ N(0, I_q), a density on the sphere S^(q-1):
+        log p(x) = -(q/2) log(x^T (L L^T)^-1 x) - log det L - log area(S^(q-1))."""
     arg_constraints = {'scale_tril': constraints.lower_cholesky}
     has_rsample = True
 
     def __init__(self, scale_tril, validate_args=None, eps=1e-6):
         q = scale_tril.size(-1)
-        assert q > 1 and scale_tril.shape[-2:] == (q, q)
+        if q < 2 or scale_tril.shape[-2:] != (q, q):
+            raise AssertionError("scale_tril must be (..., q, q) with q > 1")
+        self.q = q
+        self.eps = eps
         self.scale_tril = scale_tril
         self._unbroadcasted_scale_tril = scale_tril
-        self.q = q
-        self.area = 2 * math.pi ** (0.5 * q) / math.gamma(0.5 * q)
-        self.eps = eps
+        self.area = 2 * math.pi ** (q / 2) / math.gamma(q / 2)
         super().__init__(scale_tril.shape[:-2], (q,), validate_args=False)
 
     def log_prob(self, value):
-        L = self.scale_tril
-        shape = torch.broadcast_shapes(value.shape[:-1], L.shape[:-2])
-        y = torch.linalg.solve_triangular(L.expand(shape + L.shape[-2:]),
-                                          value.expand(shape + (self.q,)).unsqueeze(-1), upper=False).squeeze(-1)
-        half_log_det = L.diagonal(dim1=-2, dim2=-1).log().sum(-1)
-        return y.square().sum(-1).log() * (-self.q / 2) - half_log_det - math.log(self.area)
+        whitened = _forward_substitute(self.scale_tril, value)
+        log_det = self.scale_tril.diagonal(dim1=-2, dim2=-1).log().sum(-1)
+        return -0.5 * self.q * whitened.square().sum(-1).log() - log_det - math.log(self.area)
 
     def rsample(self, sample_shape=torch.Size()):
-        shape = self._extended_shape(sample_shape)
-        z = torch.randn(shape, dtype=self.scale_tril.dtype, device=self.scale_tril.device)
-        g = (self.scale_tril @ z.unsqueeze(-1)).squeeze(-1)
-        norm = g.norm(dim=-1, keepdim=True)
-        pole = torch.zeros_like(g)
-        pole[..., 0] = 1.0
-        return torch.where(norm < self.eps, pole, g / norm)
+        noise = torch.randn(self._extended_shape(sample_shape), dtype=self.scale_tril.dtype,
+                            device=self.scale_tril.device)
+        direction = torch.einsum('...ij,...j->...i', self.scale_tril, noise)
+        length = direction.norm(dim=-1, keepdim=True)
+        north_pole = torch.zeros_like(direction)
+        north_pole[..., 0] = 1
+        return torch.where(length < self.eps, north_pole, direction / length.clamp(min=1e-38))
 
 
 class VonMisesUniformMix(VonMises):
-    """(1 - uniform_mix) von Mises + uniform_mix uniform on the circle."""
+    """Yaw proposal of the 4DoF layer: with probability `uniform_mix` uniform on the circle, otherwise von Mises."""
 
     def __init__(self, loc, concentration, uniform_mix=0.25, **kwargs):
-        super(VonMisesUniformMix, self).__init__(loc, concentration, **kwargs)
+        super().__init__(loc, concentration, **kwargs)
         self.uniform_mix = uniform_mix
 
     @torch.no_grad()
     def sample(self, sample_shape=torch.Size()):
-        assert len(sample_shape) == 1
-        total = sample_shape[0]
-        n_uniform = round(total * self.uniform_mix)
-        shape_u = self._extended_shape((n_uniform,))
-        uni = (torch.rand(shape_u, dtype=self.loc.dtype, device=self.loc.device) * 2 - 1) * math.pi
-        vm = super(VonMisesUniformMix, self).sample((total - n_uniform,))
-        return torch.cat((uni, vm), dim=0)
+        """Stratified like the reference: the first round(n * uniform_mix) draws are uniform, the rest von Mises."""
+        if len(sample_shape) != 1:
+            raise AssertionError("sample_shape must be one-dimensional")
+        n = sample_shape[0]
+        n_flat = round(n * self.uniform_mix)
+        flat_shape = self._extended_shape((n_flat,))
+        flat = math.pi * (2 * torch.rand(flat_shape, dtype=self.loc.dtype, device=self.loc.device) - 1)
+        peaked = VonMises.sample(self, (n - n_flat,))
+        return torch.cat((flat, peaked), dim=0)
 
     def log_prob(self, value):
-        vm = super(VonMisesUniformMix, self).log_prob(value) + math.log(1 - self.uniform_mix)
-        flat = torch.full_like(vm, math.log(self.uniform_mix / (2 * math.pi)))
-        return torch.logaddexp(vm, flat)
+        peaked = VonMises.log_prob(self, value) + math.log1p(-self.uniform_mix)
+        flat = math.log(self.uniform_mix) - math.log(2 * math.pi)
+        return torch.logaddexp(peaked, torch.full_like(peaked, flat))

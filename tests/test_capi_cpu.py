@@ -121,3 +121,47 @@ def test_torch_side_helpers_match_oracle():
     w2d = torch.ones_like(x2d)
     e = orc.evaluate(x3d, x2d, w2d, pose, orc.Camera(cam_mats, 0.1), 1e9, want_jac=True)
     assert torch.allclose(jac.flatten(-3, -2), e["jac"], rtol=1e-9, atol=1e-9)
+
+
+def test_distribution_and_cost_classes_match_oracle():
+    """Public utility classes (CPU-capable torch code) against the pinned oracle formulas."""
+    from oracle import pnp_oracle as orc
+    from epropnp.cost_fun import AdaptiveHuberPnPCost, HuberPnPCost
+    from epropnp.distributions import AngularCentralGaussian, VonMisesUniformMix
+    g = torch.Generator().manual_seed(11)
+    d = torch.float64
+    A = torch.randn(5, 4, 4, generator=g, dtype=d)
+    L = torch.linalg.cholesky(A @ A.transpose(-1, -2) + 0.2 * torch.eye(4, dtype=d))
+    x = torch.randn(7, 5, 4, generator=g, dtype=d)
+    x = x / x.norm(dim=-1, keepdim=True)
+    acg = AngularCentralGaussian(L)
+    assert torch.allclose(acg.log_prob(x), orc.acg_logpdf(x, L), rtol=1e-10, atol=1e-10)
+    s = acg.sample((1000,))
+    assert s.shape == (1000, 5, 4) and torch.allclose(s.norm(dim=-1), torch.ones(1000, 5, dtype=d))
+    loc, kappa = torch.randn(5, generator=g, dtype=d), torch.rand(5, generator=g, dtype=d) * 30 + 0.1
+    yaw = (torch.rand(9, 5, generator=g, dtype=d) * 2 - 1) * 3.14159
+    vm = VonMisesUniformMix(loc, kappa)
+    assert torch.allclose(vm.log_prob(yaw), orc.vm_mix_logpdf(yaw, loc, kappa), rtol=1e-9, atol=1e-9)
+    smp = vm.sample((64,))
+    assert smp.shape == (64, 5) and smp.abs().max() <= 3.1416
+    # HuberPnPCost.compute against the oracle's evaluate (cost, rescaled residual, rescaled Jacobian)
+    B, N = 3, 11
+    x3d = torch.randn(B, N, 3, generator=g, dtype=d)
+    pose = torch.tensor([[0.1, -0.2, 6.0, 1.0, 0.0, 0.0, 0.0]], dtype=d).repeat(B, 1)
+    K = torch.tensor([[800., 0, 320], [0, 800, 240], [0, 0, 1]], dtype=d).expand(B, 3, 3)
+    from epropnp.camera import PerspectiveCamera
+    cam = PerspectiveCamera(cam_mats=K, z_min=0.1)
+    u, jac_cam = cam.project(x3d, pose, out_jac=True)
+    x2d = u + 3 * torch.randn(B, N, 2, generator=g, dtype=d)
+    w2d = torch.rand(B, N, 2, generator=g, dtype=d) + 0.5
+    cf = AdaptiveHuberPnPCost(relative_delta=0.3)
+    cf.set_param(x2d, w2d)
+    assert torch.allclose(cf.delta, orc.adaptive_delta(x2d, w2d, 0.3))
+    res, cost, jac = cf.compute(u, x2d, w2d, jac_cam=jac_cam, out_residual=True, out_cost=True, out_jacobian=True)
+    e = orc.evaluate(x3d, x2d, w2d, pose, orc.Camera(K, 0.1), cf.delta, want_jac=True)
+    assert torch.allclose(cost, e["cost"]) and torch.allclose(res, e["residual"]) and torch.allclose(jac, e["jac"])
+    buf = torch.empty(B, dtype=d)
+    assert cf.compute(u, x2d, w2d, out_cost=buf)[1] is buf and torch.allclose(buf, e["cost"])
+    c2 = cf.shallow_copy().repeat_(2)
+    assert c2.delta.shape == (2 * B,) and isinstance(c2, AdaptiveHuberPnPCost)
+    assert HuberPnPCost(delta=2.0).shallow_copy().delta == 2.0
