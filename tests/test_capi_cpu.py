@@ -165,3 +165,16 @@ def test_distribution_and_cost_classes_match_oracle():
     c2 = cf.shallow_copy().repeat_(2)
     assert c2.delta.shape == (2 * B,) and isinstance(c2, AdaptiveHuberPnPCost)
     assert HuberPnPCost(delta=2.0).shallow_copy().delta == 2.0
+
+
+def test_plain_c_host_links_and_runs(handle, tmp_path):
+    """The boundary is a C ABI: a C99 program built with gcc against include/epropnp_b200.h links to the library
+    and exercises the device-free entry points."""
+    import subprocess
+    exe = str(tmp_path / "host_c")
+    lib_dir = os.path.dirname(capi.lib_path())
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "host_c.c"), "-o", exe, "-L", lib_dir, "-lepropnp_b200",
+                    "-Wl,-rpath," + lib_dir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
