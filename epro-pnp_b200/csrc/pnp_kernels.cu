@@ -26,6 +26,10 @@
 namespace {
 using namespace pnp;
 
+#if (defined(EPNP_SWEEP_NOCLAMP) || defined(EPNP_SWEEP_SPLIT)) && !defined(EPNP_SWEEP_RSQ)
+#define EPNP_SWEEP_RSQ 1
+#endif
+
 constexpr int NT = 128;                 // threads per CTA
 constexpr int NW = NT / 32;
 constexpr int CH = 128;                 // correspondences per TMA chunk (2 slots x 3.5 KB)
@@ -308,12 +312,35 @@ __device__ void eval_normal_eq(const float* pts, int N, const float* pose, const
     // per-point scalar walk over the 64-byte records would cause
     const float4* p4 = reinterpret_cast<const float4*>(pts);
     const int npair = (N + 1) >> 1;
+#if defined(EPNP_LM_PACKED)
+    // experiment (off by default): u-row / v-row of the Jacobian in the two lanes of packed fp32x2 registers
+    {
+        constexpr int NP = Dim<DOF>::NA + DOF;
+        pnp::V2 acc2[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) acc2[i] = pnp::v2splat(0.f);
+        const pnp::V2 kuv[3] = {pnp::v2(cam.k[0], cam.k[3]), pnp::v2(cam.k[1], cam.k[4]), pnp::v2(cam.k[2], cam.k[5])};
+        float cost = 0.f;
+        for (int j = threadIdx.x; j < npair; j += NT) {
+            const float4 q0 = p4[4 * j], q1 = p4[4 * j + 1], q2 = p4[4 * j + 2], q3 = p4[4 * j + 3];
+            point_normal_eq_rows<DOF, CLIP>(R, t, cam, kuv, delta, huber_eps, q0.x, q0.z, q1.x, q1.z, q2.x, q2.z, q3.x,
+                                            acc2, cost);
+            if (2 * j + 1 < N)
+                point_normal_eq_rows<DOF, CLIP>(R, t, cam, kuv, delta, huber_eps, q0.y, q0.w, q1.y, q1.w, q2.y, q2.w,
+                                                q3.y, acc2, cost);
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) acc[i] = acc2[i].x + acc2[i].y;
+        acc[NP] = cost;
+    }
+#else
     for (int j = threadIdx.x; j < npair; j += NT) {
         const float4 q0 = p4[4 * j], q1 = p4[4 * j + 1], q2 = p4[4 * j + 2], q3 = p4[4 * j + 3];
         point_normal_eq<DOF, CLIP>(R, t, cam, delta, huber_eps, q0.x, q0.z, q1.x, -q1.z, -q2.x, q2.z, q3.x, acc);
         if (2 * j + 1 < N)
             point_normal_eq<DOF, CLIP>(R, t, cam, delta, huber_eps, q0.y, q0.w, q1.y, -q1.w, -q2.y, q2.w, q3.y, acc);
     }
+#endif
     const float tot = warp_transpose_sum(acc);
     red[(threadIdx.x >> 5) * 32 + (threadIdx.x & 31)] = tot;
     __syncthreads();
@@ -431,6 +458,46 @@ __device__ __forceinline__ float2 pair_cost(const float2 (&P2)[12], const Cam& c
     return make_float2(s.x <= d2.x ? inl.x : outl.x, s.y <= d2.x ? inl.y : outl.y);
 }
 
+#if defined(EPNP_SWEEP_RSQ)
+// experiments (off by default), all on pnp::pair_cost_rsq -- one MUFU.RSQ per point instead of RCP + SQRT, Huber
+// without selects, accumulation folded into the last FFMA2:
+//   EPNP_SWEEP_RSQ      the formulation itself
+//   EPNP_SWEEP_NOCLAMP  + drop the z clamp when pose_depth_margin() proves it idle for the whole warp
+//   EPNP_SWEEP_SPLIT    + two samples per thread over half of the points each (pair-record loads amortised)
+struct SweepRsqrt {
+    __device__ __forceinline__ float operator()(float x) const { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+};
+template <bool BOUNDED, bool CLAMPZ>
+__device__ __forceinline__ float2 pair_cost_acc(const float2 (&P2)[12], const Cam& cam, float delta, float2 acc,
+                                                const float4 q0, const float4 q1, const float4 q2, const float4 q3) {
+    return pnp::pair_cost_rsq<BOUNDED, CLAMPZ>(P2, cam, delta, make_float2(q0.x, q0.y), make_float2(q0.z, q0.w),
+                                               make_float2(q1.x, q1.y), make_float2(q1.z, q1.w),
+                                               make_float2(q2.x, q2.y), make_float2(q2.z, q2.w),
+                                               make_float2(q3.x, q3.y), acc, SweepRsqrt());
+}
+template <bool BOUNDED, bool CLAMPZ = true>
+__device__ __forceinline__ float sweep_cost(const float4* pts4, int N, const float* P, const Cam& cam, float delta) {
+    float2 P2[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) P2[k] = splat(P[k]);
+    float2 c0 = splat(0.f), c1 = splat(0.f), c2 = splat(0.f), c3 = splat(0.f);
+    const int npair = (N + 1) >> 1;
+    int j = 0;
+    for (; j + 4 <= npair; j += 4) {
+        const float4* q = pts4 + 4 * j;
+        c0 = pair_cost_acc<BOUNDED, CLAMPZ>(P2, cam, delta, c0, q[0], q[1], q[2], q[3]);
+        c1 = pair_cost_acc<BOUNDED, CLAMPZ>(P2, cam, delta, c1, q[4], q[5], q[6], q[7]);
+        c2 = pair_cost_acc<BOUNDED, CLAMPZ>(P2, cam, delta, c2, q[8], q[9], q[10], q[11]);
+        c3 = pair_cost_acc<BOUNDED, CLAMPZ>(P2, cam, delta, c3, q[12], q[13], q[14], q[15]);
+    }
+    for (; j < npair; ++j) {
+        const float4* q = pts4 + 4 * j;
+        c0 = pair_cost_acc<BOUNDED, CLAMPZ>(P2, cam, delta, c0, q[0], q[1], q[2], q[3]);
+    }
+    c0 = __fadd2_rn(c0, c2); c1 = __fadd2_rn(c1, c3);
+    return (c0.x + c0.y) + (c1.x + c1.y);
+}
+#else
 template <bool BOUNDED>
 __device__ __forceinline__ float sweep_cost(const float4* pts4, int N, const float* P, const Cam& cam, float delta) {
     float2 P2[12];
@@ -454,6 +521,7 @@ __device__ __forceinline__ float sweep_cost(const float4* pts4, int N, const flo
     c0 = __fadd2_rn(c0, c2); c1 = __fadd2_rn(c1, c3);
     return (c0.x + c0.y) + (c1.x + c1.y);
 }
+#endif
 
 template <int DOF>
 __device__ __forceinline__ float pose_cost(const float* pts, int N, const float* pose, const Cam& cam, float delta) {
@@ -463,6 +531,121 @@ __device__ __forceinline__ float pose_cost(const float* pts, int N, const float*
     const float4* pts4 = reinterpret_cast<const float4*>(pts);
     return cam.bounded ? sweep_cost<true>(pts4, N, P, cam, delta) : sweep_cost<false>(pts4, N, P, cam, delta);
 }
+
+#if defined(EPNP_SWEEP_NOCLAMP) || defined(EPNP_SWEEP_SPLIT)
+// Largest |X| over the resident points (every thread gets it): the `radius` of pose_depth_margin.
+__device__ __forceinline__ float object_radius(const float* pts, int N, float* red, int half) {
+    const float4* p4 = reinterpret_cast<const float4*>(pts);
+    const int npair = (N + 1) >> 1;
+    float r2 = 0.f;
+    for (int j = threadIdx.x; j < npair; j += NT) {
+        const float4 q0 = p4[4 * j], q1 = p4[4 * j + 1];
+        r2 = fmaxf(r2, fmaxf(fmaf(q0.x, q0.x, fmaf(q0.z, q0.z, q1.x * q1.x)), fmaf(q0.y, q0.y, fmaf(q0.w, q0.w, q1.y * q1.y))));
+    }
+    return sqrtf(block_max(r2, red, half));
+}
+
+// pose_cost with the clamp-free loop when the whole warp's poses keep every point in front of z_min
+// (radius < 0: unknown, always clamp).
+template <int DOF>
+__device__ __forceinline__ float pose_cost(const float* pts, int N, const float* pose, const Cam& cam, float delta,
+                                           float radius) {
+    float R[9], P[12];
+    pose_to_rot<DOF>(pose, R);
+    make_proj(cam.k, R, pose, P);
+    const float4* pts4 = reinterpret_cast<const float4*>(pts);
+    bool free_z = false;
+#if defined(EPNP_SWEEP_NOCLAMP)
+    if (radius >= 0.f) free_z = __all_sync(__activemask(), pose_depth_margin(P, radius, cam.z_min) >= 0.f);
+#endif
+    if (free_z) return cam.bounded ? sweep_cost<true, false>(pts4, N, P, cam, delta) : sweep_cost<false, false>(pts4, N, P, cam, delta);
+    return cam.bounded ? sweep_cost<true, true>(pts4, N, P, cam, delta) : sweep_cost<false, true>(pts4, N, P, cam, delta);
+}
+#endif
+
+#if defined(EPNP_SWEEP_SPLIT)
+// Two poses over the pair records [j0, j1): every record is loaded once and used for both.
+template <bool BOUNDED, bool CLAMPZ>
+__device__ __forceinline__ void sweep_cost2(const float4* pts4, int j0, int j1, const float* Pa, const float* Pb,
+                                            const Cam& cam, float delta, float& ca, float& cb) {
+    float2 A2[12], B2[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { A2[k] = splat(Pa[k]); B2[k] = splat(Pb[k]); }
+    float2 a0 = splat(0.f), a1 = splat(0.f), b0 = splat(0.f), b1 = splat(0.f);
+    int j = j0;
+    for (; j + 2 <= j1; j += 2) {
+        const float4* q = pts4 + 4 * j;
+        const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
+        a0 = pair_cost_acc<BOUNDED, CLAMPZ>(A2, cam, delta, a0, q0, q1, q2, q3);
+        b0 = pair_cost_acc<BOUNDED, CLAMPZ>(B2, cam, delta, b0, q0, q1, q2, q3);
+        a1 = pair_cost_acc<BOUNDED, CLAMPZ>(A2, cam, delta, a1, q4, q5, q6, q7);
+        b1 = pair_cost_acc<BOUNDED, CLAMPZ>(B2, cam, delta, b1, q4, q5, q6, q7);
+    }
+    for (; j < j1; ++j) {
+        const float4* q = pts4 + 4 * j;
+        const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+        a0 = pair_cost_acc<BOUNDED, CLAMPZ>(A2, cam, delta, a0, q0, q1, q2, q3);
+        b0 = pair_cost_acc<BOUNDED, CLAMPZ>(B2, cam, delta, b0, q0, q1, q2, q3);
+    }
+    a0 = __fadd2_rn(a0, a1); b0 = __fadd2_rn(b0, b1);
+    ca = a0.x + a0.y; cb = b0.x + b0.y;
+}
+
+// Costs of the S new samples smp[m0 .. m0+S) of an AMIS iteration.  Work item w = (sample pair k, point half h):
+// the two halves of a sample's cost land in cst[m] (h = 0) and lw[m] (h = 1, free until the weights pass, which
+// folds it in).  Odd S: whole sweeps, lw[m] = 0.
+template <int DOF>
+__device__ void sweep_new_samples(const float* pts, int N, const float* smp, float* cst, float* lw, int m0, int S,
+                                  const Cam& cam, float delta, float radius) {
+    constexpr int PD = Dim<DOF>::POSE;
+    const float4* pts4 = reinterpret_cast<const float4*>(pts);
+    if (S & 1) {
+        for (int s = threadIdx.x; s < S; s += NT) {
+            float pose[PD];
+#pragma unroll
+            for (int k = 0; k < PD; ++k) pose[k] = smp[(m0 + s) * PD + k];
+            cst[m0 + s] = pose_cost<DOF>(pts, N, pose, cam, delta, radius);
+            lw[m0 + s] = 0.f;
+        }
+        return;
+    }
+    const int npair = (N + 1) >> 1, H = S >> 1;
+    const int jmid = min(npair, ((npair >> 1) + 1) & ~1);
+    for (int w = threadIdx.x; w < S; w += NT) {
+        const int k = w % H, h = w / H;
+        const int ma = m0 + 2 * k, mb = ma + 1;
+        float Pa[12], Pb[12];
+        {
+            float pose[PD], R[9];
+#pragma unroll
+            for (int c = 0; c < PD; ++c) pose[c] = smp[ma * PD + c];
+            pose_to_rot<DOF>(pose, R);
+            make_proj(cam.k, R, pose, Pa);
+#pragma unroll
+            for (int c = 0; c < PD; ++c) pose[c] = smp[mb * PD + c];
+            pose_to_rot<DOF>(pose, R);
+            make_proj(cam.k, R, pose, Pb);
+        }
+        bool free_z = false;
+#if defined(EPNP_SWEEP_NOCLAMP)
+        if (radius >= 0.f)
+            free_z = __all_sync(__activemask(), fminf(pose_depth_margin(Pa, radius, cam.z_min),
+                                                      pose_depth_margin(Pb, radius, cam.z_min)) >= 0.f);
+#endif
+        const int j0 = h ? jmid : 0, j1 = h ? npair : jmid;
+        float ca, cb;
+        if (free_z) {
+            if (cam.bounded) sweep_cost2<true, false>(pts4, j0, j1, Pa, Pb, cam, delta, ca, cb);
+            else sweep_cost2<false, false>(pts4, j0, j1, Pa, Pb, cam, delta, ca, cb);
+        } else {
+            if (cam.bounded) sweep_cost2<true, true>(pts4, j0, j1, Pa, Pb, cam, delta, ca, cb);
+            else sweep_cost2<false, true>(pts4, j0, j1, Pa, Pb, cam, delta, ca, cb);
+        }
+        float* dst = h ? lw : cst;
+        dst[ma] = ca; dst[mb] = cb;
+    }
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // AMIS loop for the resident object (6DoF).  sh.prop[0] must not be set yet; pose / cov are read from
@@ -479,6 +662,11 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
 
     if (tid == st) initial_fit6(pose_opt, cov, p.acg_dispersion, sh.prop[0]);
     PH_MARK(a, PH_INIT_FIT);
+#if defined(EPNP_SWEEP_NOCLAMP)
+    const float radius = object_radius(pts4, a.N, sh.red, 0);
+#elif defined(EPNP_SWEEP_SPLIT)
+    const float radius = -1.f;
+#endif
     __syncthreads();
 
     for (int i = 0; i < I; ++i) {
@@ -502,9 +690,19 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
             float* out = a.pose_samples + ((size_t)obj * M + m) * 7;
 #pragma unroll
             for (int k = 0; k < 7; ++k) out[k] = q[k];
+#if defined(EPNP_SWEEP_SPLIT)
+            // cost: sweep_new_samples below, once every new sample of the iteration is in shared memory
+#elif defined(EPNP_SWEEP_NOCLAMP)
+            cst[m] = pose_cost<6>(pts4, a.N, q, cam, delta, radius);
+#else
             cst[m] = pose_cost<6>(pts4, a.N, q, cam, delta);
+#endif
             for (int j = 0; j <= i; ++j) logp[j * M + m] = proposal_logpdf6(sh.prop[j], q);
         }
+#if defined(EPNP_SWEEP_SPLIT)
+        __syncthreads();
+        sweep_new_samples<6>(pts4, a.N, smp, cst, lw, i * S, S, cam, delta, radius);
+#endif
         PH_MARK(a, PH_DRAW_SWEEP);
         // ---- the new proposal on all earlier samples
         for (int m = tid; m < i * S; m += NT) {
@@ -524,7 +722,13 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
             for (int j = 1; j <= i; ++j) top = fmaxf(top, logp[j * M + m]);
             float acc = 0.f;
             for (int j = 0; j <= i; ++j) acc += expf(logp[j * M + m] - top);
+#if defined(EPNP_SWEEP_SPLIT)
+            float cm = cst[m];
+            if (m >= i * S) { cm += lw[m]; cst[m] = cm; }       // fold the second point half of a new sample in
+            const float v = -cm - ((top + logf(acc)) - log_cnt);
+#else
             const float v = -cst[m] - ((top + logf(acc)) - log_cnt);
+#endif
             lw[m] = v;
             mx = fmaxf(mx, v);
         }
@@ -671,6 +875,11 @@ __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, 
 
     if (tid == st) initial_fit4(pose_opt, cov, p.amis_eps, sh.prop4[0]);
     PH_MARK(a, PH_INIT_FIT);
+#if defined(EPNP_SWEEP_NOCLAMP)
+    const float radius = object_radius(pts4, a.N, sh.red, 0);
+#elif defined(EPNP_SWEEP_SPLIT)
+    const float radius = -1.f;
+#endif
     __syncthreads();
 
     for (int i = 0; i < I; ++i) {
@@ -690,9 +899,19 @@ __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, 
             float* out = a.pose_samples + ((size_t)obj * M + m) * 4;
 #pragma unroll
             for (int k = 0; k < 4; ++k) { smp[m * 4 + k] = q[k]; out[k] = q[k]; }
+#if defined(EPNP_SWEEP_SPLIT)
+            // cost: sweep_new_samples below, once every new sample of the iteration is in shared memory
+#elif defined(EPNP_SWEEP_NOCLAMP)
+            cst[m] = pose_cost<4>(pts4, a.N, q, cam, delta, radius);
+#else
             cst[m] = pose_cost<4>(pts4, a.N, q, cam, delta);
+#endif
             for (int j = 0; j <= i; ++j) logp[j * M + m] = proposal_logpdf4(sh.prop4[j], q);
         }
+#if defined(EPNP_SWEEP_SPLIT)
+        __syncthreads();
+        sweep_new_samples<4>(pts4, a.N, smp, cst, lw, i * S, S, cam, delta, radius);
+#endif
         PH_MARK(a, PH_DRAW_SWEEP);
         for (int m = tid; m < i * S; m += NT) logp[i * M + m] = proposal_logpdf4(sh.prop4[i], smp + m * 4);
         __syncthreads();
@@ -705,7 +924,13 @@ __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, 
             for (int j = 1; j <= i; ++j) top = fmaxf(top, logp[j * M + m]);
             float acc = 0.f;
             for (int j = 0; j <= i; ++j) acc += expf(logp[j * M + m] - top);
+#if defined(EPNP_SWEEP_SPLIT)
+            float cm = cst[m];
+            if (m >= i * S) { cm += lw[m]; cst[m] = cm; }       // fold the second point half of a new sample in
+            const float v = -cm - ((top + logf(acc)) - log_cnt);
+#else
             const float v = -cst[m] - ((top + logf(acc)) - log_cnt);
+#endif
             lw[m] = v;
             mx = fmaxf(mx, v);
         }

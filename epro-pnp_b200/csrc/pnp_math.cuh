@@ -40,6 +40,39 @@ template <int DOF> struct Dim {
     static constexpr int NV = NA + DOF + 1;            // + J^T r + cost
 };
 
+// ------------------------------------------------------------------------------------------------
+// Two-lane fp32 value.  On sm_100a each op below is ONE packed instruction (FFMA2 / FMUL2 / FADD2); the host
+// build evaluates the lanes with scalar fmaf so the packed formulas can be checked on the CPU.
+#if defined(__CUDACC__)
+typedef float2 V2;
+#else
+struct alignas(8) V2 { float x, y; };
+#endif
+PNP_HD V2 v2(float x, float y) { V2 r; r.x = x; r.y = y; return r; }
+PNP_HD V2 v2splat(float x) { return v2(x, x); }
+PNP_HD V2 v2fma(V2 a, V2 b, V2 c) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(a, b, c);
+#else
+    return v2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+PNP_HD V2 v2mul(V2 a, V2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul2_rn(a, b);
+#else
+    return v2(a.x * b.x, a.y * b.y);
+#endif
+}
+PNP_HD V2 v2add(V2 a, V2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd2_rn(a, b);
+#else
+    return v2(a.x + b.x, a.y + b.y);
+#endif
+}
+PNP_HD V2 v2neg(V2 a) { return v2(-a.x, -a.y); }
+
 // packed upper-triangular index, row-major: (i, j>=i)
 PNP_HD constexpr int tri(int i, int j, int n) { return i * n - i * (i - 1) / 2 + (j - i); }
 
@@ -120,6 +153,49 @@ PNP_HD float point_cost(const float* P, const Cam& c, float delta, float half_d2
     float s2 = fmaf(rx, rx, ry * ry);
     float s = sq(s2);
     return (s <= delta) ? 0.5f * s2 : fmaf(delta, s, -half_d2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Packed form of point_cost for TWO correspondences (lanes x / y) under one pre-multiplied projection, with ONE
+// special-function op per point instead of two (build option EPNP_SWEEP_RSQ).  With z = max(zh, z_min) > 0:
+//     r = ((xh/z - u) wu, (yh/z - v) wv)   =>   |r| = sqrt(q) / z,   q = ((xh - u z) wu)^2 + ((yh - v z) wv)^2
+//     |r| = q * rsqrt(q z^2)                     one rsqrt, no reciprocal (the tiny addend keeps q = 0 finite)
+//     clamp(xh/z, lb, ub) = clamp(xh, lb z, ub z) / z                                   (bounded cameras)
+//     Huber(s) = m (s - m/2),  m = min(s, delta)   both branches in one expression, no select, no cancellation
+// Returns acc + (Huber cost of point 0, Huber cost of point 1).  P2[k] = (P[k], P[k]); nu / nv are the NEGATED
+// observations as the staged pair records hold them.
+struct ExactRsqrt { PNP_HD float operator()(float x) const { return 1.0f / sqrtf(x); } };
+
+// CLAMPZ = false: the caller has shown zh >= z_min for every point of the object under this pose
+// (pose_depth_margin below), so the clamp is the identity and its two scalar FMNMX are dropped.
+template <bool BOUNDED, bool CLAMPZ = true, class Rsqrt = ExactRsqrt>
+PNP_HD V2 pair_cost_rsq(const V2* P2, const Cam& c, float delta, V2 X, V2 Y, V2 Z, V2 nu, V2 nv, V2 wu, V2 wv,
+                        V2 acc, Rsqrt rsq) {
+    V2 xh = v2fma(P2[0], X, v2fma(P2[1], Y, v2fma(P2[2], Z, P2[3])));
+    V2 yh = v2fma(P2[4], X, v2fma(P2[5], Y, v2fma(P2[6], Z, P2[7])));
+    const V2 zh = v2fma(P2[8], X, v2fma(P2[9], Y, v2fma(P2[10], Z, P2[11])));
+    const V2 z = CLAMPZ ? v2(fmaxf(zh.x, c.z_min), fmaxf(zh.y, c.z_min)) : zh;
+    if (BOUNDED) {
+        const V2 lx = v2mul(v2splat(c.lbx), z), ux = v2mul(v2splat(c.ubx), z);
+        const V2 ly = v2mul(v2splat(c.lby), z), uy = v2mul(v2splat(c.uby), z);
+        xh = v2(fminf(fmaxf(xh.x, lx.x), ux.x), fminf(fmaxf(xh.y, lx.y), ux.y));
+        yh = v2(fminf(fmaxf(yh.x, ly.x), uy.x), fminf(fmaxf(yh.y, ly.y), uy.y));
+    }
+    const V2 a = v2mul(v2fma(nu, z, xh), wu);
+    const V2 b = v2mul(v2fma(nv, z, yh), wv);
+    const V2 q = v2fma(a, a, v2mul(b, b));
+    const V2 qz = v2fma(q, v2mul(z, z), v2splat(1e-30f));
+    const V2 s = v2mul(q, v2(rsq(qz.x), rsq(qz.y)));
+    const V2 m = v2(fminf(s.x, delta), fminf(s.y, delta));
+    return v2fma(m, v2fma(m, v2splat(-0.5f), s), acc);
+}
+
+// Lower bound of zh = P[8..10] . X + P[11] over every point with |X| <= radius (Cauchy-Schwarz), minus z_min,
+// with a relative safety margin for the fp32 rounding of both sides: >= 0 means no point of the object can
+// reach the z clamp under this pose.
+PNP_HD float pose_depth_margin(const float* P, float radius, float z_min) {
+    const float reach = sqrtf(fmaf(P[8], P[8], fmaf(P[9], P[9], P[10] * P[10]))) * radius;
+    return (P[11] - reach) - z_min - 1e-5f * (fabsf(P[11]) + reach + z_min);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -230,6 +306,89 @@ PNP_HD void point_normal_eq(const float* R, const float* t, const Cam& c, float 
     }
 #pragma unroll
     for (int i = 0; i < DOF; ++i) acc[NA + i] = fmaf(jx[i], rx, fmaf(jy[i], ry, acc[NA + i]));
+}
+
+// 1/x and sqrt(x) without the slow-path branches of the IEEE forms: special-function seed plus one Newton step
+// (x is a clamped depth >= z_min, resp. a sum of squares; neither needs denormal or negative handling).
+PNP_HD float rcp_newton(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+#else
+    return 1.0f / x;
+#endif
+}
+PNP_HD float sqrt_newton(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaxf(x, 1e-30f)));
+    const float s = x * y;
+    return fmaf(0.5f * y, fmaf(-s, s, x), s);
+#else
+    return sqrtf(x);
+#endif
+}
+
+// Row-packed form of point_normal_eq (build option EPNP_LM_PACKED): lane x carries the u-row of the 2xDOF
+// Jacobian, lane y the v-row, so the DOF(DOF+1)/2 + DOF accumulations are one FFMA2 each instead of two FFMA.
+//   acc2[k].x + acc2[k].y == acc[k] of point_normal_eq (k < NA + DOF), `cost` == acc[NA + DOF]
+// kuv[i] = (K[0][i], K[1][i]); `nu`, `nv` are the NEGATED observations as the staged pair records hold them.
+template <int DOF, bool CLIP>
+PNP_HD void point_normal_eq_rows(const float* R, const float* t, const Cam& c, const V2* kuv, float delta,
+                                 float huber_eps, float X, float Y, float Z, float nu, float nv, float wu,
+                                 float wv, V2* acc2, float& cost) {
+    constexpr int NA = Dim<DOF>::NA;
+    const float xr = fmaf(R[0], X, fmaf(R[1], Y, R[2] * Z));
+    const float yr = fmaf(R[3], X, fmaf(R[4], Y, R[5] * Z));
+    const float zr = fmaf(R[6], X, fmaf(R[7], Y, R[8] * Z));
+    const float xc = xr + t[0], yc = yr + t[1], zc = zr + t[2];
+    const V2 h = v2fma(kuv[0], v2splat(xc), v2fma(kuv[1], v2splat(yc), v2mul(kuv[2], v2splat(zc))));
+    const float zh = fmaf(c.k[6], xc, fmaf(c.k[7], yc, c.k[8] * zc));
+    const float z = fmaxf(zh, c.z_min);
+    const V2 iz = v2splat(rcp_newton(z));
+    V2 p = v2mul(h, iz);
+    if (c.bounded) {
+        p.x = fminf(fmaxf(p.x, c.lbx), c.ubx);
+        p.y = fminf(fmaxf(p.y, c.lby), c.uby);
+    }
+    const V2 w = v2(wu, wv);
+    V2 r = v2mul(v2add(p, v2(nu, nv)), w);
+    const float s2 = fmaf(r.x, r.x, r.y * r.y);
+    const float s = sqrt_newton(s2);
+    cost += (s <= delta) ? 0.5f * s2 : fmaf(delta, s, -0.5f * delta * delta);
+    const float sc = (s <= delta && delta >= huber_eps) ? 1.0f : sqrt_newton(fminf(delta * rcp_newton(fmaxf(s, huber_eps)), 1.0f));
+    const V2 sc2 = v2splat(sc);
+    r = v2mul(r, sc2);
+
+    V2 j[DOF];
+    j[0] = v2mul(kuv[0], iz); j[1] = v2mul(kuv[1], iz); j[2] = v2mul(v2add(kuv[2], v2neg(p)), iz);
+    if (DOF == 6) {
+        const V2 ax = v2splat(2.f * xr), ay = v2splat(2.f * yr), az = v2splat(2.f * zr);
+        j[3] = v2fma(j[1], az, v2neg(v2mul(j[2], ay)));
+        j[4] = v2fma(j[2], ax, v2neg(v2mul(j[0], az)));
+        j[5] = v2fma(j[0], ay, v2neg(v2mul(j[1], ax)));
+    } else {
+        j[3] = v2fma(j[0], v2splat(zr), v2neg(v2mul(j[2], v2splat(xr))));
+    }
+    V2 sw = v2mul(w, sc2);
+    if (CLIP) {
+        const bool cz = (z == c.z_min);
+        const bool cx = cz || (c.bounded && (p.x == c.lbx || p.x == c.ubx));
+        const bool cy = cz || (c.bounded && (p.y == c.lby || p.y == c.uby));
+        sw.x = cx ? 0.f : sw.x;
+        sw.y = cy ? 0.f : sw.y;
+    }
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) j[i] = v2mul(j[i], sw);
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) {
+#pragma unroll
+        for (int k = i; k < DOF; ++k) { acc2[idx] = v2fma(j[i], j[k], acc2[idx]); ++idx; }
+    }
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) acc2[NA + i] = v2fma(j[i], r, acc2[NA + i]);
 }
 
 // The same per-point quantities written out instead of reduced (evaluate_pnp with out_residual /

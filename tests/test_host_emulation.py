@@ -64,23 +64,27 @@ def test_point_math(emul, name):
     assert err_vs(cost, g["ref64_eval_cost"]) < 2e-5
     # normal equations = J^T J, J^T r, cost of the golden Jacobian
     NV = dof * (dof + 1) // 2 + dof + 1
-    ne = np.zeros((B, NV), np.float32)
-    emul.emul_normal_eq(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(pose),
-                        fptr(ne), clip, B, N, dof, ctypes.c_float(float(g["z_min"])), ctypes.c_float(1e-10))
     J, r = g["ref64_eval_jac"], g["ref64_eval_residual"]
     JtJ = np.einsum("bnd,bne->bde", J, J)
     iu = np.triu_indices(dof)
     want = np.concatenate([JtJ[:, iu[0], iu[1]], np.einsum("bnd,bn->bd", J, r), g["ref64_eval_cost"][:, None]], 1)
-    for b in range(B):
-        assert err_vs(ne[b, :-dof - 1], want[b, :-dof - 1]) < 5e-5
-        assert err_vs(ne[b, -dof - 1:-1], want[b, -dof - 1:-1]) < 5e-4    # J^T r: cancellation near the optimum
-    # cost of stacked poses (pre-multiplied projection path)
+    # scalar form (default build) and the row-packed form kept behind EPNP_LM_PACKED: same bounds
+    for fn in (emul.emul_normal_eq, emul.emul_normal_eq_rows):
+        ne = np.zeros((B, NV), np.float32)
+        fn(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(pose),
+           fptr(ne), clip, B, N, dof, ctypes.c_float(float(g["z_min"])), ctypes.c_float(1e-10))
+        for b in range(B):
+            assert err_vs(ne[b, :-dof - 1], want[b, :-dof - 1]) < 5e-5
+            assert err_vs(ne[b, -dof - 1:-1], want[b, -dof - 1:-1]) < 5e-4    # J^T r: cancellation near the optimum
+        assert err_vs(ne[:, -1], g["ref64_eval_cost"]) < 2e-5
+    # cost of stacked poses (pre-multiplied projection path): default form and the one-rsqrt form (EPNP_SWEEP_RSQ)
     poses = np.ascontiguousarray(g["eval_poses"], np.float32)
     S = poses.shape[0]
-    cm = np.zeros((S, B), np.float32)
-    emul.emul_cost(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(poses), fptr(cm),
-                   S, B, N, dof, ctypes.c_float(float(g["z_min"])))
-    assert err_vs(cm, g["ref64_eval_cost_multi"]) < 2e-5
+    for fn in (emul.emul_cost, emul.emul_cost_rsq):
+        cm = np.zeros((S, B), np.float32)
+        fn(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(poses), fptr(cm),
+           S, B, N, dof, ctypes.c_float(float(g["z_min"])))
+        assert err_vs(cm, g["ref64_eval_cost_multi"]) < 2e-5
 
 
 @pytest.mark.parametrize("name", golden_names())
