@@ -23,6 +23,17 @@
 
 #include "pnp_math.cuh"
 
+// Kernel launches and the dynamic shared-memory declaration are spelled through two macros so that this file also
+// builds, unchanged, under the test-only SIMT emulator (tests/simt_emul, g++ -DEPNP_SIMT_EMUL) that lets the CPU
+// suite execute the kernels' control flow.  In the nvcc build they expand to the plain CUDA forms.
+#if defined(EPNP_SIMT_EMUL)
+#define EPNP_LAUNCH(kern, grid, block, smem, stream, ...) simt::launch(grid, block, smem, [&] { kern(__VA_ARGS__); })
+#define EPNP_DYN_SMEM(type, name, align) type* name = reinterpret_cast<type*>(simt::state().dyn_smem)
+#else
+#define EPNP_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define EPNP_DYN_SMEM(type, name, align) extern __shared__ __align__(align) type name[]
+#endif
+
 namespace {
 using namespace pnp;
 
@@ -61,6 +72,23 @@ enum Phase { PH_LOAD = 0, PH_LM_EVAL, PH_LM_SERIAL, PH_COV, PH_INIT_FIT, PH_DRAW
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers: mbarrier + 1-D TMA bulk copy
+#if defined(EPNP_SIMT_EMUL)
+// emulator: an mbarrier word is {completed phases (low 32 bits), bytes still expected (high 32 bits)}; a bulk copy
+// is a memcpy that retires its bytes and completes the phase when none are left; waiting on a parity yields to the
+// other fibers until that phase has completed.  Exact libm stands in for the approximate special-function units.
+inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+inline void fence_barrier_init() {}
+inline void fence_proxy_async() {}
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { *bar += (uint64_t)bytes << 32; }
+inline void mbar_wait(uint64_t* bar, uint32_t parity) { while (((uint32_t)*bar & 1u) == parity) simt::yield(); }
+inline void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    std::memcpy(dst_smem, src, bytes);
+    *bar -= (uint64_t)bytes << 32;
+    if ((*bar >> 32) == 0) *bar = (uint32_t)*bar + 1u;
+}
+struct FastRcp { float operator()(float x) const { return 1.0f / x; } };
+struct FastSqrt { float operator()(float x) const { return sqrtf(x); } };
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -95,6 +123,7 @@ struct FastRcp {
 struct FastSqrt {
     __device__ __forceinline__ float operator()(float x) const { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 };
+#endif
 
 // ------------------------------------------------------------------------------------------------
 struct KArgs {
@@ -464,9 +493,13 @@ __device__ __forceinline__ float2 pair_cost(const float2 (&P2)[12], const Cam& c
 //   EPNP_SWEEP_RSQ      the formulation itself
 //   EPNP_SWEEP_NOCLAMP  + drop the z clamp when pose_depth_margin() proves it idle for the whole warp
 //   EPNP_SWEEP_SPLIT    + two samples per thread over half of the points each (pair-record loads amortised)
+#if defined(EPNP_SIMT_EMUL)
+struct SweepRsqrt { float operator()(float x) const { return 1.0f / sqrtf(x); } };
+#else
 struct SweepRsqrt {
     __device__ __forceinline__ float operator()(float x) const { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 };
+#endif
 template <bool BOUNDED, bool CLAMPZ>
 __device__ __forceinline__ float2 pair_cost_acc(const float2 (&P2)[12], const Cam& cam, float delta, float2 acc,
                                                 const float4 q0, const float4 q1, const float4 q2, const float4 q3) {
@@ -987,7 +1020,7 @@ __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, 
 // Kernels
 template <int DOF, bool DO_LM, bool DO_AMIS>
 __global__ void __launch_bounds__(NT, 4) solve_kernel(const KArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
     SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
     float* dyn = reinterpret_cast<float*>(smem_raw);
     const SmemPlan pl = plan_smem<DOF>(a.N, a.p.mc_samples, a.p.mc_iter, DO_AMIS);
@@ -1024,7 +1057,7 @@ __global__ void __launch_bounds__(NT, 4) solve_kernel(const KArgs a) {
 // cost of S poses per object: poses (S, B, D) -> cost (S, B)
 template <int DOF>
 __global__ void __launch_bounds__(NT, 4) cost_kernel(const KArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
     SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
     float* dyn = reinterpret_cast<float*>(smem_raw);
     const SmemPlan pl = plan_smem<DOF>(a.N, 0, 0, false);
@@ -1091,9 +1124,13 @@ __global__ void __launch_bounds__(NT) evaluate_full_kernel(const KArgs a, float*
 constexpr int BW_PPT = 4;               // correspondences per thread and tile
 constexpr int BW_POSE_TILE = 1024;      // poses staged per tile (13 floats each)
 
+#if defined(EPNP_SIMT_EMUL)
+struct FastRsqrt { float operator()(float x) const { return 1.0f / sqrtf(x); } };
+#else
 struct FastRsqrt {
     __device__ __forceinline__ float operator()(float x) const { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 };
+#endif
 
 // Reverse mode of the cost for TWO correspondences at once (packed fp32x2; same math per half as
 // pnp::point_cost_backward, with s = s2 * rsqrt(s2) and delta / s = delta * rsqrt(s2) from one MUFU.RSQ).
@@ -1152,7 +1189,7 @@ struct BwArgs {
 
 template <int DOF>
 __global__ void __launch_bounds__(NT, 4) cost_backward_kernel(const BwArgs a) {
-    extern __shared__ __align__(16) float bw_smem[];
+    EPNP_DYN_SMEM(float, bw_smem, 16);
     float* Pm = bw_smem;                                 // [tile][12]
     float* gs = bw_smem + BW_POSE_TILE * 12;             // [tile]
     float* red = gs + BW_POSE_TILE;                      // 2 * NW * 32
@@ -1311,7 +1348,7 @@ int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream) 
         rounds = (k <= 0) ? persistent_rounds : (k < persistent_rounds ? k : persistent_rounds);
     }
     const int grid = (a.B + rounds - 1) / rounds;
-    kern<<<grid, NT, smem_bytes, stream>>>(a);
+    EPNP_LAUNCH(kern, grid, NT, smem_bytes, stream, a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
     return EPNP_OK;
@@ -1375,7 +1412,7 @@ int epnp_adaptive_delta_f32(const float* x2d, const float* w2d, float relative_d
                             void* stream) {
     if (!x2d || !w2d || !delta || B < 0 || N <= 0) return EPNP_ERR_BAD_ARG;
     if (B == 0) return EPNP_OK;
-    adaptive_delta_kernel<<<B, NT, 0, (cudaStream_t)stream>>>(x2d, w2d, relative_delta, delta, N);
+    EPNP_LAUNCH(adaptive_delta_kernel, B, NT, 0, (cudaStream_t)stream, x2d, w2d, relative_delta, delta, N);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
 }
@@ -1409,8 +1446,8 @@ int epnp_evaluate_f32(const float* x3d, const float* x2d, const float* w2d, cons
     if (rc != EPNP_OK) return rc;
     if (!pose) return EPNP_ERR_BAD_ARG;
     if (B == 0) return EPNP_OK;
-    if (dof == 6) evaluate_full_kernel<6><<<B, NT, 0, (cudaStream_t)stream>>>(a, residual, jac, cost, clip_jac, huber_eps);
-    else evaluate_full_kernel<4><<<B, NT, 0, (cudaStream_t)stream>>>(a, residual, jac, cost, clip_jac, huber_eps);
+    if (dof == 6) EPNP_LAUNCH(evaluate_full_kernel<6>, B, NT, 0, (cudaStream_t)stream, a, residual, jac, cost, clip_jac, huber_eps);
+    else EPNP_LAUNCH(evaluate_full_kernel<4>, B, NT, 0, (cudaStream_t)stream, a, residual, jac, cost, clip_jac, huber_eps);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
 }
@@ -1511,10 +1548,10 @@ int epnp_cost_backward_f32(const float* x3d, const float* x2d, const float* w2d,
     const int grid = B < sms * 4 ? B : sms * 4;
     if (dof == 6) {
         if ((e = cudaFuncSetAttribute(cost_backward_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return cuda_fail(e);
-        cost_backward_kernel<6><<<grid, NT, smem, (cudaStream_t)stream>>>(a);
+        EPNP_LAUNCH(cost_backward_kernel<6>, grid, NT, smem, (cudaStream_t)stream, a);
     } else {
         if ((e = cudaFuncSetAttribute(cost_backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return cuda_fail(e);
-        cost_backward_kernel<4><<<grid, NT, smem, (cudaStream_t)stream>>>(a);
+        EPNP_LAUNCH(cost_backward_kernel<4>, grid, NT, smem, (cudaStream_t)stream, a);
     }
     e = cudaGetLastError();
     return e == cudaSuccess ? EPNP_OK : cuda_fail(e);

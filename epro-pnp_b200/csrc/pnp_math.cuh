@@ -43,7 +43,7 @@ template <int DOF> struct Dim {
 // ------------------------------------------------------------------------------------------------
 // Two-lane fp32 value.  On sm_100a each op below is ONE packed instruction (FFMA2 / FMUL2 / FADD2); the host
 // build evaluates the lanes with scalar fmaf so the packed formulas can be checked on the CPU.
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(EPNP_SIMT_EMUL)
 typedef float2 V2;
 #else
 struct alignas(8) V2 { float x, y; };

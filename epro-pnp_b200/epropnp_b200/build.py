@@ -21,6 +21,18 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE]
 
 
+# Build-option experiments of the kernels: off in the shipped build; tools/variants.py builds
+# and A/Bs them on a GPU box, tests/test_simt_emul_cpu.py runs them under the CPU SIMT emulator.
+EXPERIMENTS = {
+    "lm_packed": ["-DEPNP_LM_PACKED"],
+    "sweep_rsq": ["-DEPNP_SWEEP_RSQ"],
+    "sweep_noclamp": ["-DEPNP_SWEEP_NOCLAMP"],
+    "sweep_split": ["-DEPNP_SWEEP_SPLIT"],
+    "sweep_split_noclamp": ["-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
+    "all": ["-DEPNP_LM_PACKED", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
+}
+
+
 def _newer(target, sources):
     if not os.path.exists(target):
         return True

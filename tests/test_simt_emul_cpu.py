@@ -1,0 +1,96 @@
+"""The REAL kernel source on the CPU: epro-pnp_b200/csrc/pnp_kernels.cu compiled by g++ against the SIMT emulator
+in tests/simt_emul/ (128 fibers per CTA, barriers and warp shuffles emulated), driven through the same C ABI /
+epropnp_b200.native / drop-in classes as on the GPU, and held to the SAME assertions as the `-m gpu` parity tests --
+the test functions below are the GPU suite's own, re-collected here with a `cuda_device` fixture that installs the
+emulated backend.
+
+Scope (see tests/simt_emul/cuda_runtime.h): control flow, shared-memory bookkeeping, reductions, the LM state machine
+and the AMIS loop of the shipped kernels, plus the C ABI's argument handling.  Not covered: races, TMA / mbarrier
+phases, approximate special-function units, performance -- those are what `-m gpu` is for.
+"""
+import pytest
+import torch
+
+import simt_native
+import test_autograd_gpu as _ag
+import test_dropin_gpu as _dg
+import test_gpu_edges as _ge
+import test_gpu_parity as _gp
+
+
+@pytest.fixture
+def cuda_device(monkeypatch):
+    return simt_native.install(monkeypatch)
+
+
+# ---- goldens and oracle comparisons of the GPU parity suite
+test_golden_evaluate = _gp.test_golden_evaluate
+test_golden_lm_solve = _gp.test_golden_lm_solve
+test_golden_amis_from_reference_solution = _gp.test_golden_amis_from_reference_solution
+test_golden_fused_lm_amis = _gp.test_golden_fused_lm_amis
+test_golden_fused_lm_amis_4dof = _gp.test_golden_fused_lm_amis_4dof
+
+# ---- edge cases
+test_parameter_corners_against_oracle = _ge.test_parameter_corners_against_oracle
+test_tiny_point_sets = _ge.test_tiny_point_sets
+test_all_points_behind_camera = _ge.test_all_points_behind_camera
+test_nan_object_does_not_leak = _ge.test_nan_object_does_not_leak
+
+# ---- the drop-in classes on top of the emulated kernels
+test_lmsolver_forward = _dg.test_lmsolver_forward
+test_evaluate_pnp_semantics = _dg.test_evaluate_pnp_semantics
+test_monte_carlo_forward = _dg.test_monte_carlo_forward
+test_layer_forward_and_4dof = _dg.test_layer_forward_and_4dof
+# (test_rslm_init_and_force_init_solve is left to the GPU: its ~10^4 tiny LM solves take minutes under emulation)
+
+# ---- backward kernel and the autograd bridge
+test_monte_carlo_backward_matches_reference = _ag.test_monte_carlo_backward_matches_reference
+test_cost_backward_kernel_against_oracle_autograd = _ag.test_cost_backward_kernel_against_oracle_autograd
+test_evaluate_pnp_cost_is_differentiable = _ag.test_evaluate_pnp_cost_is_differentiable
+
+
+# ------------------------------------------------------------------------------------------------
+# The build-option experiments (epropnp_b200.build.EXPERIMENTS): each variant's kernel source
+# under the emulator, on the assertions of the GPU suite that exercise the code it changes.
+from conftest import golden_names  # noqa: E402
+from epropnp_b200.build import EXPERIMENTS  # noqa: E402
+
+
+@pytest.fixture(params=sorted(EXPERIMENTS))
+def variant_device(request, monkeypatch):
+    return simt_native.install(monkeypatch, EXPERIMENTS[request.param])
+
+
+@pytest.mark.parametrize("name", golden_names("mc6"))
+def test_variant_golden_fused_lm_amis(variant_device, name):
+    _gp.test_golden_fused_lm_amis(variant_device, name)
+
+
+@pytest.mark.parametrize("name", golden_names("mc6"))
+def test_variant_golden_amis(variant_device, name):
+    _gp.test_golden_amis_from_reference_solution(variant_device, name)
+
+
+def test_variant_golden_fused_4dof(variant_device):
+    _gp.test_golden_fused_lm_amis_4dof(variant_device)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_variant_golden_lm_and_cost(variant_device, name):
+    _gp.test_golden_evaluate(variant_device, name)
+    _gp.test_golden_lm_solve(variant_device, name)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 7])
+def test_variant_tiny_point_sets(variant_device, N):
+    _ge.test_tiny_point_sets(variant_device, N)
+
+
+def test_variant_degenerate_inputs(variant_device):
+    _ge.test_all_points_behind_camera(variant_device)
+    _ge.test_nan_object_does_not_leak(variant_device)
+
+
+@pytest.mark.parametrize("M,I,acg,lm_iter", [(128, 1, 3, 10), (126, 2, 1, 5), (1024, 8, 2, 4)])
+def test_variant_parameter_corners(variant_device, M, I, acg, lm_iter):
+    _ge.test_parameter_corners_against_oracle(variant_device, M, I, acg, lm_iter)

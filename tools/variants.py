@@ -30,15 +30,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(REPO, "epro-pnp_b200"))
 from epropnp_b200 import build as B  # noqa: E402
 
-VARIANTS = collections.OrderedDict([
-    ("default", []),
-    ("lm_packed", ["-DEPNP_LM_PACKED"]),
-    ("sweep_rsq", ["-DEPNP_SWEEP_RSQ"]),
-    ("sweep_noclamp", ["-DEPNP_SWEEP_NOCLAMP"]),
-    ("sweep_split", ["-DEPNP_SWEEP_SPLIT"]),
-    ("sweep_split_noclamp", ["-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"]),
-    ("all", ["-DEPNP_LM_PACKED", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"]),
-])
+VARIANTS = collections.OrderedDict([("default", [])] + list(B.EXPERIMENTS.items()))
 VDIR = os.path.join(B.LIB_DIR, "variants")
 SRC = os.path.join(B.CSRC, "pnp_kernels.cu")
 
