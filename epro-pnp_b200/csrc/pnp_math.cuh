@@ -658,7 +658,11 @@ template <int DOF> PNP_HD void lm_propose(LMState<DOF>& s, const Params& p) {
         const float d = s.a[tri(i, i, DOF)];
         add[i] = fmaf(fminf(fmaxf(d, p.min_lm_diagonal), p.max_lm_diagonal), inv_radius, p.eps);
     }
+#if defined(EPNP_LM_NOREFINE)
+    s.model_change = damped_step<DOF, float>(s.a, s.g, add, step);       // experiment: plain fp32 step
+#else
     s.model_change = damped_step_refined<DOF>(s.a, s.g, add, step);
+#endif
     pose_add<DOF>(s.pose, step, s.pose_new);
 }
 

@@ -30,6 +30,8 @@ EXPERIMENTS = {
     "sweep_split": ["-DEPNP_SWEEP_SPLIT"],
     "sweep_split_noclamp": ["-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
     "all": ["-DEPNP_LM_PACKED", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
+    "lm_norefine": ["-DEPNP_LM_NOREFINE"],
+    "all_norefine": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
 }
 
 
