@@ -242,6 +242,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
+                    help="N > 1: 'nccl' = overlapped all_gather_into_tensor (default, the measured configuration); "
+                         "'peer' = copy-engine pulls from IPC-mapped peer buffers (sharded.PeerGather, experimental)")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="objects per GPU (default: the metric's 4096)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -255,7 +258,7 @@ def main():
 
     import torch.distributed as dist
     from epropnp_b200 import native
-    from epropnp_b200.sharded import gather_results_async
+    from epropnp_b200.sharded import PeerGather, gather_results_async
     from epropnp_b200.synth import make_problem
 
     torch.cuda.set_device(local_rank)
@@ -288,17 +291,23 @@ def main():
                                     want_cost=True, want_cost_init=False)
 
     pending = None
+    peer_gather = None
 
     def step(i):
         """One batch: fused solve, then the gather of (pose_opt, logw).  For N > 1 the gather is asynchronous and the
         previous batch's gather is awaited only after this batch's solve is enqueued, so exchange i overlaps solve
         i+1 (batches are independent); every gather completes inside the timed region (drain() before t_end)."""
-        nonlocal pending
+        nonlocal pending, peer_gather
         out = solve(i)
         if world > 1:
             if pending is not None:
                 pending.wait()
-            pending = gather_results_async(out, B_total, keys=("pose_opt", "logw"))
+            if args.gather == "peer":
+                if peer_gather is None:
+                    peer_gather = PeerGather(out, B_total, keys=("pose_opt", "logw"), depth=3)
+                pending = peer_gather.start(out)
+            else:
+                pending = gather_results_async(out, B_total, keys=("pose_opt", "logw"))
         return out
 
     def drain():
@@ -411,7 +420,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"fused EProPnP6DoF.monte_carlo_forward: LM({LM_ITER}) + cov + AMIS({MC_ITER}x"
                                    f"{MC_SAMPLES // MC_ITER}), B={Bg}/GPU, N={N_PTS}, M={MC_SAMPLES}, in-kernel Philox",
-                       "global_batch": B_total, "parallelism": f"batch-split x{world}, gather(pose,logw) only, gather of batch i overlapped with solve of batch i+1",
+                       "global_batch": B_total, "parallelism": f"batch-split x{world}, gather(pose,logw) only ({args.gather}), gather of batch i overlapped with solve of batch i+1",
                        "l2": f"rotating {ROTATING_SETS} input sets ({ROTATING_SETS * 28 * N_PTS * Bg / 1e6:.0f} MB > 126 MB L2)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(), "peak_source": peak_src,
