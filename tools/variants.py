@@ -133,7 +133,7 @@ def cmd_run(args):
             vals = []
             for _ in range(args.repeats):
                 b = subprocess.run(["timeout", "600", sys.executable, "bench.py", "--steps", str(args.steps), "--warmup",
-                                    str(args.warmup), "--no-cpu-baseline"], cwd=REPO, env=env, capture_output=True, text=True)
+                                    str(args.warmup), "--no-cpu-baseline", "--no-e2e"], cwd=REPO, env=env, capture_output=True, text=True)
                 line = [l for l in b.stdout.splitlines() if l.startswith("{")]
                 if b.returncode == 0 and line:
                     j = json.loads(line[-1])
@@ -160,11 +160,12 @@ if __name__ == "__main__":
         if name == "build":
             p.add_argument("--force", action="store_true")
         if name == "run":
-            p.add_argument("--tests", default="tests/test_gpu_parity.py tests/test_gpu_edges.py tests/test_dropin_gpu.py")
+            p.add_argument("--tests", default="tests/test_gpu_parity.py tests/test_gpu_edges.py",
+                           help="pytest selection run per variant (add '-k golden' for a quicker pass)")
             p.add_argument("--test-timeout", type=int, default=900)
-            p.add_argument("--steps", type=int, default=200)
+            p.add_argument("--steps", type=int, default=300)
             p.add_argument("--warmup", type=int, default=5)
-            p.add_argument("--repeats", type=int, default=2)
+            p.add_argument("--repeats", type=int, default=1)
     a = ap.parse_args()
     for n in a.names:
         if n not in VARIANTS:
