@@ -30,6 +30,8 @@ test_golden_amis_from_reference_solution = _gp.test_golden_amis_from_reference_s
 test_golden_fused_lm_amis = _gp.test_golden_fused_lm_amis
 test_golden_fused_lm_amis_4dof = _gp.test_golden_fused_lm_amis_4dof
 
+test_fused_against_oracle_north_star_shape = _gp.test_fused_against_oracle_north_star_shape
+
 # ---- edge cases
 test_parameter_corners_against_oracle = _ge.test_parameter_corners_against_oracle
 test_tiny_point_sets = _ge.test_tiny_point_sets
@@ -99,3 +101,10 @@ def test_variant_degenerate_inputs(variant_device):
 @pytest.mark.parametrize("M,I,acg,lm_iter", [(128, 1, 3, 10), (126, 2, 1, 5), (1024, 8, 2, 4)])
 def test_variant_parameter_corners(variant_device, M, I, acg, lm_iter):
     _ge.test_parameter_corners_against_oracle(variant_device, M, I, acg, lm_iter)
+
+
+@pytest.mark.parametrize("variant", ["all", "all_norefine"])
+def test_variant_north_star_shape(monkeypatch, variant):
+    """N = 512, M = 512 against the fp64 / fp32 oracle, including the north star's own <= 1e-4 statement."""
+    dev = simt_native.install(monkeypatch, EXPERIMENTS[variant])
+    _gp.test_fused_against_oracle_north_star_shape(dev, 48, 512, 512, 4)
