@@ -7,6 +7,7 @@ batched hot loops run in hand-written sm_100a CUDA behind libepropnp_b200.so:
     epropnp.cost_fun              HuberPnPCost / AdaptiveHuberPnPCost
     epropnp.common                evaluate_pnp, pnp_normalize, pnp_denormalize, rotation helpers
     epropnp.distributions         AngularCentralGaussian / VonMisesUniformMix
+    epropnp.builder               build_pnp / build_camera / build_cost_fun + registries (detection-style configs)
 
 Put `<repo>/epro-pnp_b200` on sys.path (instead of the reference checkout) and existing imports keep
 working.  The solve / Monte-Carlo paths have no CPU or PyTorch fallback: CPU tensors raise.

@@ -6,9 +6,11 @@ torch ops and is not what LMSolver / EProPnP* execute).
 """
 import torch
 
+from .builder import CAMERA
 from .common import _pose_rot, skew
 
 
+@CAMERA.register_module()
 class PerspectiveCamera(object):
 
     def __init__(self, cam_mats=None, z_min=0.1, img_shape=None, allowed_border=200, lb=None, ub=None):

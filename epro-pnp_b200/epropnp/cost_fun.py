@@ -7,6 +7,7 @@ callers that already hold projected points; it is a few elementwise torch ops an
 import torch
 
 from epropnp_b200 import native
+from .builder import COSTFUN
 
 
 def huber_kernel(s_sqrt, delta):
@@ -50,6 +51,7 @@ class _DeltaHolder(object):
         return self._apply(lambda d: d.repeat(*batch_repeat))
 
 
+@COSTFUN.register_module()
 class HuberPnPCost(_DeltaHolder):
 
     def __init__(self, delta=1.0, eps=1e-10):
@@ -89,6 +91,7 @@ class HuberPnPCost(_DeltaHolder):
         return HuberPnPCost(delta=self.delta, eps=self.eps)
 
 
+@COSTFUN.register_module()
 class AdaptiveHuberPnPCost(HuberPnPCost):
     """Huber threshold tied to the data: delta_b = relative_delta * mean(w2d_b) * std(x2d_b)."""
 

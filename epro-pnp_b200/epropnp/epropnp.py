@@ -20,6 +20,7 @@ from abc import ABCMeta, abstractmethod
 import torch
 
 from epropnp_b200 import native
+from .builder import PNP, build_pnp
 from .common import evaluate_pnp, pnp_normalize, pnp_denormalize
 
 
@@ -55,7 +56,7 @@ class EProPnPBase(torch.nn.Module, metaclass=ABCMeta):
         self.iter_samples = self.mc_samples // self.num_iter
         self.eps = eps
         self.normalize = normalize
-        self.solver = solver
+        self.solver = build_pnp(solver)                  # instance, None, or a config dict
 
     @property
     @abstractmethod
@@ -149,6 +150,7 @@ class EProPnPBase(torch.nn.Module, metaclass=ABCMeta):
         return pose_opt, cost, pose_opt_plus, pose_samples, logw, cost_init
 
 
+@PNP.register_module()
 class EProPnP4DoF(EProPnPBase):
     """4DoF pose [x, y, z, yaw]; proposals: translation ~ multivariate t (df 3), yaw ~ 0.75 von Mises +
     0.25 uniform (reference epropnp.py:199-260).  `amis_noise` = (normal3 (B,M,3), chi2 (B,M), yaw (B,M)):
@@ -158,6 +160,7 @@ class EProPnP4DoF(EProPnPBase):
     dof = 4
 
 
+@PNP.register_module()
 class EProPnP6DoF(EProPnPBase):
     """6DoF pose [x, y, z, w, i, j, k]; proposals: translation ~ multivariate t (df 3), orientation ~
     angular central Gaussian (reference epropnp.py:263-342)."""

@@ -15,6 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from epropnp_b200 import native
+from .builder import PNP, build_pnp
 from .common import evaluate_pnp, pnp_normalize, pnp_denormalize
 
 
@@ -25,6 +26,7 @@ def solve_wrapper(b, A):
     return b + A.reshape_as(b)
 
 
+@PNP.register_module()
 class LMSolver(nn.Module):
     """Levenberg-Marquardt solver with a fixed number of iterations.
 
@@ -43,7 +45,7 @@ class LMSolver(nn.Module):
         self.max_trust_region_radius = max_trust_region_radius
         self.eps = eps
         self.normalize = normalize
-        self.init_solver = init_solver
+        self.init_solver = build_pnp(init_solver)        # instance, None, or a config dict (detection-style configs)
 
     # ------------------------------------------------------------------ native parameter block
     def native_params(self, camera, cost_fun, fast_mode=False, **extra):
@@ -136,6 +138,7 @@ class LMSolver(nn.Module):
         return torch.cat((pose_opt[..., :3] + step[..., :3], F.normalize(q + dq, dim=-1)), dim=-1)
 
 
+@PNP.register_module()
 class RSLMSolver(LMSolver):
     """Random-sample LM: a RANSAC-like initialiser for ambiguous problems (levenberg_marquardt.py:268-353)."""
 

@@ -171,3 +171,35 @@ def test_autograd_bridge_against_reference_gradients(name):
     # evaluate_pnp cost with gradients
     c = evaluate_pnp(x3d, x2d, w2d, pose_init, camera, cost_fun, out_cost=True)[1]
     assert c.requires_grad and err_vs(c.detach(), g["ref64_grad_cost_init"]) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ config builders
+def test_builders_construct_nested_configs():
+    """Detection-style configs (EPro-PnP-Det/configs/*: dicts with `type`, nested solver / init_solver)."""
+    from epropnp.builder import CAMERA, COSTFUN, PNP, build_camera, build_cost_fun, build_pnp
+    from epropnp.camera import PerspectiveCamera
+    from epropnp.cost_fun import AdaptiveHuberPnPCost
+    from epropnp.epropnp import EProPnP4DoF, EProPnP6DoF
+    from epropnp.levenberg_marquardt import LMSolver, RSLMSolver
+    assert {"LMSolver", "RSLMSolver", "EProPnP4DoF", "EProPnP6DoF"} <= set(PNP.module_dict)
+    assert "PerspectiveCamera" in CAMERA and {"HuberPnPCost", "AdaptiveHuberPnPCost"} <= set(COSTFUN.module_dict)
+    pnp = build_pnp(dict(type="EProPnP4DoF", mc_samples=512, num_iter=4,
+                         solver=dict(type="LMSolver", dof=4, num_iter=5,
+                                     init_solver=dict(type="RSLMSolver", dof=4, num_points=16, num_proposals=64, num_iter=3))))
+    assert isinstance(pnp, EProPnP4DoF) and isinstance(pnp.solver, LMSolver) and pnp.solver.num_iter == 5
+    assert isinstance(pnp.solver.init_solver, RSLMSolver) and pnp.solver.init_solver.num_proposals == 64
+    assert pnp.iter_samples == 128
+    cam = build_camera(dict(type="PerspectiveCamera"), z_min=0.5)
+    assert isinstance(cam, PerspectiveCamera) and cam.z_min == 0.5
+    cost = build_cost_fun(dict(type="AdaptiveHuberPnPCost", relative_delta=0.5))
+    assert isinstance(cost, AdaptiveHuberPnPCost)
+    # instances pass through (canonical / 6DoF style), unknown names and missing `type` are errors
+    solver = LMSolver(dof=6)
+    assert EProPnP6DoF(solver=solver).solver is solver
+    assert build_pnp(dict(type=EProPnP6DoF, mc_samples=64, num_iter=2, solver=solver)).mc_samples == 64
+    with pytest.raises(KeyError):
+        build_pnp(dict(type="NoSuchSolver"))
+    with pytest.raises(KeyError):
+        build_pnp(dict(dof=4))
+    with pytest.raises(KeyError):
+        PNP.register_module(module=LMSolver)          # duplicate registration
