@@ -1,0 +1,81 @@
+"""The 6DoF repository's call sequences (EPro-PnP-6DoF/lib/train.py:157-193, lib/test.py:196-221) on the drop-in
+package with the kernels under the CPU SIMT emulator: sub-sampled dense correspondences (advanced indexing, expanded
+camera matrix, per-object tensor bounds), training forward with pose_init / force_init_solve / with_pose_opt_plus and
+the three losses back-propagated, then the test-time Gauss-Newton path and the visualisation Monte-Carlo pass."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import simt_native
+from epropnp.camera import PerspectiveCamera
+from epropnp.cost_fun import AdaptiveHuberPnPCost
+from epropnp.epropnp import EProPnP6DoF
+from epropnp.levenberg_marquardt import LMSolver, RSLMSolver
+from epropnp_b200.synth import make_problem
+
+
+@pytest.fixture
+def dev(monkeypatch):
+    return simt_native.install(monkeypatch)
+
+
+def _dense_batch(bs, res, seed):
+    pc = make_problem(bs, res * res, seed=seed, grid2d=True)
+    rng = np.random.RandomState(seed)
+    keep = torch.from_numpy(np.stack([rng.choice(res * res, size=res * res // 4, replace=False) for _ in range(bs)]))
+    rows = torch.arange(bs)[:, None]
+    return pc, pc["x3d"][rows, keep], pc["x2d"][rows, keep], keep, rows
+
+
+def test_training_step(dev):
+    bs, res = 3, 16
+    pc, x3d0, x2d, keep, rows = _dense_batch(bs, res, seed=31)
+    x3d = x3d0.clone().requires_grad_(True)
+    w_logit = (0.3 * torch.randn(bs, res * res, 2, generator=torch.Generator().manual_seed(1))).requires_grad_(True)
+    scale = torch.full((bs, 2), 40.0, requires_grad=True)
+    w2d = w_logit[rows, keep]
+    w2d = (w2d - w2d.mean(dim=1, keepdim=True) - math.log(w2d.size(1))).exp() * scale[:, None, :]   # train.py:164
+    lo, hi = x2d.amin(dim=1), x2d.amax(dim=1)
+    camera = PerspectiveCamera(cam_mats=pc["cam_mats"][0][None].expand(bs, -1, -1), z_min=0.01,
+                               lb=lo - 30.0, ub=hi + 30.0)
+    cost_fun = AdaptiveHuberPnPCost(relative_delta=0.1)
+    cost_fun.set_param(x2d, w2d)
+    assert cost_fun.delta.requires_grad                      # delta depends on w2d: gradients flow through it
+    epropnp = EProPnP6DoF(mc_samples=128, num_iter=4,
+                          solver=LMSolver(dof=6, num_iter=5,
+                                          init_solver=RSLMSolver(dof=6, num_points=8, num_proposals=8, num_iter=3)))
+    gt = pc["pose_gt"]
+    torch.manual_seed(7)
+    _, _, pose_opt_plus, _, logw, cost_tgt = epropnp.monte_carlo_forward(
+        x3d, x2d, w2d, camera, cost_fun, pose_init=gt, force_init_solve=True, with_pose_opt_plus=True)
+    loss_mc = (cost_tgt + torch.logsumexp(logw, dim=0)).mean() / 10.0                # monte_carlo_pose_loss.py:27-33
+    loss_t = (pose_opt_plus[:, :3] - gt[:, :3]).norm(dim=-1)
+    loss_t = torch.where(loss_t < 0.05, 0.5 * loss_t.square() / 0.05, loss_t - 0.025).mean()
+    dot = (pose_opt_plus[:, None, 3:] @ gt[:, 3:, None]).squeeze(-1).squeeze(-1)
+    loss_r = ((1 - dot.square()) * 2).mean()
+    (0.02 * loss_mc + 0.1 * loss_t + 0.1 * loss_r).backward()
+    for t in (x3d, w_logit, scale):
+        assert t.grad is not None and torch.isfinite(t.grad).all() and t.grad.abs().sum() > 0
+    unused = torch.ones(bs, res * res, dtype=torch.bool)
+    unused[rows, keep] = False
+    assert w_logit.grad[unused].abs().sum() == 0             # only the sampled correspondences receive gradient
+
+
+def test_inference_step(dev):
+    bs, res = 2, 16
+    pc = make_problem(bs, res * res, seed=32, grid2d=True)
+    x3d, x2d, w2d = pc["x3d"], pc["x2d"], pc["w2d"]
+    camera = PerspectiveCamera(cam_mats=pc["cam_mats"][0][None].expand(bs, -1, -1), z_min=0.01)
+    cost_fun = AdaptiveHuberPnPCost(relative_delta=0.1)
+    epropnp = EProPnP6DoF(mc_samples=128, num_iter=4, solver=LMSolver(dof=6, num_iter=3))
+    with torch.no_grad():
+        cost_fun.set_param(x2d, w2d)
+        pose_opt = epropnp(x3d, x2d, w2d, camera, cost_fun, pose_init=pc["pose_init"], fast_mode=True)[0]
+        _, _, _, samples, logw, _ = epropnp.monte_carlo_forward(x3d, x2d, w2d, camera, cost_fun, pose_init=pose_opt,
+                                                               force_init_solve=False, fast_mode=True)
+    gt = pc["pose_gt"]
+    assert ((pose_opt[:, :3] - gt[:, :3]).norm(dim=-1) < 0.05).all()
+    assert (1 - (pose_opt[:, 3:] * gt[:, 3:]).sum(-1).abs() < 1e-3).all()
+    assert samples[:, :1].shape == (128, 1, 7) and logw[:, :1].shape == (128, 1) and torch.isfinite(logw).all()
