@@ -6,8 +6,10 @@
 // What this buys the CPU suite (-m "not gpu"): the REAL kernel source -- staging and pair-record packing, the
 // block reductions, the LM state machine, the AMIS loop and its shared-memory bookkeeping, the C ABI's argument
 // handling -- runs against the golden vectors without a GPU, including the build-option experiments
-// (tools/variants.py).  What it cannot show: memory-model races, TMA / mbarrier phase logic (bulk copies complete
-// synchronously here), the approximate special-function units (exact libm here), performance.
+// (tools/variants.py).  Missing barriers are probed by re-running with the fibers scheduled in descending and in
+// randomly permuted order (simt_set_schedule): results must be bit-identical.  What it cannot show: memory-model /
+// async-proxy ordering, real TMA latency (bulk copies complete synchronously here), the approximate
+// special-function units (exact libm here), performance.
 // It is not a product path: the shipped library is nvcc-built and has no CPU fallback.
 #pragma once
 #include <ucontext.h>
@@ -77,6 +79,9 @@ inline uint3& bidx() { static uint3 v{0, 0, 0}; return v; }
 inline dim3& bdim() { static dim3 v; return v; }
 inline dim3& gdim() { static dim3 v; return v; }
 
+inline int& schedule_mode() { static int m = 0; return m; }
+inline uint64_t& schedule_seed() { static uint64_t v = 1; return v; }
+
 inline void yield() {
     BlockState& s = state();
     swapcontext(&s.fibers[s.cur].ctx, &s.sched);
@@ -142,9 +147,22 @@ inline void run_block(int nthreads, const std::function<void()>& body) {
         f.ctx.uc_link = &s.sched;
         makecontext(&f.ctx, (void (*)())fiber_main, 0);
     }
+    // Scheduling order of the fibers between synchronisation points: 0 = ascending thread index, 1 = descending,
+    // 2 = a fresh pseudo-random permutation every round.  Results must not depend on it: a kernel whose output
+    // changes with the order has an unsynchronised inter-thread dependency (what racecheck reports on hardware).
+    std::vector<int> order(nthreads);
+    for (int t = 0; t < nthreads; ++t) order[t] = (schedule_mode() == 1) ? nthreads - 1 - t : t;
+    uint64_t rng = schedule_seed() * 6364136223846793005ull + 1442695040888963407ull;
     long spins = 0;
     while (s.live > 0) {
-        for (int t = 0; t < nthreads; ++t) {
+        if (schedule_mode() == 2) {
+            for (int t = nthreads - 1; t > 0; --t) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(order[t], order[(int)((rng >> 33) % (uint64_t)(t + 1))]);
+            }
+        }
+        for (int i = 0; i < nthreads; ++i) {
+            const int t = order[i];
             if (s.fibers[t].done) continue;
             s.cur = t;
             tidx() = uint3{(unsigned)t, 0, 0};
@@ -219,3 +237,9 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(dst, src, n); return cudaSuccess; }
+
+// test hook: pick the fiber scheduling order (see run_block)
+extern "C" inline __attribute__((used, visibility("default"))) void simt_set_schedule(int mode, unsigned long long seed) {
+    simt::schedule_mode() = mode;
+    simt::schedule_seed() = seed;
+}

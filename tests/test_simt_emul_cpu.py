@@ -108,3 +108,43 @@ def test_variant_north_star_shape(monkeypatch, variant):
     """N = 512, M = 512 against the fp64 / fp32 oracle, including the north star's own <= 1e-4 statement."""
     dev = simt_native.install(monkeypatch, EXPERIMENTS[variant])
     _gp.test_fused_against_oracle_north_star_shape(dev, 48, 512, 512, 4)
+
+
+# ------------------------------------------------------------------------------------------------
+# Scheduling-order invariance: the emulator runs a CTA's threads one after another between synchronisation points.
+# Ascending, descending and randomly permuted orders must give bit-identical results; a difference means one thread
+# consumed what another produced without a barrier in between (the class of bug racecheck reports on hardware --
+# the round-1 `pad_last_pair` hazard is caught by exactly this test when re-introduced).
+def _all_outputs(dev, dof, odd_points):
+    from epropnp_b200 import native
+    from epropnp_b200.synth import make_noise, make_problem
+    B, N, M, I = 3, (37 if odd_points else 64), 128, 4
+    pc = make_problem(B, N, seed=77, dof=dof)
+    prob = native.Problem(pc["x3d"], pc["x2d"], pc["w2d"], pc["cam_mats"], -50.0, 700.0,
+                          native.adaptive_delta(pc["x2d"], pc["w2d"], 0.5))
+    p = native.default_params(dof, mc_samples=M, mc_iter=I)
+    out = native.lm_amis_fused(prob, pc["pose_init"], p, seed=5, want_cost=True, want_plus=True)
+    res = [out[k] for k in ("pose_opt", "pose_cov", "cost", "pose_opt_plus", "pose_samples", "logw")]
+    res.append(native.evaluate_cost(prob, out["pose_samples"].transpose(0, 1)[:9].contiguous(), dof, 0.1))
+    res.extend(native.evaluate_full(prob, pc["pose_init"], dof, 0.1, 1e-10, True, True, True, True))
+    grads = native.cost_backward(prob, dof, 0.1, out["pose_samples"], torch.ones(B, M) / M)
+    res.extend(g for g in grads if g is not None)
+    return [t.clone() for t in res if t is not None]
+
+
+@pytest.mark.parametrize("variant", ["default"] + EMULATED_VARIANTS)
+@pytest.mark.parametrize("dof,odd_points", [(6, False), (6, True), (4, True)])
+def test_results_do_not_depend_on_thread_schedule(monkeypatch, variant, dof, odd_points):
+    flags = EXPERIMENTS.get(variant, ())
+    dev = simt_native.install(monkeypatch, flags)
+    lib = simt_native.handle(flags)
+    try:
+        lib.simt_set_schedule(0, 1)
+        base = _all_outputs(dev, dof, odd_points)
+        for mode, seed in ((1, 1), (2, 11), (2, 12)):
+            lib.simt_set_schedule(mode, seed)
+            for a, b in zip(base, _all_outputs(dev, dof, odd_points)):
+                assert torch.equal(a, b, ) or (torch.isnan(a) == torch.isnan(b)).all() and torch.equal(
+                    torch.nan_to_num(a), torch.nan_to_num(b)), (variant, mode, seed)
+    finally:
+        lib.simt_set_schedule(0, 1)
