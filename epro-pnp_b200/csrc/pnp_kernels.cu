@@ -1080,6 +1080,125 @@ __global__ void __launch_bounds__(NT, 4) cost_kernel(const KArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Random-sample LM initialiser (RSLMSolver.solve, levenberg_marquardt.py:300-353) for one object per CTA:
+// thread <-> hypothesis.  A thread runs the whole LM / GN iteration of its hypothesis serially over that
+// hypothesis' n sampled correspondences (read out of the object's resident pair records: the (P*B, n, .) gathered
+// copies, the P-fold repeated cameras and the P*B tiny solves of the reference do not exist), scores the result
+// on ALL N points with the same sweep the AMIS loop uses, and the CTA keeps the cheapest hypothesis.
+struct RslmArgs {
+    KArgs k;                    // correspondences, camera, bounds, delta, B, N, LM parameters
+    const int* inds;            // (P, B, n) indices of the sampled correspondences, within the object
+    const float* start;         // (P, B, D) starting poses
+    float* pose_best;           // (B, D)
+    float* cost_best;           // (B)
+    float* pose_all;            // [opt] (P, B, D)
+    float* cost_all;            // [opt] (P, B)
+    int P, n;
+};
+
+// Order of torch.min over the hypotheses (levenberg_marquardt.py:350): a NaN cost wins (min propagates NaN), then the
+// smaller cost, then the earlier hypothesis.
+__device__ __forceinline__ bool cheaper_hypothesis(float c, int h, float wc, int wh) {
+    const bool cn = (c != c), wn = (wc != wc);
+    if (cn != wn) return cn;
+    if (cn) return h < wh;
+    return c < wc || (c == wc && h < wh);
+}
+
+template <int DOF, bool CLIP>
+__device__ __forceinline__ void eval_subset(const float* pts, const int* idx, int n, const float* pose, const Cam& cam,
+                                            float delta, float huber_eps, float* acc) {
+    constexpr int NV = Dim<DOF>::NV;
+    float R[9];
+    pose_to_rot<DOF>(pose, R);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+    for (int i = 0; i < n; ++i) {
+        const int j = __ldg(idx + i);
+        const float* q = pts + (j >> 1) * 16 + (j & 1);
+        point_normal_eq<DOF, CLIP>(R, pose, cam, delta, huber_eps, q[0], q[2], q[4], -q[6], -q[8], q[10], q[12], acc);
+    }
+}
+
+template <int DOF>
+__global__ void __launch_bounds__(NT, 2) rslm_kernel(const RslmArgs r) {
+    const KArgs& a = r.k;
+    EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
+    SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
+    float* dyn = reinterpret_cast<float*>(smem_raw);
+    const SmemPlan pl = plan_smem<DOF>(a.N, 0, 0, false);
+    float* pts = dyn + pl.pts;
+    constexpr int PD = Dim<DOF>::POSE;
+    const Params& p = a.p;
+    const int tid = threadIdx.x;
+    float* best_cost = sh.red;                                  // [NT]
+    int* best_hyp = reinterpret_cast<int*>(sh.red + NT);        // [NT]
+    Loader ld(a, sh.bar, dyn + pl.stage);
+    ld.prologue();
+    for (int it = 0; it < ld.n_my; ++it) {
+        const int obj = (int)blockIdx.x + it * (int)gridDim.x;
+        ld.load_object(it, obj, pts);
+        const Cam cam = load_cam(a, obj);
+        const float delta = __ldg(a.delta + obj);
+        float my_cost = CUDART_INF_F, my_pose[PD];
+        int my_hyp = -1;
+        for (int h = tid; h < r.P; h += NT) {
+            const int* idx = r.inds + ((size_t)h * a.B + obj) * r.n;
+            LMState<DOF> s;
+#pragma unroll
+            for (int i = 0; i < PD; ++i) s.pose[i] = __ldg(r.start + ((size_t)h * a.B + obj) * PD + i);
+            s.radius = p.initial_radius;
+            s.shrink = 2.0f;
+            float acc[Dim<DOF>::NV];
+            if (!p.fast_mode) {
+                eval_subset<DOF, true>(pts, idx, r.n, s.pose, cam, delta, p.huber_eps, acc);
+                lm_adopt<DOF>(s, acc);
+                if (p.lm_iter > 0) lm_propose<DOF>(s, p);
+                for (int k = 0; k < p.lm_iter; ++k) {
+                    eval_subset<DOF, true>(pts, idx, r.n, s.pose_new, cam, delta, p.huber_eps, acc);
+                    lm_update<DOF>(s, acc, p);
+                    if (k + 1 < p.lm_iter) lm_propose<DOF>(s, p);
+                }
+            } else {
+                for (int k = 0; k < p.lm_iter; ++k) {
+                    eval_subset<DOF, false>(pts, idx, r.n, s.pose, cam, delta, p.huber_eps, acc);
+                    gn_advance<DOF>(s.pose, acc, p.eps, s.pose);
+                }
+            }
+            const float c = pose_cost<DOF>(pts, a.N, s.pose, cam, delta);       // score on the full set
+            if (r.pose_all) {
+#pragma unroll
+                for (int i = 0; i < PD; ++i) r.pose_all[((size_t)h * a.B + obj) * PD + i] = s.pose[i];
+            }
+            if (r.cost_all) r.cost_all[(size_t)h * a.B + obj] = c;
+            if (my_hyp < 0 || cheaper_hypothesis(c, h, my_cost, my_hyp)) {
+                my_cost = c; my_hyp = h;
+#pragma unroll
+                for (int i = 0; i < PD; ++i) my_pose[i] = s.pose[i];
+            }
+        }
+        best_cost[tid] = my_cost;
+        best_hyp[tid] = my_hyp;
+        __syncthreads();
+        if (tid == 0) {
+            int w = -1;
+            for (int t = 0; t < NT; ++t) {
+                if (best_hyp[t] < 0) continue;
+                if (w < 0 || cheaper_hypothesis(best_cost[t], best_hyp[t], best_cost[w], best_hyp[w])) w = t;
+            }
+            best_hyp[0] = w;                                    // the winning THREAD (it still holds the pose)
+        }
+        __syncthreads();
+        if (tid == best_hyp[0]) {
+#pragma unroll
+            for (int i = 0; i < PD; ++i) r.pose_best[(size_t)obj * PD + i] = my_pose[i];
+            r.cost_best[obj] = my_cost;
+        }
+        __syncthreads();            // pts and the reduction arrays are reused by the next object
+    }
+}
+
 // residual / Jacobian / cost written out per point (API parity with evaluate_pnp's out_* tensors)
 template <int DOF>
 __global__ void __launch_bounds__(NT) evaluate_full_kernel(const KArgs a, float* residual, float* jac, float* cost,
@@ -1466,6 +1585,43 @@ int epnp_lm_solve_f32(const float* x3d, const float* x2d, const float* w2d, cons
     if (!pose_init || !pose_opt || p->lm_iter < 0) return EPNP_ERR_BAD_ARG;
     if (p->dof == 6) return launch_persistent(solve_kernel<6, true, false>, a, plan_smem<6>(N, 0, 0, false).total_bytes, (cudaStream_t)stream);
     return launch_persistent(solve_kernel<4, true, false>, a, plan_smem<4>(N, 0, 0, false).total_bytes, (cudaStream_t)stream);
+}
+
+int epnp_rslm_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                  const float* lb, const float* ub, const float* delta, const int* inds, const float* start,
+                  float* pose_best, float* cost_best, float* pose_all, float* cost_all,
+                  int P, int n, int B, int N, const EpnpParams* p, void* stream) {
+    if (!p) return EPNP_ERR_BAD_ARG;
+    RslmArgs r{};
+    KArgs& a = r.k;
+    a.x3d = x3d; a.x2d = x2d; a.w2d = w2d; a.cam = cam_mats; a.lb = lb; a.ub = ub; a.delta = delta;
+    a.B = B; a.N = N; a.p = *p;
+    r.inds = inds; r.start = start; r.pose_best = pose_best; r.cost_best = cost_best;
+    r.pose_all = pose_all; r.cost_all = cost_all; r.P = P; r.n = n;
+    int rc = check_common(a);
+    if (rc != EPNP_OK) return rc;
+    if (!inds || !start || !pose_best || !cost_best || P <= 0 || n <= 0 || p->lm_iter < 0) return EPNP_ERR_BAD_ARG;
+    if (B == 0) return EPNP_OK;
+    const int smem_bytes = (p->dof == 6) ? plan_smem<6>(N, 0, 0, false).total_bytes : plan_smem<4>(N, 0, 0, false).total_bytes;
+    if ((size_t)smem_bytes > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
+    a.use_tma = (N % 4 == 0) && aligned16(x3d) && aligned16(x2d) && aligned16(w2d);
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    a.num_sms = sms;
+    if (p->dof == 6) {
+        e = cudaFuncSetAttribute(rslm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        EPNP_LAUNCH(rslm_kernel<6>, B, NT, smem_bytes, (cudaStream_t)stream, r);
+    } else {
+        e = cudaFuncSetAttribute(rslm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        EPNP_LAUNCH(rslm_kernel<4>, B, NT, smem_bytes, (cudaStream_t)stream, r);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
 }
 
 int epnp_amis_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,

@@ -9,6 +9,7 @@ What runs where:
     all P*B mini-problems in one launch and scores the P hypotheses per object in one more.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -138,6 +139,12 @@ class LMSolver(nn.Module):
         return torch.cat((pose_opt[..., :3] + step[..., :3], F.normalize(q + dq, dim=-1)), dim=-1)
 
 
+def _fused_rslm():
+    """EPNP_FUSED_RSLM=1 selects the single-launch initialiser (thread <-> hypothesis, epnp_rslm_f32).  Opt-in until its
+    first hardware run: it was written and validated on the CPU emulation of the kernels only."""
+    return os.environ.get("EPNP_FUSED_RSLM", "0") not in ("", "0")
+
+
 @PNP.register_module()
 class RSLMSolver(LMSolver):
     """Random-sample LM: a RANSAC-like initialiser for ambiguous problems (levenberg_marquardt.py:268-353)."""
@@ -161,6 +168,27 @@ class RSLMSolver(LMSolver):
             depth = math.sqrt(2 / 3) * obj_std.norm(dim=-1) / ray_std.norm(dim=-1).clamp(min=eps)
         return direction * depth.unsqueeze(-1)
 
+    def _starting_hypotheses(self, x3d, x2d, camera):
+        """(P, B, D): centre-based translation, uniformly random orientation (:314-324)."""
+        P, bs = self.num_proposals, x2d.size(0)
+        start = x2d.new_empty((P, bs, self._pose_dim()))
+        start[..., :3] = self.center_based_init(x2d, x3d, camera)
+        if self.dof == 4:
+            start[..., 3] = torch.rand((P, bs), dtype=x2d.dtype, device=x2d.device) * (2 * math.pi)
+        else:
+            q = torch.randn((P, bs, 4), dtype=x2d.dtype, device=x2d.device)
+            qn = q.norm(dim=-1, keepdim=True)
+            unit = q.new_tensor([1., 0., 0., 0.])
+            start[..., 3:] = torch.where(qn < self.eps, unit, q / qn)
+        return start
+
+    def _solve_fused(self, x3d, x2d, w2d, camera, cost_fun, inds, fast_mode):
+        """One launch for all hypotheses of all objects (epnp_rslm_f32): nothing is gathered or repeated."""
+        start = self._starting_hypotheses(x3d, x2d, camera)
+        prob = native.Problem(x3d, x2d, w2d, camera.cam_mats, camera.lb, camera.ub, cost_fun.delta)
+        out = native.rslm(prob, inds, start, self.native_params(camera, cost_fun, fast_mode))
+        return out["pose"].to(x2d.dtype), None, out["cost"].to(x2d.dtype)
+
     @torch.no_grad()
     def solve(self, x3d, x2d, w2d, camera, cost_fun, **kwargs):
         """-> pose (B, 4|7), None, min_cost (B)."""
@@ -173,19 +201,13 @@ class RSLMSolver(LMSolver):
         # weighted subsets without replacement, one row per (proposal, object)
         prob_rows = w2d.mean(dim=-1).unsqueeze(0).expand(P, bs, pn).reshape(P * bs, pn)
         inds = torch.multinomial(prob_rows, n).reshape(P, bs, n)
+        if _fused_rslm():
+            return self._solve_fused(x3d, x2d, w2d, camera, cost_fun, inds, kwargs.get("fast_mode", False))
         inds = inds + (torch.arange(bs, device=inds.device) * pn)[:, None]
         sub3 = x3d.reshape(-1, 3)[inds].reshape(P * bs, n, 3)
         sub2 = x2d.reshape(-1, 2)[inds].reshape(P * bs, n, 2)
         subw = w2d.reshape(-1, 2)[inds].reshape(P * bs, n, 2)
-        start = x2d.new_empty((P, bs, pd))
-        start[..., :3] = self.center_based_init(x2d, x3d, camera)
-        if self.dof == 4:
-            start[..., 3] = torch.rand((P, bs), dtype=x2d.dtype, device=x2d.device) * (2 * math.pi)
-        else:
-            q = torch.randn((P, bs, 4), dtype=x2d.dtype, device=x2d.device)
-            qn = q.norm(dim=-1, keepdim=True)
-            unit = q.new_tensor([1., 0., 0., 0.])
-            start[..., 3:] = torch.where(qn < self.eps, unit, q / qn)
+        start = self._starting_hypotheses(x3d, x2d, camera)
         cam_p = camera.shallow_copy().repeat_(P)
         cost_p = cost_fun.shallow_copy().repeat_(P)
         fast_mode = kwargs.get("fast_mode", False)

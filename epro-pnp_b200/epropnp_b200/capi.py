@@ -42,6 +42,7 @@ _SIGNATURES = {
     "epnp_evaluate_cost_f32": (ctypes.c_int, [_P] * 9 + [_I, _I, _I, _I, _F, _P]),
     "epnp_evaluate_f32": (ctypes.c_int, [_P] * 11 + [_I, _I, _I, _I, _F, _F, _P]),
     "epnp_lm_solve_f32": (ctypes.c_int, [_P] * 13 + [_I, _I, ctypes.POINTER(EpnpParams), _P]),
+    "epnp_rslm_f32": (ctypes.c_int, [_P] * 13 + [_I, _I, _I, _I, ctypes.POINTER(EpnpParams), _P]),
     "epnp_amis_f32": (ctypes.c_int, [_P] * 12 + [ctypes.c_uint64, ctypes.c_uint32] + [_P] * 3
                       + [_I, _I, ctypes.POINTER(EpnpParams), _P]),
     "epnp_lm_amis_fused_f32": (ctypes.c_int, [_P] * 11 + [ctypes.c_uint64, ctypes.c_uint32] + [_P] * 8
@@ -99,6 +100,12 @@ def ptr(t):
     if t is None:
         return None
     assert t.dtype == torch.float32 and t.is_contiguous(), "native path needs contiguous float32"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def iptr(t):
+    """Pointer of a contiguous int32 tensor."""
+    assert t.dtype == torch.int32 and t.is_contiguous(), "index arguments are contiguous int32"
     return ctypes.c_void_p(t.data_ptr())
 
 

@@ -118,6 +118,23 @@ def lm_solve(prob: Problem, pose_init, params, want_cov=False, want_cost=False, 
     return out
 
 
+def rslm(prob: Problem, inds, start, params, want_all=False):
+    """Fused random-sample LM initialiser (epnp_rslm_f32): inds (P, B, n) integer indices within each object, start
+    (P, B, D) -> dict(pose (B, D), cost (B), pose_all (P, B, D) | None, cost_all (P, B) | None)."""
+    D = 7 if params.dof == 6 else 4
+    P, B, n = inds.shape
+    assert B == prob.B and start.shape == (P, B, D)
+    inds32 = inds.detach().to(device=prob.device, dtype=torch.int32).contiguous()
+    start = _f32c(start)
+    out = dict(pose=prob.empty(B, D), cost=prob.empty(B),
+               pose_all=prob.empty(P, B, D) if want_all else None, cost_all=prob.empty(P, B) if want_all else None)
+    with torch.cuda.device(prob.device):
+        check(lib().epnp_rslm_f32(*prob.common_ptrs(), capi.iptr(inds32), ptr(start), ptr(out["pose"]), ptr(out["cost"]),
+                                  ptr(out["pose_all"]), ptr(out["cost_all"]), P, n, B, prob.N, ctypes.byref(params),
+                                  stream_ptr(prob.device)), "epnp_rslm_f32")
+    return out
+
+
 def _noise_ptrs(noise):
     if noise is None:
         return None, None, None, ()

@@ -92,6 +92,18 @@ int epnp_evaluate_f32(const float* x3d, const float* x2d, const float* w2d, cons
                       float* residual, float* jac, float* cost, int clip_jac,
                       int B, int N, int dof, float z_min, float huber_eps, void* stream);
 
+/* RSLMSolver.solve after the hypotheses are drawn (levenberg_marquardt.py:300-353): for every object, P starting
+ * poses, each refined by LM / GN on its own n sampled correspondences, scored on all N correspondences, cheapest
+ * kept.  Replaces the reference's gather of (P*B, n, .) mini-problems, the P-fold repeated camera / cost objects,
+ * the solve of P*B tiny problems and the stacked evaluate_pnp (:326-352).
+ *   inds (P, B, n) int32: sampled correspondence indices WITHIN the object (the torch.multinomial draw, :310-312)
+ *   start (P, B, D): starting poses (centre-based translation + random orientation, :314-324)
+ *   pose_best (B, D), cost_best (B); pose_all [opt] (P, B, D), cost_all [opt] (P, B)                          */
+int epnp_rslm_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                  const float* lb, const float* ub, const float* delta, const int* inds, const float* start,
+                  float* pose_best, float* cost_best, float* pose_all, float* cost_all,
+                  int P, int n, int B, int N, const EpnpParams* p, void* stream);
+
 /* LMSolver.solve with a given pose_init (levenberg_marquardt.py:80-190, _lm_iter :192-241, GN
  * fast mode :136-152) plus, when pose_opt_plus != NULL, the extra Gauss-Newton step of
  * LMSolver.forward (:66-68, gn_step :243-253, pose_add :255-265).

@@ -26,7 +26,9 @@ def _layer():
                                       init_solver=dict(type="RSLMSolver", dof=4, num_points=16, num_proposals=8, num_iter=3))))
 
 
-def test_inference_sequence(dev):
+@pytest.mark.parametrize("fused_rslm", ["0", "1"])
+def test_inference_sequence(dev, monkeypatch, fused_rslm):
+    monkeypatch.setenv("EPNP_FUSED_RSLM", fused_rslm)         # "1": the single-launch initialiser (epnp_rslm_f32)
     B, N = 3, 48
     pc = make_problem(B, N, seed=21, dof=4)
     x3d, x2d, w2d, gt = pc["x3d"], pc["x2d"], pc["w2d"], pc["pose_gt"]

@@ -1,0 +1,26 @@
+"""The fused random-sample LM initialiser on a real GPU: the same assertions as tests/test_rslm_fused_cpu.py (which
+runs them on the CPU emulation of the kernels).  The kernel has not had its first hardware run yet, so this file is
+gated by the environment until it has:
+    gpurun -- 'EPNP_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_rslm_fused_gpu.py -q'"""
+import os
+
+import pytest
+import torch
+
+import test_rslm_fused_cpu as _cpu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def dev():
+    if not os.environ.get("EPNP_TEST_EXPERIMENTAL"):
+        pytest.skip("experimental kernel: set EPNP_TEST_EXPERIMENTAL=1")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+test_every_hypothesis_matches_the_unfused_path = _cpu.test_every_hypothesis_matches_the_unfused_path
+test_solver_class_uses_it_when_asked = _cpu.test_solver_class_uses_it_when_asked
+test_nan_hypothesis_wins_like_torch_min = _cpu.test_nan_hypothesis_wins_like_torch_min

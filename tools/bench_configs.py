@@ -75,6 +75,25 @@ def main():
     ms = timed(lambda: native.evaluate_cost(prob, poses, 6, 0.1))
     out.append(dict(config="evaluate_pnp cost, 128 poses x 4096 objects x 512 pts", B=4096, ms=ms,
                     pose_point_pairs_per_s=S * 4096 * 512 / ms * 1e3))
+    # random-sample LM initialiser (RSLMSolver.solve): the unfused path (gather + P*B tiny solves + stacked evaluate_pnp)
+    # against the single-launch kernel (EPNP_FUSED_RSLM=1), demo-notebook and detection configurations
+    if os.environ.get("EPNP_BENCH_RSLM"):
+        sys.path.insert(0, os.path.join(ROOT, "epro-pnp_b200"))
+        from epropnp.camera import PerspectiveCamera
+        from epropnp.cost_fun import AdaptiveHuberPnPCost
+        from epropnp.levenberg_marquardt import RSLMSolver
+        for dof, B, N, n, P, K in ((6, 256, 64, 8, 128, 5), (4, 512, 64, 16, 64, 3)):
+            pc = {k: v.to(dev) for k, v in make_problem(B, N, seed=3, dof=dof).items()}
+            camera = PerspectiveCamera(cam_mats=pc["cam_mats"])
+            cost_fun = AdaptiveHuberPnPCost(relative_delta=0.5)
+            cost_fun.set_param(pc["x2d"], pc["w2d"])
+            solver = RSLMSolver(dof=dof, num_points=n, num_proposals=P, num_iter=K)
+            row = dict(config=f"RSLM init, dof={dof}, N={N}, {P} proposals x {n} points x LM({K})", B=B)
+            for flag, key in (("0", "ms_unfused"), ("1", "ms_fused")):
+                os.environ["EPNP_FUSED_RSLM"] = flag
+                row[key] = timed(lambda: solver.solve(pc["x3d"], pc["x2d"], pc["w2d"], camera, cost_fun), iters=10)
+            os.environ["EPNP_FUSED_RSLM"] = "0"
+            out.append(row)
     for r in out:
         print(json.dumps(r))
 
