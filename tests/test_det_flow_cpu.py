@@ -21,9 +21,10 @@ def dev(monkeypatch):
 
 
 def _layer():
-    return build_pnp(dict(type="EProPnP4DoF", mc_samples=128, num_iter=4,
-                          solver=dict(type="LMSolver", dof=4, num_iter=5,
-                                      init_solver=dict(type="RSLMSolver", dof=4, num_points=16, num_proposals=8, num_iter=3))))
+    """The layer exactly as EPro-PnP-Det/configs/epropnp_det_basic.py:98-111 builds it (fewer samples / proposals only)."""
+    return build_pnp(dict(type="EProPnP4DoF", mc_samples=128, num_iter=4, normalize=True,
+                          solver=dict(type="LMSolver", num_iter=10, normalize=True,
+                                      init_solver=dict(type="RSLMSolver", num_points=16, num_proposals=16, num_iter=3))))
 
 
 @pytest.mark.parametrize("fused_rslm", ["0", "1"])
