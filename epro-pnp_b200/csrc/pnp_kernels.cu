@@ -1199,6 +1199,80 @@ __global__ void __launch_bounds__(NT, 2) rslm_kernel(const RslmArgs r) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of pose_opt_plus = pose (+) gn_step(pose) w.r.t. the correspondences and the Huber delta (the
+// derivative-regularisation branch of training, LMSolver.forward :66-68 with autograd on).  One CTA per object:
+// re-evaluate the normal equations, let the serial lane form step, dL/dstep (through pose_add) and
+// v = -(H + eps I)^-1 dL/dstep, then thread <-> correspondence with forward-mode duals (pnp::gn_step_point_backward).
+struct GnBwArgs {
+    KArgs k;                    // correspondences, camera, bounds, delta, poses = pose (B, D), p.eps / huber_eps / z_min
+    const float* gplus;         // (B, D)  dL/d pose_opt_plus
+    float *gx3d, *gx2d, *gw2d;  // [opt] (B, N, 3|2|2)
+    float* gdelta;              // [opt] (B)
+};
+
+template <int DOF>
+__global__ void __launch_bounds__(NT, 2) gn_plus_backward_kernel(const GnBwArgs g) {
+    const KArgs& a = g.k;
+    EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
+    SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
+    float* dyn = reinterpret_cast<float*>(smem_raw);
+    const SmemPlan pl = plan_smem<DOF>(a.N, 0, 0, false);
+    float* pts = dyn + pl.pts;
+    constexpr int PD = Dim<DOF>::POSE, NA = Dim<DOF>::NA;
+    const int tid = threadIdx.x;
+    Loader ld(a, sh.bar, dyn + pl.stage);
+    ld.prologue();
+    for (int it = 0; it < ld.n_my; ++it) {
+        const int obj = (int)blockIdx.x + it * (int)gridDim.x;
+        ld.load_object(it, obj, pts);
+        const Cam cam = load_cam(a, obj);
+        const float delta = __ldg(a.delta + obj);
+        if (tid < PD) sh.lm.pose[tid] = __ldg(a.poses + (size_t)obj * PD + tid);
+        __syncthreads();
+        eval_normal_eq<DOF, true>(pts, a.N, sh.lm.pose, cam, delta, a.p.huber_eps, sh.red, sh.ev);
+        float* step = sh.cov;               // [DOF]
+        float* vvec = sh.cov + DOF;         // [DOF]
+        if (tid == 0) {
+            float add[DOF], st[DOF], sbar[DOF], vv[DOF], gout[PD], pose[PD];
+#pragma unroll
+            for (int i = 0; i < DOF; ++i) add[i] = a.p.eps;
+#pragma unroll
+            for (int i = 0; i < PD; ++i) { pose[i] = sh.lm.pose[i]; gout[i] = __ldg(g.gplus + (size_t)obj * PD + i); }
+            damped_step_refined<DOF>(sh.ev, sh.ev + NA, add, st);
+            pose_add_backward<DOF>(pose, st, gout, sbar);
+            damped_step_refined<DOF>(sh.ev, sbar, add, vv);
+#pragma unroll
+            for (int i = 0; i < DOF; ++i) { step[i] = st[i]; vvec[i] = vv[i]; }
+        }
+        __syncthreads();
+        float R[9], t[3], sv[DOF], vv[DOF];
+        {
+            float ps[PD];
+#pragma unroll
+            for (int i = 0; i < PD; ++i) ps[i] = sh.lm.pose[i];
+            pose_to_rot<DOF>(ps, R);
+            t[0] = ps[0]; t[1] = ps[1]; t[2] = ps[2];
+#pragma unroll
+            for (int i = 0; i < DOF; ++i) { sv[i] = step[i]; vv[i] = vvec[i]; }
+        }
+        float gd[1] = {0.f};
+        for (int n = tid; n < a.N; n += NT) {
+            const float* q = pts + (n >> 1) * 16 + (n & 1);
+            float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            gn_step_point_backward<DOF>(R, t, cam, delta, a.p.huber_eps, q[0], q[2], q[4], -q[6], -q[8], q[10], q[12], vv, sv, gr);
+            const size_t o = (size_t)obj * a.N + n;
+            if (g.gx3d) { g.gx3d[o * 3] = gr[0]; g.gx3d[o * 3 + 1] = gr[1]; g.gx3d[o * 3 + 2] = gr[2]; }
+            if (g.gx2d) { g.gx2d[o * 2] = gr[3]; g.gx2d[o * 2 + 1] = gr[4]; }
+            if (g.gw2d) { g.gw2d[o * 2] = gr[5]; g.gw2d[o * 2 + 1] = gr[6]; }
+            gd[0] += gr[7];
+        }
+        block_sum<1>(gd, sh.red, 0);
+        if (tid == 0 && g.gdelta) g.gdelta[obj] = gd[0];
+        __syncthreads();            // pts, pose and the step vectors are reused by the next object
+    }
+}
+
 // residual / Jacobian / cost written out per point (API parity with evaluate_pnp's out_* tensors)
 template <int DOF>
 __global__ void __launch_bounds__(NT) evaluate_full_kernel(const KArgs a, float* residual, float* jac, float* cost,
@@ -1585,6 +1659,44 @@ int epnp_lm_solve_f32(const float* x3d, const float* x2d, const float* w2d, cons
     if (!pose_init || !pose_opt || p->lm_iter < 0) return EPNP_ERR_BAD_ARG;
     if (p->dof == 6) return launch_persistent(solve_kernel<6, true, false>, a, plan_smem<6>(N, 0, 0, false).total_bytes, (cudaStream_t)stream);
     return launch_persistent(solve_kernel<4, true, false>, a, plan_smem<4>(N, 0, 0, false).total_bytes, (cudaStream_t)stream);
+}
+
+int epnp_gn_plus_backward_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                              const float* lb, const float* ub, const float* delta, const float* pose,
+                              const float* grad_pose_plus, float* grad_x3d, float* grad_x2d, float* grad_w2d,
+                              float* grad_delta, int B, int N, int dof, float z_min, float eps, float huber_eps,
+                              void* stream) {
+    GnBwArgs g{};
+    KArgs& a = g.k;
+    a.x3d = x3d; a.x2d = x2d; a.w2d = w2d; a.cam = cam_mats; a.lb = lb; a.ub = ub; a.delta = delta;
+    a.poses = pose; a.B = B; a.N = N;
+    epnp_default_params(&a.p, dof);
+    a.p.z_min = z_min; a.p.eps = eps; a.p.huber_eps = huber_eps;
+    g.gplus = grad_pose_plus; g.gx3d = grad_x3d; g.gx2d = grad_x2d; g.gw2d = grad_w2d; g.gdelta = grad_delta;
+    int rc = check_common(a);
+    if (rc != EPNP_OK) return rc;
+    if (!pose || !grad_pose_plus) return EPNP_ERR_BAD_ARG;
+    if (B == 0) return EPNP_OK;
+    const int smem_bytes = (dof == 6) ? plan_smem<6>(N, 0, 0, false).total_bytes : plan_smem<4>(N, 0, 0, false).total_bytes;
+    if ((size_t)smem_bytes > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
+    a.use_tma = (N % 4 == 0) && aligned16(x3d) && aligned16(x2d) && aligned16(w2d);
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    a.num_sms = sms;
+    if (dof == 6) {
+        e = cudaFuncSetAttribute(gn_plus_backward_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        EPNP_LAUNCH(gn_plus_backward_kernel<6>, B, NT, smem_bytes, (cudaStream_t)stream, g);
+    } else {
+        e = cudaFuncSetAttribute(gn_plus_backward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        EPNP_LAUNCH(gn_plus_backward_kernel<4>, B, NT, smem_bytes, (cudaStream_t)stream, g);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
 }
 
 int epnp_rslm_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,

@@ -441,6 +441,165 @@ PNP_HD float point_residual_jac(const float* R, const float* t, const Cam& c, fl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Backward of the differentiable Gauss-Newton step (LMSolver.gn_step evaluated with autograd on,
+// levenberg_marquardt.py:243-253 through camera.py:119-129 and cost_fun.py:52-84).
+//   step = -(H + eps I)^-1 g,   H = sum_n J~_n^T J~_n,   g = sum_n J~_n^T r~_n         (pose detached)
+// With sbar = dL/dstep and v = -(H + eps I)^-1 sbar:   dL = sum_n d[ b_n . (J~_n v) + a_n . (r~_n + J~_n step) ]
+// where a_n = J~_n v and b_n = r~_n + J~_n step are held constant.  The per-point scalar is differentiated in
+// forward mode: Dual<8> carries the tangents w.r.t. (X, Y, Z, u, v, wu, wv, delta) through the same formulas as
+// point_residual_jac, so clamps, the Huber rescale and the clip mask differentiate exactly as torch's autograd does.
+template <int ND> struct Dual {
+    float v;
+    float d[ND];
+};
+template <int ND> PNP_HD Dual<ND> dual_const(float c) {
+    Dual<ND> r; r.v = c;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = 0.f;
+    return r;
+}
+template <int ND> PNP_HD Dual<ND> dual_seed(float c, int k) { Dual<ND> r = dual_const<ND>(c); r.d[k] = 1.f; return r; }
+template <int ND> PNP_HD Dual<ND> operator+(const Dual<ND>& a, const Dual<ND>& b) {
+    Dual<ND> r; r.v = a.v + b.v;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = a.d[i] + b.d[i];
+    return r;
+}
+template <int ND> PNP_HD Dual<ND> operator-(const Dual<ND>& a, const Dual<ND>& b) {
+    Dual<ND> r; r.v = a.v - b.v;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = a.d[i] - b.d[i];
+    return r;
+}
+template <int ND> PNP_HD Dual<ND> operator*(const Dual<ND>& a, const Dual<ND>& b) {
+    Dual<ND> r; r.v = a.v * b.v;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = fmaf(a.v, b.d[i], a.d[i] * b.v);
+    return r;
+}
+template <int ND> PNP_HD Dual<ND> operator*(const Dual<ND>& a, float c) {
+    Dual<ND> r; r.v = a.v * c;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = a.d[i] * c;
+    return r;
+}
+template <int ND> PNP_HD Dual<ND> operator+(const Dual<ND>& a, float c) { Dual<ND> r = a; r.v += c; return r; }
+template <int ND> PNP_HD Dual<ND> dual_recip(const Dual<ND>& a) {
+    Dual<ND> r; r.v = 1.0f / a.v;
+    const float k = -r.v * r.v;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = a.d[i] * k;
+    return r;
+}
+template <int ND> PNP_HD Dual<ND> dual_sqrt(const Dual<ND>& a) {            // a.v > 0
+    Dual<ND> r; r.v = sqrtf(a.v);
+    const float k = 0.5f / r.v;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = a.d[i] * k;
+    return r;
+}
+template <int ND> PNP_HD Dual<ND> dual_gate(const Dual<ND>& a, float value, bool pass) {   // clamp: value replaced, tangent gated
+    Dual<ND> r; r.v = value;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) r.d[i] = pass ? a.d[i] : 0.f;
+    return r;
+}
+
+// One correspondence's contribution to dL/d(X, Y, Z, u, v, wu, wv, delta) (grad[0..8), accumulated with +=).
+// R, t: rotation / translation of the (detached) pose; vv = v, sv = step (DOF-vectors).
+template <int DOF>
+PNP_HD void gn_step_point_backward(const float* R, const float* t, const Cam& c, float delta, float huber_eps,
+                                   float X, float Y, float Z, float u, float v, float wu, float wv,
+                                   const float* vv, const float* sv, float* grad) {
+    typedef Dual<8> D;
+    const D dX = dual_seed<8>(X, 0), dY = dual_seed<8>(Y, 1), dZ = dual_seed<8>(Z, 2);
+    const D du = dual_seed<8>(u, 3), dv = dual_seed<8>(v, 4), dwu = dual_seed<8>(wu, 5), dwv = dual_seed<8>(wv, 6);
+    const D dd = dual_seed<8>(delta, 7);
+    const D xr = dX * R[0] + dY * R[1] + dZ * R[2];
+    const D yr = dX * R[3] + dY * R[4] + dZ * R[5];
+    const D zr = dX * R[6] + dY * R[7] + dZ * R[8];
+    const D xc = xr + t[0], yc = yr + t[1], zc = zr + t[2];
+    const float* K = c.k;
+    const D xh = xc * K[0] + yc * K[1] + zc * K[2];
+    const D yh = xc * K[3] + yc * K[4] + zc * K[5];
+    const D zh = xc * K[6] + yc * K[7] + zc * K[8];
+    const bool z_free = zh.v >= c.z_min;                                   // z.clamp(min=z_min): tangent passes iff zh >= z_min
+    const D z = dual_gate(zh, fmaxf(zh.v, c.z_min), z_free);
+    const D iz = dual_recip(z);
+    D px = xh * iz, py = yh * iz;
+    if (c.bounded) {
+        const float cx = fminf(fmaxf(px.v, c.lbx), c.ubx), cy = fminf(fmaxf(py.v, c.lby), c.uby);
+        px = dual_gate(px, cx, cx == px.v);
+        py = dual_gate(py, cy, cy == py.v);
+    }
+    const D ex = px - du, ey = py - dv;
+    D rx = ex * dwu, ry = ey * dwv;
+    const D s2 = rx * rx + ry * ry;
+    // sqrt(rho') = sqrt(min(delta / max(s, eps), 1)): constant 1 for inliers
+    D sc = dual_const<8>(1.0f);
+    const float s = sqrtf(s2.v);
+    if (!(s <= delta && delta >= huber_eps)) {
+        const float sm = fmaxf(s, huber_eps);
+        const float ratio = delta / sm;
+        if (ratio < 1.0f) {
+            const D sd = (s >= huber_eps && s > 0.f) ? dual_sqrt(s2) : dual_const<8>(sm);
+            sc = dual_sqrt(dd * dual_recip(sd));
+        }
+    }
+    rx = rx * sc; ry = ry * sc;
+    // clip mask (constant): rows whose projection sits on a clamp carry no Jacobian
+    const bool cz = (z.v == c.z_min);
+    const bool clip_x = cz || (c.bounded && (px.v == c.lbx || px.v == c.ubx));
+    const bool clip_y = cz || (c.bounded && (py.v == c.lby || py.v == c.uby));
+    const D sx = clip_x ? dual_const<8>(0.f) : dwu * sc;
+    const D sy = clip_y ? dual_const<8>(0.f) : dwv * sc;
+    // (J_cam w)_row = (K_row0 m_x + K_row1 m_y + (K_row2 - p_row) m_z) / z,  m(w) = w_t + d(x_rot)/d(rot) w_r
+    D Au, Av, Bu, Bv;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        const float* w = which == 0 ? vv : sv;
+        D mx, my, mz;
+        if (DOF == 6) {
+            mx = (yr * w[5] - zr * w[4]) * 2.0f + w[0];
+            my = (zr * w[3] - xr * w[5]) * 2.0f + w[1];
+            mz = (xr * w[4] - yr * w[3]) * 2.0f + w[2];
+        } else {
+            mx = zr * w[3] + w[0];
+            my = dual_const<8>(w[1]);
+            mz = xr * (-w[3]) + w[2];
+        }
+        const D ju = (mx * K[0] + my * K[1] + (dual_const<8>(K[2]) - px) * mz) * iz * sx;
+        const D jv = (mx * K[3] + my * K[4] + (dual_const<8>(K[5]) - py) * mz) * iz * sy;
+        if (which == 0) { Au = ju; Av = jv; } else { Bu = ju; Bv = jv; }
+    }
+    const float au = Au.v, av = Av.v;                      // a = J~ v
+    const float bu = rx.v + Bu.v, bv = ry.v + Bv.v;        // b = r~ + J~ step
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        grad[k] += bu * Au.d[k] + au * (rx.d[k] + Bu.d[k]) + bv * Av.d[k] + av * (ry.d[k] + Bv.d[k]);
+}
+
+// dL/dstep from dL/d(pose (+) step) (pose_add: translation plain, quaternion q' = normalize(q + T(q) step_r))
+template <int DOF> PNP_HD void pose_add_backward(const float* pose, const float* step, const float* gout, float* gstep) {
+    gstep[0] = gout[0]; gstep[1] = gout[1]; gstep[2] = gout[2];
+    if (DOF == 4) { gstep[3] = gout[3]; return; }
+    const float w = pose[3], x = pose[4], y = pose[5], z = pose[6];
+    const float a = step[3], b = step[4], c = step[5];
+    const float q[4] = {w + (x * a + y * b + z * c), x + (-w * a - z * b + y * c), y + (z * a - w * b - x * c),
+                        z + (-y * a + x * b - w * c)};
+    const float n = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+    const float inv = 1.0f / n;
+    const float dot = (q[0] * gout[3] + q[1] * gout[4] + q[2] * gout[5] + q[3] * gout[6]) * inv * inv;
+    float gq[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gq[i] = (gout[3 + i] - q[i] * dot) * inv;
+    // q~ = q + T step_r with T = [[x, y, z], [-w, -z, y], [z, -w, -x], [-y, x, -w]]
+    gstep[3] = x * gq[0] - w * gq[1] + z * gq[2] - y * gq[3];
+    gstep[4] = y * gq[0] - z * gq[1] - w * gq[2] + x * gq[3];
+    gstep[5] = z * gq[0] + y * gq[1] - x * gq[2] - w * gq[3];
+}
+
+// ------------------------------------------------------------------------------------------------
 // Small symmetric-positive-definite linear algebra, N <= 6, static indexing only, templated on the
 // working precision.  The per-point loops are fp32; these once-per-object factorizations run in fp64
 // (`Hi`): the matrices are ill-conditioned by construction (information ~1e5 next to an identity

@@ -7,7 +7,8 @@
     evaluate_pnp(out_cost=True)     same kernel
     pose_opt_plus                   one un-damped Gauss-Newton step at the (detached) solution; differentiated
                                     by torch autograd through `PerspectiveCamera.project` + `HuberPnPCost.compute`
-                                    (a single evaluation, levenberg_marquardt.py:243-253 -- not the iterated path)
+                                    (a single evaluation, levenberg_marquardt.py:243-253 -- not the iterated path),
+                                    or, with EPNP_NATIVE_GN_STEP=1, by the native kernel epnp_gn_plus_backward_f32
 
 Gradients w.r.t. poses (pose_init / stacked hypotheses) are not provided: the reference's losses never use
 them (pose_init is the ground truth, lib/train.py:178-180), and asking for them raises.
@@ -124,6 +125,46 @@ def monte_carlo_autograd(x3d, x2d, w2d, camera, cost_fun, pose_start, pose_init,
         x3d, x2d, w2d, _delta_tensor(cost_fun.delta, x2d), camera.cam_mats, camera.lb, camera.ub, pose_start.detach(),
         None if pose_init is None else pose_init.detach(), params, noise, seed, bool(want_cost), float(camera.z_min))
     return pose_opt, (cost if want_cost else None), samples, logw, (cost_init if pose_init is not None else None)
+
+
+class _PosePlus(torch.autograd.Function):
+    """pose (+) gn_step(pose) with a native backward (epnp_gn_plus_backward_f32)."""
+
+    @staticmethod
+    def forward(ctx, x3d, x2d, w2d, delta, cam_mats, lb, ub, pose, params, huber_eps):
+        prob = native.Problem(x3d, x2d, w2d, cam_mats, lb, ub, delta)
+        plus = native.lm_solve(prob, pose, params, want_plus=True)["pose_opt_plus"]
+        ctx.prob, ctx.pose, ctx.dof = prob, pose.detach(), params.dof
+        ctx.consts = (float(params.z_min), float(params.eps), float(huber_eps))
+        ctx.in_like = (x3d, x2d, w2d, delta if torch.is_tensor(delta) else None)
+        ctx.needs = (x3d.requires_grad, x2d.requires_grad, w2d.requires_grad,
+                     torch.is_tensor(delta) and delta.requires_grad)
+        return plus.to(x3d.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_plus):
+        z_min, eps, huber_eps = ctx.consts
+        grads = native.gn_plus_backward(ctx.prob, ctx.pose, grad_plus, ctx.dof, z_min, eps, huber_eps, want=ctx.needs)
+        g3, g2, gw, gd = _grads_to(ctx.in_like, grads)
+        return g3, g2, gw, gd, None, None, None, None, None, None
+
+
+def native_gn_step_enabled():
+    """EPNP_NATIVE_GN_STEP=1: differentiate pose_opt_plus with the native kernel instead of the torch composite.
+    Opt-in until its first hardware run (written and checked against the composite on the CPU emulation of the kernels)."""
+    import os
+    return os.environ.get("EPNP_NATIVE_GN_STEP", "0") not in ("", "0")
+
+
+def pose_plus_autograd(solver, x3d, x2d, w2d, pose, camera, cost_fun):
+    """Differentiable pose (+) one un-damped Gauss-Newton step at the detached `pose` (LMSolver.forward :66-68)."""
+    if not native_gn_step_enabled():
+        return solver.pose_add(pose, gn_step_autograd(solver, x3d, x2d, w2d, pose, camera, cost_fun), camera)
+    params = solver.native_params(camera, cost_fun, False)
+    params.lm_iter = 0                                       # evaluate the step at `pose` itself
+    delta = cost_fun.delta
+    return _PosePlus.apply(x3d, x2d, w2d, delta if torch.is_tensor(delta) else float(delta), camera.cam_mats,
+                           camera.lb, camera.ub, pose.detach(), params, float(getattr(cost_fun, "eps", 1e-10)))
 
 
 def gn_step_autograd(solver, x3d, x2d, w2d, pose, camera, cost_fun):

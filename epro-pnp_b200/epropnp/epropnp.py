@@ -133,14 +133,13 @@ class EProPnPBase(torch.nn.Module, metaclass=ABCMeta):
 
         if num_obj > 0 and differentiable:
             # training path: forward = the same fused kernel, backward = native Monte-Carlo cost gradient
-            from .autograd import gn_step_autograd, monte_carlo_autograd
+            from .autograd import monte_carlo_autograd, pose_plus_autograd
             pose_opt, cost, samples_bm, logw_bm, cost_init = monte_carlo_autograd(
                 x3d, x2d, w2d, camera, cost_fun, start, pose_init, params, amis_noise, seed, with_cost)
             pose_samples, logw = samples_bm.transpose(0, 1), logw_bm.transpose(0, 1)
             pose_opt_plus = None
             if with_plus:
-                step = gn_step_autograd(self.solver, x3d, x2d, w2d, pose_opt, camera, cost_fun)
-                pose_opt_plus = self.solver.pose_add(pose_opt, step, camera)
+                pose_opt_plus = pose_plus_autograd(self.solver, x3d, x2d, w2d, pose_opt, camera, cost_fun)
 
         if self.normalize:
             pose_opt = pnp_denormalize(transform, pose_opt)

@@ -74,8 +74,8 @@ class LMSolver(nn.Module):
             x3d, x2d, w2d, camera, cost_fun, pose_init=pose_init,
             with_pose_opt_plus=with_pose_opt_plus and not differentiable, **kwargs)
         if differentiable:       # y* (+) GN step, differentiable w.r.t. the correspondences (:66-68)
-            from .autograd import gn_step_autograd
-            pose_opt_plus = self.pose_add(pose_opt, gn_step_autograd(self, x3d, x2d, w2d, pose_opt, camera, cost_fun), camera)
+            from .autograd import pose_plus_autograd
+            pose_opt_plus = pose_plus_autograd(self, x3d, x2d, w2d, pose_opt, camera, cost_fun)
         if normalize:
             pose_opt = pnp_denormalize(transform, pose_opt)
             if pose_cov is not None:

@@ -135,6 +135,22 @@ def rslm(prob: Problem, inds, start, params, want_all=False):
     return out
 
 
+def gn_plus_backward(prob: Problem, pose, grad_pose_plus, dof, z_min, eps, huber_eps, want=(True, True, True, True)):
+    """dL/d(x3d, x2d, w2d, delta) of pose_opt_plus = pose (+) gn_step(pose) (epnp_gn_plus_backward_f32)."""
+    B, N = prob.B, prob.N
+    pose, gp = _f32c(pose), _f32c(grad_pose_plus)
+    g3 = prob.empty(B, N, 3) if want[0] else None
+    g2 = prob.empty(B, N, 2) if want[1] else None
+    gw = prob.empty(B, N, 2) if want[2] else None
+    gd = prob.empty(B) if want[3] else None
+    with torch.cuda.device(prob.device):
+        check(lib().epnp_gn_plus_backward_f32(*prob.common_ptrs(), ptr(pose), ptr(gp), ptr(g3), ptr(g2), ptr(gw), ptr(gd),
+                                              B, N, dof, ctypes.c_float(z_min), ctypes.c_float(eps),
+                                              ctypes.c_float(huber_eps), stream_ptr(prob.device)),
+              "epnp_gn_plus_backward_f32")
+    return g3, g2, gw, gd
+
+
 def _noise_ptrs(noise):
     if noise is None:
         return None, None, None, ()

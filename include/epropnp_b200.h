@@ -92,6 +92,17 @@ int epnp_evaluate_f32(const float* x3d, const float* x2d, const float* w2d, cons
                       float* residual, float* jac, float* cost, int clip_jac,
                       int B, int N, int dof, float z_min, float huber_eps, void* stream);
 
+/* Backward of the derivative-regularisation branch: pose_opt_plus = pose (+) gn_step(pose) with the pose detached
+ * (LMSolver.forward :66-68, gn_step :243-253, pose_add :255-265, evaluated with autograd on in the reference:
+ * camera.py:119-129, cost_fun.py:52-84).  Given dL/d pose_opt_plus (B, D), writes dL/d x3d (B, N, 3), dL/d x2d
+ * (B, N, 2), dL/d w2d (B, N, 2) and dL/d delta (B) (each optional).  The forward value is what
+ * epnp_lm_solve_f32 returns in pose_opt_plus (lm_iter = 0 evaluates the step at pose_init).                      */
+int epnp_gn_plus_backward_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                              const float* lb, const float* ub, const float* delta, const float* pose,
+                              const float* grad_pose_plus, float* grad_x3d, float* grad_x2d, float* grad_w2d,
+                              float* grad_delta, int B, int N, int dof, float z_min, float eps, float huber_eps,
+                              void* stream);
+
 /* RSLMSolver.solve after the hypotheses are drawn (levenberg_marquardt.py:300-353): for every object, P starting
  * poses, each refined by LM / GN on its own n sampled correspondences, scored on all N correspondences, cheapest
  * kept.  Replaces the reference's gather of (P*B, n, .) mini-problems, the P-fold repeated camera / cost objects,

@@ -94,6 +94,30 @@ def main():
                 row[key] = timed(lambda: solver.solve(pc["x3d"], pc["x2d"], pc["w2d"], camera, cost_fun), iters=10)
             os.environ["EPNP_FUSED_RSLM"] = "0"
             out.append(row)
+    # derivative-regularisation branch: pose_opt_plus forward + backward, torch composite vs native kernel
+    if os.environ.get("EPNP_BENCH_GN_PLUS"):
+        sys.path.insert(0, os.path.join(ROOT, "epro-pnp_b200"))
+        from epropnp import autograd as ag
+        from epropnp.camera import PerspectiveCamera
+        from epropnp.cost_fun import AdaptiveHuberPnPCost
+        from epropnp.levenberg_marquardt import LMSolver
+        for B in (1024, 4096):
+            pc = {k: v.to(dev) for k, v in make_problem(B, 512, seed=5).items()}
+            x3d, w2d = pc["x3d"].clone().requires_grad_(True), pc["w2d"].clone().requires_grad_(True)
+            camera = PerspectiveCamera(cam_mats=pc["cam_mats"])
+            cost_fun = AdaptiveHuberPnPCost(relative_delta=0.5)
+            cost_fun.set_param(pc["x2d"], w2d)
+            solver = LMSolver(dof=6, num_iter=10)
+            row = dict(config="pose_opt_plus forward + backward (derivative regularisation), N=512", B=B)
+
+            def step():
+                x3d.grad = w2d.grad = None
+                ag.pose_plus_autograd(solver, x3d, pc["x2d"], w2d, pc["pose_init"], camera, cost_fun).square().sum().backward()
+            for flag, key in (("0", "ms_composite"), ("1", "ms_native")):
+                os.environ["EPNP_NATIVE_GN_STEP"] = flag
+                row[key] = timed(step, iters=10)
+            os.environ["EPNP_NATIVE_GN_STEP"] = "0"
+            out.append(row)
     for r in out:
         print(json.dumps(r))
 
