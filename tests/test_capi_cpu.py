@@ -178,3 +178,17 @@ def test_plain_c_host_links_and_runs(handle, tmp_path):
                     "-Wl,-rpath," + lib_dir], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+
+
+def test_validated_kernels_are_bit_identical():
+    """The default build's kernels that were validated on hardware must not change without a new GPU validation:
+    experiments sit behind build options, new entry points bring their own kernels (tools/sass_identity.py)."""
+    import importlib.util
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    spec = importlib.util.spec_from_file_location("sass_identity", os.path.join(ROOT, "tools", "sass_identity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    changed, _ = mod.compare(build.build_library())
+    assert changed == []
