@@ -380,6 +380,47 @@ __device__ void eval_normal_eq(const float* pts, int N, const float* pose, const
     __syncthreads();
 }
 
+#if defined(EPNP_LM_COST_FIRST)
+// experiment (off by default): Huber cost of ONE pose over all resident points, block-parallel (each thread its share
+// of the pair records, packed fp32x2, rsqrt seed + one Newton step so the value tracks the normal-equation pass's
+// cost to ~1 ulp), every thread gets the total.
+struct RefinedRsqrt {
+#if defined(EPNP_SIMT_EMUL)
+    float operator()(float x) const { return 1.0f / sqrtf(x); }
+#else
+    __device__ __forceinline__ float operator()(float x) const {
+        float y;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y * fmaf(-0.5f * x * y, y, 1.5f);
+    }
+#endif
+};
+template <int DOF>
+__device__ float block_cost(const float* pts, int N, const float* pose_smem, const Cam& cam, float delta, float* red) {
+    float R[9], P[12], ps[Dim<DOF>::POSE];
+#pragma unroll
+    for (int i = 0; i < Dim<DOF>::POSE; ++i) ps[i] = pose_smem[i];
+    pose_to_rot<DOF>(ps, R);
+    make_proj(cam.k, R, ps, P);
+    float2 P2[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) P2[k] = make_float2(P[k], P[k]);
+    const float4* p4 = reinterpret_cast<const float4*>(pts);
+    const int npair = (N + 1) >> 1;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int j = threadIdx.x; j < npair; j += NT) {
+        const float4 q0 = p4[4 * j], q1 = p4[4 * j + 1], q2 = p4[4 * j + 2], q3 = p4[4 * j + 3];
+        const float2 X = make_float2(q0.x, q0.y), Y = make_float2(q0.z, q0.w), Z = make_float2(q1.x, q1.y);
+        const float2 nu = make_float2(q1.z, q1.w), nv = make_float2(q2.x, q2.y), wu = make_float2(q2.z, q2.w), wv = make_float2(q3.x, q3.y);
+        acc = cam.bounded ? pnp::pair_cost_rsq<true, true>(P2, cam, delta, X, Y, Z, nu, nv, wu, wv, acc, RefinedRsqrt())
+                          : pnp::pair_cost_rsq<false, true>(P2, cam, delta, X, Y, Z, nu, nv, wu, wv, acc, RefinedRsqrt());
+    }
+    float v[1] = {acc.x + acc.y};
+    block_sum<1>(v, red, 1);
+    return v[0];
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // LM / GN solve of the object resident in pts4.  Leaves the solution in sh.lm.pose, the covariance
 // in sh.cov (when want_cov) and writes the requested outputs.
@@ -408,6 +449,21 @@ __device__ void lm_phase(const KArgs& a, SmemHead<DOF>& sh, const float* pts4, c
         }
         PH_MARK(a, PH_LM_SERIAL);
         __syncthreads();
+#if defined(EPNP_LM_COST_FIRST)
+        for (int it = 0; it < p.lm_iter; ++it) {
+            const float cost_new = block_cost<DOF>(pts4, a.N, sh.lm.pose_new, cam, delta, sh.red);
+            if (tid == st) sh.ev[31] = lm_decide<DOF>(sh.lm, cost_new, p) ? 1.f : 0.f;
+            __syncthreads();
+            if (sh.ev[31] != 0.f) {             // accepted (CTA-uniform): linearise at the new pose
+                eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);
+                if (tid == st) lm_adopt<DOF>(sh.lm, sh.ev);
+            }
+            PH_MARK(a, PH_LM_EVAL);
+            if (tid == st && it + 1 < p.lm_iter) lm_propose<DOF>(sh.lm, p);
+            PH_MARK(a, PH_LM_SERIAL);
+            __syncthreads();
+        }
+#else
         for (int it = 0; it < p.lm_iter; ++it) {
             eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose_new, cam, delta, p.huber_eps, sh.red, sh.ev);
             PH_MARK(a, PH_LM_EVAL);
@@ -418,6 +474,7 @@ __device__ void lm_phase(const KArgs& a, SmemHead<DOF>& sh, const float* pts4, c
             PH_MARK(a, PH_LM_SERIAL);
             __syncthreads();
         }
+#endif
     } else {
         for (int it = 0; it < p.lm_iter; ++it) {
             eval_normal_eq<DOF, false>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);

@@ -848,6 +848,28 @@ template <int DOF> PNP_HD bool lm_update(LMState<DOF>& s, const float* acc, cons
     return ok;
 }
 
+// Accept / reject from the candidate's COST alone (build option EPNP_LM_COST_FIRST): the rule of lm_update, but the
+// candidate's normal equations are evaluated (and adopted with lm_adopt) only when the step is accepted -- after the
+// first few iterations most steps are rejected, and a cost-only pass is ~1/10 of a normal-equation pass.
+template <int DOF> PNP_HD bool lm_decide(LMState<DOF>& s, float cost_new, const Params& p) {
+    const float rho = (s.cost - cost_new) / s.model_change;
+    const bool ok = (rho >= p.min_relative_decrease) && (s.model_change > 0.0f);
+    if (ok) {
+#pragma unroll
+        for (int i = 0; i < Dim<DOF>::POSE; ++i) s.pose[i] = s.pose_new[i];
+        const float q = 2.0f * rho - 1.0f;
+        s.radius = s.radius / fmaxf(1.0f - q * q * q, 1.0f / 3.0f);
+    }
+    s.radius = fmaxf(fminf(s.radius, p.max_radius), p.eps);
+    if (ok) {
+        s.shrink = 2.0f;
+    } else {
+        s.radius = s.radius / s.shrink;
+        s.shrink *= 2.0f;
+    }
+    return ok;
+}
+
 // Gauss-Newton step (fast mode :136-152 and gn_step :243-253): pose_out = pose (+) -(A+eps I)^-1 g
 template <int DOF> PNP_HD void gn_advance(const float* pose, const float* acc, float eps, float* pose_out) {
     float add[DOF], step[DOF];

@@ -31,6 +31,8 @@ EXPERIMENTS = {
     "sweep_split_noclamp": ["-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
     "all": ["-DEPNP_LM_PACKED", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
     "lm_norefine": ["-DEPNP_LM_NOREFINE"],
+    "lm_cost_first": ["-DEPNP_LM_COST_FIRST"],
+    "everything": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
     "all_norefine": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
 }
 
