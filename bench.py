@@ -245,6 +245,9 @@ def main():
     ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
                     help="N > 1: 'nccl' = overlapped all_gather_into_tensor (default, the measured configuration); "
                          "'peer' = copy-engine pulls from IPC-mapped peer buffers (sharded.PeerGather, experimental)")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0,
+                    help="N > 1: cap the CTAs NCCL may use per collective (sets NCCL_MAX_CTAS before the communicator is "
+                         "created; 0 = NCCL's default).  The overlapped gather shares the SMs with the next solve.")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="objects per GPU (default: the metric's 4096)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -266,6 +269,8 @@ def main():
     saved_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if args.nccl_max_ctas > 0:
+            os.environ["NCCL_MAX_CTAS"] = str(args.nccl_max_ctas)
         # NCCL prints its version banner on stdout at communicator creation; keep stdout = the one JSON line
         sys.stdout.flush()
         saved_stdout = os.dup(1)
@@ -420,7 +425,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"fused EProPnP6DoF.monte_carlo_forward: LM({LM_ITER}) + cov + AMIS({MC_ITER}x"
                                    f"{MC_SAMPLES // MC_ITER}), B={Bg}/GPU, N={N_PTS}, M={MC_SAMPLES}, in-kernel Philox",
-                       "global_batch": B_total, "parallelism": f"batch-split x{world}, gather(pose,logw) only ({args.gather}), gather of batch i overlapped with solve of batch i+1",
+                       "global_batch": B_total, "parallelism": f"batch-split x{world}, gather(pose,logw) only ({args.gather}{", NCCL_MAX_CTAS=" + str(args.nccl_max_ctas) if args.nccl_max_ctas else ""}), gather of batch i overlapped with solve of batch i+1",
                        "l2": f"rotating {ROTATING_SETS} input sets ({ROTATING_SETS * 28 * N_PTS * Bg / 1e6:.0f} MB > 126 MB L2)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(), "peak_source": peak_src,
