@@ -226,7 +226,11 @@ enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum { cudaDevAttrMultiProcessorCount = 16 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2 };
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) {          // SM count; SIMT_EMUL_SMS shrinks the "device"
+    const char* e = std::getenv("SIMT_EMUL_SMS");
+    *v = (e && std::atoi(e) > 0) ? std::atoi(e) : 148;
+    return cudaSuccess;
+}
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 4; return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
