@@ -169,3 +169,28 @@ def test_persistent_grid_matches_one_object_per_cta(cuda_device, monkeypatch):
         out = native.lm_amis_fused(prob, pc["pose_init"], p, seed=9, want_cost=True)
         for k in ("pose_opt", "cost", "pose_samples", "logw"):
             assert torch.equal(out[k], ref[k]), (cap, k)
+
+
+@pytest.mark.parametrize("n_chunks,bounded", [(1, False), (3, True), (64, False)])
+def test_host_buffer_entry_point_chunking(cuda_device, monkeypatch, n_chunks, bounded):
+    """epnp_lm_amis_fused_host_f32 (host buffers, chunked copy / solve / copy-back pipeline): workspace layout, chunk
+    boundaries and per-chunk object offsets of the Philox stream give the device-resident call's results bit for bit."""
+    from epropnp_b200 import native
+    from epropnp_b200.synth import make_problem
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)       # no CUDA runtime here
+    monkeypatch.setattr(torch, "empty", (lambda f: (lambda *a, pin_memory=False, **k: f(*a, **k)))(torch.empty))
+    B, N = 11, 24
+    pc = make_problem(B, N, seed=8)
+    delta = native.adaptive_delta(pc["x2d"], pc["w2d"], 0.5)
+    lb, ub = ((pc["x2d"].amin(1) - 3.0).contiguous(), (pc["x2d"].amax(1) + 3.0).contiguous()) if bounded else (None, None)
+    prob = native.Problem(pc["x3d"], pc["x2d"], pc["w2d"], pc["cam_mats"], lb, ub, delta)
+    p = native.default_params(6, lm_iter=3, mc_samples=16, mc_iter=2)
+    ref = native.lm_amis_fused(prob, pc["pose_init"], p, seed=77, obj_offset=5, want_cost=True)
+    host = dict(x3d=pc["x3d"], x2d=pc["x2d"], w2d=pc["w2d"], cam_mats=pc["cam_mats"].contiguous(), delta=delta,
+                pose_init=pc["pose_init"], lb=lb, ub=ub)
+    ws = torch.empty(native.fused_workspace_bytes(B, N, p), dtype=torch.uint8)
+    res = native.lm_amis_fused_host(host, p, ws, n_chunks=n_chunks, seed=77, obj_offset=5)
+    for k in ("pose_opt", "logw", "pose_samples", "pose_cov", "cost"):
+        assert torch.equal(res[k], ref[k]), k
+    with pytest.raises(native.NativeError):                                            # workspace one byte short
+        native.lm_amis_fused_host(host, p, ws[:-1], n_chunks=n_chunks, seed=77)
