@@ -291,12 +291,53 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32]) {
     return v[0];
 }
 
+#if defined(EPNP_FAST_BLOCKSUM)
+// experiment (off by default): W values per lane (W = 8, 16 or 32) -> lane l holds the warp total of
+// v[l >> (5 - log2 W)]: log2(W) transposed-butterfly stages (W - 1 shuffles) + plain butterfly adds for the rest,
+// instead of 5 shuffles per value.
+template <int W> __device__ __forceinline__ float warp_transpose_sum_w(float (&v)[W]) {
+    static_assert(W == 8 || W == 16 || W == 32, "W must be 8, 16 or 32");
+    const int lane = threadIdx.x & 31;
+    int m = 16;
+#pragma unroll
+    for (int half = W / 2; half >= 1; half >>= 1, m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const float keep = up ? v[k + half] : v[k];
+            const float send = up ? v[k] : v[k + half];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (int o = 16 / W; o >= 1; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;
+}
+#endif
+
 // Block-wide sums of K values per thread; every thread gets the totals.  `red` holds two halves of
 // NW*32 floats: call sites alternate `half` so one __syncthreads per reduction is enough (a thread can be
 // at most one reduction ahead of the slowest reader, and then it writes the other half).
 template <int K> __device__ __forceinline__ void block_sum(float (&v)[K], float* red, int half) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* r = red + half * (NW * 32);
+#if defined(EPNP_FAST_BLOCKSUM)
+    if constexpr (K > 2) {
+        constexpr int W = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+        static_assert(K <= 32, "block_sum: at most 32 values");
+        float w[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) w[k] = k < K ? v[k] : 0.f;
+        const float tot = warp_transpose_sum_w<W>(w);
+        constexpr int SH = W == 8 ? 2 : (W == 16 ? 1 : 0);
+        if ((lane & ((1 << SH) - 1)) == 0 && (lane >> SH) < K) r[warp * 32 + (lane >> SH)] = tot;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = (r[k] + r[32 + k]) + (r[64 + k] + r[96 + k]);
+        return;
+    }
+#endif
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll

@@ -32,7 +32,9 @@ EXPERIMENTS = {
     "all": ["-DEPNP_LM_PACKED", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
     "lm_norefine": ["-DEPNP_LM_NOREFINE"],
     "lm_cost_first": ["-DEPNP_LM_COST_FIRST"],
-    "everything": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
+    "fast_blocksum": ["-DEPNP_FAST_BLOCKSUM"],
+    "everything": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
+                   "-DEPNP_FAST_BLOCKSUM"],
     "all_norefine": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
 }
 

@@ -61,7 +61,7 @@ from epropnp_b200.build import EXPERIMENTS  # noqa: E402
 # every option is exercised alone or in a combination ("all" = packed LM + split + clamp-free sweep; "everything" adds
 # the plain fp32 LM step and the cost-first LM loop); the remaining EXPERIMENTS entries are unions of these and are
 # left to tools/variants.py
-EMULATED_VARIANTS = ["lm_packed", "lm_cost_first", "sweep_rsq", "sweep_noclamp", "sweep_split", "all", "everything"]
+EMULATED_VARIANTS = ["lm_packed", "lm_cost_first", "fast_blocksum", "sweep_rsq", "sweep_noclamp", "sweep_split", "all", "everything"]
 
 
 @pytest.fixture(params=EMULATED_VARIANTS)

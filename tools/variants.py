@@ -11,6 +11,7 @@ shown them parity-green and faster:
     EPNP_SWEEP_SPLIT     ... + two samples per thread over half of the points each
     EPNP_LM_NOREFINE     LM step from the plain fp32 Cholesky solve (no fp64-residual refinement on the serial lane)
     EPNP_LM_COST_FIRST   LM accept / reject from a cost-only pass; normal equations only for accepted steps
+    EPNP_FAST_BLOCKSUM   block reductions of the AMIS refit as transposed butterflies (16-31 shuffles instead of 5 per value)
 
     python tools/variants.py build            # every variant -> epro-pnp_b200/lib/variants/ (they travel with gpurun)
     python tools/variants.py static           # registers / spills / hot-loop instruction mix per variant (no GPU)
