@@ -115,7 +115,9 @@ def cmd_static(args):
 
 
 def cmd_run(args):
-    names = args.names or list(VARIANTS)
+    # default selection: every option on its own + everything together (the unions in between are left to the caller)
+    names = args.names or ["default", "lm_packed", "lm_norefine", "lm_cost_first", "fast_blocksum", "sweep_rsq",
+                           "sweep_noclamp", "sweep_split", "everything"]
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     out_path = os.path.join(REPO, "gpurun_out", "variants.jsonl")
     B.build_library()
