@@ -166,7 +166,7 @@ if __name__ == "__main__":
         if name == "run":
             p.add_argument("--tests", default="tests/test_gpu_parity.py tests/test_gpu_edges.py",
                            help="pytest selection run per variant (add '-k golden' for a quicker pass)")
-            p.add_argument("--test-timeout", type=int, default=900)
+            p.add_argument("--test-timeout", type=int, default=400)
             p.add_argument("--steps", type=int, default=300)
             p.add_argument("--warmup", type=int, default=5)
             p.add_argument("--repeats", type=int, default=1)
