@@ -255,4 +255,4 @@ def lm_amis_fused_host(host, params, workspace, n_chunks=8, seed=0, obj_offset=0
 
 
 __all__ = ["Problem", "adaptive_delta", "cost_backward", "evaluate_cost", "evaluate_full", "lm_solve", "amis", "lm_amis_fused",
-           "lm_amis_fused_host", "fused_workspace_bytes", "default_params", "NativeError", "capi"]
+           "lm_amis_fused_host", "fused_workspace_bytes", "rslm", "gn_plus_backward", "default_params", "NativeError", "capi"]

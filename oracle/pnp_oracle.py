@@ -29,7 +29,7 @@ Reference map (file:line under /root/reference/epropnp/):
 """
 import math
 from dataclasses import dataclass
-from typing import Optional, Union
+from typing import Union
 
 import torch
 

@@ -1,6 +1,5 @@
 """The torch-composite pieces of the training path run on any device: checked here on CPU (float64) against
 gradients recorded from the unmodified reference's autograd (oracle/make_golden.py, grads=True cases)."""
-import numpy as np
 import pytest
 import torch
 

@@ -1,7 +1,6 @@
 """Edge cases of the native path (GPU): degenerate sizes and parameters, clamped geometry, NaN isolation,
 batch sizes that do not divide the persistent grid, the largest resident N.  Compared with the CPU oracle where
 the result is well defined, otherwise checked for the reference's documented behaviour (finite / unchanged)."""
-import numpy as np
 import pytest
 import torch
 

@@ -3,8 +3,6 @@
 import ctypes
 
 import numpy as np
-import pytest
-import torch
 from hypothesis import HealthCheck, given, settings, strategies as st
 
 from epropnp_b200 import build

@@ -118,7 +118,7 @@ def test_variant_north_star_shape(monkeypatch, variant):
 # the round-1 `pad_last_pair` hazard is caught by exactly this test when re-introduced).
 def _all_outputs(dev, dof, odd_points):
     from epropnp_b200 import native
-    from epropnp_b200.synth import make_noise, make_problem
+    from epropnp_b200.synth import make_problem
     B, N, M, I = 3, (37 if odd_points else 64), 128, 4
     pc = make_problem(B, N, seed=77, dof=dof)
     prob = native.Problem(pc["x3d"], pc["x2d"], pc["w2d"], pc["cam_mats"], -50.0, 700.0,
