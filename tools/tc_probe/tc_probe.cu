@@ -107,7 +107,7 @@ __device__ __forceinline__ void fill_operand(float* dst, const float* src /*rows
 }
 
 // ---------------------------------------------------------------------------------------------- probe 1
-__global__ void __launch_bounds__(128) correctness_kernel(const float* A, const float* B, float* D, int N, int hyp) {
+__global__ void __launch_bounds__(128) correctness_kernel(const float* A, const float* B, float* D, int N, int hyp, int dup_b) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* sA = reinterpret_cast<float*>(smem);                     // 2 * 128 * 4 floats
     float* sB = sA + 2 * M_ROWS * 4;                                // 2 * N * 4 floats
@@ -126,7 +126,9 @@ __global__ void __launch_bounds__(128) correctness_kernel(const float* A, const 
     tc_fence_after();
     const uint32_t taddr = *slot;
     if (threadIdx.x == 0) {
-        const uint32_t chunkA = M_ROWS * 16, chunkB = (uint32_t)N * 16, group = 128;
+        // dup_b: describe B with a K-chunk stride of 0, i.e. both K-halves read chunk 0 (would save the duplicated
+        // operand copy of the split-precision scheme if the hardware accepts it)
+        const uint32_t chunkA = M_ROWS * 16, chunkB = dup_b ? 0u : (uint32_t)N * 16, group = 128;
         const uint64_t da = hyp == 0 ? make_desc(smem_u32(sA), chunkA, group) : make_desc(smem_u32(sA), group, chunkA);
         const uint64_t db = hyp == 0 ? make_desc(smem_u32(sB), chunkB, group) : make_desc(smem_u32(sB), group, chunkB);
         mma_tf32(taddr, da, db, make_idesc(M_ROWS, N), 0u);
@@ -288,7 +290,7 @@ int main(int argc, char** argv) {
     for (int hyp = 0; hyp < 2; ++hyp) {
         CK(cudaMemset(dD, 0xFF, got.size() * 4));
         const size_t smem = (2 * M_ROWS * 4 + 2 * N * 4) * 4 + 64;
-        correctness_kernel<<<1, 128, smem>>>(dA, dB, dD, N, hyp);
+        correctness_kernel<<<1, 128, smem>>>(dA, dB, dD, N, hyp, 0);
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(got.data(), dD, got.size() * 4, cudaMemcpyDeviceToHost));
         double worst = 0;
@@ -302,7 +304,23 @@ int main(int argc, char** argv) {
         std::printf(", \"hypothesis_%d\": {\"lbo_is\": \"%s\", \"max_abs_err\": %.4g, \"mismatches\": %ld, \"of\": %zu}", hyp,
                     hyp == 0 ? "K-chunk stride" : "8-row-group stride", worst, bad, got.size());
     }
-    (void)tf32_trunc;
+    {   // zero K-chunk stride on B: D = A[:, 0:4] B[:, 0:4]^T + A[:, 4:8] B[:, 0:4]^T
+        for (int m = 0; m < M_ROWS; ++m)
+            for (int n = 0; n < N; ++n) {
+                float s = 0.f;
+                for (int k = 0; k < KDIM; ++k) s += A[m * KDIM + k] * B[n * KDIM + (k % 4)];
+                ref[(size_t)m * N + n] = s;
+            }
+        CK(cudaMemset(dD, 0xFF, got.size() * 4));
+        const size_t smem = (2 * M_ROWS * 4 + 2 * N * 4) * 4 + 64;
+        correctness_kernel<<<1, 128, smem>>>(dA, dB, dD, N, good_hyp, 1);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(got.data(), dD, got.size() * 4, cudaMemcpyDeviceToHost));
+        long bad = 0;
+        for (size_t i = 0; i < got.size(); ++i)
+            if (!(std::fabs((double)got[i] - (double)ref[i]) <= 1e-6)) ++bad;
+        std::printf(", \"zero_chunk_stride_on_b\": {\"mismatches\": %ld, \"of\": %zu}", bad, got.size());
+    }
     // ---------------- probe 2: sweep throughput, tensor-core projection vs CUDA-core projection
     {
         const int NP = 512, reps = 64, blocks = 148 * 4;
