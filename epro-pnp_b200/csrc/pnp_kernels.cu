@@ -37,7 +37,7 @@
 namespace {
 using namespace pnp;
 
-#if (defined(EPNP_SWEEP_NOCLAMP) || defined(EPNP_SWEEP_SPLIT)) && !defined(EPNP_SWEEP_RSQ)
+#if (defined(EPNP_SWEEP_NOCLAMP) || defined(EPNP_SWEEP_SPLIT) || defined(EPNP_TF32X3_NUMERICS)) && !defined(EPNP_SWEEP_RSQ)
 #define EPNP_SWEEP_RSQ 1
 #endif
 

@@ -8,6 +8,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "epropnp_b200.h"
 
@@ -166,14 +167,50 @@ PNP_HD float point_cost(const float* P, const Cam& c, float delta, float half_d2
 // observations as the staged pair records hold them.
 struct ExactRsqrt { PNP_HD float operator()(float x) const { return 1.0f / sqrtf(x); } };
 
+#if defined(EPNP_TF32X3_NUMERICS)
+PNP_HD float tf32_hi(float x) {                           // keep sign, exponent and the top 10 mantissa bits
+    uint32_t u;
+#if defined(__CUDA_ARCH__)
+    u = __float_as_uint(x) & 0xFFFFE000u;
+    return __uint_as_float(u);
+#else
+    memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4);
+    return x;
+#endif
+}
+// one row of K[R|t] times (X, Y, Z, 1) from split operands: sum_k (hi hi + lo hi + hi lo), fp32 accumulation
+PNP_HD float tf32x3_row(const V2* P2, int r, float X, float Y, float Z) {
+    const float x[4] = {X, Y, Z, 1.0f};
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float p = P2[r + k].x, ph = tf32_hi(p), pl = tf32_hi(p - ph);
+        const float xh = tf32_hi(x[k]), xl = tf32_hi(x[k] - xh);
+        acc = fmaf(ph, xh, acc);
+        acc = fmaf(pl, xh, acc);
+        acc = fmaf(ph, xl, acc);
+    }
+    return acc;
+}
+#endif
+
 // CLAMPZ = false: the caller has shown zh >= z_min for every point of the object under this pose
 // (pose_depth_margin below), so the clamp is the identity and its two scalar FMNMX are dropped.
 template <bool BOUNDED, bool CLAMPZ = true, class Rsqrt = ExactRsqrt>
 PNP_HD V2 pair_cost_rsq(const V2* P2, const Cam& c, float delta, V2 X, V2 Y, V2 Z, V2 nu, V2 nv, V2 wu, V2 wv,
                         V2 acc, Rsqrt rsq) {
+#if defined(EPNP_TF32X3_NUMERICS)
+    // numerics study only: the projection as the tcgen05 plan would compute it -- operands split into
+    // TF32 hi + lo parts, products hi*hi + lo*hi + hi*lo accumulated in fp32 -- on the ordinary sweep's control flow,
+    // so the whole parity suite can be run on these numerics before any tensor-core code exists
+    V2 xh = v2(tf32x3_row(P2, 0, X.x, Y.x, Z.x), tf32x3_row(P2, 0, X.y, Y.y, Z.y));
+    V2 yh = v2(tf32x3_row(P2, 4, X.x, Y.x, Z.x), tf32x3_row(P2, 4, X.y, Y.y, Z.y));
+    const V2 zh = v2(tf32x3_row(P2, 8, X.x, Y.x, Z.x), tf32x3_row(P2, 8, X.y, Y.y, Z.y));
+#else
     V2 xh = v2fma(P2[0], X, v2fma(P2[1], Y, v2fma(P2[2], Z, P2[3])));
     V2 yh = v2fma(P2[4], X, v2fma(P2[5], Y, v2fma(P2[6], Z, P2[7])));
     const V2 zh = v2fma(P2[8], X, v2fma(P2[9], Y, v2fma(P2[10], Z, P2[11])));
+#endif
     const V2 z = CLAMPZ ? v2(fmaxf(zh.x, c.z_min), fmaxf(zh.y, c.z_min)) : zh;
     if (BOUNDED) {
         const V2 lx = v2mul(v2splat(c.lbx), z), ux = v2mul(v2splat(c.ubx), z);

@@ -33,6 +33,7 @@ EXPERIMENTS = {
     "lm_norefine": ["-DEPNP_LM_NOREFINE"],
     "lm_cost_first": ["-DEPNP_LM_COST_FIRST"],
     "fast_blocksum": ["-DEPNP_FAST_BLOCKSUM"],
+    "tf32x3_numerics": ["-DEPNP_TF32X3_NUMERICS"],        # accuracy study of the tensor-core plan, not a speed-up
     "everything": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
                    "-DEPNP_FAST_BLOCKSUM"],
     "all_norefine": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],

@@ -194,3 +194,17 @@ def test_host_buffer_entry_point_chunking(cuda_device, monkeypatch, n_chunks, bo
         assert torch.equal(res[k], ref[k]), k
     with pytest.raises(native.NativeError):                                            # workspace one byte short
         native.lm_amis_fused_host(host, p, ws[:-1], n_chunks=n_chunks, seed=77)
+
+
+# ------------------------------------------------------------------------------------------------
+# Accuracy gate of the tensor-core plan: the ordinary sweep with the projection computed the
+# way tcgen05 kind::tf32 would (operands split into TF32 hi + lo, hi*hi + lo*hi + hi*lo, fp32 accumulation).
+@pytest.mark.parametrize("name", golden_names("mc6"))
+def test_tf32x3_projection_numerics_keep_parity(monkeypatch, name):
+    dev = simt_native.install(monkeypatch, EXPERIMENTS["tf32x3_numerics"])
+    _gp.test_golden_fused_lm_amis(dev, name)
+
+
+def test_tf32x3_projection_numerics_at_north_star_shape(monkeypatch):
+    dev = simt_native.install(monkeypatch, EXPERIMENTS["tf32x3_numerics"])
+    _gp.test_fused_against_oracle_north_star_shape(dev, 48, 512, 512, 4)
