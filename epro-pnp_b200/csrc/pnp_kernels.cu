@@ -16,6 +16,12 @@
 //     all N points with the pre-multiplied projection K[R|t] (points are smem broadcasts), evaluates
 //     the proposal densities it needs; the proposal refit is a handful of block reductions.
 // No tensor cores: the only contraction is 6-deep, the work is FP32-pipe + MUFU bound.
+//
+// Build options (all OFF in the shipped library; DESIGN.md section 9.2, tools/variants.py, and the CPU emulation in
+// tests/simt_emul run every one of them): EPNP_LM_PACKED, EPNP_LM_NOREFINE, EPNP_LM_COST_FIRST, EPNP_SWEEP_RSQ,
+// EPNP_SWEEP_NOCLAMP, EPNP_SWEEP_SPLIT, EPNP_FAST_BLOCKSUM (candidate speed-ups awaiting their first GPU A/B),
+// EPNP_TF32X3_NUMERICS (accuracy study), EPNP_PHASE_TIMERS (profiling), EPNP_SIMT_EMUL (g++ build for the emulator).
+// The kernels of the default build are pinned by profiles/validated_sass.json (tools/sass_identity.py).
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
