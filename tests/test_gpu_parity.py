@@ -268,7 +268,7 @@ def test_lm_flip_rate_at_north_star_shape(big):
     """LM poses of 1024 objects (N = 512) against the fp64 oracle: <= 1e-4 for (almost) all, the rest must
     be cost-equivalent accept/reject flips; the flip rate is printed for the record."""
     from oracle import pnp_oracle as orc
-    n = 1024
+    n = min(1024, big["prob"].B)
     d = torch.float64
     cam = orc.Camera(big["cam_mats"][:n].cpu().to(d), 0.1)
     x3d, x2d, w2d = (big[k][:n].cpu().to(d) for k in ("x3d", "x2d", "w2d"))
@@ -281,7 +281,7 @@ def test_lm_flip_rate_at_north_star_shape(big):
 
 def test_tma_and_plain_loader_agree(big):
     """Misaligned input pointers force the non-TMA loader; the results must not change by a bit."""
-    n = 64
+    n = min(64, big["prob"].B)
     def shifted(t):
         buf = torch.empty(t[:n].numel() + 1, dtype=t.dtype, device=t.device)
         buf[1:].copy_(t[:n].reshape(-1))
@@ -296,8 +296,8 @@ def test_tma_and_plain_loader_agree(big):
 
 
 def test_point_permutation_invariance(big):
-    n = 128
-    perm = torch.randperm(512, device=big["x3d"].device, generator=None)
+    n = min(128, big["prob"].B)
+    perm = torch.randperm(big["prob"].N, device=big["x3d"].device, generator=None)
     sub = native.Problem(big["x3d"][:n], big["x2d"][:n], big["w2d"][:n], big["cam_mats"][:n], None, None, big["delta"][:n])
     subp = native.Problem(big["x3d"][:n][:, perm], big["x2d"][:n][:, perm], big["w2d"][:n][:, perm], big["cam_mats"][:n],
                           None, None, big["delta"][:n])
@@ -310,7 +310,7 @@ def test_point_permutation_invariance(big):
 def test_philox_draws_are_statistically_equivalent(big):
     """Production RNG (in-kernel Philox) vs injected torch noise: same evidence estimate per object
     (log mean weight) within Monte-Carlo error, and matching ESS distribution."""
-    n, M = 256, 512
+    n, M = min(256, big["prob"].B), int(big["params"].mc_samples)
     dev = big["x3d"].device
     sub = native.Problem(big["x3d"][:n], big["x2d"][:n], big["w2d"][:n], big["cam_mats"][:n], None, None, big["delta"][:n])
     noise = tuple(t.to(dev) for t in make_noise(n, M, seed=77))

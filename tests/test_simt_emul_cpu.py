@@ -208,3 +208,36 @@ def test_tf32x3_projection_numerics_keep_parity(monkeypatch, name):
 def test_tf32x3_projection_numerics_at_north_star_shape(monkeypatch):
     dev = simt_native.install(monkeypatch, EXPERIMENTS["tf32x3_numerics"])
     _gp.test_fused_against_oracle_north_star_shape(dev, 48, 512, 512, 4)
+
+
+# ------------------------------------------------------------------------------------------------
+# The size-independent properties the GPU suite checks at B = 4096 (determinism, shard invariance with object
+# offsets, TMA vs plain loader, point-permutation invariance, sanity of the weights), at a size the emulator affords.
+_BIG = {}
+
+
+def _small_big(flags):
+    from epropnp_b200 import native
+    from epropnp_b200.synth import make_problem
+    d = {k: v for k, v in make_problem(12, 512, seed=7).items()}
+    d["delta"] = native.adaptive_delta(d["x2d"], d["w2d"], 0.5)
+    d["prob"] = native.Problem(d["x3d"], d["x2d"], d["w2d"], d["cam_mats"], None, None, d["delta"])
+    d["params"] = native.default_params(6, mc_samples=512, mc_iter=4)
+    d["out"] = native.lm_amis_fused(d["prob"], d["pose_init"], d["params"], seed=1234, want_cost=True)
+    return d
+
+
+@pytest.fixture(params=["default", "everything"])
+def big(request, monkeypatch):
+    flags = tuple(EXPERIMENTS.get(request.param, ()))
+    simt_native.install(monkeypatch, flags)
+    if flags not in _BIG:
+        _BIG[flags] = _small_big(flags)
+    return _BIG[flags]
+
+
+test_full_size_sanity = _gp.test_full_size_sanity
+test_full_size_deterministic_and_shard_invariant = _gp.test_full_size_deterministic_and_shard_invariant
+test_lm_flip_rate_at_north_star_shape = _gp.test_lm_flip_rate_at_north_star_shape
+test_tma_and_plain_loader_agree = _gp.test_tma_and_plain_loader_agree
+test_point_permutation_invariance = _gp.test_point_permutation_invariance
