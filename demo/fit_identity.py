@@ -90,19 +90,20 @@ def pose_errors(pose, gt):
     return dist_t.mean().item(), (2 * torch.acos(dot)).mean().item()
 
 
-def run(steps=300, batch_size=256, seed=0, log_every=50, verbose=True):
-    device = torch.device("cuda:0")
+def run(steps=300, batch_size=256, seed=0, log_every=50, verbose=True, device=None, test_size=1024):
+    device = torch.device("cuda:0") if device is None else device
     torch.manual_seed(seed)
     gen = torch.Generator().manual_seed(seed)
     in_pose, out_pose = make_data(steps * batch_size, device, 0.01, gen)
-    test_in, _ = make_data(1024, device, 0.0, gen)
+    test_in, _ = make_data(test_size, device, 0.0, gen)
     cam = torch.eye(3, device=device)
     model = Model().to(device)
     loss_fn = MonteCarloPoseLoss().to(device)
     opt = torch.optim.Adam([{"params": model.mlp.parameters()}, {"params": model.log_weight_scale, "lr": 1e-2}], lr=1e-4)
-    e0 = pose_errors(model.forward_test(test_in, cam.expand(1024, -1, -1)), test_in)
+    e0 = pose_errors(model.forward_test(test_in, cam.expand(test_size, -1, -1)), test_in)
     hist = []
-    torch.cuda.synchronize()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
     t0 = time.time()
     for it in range(steps):
         bi, bo = in_pose[it * batch_size:(it + 1) * batch_size], out_pose[it * batch_size:(it + 1) * batch_size]
@@ -119,9 +120,10 @@ def run(steps=300, batch_size=256, seed=0, log_every=50, verbose=True):
         hist.append((loss_mc.item(), loss_t.item(), loss_r.item()))
         if verbose and (it % log_every == 0 or it == steps - 1):
             print(f"step {it + 1}/{steps}: loss_mc={hist[-1][0]:.4f} loss_t={hist[-1][1]:.4f} loss_r={hist[-1][2]:.4f}", flush=True)
-    torch.cuda.synchronize()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
     dt = time.time() - t0
-    e1 = pose_errors(model.forward_test(test_in, cam.expand(1024, -1, -1)), test_in)
+    e1 = pose_errors(model.forward_test(test_in, cam.expand(test_size, -1, -1)), test_in)
     k = max(1, steps // 10)
     first = sum(h[0] for h in hist[:k]) / k
     last = sum(h[0] for h in hist[-k:]) / k

@@ -79,3 +79,19 @@ def test_inference_step(dev):
     assert ((pose_opt[:, :3] - gt[:, :3]).norm(dim=-1) < 0.05).all()
     assert (1 - (pose_opt[:, 3:] * gt[:, 3:]).sum(-1).abs() < 1e-3).all()
     assert samples[:, :1].shape == (128, 1, 7) and logw[:, :1].shape == (128, 1) and torch.isfinite(logw).all()
+
+
+@pytest.mark.parametrize("fused_rslm", ["1"])     # "0" works too but spends a minute emulating 128-thread CTAs on 8-point problems
+def test_demo_training_loop_runs(dev, monkeypatch, fused_rslm):
+    """demo/fit_identity.py (the reference notebook's experiment) for a few optimiser steps on the emulated kernels:
+    RSLM initialisation in every forward, fused LM + AMIS, native backward, Adam.  (That the loss falls is the GPU
+    test's business -- tests/test_demo_gpu.py runs 160 steps.)"""
+    import os
+    import sys
+    from conftest import ROOT
+    monkeypatch.setenv("EPNP_FUSED_RSLM", fused_rslm)
+    sys.path.insert(0, os.path.join(ROOT, "demo"))
+    import fit_identity
+    out = fit_identity.run(steps=3, batch_size=4, verbose=False, device=dev, test_size=4)
+    assert out["finite"] and out["steps"] == 3
+    assert all(math.isfinite(out[k]) for k in ("loss_mc_first", "loss_mc_last", "test_t_err_before", "test_t_err_after"))
