@@ -163,15 +163,31 @@ struct SmemPlan {        // offsets in floats from the start of dynamic smem
     int stage, pts, smp, cost, logp, lw, total_bytes;
 };
 
+// alias_stage (build option EPNP_ALIAS_STAGE, one object per CTA only): the staging ring is dead once the object is
+// packed and the sample buffer is not written before the AMIS loop, so the ring lives inside it.
 template <int DOF>
-__host__ __device__ inline SmemPlan plan_smem(int N, int M, int I, bool amis) {
+__host__ __device__ inline bool can_alias_stage(int M, bool amis) {
+#if defined(EPNP_ALIAS_STAGE)
+    return amis && Dim<DOF>::POSE * M >= 2 * STAGE_FLOATS;
+#else
+    return false;
+#endif
+}
+template <int DOF>
+__host__ __device__ inline SmemPlan plan_smem(int N, int M, int I, bool amis, bool alias_stage = false) {
     SmemPlan s;
     int off = (int)((sizeof(SmemHead<DOF>) + 127) / 128 * 128 / 4);
-    s.stage = off; off += 2 * STAGE_FLOATS;
+    const bool alias = alias_stage && can_alias_stage<DOF>(M, amis);
+    s.stage = off; if (!alias) off += 2 * STAGE_FLOATS;
     s.pts = off; off += 16 * ((N + 1) / 2);        // 64 B per pair of points
     s.smp = off; if (amis) off += Dim<DOF>::POSE * M;
+    if (alias) s.stage = s.smp;
     s.cost = off; if (amis) off += M;
+#if defined(EPNP_AMIS_LSE)
+    s.logp = off; if (amis) off += M;               // running log-sum-exp of the proposal densities, one per sample
+#else
     s.logp = off; if (amis) off += I * M;
+#endif
     s.lw = off; if (amis) off += M;
     s.total_bytes = off * 4;
     return s;
@@ -784,6 +800,24 @@ __device__ void sweep_new_samples(const float* pts, int N, const float* smp, flo
 }
 #endif
 
+#if defined(EPNP_AMIS_LSE)
+// experiment (off by default): the mixture density of a sample is kept as ONE running log-sum-exp over the proposals
+// seen so far instead of one log-density per (proposal, sample) -- (I - 1) * M floats less shared memory.
+struct RunningLse {
+    float top, acc;
+    __device__ __forceinline__ void start(float lp) { top = lp; acc = 1.f; }
+    __device__ __forceinline__ void add(float lp) {
+        if (lp > top) { acc = fmaf(acc, expf(top - lp), 1.f); top = lp; }
+        else acc += expf(lp - top);
+    }
+    __device__ __forceinline__ float value() const { return top + logf(acc); }
+};
+__device__ __forceinline__ float log_add_exp(float a, float b) {
+    const float hi = fmaxf(a, b), lo = fminf(a, b);
+    return (lo == -CUDART_INF_F) ? hi : hi + log1pf(expf(lo - hi));
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // AMIS loop for the resident object (6DoF).  sh.prop[0] must not be set yet; pose / cov are read from
 // pose_opt[7] / cov[36] (shared or registers of thread 0 -- passed as shared pointers).
@@ -834,7 +868,16 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
 #else
             cst[m] = pose_cost<6>(pts4, a.N, q, cam, delta);
 #endif
+#if defined(EPNP_AMIS_LSE)
+            {
+                RunningLse l;
+                l.start(proposal_logpdf6(sh.prop[0], q));
+                for (int j = 1; j <= i; ++j) l.add(proposal_logpdf6(sh.prop[j], q));
+                logp[m] = l.value();
+            }
+#else
             for (int j = 0; j <= i; ++j) logp[j * M + m] = proposal_logpdf6(sh.prop[j], q);
+#endif
         }
 #if defined(EPNP_SWEEP_SPLIT)
         __syncthreads();
@@ -846,7 +889,11 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
             float q[7];
 #pragma unroll
             for (int k = 0; k < 7; ++k) q[k] = smp[m * 7 + k];
+#if defined(EPNP_AMIS_LSE)
+            logp[m] = log_add_exp(logp[m], proposal_logpdf6(sh.prop[i], q));
+#else
             logp[i * M + m] = proposal_logpdf6(sh.prop[i], q);
+#endif
         }
         __syncthreads();
         PH_MARK(a, PH_LOGP_OLD);
@@ -855,10 +902,14 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
         const float log_cnt = logf((float)(i + 1));
         float mx = -CUDART_INF_F;
         for (int m = tid; m < n; m += NT) {
+#if defined(EPNP_AMIS_LSE)
+            const float top = logp[m], acc = 1.f;               // logp[m] already is the log-sum-exp
+#else
             float top = logp[m];
             for (int j = 1; j <= i; ++j) top = fmaxf(top, logp[j * M + m]);
             float acc = 0.f;
             for (int j = 0; j <= i; ++j) acc += expf(logp[j * M + m] - top);
+#endif
 #if defined(EPNP_SWEEP_SPLIT)
             float cm = cst[m];
             if (m >= i * S) { cm += lw[m]; cst[m] = cm; }       // fold the second point half of a new sample in
@@ -1043,24 +1094,41 @@ __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, 
 #else
             cst[m] = pose_cost<4>(pts4, a.N, q, cam, delta);
 #endif
+#if defined(EPNP_AMIS_LSE)
+            {
+                RunningLse l;
+                l.start(proposal_logpdf4(sh.prop4[0], q));
+                for (int j = 1; j <= i; ++j) l.add(proposal_logpdf4(sh.prop4[j], q));
+                logp[m] = l.value();
+            }
+#else
             for (int j = 0; j <= i; ++j) logp[j * M + m] = proposal_logpdf4(sh.prop4[j], q);
+#endif
         }
 #if defined(EPNP_SWEEP_SPLIT)
         __syncthreads();
         sweep_new_samples<4>(pts4, a.N, smp, cst, lw, i * S, S, cam, delta, radius);
 #endif
         PH_MARK(a, PH_DRAW_SWEEP);
+#if defined(EPNP_AMIS_LSE)
+        for (int m = tid; m < i * S; m += NT) logp[m] = log_add_exp(logp[m], proposal_logpdf4(sh.prop4[i], smp + m * 4));
+#else
         for (int m = tid; m < i * S; m += NT) logp[i * M + m] = proposal_logpdf4(sh.prop4[i], smp + m * 4);
+#endif
         __syncthreads();
         PH_MARK(a, PH_LOGP_OLD);
         const int n = (i + 1) * S;
         const float log_cnt = logf((float)(i + 1));
         float mx = -CUDART_INF_F;
         for (int m = tid; m < n; m += NT) {
+#if defined(EPNP_AMIS_LSE)
+            const float top = logp[m], acc = 1.f;               // logp[m] already is the log-sum-exp
+#else
             float top = logp[m];
             for (int j = 1; j <= i; ++j) top = fmaxf(top, logp[j * M + m]);
             float acc = 0.f;
             for (int j = 0; j <= i; ++j) acc += expf(logp[j * M + m] - top);
+#endif
 #if defined(EPNP_SWEEP_SPLIT)
             float cm = cst[m];
             if (m >= i * S) { cm += lw[m]; cst[m] = cm; }       // fold the second point half of a new sample in
@@ -1122,12 +1190,20 @@ __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, 
 
 // ------------------------------------------------------------------------------------------------
 // Kernels
+#if !defined(EPNP_CTAS_PER_SM)
+#define EPNP_CTAS_PER_SM 4              // build option: 5 needs <= 96 registers and <= 44 KB of shared memory per CTA
+#endif
 template <int DOF, bool DO_LM, bool DO_AMIS>
-__global__ void __launch_bounds__(NT, 4) solve_kernel(const KArgs a) {
+__global__ void __launch_bounds__(NT, EPNP_CTAS_PER_SM) solve_kernel(const KArgs a) {
     EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
     SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
     float* dyn = reinterpret_cast<float*>(smem_raw);
+#if defined(EPNP_ALIAS_STAGE)
+    // one object per CTA (grid == B): nothing is prefetched during the solve, the ring may live in the sample buffer
+    const SmemPlan pl = plan_smem<DOF>(a.N, a.p.mc_samples, a.p.mc_iter, DO_AMIS, gridDim.x >= (unsigned)a.B);
+#else
     const SmemPlan pl = plan_smem<DOF>(a.N, a.p.mc_samples, a.p.mc_iter, DO_AMIS);
+#endif
     float* pts4 = dyn + pl.pts;
 
     Loader ld(a, sh.bar, dyn + pl.stage);
@@ -1615,7 +1691,8 @@ int check_common(const KArgs& a) {
 }
 
 template <class Kern>
-int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream) {
+int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream, int smem_bytes_single = 0) {
+    (void)smem_bytes_single;            // EPNP_ALIAS_STAGE: dynamic shared memory when every CTA solves one object
     if (a.B == 0) return EPNP_OK;
     if ((size_t)smem_bytes > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
     a.use_tma = (a.N % 4 == 0) && aligned16(a.x3d) && aligned16(a.x2d) && aligned16(a.w2d);
@@ -1645,6 +1722,9 @@ int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream) 
         rounds = (k <= 0) ? persistent_rounds : (k < persistent_rounds ? k : persistent_rounds);
     }
     const int grid = (a.B + rounds - 1) / rounds;
+#if defined(EPNP_ALIAS_STAGE)
+    if (rounds == 1 && smem_bytes_single > 0) smem_bytes = smem_bytes_single;      // the kernel sees grid == B too
+#endif
     EPNP_LAUNCH(kern, grid, NT, smem_bytes, stream, a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
@@ -1861,9 +1941,9 @@ int epnp_amis_f32(const float* x3d, const float* x2d, const float* w2d, const fl
     if (any && !all) return EPNP_ERR_BAD_ARG;
     if (p->dof == 6)
         return launch_persistent(solve_kernel<6, false, true>, a, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes,
-                                 (cudaStream_t)stream);
+                                 (cudaStream_t)stream, plan_smem<6>(N, p->mc_samples, p->mc_iter, true, true).total_bytes);
     return launch_persistent(solve_kernel<4, false, true>, a, plan_smem<4>(N, p->mc_samples, p->mc_iter, true).total_bytes,
-                             (cudaStream_t)stream);
+                             (cudaStream_t)stream, plan_smem<4>(N, p->mc_samples, p->mc_iter, true, true).total_bytes);
 }
 
 int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
@@ -1891,9 +1971,9 @@ int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d,
     if (any && !all) return EPNP_ERR_BAD_ARG;
     if (p->dof == 6)
         return launch_persistent(solve_kernel<6, true, true>, a, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes,
-                                 (cudaStream_t)stream);
+                                 (cudaStream_t)stream, plan_smem<6>(N, p->mc_samples, p->mc_iter, true, true).total_bytes);
     return launch_persistent(solve_kernel<4, true, true>, a, plan_smem<4>(N, p->mc_samples, p->mc_iter, true).total_bytes,
-                             (cudaStream_t)stream);
+                             (cudaStream_t)stream, plan_smem<4>(N, p->mc_samples, p->mc_iter, true, true).total_bytes);
 }
 
 int epnp_cost_backward_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,

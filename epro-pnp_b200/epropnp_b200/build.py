@@ -34,6 +34,13 @@ EXPERIMENTS = {
     "lm_cost_first": ["-DEPNP_LM_COST_FIRST"],
     "fast_blocksum": ["-DEPNP_FAST_BLOCKSUM"],
     "tf32x3_numerics": ["-DEPNP_TF32X3_NUMERICS"],        # accuracy study of the tensor-core plan, not a speed-up
+    "amis_lse": ["-DEPNP_AMIS_LSE"],
+    "alias_stage": ["-DEPNP_ALIAS_STAGE"],
+    # five resident CTAs per SM: 96 registers (the packed LM evaluation would spill) and 39.8 KB of shared memory per CTA
+    "five_ctas": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
+                  "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE", "-DEPNP_CTAS_PER_SM=5"],
+    "four_ctas_same_code": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
+                            "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE"],
     "everything": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
                    "-DEPNP_FAST_BLOCKSUM"],
     "all_norefine": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],

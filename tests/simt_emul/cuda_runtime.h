@@ -176,14 +176,21 @@ template <class F>
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call) {
     BlockState& s = state();
     const std::function<void()> body = kernel_call;
-    unsigned char* smem = (unsigned char*)std::aligned_alloc(1024, ((smem_bytes + 1023) / 1024 + 1) * 1024);
-    s.dyn_smem = smem;
+    constexpr size_t kGuard = 16384;                  // canary behind the requested bytes: writes past the launch's
+    unsigned char* smem = (unsigned char*)std::aligned_alloc(1024, ((smem_bytes + kGuard + 1023) / 1024 + 1) * 1024);
+    s.dyn_smem = smem;                                // dynamic shared memory size must not go unnoticed
     gdim() = grid;
     bdim() = block;
     for (unsigned b = 0; b < grid.x; ++b) {
         bidx() = uint3{b, 0, 0};
         std::memset(smem, 0xCD, smem_bytes);          // poison: a read of never-written shared memory shows up
+        std::memset(smem + smem_bytes, 0xEE, kGuard);
         run_block((int)block.x, body);
+        for (size_t i = 0; i < kGuard; ++i)
+            if (smem[smem_bytes + i] != 0xEE) {
+                std::fprintf(stderr, "simt_emul: write %zu bytes past the %zu bytes of dynamic shared memory\n", i, smem_bytes);
+                std::abort();
+            }
     }
     s.dyn_smem = nullptr;
     std::free(smem);
