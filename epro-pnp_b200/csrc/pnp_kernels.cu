@@ -47,6 +47,28 @@ using namespace pnp;
 #define EPNP_SWEEP_RSQ 1
 #endif
 
+#if defined(EPNP_NO_LW) && !defined(EPNP_AMIS_LSE)
+#define EPNP_AMIS_LSE 1                 // recomputing a log-weight needs the mixture density as a single value
+#endif
+// EPNP_NO_LW (experiment): no per-sample log-weight buffer in shared memory (-4 M bytes).  A log-weight is
+// -cost - (lse - log count); the refit passes recompute it where they need it, the last iteration writes it straight
+// to the output, and the split sweep parks the second point half of a new sample's cost in the object's (not yet
+// written) log-weight OUTPUT slot instead.
+#if defined(EPNP_NO_LW)
+#define LW_STORE(m, v)
+#define LW_LOGWEIGHT(m) (-cst[m] - (logp[m] - log_cnt))
+#define LW_E(m) expf(LW_LOGWEIGHT(m) - mx)
+#define LW_E_STORE(m, e)
+#define LW_W(m) (LW_E(m) * inv_sum)
+#define LW_W_STORE(m, w)
+#else
+#define LW_STORE(m, v) lw[m] = (v)
+#define LW_E(m) expf(lw[m] - mx)
+#define LW_E_STORE(m, e) lw[m] = (e)
+#define LW_W(m) (lw[m] * inv_sum)
+#define LW_W_STORE(m, w) lw[m] = (w)
+#endif
+
 constexpr int NT = 128;                 // threads per CTA
 constexpr int NW = NT / 32;
 constexpr int CH = 128;                 // correspondences per TMA chunk (2 slots x 3.5 KB)
@@ -188,7 +210,11 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int M, int I, bool amis, bo
 #else
     s.logp = off; if (amis) off += I * M;
 #endif
+#if defined(EPNP_NO_LW)
+    s.lw = off;                                     // no log-weight buffer
+#else
     s.lw = off; if (amis) off += M;
+#endif
     s.total_bytes = off * 4;
     return s;
 }
@@ -881,7 +907,11 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
         }
 #if defined(EPNP_SWEEP_SPLIT)
         __syncthreads();
+#if defined(EPNP_NO_LW)
+        sweep_new_samples<6>(pts4, a.N, smp, cst, a.logw + (size_t)obj * M, i * S, S, cam, delta, radius);
+#else
         sweep_new_samples<6>(pts4, a.N, smp, cst, lw, i * S, S, cam, delta, radius);
+#endif
 #endif
         PH_MARK(a, PH_DRAW_SWEEP);
         // ---- the new proposal on all earlier samples
@@ -912,17 +942,27 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
 #endif
 #if defined(EPNP_SWEEP_SPLIT)
             float cm = cst[m];
+#if defined(EPNP_NO_LW)
+            if (m >= i * S) { cm += a.logw[(size_t)obj * M + m]; cst[m] = cm; }   // second half parked in the output slot
+#else
             if (m >= i * S) { cm += lw[m]; cst[m] = cm; }       // fold the second point half of a new sample in
+#endif
             const float v = -cm - ((top + logf(acc)) - log_cnt);
 #else
             const float v = -cst[m] - ((top + logf(acc)) - log_cnt);
 #endif
+#if defined(EPNP_NO_LW)
+            if (i == I - 1) a.logw[(size_t)obj * M + m] = v;    // n == M on the last iteration: every slot gets its value
+#else
             lw[m] = v;
+#endif
             mx = fmaxf(mx, v);
         }
         PH_MARK(a, PH_WEIGHTS);
         if (i == I - 1) {
+#if !defined(EPNP_NO_LW)
             for (int m = tid; m < M; m += NT) a.logw[(size_t)obj * M + m] = lw[m];
+#endif
             PH_MARK(a, PH_OUTPUT);
             break;
         }
@@ -941,8 +981,8 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
 #pragma unroll
             for (int r = 0; r < 15; ++r) acc[r] = 0.f;
             for (int m = tid; m < n; m += NT) {
-                const float e = expf(lw[m] - mx);
-                lw[m] = e;
+                const float e = LW_E(m);
+                LW_E_STORE(m, e);
                 const float* s7 = smp + m * 7;
                 acc[0] += e;
                 acc[1] = fmaf(e, s7[0], acc[1]); acc[2] = fmaf(e, s7[1], acc[2]); acc[3] = fmaf(e, s7[2], acc[3]);
@@ -978,8 +1018,8 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
 #pragma unroll
             for (int r = 0; r < 17; ++r) acc[r] = 0.f;
             for (int m = tid; m < n; m += NT) {
-                const float w = lw[m] * inv_sum;                         // normalised softmax weight
-                lw[m] = w;
+                const float w = LW_W(m);                                 // normalised softmax weight
+                LW_W_STORE(m, w);
                 const float* s7 = smp + m * 7;
                 const float d0 = s7[0] - mean[0], d1 = s7[1] - mean[1], d2 = s7[2] - mean[2];
                 acc[11] = fmaf(w * d0, d0, acc[11]); acc[12] = fmaf(w * d0, d1, acc[12]); acc[13] = fmaf(w * d0, d2, acc[13]);
@@ -1013,7 +1053,11 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
             for (int r = 0; r < 11; ++r) acc[r] = 0.f;
             for (int m = tid; m < n; m += NT) {
                 const float* q = smp + m * 7 + 3;
+#if defined(EPNP_NO_LW)
+                const float wm = LW_W(m) / fmaxf(quad4(lam_inv, q), p.amis_eps);
+#else
                 const float wm = lw[m] / fmaxf(quad4(lam_inv, q), p.amis_eps);
+#endif
                 acc[0] += wm;
                 int idx = 1;
 #pragma unroll
@@ -1107,7 +1151,11 @@ __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, 
         }
 #if defined(EPNP_SWEEP_SPLIT)
         __syncthreads();
+#if defined(EPNP_NO_LW)
+        sweep_new_samples<4>(pts4, a.N, smp, cst, a.logw + (size_t)obj * M, i * S, S, cam, delta, radius);
+#else
         sweep_new_samples<4>(pts4, a.N, smp, cst, lw, i * S, S, cam, delta, radius);
+#endif
 #endif
         PH_MARK(a, PH_DRAW_SWEEP);
 #if defined(EPNP_AMIS_LSE)
@@ -1131,17 +1179,27 @@ __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, 
 #endif
 #if defined(EPNP_SWEEP_SPLIT)
             float cm = cst[m];
+#if defined(EPNP_NO_LW)
+            if (m >= i * S) { cm += a.logw[(size_t)obj * M + m]; cst[m] = cm; }   // second half parked in the output slot
+#else
             if (m >= i * S) { cm += lw[m]; cst[m] = cm; }       // fold the second point half of a new sample in
+#endif
             const float v = -cm - ((top + logf(acc)) - log_cnt);
 #else
             const float v = -cst[m] - ((top + logf(acc)) - log_cnt);
 #endif
+#if defined(EPNP_NO_LW)
+            if (i == I - 1) a.logw[(size_t)obj * M + m] = v;    // n == M on the last iteration: every slot gets its value
+#else
             lw[m] = v;
+#endif
             mx = fmaxf(mx, v);
         }
         PH_MARK(a, PH_WEIGHTS);
         if (i == I - 1) {
+#if !defined(EPNP_NO_LW)
             for (int m = tid; m < M; m += NT) a.logw[(size_t)obj * M + m] = lw[m];
+#endif
             PH_MARK(a, PH_OUTPUT);
             break;
         }
@@ -1149,8 +1207,8 @@ __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, 
         mx = block_max(mx, sh.red, 0);
         float accB[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int m = tid; m < n; m += NT) {
-            const float e = expf(lw[m] - mx);
-            lw[m] = e;
+            const float e = LW_E(m);
+            LW_E_STORE(m, e);
             const float* s4 = smp + m * 4;
             float sn, cs;
             sincosf(s4[3], &sn, &cs);
@@ -1163,7 +1221,7 @@ __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, 
         const float mean[3] = {accB[1] * inv_sum, accB[2] * inv_sum, accB[3] * inv_sum};
         float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int m = tid; m < n; m += NT) {
-            const float w = lw[m] * inv_sum;
+            const float w = LW_W(m);
             const float* s4 = smp + m * 4;
             const float d0 = s4[0] - mean[0], d1 = s4[1] - mean[1], d2 = s4[2] - mean[2];
             tc[0] = fmaf(w * d0, d0, tc[0]); tc[1] = fmaf(w * d0, d1, tc[1]); tc[2] = fmaf(w * d0, d2, tc[2]);

@@ -61,7 +61,7 @@ from epropnp_b200.build import EXPERIMENTS  # noqa: E402
 # every option is exercised alone or in a combination ("all" = packed LM + split + clamp-free sweep; "everything" adds
 # the plain fp32 LM step and the cost-first LM loop); the remaining EXPERIMENTS entries are unions of these and are
 # left to tools/variants.py
-EMULATED_VARIANTS = ["lm_packed", "lm_cost_first", "fast_blocksum", "amis_lse", "alias_stage", "five_ctas", "sweep_rsq", "sweep_noclamp", "sweep_split", "all", "everything"]
+EMULATED_VARIANTS = ["lm_packed", "lm_cost_first", "fast_blocksum", "amis_lse", "alias_stage", "no_lw", "five_ctas", "six_ctas", "sweep_rsq", "sweep_noclamp", "sweep_split", "all", "everything"]
 
 
 @pytest.fixture(params=EMULATED_VARIANTS)
@@ -104,7 +104,7 @@ def test_variant_parameter_corners(variant_device, M, I, acg, lm_iter):
     _ge.test_parameter_corners_against_oracle(variant_device, M, I, acg, lm_iter)
 
 
-@pytest.mark.parametrize("variant", ["all", "everything", "five_ctas"])
+@pytest.mark.parametrize("variant", ["all", "everything", "five_ctas", "six_ctas"])
 def test_variant_north_star_shape(monkeypatch, variant):
     """N = 512, M = 512 against the fp64 / fp32 oracle, including the north star's own <= 1e-4 statement."""
     dev = simt_native.install(monkeypatch, EXPERIMENTS[variant])
@@ -133,7 +133,7 @@ def _all_outputs(dev, dof, odd_points):
     return [t.clone() for t in res if t is not None]
 
 
-@pytest.mark.parametrize("variant", ["default", "sweep_split", "everything", "five_ctas"])
+@pytest.mark.parametrize("variant", ["default", "sweep_split", "everything", "five_ctas", "six_ctas"])
 @pytest.mark.parametrize("dof,odd_points", [(6, False), (6, True), (4, True)])
 def test_results_do_not_depend_on_thread_schedule(monkeypatch, variant, dof, odd_points):
     flags = EXPERIMENTS.get(variant, ())
@@ -227,7 +227,7 @@ def _small_big(flags):
     return d
 
 
-@pytest.fixture(params=["default", "everything", "five_ctas"])
+@pytest.fixture(params=["default", "everything", "five_ctas", "six_ctas"])
 def big(request, monkeypatch):
     flags = tuple(EXPERIMENTS.get(request.param, ()))
     simt_native.install(monkeypatch, flags)

@@ -15,6 +15,7 @@ shown them parity-green and faster:
     EPNP_AMIS_LSE        mixture densities as one running log-sum-exp per sample (-6 KB shared memory at M = 512, I = 4)
     EPNP_ALIAS_STAGE     staging ring inside the sample buffer when every CTA solves one object (-7 KB)
     EPNP_CTAS_PER_SM=5   launch bounds for five resident CTAs (96 registers; needs the two options above: 39.8 KB / CTA)
+    EPNP_NO_LW           no log-weight buffer in shared memory (recomputed where needed): 37.0 KB / CTA, six CTAs at 80 registers
 
     python tools/variants.py build            # every variant -> epro-pnp_b200/lib/variants/ (they travel with gpurun)
     python tools/variants.py static           # registers / spills / hot-loop instruction mix per variant (no GPU)
@@ -120,7 +121,7 @@ def cmd_static(args):
 def cmd_run(args):
     # default selection: every option on its own + everything together (the unions in between are left to the caller)
     names = args.names or ["default", "lm_packed", "lm_norefine", "lm_cost_first", "fast_blocksum", "sweep_rsq",
-                           "sweep_noclamp", "sweep_split", "everything", "four_ctas_same_code", "five_ctas"]
+                           "sweep_noclamp", "sweep_split", "everything", "four_ctas_same_code", "five_ctas", "six_ctas"]
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     out_path = os.path.join(REPO, "gpurun_out", "variants.jsonl")
     B.build_library()
