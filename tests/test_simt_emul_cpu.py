@@ -58,15 +58,43 @@ from conftest import golden_names  # noqa: E402
 from epropnp_b200.build import EXPERIMENTS  # noqa: E402
 
 
-# every option is exercised alone or in a combination ("all" = packed LM + split + clamp-free sweep; "everything" adds
-# the plain fp32 LM step and the cost-first LM loop); the remaining EXPERIMENTS entries are unions of these and are
-# left to tools/variants.py
-EMULATED_VARIANTS = ["lm_packed", "lm_cost_first", "fast_blocksum", "amis_lse", "alias_stage", "no_lw", "five_ctas", "six_ctas", "sweep_rsq", "sweep_noclamp", "sweep_split", "all", "everything"]
+# The combinations that are candidates for the default build get the full matrix; every single option additionally
+# runs alone on a reduced set (fused goldens incl. 4-DoF, the odd-sample-count corner, the smallest point sets).
+CANDIDATE_VARIANTS = ["everything", "five_ctas", "six_ctas"]
+SINGLE_OPTIONS = ["lm_packed", "lm_cost_first", "fast_blocksum", "amis_lse", "alias_stage", "no_lw", "sweep_rsq",
+                  "sweep_noclamp", "sweep_split"]
+EMULATED_VARIANTS = SINGLE_OPTIONS + CANDIDATE_VARIANTS
 
 
-@pytest.fixture(params=EMULATED_VARIANTS)
+@pytest.fixture(params=CANDIDATE_VARIANTS)
 def variant_device(request, monkeypatch):
     return simt_native.install(monkeypatch, EXPERIMENTS[request.param])
+
+
+@pytest.fixture(params=SINGLE_OPTIONS)
+def option_device(request, monkeypatch):
+    return simt_native.install(monkeypatch, EXPERIMENTS[request.param])
+
+
+@pytest.mark.parametrize("name", ["mc6_basic", "mc6_bounds"])
+def test_option_golden_fused_lm_amis(option_device, name):
+    _gp.test_golden_fused_lm_amis(option_device, name)
+
+
+def test_option_golden_fused_4dof(option_device):
+    _gp.test_golden_fused_lm_amis_4dof(option_device)
+
+
+@pytest.mark.parametrize("name", ["lm6_ragged", "lm6_bounds", "gn4_fast"])
+def test_option_golden_lm_and_cost(option_device, name):
+    _gp.test_golden_evaluate(option_device, name)
+    _gp.test_golden_lm_solve(option_device, name)
+
+
+def test_option_odd_sample_count_and_tiny_sets(option_device):
+    _ge.test_parameter_corners_against_oracle(option_device, 126, 2, 1, 5)
+    _ge.test_tiny_point_sets(option_device, 1)
+    _ge.test_tiny_point_sets(option_device, 5)
 
 
 @pytest.mark.parametrize("name", golden_names("mc6"))
@@ -104,7 +132,7 @@ def test_variant_parameter_corners(variant_device, M, I, acg, lm_iter):
     _ge.test_parameter_corners_against_oracle(variant_device, M, I, acg, lm_iter)
 
 
-@pytest.mark.parametrize("variant", ["all", "everything", "five_ctas", "six_ctas"])
+@pytest.mark.parametrize("variant", CANDIDATE_VARIANTS)
 def test_variant_north_star_shape(monkeypatch, variant):
     """N = 512, M = 512 against the fp64 / fp32 oracle, including the north star's own <= 1e-4 statement."""
     dev = simt_native.install(monkeypatch, EXPERIMENTS[variant])
