@@ -1761,6 +1761,11 @@ int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream, 
     if (e != cudaSuccess) return cuda_fail(e);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return cuda_fail(e);
+#if defined(EPNP_CTAS_PER_SM) && EPNP_CTAS_PER_SM > 4
+    // five / six resident CTAs need (nearly) the whole 228 KB of the SM as shared memory: ask for the full carve-out
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return cuda_fail(e);
+#endif
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem_bytes);
     if (e != cudaSuccess) return cuda_fail(e);
     if (occ < 1) return EPNP_ERR_TOO_MANY_POINTS;

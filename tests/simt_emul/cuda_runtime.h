@@ -229,7 +229,7 @@ enum { cudaSuccess = 0 };
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
-enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 enum { cudaDevAttrMultiProcessorCount = 16 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2 };
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
