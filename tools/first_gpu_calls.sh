@@ -1,0 +1,44 @@
+#!/usr/bin/env bash
+# The GPU calls that measure what was written after round 1's GPU budget was spent.
+# Every step is wrapped in its own timeout and writes under gpurun_out/; run each block as ONE gpurun call:
+#
+#   gpurun --timeout 1700 -- 'bash tools/first_gpu_calls.sh variants'        # 1 GPU, ~20 min
+#   gpurun --timeout 900  -- 'bash tools/first_gpu_calls.sh experimental'    # 1 GPU, ~8 min
+#   gpurun --gpus 2 --timeout 700 -- 'bash tools/first_gpu_calls.sh two_gpu' # 2 GPUs, ~6 min (charged x2)
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+case "${1:-}" in
+  variants)
+    # A/B of the kernel build options: per variant the GPU parity + edge tests, then one bench line
+    python tools/variants.py build > gpurun_out/variants_build.log 2>&1
+    timeout 1500 python tools/variants.py run 2>&1 | tee gpurun_out/variants_run.log | tail -20
+    ;;
+  experimental)
+    # the two opt-in kernels, their timings, the copy ceiling of the box, the e2e chunk sweep, the tcgen05 probe
+    EPNP_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_rslm_fused_gpu.py tests/test_gn_plus_backward_gpu.py -q \
+        2>&1 | tee gpurun_out/experimental_tests.log | tail -5
+    EPNP_BENCH_RSLM=1 EPNP_BENCH_GN_PLUS=1 timeout 400 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err
+    timeout 120 python tools/pcie_probe.py > gpurun_out/pcie_probe.json 2>&1
+    for c in 4 7 8 14; do
+      EPNP_E2E_CHUNKS=$c timeout 200 python bench.py --steps 100 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/e2e_chunks_$c.json
+    done
+    (cd tools/tc_probe && nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tc_probe tc_probe.cu \
+        && timeout 60 ./tc_probe) > gpurun_out/tc_probe.json 2>&1
+    tail -c 600 gpurun_out/tc_probe.json
+    ;;
+  two_gpu)
+    EPNP_TEST_PEER_GATHER=1 timeout 300 python -m pytest tests/test_peer_gather_gpu.py -q 2>&1 | tee gpurun_out/peer_gather_test.log | tail -3
+    i=0
+    for g in "--gather nccl" "--gather nccl --nccl-max-ctas 2" "--gather peer"; do
+      i=$((i + 1))
+      timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$i \
+          bench.py --gpus 2 --steps 300 --warmup 5 $g --no-cpu-baseline --no-e2e 2> gpurun_out/two_gpu_$i.err | tail -1 > gpurun_out/two_gpu_$i.json
+      cat gpurun_out/two_gpu_$i.json | cut -c1-300
+    done
+    ;;
+  *)
+    echo "usage: $0 variants | experimental | two_gpu" >&2
+    exit 2
+    ;;
+esac
