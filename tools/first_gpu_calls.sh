@@ -37,8 +37,21 @@ case "${1:-}" in
       cat gpurun_out/two_gpu_$i.json | cut -c1-300
     done
     ;;
+  revalidate)
+    # after a variant has been adopted as the default build: the full evidence set again
+    #   gpurun --timeout 1500 -- 'bash tools/first_gpu_calls.sh revalidate'
+    timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tee gpurun_out/gpu_tests.log | tail -3
+    timeout 300 python tools/sanitize.py > gpurun_out/sanitizer.txt 2>&1; tail -5 gpurun_out/sanitizer.txt
+    timeout 200 python bench.py --steps 400 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench.json; cut -c1-400 gpurun_out/bench.json
+    timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+        python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -c 1 -o gpurun_out/fused_full \
+        python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+    timeout 200 python tools/phase_profile.py 4096 512 512 > gpurun_out/phase_cycles.txt 2>&1; tail -15 gpurun_out/phase_cycles.txt
+    python tools/sass_identity.py --write epro-pnp_b200/lib/libepropnp_b200.so > /dev/null && cp profiles/validated_sass.json gpurun_out/
+    ;;
   *)
-    echo "usage: $0 variants | experimental | two_gpu" >&2
+    echo "usage: $0 variants | experimental | two_gpu | revalidate" >&2
     exit 2
     ;;
 esac
