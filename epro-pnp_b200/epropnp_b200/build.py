@@ -17,8 +17,13 @@ INCLUDE = os.path.join(REPO_ROOT, "include")
 LIB_PATH = os.path.join(LIB_DIR, "libepropnp_b200.so")
 EMUL_PATH = os.path.join(LIB_DIR, "libhost_emul.so")
 
+# Build options of the SHIPPED library (see EXPERIMENTS below).  Empty: the round-1 kernels as validated on hardware.
+# Adopting a measured variant = listing its options here and rewriting profiles/validated_sass.json in the same commit
+# (tools/first_gpu_calls.sh revalidate); the CPU emulation and the profiling build follow this list.
+DEFAULT_OPTIONS = []
+
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE]
+              "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE] + DEFAULT_OPTIONS
 
 
 # Build-option experiments of the kernels: off in the shipped build; tools/variants.py builds

@@ -22,7 +22,7 @@ _handles = {}
 
 
 def build_emulated(flags=()):
-    flags = tuple(flags)
+    flags = tuple(build.DEFAULT_OPTIONS) + tuple(f for f in flags if f not in build.DEFAULT_OPTIONS)
     tag = hashlib.sha1(" ".join(flags).encode()).hexdigest()[:8] if flags else "default"
     out = os.path.join(build.LIB_DIR, f"libepropnp_simt_{tag}.so")
     src = os.path.join(build.CSRC, "pnp_kernels.cu")
