@@ -48,6 +48,12 @@ EXPERIMENTS = {
     "six_ctas": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
                  "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW", "-DEPNP_CTAS_PER_SM=6"],
     "no_lw": ["-DEPNP_NO_LW"],
+    # the same residency with the shipped sweep arithmetic (18 packed FP ops + 4 MUFU per pair-sample instead of 20 + 2):
+    # separates "more resident CTAs" from "different sweep formula" in the A/B
+    "five_ctas_plain_sweep": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE",
+                              "-DEPNP_ALIAS_STAGE", "-DEPNP_CTAS_PER_SM=5"],
+    "six_ctas_plain_sweep": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE",
+                             "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW", "-DEPNP_CTAS_PER_SM=6"],
     "four_ctas_same_code": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
                             "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE"],
     "everything": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",

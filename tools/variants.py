@@ -122,7 +122,8 @@ def cmd_run(args):
     # default selection: every option on its own + everything together (the unions in between are left to the caller)
     # default selection: the candidate combinations first (if the call runs out of time the single options are the ones
     # lost), then every option on its own for attribution
-    names = args.names or ["default", "everything", "four_ctas_same_code", "five_ctas", "six_ctas", "lm_packed",
+    names = args.names or ["default", "everything", "four_ctas_same_code", "five_ctas", "six_ctas", "five_ctas_plain_sweep",
+                           "six_ctas_plain_sweep", "lm_packed",
                            "lm_norefine", "lm_cost_first", "fast_blocksum", "sweep_rsq", "sweep_noclamp", "sweep_split"]
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     out_path = os.path.join(REPO, "gpurun_out", "variants.jsonl")
