@@ -48,6 +48,9 @@ EXPERIMENTS = {
     "six_ctas": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
                  "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW", "-DEPNP_CTAS_PER_SM=6"],
     "no_lw": ["-DEPNP_NO_LW"],
+    "sweep_huber_m": ["-DEPNP_SWEEP_HUBER_M"],            # shipped sweep arithmetic with the select-free Huber only
+    "six_ctas_huber_m": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE",
+                         "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW", "-DEPNP_SWEEP_HUBER_M", "-DEPNP_CTAS_PER_SM=6"],
     # the same residency with the shipped sweep arithmetic (18 packed FP ops + 4 MUFU per pair-sample instead of 20 + 2):
     # separates "more resident CTAs" from "different sweep formula" in the A/B
     "five_ctas_plain_sweep": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE",

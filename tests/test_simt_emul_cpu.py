@@ -61,7 +61,7 @@ from epropnp_b200.build import EXPERIMENTS  # noqa: E402
 # The combinations that are candidates for the default build get the full matrix; every single option additionally
 # runs alone on a reduced set (fused goldens incl. 4-DoF, the odd-sample-count corner, the smallest point sets).
 CANDIDATE_VARIANTS = ["everything", "five_ctas", "six_ctas", "six_ctas_plain_sweep"]
-SINGLE_OPTIONS = ["lm_packed", "lm_cost_first", "fast_blocksum", "amis_lse", "alias_stage", "no_lw", "sweep_rsq",
+SINGLE_OPTIONS = ["lm_packed", "lm_cost_first", "fast_blocksum", "amis_lse", "alias_stage", "no_lw", "sweep_huber_m", "sweep_rsq",
                   "sweep_noclamp", "sweep_split"]
 EMULATED_VARIANTS = SINGLE_OPTIONS + CANDIDATE_VARIANTS
 

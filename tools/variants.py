@@ -6,6 +6,7 @@ preprocessor options (they compile to nothing when off, so the default SASS is b
 shown them parity-green and faster:
 
     EPNP_LM_PACKED       LM normal equations with the Jacobian's u / v rows in the two lanes of fp32x2 registers
+    EPNP_SWEEP_HUBER_M   the shipped sweep (reciprocal + square root) with the select-free Huber only: 17 packed FP ops
     EPNP_SWEEP_RSQ       AMIS cost sweep with one MUFU.RSQ per point (no reciprocal), select-free Huber
     EPNP_SWEEP_NOCLAMP   ... + clamp-free loop when the pose keeps the whole object in front of z_min
     EPNP_SWEEP_SPLIT     ... + two samples per thread over half of the points each
@@ -123,7 +124,7 @@ def cmd_run(args):
     # default selection: the candidate combinations first (if the call runs out of time the single options are the ones
     # lost), then every option on its own for attribution
     names = args.names or ["default", "everything", "four_ctas_same_code", "five_ctas", "six_ctas", "five_ctas_plain_sweep",
-                           "six_ctas_plain_sweep", "lm_packed",
+                           "six_ctas_plain_sweep", "six_ctas_huber_m", "sweep_huber_m", "lm_packed",
                            "lm_norefine", "lm_cost_first", "fast_blocksum", "sweep_rsq", "sweep_noclamp", "sweep_split"]
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     out_path = os.path.join(REPO, "gpurun_out", "variants.jsonl")
