@@ -263,6 +263,29 @@ __global__ void __launch_bounds__(128, 4) sweep_kernel(const float* Aall /*6 x 1
     if (mode == 0 && warp == 0) tmem_dealloc(taddr, 256);
 }
 
+// ---------------------------------------------------------------------------------------------- probe 3
+// Legacy warp-level path: mma.sync.m16n8k8 TF32 (operands and accumulators in registers, no TMEM, no descriptors).
+// Its rate decides whether the projection could move to the tensor pipe WITHOUT the shared-memory / TMEM cost of the
+// tcgen05 plan: 12 such MMAs per warp give the 3x4 projection (3xTF32 split) of 32 samples x 8 points.
+__global__ void __launch_bounds__(128) mma_sync_rate_kernel(float* out, int iters) {
+    uint32_t a[4] = {0x3f800000u + threadIdx.x, 0x3f900000u, 0x3fa00000u, 0x3fb00000u}, b[2] = {0x3f000000u, 0x3f100000u};
+    float d[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)          // 8 independent accumulator tiles per warp: latency hidden
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                         "{%0, %1, %2, %3};"
+                         : "+f"(d[i][0]), "+f"(d[i][1]), "+f"(d[i][2]), "+f"(d[i][3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += d[i][0] + d[i][1] + d[i][2] + d[i][3];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 float tf32_trunc(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xFFFFE000u; std::memcpy(&x, &u, 4); return x; }
 
 }  // namespace
@@ -386,6 +409,26 @@ int main(int argc, char** argv) {
             if (d > worst || d != d) worst = d;
         }
         std::printf(", \"sweep_rel_diff_tc_vs_cuda\": %.3g, \"sweep_note\": \"both modes: 128 threads, %zu B smem per CTA, descriptor hypothesis %d\"", worst, smem, good_hyp);
+    }
+    {   // probe 3: mma.sync m16n8k8 TF32 rate, 4 warps per CTA, 4 CTAs per SM
+        const int blocks = 148 * 4, iters = 4096;
+        float* dout;
+        CK(cudaMalloc(&dout, (size_t)blocks * 128 * 4));
+        mma_sync_rate_kernel<<<blocks, 128>>>(dout, 64);
+        CK(cudaDeviceSynchronize());
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0));
+        mma_sync_rate_kernel<<<blocks, 128>>>(dout, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double mmas = (double)blocks * 4 * 8 * iters;               // warp-level instructions
+        const double macs = mmas * 16 * 8 * 8;
+        std::printf(", \"mma_sync_m16n8k8_tf32\": {\"ms\": %.4f, \"tflops\": %.2f, \"warp_mma_per_us_per_sm\": %.1f, "
+                    "\"note\": \"needs >= ~256 MAC/clk/SM-subpartition to carry the projection (12 MMAs per 32 samples x 8 points)\"}",
+                    ms, 2.0 * macs / (ms * 1e-3) / 1e12, mmas / (ms * 1e3) / 148.0);
     }
     std::printf("}\n");
     return 0;
