@@ -286,6 +286,20 @@ __global__ void __launch_bounds__(128) mma_sync_rate_kernel(float* out, int iter
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Fragment layout of mma.sync.m16n8k8 (tf32) as I read the PTX ISA -- g = lane / 4, t = lane % 4:
+//   A (16x8): a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)     B (8x8): b0 (k = t, n = g)  b1 (k = t+4, n = g)
+//   D (16x8): d0 (g, 2t)  d1 (g, 2t+1)  d2 (g+8, 2t)  d3 (g+8, 2t+1)
+__global__ void mma_sync_layout_kernel(const float* A /*16x8*/, const float* B /*8(k)x8(n)*/, float* D /*16x8*/) {
+    const int lane = threadIdx.x, g = lane >> 2, t = lane & 3;
+    const uint32_t a0 = __float_as_uint(A[g * 8 + t]), a1 = __float_as_uint(A[(g + 8) * 8 + t]);
+    const uint32_t a2 = __float_as_uint(A[g * 8 + t + 4]), a3 = __float_as_uint(A[(g + 8) * 8 + t + 4]);
+    const uint32_t b0 = __float_as_uint(B[t * 8 + g]), b1 = __float_as_uint(B[(t + 4) * 8 + g]);
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    D[g * 8 + 2 * t] = d0; D[g * 8 + 2 * t + 1] = d1; D[(g + 8) * 8 + 2 * t] = d2; D[(g + 8) * 8 + 2 * t + 1] = d3;
+}
+
 float tf32_trunc(float x) { uint32_t u; std::memcpy(&u, &x, 4); u &= 0xFFFFE000u; std::memcpy(&x, &u, 4); return x; }
 
 }  // namespace
@@ -409,6 +423,27 @@ int main(int argc, char** argv) {
             if (d > worst || d != d) worst = d;
         }
         std::printf(", \"sweep_rel_diff_tc_vs_cuda\": %.3g, \"sweep_note\": \"both modes: 128 threads, %zu B smem per CTA, descriptor hypothesis %d\"", worst, smem, good_hyp);
+    }
+    {   // probe 3a: do I have the mma.sync fragment layout right? (exact inputs, exact comparison)
+        std::vector<float> a(16 * 8), b(8 * 8), want(16 * 8), have(16 * 8);
+        for (auto& v : a) v = rnd();
+        for (auto& v : b) v = rnd();
+        for (int m = 0; m < 16; ++m)
+            for (int n = 0; n < 8; ++n) {
+                float acc = 0.f;
+                for (int k = 0; k < 8; ++k) acc += a[m * 8 + k] * b[k * 8 + n];
+                want[m * 8 + n] = acc;
+            }
+        float *da, *db, *dd;
+        CK(cudaMalloc(&da, a.size() * 4)); CK(cudaMalloc(&db, b.size() * 4)); CK(cudaMalloc(&dd, have.size() * 4));
+        CK(cudaMemcpy(da, a.data(), a.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+        mma_sync_layout_kernel<<<1, 32>>>(da, db, dd);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(have.data(), dd, have.size() * 4, cudaMemcpyDeviceToHost));
+        int bad = 0;
+        for (size_t i = 0; i < have.size(); ++i) bad += !(std::fabs(have[i] - want[i]) <= 1e-6f);
+        std::printf(", \"mma_sync_fragment_layout_mismatches\": %d", bad);
     }
     {   // probe 3: mma.sync m16n8k8 TF32 rate, 4 warps per CTA, 4 CTAs per SM
         const int blocks = 148 * 4, iters = 4096;
