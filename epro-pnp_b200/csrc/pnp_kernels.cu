@@ -43,6 +43,9 @@
 namespace {
 using namespace pnp;
 
+#if defined(EPNP_SWEEP_MMA) && !defined(EPNP_SWEEP_SPLIT)
+#define EPNP_SWEEP_SPLIT 1              // the tensor-pipe sweep reuses the draw-then-sweep control flow
+#endif
 #if (defined(EPNP_SWEEP_NOCLAMP) || defined(EPNP_SWEEP_SPLIT) || defined(EPNP_TF32X3_NUMERICS)) && !defined(EPNP_SWEEP_RSQ)
 #define EPNP_SWEEP_RSQ 1
 #endif
@@ -67,6 +70,14 @@ using namespace pnp;
 #define LW_E_STORE(m, e) lw[m] = (e)
 #define LW_W(m) (lw[m] * inv_sum)
 #define LW_W_STORE(m, w) lw[m] = (w)
+#endif
+
+#if defined(EPNP_SWEEP_MMA)
+#define EPNP_PTAB_PARAM , float* ptab
+#define EPNP_PTAB_ARG(x) , (x)
+#else
+#define EPNP_PTAB_PARAM
+#define EPNP_PTAB_ARG(x)
 #endif
 
 constexpr int NT = 128;                 // threads per CTA
@@ -877,6 +888,101 @@ __device__ void sweep_new_samples(const float* pts, int N, const float* smp, flo
 }
 #endif
 
+#if defined(EPNP_SWEEP_MMA)
+// experiment (off by default): the sweep's 3x4 projection on the tensor pipe through the legacy warp-level
+// mma.sync.m16n8k8 TF32 instruction (SASS HMMA.1688.F32.TF32), operands in registers -- no TMEM, no descriptors, no
+// extra point storage.  Error-compensated 3xTF32: D = [P_hi | P_lo] [X_hi ; X_hi] + [P_hi | 0] [X_lo ; 0].
+//   work item = (tile of 16 samples, half of the points); a warp takes items warp, warp + 4, ...
+//   A fragments: P[s][4 r + t] of samples s0 = 16 ti + g and s0 + 8 from the table `ptab` (S x 12, built here)
+//   B fragments: coordinate t of point 8 tl + g, one LDS.32 from the pair records, split with two ALU ops
+//   D fragments: (s0 | s0 + 8) x points (2t, 2t + 1) -- the register pairs the packed Huber tail consumes
+// Returns false (nothing done) when the shape does not fit; the caller then runs the CUDA-core path.
+__device__ __forceinline__ float tf32_hi_bits(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[4], float b0, float b1) {
+#if defined(EPNP_SIMT_EMUL)
+    simt::mma_m16n8k8_tf32(d, a, b0, b1);
+#else
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])),
+                   "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+#endif
+}
+
+template <int DOF, bool BOUNDED>
+__device__ __forceinline__ void sweep_mma_items(const float* pts, int N, const float* ptab, float* cst, float* lw,
+                                                int m0, int S, const Cam& cam, float delta);
+
+template <int DOF>
+__device__ bool sweep_new_samples_mma(const float* pts, int N, const float* smp, float* ptab, float* cst, float* lw,
+                                      int m0, int S, const Cam& cam, float delta) {
+    if (ptab == nullptr || (S & 15) != 0) return false;
+    constexpr int PD = Dim<DOF>::POSE;
+    for (int s = threadIdx.x; s < S; s += NT) {          // the new samples' K[R|t], one row of the table each
+        float pose[PD], R[9], P[12];
+#pragma unroll
+        for (int c = 0; c < PD; ++c) pose[c] = smp[(m0 + s) * PD + c];
+        pose_to_rot<DOF>(pose, R);
+        make_proj(cam.k, R, pose, P);
+#pragma unroll
+        for (int c = 0; c < 12; ++c) ptab[s * 12 + c] = P[c];
+    }
+    __syncthreads();
+    if (cam.bounded) sweep_mma_items<DOF, true>(pts, N, ptab, cst, lw, m0, S, cam, delta);
+    else sweep_mma_items<DOF, false>(pts, N, ptab, cst, lw, m0, S, cam, delta);
+    return true;
+}
+
+template <int DOF, bool BOUNDED>
+__device__ __forceinline__ void sweep_mma_items(const float* pts, int N, const float* ptab, float* cst, float* lw,
+                                                int m0, int S, const Cam& cam, float delta) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int npair = (N + 1) >> 1, npts = 2 * npair;    // even-padded point count (the pad carries zero weights)
+    const int ntile = (npts + 7) >> 3, tmid = (ntile + 1) >> 1, T = S >> 4;
+    for (int item = warp; item < 2 * T; item += NW) {
+        const int ti = item >> 1, h = item & 1;
+        const int s0 = ti * 16 + g, s1 = s0 + 8;
+        float ah[3][2], al[3][2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float p0 = ptab[s0 * 12 + 4 * r + t], p1 = ptab[s1 * 12 + 4 * r + t];
+            ah[r][0] = tf32_hi_bits(p0); al[r][0] = p0 - ah[r][0];
+            ah[r][1] = tf32_hi_bits(p1); al[r][1] = p1 - ah[r][1];
+        }
+        V2 acc0 = v2splat(0.f), acc1 = v2splat(0.f);
+        const int t0 = h ? tmid : 0, t1 = h ? ntile : tmid;
+        for (int tl = t0; tl < t1; ++tl) {
+            const int pt = min(tl * 8 + g, npts - 1);
+            const float c = (t < 3) ? pts[(pt >> 1) * 16 + 2 * t + (pt & 1)] : 1.0f;
+            const float bh = tf32_hi_bits(c), bl = c - bh;
+            float d[3][4];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.f;
+                const float a1[4] = {ah[r][0], ah[r][1], al[r][0], al[r][1]};
+                const float a2[4] = {ah[r][0], ah[r][1], 0.f, 0.f};
+                mma_tf32_16x8x8(d[r], a1, bh, bh);
+                mma_tf32_16x8x8(d[r], a2, bl, 0.f);
+            }
+            const int pair = tl * 4 + t;
+            const bool valid = pair < npair;
+            const float* rec = pts + min(pair, npair - 1) * 16;
+            const V2 nu = v2(rec[6], rec[7]), nv = v2(rec[8], rec[9]);
+            const V2 wu = valid ? v2(rec[10], rec[11]) : v2splat(0.f), wv = valid ? v2(rec[12], rec[13]) : v2splat(0.f);
+            acc0 = pair_cost_tail<BOUNDED>(v2(d[0][0], d[0][1]), v2(d[1][0], d[1][1]), v2(d[2][0], d[2][1]), cam, delta, nu, nv, wu, wv, acc0, SweepRsqrt());
+            acc1 = pair_cost_tail<BOUNDED>(v2(d[0][2], d[0][3]), v2(d[1][2], d[1][3]), v2(d[2][2], d[2][3]), cam, delta, nu, nv, wu, wv, acc1, SweepRsqrt());
+        }
+        float c0 = acc0.x + acc0.y, c1 = acc1.x + acc1.y;
+        c0 += __shfl_xor_sync(0xffffffffu, c0, 1); c0 += __shfl_xor_sync(0xffffffffu, c0, 2);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, 1); c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
+        if (t == 0) {
+            float* dst = h ? lw : cst;
+            dst[m0 + s0] = c0; dst[m0 + s1] = c1;
+        }
+    }
+}
+#endif
+
 #if defined(EPNP_AMIS_LSE)
 // experiment (off by default): the mixture density of a sample is kept as ONE running log-sum-exp over the proposals
 // seen so far instead of one log-density per (proposal, sample) -- (I - 1) * M floats less shared memory.
@@ -900,7 +1006,7 @@ __device__ __forceinline__ float log_add_exp(float a, float b) {
 // pose_opt[7] / cov[36] (shared or registers of thread 0 -- passed as shared pointers).
 __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, float* smp, float* cst,
                             float* logp, float* lw, const Cam& cam, float delta, int obj,
-                            const float* pose_opt, const float* cov) {
+                            const float* pose_opt, const float* cov EPNP_PTAB_PARAM) {
     const Params& p = a.p;
     const int tid = threadIdx.x;
     const int M = p.mc_samples, I = p.mc_iter, S = M / I;
@@ -959,10 +1065,14 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
 #if defined(EPNP_SWEEP_SPLIT)
         __syncthreads();
 #if defined(EPNP_NO_LW)
-        sweep_new_samples<6>(pts4, a.N, smp, cst, a.logw + (size_t)obj * M, i * S, S, cam, delta, radius);
+        float* const half1 = a.logw + (size_t)obj * M;
 #else
-        sweep_new_samples<6>(pts4, a.N, smp, cst, lw, i * S, S, cam, delta, radius);
+        float* const half1 = lw;
 #endif
+#if defined(EPNP_SWEEP_MMA)
+        if (!sweep_new_samples_mma<6>(pts4, a.N, smp, ptab, cst, half1, i * S, S, cam, delta))
+#endif
+        sweep_new_samples<6>(pts4, a.N, smp, cst, half1, i * S, S, cam, delta, radius);
 #endif
         PH_MARK(a, PH_DRAW_SWEEP);
         // ---- the new proposal on all earlier samples
@@ -1148,7 +1258,7 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
 // is no base noise to replay).
 __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, float* smp, float* cst,
                             float* logp, float* lw, const Cam& cam, float delta, int obj,
-                            const float* pose_opt, const float* cov) {
+                            const float* pose_opt, const float* cov EPNP_PTAB_PARAM) {
     const Params& p = a.p;
     const int tid = threadIdx.x;
     const int M = p.mc_samples, I = p.mc_iter, S = M / I;
@@ -1203,10 +1313,14 @@ __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, 
 #if defined(EPNP_SWEEP_SPLIT)
         __syncthreads();
 #if defined(EPNP_NO_LW)
-        sweep_new_samples<4>(pts4, a.N, smp, cst, a.logw + (size_t)obj * M, i * S, S, cam, delta, radius);
+        float* const half1 = a.logw + (size_t)obj * M;
 #else
-        sweep_new_samples<4>(pts4, a.N, smp, cst, lw, i * S, S, cam, delta, radius);
+        float* const half1 = lw;
 #endif
+#if defined(EPNP_SWEEP_MMA)
+        if (!sweep_new_samples_mma<4>(pts4, a.N, smp, ptab, cst, half1, i * S, S, cam, delta))
+#endif
+        sweep_new_samples<4>(pts4, a.N, smp, cst, half1, i * S, S, cam, delta, radius);
 #endif
         PH_MARK(a, PH_DRAW_SWEEP);
 #if defined(EPNP_AMIS_LSE)
@@ -1333,12 +1447,20 @@ __global__ void __launch_bounds__(NT, EPNP_CTAS_PER_SM) solve_kernel(const KArgs
                 if (threadIdx.x < DOF * DOF) sh.cov[threadIdx.x] = __ldg(a.pose_cov_in + (size_t)obj * DOF * DOF + threadIdx.x);
                 __syncthreads();
             }
+#if defined(EPNP_SWEEP_MMA)
+            // table of the current iteration's K[R|t] (12 floats per new sample): the staging ring, which is idle once
+            // the object is packed -- unless this CTA prefetches its next object (persistent grid) or the ring is
+            // aliased into the sample buffer, in which case the tensor-pipe sweep is not used
+            float* ptab = nullptr;
+            if (gridDim.x >= (unsigned)a.B && pl.stage != pl.smp && 12 * (a.p.mc_samples / a.p.mc_iter) <= 2 * STAGE_FLOATS)
+                ptab = dyn + pl.stage;
+#endif
             if constexpr (DOF == 6)
                 amis_phase6(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.lw, cam, delta, obj,
-                            sh.lm.pose, sh.cov);
+                            sh.lm.pose, sh.cov EPNP_PTAB_ARG(ptab));
             else
                 amis_phase4(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.lw, cam, delta, obj,
-                            sh.lm.pose, sh.cov);
+                            sh.lm.pose, sh.cov EPNP_PTAB_ARG(ptab));
         }
     }
 }

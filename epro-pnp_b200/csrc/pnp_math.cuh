@@ -194,23 +194,9 @@ PNP_HD float tf32x3_row(const V2* P2, int r, float X, float Y, float Z) {
 }
 #endif
 
-// CLAMPZ = false: the caller has shown zh >= z_min for every point of the object under this pose
-// (pose_depth_margin below), so the clamp is the identity and its two scalar FMNMX are dropped.
+// The part of pair_cost_rsq after the projection: (xh, yh, zh) of two correspondences -> acc + their Huber costs.
 template <bool BOUNDED, bool CLAMPZ = true, class Rsqrt = ExactRsqrt>
-PNP_HD V2 pair_cost_rsq(const V2* P2, const Cam& c, float delta, V2 X, V2 Y, V2 Z, V2 nu, V2 nv, V2 wu, V2 wv,
-                        V2 acc, Rsqrt rsq) {
-#if defined(EPNP_TF32X3_NUMERICS)
-    // numerics study only (DESIGN.md 9.3): the projection as the tcgen05 plan would compute it -- operands split into
-    // TF32 hi + lo parts, products hi*hi + lo*hi + hi*lo accumulated in fp32 -- on the ordinary sweep's control flow,
-    // so the whole parity suite can be run on these numerics before any tensor-core code exists
-    V2 xh = v2(tf32x3_row(P2, 0, X.x, Y.x, Z.x), tf32x3_row(P2, 0, X.y, Y.y, Z.y));
-    V2 yh = v2(tf32x3_row(P2, 4, X.x, Y.x, Z.x), tf32x3_row(P2, 4, X.y, Y.y, Z.y));
-    const V2 zh = v2(tf32x3_row(P2, 8, X.x, Y.x, Z.x), tf32x3_row(P2, 8, X.y, Y.y, Z.y));
-#else
-    V2 xh = v2fma(P2[0], X, v2fma(P2[1], Y, v2fma(P2[2], Z, P2[3])));
-    V2 yh = v2fma(P2[4], X, v2fma(P2[5], Y, v2fma(P2[6], Z, P2[7])));
-    const V2 zh = v2fma(P2[8], X, v2fma(P2[9], Y, v2fma(P2[10], Z, P2[11])));
-#endif
+PNP_HD V2 pair_cost_tail(V2 xh, V2 yh, V2 zh, const Cam& c, float delta, V2 nu, V2 nv, V2 wu, V2 wv, V2 acc, Rsqrt rsq) {
     const V2 z = CLAMPZ ? v2(fmaxf(zh.x, c.z_min), fmaxf(zh.y, c.z_min)) : zh;
     if (BOUNDED) {
         const V2 lx = v2mul(v2splat(c.lbx), z), ux = v2mul(v2splat(c.ubx), z);
@@ -225,6 +211,26 @@ PNP_HD V2 pair_cost_rsq(const V2* P2, const Cam& c, float delta, V2 X, V2 Y, V2 
     const V2 s = v2mul(q, v2(rsq(qz.x), rsq(qz.y)));
     const V2 m = v2(fminf(s.x, delta), fminf(s.y, delta));
     return v2fma(m, v2fma(m, v2splat(-0.5f), s), acc);
+}
+
+// CLAMPZ = false: the caller has shown zh >= z_min for every point of the object under this pose
+// (pose_depth_margin below), so the clamp is the identity and its two scalar FMNMX are dropped.
+template <bool BOUNDED, bool CLAMPZ = true, class Rsqrt = ExactRsqrt>
+PNP_HD V2 pair_cost_rsq(const V2* P2, const Cam& c, float delta, V2 X, V2 Y, V2 Z, V2 nu, V2 nv, V2 wu, V2 wv,
+                        V2 acc, Rsqrt rsq) {
+#if defined(EPNP_TF32X3_NUMERICS)
+    // numerics study only (DESIGN.md 9.3): the projection as the tcgen05 plan would compute it -- operands split into
+    // TF32 hi + lo parts, products hi*hi + lo*hi + hi*lo accumulated in fp32 -- on the ordinary sweep's control flow,
+    // so the whole parity suite can be run on these numerics before any tensor-core code exists
+    const V2 xh = v2(tf32x3_row(P2, 0, X.x, Y.x, Z.x), tf32x3_row(P2, 0, X.y, Y.y, Z.y));
+    const V2 yh = v2(tf32x3_row(P2, 4, X.x, Y.x, Z.x), tf32x3_row(P2, 4, X.y, Y.y, Z.y));
+    const V2 zh = v2(tf32x3_row(P2, 8, X.x, Y.x, Z.x), tf32x3_row(P2, 8, X.y, Y.y, Z.y));
+#else
+    const V2 xh = v2fma(P2[0], X, v2fma(P2[1], Y, v2fma(P2[2], Z, P2[3])));
+    const V2 yh = v2fma(P2[4], X, v2fma(P2[5], Y, v2fma(P2[6], Z, P2[7])));
+    const V2 zh = v2fma(P2[8], X, v2fma(P2[9], Y, v2fma(P2[10], Z, P2[11])));
+#endif
+    return pair_cost_tail<BOUNDED, CLAMPZ>(xh, yh, zh, c, delta, nu, nv, wu, wv, acc, rsq);
 }
 
 // Lower bound of zh = P[8..10] . X + P[11] over every point with |X| <= radius (Cauchy-Schwarz), minus z_min,

@@ -48,6 +48,13 @@ EXPERIMENTS = {
     "six_ctas": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
                  "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW", "-DEPNP_CTAS_PER_SM=6"],
     "no_lw": ["-DEPNP_NO_LW"],
+    # the projection on the tensor pipe through the legacy mma.sync m16n8k8 TF32 instruction (3xTF32), 4 CTAs/SM
+    "sweep_mma": ["-DEPNP_SWEEP_MMA"],
+    "sweep_mma_all": ["-DEPNP_SWEEP_MMA", "-DEPNP_SWEEP_NOCLAMP", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST",
+                      "-DEPNP_FAST_BLOCKSUM"],
+    # ... at five CTAs per SM: 96 registers; the staging ring holds the K[R|t] table, so no aliasing -- 44.9 KB per CTA
+    "five_ctas_mma": ["-DEPNP_SWEEP_MMA", "-DEPNP_SWEEP_NOCLAMP", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST",
+                      "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_NO_LW", "-DEPNP_CTAS_PER_SM=5"],
     "sweep_huber_m": ["-DEPNP_SWEEP_HUBER_M"],            # shipped sweep arithmetic with the select-free Huber only
     "six_ctas_huber_m": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE",
                          "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW", "-DEPNP_SWEEP_HUBER_M", "-DEPNP_CTAS_PER_SM=6"],

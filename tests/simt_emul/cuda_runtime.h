@@ -218,6 +218,35 @@ inline int __all_sync(unsigned mask, int pred) {
     if (mask == kEmulActiveMask) return pred != 0;
     std::fprintf(stderr, "simt_emul: __all_sync with an explicit mask is not emulated\n"); std::abort();
 }
+inline uint32_t __float_as_uint(float x) { uint32_t u; std::memcpy(&u, &x, 4); return u; }
+inline float __uint_as_float(uint32_t u) { float x; std::memcpy(&x, &u, 4); return x; }
+
+namespace simt {
+// mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 as a warp collective (PTX ISA fragment layout, g = lane / 4,
+// t = lane % 4):  A a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  B b0 (k = t, n = g) b1 (k = t+4, n = g);
+// D d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1).  Inputs are truncated to TF32, accumulation is fp32.
+inline float tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+inline void mma_m16n8k8_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
+    static float xa[kMaxThreads][4], xb[kMaxThreads][2];
+    BlockState& s = state();
+    const int me = s.cur, base = me & ~31, lane = me & 31, g = lane >> 2, t = lane & 3;
+    for (int i = 0; i < 4; ++i) xa[me][i] = tf32(a[i]);
+    xb[me][0] = tf32(b0); xb[me][1] = tf32(b1);
+    syncwarp();
+    for (int i = 0; i < 4; ++i) {
+        const int row = g + ((i & 2) ? 8 : 0), col = 2 * t + (i & 1);
+        float acc = d[i];
+        for (int k = 0; k < 8; ++k) {
+            const float av = xa[base + (row & 7) * 4 + (k & 3)][(row >= 8 ? 1 : 0) + (k >= 4 ? 2 : 0)];
+            const float bv = xb[base + col * 4 + (k & 3)][k >= 4 ? 1 : 0];
+            acc = fmaf(av, bv, acc);
+        }
+        d[i] = acc;
+    }
+    syncwarp();
+}
+}  // namespace simt
+
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 inline float atomicAdd(float* p, float v) { const float o = *p; *p = o + v; return o; }

@@ -9,6 +9,7 @@ shown them parity-green and faster:
     EPNP_SWEEP_HUBER_M   the shipped sweep (reciprocal + square root) with the select-free Huber only: 17 packed FP ops
     EPNP_SWEEP_RSQ       AMIS cost sweep with one MUFU.RSQ per point (no reciprocal), select-free Huber
     EPNP_SWEEP_NOCLAMP   ... + clamp-free loop when the pose keeps the whole object in front of z_min
+    EPNP_SWEEP_MMA       ... the 3x4 projection on the tensor pipe (mma.sync m16n8k8 TF32, error-compensated 3xTF32)
     EPNP_SWEEP_SPLIT     ... + two samples per thread over half of the points each
     EPNP_LM_NOREFINE     LM step from the plain fp32 Cholesky solve (no fp64-residual refinement on the serial lane)
     EPNP_LM_COST_FIRST   LM accept / reject from a cost-only pass; normal equations only for accepted steps
@@ -123,7 +124,8 @@ def cmd_run(args):
     # default selection: every option on its own + everything together (the unions in between are left to the caller)
     # default selection: the candidate combinations first (if the call runs out of time the single options are the ones
     # lost), then every option on its own for attribution
-    names = args.names or ["default", "six_ctas_huber_m", "six_ctas_plain_sweep", "six_ctas", "five_ctas_plain_sweep", "five_ctas",
+    names = args.names or ["default", "six_ctas_huber_m", "six_ctas_plain_sweep", "six_ctas", "five_ctas_mma", "sweep_mma_all",
+                           "five_ctas_plain_sweep", "five_ctas",
                            "everything", "four_ctas_same_code", "lm_cost_first", "lm_norefine", "sweep_huber_m", "sweep_rsq",
                            "sweep_split", "sweep_noclamp", "fast_blocksum", "lm_packed"]
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
