@@ -60,9 +60,9 @@ from epropnp_b200.build import EXPERIMENTS  # noqa: E402
 
 # The combinations that are candidates for the default build get the full matrix; every single option additionally
 # runs alone on a reduced set (fused goldens incl. 4-DoF, the odd-sample-count corner, the smallest point sets).
-CANDIDATE_VARIANTS = ["everything", "five_ctas", "six_ctas", "six_ctas_plain_sweep", "sweep_mma_all", "five_ctas_mma"]
+CANDIDATE_VARIANTS = ["everything", "six_ctas", "six_ctas_plain_sweep", "five_ctas_mma"]
 SINGLE_OPTIONS = ["lm_packed", "lm_cost_first", "fast_blocksum", "amis_lse", "alias_stage", "no_lw", "sweep_huber_m", "sweep_rsq",
-                  "sweep_noclamp", "sweep_split", "sweep_mma"]
+                  "sweep_noclamp", "sweep_split", "sweep_mma", "sweep_mma_all", "five_ctas"]
 EMULATED_VARIANTS = SINGLE_OPTIONS + CANDIDATE_VARIANTS
 
 
@@ -161,7 +161,7 @@ def _all_outputs(dev, dof, odd_points):
     return [t.clone() for t in res if t is not None]
 
 
-@pytest.mark.parametrize("variant", ["default", "sweep_split", "everything", "five_ctas", "six_ctas", "sweep_mma_all"])
+@pytest.mark.parametrize("variant", ["default", "sweep_split", "six_ctas", "five_ctas_mma"])
 @pytest.mark.parametrize("dof,odd_points", [(6, False), (6, True), (4, True)])
 def test_results_do_not_depend_on_thread_schedule(monkeypatch, variant, dof, odd_points):
     flags = EXPERIMENTS.get(variant, ())
@@ -255,7 +255,7 @@ def _small_big(flags):
     return d
 
 
-@pytest.fixture(params=["default", "everything", "five_ctas", "six_ctas", "sweep_mma_all"])
+@pytest.fixture(params=["default", "six_ctas", "five_ctas_mma"])
 def big(request, monkeypatch):
     flags = tuple(EXPERIMENTS.get(request.param, ()))
     simt_native.install(monkeypatch, flags)
