@@ -179,24 +179,33 @@ def test_results_do_not_depend_on_thread_schedule(monkeypatch, variant, dof, odd
         lib.simt_set_schedule(0, 1)
 
 
-def test_persistent_grid_matches_one_object_per_cta(cuda_device, monkeypatch):
+@pytest.mark.parametrize("variant", ["default", "six_ctas", "five_ctas_mma"])
+def test_persistent_grid_matches_one_object_per_cta(monkeypatch, variant):
     """EPNP_MAX_OBJECTS_PER_CTA=0: CTAs stride over several objects and the next object's chunks are prefetched while
     the current one is solved (staging-ring slot / parity bookkeeping across objects).  Same results, bit for bit."""
     from epropnp_b200 import native
     from epropnp_b200.synth import make_problem
+    simt_native.install(monkeypatch, EXPERIMENTS.get(variant, ()))
     monkeypatch.setenv("SIMT_EMUL_SMS", "2")                  # an emulated device with 2 SMs x 4 resident CTAs
     B, N = 2 * 4 * 3 + 5, 132                                 # 3-4 objects per CTA, two TMA chunks per object
     pc = make_problem(B, N, seed=5)
     prob = native.Problem(pc["x3d"], pc["x2d"], pc["w2d"], pc["cam_mats"], None, None,
                           native.adaptive_delta(pc["x2d"], pc["w2d"], 0.5))
-    p = native.default_params(6, lm_iter=2, mc_samples=16, mc_iter=2)
+    p = native.default_params(6, lm_iter=2, mc_samples=32, mc_iter=2)     # 16 samples per iteration: one MMA sample tile
     monkeypatch.delenv("EPNP_MAX_OBJECTS_PER_CTA", raising=False)
     ref = native.lm_amis_fused(prob, pc["pose_init"], p, seed=9, want_cost=True)
     for cap in ("0", "2"):
         monkeypatch.setenv("EPNP_MAX_OBJECTS_PER_CTA", cap)
         out = native.lm_amis_fused(prob, pc["pose_init"], p, seed=9, want_cost=True)
         for k in ("pose_opt", "cost", "pose_samples", "logw"):
-            assert torch.equal(out[k], ref[k]), (cap, k)
+            if variant == "five_ctas_mma" and k in ("pose_samples", "logw"):
+                # a prefetching CTA has no idle staging ring for the K[R|t] table and runs the CUDA-core sweep:
+                # same samples of the first iteration, costs equal up to the 3xTF32 rounding
+                S = p.mc_samples // p.mc_iter
+                assert torch.equal(out["pose_samples"][:, :S], ref["pose_samples"][:, :S])
+                assert (out["logw"][:, :S] - ref["logw"][:, :S]).abs().max() < 1e-3 * ref["logw"][:, :S].abs().max()
+            else:
+                assert torch.equal(out[k], ref[k]), (variant, cap, k)
 
 
 @pytest.mark.parametrize("n_chunks,bounded", [(1, False), (3, True), (64, False)])
