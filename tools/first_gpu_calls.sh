@@ -13,6 +13,10 @@ case "${1:-}" in
     # A/B of the kernel build options: per variant the GPU parity + edge tests, then one bench line
     python tools/variants.py build > gpurun_out/variants_build.log 2>&1
     timeout 1500 python tools/variants.py run 2>&1 | tee gpurun_out/variants_run.log | tail -20
+    # where a CTA's time goes in the shipped build and in the two leading candidates
+    for v in "" six_ctas_huber_m five_ctas_mma; do
+      timeout 120 python tools/phase_profile.py 4096 512 512 $v > gpurun_out/phase_cycles_${v:-shipped}.txt 2>&1
+    done
     ;;
   experimental)
     # the two opt-in kernels, their timings, the copy ceiling of the box, the e2e chunk sweep, the tcgen05 probe
