@@ -235,6 +235,9 @@ __host__ __device__ inline SmemPlan plan_smem(int N, int M, int I, bool amis, bo
 __device__ __forceinline__ void store_point(float* pts, int n, float X, float Y, float Z, float u, float v, float wu, float wv) {
     float* p = pts + (n >> 1) * 16 + (n & 1);
     p[0] = X; p[2] = Y; p[4] = Z; p[6] = -u; p[8] = -v; p[10] = wu; p[12] = wv;
+#if defined(EPNP_SWEEP_MMA)
+    p[14] = 1.0f;           // the homogeneous coordinate, so that a B fragment is one load for every lane
+#endif
 }
 // odd N: the second half of the last pair is a zero-weight copy of the last point (contributes exactly 0);
 // written by the SAME thread that stores point N-1, so no other thread's data is read
@@ -891,7 +894,7 @@ __device__ void sweep_new_samples(const float* pts, int N, const float* smp, flo
 #if defined(EPNP_SWEEP_MMA)
 // experiment (off by default): the sweep's 3x4 projection on the tensor pipe through the legacy warp-level
 // mma.sync.m16n8k8 TF32 instruction (SASS HMMA.1688.F32.TF32), operands in registers -- no TMEM, no descriptors, no
-// extra point storage.  Error-compensated 3xTF32: D = [P_hi | P_lo] [X_hi ; X_hi] + [P_hi | 0] [X_lo ; 0].
+// extra point storage.  Error-compensated 3xTF32: D = [P_hi | P_lo] [X_hi ; X_hi] + [P_hi | P_lo] [X_lo ; 0].
 //   work item = (tile of 16 samples, half of the points); a warp takes items warp, warp + 4, ...
 //   A fragments: P[s][4 r + t] of samples s0 = 16 ti + g and s0 + 8 from the table `ptab` (S x 12, built here)
 //   B fragments: coordinate t of point 8 tl + g, one LDS.32 from the pair records, split with two ALU ops
@@ -910,48 +913,135 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[
 }
 
 template <int DOF, bool BOUNDED>
-__device__ __forceinline__ void sweep_mma_items(const float* pts, int N, const float* ptab, float* cst, float* lw,
-                                                int m0, int S, const Cam& cam, float delta);
+__device__ __forceinline__ void sweep_mma_items(const float* pts, int N, const float* smp, const float* ptab, float* cst,
+                                                float* lw, int m0, int S, const Cam& cam, float delta, float radius);
 
 template <int DOF>
 __device__ bool sweep_new_samples_mma(const float* pts, int N, const float* smp, float* ptab, float* cst, float* lw,
-                                      int m0, int S, const Cam& cam, float delta) {
-    if (ptab == nullptr || (S & 15) != 0) return false;
+                                      int m0, int S, const Cam& cam, float delta, float radius) {
+    if ((S & 15) != 0) return false;
     constexpr int PD = Dim<DOF>::POSE;
-    for (int s = threadIdx.x; s < S; s += NT) {          // the new samples' K[R|t], one row of the table each
-        float pose[PD], R[9], P[12];
+    if (ptab != nullptr) {                               // the new samples' K[R|t], one row of the table each
+        for (int s = threadIdx.x; s < S; s += NT) {
+            float pose[PD], R[9], P[12];
 #pragma unroll
-        for (int c = 0; c < PD; ++c) pose[c] = smp[(m0 + s) * PD + c];
-        pose_to_rot<DOF>(pose, R);
-        make_proj(cam.k, R, pose, P);
+            for (int c = 0; c < PD; ++c) pose[c] = smp[(m0 + s) * PD + c];
+            pose_to_rot<DOF>(pose, R);
+            make_proj(cam.k, R, pose, P);
 #pragma unroll
-        for (int c = 0; c < 12; ++c) ptab[s * 12 + c] = P[c];
-    }
-    __syncthreads();
-    if (cam.bounded) sweep_mma_items<DOF, true>(pts, N, ptab, cst, lw, m0, S, cam, delta);
-    else sweep_mma_items<DOF, false>(pts, N, ptab, cst, lw, m0, S, cam, delta);
+            for (int c = 0; c < 12; ++c) ptab[s * 12 + c] = P[c];
+        }
+        __syncthreads();
+    }                                                    // no table (no idle shared memory): columns computed per item
+    if (cam.bounded) sweep_mma_items<DOF, true>(pts, N, smp, ptab, cst, lw, m0, S, cam, delta, radius);
+    else sweep_mma_items<DOF, false>(pts, N, smp, ptab, cst, lw, m0, S, cam, delta, radius);
     return true;
 }
 
+// Column t of K [R | t] of one sample (what a lane's A fragments hold), straight from the pose.
+template <int DOF>
+__device__ __forceinline__ void proj_column(const float* pose, const float* K, int t, float (&col)[3]) {
+    float R[9];
+    pose_to_rot<DOF>(pose, R);
+    const float v0 = t == 0 ? R[0] : (t == 1 ? R[1] : (t == 2 ? R[2] : pose[0]));
+    const float v1 = t == 0 ? R[3] : (t == 1 ? R[4] : (t == 2 ? R[5] : pose[1]));
+    const float v2 = t == 0 ? R[6] : (t == 1 ? R[7] : (t == 2 ? R[8] : pose[2]));
+#pragma unroll
+    for (int r = 0; r < 3; ++r) col[r] = K[r * 3 + 0] * v0 + K[r * 3 + 1] * v1 + K[r * 3 + 2] * v2;
+}
+
 template <int DOF, bool BOUNDED>
-__device__ __forceinline__ void sweep_mma_items(const float* pts, int N, const float* ptab, float* cst, float* lw,
-                                                int m0, int S, const Cam& cam, float delta) {
+__device__ __forceinline__ void sweep_mma_items(const float* pts, int N, const float* smp, const float* ptab, float* cst,
+                                                float* lw, int m0, int S, const Cam& cam, float delta, float radius) {
+    constexpr int PD = Dim<DOF>::POSE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int npair = (N + 1) >> 1, npts = 2 * npair;    // even-padded point count (the pad carries zero weights)
     const int ntile = (npts + 7) >> 3, tmid = (ntile + 1) >> 1, T = S >> 4;
     for (int item = warp; item < 2 * T; item += NW) {
         const int ti = item >> 1, h = item & 1;
         const int s0 = ti * 16 + g, s1 = s0 + 8;
-        float ah[3][2], al[3][2];
+        float ah[3][2], al[3][2], c0v[3], c1v[3];
+        if (ptab != nullptr) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { c0v[r] = ptab[s0 * 12 + 4 * r + t]; c1v[r] = ptab[s1 * 12 + 4 * r + t]; }
+        } else {
+            float pose[PD];
+#pragma unroll
+            for (int c = 0; c < PD; ++c) pose[c] = smp[(m0 + s0) * PD + c];
+            proj_column<DOF>(pose, cam.k, t, c0v);
+#pragma unroll
+            for (int c = 0; c < PD; ++c) pose[c] = smp[(m0 + s1) * PD + c];
+            proj_column<DOF>(pose, cam.k, t, c1v);
+        }
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const float p0 = ptab[s0 * 12 + 4 * r + t], p1 = ptab[s1 * 12 + 4 * r + t];
-            ah[r][0] = tf32_hi_bits(p0); al[r][0] = p0 - ah[r][0];
-            ah[r][1] = tf32_hi_bits(p1); al[r][1] = p1 - ah[r][1];
+            ah[r][0] = tf32_hi_bits(c0v[r]); al[r][0] = c0v[r] - ah[r][0];
+            ah[r][1] = tf32_hi_bits(c1v[r]); al[r][1] = c1v[r] - ah[r][1];
         }
+        // ONE A quad per projection row, [P_hi | P_lo]: the second MMA multiplies it by [X_lo ; 0], so the unwanted
+        // P_lo X_lo term drops out without a second set of fragments
+        float a1[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { a1[r][0] = ah[r][0]; a1[r][1] = ah[r][1]; a1[r][2] = al[r][0]; a1[r][3] = al[r][1]; }
         V2 acc0 = v2splat(0.f), acc1 = v2splat(0.f);
         const int t0 = h ? tmid : 0, t1 = h ? ntile : tmid;
-        for (int tl = t0; tl < t1; ++tl) {
+        const int full1 = min(t1, npts >> 3);            // tiles [t0, full1) hold 8 real points each
+        bool free_z = false;
+#if defined(EPNP_SWEEP_NOCLAMP)
+        if (radius >= 0.f) {
+            // pose_depth_margin of the lane's two samples from the third projection row, whose four entries sit in
+            // the four lanes of the group: |P[8..10]| and P[11] by two exchanges
+            float q0 = (t < 3) ? c0v[2] * c0v[2] : 0.f, q1 = (t < 3) ? c1v[2] * c1v[2] : 0.f;
+            q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+            q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+            const float tz0 = __shfl_sync(0xffffffffu, c0v[2], (lane & ~3) | 3), tz1 = __shfl_sync(0xffffffffu, c1v[2], (lane & ~3) | 3);
+            const float r0 = sqrtf(q0) * radius, r1 = sqrtf(q1) * radius;
+            const float m0z = (tz0 - r0) - cam.z_min - 1e-5f * (fabsf(tz0) + r0 + cam.z_min);
+            const float m1z = (tz1 - r1) - cam.z_min - 1e-5f * (fabsf(tz1) + r1 + cam.z_min);
+            free_z = __all_sync(0xffffffffu, fminf(m0z, m1z) >= 0.f);
+        }
+#endif
+        // lane-private cursors: coordinate t (pad slot 14 holds the homogeneous 1) of point 8 tl + g, record of pair 4 tl + t
+        const float* bp = pts + (g >> 1) * 16 + (t < 3 ? 2 * t : 14) + (g & 1) + t0 * 64;
+        const float* up = pts + t * 16 + t0 * 64;
+        if (free_z) {
+            for (int tl = t0; tl < full1; ++tl, bp += 64, up += 64) {
+                const float c = *bp;
+                const float bh = tf32_hi_bits(c), bl = c - bh;
+                float d[3][4];
+    #pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.f;
+                    mma_tf32_16x8x8(d[r], a1[r], bh, bh);
+                    mma_tf32_16x8x8(d[r], a1[r], bl, 0.f);
+                }
+                const float2 nu2 = *reinterpret_cast<const float2*>(up + 6);
+                const float4 mid = *reinterpret_cast<const float4*>(up + 8);
+                const float2 wv2 = *reinterpret_cast<const float2*>(up + 12);
+                const V2 nu = v2(nu2.x, nu2.y), nv = v2(mid.x, mid.y), wu = v2(mid.z, mid.w), wv = v2(wv2.x, wv2.y);
+                acc0 = pair_cost_tail<BOUNDED, false>(v2(d[0][0], d[0][1]), v2(d[1][0], d[1][1]), v2(d[2][0], d[2][1]), cam, delta, nu, nv, wu, wv, acc0, SweepRsqrt());
+                acc1 = pair_cost_tail<BOUNDED, false>(v2(d[0][2], d[0][3]), v2(d[1][2], d[1][3]), v2(d[2][2], d[2][3]), cam, delta, nu, nv, wu, wv, acc1, SweepRsqrt());
+            }
+        } else {
+            for (int tl = t0; tl < full1; ++tl, bp += 64, up += 64) {
+                const float c = *bp;
+                const float bh = tf32_hi_bits(c), bl = c - bh;
+                float d[3][4];
+    #pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.f;
+                    mma_tf32_16x8x8(d[r], a1[r], bh, bh);
+                    mma_tf32_16x8x8(d[r], a1[r], bl, 0.f);
+                }
+                const float2 nu2 = *reinterpret_cast<const float2*>(up + 6);
+                const float4 mid = *reinterpret_cast<const float4*>(up + 8);
+                const float2 wv2 = *reinterpret_cast<const float2*>(up + 12);
+                const V2 nu = v2(nu2.x, nu2.y), nv = v2(mid.x, mid.y), wu = v2(mid.z, mid.w), wv = v2(wv2.x, wv2.y);
+                acc0 = pair_cost_tail<BOUNDED>(v2(d[0][0], d[0][1]), v2(d[1][0], d[1][1]), v2(d[2][0], d[2][1]), cam, delta, nu, nv, wu, wv, acc0, SweepRsqrt());
+                acc1 = pair_cost_tail<BOUNDED>(v2(d[0][2], d[0][3]), v2(d[1][2], d[1][3]), v2(d[2][2], d[2][3]), cam, delta, nu, nv, wu, wv, acc1, SweepRsqrt());
+            }
+        }
+        for (int tl = max(t0, full1); tl < t1; ++tl) {   // the (at most one) partial tile: clamped loads, masked weights
             const int pt = min(tl * 8 + g, npts - 1);
             const float c = (t < 3) ? pts[(pt >> 1) * 16 + 2 * t + (pt & 1)] : 1.0f;
             const float bh = tf32_hi_bits(c), bl = c - bh;
@@ -959,10 +1049,8 @@ __device__ __forceinline__ void sweep_mma_items(const float* pts, int N, const f
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.f;
-                const float a1[4] = {ah[r][0], ah[r][1], al[r][0], al[r][1]};
-                const float a2[4] = {ah[r][0], ah[r][1], 0.f, 0.f};
-                mma_tf32_16x8x8(d[r], a1, bh, bh);
-                mma_tf32_16x8x8(d[r], a2, bl, 0.f);
+                mma_tf32_16x8x8(d[r], a1[r], bh, bh);
+                mma_tf32_16x8x8(d[r], a1[r], bl, 0.f);
             }
             const int pair = tl * 4 + t;
             const bool valid = pair < npair;
@@ -1070,7 +1158,7 @@ __device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, 
         float* const half1 = lw;
 #endif
 #if defined(EPNP_SWEEP_MMA)
-        if (!sweep_new_samples_mma<6>(pts4, a.N, smp, ptab, cst, half1, i * S, S, cam, delta))
+        if (!sweep_new_samples_mma<6>(pts4, a.N, smp, ptab, cst, half1, i * S, S, cam, delta, radius))
 #endif
         sweep_new_samples<6>(pts4, a.N, smp, cst, half1, i * S, S, cam, delta, radius);
 #endif
@@ -1318,7 +1406,7 @@ __device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, 
         float* const half1 = lw;
 #endif
 #if defined(EPNP_SWEEP_MMA)
-        if (!sweep_new_samples_mma<4>(pts4, a.N, smp, ptab, cst, half1, i * S, S, cam, delta))
+        if (!sweep_new_samples_mma<4>(pts4, a.N, smp, ptab, cst, half1, i * S, S, cam, delta, radius))
 #endif
         sweep_new_samples<4>(pts4, a.N, smp, cst, half1, i * S, S, cam, delta, radius);
 #endif

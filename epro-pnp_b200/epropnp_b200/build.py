@@ -55,6 +55,9 @@ EXPERIMENTS = {
     # ... at five CTAs per SM: 96 registers; the staging ring holds the K[R|t] table, so no aliasing -- 44.9 KB per CTA
     "five_ctas_mma": ["-DEPNP_SWEEP_MMA", "-DEPNP_SWEEP_NOCLAMP", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST",
                       "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_NO_LW", "-DEPNP_CTAS_PER_SM=5"],
+    # ... and at six: the K[R|t] columns are computed per work item (no table, the ring is aliased away), 80 registers
+    "six_ctas_mma": ["-DEPNP_SWEEP_MMA", "-DEPNP_SWEEP_NOCLAMP", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST",
+                     "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW", "-DEPNP_CTAS_PER_SM=6"],
     "sweep_huber_m": ["-DEPNP_SWEEP_HUBER_M"],            # shipped sweep arithmetic with the select-free Huber only
     "six_ctas_huber_m": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE",
                          "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW", "-DEPNP_SWEEP_HUBER_M", "-DEPNP_CTAS_PER_SM=6"],

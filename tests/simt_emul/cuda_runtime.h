@@ -210,12 +210,33 @@ inline float __shfl_xor_sync(unsigned, float v, int m) {
     float r; std::memcpy(&r, &b, 4);
     return r;
 }
+inline float __shfl_sync(unsigned, float v, int src_lane) {
+    simt::BlockState& s = simt::state();
+    const int me = s.cur;
+    uint32_t b; std::memcpy(&b, &v, 4);
+    s.slot[me] = b;
+    simt::syncwarp();
+    const uint32_t r = s.slot[(me & ~31) | (src_lane & 31)];
+    simt::syncwarp();
+    float out; std::memcpy(&out, &r, 4);
+    return out;
+}
 // the only use of __activemask() in the kernels is as the mask of a vote whose outcome selects between two
 // equivalent code paths per thread; a per-thread answer is a legal outcome of that vote
 constexpr unsigned kEmulActiveMask = 0xA5A5A5A5u;
 inline unsigned __activemask() { return kEmulActiveMask; }
 inline int __all_sync(unsigned mask, int pred) {
     if (mask == kEmulActiveMask) return pred != 0;
+    if (mask == 0xffffffffu) {              // full-warp vote: every lane of the warp takes part
+        simt::BlockState& s = simt::state();
+        const int me = s.cur, base = me & ~31;
+        s.slot[me] = pred != 0;
+        simt::syncwarp();
+        int all = 1;
+        for (int l = 0; l < 32 && base + l < s.nthreads; ++l) all &= (int)s.slot[base + l];
+        simt::syncwarp();
+        return all;
+    }
     std::fprintf(stderr, "simt_emul: __all_sync with an explicit mask is not emulated\n"); std::abort();
 }
 inline uint32_t __float_as_uint(float x) { uint32_t u; std::memcpy(&u, &x, 4); return u; }

@@ -62,7 +62,7 @@ from epropnp_b200.build import EXPERIMENTS  # noqa: E402
 # runs alone on a reduced set (fused goldens incl. 4-DoF, the odd-sample-count corner, the smallest point sets).
 CANDIDATE_VARIANTS = ["everything", "six_ctas", "six_ctas_plain_sweep", "five_ctas_mma"]
 SINGLE_OPTIONS = ["lm_packed", "lm_cost_first", "fast_blocksum", "amis_lse", "alias_stage", "no_lw", "sweep_huber_m", "sweep_rsq",
-                  "sweep_noclamp", "sweep_split", "sweep_mma", "sweep_mma_all", "five_ctas"]
+                  "sweep_noclamp", "sweep_split", "sweep_mma", "sweep_mma_all", "five_ctas", "six_ctas_mma"]
 EMULATED_VARIANTS = SINGLE_OPTIONS + CANDIDATE_VARIANTS
 
 

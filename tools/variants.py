@@ -124,7 +124,7 @@ def cmd_run(args):
     # default selection: every option on its own + everything together (the unions in between are left to the caller)
     # default selection: the candidate combinations first (if the call runs out of time the single options are the ones
     # lost), then every option on its own for attribution
-    names = args.names or ["default", "six_ctas_huber_m", "six_ctas_plain_sweep", "six_ctas", "five_ctas_mma", "sweep_mma_all",
+    names = args.names or ["default", "six_ctas_huber_m", "six_ctas_plain_sweep", "six_ctas", "five_ctas_mma", "six_ctas_mma", "sweep_mma_all",
                            "five_ctas_plain_sweep", "five_ctas",
                            "everything", "four_ctas_same_code", "lm_cost_first", "lm_norefine", "sweep_huber_m", "sweep_rsq",
                            "sweep_split", "sweep_noclamp", "fast_blocksum", "lm_packed"]
