@@ -95,7 +95,9 @@ def sass_loops(so, pattern="solve_kernelILi6ELb1ELb1"):
                 body = lines[amap[t]:i + 1]
                 c = collections.Counter(op(x) for x in body)
                 fp = sum(c.get(k, 0) for k in ("FFMA", "FFMA2", "FMUL", "FMUL2", "FADD", "FADD2"))
-                if len(body) >= 60 and fp > 30 and c.get("BAR", 0) == 0 and len(body) < 600:
+                if c.get("HMMA", 0) and c.get("BAR", 0) == 0 and len(body) < 200:
+                    out.append((len(body), dict(c.most_common(8))))
+                elif len(body) >= 60 and fp > 30 and c.get("BAR", 0) == 0 and len(body) < 600:
                     out.append((len(body), dict(c.most_common(8))))
         out.insert(0, ("total_sass_instructions", len(lines)))
     return out
@@ -114,7 +116,7 @@ def cmd_static(args):
         loops = sass_loops(vpath(name))
         print("  ", loops[0])
         for n, mix in loops[1:]:
-            kind = "sweep" if mix.get("FFMA2", 0) >= 30 and mix.get("MUFU", 0) >= 4 and mix.get("LDS", 0) >= 4 and "FFMA" not in mix \
+            kind = "mma-tile" if mix.get("HMMA", 0) else "sweep" if mix.get("FFMA2", 0) >= 30 and mix.get("MUFU", 0) >= 4 and mix.get("LDS", 0) >= 4 and "FFMA" not in mix \
                 else ("lm-eval" if (mix.get("FFMA", 0) + mix.get("FFMA2", 0)) >= 90 else "other")
             if kind != "other":
                 print(f"   {kind:8s} loop {n:4d} instr  {mix}")
