@@ -62,7 +62,7 @@ from epropnp_b200.build import EXPERIMENTS  # noqa: E402
 # runs alone on a reduced set (fused goldens incl. 4-DoF, the odd-sample-count corner, the smallest point sets).
 CANDIDATE_VARIANTS = ["everything", "six_ctas", "six_ctas_plain_sweep", "five_ctas_mma"]
 SINGLE_OPTIONS = ["lm_packed", "lm_cost_first", "fast_blocksum", "amis_lse", "alias_stage", "no_lw", "sweep_huber_m", "sweep_rsq",
-                  "sweep_noclamp", "sweep_split", "sweep_mma", "sweep_mma_all", "five_ctas", "six_ctas_mma"]
+                  "sweep_noclamp", "sweep_split", "sweep_mma", "six_ctas_mma"]
 EMULATED_VARIANTS = SINGLE_OPTIONS + CANDIDATE_VARIANTS
 
 
@@ -76,7 +76,7 @@ def option_device(request, monkeypatch):
     return simt_native.install(monkeypatch, EXPERIMENTS[request.param])
 
 
-@pytest.mark.parametrize("name", ["mc6_basic", "mc6_bounds"])
+@pytest.mark.parametrize("name", ["mc6_bounds"])
 def test_option_golden_fused_lm_amis(option_device, name):
     _gp.test_golden_fused_lm_amis(option_device, name)
 
@@ -85,7 +85,7 @@ def test_option_golden_fused_4dof(option_device):
     _gp.test_golden_fused_lm_amis_4dof(option_device)
 
 
-@pytest.mark.parametrize("name", ["lm6_ragged", "lm6_bounds", "gn4_fast"])
+@pytest.mark.parametrize("name", ["lm6_ragged", "gn4_fast"])
 def test_option_golden_lm_and_cost(option_device, name):
     _gp.test_golden_evaluate(option_device, name)
     _gp.test_golden_lm_solve(option_device, name)
