@@ -1995,6 +1995,69 @@ __global__ void __launch_bounds__(NT) adaptive_delta_kernel(const float* x2d, co
     if (threadIdx.x == 0) delta[obj] = mw * sqrtf((v[0] + v[1]) / (float)(N - 1)) * rel;
 }
 
+// Epilogue on the AMIS outputs (the step after the path).  One CTA per object reads the
+// object's M log-weights (and, for the score, the x / z components of its M pose samples) once and writes
+//   lse[b]      = logsumexp_m logw[b, m]                        (Monte-Carlo pose loss: loss_pred)
+//   loss[b]     = cost_target[b] + lse[b], NaN -> 0              (the per-object loss before its mean)
+//   weights     = softmax_m logw[b, :]                           (Det: pose_sample_logweights.softmax(dim=0))
+//   score_te[b] = sum_m weights[m] * clamp((2.5 - log2 |(x,z)_m - (x,z)_opt|) / 4, 0, 1)   (Det 'te' MC score)
+// with torch's conventions at the infinities (all -inf -> lse -inf, any NaN -> NaN).
+template <int PD>
+__global__ void __launch_bounds__(NT) mc_epilogue_kernel(const float* logw, const float* samples, const float* pose_opt,
+                                                       const float* cost_target, float* lse_out, float* loss_out,
+                                                       float* weights, float* score_out, int M) {
+    __shared__ float red[2 * NW * 32];
+    const int obj = blockIdx.x, tid = threadIdx.x;
+    const float* l = logw + (size_t)obj * M;
+    float mx = -CUDART_INF_F;
+    bool any_nan = false;
+    for (int m = tid; m < M; m += NT) { const float v = __ldg(l + m); mx = fmaxf(mx, v); any_nan |= (v != v); }
+    mx = block_max(mx, red, 0);
+    const float ref = (fabsf(mx) == CUDART_INF_F) ? 0.f : mx;          // torch.logsumexp: an infinite max is not subtracted
+    const bool want_score = samples != nullptr && pose_opt != nullptr && score_out != nullptr;
+    float ox = 0.f, oz = 0.f;
+    if (want_score) { ox = __ldg(pose_opt + (size_t)obj * PD); oz = __ldg(pose_opt + (size_t)obj * PD + 2); }
+    float acc[3] = {0.f, 0.f, any_nan ? 1.f : 0.f};                    // sum e, sum e * score, NaN seen
+    for (int m = tid; m < M; m += NT) {
+        const float e = expf(__ldg(l + m) - ref);
+        acc[0] += e;
+        if (want_score) {
+            const float* sp = samples + ((size_t)obj * M + m) * PD;
+            const float dx = __ldg(sp) - ox, dz = __ldg(sp + 2) - oz;
+            const float dev = sqrtf(fmaf(dx, dx, dz * dz));
+            const float sc = fminf(fmaxf((2.5f - log2f(dev)) * 0.25f, 0.f), 1.f);
+            acc[1] = fmaf(e, sc, acc[1]);
+        }
+    }
+    block_sum<3>(acc, red, 1);
+    const float nan_in = acc[2] > 0.f ? CUDART_NAN_F : 0.f;            // fmaxf drops NaNs: put them back
+    const float lse = logf(acc[0]) + ref + nan_in;
+    const float inv = (mx == CUDART_INF_F) ? CUDART_NAN_F : 1.0f / acc[0];   // softmax: inf - inf poisons the whole object
+    if (tid == 0) {
+        if (lse_out) lse_out[obj] = lse;
+        if (loss_out) {
+            const float v = (cost_target ? __ldg(cost_target + obj) : 0.f) + lse;
+            loss_out[obj] = (v != v) ? 0.f : v;
+        }
+        if (want_score) score_out[obj] = acc[1] * inv + nan_in;
+    }
+    if (weights) {
+        float* w = weights + (size_t)obj * M;
+        for (int m = tid; m < M; m += NT) w[m] = expf(__ldg(l + m) - ref) * inv;
+    }
+}
+
+// Backward of lse (and of the NaN -> 0 mask): grad_logw[b, m] = g[b] * exp(logw[b, m] - lse[b]); g[b] == 0 gives exact zeros
+// (masked objects have lse = NaN).
+__global__ void __launch_bounds__(NT) mc_lse_backward_kernel(const float* logw, const float* lse, const float* g,
+                                                           float* grad_logw, int M) {
+    const int obj = blockIdx.x;
+    const float gb = __ldg(g + obj), ls = __ldg(lse + obj);
+    const float* l = logw + (size_t)obj * M;
+    float* o = grad_logw + (size_t)obj * M;
+    for (int m = threadIdx.x; m < M; m += NT) o[m] = (gb == 0.f) ? 0.f : gb * expf(__ldg(l + m) - ls);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side
 int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return EPNP_ERR_CUDA; }
@@ -2114,6 +2177,31 @@ int epnp_adaptive_delta_f32(const float* x2d, const float* w2d, float relative_d
     if (!x2d || !w2d || !delta || B < 0 || N <= 0) return EPNP_ERR_BAD_ARG;
     if (B == 0) return EPNP_OK;
     EPNP_LAUNCH(adaptive_delta_kernel, B, NT, 0, (cudaStream_t)stream, x2d, w2d, relative_delta, delta, N);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
+}
+
+int epnp_mc_epilogue_f32(const float* logw, const float* pose_samples, const float* pose_opt, const float* cost_target,
+                         float* lse, float* loss, float* weights, float* score_te, int B, int M, int dof, void* stream) {
+    if (!logw || B < 0 || M <= 0 || (dof != 4 && dof != 6)) return EPNP_ERR_BAD_ARG;
+    if (!lse && !loss && !weights && !score_te) return EPNP_ERR_BAD_ARG;
+    if (score_te && (!pose_samples || !pose_opt)) return EPNP_ERR_BAD_ARG;
+    if (B == 0) return EPNP_OK;
+    if (dof == 6)
+        EPNP_LAUNCH(mc_epilogue_kernel<7>, B, NT, 0, (cudaStream_t)stream, logw, pose_samples, pose_opt, cost_target, lse, loss,
+                    weights, score_te, M);
+    else
+        EPNP_LAUNCH(mc_epilogue_kernel<4>, B, NT, 0, (cudaStream_t)stream, logw, pose_samples, pose_opt, cost_target, lse, loss,
+                    weights, score_te, M);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
+}
+
+int epnp_mc_lse_backward_f32(const float* logw, const float* lse, const float* grad_lse, float* grad_logw, int B, int M,
+                             void* stream) {
+    if (!logw || !lse || !grad_lse || !grad_logw || B < 0 || M <= 0) return EPNP_ERR_BAD_ARG;
+    if (B == 0) return EPNP_OK;
+    EPNP_LAUNCH(mc_lse_backward_kernel, B, NT, 0, (cudaStream_t)stream, logw, lse, grad_lse, grad_logw, M);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
 }

@@ -7,6 +7,7 @@ batched hot loops run in hand-written sm_100a CUDA behind libepropnp_b200.so:
     epropnp.cost_fun              HuberPnPCost / AdaptiveHuberPnPCost
     epropnp.common                evaluate_pnp, pnp_normalize, pnp_denormalize, rotation helpers
     epropnp.distributions         AngularCentralGaussian / VonMisesUniformMix
+    epropnp.monte_carlo_pose_loss MonteCarloPoseLoss (6DoF and detection flavours), mc_logsumexp / mc_sample_weights / mc_score_te
     epropnp.builder               build_pnp / build_camera / build_cost_fun + registries (detection-style configs)
 
 Put `<repo>/epro-pnp_b200` on sys.path (instead of the reference checkout) and existing imports keep

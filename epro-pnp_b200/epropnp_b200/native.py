@@ -256,3 +256,50 @@ def lm_amis_fused_host(host, params, workspace, n_chunks=8, seed=0, obj_offset=0
 
 __all__ = ["Problem", "adaptive_delta", "cost_backward", "evaluate_cost", "evaluate_full", "lm_solve", "amis", "lm_amis_fused",
            "lm_amis_fused_host", "fused_workspace_bytes", "rslm", "gn_plus_backward", "default_params", "NativeError", "capi"]
+
+
+def mc_epilogue(logw_bm, pose_samples_bmd=None, pose_opt=None, cost_target=None, want_lse=True, want_loss=False,
+                want_weights=False, want_score=False):
+    """One pass over the object-major AMIS outputs (epnp_mc_epilogue_f32): logw (B, M) [, pose_samples (B, M, D),
+    pose_opt (B, D), cost_target (B)] -> dict(lse (B), loss (B), weights (B, M), score_te (B)), absent ones None."""
+    _need_cuda(logw_bm, "logw")
+    B, M = logw_bm.shape
+    logw_bm = _f32c(logw_bm)
+    dev = logw_bm.device
+    dof = 6
+    if want_score:
+        if pose_samples_bmd is None or pose_opt is None:
+            raise ValueError("the MC score needs pose_samples (B, M, D) and pose_opt (B, D)")
+        D = pose_samples_bmd.shape[-1]
+        if D not in (4, 7) or tuple(pose_samples_bmd.shape) != (B, M, D) or tuple(pose_opt.shape) != (B, D):
+            raise ValueError("pose_samples must be (B, M, D) and pose_opt (B, D) with D = 4 or 7")
+        dof = 6 if D == 7 else 4
+        pose_samples_bmd, pose_opt = _f32c(pose_samples_bmd), _f32c(pose_opt)
+    else:
+        pose_samples_bmd = pose_opt = None
+    if cost_target is not None:
+        cost_target = _f32c(cost_target).expand(B).contiguous()
+    new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    out = dict(lse=new(B) if want_lse else None, loss=new(B) if want_loss else None,
+               weights=new(B, M) if want_weights else None, score_te=new(B) if want_score else None)
+    if B == 0:
+        return out
+    with torch.cuda.device(dev):
+        check(lib().epnp_mc_epilogue_f32(ptr(logw_bm), ptr(pose_samples_bmd), ptr(pose_opt), ptr(cost_target),
+                                         ptr(out["lse"]), ptr(out["loss"]), ptr(out["weights"]), ptr(out["score_te"]),
+                                         B, M, dof, stream_ptr(dev)), "epnp_mc_epilogue_f32")
+    return out
+
+
+def mc_lse_backward(logw_bm, lse, grad_lse):
+    """grad_logw (B, M) = grad_lse[b] * exp(logw[b, m] - lse[b]) (epnp_mc_lse_backward_f32)."""
+    _need_cuda(logw_bm, "logw")
+    B, M = logw_bm.shape
+    logw_bm, lse, grad_lse = _f32c(logw_bm), _f32c(lse), _f32c(grad_lse)
+    out = torch.empty_like(logw_bm)
+    if B == 0:
+        return out
+    with torch.cuda.device(logw_bm.device):
+        check(lib().epnp_mc_lse_backward_f32(ptr(logw_bm), ptr(lse), ptr(grad_lse), ptr(out), B, M,
+                                             stream_ptr(logw_bm.device)), "epnp_mc_lse_backward_f32")
+    return out

@@ -170,6 +170,23 @@ int epnp_cost_backward_f32(const float* x3d, const float* x2d, const float* w2d,
                            float* grad_x3d, float* grad_x2d, float* grad_w2d, float* grad_delta,
                            int B, int N, int dof, float z_min, void* stream);
 
+/* Epilogue on the AMIS outputs -- the step AFTER the path in every caller of monte_carlo_forward (one pass over the
+ * object-major log-weights instead of a dozen torch ops on (M, B) views):
+ *   lse (B)        = logsumexp_m logw[b, m]      -- `loss_pred` of MonteCarloPoseLoss.forward
+ *                    (EPro-PnP-6DoF/lib/models/monte_carlo_pose_loss.py:27-28, EPro-PnP-Det/epropnp_det/models/losses/
+ *                    monte_carlo_pose_loss.py:21-22)
+ *   loss (B)       = cost_target[b] + lse[b], NaN replaced by 0 (same files :30-31 / :24-25); cost_target [opt]
+ *   weights (B, M) = softmax_m logw[b, :]        -- deform_pnp_head.py:524
+ *   score_te (B)   = sum_m weights[b, m] * clamp((2.5 - log2 ||(x, z)_{b,m} - (x, z)_opt,b||) / 4, 0, 1)
+ *                    -- the Monte-Carlo 'te' score, deform_pnp_head.py:533-536; needs pose_samples (B, M, D), pose_opt (B, D)
+ * Every output is [opt]; at least one must be given.                                                              */
+int epnp_mc_epilogue_f32(const float* logw /*(B,M)*/, const float* pose_samples, const float* pose_opt,
+                         const float* cost_target, float* lse, float* loss, float* weights, float* score_te,
+                         int B, int M, int dof, void* stream);
+/* Backward of lse: grad_logw (B, M) = grad_lse[b] * exp(logw[b, m] - lse[b]), exactly 0 where grad_lse[b] == 0.     */
+int epnp_mc_lse_backward_f32(const float* logw, const float* lse, const float* grad_lse, float* grad_logw,
+                             int B, int M, void* stream);
+
 /* Same as epnp_lm_amis_fused_f32 with HOST buffers (pinned for full speed): copies the inputs to
  * the caller-provided device workspace, runs the fused kernel and copies the results back, all on
  * `stream`, in `n_chunks` object chunks through a copy-in / solve / copy-out pipeline (helper streams owned by

@@ -118,6 +118,28 @@ def main():
                 row[key] = timed(step, iters=10)
             os.environ["EPNP_NATIVE_GN_STEP"] = "0"
             out.append(row)
+    # the step after the path: Monte-Carlo pose loss forward + backward and the Det MC score, torch composite on the
+    # layer's (M, B) views vs the native one-pass epilogue
+    if os.environ.get("EPNP_BENCH_MC_EPILOGUE"):
+        sys.path.insert(0, os.path.join(ROOT, "epro-pnp_b200"))
+        from epropnp import monte_carlo_pose_loss as mcl
+        for B, D in ((4096, 7), (4096, 4)):
+            logw = (torch.randn(B, 512, device=dev) * 3).transpose(0, 1).requires_grad_(True)
+            samples = torch.randn(B, 512, D, device=dev).transpose(0, 1)
+            opt, ct = torch.randn(B, D, device=dev), torch.rand(B, device=dev)
+            loss_fn = mcl.MonteCarloPoseLoss().to(dev).eval()
+            row = dict(config=f"MC pose loss fwd+bwd and MC te-score on (512, {B}) log-weights, D={D}", B=B,
+                       bytes_min=B * 512 * 4 * 3 + B * 512 * D * 4)
+
+            def step():
+                logw.grad = None
+                loss_fn(logw, ct, 1.0).backward()
+                mcl.mc_score_te(samples, opt, logw.detach())
+            for flag, key in (("0", "ms_composite"), ("1", "ms_native")):
+                os.environ["EPNP_NATIVE_MC_EPILOGUE"] = flag
+                row[key] = timed(step, iters=20)
+            os.environ["EPNP_NATIVE_MC_EPILOGUE"] = "0"
+            out.append(row)
     for r in out:
         print(json.dumps(r))
 

@@ -20,9 +20,9 @@ case "${1:-}" in
     ;;
   experimental)
     # the two opt-in kernels, their timings, the copy ceiling of the box, the e2e chunk sweep, the tcgen05 probe
-    EPNP_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_rslm_fused_gpu.py tests/test_gn_plus_backward_gpu.py -q \
+    EPNP_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_rslm_fused_gpu.py tests/test_gn_plus_backward_gpu.py tests/test_mc_epilogue_gpu.py -q \
         2>&1 | tee gpurun_out/experimental_tests.log | tail -5
-    EPNP_BENCH_RSLM=1 EPNP_BENCH_GN_PLUS=1 timeout 400 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err
+    EPNP_BENCH_RSLM=1 EPNP_BENCH_GN_PLUS=1 EPNP_BENCH_MC_EPILOGUE=1 timeout 400 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err
     timeout 120 python tools/pcie_probe.py > gpurun_out/pcie_probe.json 2>&1
     for c in 4 7 8 14; do
       EPNP_E2E_CHUNKS=$c timeout 200 python bench.py --steps 100 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/e2e_chunks_$c.json
