@@ -27,6 +27,11 @@ case "${1:-}" in
     for c in 4 7 8 14; do
       EPNP_E2E_CHUNKS=$c timeout 200 python bench.py --steps 100 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/e2e_chunks_$c.json
     done
+    # batches in flight: does the next batch fill the previous batch's last wave?  (1 = the shipped bench configuration)
+    for st in 1 2 3; do
+      timeout 200 python bench.py --steps 400 --warmup 3 --streams $st --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 > gpurun_out/streams_$st.json
+      cut -c1-200 gpurun_out/streams_$st.json
+    done
     (cd tools/tc_probe && nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tc_probe tc_probe.cu \
         && timeout 60 ./tc_probe) > gpurun_out/tc_probe.json 2>&1
     tail -c 600 gpurun_out/tc_probe.json
@@ -34,7 +39,7 @@ case "${1:-}" in
   two_gpu)
     EPNP_TEST_PEER_GATHER=1 timeout 300 python -m pytest tests/test_peer_gather_gpu.py -q 2>&1 | tee gpurun_out/peer_gather_test.log | tail -3
     i=0
-    for g in "--gather nccl" "--gather nccl --nccl-max-ctas 2" "--gather peer"; do
+    for g in "--gather nccl" "--gather nccl --nccl-max-ctas 2" "--gather peer" "--gather nccl --streams 2" "--gather peer --streams 2"; do
       i=$((i + 1))
       timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$i \
           bench.py --gpus 2 --steps 300 --warmup 5 $g --no-cpu-baseline --no-e2e 2> gpurun_out/two_gpu_$i.err | tail -1 > gpurun_out/two_gpu_$i.json
