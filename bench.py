@@ -37,6 +37,10 @@ import torch  # noqa: E402
 B_PER_GPU, N_PTS, MC_SAMPLES, MC_ITER, LM_ITER = 4096, 512, 512, 4, 10
 ROTATING_SETS = 4                         # 4 x 58.7 MB of inputs > 126 MB L2
 E2E_CHUNKS = int(os.environ.get("EPNP_E2E_CHUNKS", "4"))   # object chunks of the host-buffer pipeline
+# host-buffer calls in flight: with 2, consecutive steps alternate between two (stream, workspace, pinned result set)
+# triples, so step i+1's upload runs under step i's solve / download (a double-buffered input pipeline).  1 = every
+# step waits for the previous one (the measured round-1 configuration).
+E2E_LANES = max(1, int(os.environ.get("EPNP_E2E_LANES", "1")))
 METRIC = "PnP objects/sec (B=4096,N=512,M=512)"
 
 
@@ -417,16 +421,31 @@ def main():
         host = {k: pc[k].contiguous().pin_memory() for k in ("x3d", "x2d", "w2d", "cam_mats", "pose_init")}
         host["delta"] = sets[0]["delta"].cpu().pin_memory()
         shift0 = {k: v for k, v in host.items()}
-        ws = torch.empty(native.fused_workspace_bytes(Bg, N_PTS, params), dtype=torch.uint8, device=dev)
-        res = None
+        wss = [torch.empty(native.fused_workspace_bytes(Bg, N_PTS, params), dtype=torch.uint8, device=dev)
+               for _ in range(E2E_LANES)]
+        ress = [None] * E2E_LANES
+        e_lanes = [torch.cuda.Stream(dev) for _ in range(E2E_LANES)] if E2E_LANES > 1 else [torch.cuda.current_stream(dev)]
         e_steps = max(3, min(args.steps, 50))
-        for i in range(2):
-            res = native.lm_amis_fused_host(shift0, params, ws, n_chunks=E2E_CHUNKS, seed=77 + i, obj_offset=rank * Bg, out=res)
+
+        def e2e_step(i, seed):
+            k = i % E2E_LANES
+            with torch.cuda.stream(e_lanes[k]):
+                ress[k] = native.lm_amis_fused_host(shift0, params, wss[k], n_chunks=E2E_CHUNKS, seed=seed + i,
+                                                    obj_offset=rank * Bg, out=ress[k])
+            return ress[k]
+        for i in range(2 * E2E_LANES):
+            res = e2e_step(i, 77)
         fence()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if E2E_LANES > 1:
+            for s in e_lanes:
+                s.wait_stream(torch.cuda.current_stream(dev))
         for i in range(e_steps):
-            res = native.lm_amis_fused_host(shift0, params, ws, n_chunks=E2E_CHUNKS, seed=99 + i, obj_offset=rank * Bg, out=res)
+            res = e2e_step(i, 99)
+        if E2E_LANES > 1:
+            for s in e_lanes:
+                torch.cuda.current_stream(dev).wait_stream(s)
         e1.record()
         fence()
         te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -435,7 +454,7 @@ def main():
         h2d = sum(host[k].numel() * 4 for k in host)
         d2h = sum(v.numel() * 4 for v in res.values() if v is not None)
         e2e = {"value": B_total * e_steps / (te.item() * 1e-3), "unit": "objects/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": e_steps, "chunks": E2E_CHUNKS,
+               "d2h_bytes_per_step": d2h, "steps": e_steps, "chunks": E2E_CHUNKS, "calls_in_flight": E2E_LANES,
                "path": "epnp_lm_amis_fused_host_f32 (pinned host buffers, chunked copy/solve overlap)"}
 
     if rank == 0:

@@ -254,10 +254,6 @@ def lm_amis_fused_host(host, params, workspace, n_chunks=8, seed=0, obj_offset=0
     return out
 
 
-__all__ = ["Problem", "adaptive_delta", "cost_backward", "evaluate_cost", "evaluate_full", "lm_solve", "amis", "lm_amis_fused",
-           "lm_amis_fused_host", "fused_workspace_bytes", "rslm", "gn_plus_backward", "default_params", "NativeError", "capi"]
-
-
 def mc_epilogue(logw_bm, pose_samples_bmd=None, pose_opt=None, cost_target=None, want_lse=True, want_loss=False,
                 want_weights=False, want_score=False):
     """One pass over the object-major AMIS outputs (epnp_mc_epilogue_f32): logw (B, M) [, pose_samples (B, M, D),
@@ -303,3 +299,7 @@ def mc_lse_backward(logw_bm, lse, grad_lse):
         check(lib().epnp_mc_lse_backward_f32(ptr(logw_bm), ptr(lse), ptr(grad_lse), ptr(out), B, M,
                                              stream_ptr(logw_bm.device)), "epnp_mc_lse_backward_f32")
     return out
+
+
+__all__ = ["Problem", "adaptive_delta", "cost_backward", "evaluate_cost", "evaluate_full", "lm_solve", "amis", "lm_amis_fused",
+           "lm_amis_fused_host", "fused_workspace_bytes", "rslm", "gn_plus_backward", "mc_epilogue", "mc_lse_backward", "default_params", "NativeError", "capi"]

@@ -3,7 +3,7 @@
 # Every step is wrapped in its own timeout and writes under gpurun_out/; run each block as ONE gpurun call:
 #
 #   gpurun --timeout 1700 -- 'bash tools/first_gpu_calls.sh variants'        # 1 GPU, ~20 min
-#   gpurun --timeout 900  -- 'bash tools/first_gpu_calls.sh experimental'    # 1 GPU, ~8 min
+#   gpurun --timeout 1300 -- 'bash tools/first_gpu_calls.sh experimental'    # 1 GPU, ~8 min
 #   gpurun --gpus 2 --timeout 700 -- 'bash tools/first_gpu_calls.sh two_gpu' # 2 GPUs, ~6 min (charged x2)
 set -u
 cd "$(dirname "$0")/.."
@@ -27,6 +27,18 @@ case "${1:-}" in
     for c in 4 7 8 14; do
       EPNP_E2E_CHUNKS=$c timeout 200 python bench.py --steps 100 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/e2e_chunks_$c.json
     done
+    # two host-buffer calls in flight (double-buffered workspace + results): step i+1 uploads under step i's solve
+    for c in 4 7; do
+      EPNP_E2E_LANES=2 EPNP_E2E_CHUNKS=$c timeout 200 python bench.py --steps 100 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/e2e_lanes2_chunks_$c.json
+    done
+    python - <<'PY'
+import glob, json
+for f in sorted(glob.glob("gpurun_out/e2e_*.json")):
+    try:
+        e = json.load(open(f))["e2e"]; print(f, round(e["value"]), "objects/s", e.get("chunks"), e.get("calls_in_flight"))
+    except Exception as x:
+        print(f, "unreadable:", x)
+PY
     # batches in flight: does the next batch fill the previous batch's last wave?  (1 = the shipped bench configuration)
     for st in 1 2 3; do
       timeout 200 python bench.py --steps 400 --warmup 3 --streams $st --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 > gpurun_out/streams_$st.json
