@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/mc_loss.npz by running the UNMODIFIED reference loss
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/epilogue/mc_loss.npz by running the UNMODIFIED reference loss
 (/root/reference/EPro-PnP-6DoF/lib/models/monte_carlo_pose_loss.py, imports only torch) on seeded log-weights that
 include the corner cases it special-cases (a NaN object) and the infinities torch.logsumexp defines (all -inf, a +inf).
 
@@ -68,6 +68,6 @@ out["ref64_lse_edge"] = torch.logsumexp(logw_edge, dim=0).numpy()
 out["ref64_weights_edge"] = logw_edge.softmax(dim=0).numpy()
 out.update(logw=logw.numpy(), cost_target=cost_target.numpy(), norm_in=norm_in.numpy(), coef=coef.numpy(),
            init_norm_factor=np.float64(1.5), momentum=np.float64(0.01))
-path = os.path.join(os.path.dirname(HERE), "tests", "golden", "mc_loss.npz")
+path = os.path.join(os.path.dirname(HERE), "tests", "golden", "epilogue", "mc_loss.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})

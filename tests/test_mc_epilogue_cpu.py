@@ -1,6 +1,6 @@
 """Row f4 -- the step after monte_carlo_forward: MonteCarloPoseLoss / softmax weights / Monte-Carlo score.
 
-  * the torch composite (the default) against tests/golden/mc_loss.npz, which oracle/make_golden_mc_loss.py records by
+  * the torch composite (the default) against tests/golden/epilogue/mc_loss.npz, which oracle/make_golden_mc_loss.py records by
     RUNNING the reference's own loss class (6DoF flavour; loss, gradients, EMA norm factor, train and eval mode);
   * the native epilogue kernels (epnp_mc_epilogue_f32 / epnp_mc_lse_backward_f32), executed from the real kernel source
     under the CPU SIMT emulator, against the same vectors, including torch.logsumexp's conventions at NaN / -inf / +inf.
@@ -14,7 +14,7 @@ from conftest import load_golden
 from epropnp import monte_carlo_pose_loss as mcl
 from epropnp_b200 import native
 
-G = load_golden("mc_loss")
+G = load_golden("epilogue/mc_loss")
 FINITE = [b for b in range(G["logw"].shape[1]) if b != 5]        # object 5 holds a NaN log-weight
 
 
