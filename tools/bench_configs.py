@@ -57,6 +57,14 @@ def main():
         ms = timed(lambda: native.lm_solve(prob, p0, p, want_cov=True), iters=10)
         out.append(dict(config="#4 dense GN(3) only (test-time path, lib/test.py:209-211), N=4096", B=B, ms=ms,
                         objects_per_s=B / ms * 1e3, hbm_gbs=B * 114932 / ms / 1e6))
+    # detection variant (EPro-PnP-Det/configs/epropnp_det_basic.py:98-111): EProPnP4DoF, 8 heads x 32 points = 256
+    # correspondences per object, LM(10) + AMIS(4x128), in-kernel von Mises / uniform yaw sampler
+    for B in (1024, 4096):
+        prob, p0 = setup(B, 256, 0.5, dof=4)
+        p = native.default_params(4, lm_iter=10, mc_samples=512, mc_iter=4)
+        ms = timed(lambda: native.lm_amis_fused(prob, p0, p, seed=1))
+        out.append(dict(config="Det: EProPnP4DoF LM(10)+AMIS(4x128), N=256", B=B, ms=ms, objects_per_s=B / ms * 1e3,
+                        hbm_gbs=B * (28 * 256 + 36 + 4 + 16 + 16 + 64 + 4 + 20 * 512) / ms / 1e6))
     # training step: fused forward + native Monte-Carlo cost backward (513 poses per object)
     for B in (1024, 4096):
         prob, p0 = setup(B, 512, 0.5)
