@@ -21,7 +21,7 @@ shown them parity-green and faster:
 
     python tools/variants.py build            # every variant -> epro-pnp_b200/lib/variants/ (they travel with gpurun)
     python tools/variants.py static           # registers / spills / hot-loop instruction mix per variant (no GPU)
-    python tools/variants.py run [names...]   # GPU box: per variant, parity tests then bench.py -> gpurun_out/variants.jsonl
+    python tools/variants.py run [names...]   # GPU box: bench.py per variant, then the parity tests of the faster ones -> gpurun_out/variants.jsonl
 
 `run` swaps each variant in as lib/libepropnp_b200.so for the duration of its tests + bench and restores the
 default build afterwards, so tests and bench exercise exactly the code path a default build of that variant would.
@@ -136,31 +136,56 @@ def cmd_run(args):
     keep = B.LIB_PATH + ".default_build"
     shutil.copy(B.LIB_PATH, keep)
     env = dict(os.environ, PYTHONPATH=os.path.join(REPO, "epro-pnp_b200") + os.pathsep + os.environ.get("PYTHONPATH", ""))
+
+    def bench(name):
+        vals = []
+        for _ in range(args.repeats):
+            b = subprocess.run(["timeout", "150", sys.executable, "bench.py", "--steps", str(args.steps), "--warmup",
+                                str(args.warmup), "--no-cpu-baseline", "--no-e2e"], cwd=REPO, env=env, capture_output=True, text=True)
+            line = [l for l in b.stdout.splitlines() if l.startswith("{")]
+            if b.returncode == 0 and line:
+                j = json.loads(line[-1])
+                vals.append(dict(value=j["value"], ms_per_step=j["ms_per_step"], sm_mhz=j.get("clocks", {}).get("sm_mhz")))
+            else:
+                vals.append(dict(error=(b.stderr or b.stdout)[-1500:]))
+        return vals
+
+    def tests(name, rec):
+        t = subprocess.run(["timeout", str(args.test_timeout), sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu"]
+                           + args.tests.split(), cwd=REPO, env=env, capture_output=True, text=True)
+        rec["tests_rc"] = t.returncode
+        rec["tests_tail"] = t.stdout.strip().splitlines()[-1:] if t.stdout.strip() else []
+        if t.returncode != 0:
+            rec["tests_fail"] = t.stdout[-3000:]
+
+    def emit(rec):
+        with open(out_path, "a") as f:
+            f.write(json.dumps(rec) + "\n")
+        print(json.dumps(rec)[:400], flush=True)
+
+    def best(vals):
+        return max((v.get("value", 0.0) for v in vals), default=0.0)
+
     try:
+        # pass 1: one bench line per variant (about 20 s each) -- a variant that is not faster needs no parity run
+        speed = {}
         for name in names:
-            rec = dict(variant=name, flags=VARIANTS[name])
             shutil.copy(build_variant(name), B.LIB_PATH)
-            t = subprocess.run(["timeout", str(args.test_timeout), sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu"]
-                               + args.tests.split(), cwd=REPO, env=env, capture_output=True, text=True)
-            rec["tests_rc"] = t.returncode
-            rec["tests_tail"] = t.stdout.strip().splitlines()[-1:] if t.stdout.strip() else []
-            if t.returncode != 0:
-                rec["tests_fail"] = t.stdout[-3000:]
-            vals = []
-            for _ in range(args.repeats):
-                b = subprocess.run(["timeout", "600", sys.executable, "bench.py", "--steps", str(args.steps), "--warmup",
-                                    str(args.warmup), "--no-cpu-baseline", "--no-e2e"], cwd=REPO, env=env, capture_output=True, text=True)
-                line = [l for l in b.stdout.splitlines() if l.startswith("{")]
-                if b.returncode == 0 and line:
-                    j = json.loads(line[-1])
-                    vals.append(dict(value=j["value"], ms_per_step=j["ms_per_step"], e2e=j.get("e2e", {}).get("value"),
-                                     sm_mhz=j.get("clocks", {}).get("sm_mhz")))
-                else:
-                    vals.append(dict(error=(b.stderr or b.stdout)[-1500:]))
-            rec["bench"] = vals
-            with open(out_path, "a") as f:
-                f.write(json.dumps(rec) + "\n")
-            print(json.dumps(rec)[:400], flush=True)
+            speed[name] = bench(name)
+            emit(dict(variant=name, flags=VARIANTS[name], phase="bench", bench=speed[name]))
+        base = best(speed.get("default", [])) or min((best(v) for v in speed.values() if best(v) > 0), default=0.0)
+        # pass 2: the GPU parity + edge tests, fastest first, for the variants that beat the default build
+        winners = sorted((n for n in names if n != "default" and best(speed[n]) > base * args.min_gain),
+                         key=lambda n: -best(speed[n]))
+        if args.all_tests:
+            winners += [n for n in names if n not in winners and n != "default"]
+        for name in winners[:args.max_tested] if args.max_tested > 0 else winners:
+            rec = dict(variant=name, flags=VARIANTS[name], phase="tests", speedup=best(speed[name]) / base if base else None)
+            shutil.copy(build_variant(name), B.LIB_PATH)
+            tests(name, rec)
+            emit(rec)
+        emit(dict(phase="summary", default=base, ranking=[(n, round(best(speed[n]) / base, 4) if base else None)
+                                                         for n in sorted(speed, key=lambda n: -best(speed[n]))]))
     finally:
         shutil.copy(keep, B.LIB_PATH)
         os.remove(keep)
@@ -182,6 +207,9 @@ if __name__ == "__main__":
             p.add_argument("--steps", type=int, default=300)
             p.add_argument("--warmup", type=int, default=5)
             p.add_argument("--repeats", type=int, default=1)
+            p.add_argument("--min-gain", type=float, default=1.01, help="parity-test only variants at least this much faster than default")
+            p.add_argument("--max-tested", type=int, default=8, help="at most this many variants get the parity run (0 = no limit)")
+            p.add_argument("--all-tests", action="store_true", help="parity-test the slower variants too (after the faster ones)")
     a = ap.parse_args()
     for n in a.names:
         if n not in VARIANTS:
