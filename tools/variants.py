@@ -104,8 +104,13 @@ def sass_loops(so, pattern="solve_kernelILi6ELb1ELb1"):
 
 
 def cmd_build(args):
-    for name in (args.names or VARIANTS):
-        print(build_variant(name, force=args.force), ptxas_summary(name))
+    # nvcc runs are independent: build them side by side (about 30 s each)
+    from concurrent.futures import ThreadPoolExecutor
+    names = list(args.names or VARIANTS)
+    with ThreadPoolExecutor(max_workers=max(1, min(len(names), (os.cpu_count() or 2)))) as pool:
+        outs = list(pool.map(lambda n: build_variant(n, force=args.force), names))
+    for name, out in zip(names, outs):
+        print(out, ptxas_summary(name))
 
 
 def cmd_static(args):
