@@ -2120,6 +2120,19 @@ int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream, 
 
 unsigned long long* g_prof_buffer = nullptr;     // set by epnp_debug_set_phase_buffer (profiling build)
 
+// Objects the device solves at once with the fused kernel: SMs x resident CTAs per SM (one CTA per object).  Used by
+// the host-buffer entry point to cut the batch at whole waves.  0 when it cannot be determined.
+template <class Kern>
+int resident_objects(Kern kern, int smem_bytes) {
+    int dev = 0, sms = 0, occ = 0;
+    if ((size_t)smem_bytes > SMEM_LIMIT) return 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem_bytes) != cudaSuccess) return 0;
+    return sms * occ;
+}
+
 int check_amis_params(const Params& p) {
     if (p.mc_iter <= 0 || p.mc_iter > MAX_ITER || p.mc_samples <= 0 || p.mc_samples % p.mc_iter != 0) return EPNP_ERR_BAD_ARG;
     if (p.acg_mle_iter < 0) return EPNP_ERR_BAD_ARG;
@@ -2491,6 +2504,20 @@ int epnp_lm_amis_fused_host_f32(const float* x3d_host, const float* x2d_host, co
     if (B == 0) return EPNP_OK;
     const WsLayout w = ws_layout(B, N, p);
     if (workspace_bytes < w.total) return EPNP_ERR_BAD_ARG;
+    // n_chunks = 0: cut the batch at whole waves of resident CTAs (a chunk of 1.7 waves costs 2), as few waves per chunk
+    // as the 64-chunk limit allows; n_chunks >= 1: that many equal chunks
+    int chunk_objects = 0;
+    if (n_chunks == 0) {
+        if (check_amis_params(*p) != EPNP_OK) return EPNP_ERR_BAD_ARG;
+        const int wave = (p->dof == 6)
+            ? resident_objects(solve_kernel<6, true, true>, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes)
+            : resident_objects(solve_kernel<4, true, true>, plan_smem<4>(N, p->mc_samples, p->mc_iter, true).total_bytes);
+        if (wave > 0) {
+            const int waves_per_chunk = (B + 64 * wave - 1) / (64 * wave);
+            chunk_objects = wave * waves_per_chunk;
+            n_chunks = (B + chunk_objects - 1) / chunk_objects;
+        }
+    }
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > B) n_chunks = B;
     if (n_chunks > 64) n_chunks = 64;
@@ -2513,7 +2540,8 @@ int epnp_lm_amis_fused_host_f32(const float* x3d_host, const float* x2d_host, co
     EPNP_TRY(cudaStreamWaitEvent(g_pipe.k[1], fork, 0));
     EPNP_TRY(cudaStreamWaitEvent(g_pipe.out, fork, 0));
     for (int c = 0; c < n_chunks; ++c) {
-        const int b0 = (int)((long long)B * c / n_chunks), b1 = (int)((long long)B * (c + 1) / n_chunks);
+        const int b0 = chunk_objects ? c * chunk_objects : (int)((long long)B * c / n_chunks);
+        const int b1 = chunk_objects ? (b0 + chunk_objects < B ? b0 + chunk_objects : B) : (int)((long long)B * (c + 1) / n_chunks);
         const int nb = b1 - b0;
         if (nb <= 0) continue;
         cudaStream_t sk = g_pipe.k[c & 1];

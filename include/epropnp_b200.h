@@ -190,8 +190,9 @@ int epnp_mc_lse_backward_f32(const float* logw, const float* lse, const float* g
 /* Same as epnp_lm_amis_fused_f32 with HOST buffers (pinned for full speed): copies the inputs to
  * the caller-provided device workspace, runs the fused kernel and copies the results back, all on
  * `stream`, in `n_chunks` object chunks through a copy-in / solve / copy-out pipeline (helper streams owned by
- * the calling host thread, created on first use -- the only resource the library keeps).  Choose n_chunks so a
- * chunk still holds >= ~1000 objects (two waves of the persistent grid); 4 for B = 4096.
+ * the calling host thread, created on first use -- the only resource the library keeps).  n_chunks = 0 cuts the
+ * batch at whole waves of resident CTAs (SMs x CTAs per SM objects per chunk, as few waves per chunk as the limit of
+ * 64 chunks allows); n_chunks >= 1 asks for that many equal chunks (4 for B = 4096 is the measured configuration).
  * workspace: device memory of at least epnp_fused_workspace_bytes(B, N, p) bytes.
  * Outputs [opt] as above (pose_samples_host may be NULL to skip the largest copy).              */
 size_t epnp_fused_workspace_bytes(int B, int N, const EpnpParams* p);

@@ -208,10 +208,13 @@ def test_persistent_grid_matches_one_object_per_cta(monkeypatch, variant):
                 assert torch.equal(out[k], ref[k]), (variant, cap, k)
 
 
-@pytest.mark.parametrize("n_chunks,bounded", [(1, False), (3, True), (64, False)])
+@pytest.mark.parametrize("n_chunks,bounded", [(1, False), (3, True), (64, False), (0, False), (0, True)])
 def test_host_buffer_entry_point_chunking(cuda_device, monkeypatch, n_chunks, bounded):
     """epnp_lm_amis_fused_host_f32 (host buffers, chunked copy / solve / copy-back pipeline): workspace layout, chunk
-    boundaries and per-chunk object offsets of the Philox stream give the device-resident call's results bit for bit."""
+    boundaries and per-chunk object offsets of the Philox stream give the device-resident call's results bit for bit.
+    n_chunks = 0 cuts at whole waves: a 1-SM "device" with 4 resident CTAs (bounded: 2 SMs) -> chunks of 4 / 8 objects."""
+    if n_chunks == 0:
+        monkeypatch.setenv("SIMT_EMUL_SMS", "2" if bounded else "1")
     from epropnp_b200 import native
     from epropnp_b200.synth import make_problem
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)       # no CUDA runtime here

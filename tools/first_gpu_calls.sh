@@ -24,7 +24,7 @@ case "${1:-}" in
         2>&1 | tee gpurun_out/experimental_tests.log | tail -5
     EPNP_BENCH_RSLM=1 EPNP_BENCH_GN_PLUS=1 EPNP_BENCH_MC_EPILOGUE=1 timeout 400 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err
     timeout 120 python tools/pcie_probe.py > gpurun_out/pcie_probe.json 2>&1
-    for c in 4 7 8 14; do
+    for c in 4 7 8 14 0; do     # 0 = automatic: one wave of resident CTAs per chunk
       EPNP_E2E_CHUNKS=$c timeout 200 python bench.py --steps 100 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/e2e_chunks_$c.json
     done
     # two host-buffer calls in flight (double-buffered workspace + results): step i+1 uploads under step i's solve
