@@ -59,3 +59,38 @@ def test_gather_gloo(world, num_obj):
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(r, True) for r in range(world)]
+
+
+def _loss_worker(rank, world, port, q):
+    """Detection flavour of MonteCarloPoseLoss: the EMA norm factor is fed with the MEAN over ranks (mmdet reduce_mean,
+    EPro-PnP-Det/epropnp_det/models/losses/monte_carlo_pose_loss.py:52-55), so every rank holds the same buffer."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "epro-pnp_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from epropnp.monte_carlo_pose_loss import MonteCarloPoseLoss
+        g = torch.Generator().manual_seed(rank)
+        logw, ct = torch.randn(32, 5, generator=g), torch.rand(5, generator=g)
+        mod = MonteCarloPoseLoss(loss_weight=0.15, init_norm_factor=1.0, momentum=0.1, sync_norm_factor=True).train()
+        loss = mod(logw, ct, torch.tensor(float(rank + 1)))
+        expect_nf = 0.9 * 1.0 + 0.1 * (sum(range(1, world + 1)) / world)
+        expect = (ct + torch.logsumexp(logw, dim=0)).mean() * (0.15 / expect_nf)
+        ok = abs(mod.norm_factor.item() - expect_nf) < 1e-6 and abs(loss.item() - expect.item()) < 1e-5
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_loss_norm_factor_is_averaged_over_ranks_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_loss_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(r, True) for r in range(world)]
