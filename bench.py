@@ -41,6 +41,43 @@ E2E_CHUNKS = int(os.environ.get("EPNP_E2E_CHUNKS", "4"))   # object chunks of th
 # triples, so step i+1's upload runs under step i's solve / download (a double-buffered input pipeline).  1 = every
 # step waits for the previous one (the measured round-1 configuration).
 E2E_LANES = max(1, int(os.environ.get("EPNP_E2E_LANES", "1")))
+# EPNP_E2E_NUMA=1: allocate the pinned host buffers while the thread is bound to the CPUs NVML reports as local to the
+# GPU (first touch puts the pages on the GPU's NUMA node; a remote node costs upload bandwidth).  Off = as measured.
+E2E_NUMA = os.environ.get("EPNP_E2E_NUMA", "0") == "1"
+
+
+class gpu_local_cpus:
+    """Context manager: bind the calling thread to the GPU's CPU affinity mask (NVML), restore on exit.  Best effort:
+    any failure (no NVML, restricted cpuset) leaves the affinity untouched; `.applied` says what happened."""
+
+    def __init__(self, index, enabled):
+        self.index, self.enabled, self.applied, self.saved = index, enabled, None, None
+
+    def __enter__(self):
+        if not self.enabled:
+            return self
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+            self.saved = os.sched_getaffinity(0)
+            cpus &= self.saved
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                self.applied = len(cpus)
+        except Exception as exc:                           # noqa: BLE001 -- measurement aid only
+            self.applied = f"unavailable: {type(exc).__name__}"
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except OSError:
+                pass
+        return False
 METRIC = "PnP objects/sec (B=4096,N=512,M=512)"
 
 
@@ -418,8 +455,9 @@ def main():
     # ---- end to end: HOST (pinned) buffers through the C ABI, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        host = {k: pc[k].contiguous().pin_memory() for k in ("x3d", "x2d", "w2d", "cam_mats", "pose_init")}
-        host["delta"] = sets[0]["delta"].cpu().pin_memory()
+        with gpu_local_cpus(local_rank, E2E_NUMA) as numa:
+            host = {k: pc[k].contiguous().pin_memory() for k in ("x3d", "x2d", "w2d", "cam_mats", "pose_init")}
+            host["delta"] = sets[0]["delta"].cpu().pin_memory()
         shift0 = {k: v for k, v in host.items()}
         wss = [torch.empty(native.fused_workspace_bytes(Bg, N_PTS, params), dtype=torch.uint8, device=dev)
                for _ in range(E2E_LANES)]
@@ -454,7 +492,7 @@ def main():
         h2d = sum(host[k].numel() * 4 for k in host)
         d2h = sum(v.numel() * 4 for v in res.values() if v is not None)
         e2e = {"value": B_total * e_steps / (te.item() * 1e-3), "unit": "objects/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": e_steps, "chunks": E2E_CHUNKS, "calls_in_flight": E2E_LANES,
+               "d2h_bytes_per_step": d2h, "steps": e_steps, "chunks": E2E_CHUNKS, "calls_in_flight": E2E_LANES, "host_buffers_on_gpu_numa_node": numa.applied,
                "path": "epnp_lm_amis_fused_host_f32 (pinned host buffers, chunked copy/solve overlap)"}
 
     if rank == 0:

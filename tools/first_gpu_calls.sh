@@ -31,11 +31,14 @@ case "${1:-}" in
     for c in 4 7; do
       EPNP_E2E_LANES=2 EPNP_E2E_CHUNKS=$c timeout 200 python bench.py --steps 100 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/e2e_lanes2_chunks_$c.json
     done
+    # pinned input buffers first-touched on the GPU's NUMA node (upload measured at 40 GB/s in round 1, download 57)
+    EPNP_E2E_NUMA=1 EPNP_E2E_CHUNKS=7 timeout 200 python bench.py --steps 100 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/e2e_numa_chunks_7.json
+    EPNP_E2E_NUMA=1 EPNP_E2E_LANES=2 EPNP_E2E_CHUNKS=7 timeout 200 python bench.py --steps 100 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/e2e_numa_lanes2_chunks_7.json
     python - <<'PY'
 import glob, json
 for f in sorted(glob.glob("gpurun_out/e2e_*.json")):
     try:
-        e = json.load(open(f))["e2e"]; print(f, round(e["value"]), "objects/s", e.get("chunks"), e.get("calls_in_flight"))
+        e = json.load(open(f))["e2e"]; print(f, round(e["value"]), "objects/s", e.get("chunks"), e.get("calls_in_flight"), e.get("host_buffers_on_gpu_numa_node"))
     except Exception as x:
         print(f, "unreadable:", x)
 PY
