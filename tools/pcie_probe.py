@@ -57,6 +57,18 @@ def main():
 
         out["sizes_MB"][mb] = {"h2d_GBps": round(rate(h2d, n), 2), "d2h_GBps": round(rate(d2h, n), 2),
                                "duplex_each_GBps": round(rate(both, n), 2)}
+    # the same copies with the host buffers first-touched on the GPU's NUMA node (bench.py EPNP_E2E_NUMA=1)
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import gpu_local_cpus
+    n = 64 << 20
+    with gpu_local_cpus(0, True) as numa:
+        h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+        h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    out["gpu_numa_local_64MB"] = {"cpus_bound": numa.applied, "cpus_total": os.cpu_count(),
+                                  "h2d_GBps": round(rate(lambda: d.copy_(h_in, non_blocking=True), n), 2),
+                                  "d2h_GBps": round(rate(lambda: h_out.copy_(d, non_blocking=True), n), 2)}
     print(json.dumps(out))
 
 
