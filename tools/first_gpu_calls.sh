@@ -72,6 +72,9 @@ PY
     timeout 300 ncu --set full --clock-control none --import-source on -k regex:solve_kernel -c 1 -o gpurun_out/fused_full \
         python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
     timeout 200 python tools/phase_profile.py 4096 512 512 > gpurun_out/phase_cycles.txt 2>&1; tail -15 gpurun_out/phase_cycles.txt
+    # the other BASELINE configs (LM-only, dense, training step, detection) on the adopted build
+    timeout 400 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err; cut -c1-160 gpurun_out/configs.jsonl
+    # afterwards, in the container:  python tools/ncu_summary.py gpurun_out/fused_full.ncu-rep --tag rN --write-traffic
     python tools/sass_identity.py --write epro-pnp_b200/lib/libepropnp_b200.so > /dev/null && cp profiles/validated_sass.json gpurun_out/
     ;;
   *)
