@@ -283,7 +283,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "nccl-coalesced", "peer"],
                     help="N > 1: 'nccl' = overlapped all_gather_into_tensor (default, the measured configuration); "
                          "'peer' = copy-engine pulls from IPC-mapped peer buffers (sharded.PeerGather, experimental)")
     ap.add_argument("--nccl-max-ctas", type=int, default=0,
@@ -375,7 +375,8 @@ def main():
                     peer_gather = PeerGather(out, B_total, keys=("pose_opt", "logw"), depth=3)
                 pending = peer_gather.start(out)
             else:
-                pending = gather_results_async(out, B_total, keys=("pose_opt", "logw"))
+                pending = gather_results_async(out, B_total, keys=("pose_opt", "logw"),
+                                               coalesce=(args.gather == "nccl-coalesced"))
         return out
 
     def drain():

@@ -62,23 +62,29 @@ class PendingGather:
         return self.tensors
 
 
-def gather_results_async(result, num_obj, keys=("pose_opt", "logw"), group=None):
+def gather_results_async(result, num_obj, keys=("pose_opt", "logw"), group=None, coalesce=False):
     """Same gather, issued asynchronously (equal shards only): NCCL runs it on its own stream after the work
     already enqueued on the current stream, so the NEXT batch's solve overlaps this batch's exchange.  Objects of
-    different batches are independent; nothing inside a solve ever waits for a collective."""
+    different batches are independent; nothing inside a solve ever waits for a collective.
+    coalesce=True hands all keys to the backend as ONE grouped all-gather (one NCCL kernel instead of one per key:
+    fewer CTAs parked on the SMs the next solve wants)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return PendingGather({k: result[k] for k in keys if result.get(k) is not None}, [])
     world = dist.get_world_size(group)
     if len(set(shard_sizes(num_obj, world))) != 1:
         return PendingGather(gather_results(result, num_obj, keys, group), [])
     outs, works = {}, []
-    for k in keys:
-        local = result.get(k)
-        if local is None:
-            continue
-        out = local.new_empty((num_obj,) + tuple(local.shape[1:]))
-        works.append(dist.all_gather_into_tensor(out, local.contiguous(), group=group, async_op=True))
-        outs[k] = out
+    present = [k for k in keys if result.get(k) is not None]
+    for k in present:
+        outs[k] = result[k].new_empty((num_obj,) + tuple(result[k].shape[1:]))
+    if coalesce and len(present) > 1:
+        with dist._coalescing_manager(group=group, async_ops=True) as cm:
+            for k in present:
+                dist.all_gather_into_tensor(outs[k], result[k].contiguous(), group=group)
+        works.append(cm)
+    else:
+        for k in present:
+            works.append(dist.all_gather_into_tensor(outs[k], result[k].contiguous(), group=group, async_op=True))
     return PendingGather(outs, works)
 
 
