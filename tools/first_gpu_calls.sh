@@ -4,7 +4,7 @@
 #
 #   gpurun --timeout 1700 -- 'bash tools/first_gpu_calls.sh variants'        # 1 GPU, ~15 min: bench of every variant, then the parity tests of the faster ones
 #   gpurun --timeout 1300 -- 'bash tools/first_gpu_calls.sh experimental'    # 1 GPU, ~8 min
-#   gpurun --gpus 2 --timeout 700 -- 'bash tools/first_gpu_calls.sh two_gpu' # 2 GPUs, ~6 min (charged x2)
+#   gpurun --gpus 2 --timeout 900 -- 'bash tools/first_gpu_calls.sh two_gpu' # 2 GPUs, ~6 min (charged x2)
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
