@@ -1553,6 +1553,77 @@ __global__ void __launch_bounds__(NT, EPNP_CTAS_PER_SM) solve_kernel(const KArgs
     }
 }
 
+// Fused solve + all-gather over peer memory (multi-GPU, one node).  Same solve as solve_kernel<DOF, true, true>; when an
+// object is finished, its CTA also stores the object's pose and its M log-weights into row (obj_offset + obj) of the
+// full-batch result buffers of up to EPNP_MAX_PEERS other GPUs (pointers into their memory, mapped through CUDA IPC):
+// plain st.global over NVLink, 2 KB + 28 B per object and peer, issued object by object underneath the other CTAs'
+// math.  No gather kernel and no copy afterwards; the caller only needs a rendezvous before reading (sharded.PushGather).
+// The local outputs (a.pose_opt, a.logw) are normally the local slice of this rank's own full-batch buffers.
+constexpr int EPNP_MAX_PEERS = 8;
+struct PushArgs {
+    float* logw[EPNP_MAX_PEERS];            // (B_total, M) on each peer
+    float* pose[EPNP_MAX_PEERS];            // (B_total, D) on each peer
+    int n;
+};
+
+template <int DOF>
+__global__ void __launch_bounds__(NT, EPNP_CTAS_PER_SM) solve_push_kernel(const KArgs a, const PushArgs push) {
+    EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
+    SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
+    float* dyn = reinterpret_cast<float*>(smem_raw);
+    constexpr int PD = Dim<DOF>::POSE;
+#if defined(EPNP_ALIAS_STAGE)
+    const SmemPlan pl = plan_smem<DOF>(a.N, a.p.mc_samples, a.p.mc_iter, true, gridDim.x >= (unsigned)a.B);
+#else
+    const SmemPlan pl = plan_smem<DOF>(a.N, a.p.mc_samples, a.p.mc_iter, true);
+#endif
+    float* pts4 = dyn + pl.pts;
+    const int M = a.p.mc_samples;
+    Loader ld(a, sh.bar, dyn + pl.stage);
+    ld.prologue();
+    for (int it = 0; it < ld.n_my; ++it) {
+        const int obj = (int)blockIdx.x + it * (int)gridDim.x;
+        ld.load_object(it, obj, pts4);
+        const Cam cam = load_cam(a, obj);
+        const float delta = __ldg(a.delta + obj);
+        lm_phase<DOF>(a, sh, pts4, cam, delta, obj, true);
+#if defined(EPNP_SWEEP_MMA)
+        float* ptab = nullptr;
+        if (gridDim.x >= (unsigned)a.B && pl.stage != pl.smp && 12 * (a.p.mc_samples / a.p.mc_iter) <= 2 * STAGE_FLOATS)
+            ptab = dyn + pl.stage;
+#endif
+        if constexpr (DOF == 6)
+            amis_phase6(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.lw, cam, delta, obj,
+                        sh.lm.pose, sh.cov EPNP_PTAB_ARG(ptab));
+        else
+            amis_phase4(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.lw, cam, delta, obj,
+                        sh.lm.pose, sh.cov EPNP_PTAB_ARG(ptab));
+        // ---- push: the object's outputs, as this CTA wrote them, to the same global row on every peer
+        __syncthreads();                                        // the CTA's own global stores are visible to all its threads
+        const size_t row = (size_t)a.obj_offset + (size_t)obj;
+        const float* src = a.logw + (size_t)obj * M;
+        if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+            for (int q = threadIdx.x; q < M / 4; q += NT) {
+                const float4 v = reinterpret_cast<const float4*>(src)[q];
+                for (int r = 0; r < push.n; ++r) {
+                    float* dst = push.logw[r] + row * M;
+                    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) reinterpret_cast<float4*>(dst)[q] = v;
+                    else { dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w; }
+                }
+            }
+        } else {
+            for (int m = threadIdx.x; m < M; m += NT) {
+                const float v = src[m];
+                for (int r = 0; r < push.n; ++r) push.logw[r][row * M + m] = v;
+            }
+        }
+        if (threadIdx.x < PD) {
+            const float v = a.pose_opt[(size_t)obj * PD + threadIdx.x];
+            for (int r = 0; r < push.n; ++r) push.pose[r][row * PD + threadIdx.x] = v;
+        }
+    }
+}
+
 // cost of S poses per object: poses (S, B, D) -> cost (S, B)
 template <int DOF>
 __global__ void __launch_bounds__(NT, 4) cost_kernel(const KArgs a) {
@@ -2072,8 +2143,8 @@ int check_common(const KArgs& a) {
     return EPNP_OK;
 }
 
-template <class Kern>
-int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream, int smem_bytes_single = 0) {
+template <class Kern, class... Extra>
+int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream, int smem_bytes_single = 0, Extra... extra) {
     (void)smem_bytes_single;            // EPNP_ALIAS_STAGE: dynamic shared memory when every CTA solves one object
     if (a.B == 0) return EPNP_OK;
     if ((size_t)smem_bytes > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
@@ -2112,7 +2183,7 @@ int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream, 
 #if defined(EPNP_ALIAS_STAGE)
     if (rounds == 1 && smem_bytes_single > 0) smem_bytes = smem_bytes_single;      // the kernel sees grid == B too
 #endif
-    EPNP_LAUNCH(kern, grid, NT, smem_bytes, stream, a);
+    EPNP_LAUNCH(kern, grid, NT, smem_bytes, stream, a, extra...);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
     return EPNP_OK;
@@ -2399,6 +2470,39 @@ int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d,
                                  (cudaStream_t)stream, plan_smem<6>(N, p->mc_samples, p->mc_iter, true, true).total_bytes);
     return launch_persistent(solve_kernel<4, true, true>, a, plan_smem<4>(N, p->mc_samples, p->mc_iter, true).total_bytes,
                              (cudaStream_t)stream, plan_smem<4>(N, p->mc_samples, p->mc_iter, true, true).total_bytes);
+}
+
+int epnp_lm_amis_fused_push_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                                const float* lb, const float* ub, const float* delta, const float* pose_init,
+                                uint64_t seed, uint32_t obj_offset,
+                                float* pose_opt, float* pose_cov, float* cost, float* pose_samples, float* logw,
+                                float* const* peer_logw, float* const* peer_pose, int n_peers,
+                                int B, int N, const EpnpParams* p, void* stream) {
+    if (!p) return EPNP_ERR_BAD_ARG;
+    if (n_peers < 0 || n_peers > EPNP_MAX_PEERS || (n_peers > 0 && (!peer_logw || !peer_pose))) return EPNP_ERR_BAD_ARG;
+    KArgs a{};
+    a.x3d = x3d; a.x2d = x2d; a.w2d = w2d; a.cam = cam_mats; a.lb = lb; a.ub = ub; a.delta = delta;
+    a.pose_init = pose_init;
+    a.seed = seed; a.obj_offset = obj_offset;
+    a.pose_opt = pose_opt; a.pose_cov = pose_cov; a.cost = cost;
+    a.pose_samples = pose_samples; a.logw = logw; a.B = B; a.N = N; a.p = *p;
+    a.prof = g_prof_buffer;
+    int rc = check_common(a);
+    if (rc != EPNP_OK) return rc;
+    rc = check_amis_params(*p);
+    if (rc != EPNP_OK) return rc;
+    if (!pose_init || !pose_opt || !pose_samples || !logw || p->lm_iter < 0) return EPNP_ERR_BAD_ARG;
+    PushArgs push{};
+    push.n = n_peers;
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peer_logw[r] || !peer_pose[r]) return EPNP_ERR_BAD_ARG;
+        push.logw[r] = peer_logw[r]; push.pose[r] = peer_pose[r];
+    }
+    if (p->dof == 6)
+        return launch_persistent(solve_push_kernel<6>, a, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes,
+                                 (cudaStream_t)stream, plan_smem<6>(N, p->mc_samples, p->mc_iter, true, true).total_bytes, push);
+    return launch_persistent(solve_push_kernel<4>, a, plan_smem<4>(N, p->mc_samples, p->mc_iter, true).total_bytes,
+                             (cudaStream_t)stream, plan_smem<4>(N, p->mc_samples, p->mc_iter, true, true).total_bytes, push);
 }
 
 int epnp_cost_backward_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,

@@ -48,6 +48,8 @@ _SIGNATURES = {
                       + [_I, _I, ctypes.POINTER(EpnpParams), _P]),
     "epnp_lm_amis_fused_f32": (ctypes.c_int, [_P] * 11 + [ctypes.c_uint64, ctypes.c_uint32] + [_P] * 8
                                + [_I, _I, ctypes.POINTER(EpnpParams), _P]),
+    "epnp_lm_amis_fused_push_f32": (ctypes.c_int, [_P] * 8 + [ctypes.c_uint64, ctypes.c_uint32] + [_P] * 5
+                                    + [_P, _P, _I, _I, _I, ctypes.POINTER(EpnpParams), _P]),
     "epnp_cost_backward_f32": (ctypes.c_int, [_P] * 7 + [_P, _P, _I, _P, _P, _I] + [_P] * 4 + [_I, _I, _I, _F, _P]),
     "epnp_mc_epilogue_f32": (ctypes.c_int, [_P] * 8 + [_I, _I, _I, _P]),
     "epnp_mc_lse_backward_f32": (ctypes.c_int, [_P] * 4 + [_I, _I, _P]),

@@ -199,6 +199,43 @@ def lm_amis_fused(prob: Problem, pose_init, params, noise=None, seed=0, obj_offs
     return out
 
 
+def lm_amis_fused_push(prob: Problem, pose_init, params, pose_opt_out, logw_out, peer_logw, peer_pose, seed=0,
+                       obj_offset=0, want_cost=False, want_cov=False):
+    """Fused solve + in-kernel gather (epnp_lm_amis_fused_push_f32).  pose_opt_out (B, D) / logw_out (B, M): where the
+    LOCAL results go (contiguous; normally rows [obj_offset, obj_offset + B) of this rank's own full-batch buffers);
+    peer_logw / peer_pose: lists (<= 8) of full-batch (B_total, M) / (B_total, D) float32 tensors in OTHER GPUs'
+    memory; the kernel writes this rank's rows into each of them.  Returns dict(pose_opt, logw, pose_samples, cost,
+    pose_cov) of local tensors."""
+    D = 7 if params.dof == 6 else 4
+    B, M = prob.B, params.mc_samples
+    if len(peer_logw) != len(peer_pose) or len(peer_logw) > 8:
+        raise ValueError("peer_logw / peer_pose: equally long lists of at most 8 tensors")
+    for t, shape in ((pose_opt_out, (B, D)), (logw_out, (B, M))):
+        if tuple(t.shape) != shape or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"local output must be contiguous float32 {shape}")
+    for lw, ps in zip(peer_logw, peer_pose):
+        if lw.dtype != torch.float32 or ps.dtype != torch.float32 or not lw.is_contiguous() or not ps.is_contiguous() \
+                or lw.dim() != 2 or lw.shape[1] != M or ps.dim() != 2 or ps.shape[1] != D \
+                or lw.shape[0] < obj_offset + B or ps.shape[0] < obj_offset + B:
+            raise ValueError("peer buffers must be contiguous float32 (B_total, M) / (B_total, D) with "
+                             "B_total >= obj_offset + B")
+    pose_init = _f32c(pose_init)
+    out = dict(pose_opt=pose_opt_out, logw=logw_out, pose_samples=prob.empty(B, M, D),
+               cost=prob.empty(B) if want_cost else None,
+               pose_cov=prob.empty(B, params.dof, params.dof) if want_cov else None)
+    n = len(peer_logw)
+    arr_lw = (ctypes.c_void_p * max(n, 1))(*[t.data_ptr() for t in peer_logw])
+    arr_ps = (ctypes.c_void_p * max(n, 1))(*[t.data_ptr() for t in peer_pose])
+    with torch.cuda.device(prob.device):
+        check(lib().epnp_lm_amis_fused_push_f32(*prob.common_ptrs(), ptr(pose_init), ctypes.c_uint64(seed),
+                                                ctypes.c_uint32(obj_offset), ptr(out["pose_opt"]), ptr(out["pose_cov"]),
+                                                ptr(out["cost"]), ptr(out["pose_samples"]), ptr(out["logw"]),
+                                                ctypes.cast(arr_lw, ctypes.c_void_p), ctypes.cast(arr_ps, ctypes.c_void_p), n,
+                                                B, prob.N, ctypes.byref(params), stream_ptr(prob.device)),
+              "epnp_lm_amis_fused_push_f32")
+    return out
+
+
 def cost_backward(prob: Problem, dof, z_min, poses_a, grad_a, poses_b=None, grad_b=None,
                   want=(True, True, True, True)):
     """sum_p grad[p] * d cost(pose p) / d (x3d, x2d, w2d, delta) for object-major pose sets
@@ -302,4 +339,4 @@ def mc_lse_backward(logw_bm, lse, grad_lse):
 
 
 __all__ = ["Problem", "adaptive_delta", "cost_backward", "evaluate_cost", "evaluate_full", "lm_solve", "amis", "lm_amis_fused",
-           "lm_amis_fused_host", "fused_workspace_bytes", "rslm", "gn_plus_backward", "mc_epilogue", "mc_lse_backward", "default_params", "NativeError", "capi"]
+           "lm_amis_fused_host", "lm_amis_fused_push", "fused_workspace_bytes", "rslm", "gn_plus_backward", "mc_epilogue", "mc_lse_backward", "default_params", "NativeError", "capi"]

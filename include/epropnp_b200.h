@@ -155,6 +155,23 @@ int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d,
                            float* cost_init, float* pose_samples, float* logw, float* proposals,
                            int B, int N, const EpnpParams* p, void* stream);
 
+/* Multi-GPU form of epnp_lm_amis_fused_f32 (one process per GPU, one NVLink / NVSwitch node): the solve AND the gather
+ * of its small results in one kernel.  Every CTA, when its object is finished, additionally stores the object's
+ * pose_opt row and its M log-weights into row (obj_offset + b) of `n_peers` (<= 8) full-batch buffers that live in
+ * OTHER GPUs' memory -- peer_logw[r] (B_total, M), peer_pose[r] (B_total, D), device pointers obtained by the caller
+ * through CUDA IPC / peer access -- with plain stores over NVLink, object by object underneath the remaining math.
+ * There is no gather kernel and no copy afterwards (what replaces the NCCL all-gather of SURVEY.md section 8e); the
+ * caller needs one rendezvous of the ranks before it reads its own full-batch buffer.  pose_opt / logw are the LOCAL
+ * outputs as before -- typically the local slice [obj_offset, obj_offset + B) of this rank's own full-batch buffers.
+ * obj_offset doubles as the global object index of the Philox stream, so the assembled batch is bit-identical to the
+ * single-GPU run.  Injected noise, pose_opt_plus, cost_init and proposals are not offered by this entry point. */
+int epnp_lm_amis_fused_push_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                                const float* lb, const float* ub, const float* delta, const float* pose_init,
+                                uint64_t seed, uint32_t obj_offset,
+                                float* pose_opt, float* pose_cov, float* cost, float* pose_samples, float* logw,
+                                float* const* peer_logw, float* const* peer_pose, int n_peers,
+                                int B, int N, const EpnpParams* p, void* stream);
+
 /* Backward of the differentiable outputs of monte_carlo_forward (epropnp.py:108-113: cost_init and the
  * Monte-Carlo costs inside pose_sample_logweights; proposal densities and samples carry no gradient,
  * epropnp.py:139-140,172-179) and of evaluate_pnp(out_cost=True) (common.py:67-100): for every object
