@@ -283,7 +283,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "nccl-coalesced", "peer"],
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "nccl-coalesced", "peer", "push"],
                     help="N > 1: 'nccl' = overlapped all_gather_into_tensor (default, the measured configuration); "
                          "'peer' = copy-engine pulls from IPC-mapped peer buffers (sharded.PeerGather, experimental)")
     ap.add_argument("--nccl-max-ctas", type=int, default=0,
@@ -306,7 +306,7 @@ def main():
 
     import torch.distributed as dist
     from epropnp_b200 import native
-    from epropnp_b200.sharded import PeerGather, gather_results_async
+    from epropnp_b200.sharded import PeerGather, PushGather, gather_results_async
     from epropnp_b200.synth import make_problem
 
     torch.cuda.set_device(local_rank)
@@ -366,6 +366,16 @@ def main():
         previous batch's gather is awaited only after this batch's solve is enqueued, so exchange i overlaps solve
         i+1 (batches are independent); every gather completes inside the timed region (drain() before t_end)."""
         nonlocal pending, peer_gather
+        if world > 1 and args.gather == "push":
+            # fused solve + gather: the kernel stores every finished object's rows into all ranks' result buffers
+            if peer_gather is None:
+                peer_gather = PushGather(B_total, MC_SAMPLES, 7, dev)
+            s = sets[i % ROTATING_SETS]
+            out, nxt = peer_gather.solve(s["prob"], s["pose_init"], params, seed=1234 + i, want_cost=True, want_cov=True)
+            if pending is not None:
+                pending.wait()
+            pending = nxt
+            return out
         out = solve(i)
         if world > 1:
             if pending is not None:
@@ -522,7 +532,8 @@ def main():
                       "peak_warp_instr_per_s": issue_peak, "frac": issue_rate / issue_peak, "sm_mhz_used": clk,
                       "source": "instruction count from the committed ncu capture, time from this run"},
             "clocks": clocks, "gpu_launches": args.steps * world,
-            "kernel": "solve_kernel<6,true,true> (libepropnp_b200.so)",
+            "kernel": ("solve_push_kernel<6>" if (world > 1 and args.gather == "push") else "solve_kernel<6,true,true>")
+                      + " (libepropnp_b200.so)",
         }
         if e2e is not None:
             line["e2e"] = e2e

@@ -172,3 +172,94 @@ class _EventWork:
 
     def wait(self):
         torch.cuda.current_stream().wait_event(self.event)
+
+
+class PushGather:
+    """Fused solve + gather over peer memory (opt-in; equal shards, one NVLink / NVSwitch node, <= 9 ranks).
+
+    There is no gather step at all: every rank keeps a ring of `depth` FULL-batch result buffers (pose_opt
+    (num_obj, D), logw (num_obj, M)), exposed to the other ranks through CUDA IPC once, and the solve kernel itself
+    (native.lm_amis_fused_push -> solve_push_kernel) stores each finished object's rows into slot t mod depth of EVERY
+    rank's ring -- its own slice directly as the kernel's normal output, the peers' with plain stores over NVLink,
+    object by object underneath the remaining CTAs' math.  What is left per batch is one 4-byte all-reduce on a side
+    stream ("all ranks' kernels for batch t have finished, so every row of my slot t is in place").
+
+    Lifetime of results: the tensors a PendingGather of batch t hands out ARE ring slot t mod depth; they stay valid
+    until this rank calls solve() for batch t + valid_for (default: the usual overlapped pattern -- start batch t+1,
+    then wait for and read batch t).  Slot reuse is made safe by making the kernel of batch u wait for the rendezvous
+    of batch u - (depth - valid_for): every rank has by then started batch u - depth + valid_for, i.e. is past its
+    reads of batch u - depth.  depth - valid_for is how many batches the ranks may drift apart (1 = lock step).
+
+    Requires every process to see all GPUs of the node (torchrun's default) with peer access between them.
+    """
+
+    def __init__(self, num_obj, mc_samples, pose_dim, device, depth=4, valid_for=2, group=None):
+        from torch.multiprocessing.reductions import reduce_tensor
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PushGather needs an initialised process group")
+        self.group, self.depth, self.valid_for = group, int(depth), int(valid_for)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if len(set(shard_sizes(num_obj, self.world))) != 1:
+            raise ValueError("PushGather handles equal shards only (use gather_results for ragged batches)")
+        if self.world - 1 > 8:
+            raise ValueError("the kernel pushes to at most 8 peers")
+        if self.valid_for < 1 or self.depth - self.valid_for < 1:
+            raise ValueError("need valid_for >= 1 and depth > valid_for")
+        self.num_obj, self.per_rank = int(num_obj), int(num_obj) // self.world
+        self.device = torch.device(device)
+        self.comm = torch.cuda.Stream(self.device)
+        self.flag = torch.zeros(1, device=self.device)
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
+        self.ring = [dict(pose_opt=new(self.num_obj, pose_dim), logw=new(self.num_obj, mc_samples))
+                     for _ in range(self.depth)]
+        self.probe = torch.zeros(4, dtype=torch.float32, device=self.device)
+        mine = dict(ring=[{k: reduce_tensor(t) for k, t in slot.items()} for slot in self.ring],
+                    probe=reduce_tensor(self.probe))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self.peers = []                       # peers[r][slot][key] -> full-batch tensor in rank r's memory (None = me)
+        scratch = torch.zeros(4, dtype=torch.float32, device=self.device)
+        for r, theirs in enumerate(everyone):
+            if r == self.rank:
+                self.peers.append(None)
+                continue
+            self.peers.append([{k: fn(*a) for k, (fn, a) in slot.items()} for slot in theirs["ring"]])
+            # the kernel dereferences these pointers directly: make torch enable peer access in both directions now
+            # (it does so lazily inside cross-device copies) instead of faulting in the first launch
+            fn, a = theirs["probe"]
+            remote = fn(*a)
+            scratch.copy_(remote)
+            remote.copy_(scratch)
+        torch.cuda.synchronize(self.device)
+        self.met = {}                         # batch index -> event of its rendezvous (last `depth` kept)
+        self.step = 0
+        dist.barrier(group=group)
+
+    def solve(self, prob, pose_init, params, seed=0, want_cost=False, want_cov=False):
+        """Enqueue batch `step`: fused solve with in-kernel push.  Returns (local result dict, PendingGather of the
+        full-batch pose_opt / logw)."""
+        from . import native
+        t = self.step
+        s = t % self.depth
+        lo, hi = self.rank * self.per_rank, (self.rank + 1) * self.per_rank
+        cur = torch.cuda.current_stream(self.device)
+        gate = self.met.get(t - (self.depth - self.valid_for))
+        if gate is not None:
+            cur.wait_event(gate)              # every rank is past its reads of the slot this batch overwrites
+        others = [r for r in range(self.world) if r != self.rank]
+        out = native.lm_amis_fused_push(prob, pose_init, params, self.ring[s]["pose_opt"][lo:hi],
+                                        self.ring[s]["logw"][lo:hi],
+                                        [self.peers[r][s]["logw"] for r in others],
+                                        [self.peers[r][s]["pose_opt"] for r in others],
+                                        seed=seed, obj_offset=lo, want_cost=want_cost, want_cov=want_cov)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ready)
+            dist.all_reduce(self.flag, group=self.group)          # rendezvous: every rank's kernel of batch t is done
+            met = torch.cuda.Event()
+            met.record(self.comm)
+        self.met[t] = met
+        self.met.pop(t - self.depth, None)
+        self.step += 1
+        return out, PendingGather(dict(self.ring[s]), [_EventWork(met)])
