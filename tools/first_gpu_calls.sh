@@ -22,6 +22,9 @@ case "${1:-}" in
     # the two opt-in kernels, their timings, the copy ceiling of the box, the e2e chunk sweep, the tcgen05 probe
     EPNP_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_rslm_fused_gpu.py tests/test_gn_plus_backward_gpu.py tests/test_mc_epilogue_gpu.py -q \
         2>&1 | tee gpurun_out/experimental_tests.log | tail -5
+    # memcheck over the kernels that have never run on hardware (epilogue, push with local stand-in peers)
+    EPNP_SANITIZE_EXPERIMENTAL=1 timeout 300 compute-sanitizer --tool memcheck python tools/sanitize.py 2>&1 \
+        | grep -E "sanitize driver finished|SUMMARY|Error|error" | head -20 | tee gpurun_out/sanitizer_experimental.txt
     EPNP_BENCH_RSLM=1 EPNP_BENCH_GN_PLUS=1 EPNP_BENCH_MC_EPILOGUE=1 timeout 400 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err
     timeout 120 python tools/pcie_probe.py > gpurun_out/pcie_probe.json 2>&1
     for c in 4 7 8 14 0; do     # 0 = automatic: one wave of resident CTAs per chunk
@@ -65,7 +68,13 @@ PY
     # after a variant has been adopted as the default build: the full evidence set again
     #   gpurun --timeout 1500 -- 'bash tools/first_gpu_calls.sh revalidate'
     timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tee gpurun_out/gpu_tests.log | tail -3
-    timeout 300 python tools/sanitize.py > gpurun_out/sanitizer.txt 2>&1; tail -5 gpurun_out/sanitizer.txt
+    : > gpurun_out/sanitizer.txt
+    for tool in memcheck racecheck synccheck initcheck; do
+      echo "== $tool" >> gpurun_out/sanitizer.txt
+      EPNP_SANITIZE_EXPERIMENTAL=1 timeout 400 compute-sanitizer --tool $tool python tools/sanitize.py 2>&1 \
+          | grep -E "sanitize driver finished|SUMMARY|Error|error|hazard" | head -40 >> gpurun_out/sanitizer.txt
+    done
+    cat gpurun_out/sanitizer.txt | cut -c1-200
     timeout 200 python bench.py --steps 400 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench.json; cut -c1-400 gpurun_out/bench.json
     timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
         python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1

@@ -29,6 +29,18 @@ for dof, N, B, bounded in ((6, 64, 5, False), (6, 130, 3, True), (6, 51, 4, Fals
     native.evaluate_full(prob, d["pose_init"], dof, 0.1, 1e-10, True, True, True, True)
     g = native.cost_backward(prob, dof, 0.1, out["pose_samples"], torch.randn(B, 128, device=dev),
                              d["pose_init"].reshape(B, 1, D), torch.randn(B, 1, device=dev))
+    if os.environ.get("EPNP_SANITIZE_EXPERIMENTAL"):       # the kernels that have not had a hardware run yet
+        ep = native.mc_epilogue(out["logw"], out["pose_samples"], out["pose_opt"], cost_target=torch.rand(B, device=dev),
+                                want_lse=True, want_loss=True, want_weights=True, want_score=True)
+        native.mc_lse_backward(out["logw"], ep["lse"], torch.randn(B, device=dev))
+        # push kernel with this device standing in for two "peers" (second copies of the full-batch buffers)
+        full_lw = [torch.zeros(B + 3, 128, device=dev) for _ in range(3)]
+        full_ps = [torch.zeros(B + 3, D, device=dev) for _ in range(3)]
+        native.lm_amis_fused_push(prob, d["pose_init"], p, full_ps[0][2:2 + B], full_lw[0][2:2 + B], full_lw[1:], full_ps[1:],
+                                  seed=1, obj_offset=2, want_cost=True, want_cov=True)
+        torch.cuda.synchronize()
+        assert torch.equal(full_lw[1][2:2 + B], full_lw[0][2:2 + B]) and torch.equal(full_ps[2][2:2 + B], full_ps[0][2:2 + B])
+        assert torch.equal(full_lw[0][2:2 + B], out["logw"]) and not full_lw[1][:2].any() and not full_lw[1][2 + B:].any()
     torch.cuda.synchronize()
     assert torch.isfinite(out["logw"]).all() and all(torch.isfinite(t).all() for t in g)
 print("sanitize driver finished")
