@@ -3,7 +3,7 @@
 # Every step is wrapped in its own timeout and writes under gpurun_out/; run each block as ONE gpurun call:
 #
 #   gpurun --timeout 1700 -- 'bash tools/first_gpu_calls.sh variants'        # 1 GPU, ~15 min: bench of every variant, then the parity tests of the faster ones
-#   gpurun --timeout 1300 -- 'bash tools/first_gpu_calls.sh experimental'    # 1 GPU, ~8 min
+#   gpurun --timeout 1500 -- 'bash tools/first_gpu_calls.sh experimental'    # 1 GPU, ~15 min
 #   gpurun --gpus 2 --timeout 1200 -- 'bash tools/first_gpu_calls.sh two_gpu' # 2 GPUs, ~6 min (charged x2)
 set -u
 cd "$(dirname "$0")/.."
