@@ -167,11 +167,11 @@ class PeerGather:
 
 
 class _EventWork:
-    def __init__(self, event):
-        self.event = event
+    def __init__(self, event, cur_stream=None):
+        self.event, self.cur_stream = event, cur_stream
 
     def wait(self):
-        torch.cuda.current_stream().wait_event(self.event)
+        (self.cur_stream() if self.cur_stream is not None else torch.cuda.current_stream()).wait_event(self.event)
 
 
 class PushGather:
@@ -194,7 +194,6 @@ class PushGather:
     """
 
     def __init__(self, num_obj, mc_samples, pose_dim, device, depth=4, valid_for=2, group=None):
-        from torch.multiprocessing.reductions import reduce_tensor
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("PushGather needs an initialised process group")
         self.group, self.depth, self.valid_for = group, int(depth), int(valid_for)
@@ -207,14 +206,14 @@ class PushGather:
             raise ValueError("need valid_for >= 1 and depth > valid_for")
         self.num_obj, self.per_rank = int(num_obj), int(num_obj) // self.world
         self.device = torch.device(device)
-        self.comm = torch.cuda.Stream(self.device)
+        self.comm = self._new_stream()
         self.flag = torch.zeros(1, device=self.device)
         new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
         self.ring = [dict(pose_opt=new(self.num_obj, pose_dim), logw=new(self.num_obj, mc_samples))
                      for _ in range(self.depth)]
         self.probe = torch.zeros(4, dtype=torch.float32, device=self.device)
-        mine = dict(ring=[{k: reduce_tensor(t) for k, t in slot.items()} for slot in self.ring],
-                    probe=reduce_tensor(self.probe))
+        mine = dict(ring=[{k: self._export(t) for k, t in slot.items()} for slot in self.ring],
+                    probe=self._export(self.probe))
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
         self.peers = []                       # peers[r][slot][key] -> full-batch tensor in rank r's memory (None = me)
@@ -223,14 +222,13 @@ class PushGather:
             if r == self.rank:
                 self.peers.append(None)
                 continue
-            self.peers.append([{k: fn(*a) for k, (fn, a) in slot.items()} for slot in theirs["ring"]])
+            self.peers.append([{k: self._import(h) for k, h in slot.items()} for slot in theirs["ring"]])
             # the kernel dereferences these pointers directly: make torch enable peer access in both directions now
             # (it does so lazily inside cross-device copies) instead of faulting in the first launch
-            fn, a = theirs["probe"]
-            remote = fn(*a)
+            remote = self._import(theirs["probe"])
             scratch.copy_(remote)
             remote.copy_(scratch)
-        torch.cuda.synchronize(self.device)
+        self._device_synchronize()
         self.met = {}                         # batch index -> event of its rendezvous (last `depth` kept)
         self.step = 0
         dist.barrier(group=group)
@@ -242,7 +240,7 @@ class PushGather:
         t = self.step
         s = t % self.depth
         lo, hi = self.rank * self.per_rank, (self.rank + 1) * self.per_rank
-        cur = torch.cuda.current_stream(self.device)
+        cur = self._current_stream()
         gate = self.met.get(t - (self.depth - self.valid_for))
         if gate is not None:
             cur.wait_event(gate)              # every rank is past its reads of the slot this batch overwrites
@@ -252,14 +250,38 @@ class PushGather:
                                         [self.peers[r][s]["logw"] for r in others],
                                         [self.peers[r][s]["pose_opt"] for r in others],
                                         seed=seed, obj_offset=lo, want_cost=want_cost, want_cov=want_cov)
-        ready = torch.cuda.Event()
+        ready = self._new_event()
         ready.record(cur)
-        with torch.cuda.stream(self.comm):
+        with self._on_stream(self.comm):
             self.comm.wait_event(ready)
             dist.all_reduce(self.flag, group=self.group)          # rendezvous: every rank's kernel of batch t is done
-            met = torch.cuda.Event()
+            met = self._new_event()
             met.record(self.comm)
         self.met[t] = met
         self.met.pop(t - self.depth, None)
         self.step += 1
-        return out, PendingGather(dict(self.ring[s]), [_EventWork(met)])
+        return out, PendingGather(dict(self.ring[s]), [_EventWork(met, cur_stream=self._current_stream)])
+
+    # ---- the device-specific pieces (CUDA streams / events, CUDA IPC); the CPU test-suite substitutes host equivalents
+    def _new_stream(self):
+        return torch.cuda.Stream(self.device)
+
+    def _new_event(self):
+        return torch.cuda.Event()
+
+    def _current_stream(self):
+        return torch.cuda.current_stream(self.device)
+
+    def _on_stream(self, stream):
+        return torch.cuda.stream(stream)
+
+    def _device_synchronize(self):
+        torch.cuda.synchronize(self.device)
+
+    def _export(self, t):
+        from torch.multiprocessing.reductions import reduce_tensor
+        return reduce_tensor(t)                 # CUDA IPC handle (+ offset) of a device tensor
+
+    def _import(self, handle):
+        fn, args = handle
+        return fn(*args)

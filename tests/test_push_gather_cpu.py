@@ -74,3 +74,116 @@ def test_push_argument_checks(dev):
     with pytest.raises(ValueError):                                    # more than 8 peers
         native.lm_amis_fused_push(prob, pc["pose_init"], p, torch.empty(4, 7), torch.empty(4, 8),
                                   [torch.empty(4, 8)] * 9, [torch.empty(4, 7)] * 9)
+
+
+# ------------------------------------------------------------------------------------------------
+# sharded.PushGather's protocol (ring slots, row ranges, gates, rendezvous) in two REAL processes over gloo: the kernel
+# runs under the SIMT emulator and the peers' buffers are shared-memory host tensors standing in for CUDA-IPC mappings.
+# Streams and events are inert on the host (everything executes in program order), so this checks the bookkeeping --
+# which slot, which rows, which gate -- not the asynchronous hazards; those need tests/test_push_gather_gpu.py.
+class _HostStream:
+    def wait_event(self, e):
+        pass
+
+    def wait_stream(self, s):
+        pass
+
+
+class _HostEvent:
+    def record(self, stream=None):
+        pass
+
+
+def _host_push_gather_class():
+    import contextlib
+    from torch.multiprocessing.reductions import reduce_storage
+    from epropnp_b200.sharded import PushGather
+
+    class HostPushGather(PushGather):
+        def _new_stream(self):
+            return _HostStream()
+
+        def _new_event(self):
+            return _HostEvent()
+
+        def _current_stream(self):
+            return _HostStream()
+
+        def _on_stream(self, stream):
+            return contextlib.nullcontext()
+
+        def _device_synchronize(self):
+            pass
+
+        # reduce_tensor() of a HOST tensor embeds the storage object (only ForkingPickler shares it); export the
+        # shared-memory file of the storage itself so that all_gather_object's plain pickle carries a real handle
+        def _export(self, t):
+            t.share_memory_()
+            fn, args = reduce_storage(t.untyped_storage())
+            return (fn, args, tuple(t.shape), t.dtype)
+
+        def _import(self, handle):
+            fn, args, shape, dtype = handle
+            return torch.empty(0, dtype=dtype).set_(fn(*args), 0, shape)
+
+    return HostPushGather
+
+
+def _push_worker(rank, world, port, q):
+    import contextlib
+    import os
+    import torch.distributed as dist
+    from epropnp_b200 import capi
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.multiprocessing.set_sharing_strategy("file_system")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        capi._lib = simt_native.handle(())                       # what simt_native.install does, without pytest
+        native._need_cuda = lambda t, what: None
+        native.stream_ptr = lambda device=None: None
+        torch.cuda.device = lambda device=None: contextlib.nullcontext()
+        per, N, M, depth = 3, 16, 8, 3
+        num_obj = per * world
+        p = native.default_params(6, lm_iter=2, mc_samples=M, mc_iter=2)
+        pg = _host_push_gather_class()(num_obj, M, 7, "cpu", depth=depth, valid_for=2)
+        lo, hi = rank * per, (rank + 1) * per
+        ok, pending, expected = True, None, None
+        for step in range(2 * depth + 1):                           # every slot reused twice
+            pc = make_problem(num_obj, N, seed=70 + step)
+            delta = native.adaptive_delta(pc["x2d"], pc["w2d"], 0.5)
+            whole = native.lm_amis_fused(native.Problem(pc["x3d"], pc["x2d"], pc["w2d"], pc["cam_mats"], None, None, delta),
+                                         pc["pose_init"], p, seed=step, want_cov=False, want_cost_init=False)
+            mine = native.Problem(pc["x3d"][lo:hi], pc["x2d"][lo:hi], pc["w2d"][lo:hi], pc["cam_mats"][lo:hi], None, None,
+                                  delta[lo:hi])
+            out, nxt = pg.solve(mine, pc["pose_init"][lo:hi], p, seed=step)
+            ok = ok and torch.equal(out["pose_samples"], whole["pose_samples"][lo:hi])
+            if pending is not None:                                  # read batch t-1 after batch t was started
+                got = pending.wait()
+                ok = ok and torch.equal(got["logw"], expected["logw"]) and torch.equal(got["pose_opt"], expected["pose_opt"])
+            pending, expected = nxt, dict(logw=whole["logw"].clone(), pose_opt=whole["pose_opt"].clone())
+        got = pending.wait()
+        ok = ok and torch.equal(got["logw"], expected["logw"]) and torch.equal(got["pose_opt"], expected["pose_opt"])
+        dist.barrier()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_push_gather_protocol_two_processes_gloo():
+    import socket
+    import torch.multiprocessing as mp
+    simt_native.build_emulated(())                                   # build once, before the workers race for it
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_push_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(results) == [(r, True) for r in range(world)]
