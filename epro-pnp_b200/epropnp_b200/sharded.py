@@ -88,7 +88,38 @@ def gather_results_async(result, num_obj, keys=("pose_opt", "logw"), group=None,
     return PendingGather(outs, works)
 
 
-class PeerGather:
+class _DeviceHooks:
+    """The device-specific pieces of the peer-memory gathers (CUDA streams / events, CUDA IPC).  The CPU test-suite
+    substitutes host equivalents (inert streams, shared-memory tensors) to exercise the bookkeeping over gloo."""
+
+    def _new_stream(self):
+        return torch.cuda.Stream(self.device)
+
+    def _new_event(self):
+        return torch.cuda.Event()
+
+    def _current_stream(self):
+        return torch.cuda.current_stream(self.device)
+
+    def _on_stream(self, stream):
+        return torch.cuda.stream(stream)
+
+    def _device_synchronize(self):
+        torch.cuda.synchronize(self.device)
+
+    def _record_stream(self, tensor, stream):
+        tensor.record_stream(stream)
+
+    def _export(self, t):
+        from torch.multiprocessing.reductions import reduce_tensor
+        return reduce_tensor(t)                 # CUDA IPC handle (+ offset) of a device tensor
+
+    def _import(self, handle):
+        fn, args = handle
+        return fn(*args)
+
+
+class PeerGather(_DeviceHooks):
     """Gather WITHOUT streaming multiprocessors (opt-in; equal shards, one node).
 
     NCCL's all-gather is a kernel: while it moves the (B, M) log-weights it holds SM slots the next batch's solve
@@ -107,7 +138,6 @@ class PeerGather:
 
     def __init__(self, like, num_obj, keys=("pose_opt", "logw"), depth=2, group=None):
         """like: dict of local result tensors (shapes / dtypes of one batch), e.g. one native.lm_amis_fused result."""
-        from torch.multiprocessing.reductions import reduce_tensor
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("PeerGather needs an initialised process group")
         self.group, self.keys, self.depth = group, tuple(k for k in keys if like.get(k) is not None), int(depth)
@@ -118,11 +148,11 @@ class PeerGather:
             raise ValueError("depth >= 2: a slot must survive until the next batch's rendezvous")
         self.num_obj, self.per_rank = int(num_obj), int(num_obj) // self.world
         self.device = like[self.keys[0]].device
-        self.comm = torch.cuda.Stream(self.device)
+        self.comm = self._new_stream()
         self.flag = torch.zeros(1, device=self.device)
         # ring of export buffers, IPC handles exchanged once
         self.export = [{k: torch.empty_like(like[k]).contiguous() for k in self.keys} for _ in range(self.depth)]
-        mine = [{k: reduce_tensor(slot[k]) for k in self.keys} for slot in self.export]
+        mine = [{k: self._export(slot[k]) for k in self.keys} for slot in self.export]
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
         self.peers = []                       # peers[r][slot][key] -> tensor mapped from rank r (None for myself)
@@ -130,7 +160,7 @@ class PeerGather:
             if r == self.rank:
                 self.peers.append(None)
                 continue
-            self.peers.append([{k: fn(*a) for k, (fn, a) in slot.items()} for slot in slots])
+            self.peers.append([{k: self._import(h) for k, h in slot.items()} for slot in slots])
         self.met = [None] * self.depth        # event: rendezvous that retired the previous use of slot s
         self.step = 0
         dist.barrier(group=group)
@@ -138,32 +168,32 @@ class PeerGather:
     def start(self, result):
         """Enqueue the exchange of one batch's local `result`; returns a PendingGather."""
         s = self.step % self.depth
-        cur = torch.cuda.current_stream(self.device)
+        cur = self._current_stream()
         if self.met[s] is not None:
             cur.wait_event(self.met[s])       # every peer has finished pulling the previous content of slot s
         for k in self.keys:
             self.export[s][k].copy_(result[k], non_blocking=True)
-        ready = torch.cuda.Event()
+        ready = self._new_event()
         ready.record(cur)
         outs = {k: result[k].new_empty((self.num_obj,) + tuple(result[k].shape[1:])) for k in self.keys}
-        with torch.cuda.stream(self.comm):
+        with self._on_stream(self.comm):
             self.comm.wait_event(ready)
             dist.all_reduce(self.flag, group=self.group)          # rendezvous: slot s is complete on every rank
-            met = torch.cuda.Event()
+            met = self._new_event()
             met.record(self.comm)
             for r in range(self.world):
                 lo, hi = r * self.per_rank, (r + 1) * self.per_rank
                 for k in self.keys:
                     src = self.export[s][k] if r == self.rank else self.peers[r][s][k]
                     outs[k][lo:hi].copy_(src, non_blocking=True)
-            done = torch.cuda.Event()
+            done = self._new_event()
             done.record(self.comm)
         for k in self.keys:                   # the side stream uses these until `done`
-            outs[k].record_stream(self.comm)
+            self._record_stream(outs[k], self.comm)
         # this rendezvous is stream-ordered after the pulls of the PREVIOUS batch on every rank: it retires that slot
         self.met[(self.step - 1) % self.depth] = met
         self.step += 1
-        return PendingGather(outs, [_EventWork(done)])
+        return PendingGather(outs, [_EventWork(done, cur_stream=self._current_stream)])
 
 
 class _EventWork:
@@ -174,7 +204,7 @@ class _EventWork:
         (self.cur_stream() if self.cur_stream is not None else torch.cuda.current_stream()).wait_event(self.event)
 
 
-class PushGather:
+class PushGather(_DeviceHooks):
     """Fused solve + gather over peer memory (opt-in; equal shards, one NVLink / NVSwitch node, <= 9 ranks).
 
     There is no gather step at all: every rank keeps a ring of `depth` FULL-batch result buffers (pose_opt
@@ -261,27 +291,3 @@ class PushGather:
         self.met.pop(t - self.depth, None)
         self.step += 1
         return out, PendingGather(dict(self.ring[s]), [_EventWork(met, cur_stream=self._current_stream)])
-
-    # ---- the device-specific pieces (CUDA streams / events, CUDA IPC); the CPU test-suite substitutes host equivalents
-    def _new_stream(self):
-        return torch.cuda.Stream(self.device)
-
-    def _new_event(self):
-        return torch.cuda.Event()
-
-    def _current_stream(self):
-        return torch.cuda.current_stream(self.device)
-
-    def _on_stream(self, stream):
-        return torch.cuda.stream(stream)
-
-    def _device_synchronize(self):
-        torch.cuda.synchronize(self.device)
-
-    def _export(self, t):
-        from torch.multiprocessing.reductions import reduce_tensor
-        return reduce_tensor(t)                 # CUDA IPC handle (+ offset) of a device tensor
-
-    def _import(self, handle):
-        fn, args = handle
-        return fn(*args)
