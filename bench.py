@@ -78,6 +78,8 @@ class gpu_local_cpus:
             except OSError:
                 pass
         return False
+
+
 METRIC = "PnP objects/sec (B=4096,N=512,M=512)"
 
 
@@ -310,7 +312,9 @@ def main():
     from epropnp_b200.synth import make_problem
 
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    # EPNP_BENCH_DEVICE exists for tests/test_bench_dryrun_cpu.py, which drives this loop on the SIMT-emulated library;
+    # with the real library anything but "cuda" is refused by the native layer (no CPU path)
+    dev = torch.device(os.environ.get("EPNP_BENCH_DEVICE", "cuda"), local_rank)
     saved_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

@@ -1,0 +1,74 @@
+"""Dry run of bench.py's own arm on the CPU: the real loop (warm-up, timed region, lanes, end-to-end host-buffer section,
+JSON line) driven on the SIMT-emulated library with inert stand-ins for CUDA streams / events, at toy sizes.  It proves
+nothing about speed; it keeps a typo in a rarely used branch of the measurement script from costing a GPU call."""
+import contextlib
+import json
+import sys
+
+import pytest
+import torch
+
+import simt_native
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def wait_stream(self, s):
+        pass
+
+    def wait_event(self, e):
+        pass
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def elapsed_time(self, other):
+        return 1.0
+
+
+def run_bench(monkeypatch, capsys, argv, **module_overrides):
+    import bench
+    simt_native.install(monkeypatch)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: _Stream())
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _Stream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch, "empty", (lambda f: (lambda *a, pin_memory=False, **k: f(*a, **k)))(torch.empty))
+    monkeypatch.setenv("EPNP_BENCH_DEVICE", "cpu")
+    monkeypatch.setenv("EPNP_NO_SAMPLER", "1")
+    for k, v in dict(N_PTS=16, MC_SAMPLES=8, MC_ITER=2, LM_ITER=2, ROTATING_SETS=2, **module_overrides).items():
+        monkeypatch.setattr(bench, k, v)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--batch", "6", "--steps", "3", "--warmup", "3", "--no-cpu-baseline"] + argv)
+    bench.main()
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, "exactly one JSON line on stdout"
+    return json.loads(lines[0])
+
+
+CONTRACT = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "roofline", "clocks", "gpu_launches", "e2e")
+
+
+@pytest.mark.parametrize("argv,overrides", [([], {}), (["--streams", "2"], {}), ([], {"E2E_LANES": 2, "E2E_CHUNKS": 0}),
+                                            (["--no-e2e"], {})])
+def test_bench_loop_runs_and_prints_the_contract_line(monkeypatch, capsys, argv, overrides):
+    line = run_bench(monkeypatch, capsys, argv, **overrides)
+    for k in CONTRACT:
+        if k == "e2e" and "--no-e2e" in argv:
+            continue
+        assert k in line, k
+    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["gpu_launches"] == 3 and line["value"] > 0
+    assert line["config"]["batches_in_flight"] == (2 if "--streams" in argv else 1)
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    if "--no-e2e" not in argv:
+        e = line["e2e"]
+        assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] > 0
+        assert e["calls_in_flight"] == overrides.get("E2E_LANES", 1)
