@@ -72,3 +72,32 @@ def test_bench_loop_runs_and_prints_the_contract_line(monkeypatch, capsys, argv,
         e = line["e2e"]
         assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] > 0
         assert e["calls_in_flight"] == overrides.get("E2E_LANES", 1)
+
+
+@pytest.mark.parametrize("flags", [["--gather", "nccl"], ["--gather", "nccl-coalesced"], ["--gather", "peer"],
+                                   ["--gather", "push"], ["--gather", "push", "--streams", "2"]])
+def test_two_rank_bench_loop_over_gloo(flags):
+    """bench.py --gpus 2 as torchrun would start it, on the CPU: gloo instead of NCCL, shared-memory host tensors instead
+    of CUDA IPC (tests/bench_dryrun_worker.py).  Rank 0 must print the one JSON line; every rank must exit 0."""
+    import os
+    import socket
+    import subprocess
+    simt_native.build_emulated(())
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    here = os.path.dirname(os.path.abspath(__file__))
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(here, "bench_dryrun_worker.py"), "--gpus", "2"] + flags,
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (out, err) in zip(procs, outs):
+        assert p.returncode == 0, err[-3000:]
+    lines = [l for l in outs[0][0].splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and not [l for l in outs[1][0].splitlines() if l.startswith("{")]
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["config"]["global_batch"] == 8 and line["gpu_launches"] == 10
+    assert flags[1] in line["config"]["parallelism"]
