@@ -101,3 +101,27 @@ def test_two_rank_bench_loop_over_gloo(flags):
     line = json.loads(lines[0])
     assert line["n_gpus"] == 2 and line["config"]["global_batch"] == 8 and line["gpu_launches"] == 10
     assert flags[1] in line["config"]["parallelism"]
+
+
+def test_bench_configs_script_runs_in_toy_mode(monkeypatch, capsys):
+    """tools/bench_configs.py with every optional section switched on, at toy sizes on the emulated library."""
+    import importlib.util
+    import os
+    simt_native.install(monkeypatch)
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    for k in ("EPNP_BENCH_CONFIGS_TOY", "EPNP_BENCH_RSLM", "EPNP_BENCH_GN_PLUS", "EPNP_BENCH_MC_EPILOGUE"):
+        monkeypatch.setenv(k, "1")
+    monkeypatch.setenv("EPNP_BENCH_DEVICE", "cpu")
+    from epropnp import monte_carlo_pose_loss as mcl
+    monkeypatch.setattr(mcl, "_use_native", lambda t: os.environ.get("EPNP_NATIVE_MC_EPILOGUE", "0") == "1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_configs_toy", os.path.join(root, "tools", "bench_configs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()
+    rows = [json.loads(l) for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    names = " | ".join(r["config"] for r in rows)
+    for needle in ("#2 LM", "#3 LM", "#4 dense", "Det:", "training step", "evaluate_pnp cost", "RSLM init", "pose_opt_plus",
+                   "MC pose loss"):
+        assert needle in names, needle
+    assert all(v > 0 for r in rows for k, v in r.items() if k.startswith("ms"))
