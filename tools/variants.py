@@ -138,6 +138,10 @@ def cmd_run(args):
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     out_path = os.path.join(REPO, "gpurun_out", "variants.jsonl")
     B.build_library()
+    # anything missing or stale (e.g. the snapshot did not keep mtimes) is rebuilt side by side, not one per variant later
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(len(names), (os.cpu_count() or 2)))) as pool:
+        list(pool.map(build_variant, names))
     keep = B.LIB_PATH + ".default_build"
     shutil.copy(B.LIB_PATH, keep)
     env = dict(os.environ, PYTHONPATH=os.path.join(REPO, "epro-pnp_b200") + os.pathsep + os.environ.get("PYTHONPATH", ""))
