@@ -41,6 +41,7 @@ E2E_CHUNKS = int(os.environ.get("EPNP_E2E_CHUNKS", "4"))   # object chunks of th
 # triples, so step i+1's upload runs under step i's solve / download (a double-buffered input pipeline).  1 = every
 # step waits for the previous one (the measured round-1 configuration).
 E2E_LANES = max(1, int(os.environ.get("EPNP_E2E_LANES", "1")))
+WARM_SECONDS = 0.5            # minimum duration of back-to-back warm-up launches before the timed region
 # EPNP_E2E_NUMA=1: allocate the pinned host buffers while the thread is bound to the CPUs NVML reports as local to the
 # GPU (first touch puts the pages on the GPU's NUMA node; a remote node costs upload bandwidth).  Off = as measured.
 E2E_NUMA = os.environ.get("EPNP_E2E_NUMA", "0") == "1"
@@ -413,8 +414,8 @@ def main():
         sampler.wait_ready()
     # warm-up: at least W steps AND at least ~0.5 s of back-to-back launches -- the first ~100 ms after an idle
     # period run measurably slower (power-state ramp), which W = 3 steps of 1.5 ms do not cover
-    t_warm = time.time()
-    n_warm = 0
+    t_warm = None                # the 0.5 s start counting after the first chunk: it holds the one-off costs (module load,
+    n_warm = 0                   # NCCL communicator / IPC set-up -- seconds at N > 1), which are not back-to-back launches
     out = None
     while True:
         out = step(n_warm)       # same liveness pattern as the timed loop (previous outputs alive while the next are
@@ -423,7 +424,9 @@ def main():
             torch.cuda.synchronize()
             # the stop decision must be COLLECTIVE: every rank has to run the same number of steps (= the same number
             # of gathers); ranks deciding on their own wall clocks deadlock the next collective
-            flag = torch.tensor([1.0 if (n_warm >= args.warmup and time.time() - t_warm >= 0.5) else 0.0], device=dev)
+            if t_warm is None:
+                t_warm = time.time()
+            flag = torch.tensor([1.0 if (n_warm >= args.warmup and time.time() - t_warm >= WARM_SECONDS) else 0.0], device=dev)
             if world > 1:
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if flag.item() > 0.5:

@@ -39,7 +39,7 @@ def main():
     sharded.PushGather = _host_class(sharded.PushGather)
     os.environ.update(EPNP_BENCH_DEVICE="cpu", EPNP_NO_SAMPLER="1", LOCAL_RANK="0")
     import bench
-    for k, v in dict(N_PTS=16, MC_SAMPLES=8, MC_ITER=2, LM_ITER=2, ROTATING_SETS=2).items():
+    for k, v in dict(N_PTS=16, MC_SAMPLES=8, MC_ITER=2, LM_ITER=2, ROTATING_SETS=2, WARM_SECONDS=0.05).items():
         setattr(bench, k, v)
     sys.argv = ["bench.py", "--batch", "4", "--steps", "5", "--warmup", "3", "--no-cpu-baseline", "--no-e2e"] + sys.argv[1:]
     bench.main()

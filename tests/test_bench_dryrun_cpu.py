@@ -44,7 +44,7 @@ def run_bench(monkeypatch, capsys, argv, **module_overrides):
     monkeypatch.setattr(torch, "empty", (lambda f: (lambda *a, pin_memory=False, **k: f(*a, **k)))(torch.empty))
     monkeypatch.setenv("EPNP_BENCH_DEVICE", "cpu")
     monkeypatch.setenv("EPNP_NO_SAMPLER", "1")
-    for k, v in dict(N_PTS=16, MC_SAMPLES=8, MC_ITER=2, LM_ITER=2, ROTATING_SETS=2, **module_overrides).items():
+    for k, v in dict(N_PTS=16, MC_SAMPLES=8, MC_ITER=2, LM_ITER=2, ROTATING_SETS=2, WARM_SECONDS=0.05, **module_overrides).items():
         monkeypatch.setattr(bench, k, v)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--batch", "6", "--steps", "3", "--warmup", "3", "--no-cpu-baseline"] + argv)
     bench.main()
