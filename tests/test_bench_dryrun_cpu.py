@@ -125,3 +125,26 @@ def test_bench_configs_script_runs_in_toy_mode(monkeypatch, capsys):
                    "MC pose loss"):
         assert needle in names, needle
     assert all(v > 0 for r in rows for k, v in r.items() if k.startswith("ms"))
+
+
+def test_graft_entry_smoke_runs_on_the_emulated_library(monkeypatch, capsys):
+    """__graft_entry__.smoke() (the driver's round-end check on cuda:0) executed unchanged, with the emulated library
+    and `cuda:0` mapped to the host: its own assertions against the fp64 oracle must hold."""
+    import __graft_entry__ as entry
+    simt_native.install(monkeypatch)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    real_device = torch.device
+
+    class _Dev:
+        def __call__(self, *a, **k):
+            return real_device("cpu") if a and str(a[0]).startswith("cuda") else real_device(*a, **k)
+
+        def __instancecheck__(self, obj):
+            return isinstance(obj, real_device)
+    import torch as _t
+    monkeypatch.setattr(_t, "device", _Dev())
+    try:
+        entry.smoke()
+    finally:
+        monkeypatch.undo()
+    assert "smoke:" in capsys.readouterr().out
