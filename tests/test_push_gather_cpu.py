@@ -245,3 +245,32 @@ def test_peer_gather_protocol_two_processes_gloo():
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(results) == [(r, True) for r in range(world)]
+
+
+def test_push_and_epilogue_do_not_depend_on_thread_schedule(dev):
+    """Missing-barrier probe (as tests/test_simt_emul_cpu.py does for the validated kernels): the fibers of a CTA run in
+    descending and randomly permuted order; the pushed rows and the epilogue outputs must stay bit-identical."""
+    lib = simt_native.handle(())
+    pc = make_problem(5, 37, seed=12)
+    M = 16
+    p = native.default_params(6, lm_iter=3, mc_samples=M, mc_iter=2)
+    delta = native.adaptive_delta(pc["x2d"], pc["w2d"], 0.5)
+    prob = native.Problem(pc["x3d"], pc["x2d"], pc["w2d"], pc["cam_mats"], None, None, delta)
+
+    def run():
+        peers_lw, peers_ps = [torch.zeros(7, M) for _ in range(2)], [torch.zeros(7, 7) for _ in range(2)]
+        out = native.lm_amis_fused_push(prob, pc["pose_init"], p, torch.empty(5, 7), torch.empty(5, M), peers_lw, peers_ps,
+                                        seed=3, obj_offset=2)
+        ep = native.mc_epilogue(out["logw"], out["pose_samples"], out["pose_opt"], cost_target=torch.ones(5),
+                                want_lse=True, want_loss=True, want_weights=True, want_score=True)
+        g = native.mc_lse_backward(out["logw"], ep["lse"], torch.ones(5))
+        return peers_lw + peers_ps + [out["logw"], out["pose_opt"], ep["lse"], ep["loss"], ep["weights"], ep["score_te"], g]
+    try:
+        lib.simt_set_schedule(0, 1)
+        base = run()
+        for mode, seed in ((1, 1), (2, 11), (2, 12)):
+            lib.simt_set_schedule(mode, seed)
+            for a, b in zip(base, run()):
+                assert torch.equal(a, b), (mode, seed)
+    finally:
+        lib.simt_set_schedule(0, 1)
