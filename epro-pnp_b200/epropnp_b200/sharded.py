@@ -223,9 +223,12 @@ class PushGather(_DeviceHooks):
     Requires every process to see all GPUs of the node (torchrun's default) with peer access between them.
     """
 
-    def __init__(self, num_obj, mc_samples, pose_dim, device, depth=4, valid_for=2, group=None):
+    def __init__(self, num_obj, mc_samples, pose_dim, device, depth=4, valid_for=2, group=None, copy_out=False):
+        """copy_out=True hands out private copies of the full-batch tensors (one device-to-device copy per batch on the
+        side stream) instead of views of the ring, for callers that keep results longer than `valid_for` batches."""
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("PushGather needs an initialised process group")
+        self.copy_out = bool(copy_out)
         self.group, self.depth, self.valid_for = group, int(depth), int(valid_for)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if len(set(shard_sizes(num_obj, self.world))) != 1:
@@ -287,7 +290,15 @@ class PushGather(_DeviceHooks):
             dist.all_reduce(self.flag, group=self.group)          # rendezvous: every rank's kernel of batch t is done
             met = self._new_event()
             met.record(self.comm)
+            full, done = dict(self.ring[s]), met
+            if self.copy_out:
+                full = {k: torch.empty_like(v) for k, v in self.ring[s].items()}
+                for k, v in self.ring[s].items():
+                    full[k].copy_(v, non_blocking=True)
+                    self._record_stream(full[k], self.comm)
+                done = self._new_event()
+                done.record(self.comm)
         self.met[t] = met
         self.met.pop(t - self.depth, None)
         self.step += 1
-        return out, PendingGather(dict(self.ring[s]), [_EventWork(met, cur_stream=self._current_stream)])
+        return out, PendingGather(full, [_EventWork(done, cur_stream=self._current_stream)])

@@ -152,7 +152,7 @@ def _push_worker(rank, world, port, q):
         per, N, M, depth = 3, 16, 8, 3
         num_obj = per * world
         p = native.default_params(6, lm_iter=2, mc_samples=M, mc_iter=2)
-        pg = _host_push_gather_class()(num_obj, M, 7, "cpu", depth=depth, valid_for=2)
+        pg = _host_push_gather_class()(num_obj, M, 7, "cpu", depth=depth, valid_for=2, copy_out=bool(rank))  # both forms
         lo, hi = rank * per, (rank + 1) * per
         ok, pending, expected = True, None, None
         for step in range(2 * depth + 1):                           # every slot reused twice
