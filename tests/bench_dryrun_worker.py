@@ -41,7 +41,7 @@ def main():
     import bench
     for k, v in dict(N_PTS=16, MC_SAMPLES=8, MC_ITER=2, LM_ITER=2, ROTATING_SETS=2, WARM_SECONDS=0.05).items():
         setattr(bench, k, v)
-    sys.argv = ["bench.py", "--batch", "4", "--steps", "5", "--warmup", "3", "--no-cpu-baseline", "--no-e2e"] + sys.argv[1:]
+    sys.argv = ["bench.py", "--batch", "2", "--steps", "5", "--warmup", "3", "--no-cpu-baseline", "--no-e2e"] + sys.argv[1:]
     bench.main()
     if dist.is_initialized():
         dist.destroy_process_group()

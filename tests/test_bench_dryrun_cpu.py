@@ -46,7 +46,7 @@ def run_bench(monkeypatch, capsys, argv, **module_overrides):
     monkeypatch.setenv("EPNP_NO_SAMPLER", "1")
     for k, v in dict(N_PTS=16, MC_SAMPLES=8, MC_ITER=2, LM_ITER=2, ROTATING_SETS=2, WARM_SECONDS=0.05, **module_overrides).items():
         monkeypatch.setattr(bench, k, v)
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--batch", "6", "--steps", "3", "--warmup", "3", "--no-cpu-baseline"] + argv)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--batch", "2", "--steps", "3", "--warmup", "3", "--no-cpu-baseline"] + argv)
     bench.main()
     lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
     assert len(lines) == 1, "exactly one JSON line on stdout"
@@ -99,7 +99,7 @@ def test_two_rank_bench_loop_over_gloo(flags):
     lines = [l for l in outs[0][0].splitlines() if l.startswith("{")]
     assert len(lines) == 1 and not [l for l in outs[1][0].splitlines() if l.startswith("{")]
     line = json.loads(lines[0])
-    assert line["n_gpus"] == 2 and line["config"]["global_batch"] == 8 and line["gpu_launches"] == 10
+    assert line["n_gpus"] == 2 and line["config"]["global_batch"] == 4 and line["gpu_launches"] == 10
     assert flags[1] in line["config"]["parallelism"]
 
 
