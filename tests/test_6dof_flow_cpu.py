@@ -95,3 +95,26 @@ def test_demo_training_loop_runs(dev, monkeypatch, fused_rslm):
     out = fit_identity.run(steps=3, batch_size=4, verbose=False, device=dev, test_size=4)
     assert out["finite"] and out["steps"] == 3
     assert all(math.isfinite(out[k]) for k in ("loss_mc_first", "loss_mc_last", "test_t_err_before", "test_t_err_after"))
+
+
+def test_demo_training_loop_with_every_opt_in_kernel(dev, monkeypatch):
+    """The same loop with all three opt-in kernels switched on at once (fused RSLM initialiser, native pose_opt_plus
+    backward, native Monte-Carlo loss epilogue through the package's MonteCarloPoseLoss): what the defaults become once
+    those kernels have had their hardware run.  Gradients and losses must stay finite and close to the default path."""
+    import os
+    import sys
+    from conftest import ROOT
+    from epropnp import monte_carlo_pose_loss as mcl
+    sys.path.insert(0, os.path.join(ROOT, "demo"))
+    import fit_identity
+    monkeypatch.setenv("EPNP_FUSED_RSLM", "1")     # (the unfused initialiser spends a minute emulating 8-point CTAs)
+    base = fit_identity.run(steps=2, batch_size=4, verbose=False, device=dev, test_size=4, seed=3)
+    for k in ("EPNP_NATIVE_GN_STEP", "EPNP_NATIVE_MC_EPILOGUE"):
+        monkeypatch.setenv(k, "1")
+    monkeypatch.setattr(mcl, "_use_native", lambda t: True)
+    monkeypatch.setattr(fit_identity, "MonteCarloPoseLoss", lambda: mcl.MonteCarloPoseLoss(momentum=0.1))
+    out = fit_identity.run(steps=2, batch_size=4, verbose=False, device=dev, test_size=4, seed=3)
+    assert out["finite"] and out["steps"] == 2
+    assert math.isfinite(out["loss_mc_first"]) and math.isfinite(out["loss_mc_last"])
+    # first step: same weights, same data, same seeds -> the Monte-Carlo loss agrees to fp32 noise
+    assert abs(out["loss_mc_first"] - base["loss_mc_first"]) < 1e-3 * max(1.0, abs(base["loss_mc_first"]))
