@@ -48,6 +48,13 @@ def test_inference_sequence(dev, monkeypatch, fused_rslm):
     weights = logw.softmax(dim=0)                                                 # head: score from sample spread
     dev_te = (samples[..., [0, 2]] - pose_opt[:, [0, 2]]).norm(dim=-1)
     assert torch.isfinite((dev_te * weights).sum(dim=0)).all()
+    # the head's Monte-Carlo score (deform_pnp_head.py:533-536) through the package: torch composite == native epilogue
+    from epropnp import monte_carlo_pose_loss as mcl
+    score_ref = (((-dev_te.log2() + 2.5) / 4).clamp(min=0, max=1) * weights).sum(dim=0)
+    assert torch.allclose(mcl.mc_score_te(samples, pose_opt, logw), score_ref, atol=1e-6)
+    monkeypatch.setattr(mcl, "_use_native", lambda t: True)
+    assert torch.allclose(mcl.mc_score_te(samples, pose_opt, logw), score_ref, atol=2e-6)
+    assert torch.allclose(mcl.mc_sample_weights(logw), weights, atol=1e-6)
     # with 8 random-sample proposals most objects land on the ground truth
     good = ((pose_opt[:, :3] - gt[:, :3]).norm(dim=-1) < 0.2).float().mean()
     assert good >= 2 / 3
