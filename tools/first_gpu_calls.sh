@@ -57,7 +57,7 @@ PY
   two_gpu)
     EPNP_TEST_PEER_GATHER=1 timeout 300 python -m pytest tests/test_peer_gather_gpu.py tests/test_push_gather_gpu.py -q 2>&1 | tee gpurun_out/peer_gather_test.log | tail -3
     i=0
-    for g in "--gather nccl" "--gather nccl-coalesced" "--gather nccl --nccl-max-ctas 2" "--gather peer" "--gather push" "--gather nccl --streams 2" "--gather peer --streams 2"; do
+    for g in "--gather nccl" "--gather nccl-coalesced" "--gather nccl --nccl-max-ctas 2" "--gather nccl --nccl-max-ctas 8" "--gather peer" "--gather push" "--gather nccl --streams 2" "--gather peer --streams 2"; do
       i=$((i + 1))
       timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$i \
           bench.py --gpus 2 --steps 300 --warmup 5 $g --no-cpu-baseline --no-e2e 2> gpurun_out/two_gpu_$i.err | tail -1 > gpurun_out/two_gpu_$i.json
