@@ -71,6 +71,16 @@ EXPERIMENTS = {
                             "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE"],
     "everything": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
                    "-DEPNP_FAST_BLOCKSUM"],
+    # round-2 call 2: the measured winners without the (measured slower) cost-first LM, with / without the packed LM evaluation
+    "six_hm_nocf": ["-DEPNP_LM_NOREFINE", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW",
+                    "-DEPNP_SWEEP_HUBER_M", "-DEPNP_CTAS_PER_SM=6"],
+    "six_hm_nocf_packed": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_PACKED", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE",
+                           "-DEPNP_NO_LW", "-DEPNP_SWEEP_HUBER_M", "-DEPNP_CTAS_PER_SM=6"],
+    "five_hm_nocf": ["-DEPNP_LM_NOREFINE", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE",
+                     "-DEPNP_SWEEP_HUBER_M", "-DEPNP_CTAS_PER_SM=5"],
+    "five_hm_nocf_packed": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_PACKED", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE",
+                            "-DEPNP_SWEEP_HUBER_M", "-DEPNP_CTAS_PER_SM=5"],
+    "four_hm_nocf_packed": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_PACKED", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_SWEEP_HUBER_M"],
     "all_norefine": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
 }
 

@@ -21,6 +21,7 @@ Reference map (file:line under /root/reference/epropnp/):
     lm_solve (LM + GN fast mode)           levenberg_marquardt.py:80-241
     gn_step / pose_add                     levenberg_marquardt.py:243-265
     normalize / denormalize                common.py:103-136
+    center_based_init / rslm_solve / select_start   levenberg_marquardt.py:283-353, 115-130
     robust_cholesky                        epropnp.py:16-33
     amis_6dof (initial fit, mixture, refit) epropnp.py:87-196, 282-342
     amis_4dof (von Mises / uniform yaw)     epropnp.py:199-260; distributions.py:55-79; torch VonMises
@@ -237,6 +238,45 @@ def gn_step(x3d, x2d, w2d, cam: Camera, delta, pose, eps=1e-5):
     jtj, g = _normal_eq(e)
     jtj = jtj + eps * torch.eye(jtj.shape[-1], dtype=jtj.dtype)
     return -torch.linalg.solve(jtj, g)
+
+
+# ----------------------------------------------------------------------------- random-sample LM initialiser
+def center_based_init(x2d, x3d, cam: Camera, dof, eps=1e-6):
+    """Translation guess from the spread of the back-projected 2D points against the spread of the 3D points
+    (levenberg_marquardt.py:283-298)."""
+    homo = torch.cat((x2d, torch.ones_like(x2d[..., :1])), dim=-1)
+    rays = torch.linalg.solve(cam.cam_mats, homo.transpose(-1, -2)).transpose(-1, -2)
+    rays = rays[..., :2] / rays[..., 2:].clamp(min=eps)
+    r_std, r_mean = rays.std(dim=-2), rays.mean(dim=-2)
+    o_std = x3d.std(dim=-2)
+    if dof == 4:
+        depth = o_std[..., 1] / r_std[..., 1].clamp(min=eps)
+    else:
+        depth = math.sqrt(2 / 3) * o_std.norm(dim=-1) / r_std.norm(dim=-1).clamp(min=eps)
+    return torch.cat((r_mean, torch.ones_like(r_mean[..., :1])), dim=-1) * depth[..., None]
+
+
+def rslm_solve(x3d, x2d, w2d, cam: Camera, delta, inds, start, prm: LMParams = LMParams(num_iter=3), fast_mode=False):
+    """RSLMSolver.solve (levenberg_marquardt.py:300-353) with the random draws passed in: `inds` (P, B, n) are the
+    sampled correspondences of every hypothesis, `start` (P, B, D) the starting poses.  Every hypothesis is an
+    LM / GN solve of its n-point mini-problem, scored on the full set; the cheapest wins per object.
+    Returns dict(hyp_pose (P,B,D), hyp_cost (P,B), pose (B,D), cost (B), winner (B))."""
+    P, B, n = inds.shape
+    idx = inds.long()[..., None]                                              # (P, B, n, 1)
+    gather = lambda t: torch.gather(t[None].expand(P, *t.shape), 2, idx.expand(P, B, n, t.shape[-1])).reshape(P * B, n, -1)
+    rep = lambda t: t if not torch.is_tensor(t) or t.dim() == 0 else t[None].expand(P, *t.shape).reshape(P * B, *t.shape[1:])
+    cam_p = Camera(rep(cam.cam_mats), cam.z_min, rep(cam.lb), rep(cam.ub))
+    pose, _, _ = lm_solve(gather(x3d), gather(x2d), gather(w2d), cam_p, rep(delta), start.reshape(P * B, -1), prm,
+                          fast_mode=fast_mode)
+    pose = pose.reshape(P, B, -1)
+    cost = evaluate(x3d, x2d, w2d, pose, cam, delta)["cost"]                 # (P, B)
+    min_cost, winner = cost.min(dim=0)
+    return dict(hyp_pose=pose, hyp_cost=cost, pose=pose[winner, torch.arange(B)], cost=min_cost, winner=winner)
+
+
+def select_start(pose_init, cost_init, pose_rs, cost_rs):
+    """force_init_solve (levenberg_marquardt.py:120-128): keep pose_init where it is strictly cheaper."""
+    return torch.where((cost_init < cost_rs)[:, None], pose_init, pose_rs)
 
 
 # ----------------------------------------------------------------------------- small linear algebra

@@ -45,6 +45,44 @@ def err_vs(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def err_stats(a, b):
+    """Measured error of `a` against the reference `b`: scale-relative max (the "rel" of BASELINE.json), absolute max
+    and absolute p50 / p99, plus the scale they are relative to."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    d = np.abs(a - b).ravel()
+    scale = float(max(np.abs(b).max(), 1e-30)) if b.size else 1.0
+    if d.size == 0:
+        return dict(rel_max=0.0, abs_max=0.0, abs_p50=0.0, abs_p99=0.0, scale=scale, n=0)
+    return dict(rel_max=float(d.max() / scale), abs_max=float(d.max()), abs_p50=float(np.percentile(d, 50)),
+                abs_p99=float(np.percentile(d, 99)), scale=scale, n=int(d.size))
+
+
+# Measured parity numbers of the GPU suite: every `-m gpu` parity test records what it measured (not just pass / fail);
+# the session writes them to gpurun_out/parity_r2.json (EPNP_PARITY_OUT overrides), which is copied to profiles/.
+_PARITY = {}
+
+
+def record_parity(case, **metrics):
+    _PARITY.setdefault(case, {}).update(metrics)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _PARITY:
+        return
+    import json
+    path = os.environ.get("EPNP_PARITY_OUT", os.path.join(ROOT, "gpurun_out", "parity_r2.json"))
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    merged = {}
+    if os.path.exists(path):
+        try:
+            merged = json.load(open(path))
+        except Exception:
+            merged = {}
+    merged.update(_PARITY)
+    with open(path, "w") as f:
+        json.dump(merged, f, indent=1, sort_keys=True)
+
+
 def assert_lm_parity(pose, cost, ref_pose, ref_cost, tol, max_flip_frac=0.5, what=""):
     """LM parity per object.  A fixed-iteration trust-region solve is path dependent: an accept/reject
     decision that sits inside fp32 noise (levenberg_marquardt.py:228) sends it to a different point of a

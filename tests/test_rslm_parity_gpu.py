@@ -1,0 +1,139 @@
+"""RSLMSolver parity on the GPU against golden vectors of the UNMODIFIED reference (tests/golden/rslm/*.npz from
+oracle/make_golden_rslm.py: levenberg_marquardt.py:268-353 and the force_init_solve selection :115-130, with the
+reference's torch.multinomial / randn / rand draws taped).  The same draws go into
+
+  * the single-launch initialiser  epnp_rslm_f32          (one CTA per object, thread <-> hypothesis),
+  * the unfused path               gathered mini-problems -> epnp_lm_solve_f32 -> epnp_evaluate_cost_f32,
+  * the drop-in classes            RSLMSolver.solve and LMSolver.solve(force_init_solve=True), draws played back.
+
+A hypothesis starts from a RANDOM orientation and runs 3 LM iterations on 8-16 points: its trajectory is chaotic, and
+an accept / reject decision inside fp32 noise sends it elsewhere (the reference's own fp32 run leaves its fp64 run on a
+few hypotheses, `floor` below).  So the per-hypothesis bound is a quantile statement; the per-OBJECT result (winner
+pose, minimum cost) must match to 1e-4 or be cost-equivalent.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import err_stats, err_vs, record_parity
+from epropnp.camera import PerspectiveCamera
+from epropnp.cost_fun import AdaptiveHuberPnPCost
+from epropnp.levenberg_marquardt import LMSolver, RSLMSolver
+from epropnp_b200 import native
+from test_oracle_rslm_cpu import RSLM_CASES, load_rslm
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(g, dev):
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    lb = ub = None
+    if int(g["bounds"]) == 2:
+        lb, ub = t("lb"), t("ub")
+    delta = native.adaptive_delta(t("x2d"), t("w2d"), float(g["relative_delta"]))
+    assert err_vs(delta.cpu().numpy(), g["delta"]) < 1e-5
+    return native.Problem(t("x3d"), t("x2d"), t("w2d"), t("cam_mats"), lb, ub, delta), lb, ub
+
+
+def _hypothesis_agreement(pose, cost, g, tag):
+    """fraction of hypotheses whose pose is within 1e-4 (of scale) of the reference run `tag`, and the cost error there"""
+    ref_pose, ref_cost = g[tag + "_hyp_pose"], g[tag + "_hyp_cost"]
+    scale = np.abs(ref_pose).max()
+    close = np.abs(pose - ref_pose).max(-1) / scale < 1e-4
+    crel = np.abs(cost - ref_cost) / np.maximum(np.abs(ref_cost), 1e-30)
+    return float(close.mean()), float(crel[close].max()) if close.any() else 0.0
+
+
+def _check_object_level(pose_best, cost_best, g, what):
+    """winner per object: same pose to 1e-4, or a cost-equivalent other hypothesis (cost within 1e-4 of the reference minimum)"""
+    ref_pose, ref_cost = g["ref64_best_pose"], g["ref64_min_cost"]
+    scale = np.abs(ref_pose).max()
+    perr = np.abs(pose_best - ref_pose).max(-1) / scale
+    crel = np.abs(cost_best - ref_cost) / np.abs(ref_cost)
+    ok = (perr < 1e-4) | (crel < 1e-4)
+    assert ok.all(), f"{what}: pose err {perr}, cost err {crel}"
+    return perr, crel
+
+
+@pytest.mark.parametrize("name", RSLM_CASES)
+@pytest.mark.parametrize("path", ["fused", "unfused"])
+def test_rslm_kernels_against_reference(cuda_device, name, path):
+    g = load_rslm(name)
+    dev = cuda_device
+    prob, lb, ub = _problem(g, dev)
+    dof, P, B, n = int(g["dof"]), int(g["P"]), int(g["B"]), int(g["n"])
+    D = 7 if dof == 6 else 4
+    params = native.default_params(dof, lm_iter=int(g["rs_iter"]), fast_mode=int(g["fast_mode"]), z_min=float(g["z_min"]))
+    inds = torch.from_numpy(g["inds"]).to(dev)
+    start = torch.from_numpy(g["ref32_start"]).to(dev)
+    if path == "fused":
+        r = native.rslm(prob, inds, start, params, want_all=True)
+        pose_all, cost_all, pose_best, cost_best = r["pose_all"], r["cost_all"], r["pose"], r["cost"]
+    else:
+        rows = torch.arange(B, device=dev)[None, :, None]
+        li = inds.long()
+        mini = native.Problem(prob.x3d[rows, li].reshape(P * B, n, 3), prob.x2d[rows, li].reshape(P * B, n, 2),
+                              prob.w2d[rows, li].reshape(P * B, n, 2), prob.cam.repeat(P, 1, 1),
+                              None if lb is None else lb.repeat(P, 1), None if ub is None else ub.repeat(P, 1),
+                              prob.delta.repeat(P))
+        pose_all = native.lm_solve(mini, start.reshape(P * B, D), params)["pose_opt"].reshape(P, B, D)
+        cost_all = native.evaluate_cost(prob, pose_all, dof, params.z_min)
+        cost_best, win = cost_all.min(dim=0)
+        pose_best = pose_all[win, torch.arange(B, device=dev)]
+    pose_all, cost_all = pose_all.cpu().numpy(), cost_all.cpu().numpy()
+    frac64, cerr64 = _hypothesis_agreement(pose_all, cost_all, g, "ref64")
+    frac32, cerr32 = _hypothesis_agreement(pose_all, cost_all, g, "ref32")
+    floor_frac, _ = _hypothesis_agreement(g["ref32_hyp_pose"], g["ref32_hyp_cost"], g, "ref64")
+    # at least as many hypotheses agree with the fp64 reference as the reference's own fp32 run manages, minus 5 %
+    assert frac64 >= min(0.9, floor_frac - 0.05), (frac64, floor_frac)
+    assert cerr64 < 1e-4 and cerr32 < 1e-4
+    perr, crel = _check_object_level(pose_best.cpu().numpy(), cost_best.cpu().numpy(), g, f"{name}/{path}")
+    same_winner = float((cost_all.argmin(0) == g["ref64_winner"]).mean())
+    record_parity(f"rslm/{name}/{path}", hyp_frac_within_1em4_vs_ref64=frac64, hyp_frac_within_1em4_vs_ref32=frac32,
+                  ref32_frac_within_1em4_vs_ref64=floor_frac, hyp_cost_rel_max=max(cerr64, cerr32),
+                  best_pose_rel_max=float(perr.max()), min_cost_rel_max=float(crel.max()), same_winner=same_winner,
+                  hyp_cost=err_stats(cost_all, g["ref64_hyp_cost"]))
+
+
+class _Playback:
+    """torch.multinomial / randn / rand return the reference's taped draws, in call order."""
+
+    def __init__(self, monkeypatch, dev, multinomial, rot, dof):
+        self.q = dict(multinomial=[torch.from_numpy(x.astype(np.int64)).to(dev) for x in multinomial],
+                      rot=[torch.from_numpy(x).to(dev) for x in rot])
+        P, B, n = multinomial[0].shape
+        monkeypatch.setattr(torch, "multinomial", lambda *a, **k: self.q["multinomial"].pop(0).reshape(P * B, n))
+        monkeypatch.setattr(torch, "rand" if dof == 4 else "randn", lambda *a, **k: self.q["rot"].pop(0))
+
+
+@pytest.mark.parametrize("name", RSLM_CASES)
+def test_rslm_classes_with_reference_draws(cuda_device, name, monkeypatch):
+    g = load_rslm(name)
+    dev = cuda_device
+    t = lambda k: torch.from_numpy(g[k]).to(dev)
+    dof, P, n = int(g["dof"]), int(g["P"]), int(g["n"])
+    lb = ub = None
+    if int(g["bounds"]) == 2:
+        lb, ub = t("lb"), t("ub")
+    camera = PerspectiveCamera(cam_mats=t("cam_mats"), z_min=float(g["z_min"]), lb=lb, ub=ub)
+    cost_fun = AdaptiveHuberPnPCost(relative_delta=float(g["relative_delta"]))
+    cost_fun.set_param(t("x2d"), t("w2d"))
+    fast = bool(g["fast_mode"])
+    rs = RSLMSolver(dof=dof, num_points=n, num_proposals=P, num_iter=int(g["rs_iter"]))
+    _Playback(monkeypatch, dev, [g["inds"], g["force_inds"]], [g["rot_draw"], g["force_rot_draw"]], dof)
+    pose, none, cost = rs.solve(t("x3d"), t("x2d"), t("w2d"), camera, cost_fun, fast_mode=fast)
+    assert none is None
+    perr, crel = _check_object_level(pose.cpu().numpy(), cost.cpu().numpy(), g, name + "/RSLMSolver.solve")
+    # force_init_solve: second set of draws, use_init selection, then the solver's own iterations
+    solver = LMSolver(dof=dof, num_iter=int(g["lm_iter"]), init_solver=rs)
+    pose_opt, _, cost_opt = solver.solve(t("x3d"), t("x2d"), t("w2d"), camera, cost_fun, pose_init=t("pose_init"),
+                                         with_cost=True, force_init_solve=True, fast_mode=fast)
+    ref_pose, ref_cost = g["ref64_force_pose"], g["ref64_force_cost"]
+    scale = np.abs(ref_pose).max()
+    e_pose = np.abs(pose_opt.cpu().numpy() - ref_pose).max(-1) / scale
+    e_cost = np.abs(cost_opt.cpu().numpy() - ref_cost) / np.abs(ref_cost)
+    floor = np.abs(g["ref32_force_pose"] - ref_pose).max() / scale
+    assert ((e_pose < max(1e-4, 3 * floor)) | (e_cost < 2e-6)).all(), (e_pose, e_cost)
+    record_parity(f"rslm/{name}/classes", solve_pose_rel_max=float(perr.max()), solve_cost_rel_max=float(crel.max()),
+                  force_pose_rel_max=float(e_pose.max()), force_cost_rel_max=float(e_cost.max()),
+                  ref32_force_pose_rel_vs_ref64=float(floor))
