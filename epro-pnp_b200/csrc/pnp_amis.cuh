@@ -1,0 +1,410 @@
+// pnp_amis.cuh -- the adaptive-multiple-importance-sampling loop of EProPnPBase.monte_carlo_forward
+// (epropnp.py:132-182; 6DoF proposals :288-342, 4DoF :199-260) as a CTA-PER-OBJECT kernel.
+//
+//   * the object's correspondences are pulled from HBM once (TMA ring -> 64-byte pair records in shared memory);
+//   * one thread owns one sample of an iteration: draws it (injected noise or Philox), sweeps all N points with the
+//     pre-multiplied projection K[R|t] (points are shared-memory broadcasts, packed fp32x2 arithmetic), evaluates the
+//     proposal densities it needs; the mixture density of a sample is kept as ONE running log-sum-exp;
+//   * a log-weight is -cost - (lse - log count): it is recomputed where needed instead of stored, and the staging ring
+//     lives inside the (not yet written) sample buffer, so a CTA needs 36.1 KB at N = M = 512 and SIX CTAs share an SM;
+//   * the proposal refit is four block reductions (transposed butterflies) + a short chain on one lane.
+// The LM solution (pose, covariance) comes from global memory: lm_warp_kernel wrote it just before (same stream).
+#pragma once
+#include "pnp_device.cuh"
+
+namespace {
+
+#if !defined(EPNP_AMIS_CTAS_PER_SM)
+#define EPNP_AMIS_CTAS_PER_SM 6         // 80 registers; 6 x (36.1 KB + 1 KB reserved) of the SM's 228 KB at N = M = 512
+#endif
+
+template <int DOF> struct ProposalOf;
+template <> struct ProposalOf<6> { typedef Proposal6 type; };
+template <> struct ProposalOf<4> { typedef Proposal4 type; };
+
+template <int DOF> struct AmisHead {
+    uint64_t bar[2];
+    float red[2 * NW * 32];                 // two halves: consecutive reductions alternate, one barrier each
+    float pose[8];                          // the LM solution ...
+    float cov[DOF * DOF];                   // ... and its covariance
+    typename ProposalOf<DOF>::type prop[MAX_ITER];
+};
+
+struct AmisPlan {        // offsets in floats from the start of dynamic smem
+    int stage, pts, smp, cost, logp, total_bytes;
+};
+
+// The staging ring is dead once the object is packed and the sample buffer is not written before the AMIS loop, so the
+// ring lives inside it whenever it fits.
+template <int DOF>
+__host__ __device__ inline AmisPlan plan_amis(int N, int M) {
+    AmisPlan s;
+    int off = (int)((sizeof(AmisHead<DOF>) + 127) / 128 * 128 / 4);
+    const bool alias = Dim<DOF>::POSE * M >= 2 * STAGE_FLOATS;
+    s.stage = off; if (!alias) off += 2 * STAGE_FLOATS;
+    s.pts = off; off += 16 * ((N + 1) / 2);        // 64 B per pair of points
+    s.smp = off; off += Dim<DOF>::POSE * M;
+    if (alias) s.stage = s.smp;
+    s.cost = off; off += M;
+    s.logp = off; off += M;                         // running log-sum-exp of the proposal densities, one per sample
+    s.total_bytes = off * 4;
+    return s;
+}
+
+// running log-sum-exp over the proposals seen so far
+struct RunningLse {
+    float top, acc;
+    __device__ __forceinline__ void start(float lp) { top = lp; acc = 1.f; }
+    __device__ __forceinline__ void add(float lp) {
+        if (lp > top) { acc = fmaf(acc, expf(top - lp), 1.f); top = lp; }
+        else acc += expf(lp - top);
+    }
+    __device__ __forceinline__ float value() const { return top + logf(acc); }
+};
+__device__ __forceinline__ float log_add_exp(float a, float b) {
+    const float hi = fmaxf(a, b), lo = fminf(a, b);
+    return (lo == -CUDART_INF_F) ? hi : hi + log1pf(expf(lo - hi));
+}
+
+// ------------------------------------------------------------------------------------------------
+// AMIS loop for the resident object, 6DoF.  sh.pose / sh.cov hold the LM solution.
+__device__ void amis_phase6(const KArgs& a, AmisHead<6>& sh, const float* pts4, float* smp, float* cst, float* logp,
+                            const Cam& cam, float delta, int obj) {
+    const Params& p = a.p;
+    const int tid = threadIdx.x;
+    const int M = p.mc_samples, I = p.mc_iter, S = M / I;
+    const bool injected = a.noise_n3 != nullptr;
+    const int st = serial_thread(a);
+    float* const logw_out = a.logw + (size_t)obj * M;
+    PH_DECL;
+
+    if (tid == st) initial_fit6(sh.pose, sh.cov, p.acg_dispersion, sh.prop[0]);
+    PH_MARK(a, PH_INIT_FIT);
+    __syncthreads();
+
+    for (int i = 0; i < I; ++i) {
+        // ---- draw, cost, densities of the new samples (one sample per thread and pass)
+        for (int s = tid; s < S; s += NT) {
+            const int m = i * S + s;
+            float n3[3], n4[4], chi2;
+            if (injected) {
+                const size_t g = (size_t)obj * M + m;
+                n3[0] = __ldg(a.noise_n3 + g * 3); n3[1] = __ldg(a.noise_n3 + g * 3 + 1); n3[2] = __ldg(a.noise_n3 + g * 3 + 2);
+                chi2 = __ldg(a.noise_chi2 + g);
+                n4[0] = __ldg(a.noise_rot + g * 4); n4[1] = __ldg(a.noise_rot + g * 4 + 1);
+                n4[2] = __ldg(a.noise_rot + g * 4 + 2); n4[3] = __ldg(a.noise_rot + g * 4 + 3);
+            } else {
+                draw_base_noise(a.seed, a.obj_offset + (uint32_t)obj, (uint32_t)m, n3, chi2, n4);
+            }
+            float q[7];
+            proposal_draw6(sh.prop[i], n3, chi2, n4, q);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) smp[m * 7 + k] = q[k];
+            float* out = a.pose_samples + ((size_t)obj * M + m) * 7;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) out[k] = q[k];
+            cst[m] = pose_cost<6>(pts4, a.N, q, cam, delta);
+            RunningLse l;
+            l.start(proposal_logpdf6(sh.prop[0], q));
+            for (int j = 1; j <= i; ++j) l.add(proposal_logpdf6(sh.prop[j], q));
+            logp[m] = l.value();
+        }
+        PH_MARK(a, PH_DRAW_SWEEP);
+        // ---- the new proposal on all earlier samples
+        for (int m = tid; m < i * S; m += NT) {
+            float q[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) q[k] = smp[m * 7 + k];
+            logp[m] = log_add_exp(logp[m], proposal_logpdf6(sh.prop[i], q));
+        }
+        __syncthreads();
+        PH_MARK(a, PH_LOGP_OLD);
+        // ---- log-weights of all samples so far: -cost - log(mixture density)
+        const int n = (i + 1) * S;
+        const float log_cnt = logf((float)(i + 1));
+        auto logweight = [&](int m) { return -cst[m] - (logp[m] - log_cnt); };
+        if (i == I - 1) {
+            for (int m = tid; m < M; m += NT) logw_out[m] = logweight(m);
+            PH_MARK(a, PH_OUTPUT);
+            break;
+        }
+        float mx = -CUDART_INF_F;
+        for (int m = tid; m < n; m += NT) mx = fmaxf(mx, logweight(m));
+        PH_MARK(a, PH_WEIGHTS);
+        // ---- refit proposal i+1 to the weighted samples (estimate_params, epropnp.py:317-342).
+        // Four block reductions, one barrier each:
+        //   A  max of the log-weights
+        //   B  e = exp(lw - max): sum e, sum e t, and ACG fixed-point iteration 1 (Lambda_0 = I, so
+        //      M = q.q) -- the normalisation of the weights cancels in Lambda
+        //   C  translation covariance about the mean (+ ACG iteration 2)
+        //   D+ remaining ACG iterations
+        mx = block_max(mx, sh.red, 0);
+        float lam10[10];
+        float mean[3], inv_sum;
+        {
+            float acc[15];
+#pragma unroll
+            for (int r = 0; r < 15; ++r) acc[r] = 0.f;
+            for (int m = tid; m < n; m += NT) {
+                const float e = expf(logweight(m) - mx);
+                const float* s7 = smp + m * 7;
+                acc[0] += e;
+                acc[1] = fmaf(e, s7[0], acc[1]); acc[2] = fmaf(e, s7[1], acc[2]); acc[3] = fmaf(e, s7[2], acc[3]);
+                const float* q = s7 + 3;
+                const float mq = fmaxf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3], p.amis_eps);
+                const float wm = e / mq;
+                acc[4] += wm;
+                int idx = 5;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
+            }
+            block_sum<15>(acc, sh.red, 1);
+            inv_sum = 1.0f / acc[0];
+            mean[0] = acc[1] * inv_sum; mean[1] = acc[2] * inv_sum; mean[2] = acc[3] * inv_sum;
+            const float inv0 = 1.0f / acc[4];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) lam10[r] = acc[5 + r] * inv0;
+            lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
+        }
+        if (p.acg_mle_iter == 0) {          // degenerate configuration: Lambda stays the identity
+#pragma unroll
+            for (int r = 0; r < 10; ++r) lam10[r] = 0.f;
+            lam10[0] = lam10[4] = lam10[7] = lam10[9] = 1.f;
+        }
+        float tc[6];
+        {
+            const bool more = p.acg_mle_iter >= 2;
+            float lam_inv[16];
+            if (more) acg_scatter_inverse(lam10, lam_inv);
+            float acc[17];
+#pragma unroll
+            for (int r = 0; r < 17; ++r) acc[r] = 0.f;
+            for (int m = tid; m < n; m += NT) {
+                const float w = expf(logweight(m) - mx) * inv_sum;       // normalised softmax weight
+                const float* s7 = smp + m * 7;
+                const float d0 = s7[0] - mean[0], d1 = s7[1] - mean[1], d2 = s7[2] - mean[2];
+                acc[11] = fmaf(w * d0, d0, acc[11]); acc[12] = fmaf(w * d0, d1, acc[12]); acc[13] = fmaf(w * d0, d2, acc[13]);
+                acc[14] = fmaf(w * d1, d1, acc[14]); acc[15] = fmaf(w * d1, d2, acc[15]); acc[16] = fmaf(w * d2, d2, acc[16]);
+                if (more) {
+                    const float* q = s7 + 3;
+                    const float wm = w / fmaxf(quad4(lam_inv, q), p.amis_eps);
+                    acc[0] += wm;
+                    int idx = 1;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
+                }
+            }
+            block_sum<17>(acc, sh.red, 0);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) tc[r] = acc[11 + r];
+            if (more) {
+                const float inv0 = 1.0f / acc[0];
+#pragma unroll
+                for (int r = 0; r < 10; ++r) lam10[r] = acc[1 + r] * inv0;
+                lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
+            }
+        }
+        for (int itr = 2; itr < p.acg_mle_iter; ++itr) {
+            float lam_inv[16];
+            acg_scatter_inverse(lam10, lam_inv);
+            float acc[11];
+#pragma unroll
+            for (int r = 0; r < 11; ++r) acc[r] = 0.f;
+            for (int m = tid; m < n; m += NT) {
+                const float* q = smp + m * 7 + 3;
+                const float wm = expf(logweight(m) - mx) * inv_sum / fmaxf(quad4(lam_inv, q), p.amis_eps);
+                acc[0] += wm;
+                int idx = 1;
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
+            }
+            block_sum<11>(acc, sh.red, (itr + 1) & 1);
+            const float inv0 = 1.0f / acc[0];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) lam10[r] = acc[1 + r] * inv0;
+            lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
+        }
+        PH_MARK(a, PH_REFIT_SUMS);
+        if (tid == st) refit_finish6(mean, tc, lam10, p.acg_dispersion, sh.prop[i + 1]);
+        PH_MARK(a, PH_REFIT_FINISH);
+        __syncthreads();
+    }
+    if (a.proposals && tid < I) {
+        float* o = a.proposals + ((size_t)obj * I + tid) * PROP_FLOATS;
+        const Proposal6& pr = sh.prop[tid];
+        o[0] = pr.mu[0]; o[1] = pr.mu[1]; o[2] = pr.mu[2];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) o[3 + r] = pr.lt[r];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) o[9 + r] = pr.lr[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// AMIS loop for the resident object, 4DoF (EProPnP4DoF, epropnp.py:199-260): same skeleton as amis_phase6
+// with the yaw proposal 0.75 von Mises + 0.25 uniform.  Injected noise: noise_rot (B, M) holds the yaw
+// draws themselves (the reference samples them with numpy on the host, distributions.py:61-72, so there
+// is no base noise to replay).
+__device__ void amis_phase4(const KArgs& a, AmisHead<4>& sh, const float* pts4, float* smp, float* cst, float* logp,
+                            const Cam& cam, float delta, int obj) {
+    const Params& p = a.p;
+    const int tid = threadIdx.x;
+    const int M = p.mc_samples, I = p.mc_iter, S = M / I;
+    const bool injected = a.noise_n3 != nullptr;
+    const int st = serial_thread(a);
+    float* const logw_out = a.logw + (size_t)obj * M;
+    PH_DECL;
+
+    if (tid == st) initial_fit4(sh.pose, sh.cov, p.amis_eps, sh.prop[0]);
+    PH_MARK(a, PH_INIT_FIT);
+    __syncthreads();
+
+    for (int i = 0; i < I; ++i) {
+        for (int s = tid; s < S; s += NT) {
+            const int m = i * S + s;
+            float n3[3], chi2, q[4];
+            if (injected) {
+                const size_t g = (size_t)obj * M + m;
+                n3[0] = __ldg(a.noise_n3 + g * 3); n3[1] = __ldg(a.noise_n3 + g * 3 + 1); n3[2] = __ldg(a.noise_n3 + g * 3 + 2);
+                chi2 = __ldg(a.noise_chi2 + g);
+                q[3] = __ldg(a.noise_rot + g);
+            } else {
+                draw_base_noise_t(a.seed, a.obj_offset + (uint32_t)obj, (uint32_t)m, n3, chi2);
+                q[3] = draw_yaw(a.seed, a.obj_offset + (uint32_t)obj, (uint32_t)m, s, S, sh.prop[i].mode, sh.prop[i].kappa);
+            }
+            draw_translation(sh.prop[i].mu, sh.prop[i].lt, n3, chi2, q);
+            float* out = a.pose_samples + ((size_t)obj * M + m) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { smp[m * 4 + k] = q[k]; out[k] = q[k]; }
+            cst[m] = pose_cost<4>(pts4, a.N, q, cam, delta);
+            RunningLse l;
+            l.start(proposal_logpdf4(sh.prop[0], q));
+            for (int j = 1; j <= i; ++j) l.add(proposal_logpdf4(sh.prop[j], q));
+            logp[m] = l.value();
+        }
+        PH_MARK(a, PH_DRAW_SWEEP);
+        for (int m = tid; m < i * S; m += NT) logp[m] = log_add_exp(logp[m], proposal_logpdf4(sh.prop[i], smp + m * 4));
+        __syncthreads();
+        PH_MARK(a, PH_LOGP_OLD);
+        const int n = (i + 1) * S;
+        const float log_cnt = logf((float)(i + 1));
+        auto logweight = [&](int m) { return -cst[m] - (logp[m] - log_cnt); };
+        if (i == I - 1) {
+            for (int m = tid; m < M; m += NT) logw_out[m] = logweight(m);
+            PH_MARK(a, PH_OUTPUT);
+            break;
+        }
+        float mx = -CUDART_INF_F;
+        for (int m = tid; m < n; m += NT) mx = fmaxf(mx, logweight(m));
+        PH_MARK(a, PH_WEIGHTS);
+        // ---- refit (estimate_params, epropnp.py:232-260): A max, B sums of e, e t, e sin, e cos, C covariance
+        mx = block_max(mx, sh.red, 0);
+        float accB[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int m = tid; m < n; m += NT) {
+            const float e = expf(logweight(m) - mx);
+            const float* s4 = smp + m * 4;
+            float sn, cs;
+            sincosf(s4[3], &sn, &cs);
+            accB[0] += e;
+            accB[1] = fmaf(e, s4[0], accB[1]); accB[2] = fmaf(e, s4[1], accB[2]); accB[3] = fmaf(e, s4[2], accB[3]);
+            accB[4] = fmaf(e, sn, accB[4]); accB[5] = fmaf(e, cs, accB[5]);
+        }
+        block_sum<6>(accB, sh.red, 1);
+        const float inv_sum = 1.0f / accB[0];
+        const float mean[3] = {accB[1] * inv_sum, accB[2] * inv_sum, accB[3] * inv_sum};
+        float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int m = tid; m < n; m += NT) {
+            const float w = expf(logweight(m) - mx) * inv_sum;
+            const float* s4 = smp + m * 4;
+            const float d0 = s4[0] - mean[0], d1 = s4[1] - mean[1], d2 = s4[2] - mean[2];
+            tc[0] = fmaf(w * d0, d0, tc[0]); tc[1] = fmaf(w * d0, d1, tc[1]); tc[2] = fmaf(w * d0, d2, tc[2]);
+            tc[3] = fmaf(w * d1, d1, tc[3]); tc[4] = fmaf(w * d1, d2, tc[4]); tc[5] = fmaf(w * d2, d2, tc[5]);
+        }
+        block_sum<6>(tc, sh.red, 0);
+        PH_MARK(a, PH_REFIT_SUMS);
+        if (tid == st) refit_finish4(mean, tc, accB[4] * inv_sum, accB[5] * inv_sum, p.amis_eps, sh.prop[i + 1]);
+        PH_MARK(a, PH_REFIT_FINISH);
+        __syncthreads();
+    }
+    if (a.proposals && tid < I) {       // (B, I, 19): mu3, Lt6, mode, kappa, 0...
+        float* o = a.proposals + ((size_t)obj * I + tid) * PROP_FLOATS;
+        const Proposal4& pr = sh.prop[tid];
+        o[0] = pr.mu[0]; o[1] = pr.mu[1]; o[2] = pr.mu[2];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) o[3 + r] = pr.lt[r];
+        o[9] = pr.mode; o[10] = pr.kappa;
+#pragma unroll
+        for (int r = 11; r < PROP_FLOATS; ++r) o[r] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Optional epilogue of the multi-GPU path: when an object is finished, its CTA also stores the object's pose and its M
+// log-weights into row (obj_offset + obj) of the full-batch result buffers of up to EPNP_MAX_PEERS other GPUs (pointers
+// into their memory, mapped through CUDA IPC): plain st.global over NVLink, 2 KB + 28 B per object and peer, issued
+// object by object underneath the other CTAs' math.  No gather kernel and no copy afterwards; the caller only needs a
+// rendezvous before reading (sharded.PushGather).
+constexpr int EPNP_MAX_PEERS = 8;
+struct PushArgs {
+    float* logw[EPNP_MAX_PEERS];            // (B_total, M) on each peer
+    float* pose[EPNP_MAX_PEERS];            // (B_total, D) on each peer
+    int n;
+};
+
+// One object per CTA (blockIdx.x = object).
+template <int DOF, bool PUSH>
+__global__ void __launch_bounds__(NT, EPNP_AMIS_CTAS_PER_SM) amis_kernel(const KArgs a, const PushArgs push) {
+    EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
+    AmisHead<DOF>& sh = *reinterpret_cast<AmisHead<DOF>*>(smem_raw);
+    float* dyn = reinterpret_cast<float*>(smem_raw);
+    constexpr int PD = Dim<DOF>::POSE;
+    const int M = a.p.mc_samples;
+    const AmisPlan pl = plan_amis<DOF>(a.N, M);
+    float* pts4 = dyn + pl.pts;
+    const int obj = blockIdx.x, tid = threadIdx.x;
+    PH_DECL;
+    // The LM solution -> shared memory BEFORE this object's sample rows are written: the fused entry point may have
+    // parked the covariance there (cov_stride = M * D).  Plain loads: that memory is written later in this launch.
+    if (tid < PD) sh.pose[tid] = a.pose_opt_in[(size_t)obj * PD + tid];
+    if (tid < DOF * DOF) sh.cov[tid] = a.pose_cov_in[(size_t)obj * a.cov_stride + tid];
+    Loader ld(a, sh.bar, dyn + pl.stage);
+    ld.load_object(obj, pts4);              // ends with a __syncthreads
+    const Cam cam = load_cam(a, obj);
+    const float delta = __ldg(a.delta + obj);
+    PH_MARK(a, PH_LOAD);
+    if constexpr (DOF == 6) amis_phase6(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, cam, delta, obj);
+    else amis_phase4(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, cam, delta, obj);
+    if constexpr (PUSH) {
+        // the object's log-weights, as this CTA wrote them, and its pose to the same global row on every peer
+        __syncthreads();                                        // the CTA's own global stores are visible to all its threads
+        const size_t row = (size_t)a.obj_offset + (size_t)obj;
+        const float* src = a.logw + (size_t)obj * M;
+        if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+            for (int q = tid; q < M / 4; q += NT) {
+                const float4 v = reinterpret_cast<const float4*>(src)[q];
+                for (int r = 0; r < push.n; ++r) {
+                    float* dst = push.logw[r] + row * M;
+                    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) reinterpret_cast<float4*>(dst)[q] = v;
+                    else { dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w; }
+                }
+            }
+        } else {
+            for (int m = tid; m < M; m += NT) {
+                const float v = src[m];
+                for (int r = 0; r < push.n; ++r) push.logw[r][row * M + m] = v;
+            }
+        }
+        if (tid < PD) {
+            const float v = sh.pose[tid];
+            for (int r = 0; r < push.n; ++r) push.pose[r][row * PD + tid] = v;
+        }
+    }
+}
+
+}  // namespace

@@ -1,1652 +1,67 @@
 // pnp_kernels.cu -- sm_100a kernels of the EPro-PnP hot path and their C ABI (include/epropnp_b200.h).
 //
-// Execution model (all solve kernels):
-//   * persistent grid: one 128-thread CTA works on one object at a time and strides over the batch;
-//   * the object's correspondence set {x3d, x2d, w2d} is pulled from HBM exactly once by TMA bulk
-//     copies (cp.async.bulk -> mbarrier complete_tx) into a 2-slot staging ring, re-packed into a
-//     64-byte record per PAIR of points {X0 X1 Y0 Y1 | Z0 Z1 -u0 -u1 | -v0 -v1 wu0 wu1 | wv0 wv1 . .}
-//     in shared memory (operands of the packed fp32x2 FFMA2 the AMIS sweep runs on), and every later pass (K+1 LM evaluations, I AMIS
-//     cost sweeps over S samples) reads shared memory only; the next object's chunks are already in
-//     flight while the current object is being solved;
-//   * LM: threads stride over points, 28 partial sums (21 J^T J + 6 J^T r + cost) are reduced with
-//     a transposed butterfly (31 shuffles per warp instead of 140) and one cross-warp pass; the 6x6
-//     damped Cholesky solve, SE(3) retraction and trust-region logic run on one thread out of
-//     shared memory;
-//   * AMIS: one thread owns one sample of the iteration: draws it (injected noise or Philox), sweeps
-//     all N points with the pre-multiplied projection K[R|t] (points are smem broadcasts), evaluates
-//     the proposal densities it needs; the proposal refit is a handful of block reductions.
+//   lm_warp_kernel (pnp_lm.cuh)      Levenberg-Marquardt / Gauss-Newton pose solve, ONE WARP per object: raw correspondences
+//                                    TMA-staged into the warp's shared memory, 16 points per lane, shuffle-only reduction,
+//                                    6x6 damped Cholesky + SE(3) retraction + trust region on lane 0, no block barrier.
+//   amis_kernel (pnp_amis.cuh)       the AMIS Monte-Carlo loop, ONE CTA per object: TMA ring -> packed pair records, one
+//                                    thread per sample, packed fp32x2 cost sweep, refits as block reductions; six CTAs per SM.
+//   epnp_lm_amis_fused_f32           = lm_warp_kernel, then amis_kernel, on the caller's stream (no host round trip); the
+//                                    split is what a measurement asked for: as one kernel the LM half ran latency-bound at
+//                                    4 points per thread between block barriers.
+//   cost_kernel, evaluate_full_kernel, rslm_kernel, cost_backward_kernel, gn_plus_backward_kernel, adaptive_delta_kernel,
+//   mc_epilogue_kernel, mc_lse_backward_kernel      the steps either side of the path (CTA per object).
 // No tensor cores: the only contraction is 6-deep, the work is FP32-pipe + MUFU bound.
-//
-// Build options (all OFF in the shipped library; DESIGN.md section 9.2, tools/variants.py, and the CPU emulation in
-// tests/simt_emul run every one of them): EPNP_LM_PACKED, EPNP_LM_NOREFINE, EPNP_LM_COST_FIRST, EPNP_SWEEP_RSQ,
-// EPNP_SWEEP_NOCLAMP, EPNP_SWEEP_SPLIT, EPNP_FAST_BLOCKSUM (candidate speed-ups awaiting their first GPU A/B),
-// EPNP_TF32X3_NUMERICS (accuracy study), EPNP_PHASE_TIMERS (profiling), EPNP_SIMT_EMUL (g++ build for the emulator).
-// The kernels of the default build are pinned by profiles/validated_sass.json (tools/sass_identity.py).
+// Build options: EPNP_PHASE_TIMERS (profiling), EPNP_SIMT_EMUL (g++ build for the test-only CPU emulator).
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include <cstdlib>
 
-#include "pnp_math.cuh"
-
-// Kernel launches and the dynamic shared-memory declaration are spelled through two macros so that this file also
-// builds, unchanged, under the test-only SIMT emulator (tests/simt_emul, g++ -DEPNP_SIMT_EMUL) that lets the CPU
-// suite execute the kernels' control flow.  In the nvcc build they expand to the plain CUDA forms.
-#if defined(EPNP_SIMT_EMUL)
-#define EPNP_LAUNCH(kern, grid, block, smem, stream, ...) simt::launch(grid, block, smem, [&] { kern(__VA_ARGS__); })
-#define EPNP_DYN_SMEM(type, name, align) type* name = reinterpret_cast<type*>(simt::state().dyn_smem)
-#else
-#define EPNP_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
-#define EPNP_DYN_SMEM(type, name, align) extern __shared__ __align__(align) type name[]
-#endif
+#include "pnp_device.cuh"
+#include "pnp_lm.cuh"
+#include "pnp_amis.cuh"
 
 namespace {
-using namespace pnp;
-
-#if defined(EPNP_SWEEP_MMA) && !defined(EPNP_SWEEP_SPLIT)
-#define EPNP_SWEEP_SPLIT 1              // the tensor-pipe sweep reuses the draw-then-sweep control flow
-#endif
-#if (defined(EPNP_SWEEP_NOCLAMP) || defined(EPNP_SWEEP_SPLIT) || defined(EPNP_TF32X3_NUMERICS)) && !defined(EPNP_SWEEP_RSQ)
-#define EPNP_SWEEP_RSQ 1
-#endif
-
-#if defined(EPNP_NO_LW) && !defined(EPNP_AMIS_LSE)
-#define EPNP_AMIS_LSE 1                 // recomputing a log-weight needs the mixture density as a single value
-#endif
-// EPNP_NO_LW (experiment): no per-sample log-weight buffer in shared memory (-4 M bytes).  A log-weight is
-// -cost - (lse - log count); the refit passes recompute it where they need it, the last iteration writes it straight
-// to the output, and the split sweep parks the second point half of a new sample's cost in the object's (not yet
-// written) log-weight OUTPUT slot instead.
-#if defined(EPNP_NO_LW)
-#define LW_STORE(m, v)
-#define LW_LOGWEIGHT(m) (-cst[m] - (logp[m] - log_cnt))
-#define LW_E(m) expf(LW_LOGWEIGHT(m) - mx)
-#define LW_E_STORE(m, e)
-#define LW_W(m) (LW_E(m) * inv_sum)
-#define LW_W_STORE(m, w)
-#else
-#define LW_STORE(m, v) lw[m] = (v)
-#define LW_E(m) expf(lw[m] - mx)
-#define LW_E_STORE(m, e) lw[m] = (e)
-#define LW_W(m) (lw[m] * inv_sum)
-#define LW_W_STORE(m, w) lw[m] = (w)
-#endif
-
-#if defined(EPNP_SWEEP_MMA)
-#define EPNP_PTAB_PARAM , float* ptab
-#define EPNP_PTAB_ARG(x) , (x)
-#else
-#define EPNP_PTAB_PARAM
-#define EPNP_PTAB_ARG(x)
-#endif
-
-constexpr int NT = 128;                 // threads per CTA
-constexpr int NW = NT / 32;
-constexpr int CH = 128;                 // correspondences per TMA chunk (2 slots x 3.5 KB)
-constexpr int STAGE_FLOATS = CH * 7;    // x3d (3) + x2d (2) + w2d (2)
-constexpr int MAX_ITER = 8;             // AMIS iterations supported (reference default 4)
-constexpr int PROP_FLOATS = 19;         // proposals dump: mu3, Lt6, Lr10
-constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 thread_local int g_last_cuda_error = 0;
 
-// Phase timers (profiling build: -DEPNP_PHASE_TIMERS; tools/phase_profile.py).  Thread 0 of every CTA adds
-// the clock64() cycles it spent in each phase; the production build compiles them away.
-enum Phase { PH_LOAD = 0, PH_LM_EVAL, PH_LM_SERIAL, PH_COV, PH_INIT_FIT, PH_DRAW_SWEEP, PH_LOGP_OLD, PH_WEIGHTS,
-             PH_REFIT_SUMS, PH_REFIT_FINISH, PH_OUTPUT, PH_COUNT };
-#ifdef EPNP_PHASE_TIMERS
-#define PH_DECL long long ph_t = clock64()
-#define PH_MARK(a_, which)                                                                     \
-    do {                                                                                       \
-        if ((int)threadIdx.x == serial_thread(a_) && (a_).prof) {                                                \
-            const long long now_ = clock64();                                                  \
-            atomicAdd((a_).prof + (which), (unsigned long long)(now_ - ph_t));                 \
-            ph_t = now_;                                                                       \
-        }                                                                                      \
-    } while (0)
-#else
-#define PH_DECL
-#define PH_MARK(a_, which)
-#endif
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers: mbarrier + 1-D TMA bulk copy
-#if defined(EPNP_SIMT_EMUL)
-// emulator: an mbarrier word is {completed phases (low 32 bits), bytes still expected (high 32 bits)}; a bulk copy
-// is a memcpy that retires its bytes and completes the phase when none are left; waiting on a parity yields to the
-// other fibers until that phase has completed.  Exact libm stands in for the approximate special-function units.
-inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
-inline void fence_barrier_init() {}
-inline void fence_proxy_async() {}
-inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { *bar += (uint64_t)bytes << 32; }
-inline void mbar_wait(uint64_t* bar, uint32_t parity) { while (((uint32_t)*bar & 1u) == parity) simt::yield(); }
-inline void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-    std::memcpy(dst_smem, src, bytes);
-    *bar -= (uint64_t)bytes << 32;
-    if ((*bar >> 32) == 0) *bar = (uint32_t)*bar + 1u;
-}
-struct FastRcp { float operator()(float x) const { return 1.0f / x; } };
-struct FastSqrt { float operator()(float x) const { return sqrtf(x); } };
-#else
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-struct FastRcp {
-    __device__ __forceinline__ float operator()(float x) const { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-};
-struct FastSqrt {
-    __device__ __forceinline__ float operator()(float x) const { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-};
-#endif
-
-// ------------------------------------------------------------------------------------------------
-struct KArgs {
-    const float *x3d, *x2d, *w2d, *cam, *lb, *ub, *delta;
-    const float *pose_init;                 // LM entry
-    const float *pose_opt_in, *pose_cov_in; // AMIS-only entry
-    const float *noise_n3, *noise_chi2, *noise_rot;
-    const float *poses;                     // cost-only entry: (S, B, D)
-    float *pose_opt, *pose_cov, *cost, *pose_plus, *cost_init;
-    float *pose_samples, *logw, *proposals;
-    float *cost_out;                        // cost-only entry: (S, B)
-    int B, N, S_eval, use_tma, num_sms;
-    uint32_t obj_offset;
-    uint64_t seed;
-    unsigned long long* prof;               // phase timers (profiling build only), else unused
-    Params p;
-};
-
-// Static part of the shared-memory image (the dynamic arrays follow it).
-template <int DOF> struct SmemHead {
+// Shared-memory image of the CTA-per-object kernels that are not the AMIS loop: head, TMA ring, packed pair records.
+template <int DOF> struct ObjHead {
     uint64_t bar[2];
-    float red[2 * NW * 32];                 // two halves: consecutive reductions alternate, one barrier each
+    float red[2 * NW * 32];
     float ev[32];                           // reduced evaluation: NV floats
-    LMState<DOF> lm;
-    float cov[DOF * DOF];
-    Proposal6 prop[MAX_ITER];
-    Proposal4 prop4[MAX_ITER];
+    float pose[8];
+    float step[2 * DOF];                    // gn_plus_backward: step, v
 };
-
-struct SmemPlan {        // offsets in floats from the start of dynamic smem
-    int stage, pts, smp, cost, logp, lw, total_bytes;
-};
-
-// alias_stage (build option EPNP_ALIAS_STAGE, one object per CTA only): the staging ring is dead once the object is
-// packed and the sample buffer is not written before the AMIS loop, so the ring lives inside it.
-template <int DOF>
-__host__ __device__ inline bool can_alias_stage(int M, bool amis) {
-#if defined(EPNP_ALIAS_STAGE)
-    return amis && Dim<DOF>::POSE * M >= 2 * STAGE_FLOATS;
-#else
-    return false;
-#endif
-}
-template <int DOF>
-__host__ __device__ inline SmemPlan plan_smem(int N, int M, int I, bool amis, bool alias_stage = false) {
-    SmemPlan s;
-    int off = (int)((sizeof(SmemHead<DOF>) + 127) / 128 * 128 / 4);
-    const bool alias = alias_stage && can_alias_stage<DOF>(M, amis);
-    s.stage = off; if (!alias) off += 2 * STAGE_FLOATS;
-    s.pts = off; off += 16 * ((N + 1) / 2);        // 64 B per pair of points
-    s.smp = off; if (amis) off += Dim<DOF>::POSE * M;
-    if (alias) s.stage = s.smp;
-    s.cost = off; if (amis) off += M;
-#if defined(EPNP_AMIS_LSE)
-    s.logp = off; if (amis) off += M;               // running log-sum-exp of the proposal densities, one per sample
-#else
-    s.logp = off; if (amis) off += I * M;
-#endif
-#if defined(EPNP_NO_LW)
-    s.lw = off;                                     // no log-weight buffer
-#else
-    s.lw = off; if (amis) off += M;
-#endif
+struct ObjPlan { int stage, pts, total_bytes; };
+template <int DOF> __host__ __device__ inline ObjPlan plan_obj(int N) {
+    ObjPlan s;
+    int off = (int)((sizeof(ObjHead<DOF>) + 127) / 128 * 128 / 4);
+    s.stage = off; off += 2 * STAGE_FLOATS;
+    s.pts = off; off += 16 * ((N + 1) / 2);
     s.total_bytes = off * 4;
     return s;
-}
-
-// Packed point store.  Pair j = points (2j, 2j+1) occupies 16 floats:
-//   [0..3] X0 X1 Y0 Y1   [4..7] Z0 Z1 -u0 -u1   [8..11] -v0 -v1 wu0 wu1   [12..15] wv0 wv1 0 0
-__device__ __forceinline__ void store_point(float* pts, int n, float X, float Y, float Z, float u, float v, float wu, float wv) {
-    float* p = pts + (n >> 1) * 16 + (n & 1);
-    p[0] = X; p[2] = Y; p[4] = Z; p[6] = -u; p[8] = -v; p[10] = wu; p[12] = wv;
-#if defined(EPNP_SWEEP_MMA)
-    p[14] = 1.0f;           // the homogeneous coordinate, so that a B fragment is one load for every lane
-#endif
-}
-// odd N: the second half of the last pair is a zero-weight copy of the last point (contributes exactly 0);
-// written by the SAME thread that stores point N-1, so no other thread's data is read
-__device__ __forceinline__ void store_point_padded(float* pts, int n, int N, float X, float Y, float Z, float u, float v,
-                                                   float wu, float wv) {
-    store_point(pts, n, X, Y, Z, u, v, wu, wv);
-    if ((N & 1) && n == N - 1) store_point(pts, n + 1, X, Y, Z, u, v, 0.f, 0.f);
-}
-// ------------------------------------------------------------------------------------------------
-// Correspondence loader: TMA ring (or plain loads when pointers / N break the 16-byte rules).
-struct Loader {
-    const KArgs& a;
-    uint64_t* bar;
-    float* stage;
-    int nch, n_my, total;
-
-    __device__ Loader(const KArgs& a_, uint64_t* bar_, float* stage_) : a(a_), bar(bar_), stage(stage_) {
-        nch = (a.N + CH - 1) / CH;
-        n_my = ((int)blockIdx.x < a.B) ? (a.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-        total = n_my * nch;
-    }
-    __device__ void issue(int c) {          // one thread
-        const int obj = (int)blockIdx.x + (c / nch) * (int)gridDim.x;
-        const int k = c % nch;
-        const int npts = min(CH, a.N - k * CH);
-        const size_t first = (size_t)obj * a.N + (size_t)k * CH;
-        float* dst = stage + (c & 1) * STAGE_FLOATS;
-        uint64_t* b = bar + (c & 1);
-        mbar_expect_tx(b, (uint32_t)npts * 28u);
-        tma_load_1d(dst, a.x3d + first * 3, (uint32_t)npts * 12u, b);
-        tma_load_1d(dst + CH * 3, a.x2d + first * 2, (uint32_t)npts * 8u, b);
-        tma_load_1d(dst + CH * 5, a.w2d + first * 2, (uint32_t)npts * 8u, b);
-    }
-    __device__ void prologue() {
-        if (a.use_tma && threadIdx.x == 0) {
-            mbar_init(bar + 0, 1);
-            mbar_init(bar + 1, 1);
-            fence_barrier_init();
-        }
-        __syncthreads();
-        if (a.use_tma && threadIdx.x == 0) {
-            if (total > 0) issue(0);
-            if (total > 1) issue(1);
-        }
-    }
-    // Bring object number `it` of this CTA into the packed point array. Ends with a __syncthreads.
-    __device__ void load_object(int it, int obj, float* pts) {
-        const int tid = threadIdx.x;
-        if (a.use_tma) {
-            for (int k = 0; k < nch; ++k) {
-                const int c = it * nch + k;
-                const float* st = stage + (c & 1) * STAGE_FLOATS;
-                mbar_wait(bar + (c & 1), (uint32_t)((c >> 1) & 1));
-                const int npts = min(CH, a.N - k * CH);
-                for (int n = tid; n < npts; n += NT) {
-                    const float2 uv = reinterpret_cast<const float2*>(st + CH * 3)[n];
-                    const float2 w = reinterpret_cast<const float2*>(st + CH * 5)[n];
-                    store_point_padded(pts, k * CH + n, a.N, st[3 * n], st[3 * n + 1], st[3 * n + 2], uv.x, uv.y, w.x, w.y);
-                }
-                __syncthreads();            // slot drained (and, after the last chunk, pts complete)
-                if (tid == 0 && c + 2 < total) { fence_proxy_async(); issue(c + 2); }
-            }
-        } else {
-            const float* g3 = a.x3d + (size_t)obj * a.N * 3;
-            const float* g2 = a.x2d + (size_t)obj * a.N * 2;
-            const float* gw = a.w2d + (size_t)obj * a.N * 2;
-            for (int n = tid; n < a.N; n += NT)
-                store_point_padded(pts, n, a.N, __ldg(g3 + 3 * n), __ldg(g3 + 3 * n + 1), __ldg(g3 + 3 * n + 2),
-                                   __ldg(g2 + 2 * n), __ldg(g2 + 2 * n + 1), __ldg(gw + 2 * n), __ldg(gw + 2 * n + 1));
-            __syncthreads();
-        }
-    }
-};
-
-__device__ __forceinline__ Cam load_cam(const KArgs& a, int obj) {
-    Cam c;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) c.k[i] = __ldg(a.cam + (size_t)obj * 9 + i);
-    c.z_min = a.p.z_min;
-    c.bounded = (a.lb != nullptr && a.ub != nullptr) ? 1 : 0;
-    if (c.bounded) {
-        c.lbx = __ldg(a.lb + 2 * obj); c.lby = __ldg(a.lb + 2 * obj + 1);
-        c.ubx = __ldg(a.ub + 2 * obj); c.uby = __ldg(a.ub + 2 * obj + 1);
-    } else {
-        c.lbx = c.lby = -CUDART_INF_F; c.ubx = c.uby = CUDART_INF_F;
-    }
-    return c;
-}
-
-// The once-per-iteration serial work of a CTA (LM step solve, refit finish, first proposal) runs on lane 0
-// of ONE warp.  Co-resident CTAs of an SM are typically blockIdx, blockIdx + #SM, ...; rotating the serial
-// warp with blockIdx / #SM puts their serial chains on different SM sub-partitions (warp w -> SMSP w % 4)
-// instead of all of them competing for the scheduler of warp 0.
-__device__ __forceinline__ int serial_thread(const KArgs& a) {
-    return 32 * (int)((blockIdx.x / (unsigned)max(a.num_sms, 1)) & (NW - 1));
-}
-
-// ------------------------------------------------------------------------------------------------
-// Reductions
-// 32 values per lane -> lane j holds the warp total of v[j]   (31 shuffles)
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32]) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int half = 16; half >= 1; half >>= 1) {
-        const bool up = (lane & half) != 0;
-#pragma unroll
-        for (int k = 0; k < half; ++k) {
-            const float keep = up ? v[k + half] : v[k];
-            const float send = up ? v[k] : v[k + half];
-            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-        }
-    }
-    return v[0];
-}
-
-#if defined(EPNP_FAST_BLOCKSUM)
-// experiment (off by default): W values per lane (W = 8, 16 or 32) -> lane l holds the warp total of
-// v[l >> (5 - log2 W)]: log2(W) transposed-butterfly stages (W - 1 shuffles) + plain butterfly adds for the rest,
-// instead of 5 shuffles per value.
-template <int W> __device__ __forceinline__ float warp_transpose_sum_w(float (&v)[W]) {
-    static_assert(W == 8 || W == 16 || W == 32, "W must be 8, 16 or 32");
-    const int lane = threadIdx.x & 31;
-    int m = 16;
-#pragma unroll
-    for (int half = W / 2; half >= 1; half >>= 1, m >>= 1) {
-        const bool up = (lane & m) != 0;
-#pragma unroll
-        for (int k = 0; k < half; ++k) {
-            const float keep = up ? v[k + half] : v[k];
-            const float send = up ? v[k] : v[k + half];
-            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-        }
-    }
-    float r = v[0];
-#pragma unroll
-    for (int o = 16 / W; o >= 1; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-    return r;
-}
-#endif
-
-// Block-wide sums of K values per thread; every thread gets the totals.  `red` holds two halves of
-// NW*32 floats: call sites alternate `half` so one __syncthreads per reduction is enough (a thread can be
-// at most one reduction ahead of the slowest reader, and then it writes the other half).
-template <int K> __device__ __forceinline__ void block_sum(float (&v)[K], float* red, int half) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* r = red + half * (NW * 32);
-#if defined(EPNP_FAST_BLOCKSUM)
-    if constexpr (K > 2) {
-        constexpr int W = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
-        static_assert(K <= 32, "block_sum: at most 32 values");
-        float w[W];
-#pragma unroll
-        for (int k = 0; k < W; ++k) w[k] = k < K ? v[k] : 0.f;
-        const float tot = warp_transpose_sum_w<W>(w);
-        constexpr int SH = W == 8 ? 2 : (W == 16 ? 1 : 0);
-        if ((lane & ((1 << SH) - 1)) == 0 && (lane >> SH) < K) r[warp * 32 + (lane >> SH)] = tot;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < K; ++k) v[k] = (r[k] + r[32 + k]) + (r[64 + k] + r[96 + k]);
-        return;
-    }
-#endif
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) r[warp * 32 + k] = v[k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = (r[k] + r[32 + k]) + (r[64 + k] + r[96 + k]);
-}
-
-__device__ __forceinline__ float block_max(float v, float* red, int half) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* r = red + half * (NW * 32);
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (lane == 0) r[warp * 32] = v;
-    __syncthreads();
-    return fmaxf(fmaxf(r[0], r[32]), fmaxf(r[64], r[96]));
-}
-
-// Evaluate the normal equations at `pose` (shared memory) over all points; result in ev[0..NV).
-template <int DOF, bool CLIP>
-__device__ void eval_normal_eq(const float* pts, int N, const float* pose, const Cam& cam, float delta,
-                               float huber_eps, float* red, float* ev) {
-    constexpr int NV = Dim<DOF>::NV;
-    float R[9], t[3];
-    {
-        float ps[Dim<DOF>::POSE];
-#pragma unroll
-        for (int i = 0; i < Dim<DOF>::POSE; ++i) ps[i] = pose[i];
-        pose_to_rot<DOF>(ps, R);
-        t[0] = ps[0]; t[1] = ps[1]; t[2] = ps[2];
-    }
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    // one PAIR record (4 x LDS.128) per thread and step: 4-way bank conflicts instead of the 16-way a
-    // per-point scalar walk over the 64-byte records would cause
-    const float4* p4 = reinterpret_cast<const float4*>(pts);
-    const int npair = (N + 1) >> 1;
-#if defined(EPNP_LM_PACKED)
-    // experiment (off by default): u-row / v-row of the Jacobian in the two lanes of packed fp32x2 registers
-    {
-        constexpr int NP = Dim<DOF>::NA + DOF;
-        pnp::V2 acc2[NP];
-#pragma unroll
-        for (int i = 0; i < NP; ++i) acc2[i] = pnp::v2splat(0.f);
-        const pnp::V2 kuv[3] = {pnp::v2(cam.k[0], cam.k[3]), pnp::v2(cam.k[1], cam.k[4]), pnp::v2(cam.k[2], cam.k[5])};
-        float cost = 0.f;
-        for (int j = threadIdx.x; j < npair; j += NT) {
-            const float4 q0 = p4[4 * j], q1 = p4[4 * j + 1], q2 = p4[4 * j + 2], q3 = p4[4 * j + 3];
-            point_normal_eq_rows<DOF, CLIP>(R, t, cam, kuv, delta, huber_eps, q0.x, q0.z, q1.x, q1.z, q2.x, q2.z, q3.x,
-                                            acc2, cost);
-            if (2 * j + 1 < N)
-                point_normal_eq_rows<DOF, CLIP>(R, t, cam, kuv, delta, huber_eps, q0.y, q0.w, q1.y, q1.w, q2.y, q2.w,
-                                                q3.y, acc2, cost);
-        }
-#pragma unroll
-        for (int i = 0; i < NP; ++i) acc[i] = acc2[i].x + acc2[i].y;
-        acc[NP] = cost;
-    }
-#else
-    for (int j = threadIdx.x; j < npair; j += NT) {
-        const float4 q0 = p4[4 * j], q1 = p4[4 * j + 1], q2 = p4[4 * j + 2], q3 = p4[4 * j + 3];
-        point_normal_eq<DOF, CLIP>(R, t, cam, delta, huber_eps, q0.x, q0.z, q1.x, -q1.z, -q2.x, q2.z, q3.x, acc);
-        if (2 * j + 1 < N)
-            point_normal_eq<DOF, CLIP>(R, t, cam, delta, huber_eps, q0.y, q0.w, q1.y, -q1.w, -q2.y, q2.w, q3.y, acc);
-    }
-#endif
-    const float tot = warp_transpose_sum(acc);
-    red[(threadIdx.x >> 5) * 32 + (threadIdx.x & 31)] = tot;
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        const int j = threadIdx.x;
-        ev[j] = (red[j] + red[32 + j]) + (red[64 + j] + red[96 + j]);
-    }
-    __syncthreads();
-}
-
-#if defined(EPNP_LM_COST_FIRST)
-// experiment (off by default): Huber cost of ONE pose over all resident points, block-parallel (each thread its share
-// of the pair records, packed fp32x2, rsqrt seed + one Newton step so the value tracks the normal-equation pass's
-// cost to ~1 ulp), every thread gets the total.
-struct RefinedRsqrt {
-#if defined(EPNP_SIMT_EMUL)
-    float operator()(float x) const { return 1.0f / sqrtf(x); }
-#else
-    __device__ __forceinline__ float operator()(float x) const {
-        float y;
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-        return y * fmaf(-0.5f * x * y, y, 1.5f);
-    }
-#endif
-};
-template <int DOF>
-__device__ float block_cost(const float* pts, int N, const float* pose_smem, const Cam& cam, float delta, float* red) {
-    float R[9], P[12], ps[Dim<DOF>::POSE];
-#pragma unroll
-    for (int i = 0; i < Dim<DOF>::POSE; ++i) ps[i] = pose_smem[i];
-    pose_to_rot<DOF>(ps, R);
-    make_proj(cam.k, R, ps, P);
-    float2 P2[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) P2[k] = make_float2(P[k], P[k]);
-    const float4* p4 = reinterpret_cast<const float4*>(pts);
-    const int npair = (N + 1) >> 1;
-    float2 acc = make_float2(0.f, 0.f);
-    for (int j = threadIdx.x; j < npair; j += NT) {
-        const float4 q0 = p4[4 * j], q1 = p4[4 * j + 1], q2 = p4[4 * j + 2], q3 = p4[4 * j + 3];
-        const float2 X = make_float2(q0.x, q0.y), Y = make_float2(q0.z, q0.w), Z = make_float2(q1.x, q1.y);
-        const float2 nu = make_float2(q1.z, q1.w), nv = make_float2(q2.x, q2.y), wu = make_float2(q2.z, q2.w), wv = make_float2(q3.x, q3.y);
-        acc = cam.bounded ? pnp::pair_cost_rsq<true, true>(P2, cam, delta, X, Y, Z, nu, nv, wu, wv, acc, RefinedRsqrt())
-                          : pnp::pair_cost_rsq<false, true>(P2, cam, delta, X, Y, Z, nu, nv, wu, wv, acc, RefinedRsqrt());
-    }
-    float v[1] = {acc.x + acc.y};
-    block_sum<1>(v, red, 1);
-    return v[0];
-}
-#endif
-
-// ------------------------------------------------------------------------------------------------
-// LM / GN solve of the object resident in pts4.  Leaves the solution in sh.lm.pose, the covariance
-// in sh.cov (when want_cov) and writes the requested outputs.
-template <int DOF>
-__device__ void lm_phase(const KArgs& a, SmemHead<DOF>& sh, const float* pts4, const Cam& cam, float delta,
-                         int obj, bool want_cov) {
-    constexpr int PD = Dim<DOF>::POSE;
-    const Params& p = a.p;
-    const int tid = threadIdx.x;
-    const int st = serial_thread(a);
-    PH_DECL;
-    if (tid == st) {
-#pragma unroll
-        for (int i = 0; i < PD; ++i) sh.lm.pose[i] = __ldg(a.pose_init + (size_t)obj * PD + i);
-        sh.lm.radius = p.initial_radius;
-        sh.lm.shrink = 2.0f;
-    }
-    __syncthreads();
-    if (!p.fast_mode) {
-        eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);
-        PH_MARK(a, PH_LM_EVAL);
-        if (tid == st) {
-            lm_adopt<DOF>(sh.lm, sh.ev);
-            if (a.cost_init) a.cost_init[obj] = sh.lm.cost;
-            if (p.lm_iter > 0) lm_propose<DOF>(sh.lm, p);
-        }
-        PH_MARK(a, PH_LM_SERIAL);
-        __syncthreads();
-#if defined(EPNP_LM_COST_FIRST)
-        for (int it = 0; it < p.lm_iter; ++it) {
-            const float cost_new = block_cost<DOF>(pts4, a.N, sh.lm.pose_new, cam, delta, sh.red);
-            if (tid == st) sh.ev[31] = lm_decide<DOF>(sh.lm, cost_new, p) ? 1.f : 0.f;
-            __syncthreads();
-            if (sh.ev[31] != 0.f) {             // accepted (CTA-uniform): linearise at the new pose
-                eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);
-                if (tid == st) lm_adopt<DOF>(sh.lm, sh.ev);
-            }
-            PH_MARK(a, PH_LM_EVAL);
-            if (tid == st && it + 1 < p.lm_iter) lm_propose<DOF>(sh.lm, p);
-            PH_MARK(a, PH_LM_SERIAL);
-            __syncthreads();
-        }
-#else
-        for (int it = 0; it < p.lm_iter; ++it) {
-            eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose_new, cam, delta, p.huber_eps, sh.red, sh.ev);
-            PH_MARK(a, PH_LM_EVAL);
-            if (tid == st) {
-                lm_update<DOF>(sh.lm, sh.ev, p);
-                if (it + 1 < p.lm_iter) lm_propose<DOF>(sh.lm, p);
-            }
-            PH_MARK(a, PH_LM_SERIAL);
-            __syncthreads();
-        }
-#endif
-    } else {
-        for (int it = 0; it < p.lm_iter; ++it) {
-            eval_normal_eq<DOF, false>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);
-            if (tid == st) {
-                lm_adopt<DOF>(sh.lm, sh.ev);                 // kept for covariance / cost (pre-step)
-                if (it == 0 && a.cost_init) a.cost_init[obj] = sh.lm.cost;
-                gn_advance<DOF>(sh.lm.pose, sh.ev, p.eps, sh.lm.pose);
-            }
-            __syncthreads();
-        }
-    }
-    if (tid < PD) a.pose_opt[(size_t)obj * PD + tid] = sh.lm.pose[tid];
-    if (tid == 32 && a.cost) a.cost[obj] = sh.lm.cost;
-    if (want_cov) {
-        if (tid < DOF) {                    // one covariance column per lane (fp64 Cholesky + one solve)
-            float col[DOF];
-            pose_covariance_column<DOF>(sh.lm.a, p.eps, tid, col);
-#pragma unroll
-            for (int i = 0; i < DOF; ++i) sh.cov[i * DOF + tid] = col[i];
-        }
-        __syncthreads();
-        if (a.pose_cov && tid < DOF * DOF) a.pose_cov[(size_t)obj * DOF * DOF + tid] = sh.cov[tid];
-    }
-    PH_MARK(a, PH_COV);
-    if (a.pose_plus) {      // y* (+) one undamped GN step, clip_jac always on (gn_step default)
-        eval_normal_eq<DOF, true>(pts4, a.N, sh.lm.pose, cam, delta, p.huber_eps, sh.red, sh.ev);
-        if (tid == st) {
-            float plus[PD];
-            gn_advance<DOF>(sh.lm.pose, sh.ev, p.eps, plus);
-#pragma unroll
-            for (int i = 0; i < PD; ++i) a.pose_plus[(size_t)obj * PD + i] = plus[i];
-        }
-    }
-    __syncthreads();
-}
-
-// Huber cost of one pose over every resident point: thread-private sweep, every lane reads the same pair
-// record (shared-memory broadcast, 4 x LDS.128 per 2 points) and evaluates two points per instruction with
-// packed fp32x2 arithmetic (SASS FFMA2 / FMUL2 / FADD2).  P2[k] = (P[k], P[k]) is the pre-multiplied
-// projection K[R|t] duplicated into both halves.  Same arithmetic per half as pnp::point_cost.
-__device__ __forceinline__ float2 splat(float x) { return make_float2(x, x); }
-
-template <bool BOUNDED>
-__device__ __forceinline__ float2 pair_cost(const float2 (&P2)[12], const Cam& cam, float2 d2, float2 nhd2,
-                                            const float4 q0, const float4 q1, const float4 q2, const float4 q3) {
-    const float2 X = make_float2(q0.x, q0.y), Y = make_float2(q0.z, q0.w), Z = make_float2(q1.x, q1.y);
-    const float2 nu = make_float2(q1.z, q1.w), nv = make_float2(q2.x, q2.y);
-    const float2 wu = make_float2(q2.z, q2.w), wv = make_float2(q3.x, q3.y);
-    const float2 xh = __ffma2_rn(P2[0], X, __ffma2_rn(P2[1], Y, __ffma2_rn(P2[2], Z, P2[3])));
-    const float2 yh = __ffma2_rn(P2[4], X, __ffma2_rn(P2[5], Y, __ffma2_rn(P2[6], Z, P2[7])));
-    const float2 zh = __ffma2_rn(P2[8], X, __ffma2_rn(P2[9], Y, __ffma2_rn(P2[10], Z, P2[11])));
-    const float2 iz = make_float2(FastRcp()(fmaxf(zh.x, cam.z_min)), FastRcp()(fmaxf(zh.y, cam.z_min)));
-    float2 tx, ty;
-    if (BOUNDED) {
-        float2 px = __fmul2_rn(xh, iz), py = __fmul2_rn(yh, iz);
-        px.x = fminf(fmaxf(px.x, cam.lbx), cam.ubx); px.y = fminf(fmaxf(px.y, cam.lbx), cam.ubx);
-        py.x = fminf(fmaxf(py.x, cam.lby), cam.uby); py.y = fminf(fmaxf(py.y, cam.lby), cam.uby);
-        tx = __fadd2_rn(px, nu); ty = __fadd2_rn(py, nv);
-    } else {
-        tx = __ffma2_rn(xh, iz, nu); ty = __ffma2_rn(yh, iz, nv);
-    }
-    const float2 rx = __fmul2_rn(tx, wu), ry = __fmul2_rn(ty, wv);
-    const float2 s2 = __ffma2_rn(rx, rx, __fmul2_rn(ry, ry));
-    const float2 s = make_float2(FastSqrt()(s2.x), FastSqrt()(s2.y));
-    const float2 inl = __fmul2_rn(s2, splat(0.5f));
-    const float2 outl = __ffma2_rn(s, d2, nhd2);
-    return make_float2(s.x <= d2.x ? inl.x : outl.x, s.y <= d2.x ? inl.y : outl.y);
-}
-
-#if defined(EPNP_SWEEP_RSQ)
-// experiments (off by default), all on pnp::pair_cost_rsq -- one MUFU.RSQ per point instead of RCP + SQRT, Huber
-// without selects, accumulation folded into the last FFMA2:
-//   EPNP_SWEEP_RSQ      the formulation itself
-//   EPNP_SWEEP_NOCLAMP  + drop the z clamp when pose_depth_margin() proves it idle for the whole warp
-//   EPNP_SWEEP_SPLIT    + two samples per thread over half of the points each (pair-record loads amortised)
-#if defined(EPNP_SIMT_EMUL)
-struct SweepRsqrt { float operator()(float x) const { return 1.0f / sqrtf(x); } };
-#else
-struct SweepRsqrt {
-    __device__ __forceinline__ float operator()(float x) const { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-};
-#endif
-template <bool BOUNDED, bool CLAMPZ>
-__device__ __forceinline__ float2 pair_cost_acc(const float2 (&P2)[12], const Cam& cam, float delta, float2 acc,
-                                                const float4 q0, const float4 q1, const float4 q2, const float4 q3) {
-    return pnp::pair_cost_rsq<BOUNDED, CLAMPZ>(P2, cam, delta, make_float2(q0.x, q0.y), make_float2(q0.z, q0.w),
-                                               make_float2(q1.x, q1.y), make_float2(q1.z, q1.w),
-                                               make_float2(q2.x, q2.y), make_float2(q2.z, q2.w),
-                                               make_float2(q3.x, q3.y), acc, SweepRsqrt());
-}
-template <bool BOUNDED, bool CLAMPZ = true>
-__device__ __forceinline__ float sweep_cost(const float4* pts4, int N, const float* P, const Cam& cam, float delta) {
-    float2 P2[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) P2[k] = splat(P[k]);
-    float2 c0 = splat(0.f), c1 = splat(0.f), c2 = splat(0.f), c3 = splat(0.f);
-    const int npair = (N + 1) >> 1;
-    int j = 0;
-    for (; j + 4 <= npair; j += 4) {
-        const float4* q = pts4 + 4 * j;
-        c0 = pair_cost_acc<BOUNDED, CLAMPZ>(P2, cam, delta, c0, q[0], q[1], q[2], q[3]);
-        c1 = pair_cost_acc<BOUNDED, CLAMPZ>(P2, cam, delta, c1, q[4], q[5], q[6], q[7]);
-        c2 = pair_cost_acc<BOUNDED, CLAMPZ>(P2, cam, delta, c2, q[8], q[9], q[10], q[11]);
-        c3 = pair_cost_acc<BOUNDED, CLAMPZ>(P2, cam, delta, c3, q[12], q[13], q[14], q[15]);
-    }
-    for (; j < npair; ++j) {
-        const float4* q = pts4 + 4 * j;
-        c0 = pair_cost_acc<BOUNDED, CLAMPZ>(P2, cam, delta, c0, q[0], q[1], q[2], q[3]);
-    }
-    c0 = __fadd2_rn(c0, c2); c1 = __fadd2_rn(c1, c3);
-    return (c0.x + c0.y) + (c1.x + c1.y);
-}
-#elif defined(EPNP_SWEEP_HUBER_M)
-// experiment (off by default): the shipped sweep arithmetic (reciprocal + square root) with the select-free Huber
-// m (s - m / 2), m = min(s, delta), accumulated by its last FFMA2: 17 instead of 18 packed FP ops per point pair
-// (34 FMA-pipe cycles), no FSETP / FSEL, still 4 MUFU.
-template <bool BOUNDED>
-__device__ __forceinline__ float2 pair_cost_m(const float2 (&P2)[12], const Cam& cam, float delta, float2 acc,
-                                              const float4 q0, const float4 q1, const float4 q2, const float4 q3) {
-    const float2 X = make_float2(q0.x, q0.y), Y = make_float2(q0.z, q0.w), Z = make_float2(q1.x, q1.y);
-    const float2 nu = make_float2(q1.z, q1.w), nv = make_float2(q2.x, q2.y);
-    const float2 wu = make_float2(q2.z, q2.w), wv = make_float2(q3.x, q3.y);
-    const float2 xh = __ffma2_rn(P2[0], X, __ffma2_rn(P2[1], Y, __ffma2_rn(P2[2], Z, P2[3])));
-    const float2 yh = __ffma2_rn(P2[4], X, __ffma2_rn(P2[5], Y, __ffma2_rn(P2[6], Z, P2[7])));
-    const float2 zh = __ffma2_rn(P2[8], X, __ffma2_rn(P2[9], Y, __ffma2_rn(P2[10], Z, P2[11])));
-    const float2 iz = make_float2(FastRcp()(fmaxf(zh.x, cam.z_min)), FastRcp()(fmaxf(zh.y, cam.z_min)));
-    float2 tx, ty;
-    if (BOUNDED) {
-        float2 px = __fmul2_rn(xh, iz), py = __fmul2_rn(yh, iz);
-        px.x = fminf(fmaxf(px.x, cam.lbx), cam.ubx); px.y = fminf(fmaxf(px.y, cam.lbx), cam.ubx);
-        py.x = fminf(fmaxf(py.x, cam.lby), cam.uby); py.y = fminf(fmaxf(py.y, cam.lby), cam.uby);
-        tx = __fadd2_rn(px, nu); ty = __fadd2_rn(py, nv);
-    } else {
-        tx = __ffma2_rn(xh, iz, nu); ty = __ffma2_rn(yh, iz, nv);
-    }
-    const float2 rx = __fmul2_rn(tx, wu), ry = __fmul2_rn(ty, wv);
-    const float2 s2 = __ffma2_rn(rx, rx, __fmul2_rn(ry, ry));
-    const float2 s = make_float2(FastSqrt()(s2.x), FastSqrt()(s2.y));
-    const float2 m = make_float2(fminf(s.x, delta), fminf(s.y, delta));
-    return __ffma2_rn(m, __ffma2_rn(m, splat(-0.5f), s), acc);
-}
-template <bool BOUNDED>
-__device__ __forceinline__ float sweep_cost(const float4* pts4, int N, const float* P, const Cam& cam, float delta) {
-    float2 P2[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) P2[k] = splat(P[k]);
-    float2 c0 = splat(0.f), c1 = splat(0.f), c2 = splat(0.f), c3 = splat(0.f);
-    const int npair = (N + 1) >> 1;
-    int j = 0;
-    for (; j + 4 <= npair; j += 4) {
-        const float4* q = pts4 + 4 * j;
-        c0 = pair_cost_m<BOUNDED>(P2, cam, delta, c0, q[0], q[1], q[2], q[3]);
-        c1 = pair_cost_m<BOUNDED>(P2, cam, delta, c1, q[4], q[5], q[6], q[7]);
-        c2 = pair_cost_m<BOUNDED>(P2, cam, delta, c2, q[8], q[9], q[10], q[11]);
-        c3 = pair_cost_m<BOUNDED>(P2, cam, delta, c3, q[12], q[13], q[14], q[15]);
-    }
-    for (; j < npair; ++j) {
-        const float4* q = pts4 + 4 * j;
-        c0 = pair_cost_m<BOUNDED>(P2, cam, delta, c0, q[0], q[1], q[2], q[3]);
-    }
-    c0 = __fadd2_rn(c0, c2); c1 = __fadd2_rn(c1, c3);
-    return (c0.x + c0.y) + (c1.x + c1.y);
-}
-#else
-template <bool BOUNDED>
-__device__ __forceinline__ float sweep_cost(const float4* pts4, int N, const float* P, const Cam& cam, float delta) {
-    float2 P2[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) P2[k] = splat(P[k]);
-    const float2 d2 = splat(delta), nhd2 = splat(-0.5f * delta * delta);
-    float2 c0 = splat(0.f), c1 = splat(0.f), c2 = splat(0.f), c3 = splat(0.f);
-    const int npair = (N + 1) >> 1;
-    int j = 0;
-    for (; j + 4 <= npair; j += 4) {            // 8 points in flight per thread
-        const float4* q = pts4 + 4 * j;
-        c0 = __fadd2_rn(c0, pair_cost<BOUNDED>(P2, cam, d2, nhd2, q[0], q[1], q[2], q[3]));
-        c1 = __fadd2_rn(c1, pair_cost<BOUNDED>(P2, cam, d2, nhd2, q[4], q[5], q[6], q[7]));
-        c2 = __fadd2_rn(c2, pair_cost<BOUNDED>(P2, cam, d2, nhd2, q[8], q[9], q[10], q[11]));
-        c3 = __fadd2_rn(c3, pair_cost<BOUNDED>(P2, cam, d2, nhd2, q[12], q[13], q[14], q[15]));
-    }
-    for (; j < npair; ++j) {
-        const float4* q = pts4 + 4 * j;
-        c0 = __fadd2_rn(c0, pair_cost<BOUNDED>(P2, cam, d2, nhd2, q[0], q[1], q[2], q[3]));
-    }
-    c0 = __fadd2_rn(c0, c2); c1 = __fadd2_rn(c1, c3);
-    return (c0.x + c0.y) + (c1.x + c1.y);
-}
-#endif
-
-template <int DOF>
-__device__ __forceinline__ float pose_cost(const float* pts, int N, const float* pose, const Cam& cam, float delta) {
-    float R[9], P[12];
-    pose_to_rot<DOF>(pose, R);
-    make_proj(cam.k, R, pose, P);
-    const float4* pts4 = reinterpret_cast<const float4*>(pts);
-    return cam.bounded ? sweep_cost<true>(pts4, N, P, cam, delta) : sweep_cost<false>(pts4, N, P, cam, delta);
-}
-
-#if defined(EPNP_SWEEP_NOCLAMP) || defined(EPNP_SWEEP_SPLIT)
-// Largest |X| over the resident points (every thread gets it): the `radius` of pose_depth_margin.
-__device__ __forceinline__ float object_radius(const float* pts, int N, float* red, int half) {
-    const float4* p4 = reinterpret_cast<const float4*>(pts);
-    const int npair = (N + 1) >> 1;
-    float r2 = 0.f;
-    for (int j = threadIdx.x; j < npair; j += NT) {
-        const float4 q0 = p4[4 * j], q1 = p4[4 * j + 1];
-        r2 = fmaxf(r2, fmaxf(fmaf(q0.x, q0.x, fmaf(q0.z, q0.z, q1.x * q1.x)), fmaf(q0.y, q0.y, fmaf(q0.w, q0.w, q1.y * q1.y))));
-    }
-    return sqrtf(block_max(r2, red, half));
-}
-
-// pose_cost with the clamp-free loop when the whole warp's poses keep every point in front of z_min
-// (radius < 0: unknown, always clamp).
-template <int DOF>
-__device__ __forceinline__ float pose_cost(const float* pts, int N, const float* pose, const Cam& cam, float delta,
-                                           float radius) {
-    float R[9], P[12];
-    pose_to_rot<DOF>(pose, R);
-    make_proj(cam.k, R, pose, P);
-    const float4* pts4 = reinterpret_cast<const float4*>(pts);
-    bool free_z = false;
-#if defined(EPNP_SWEEP_NOCLAMP)
-    if (radius >= 0.f) free_z = __all_sync(__activemask(), pose_depth_margin(P, radius, cam.z_min) >= 0.f);
-#endif
-    if (free_z) return cam.bounded ? sweep_cost<true, false>(pts4, N, P, cam, delta) : sweep_cost<false, false>(pts4, N, P, cam, delta);
-    return cam.bounded ? sweep_cost<true, true>(pts4, N, P, cam, delta) : sweep_cost<false, true>(pts4, N, P, cam, delta);
-}
-#endif
-
-#if defined(EPNP_SWEEP_SPLIT)
-// Two poses over the pair records [j0, j1): every record is loaded once and used for both.
-template <bool BOUNDED, bool CLAMPZ>
-__device__ __forceinline__ void sweep_cost2(const float4* pts4, int j0, int j1, const float* Pa, const float* Pb,
-                                            const Cam& cam, float delta, float& ca, float& cb) {
-    float2 A2[12], B2[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) { A2[k] = splat(Pa[k]); B2[k] = splat(Pb[k]); }
-    float2 a0 = splat(0.f), a1 = splat(0.f), b0 = splat(0.f), b1 = splat(0.f);
-    int j = j0;
-    for (; j + 2 <= j1; j += 2) {
-        const float4* q = pts4 + 4 * j;
-        const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6], q7 = q[7];
-        a0 = pair_cost_acc<BOUNDED, CLAMPZ>(A2, cam, delta, a0, q0, q1, q2, q3);
-        b0 = pair_cost_acc<BOUNDED, CLAMPZ>(B2, cam, delta, b0, q0, q1, q2, q3);
-        a1 = pair_cost_acc<BOUNDED, CLAMPZ>(A2, cam, delta, a1, q4, q5, q6, q7);
-        b1 = pair_cost_acc<BOUNDED, CLAMPZ>(B2, cam, delta, b1, q4, q5, q6, q7);
-    }
-    for (; j < j1; ++j) {
-        const float4* q = pts4 + 4 * j;
-        const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-        a0 = pair_cost_acc<BOUNDED, CLAMPZ>(A2, cam, delta, a0, q0, q1, q2, q3);
-        b0 = pair_cost_acc<BOUNDED, CLAMPZ>(B2, cam, delta, b0, q0, q1, q2, q3);
-    }
-    a0 = __fadd2_rn(a0, a1); b0 = __fadd2_rn(b0, b1);
-    ca = a0.x + a0.y; cb = b0.x + b0.y;
-}
-
-// Costs of the S new samples smp[m0 .. m0+S) of an AMIS iteration.  Work item w = (sample pair k, point half h):
-// the two halves of a sample's cost land in cst[m] (h = 0) and lw[m] (h = 1, free until the weights pass, which
-// folds it in).  Odd S: whole sweeps, lw[m] = 0.
-template <int DOF>
-__device__ void sweep_new_samples(const float* pts, int N, const float* smp, float* cst, float* lw, int m0, int S,
-                                  const Cam& cam, float delta, float radius) {
-    constexpr int PD = Dim<DOF>::POSE;
-    const float4* pts4 = reinterpret_cast<const float4*>(pts);
-    if (S & 1) {
-        for (int s = threadIdx.x; s < S; s += NT) {
-            float pose[PD];
-#pragma unroll
-            for (int k = 0; k < PD; ++k) pose[k] = smp[(m0 + s) * PD + k];
-            cst[m0 + s] = pose_cost<DOF>(pts, N, pose, cam, delta, radius);
-            lw[m0 + s] = 0.f;
-        }
-        return;
-    }
-    const int npair = (N + 1) >> 1, H = S >> 1;
-    const int jmid = min(npair, ((npair >> 1) + 1) & ~1);
-    for (int w = threadIdx.x; w < S; w += NT) {
-        const int k = w % H, h = w / H;
-        const int ma = m0 + 2 * k, mb = ma + 1;
-        float Pa[12], Pb[12];
-        {
-            float pose[PD], R[9];
-#pragma unroll
-            for (int c = 0; c < PD; ++c) pose[c] = smp[ma * PD + c];
-            pose_to_rot<DOF>(pose, R);
-            make_proj(cam.k, R, pose, Pa);
-#pragma unroll
-            for (int c = 0; c < PD; ++c) pose[c] = smp[mb * PD + c];
-            pose_to_rot<DOF>(pose, R);
-            make_proj(cam.k, R, pose, Pb);
-        }
-        bool free_z = false;
-#if defined(EPNP_SWEEP_NOCLAMP)
-        if (radius >= 0.f)
-            free_z = __all_sync(__activemask(), fminf(pose_depth_margin(Pa, radius, cam.z_min),
-                                                      pose_depth_margin(Pb, radius, cam.z_min)) >= 0.f);
-#endif
-        const int j0 = h ? jmid : 0, j1 = h ? npair : jmid;
-        float ca, cb;
-        if (free_z) {
-            if (cam.bounded) sweep_cost2<true, false>(pts4, j0, j1, Pa, Pb, cam, delta, ca, cb);
-            else sweep_cost2<false, false>(pts4, j0, j1, Pa, Pb, cam, delta, ca, cb);
-        } else {
-            if (cam.bounded) sweep_cost2<true, true>(pts4, j0, j1, Pa, Pb, cam, delta, ca, cb);
-            else sweep_cost2<false, true>(pts4, j0, j1, Pa, Pb, cam, delta, ca, cb);
-        }
-        float* dst = h ? lw : cst;
-        dst[ma] = ca; dst[mb] = cb;
-    }
-}
-#endif
-
-#if defined(EPNP_SWEEP_MMA)
-// experiment (off by default): the sweep's 3x4 projection on the tensor pipe through the legacy warp-level
-// mma.sync.m16n8k8 TF32 instruction (SASS HMMA.1688.F32.TF32), operands in registers -- no TMEM, no descriptors, no
-// extra point storage.  Error-compensated 3xTF32: D = [P_hi | P_lo] [X_hi ; X_hi] + [P_hi | P_lo] [X_lo ; 0].
-//   work item = (tile of 16 samples, half of the points); a warp takes items warp, warp + 4, ...
-//   A fragments: P[s][4 r + t] of samples s0 = 16 ti + g and s0 + 8 from the table `ptab` (S x 12, built here)
-//   B fragments: coordinate t of point 8 tl + g, one LDS.32 from the pair records, split with two ALU ops
-//   D fragments: (s0 | s0 + 8) x points (2t, 2t + 1) -- the register pairs the packed Huber tail consumes
-// Returns false (nothing done) when the shape does not fit; the caller then runs the CUDA-core path.
-__device__ __forceinline__ float tf32_hi_bits(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[4], float b0, float b1) {
-#if defined(EPNP_SIMT_EMUL)
-    simt::mma_m16n8k8_tf32(d, a, b0, b1);
-#else
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])),
-                   "r"(__float_as_uint(a[3])), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
-#endif
-}
-
-template <int DOF, bool BOUNDED>
-__device__ __forceinline__ void sweep_mma_items(const float* pts, int N, const float* smp, const float* ptab, float* cst,
-                                                float* lw, int m0, int S, const Cam& cam, float delta, float radius);
-
-template <int DOF>
-__device__ bool sweep_new_samples_mma(const float* pts, int N, const float* smp, float* ptab, float* cst, float* lw,
-                                      int m0, int S, const Cam& cam, float delta, float radius) {
-    if ((S & 15) != 0) return false;
-    constexpr int PD = Dim<DOF>::POSE;
-    if (ptab != nullptr) {                               // the new samples' K[R|t], one row of the table each
-        for (int s = threadIdx.x; s < S; s += NT) {
-            float pose[PD], R[9], P[12];
-#pragma unroll
-            for (int c = 0; c < PD; ++c) pose[c] = smp[(m0 + s) * PD + c];
-            pose_to_rot<DOF>(pose, R);
-            make_proj(cam.k, R, pose, P);
-#pragma unroll
-            for (int c = 0; c < 12; ++c) ptab[s * 12 + c] = P[c];
-        }
-        __syncthreads();
-    }                                                    // no table (no idle shared memory): columns computed per item
-    if (cam.bounded) sweep_mma_items<DOF, true>(pts, N, smp, ptab, cst, lw, m0, S, cam, delta, radius);
-    else sweep_mma_items<DOF, false>(pts, N, smp, ptab, cst, lw, m0, S, cam, delta, radius);
-    return true;
-}
-
-// Column t of K [R | t] of one sample (what a lane's A fragments hold), straight from the pose.
-template <int DOF>
-__device__ __forceinline__ void proj_column(const float* pose, const float* K, int t, float (&col)[3]) {
-    float R[9];
-    pose_to_rot<DOF>(pose, R);
-    const float v0 = t == 0 ? R[0] : (t == 1 ? R[1] : (t == 2 ? R[2] : pose[0]));
-    const float v1 = t == 0 ? R[3] : (t == 1 ? R[4] : (t == 2 ? R[5] : pose[1]));
-    const float v2 = t == 0 ? R[6] : (t == 1 ? R[7] : (t == 2 ? R[8] : pose[2]));
-#pragma unroll
-    for (int r = 0; r < 3; ++r) col[r] = K[r * 3 + 0] * v0 + K[r * 3 + 1] * v1 + K[r * 3 + 2] * v2;
-}
-
-template <int DOF, bool BOUNDED>
-__device__ __forceinline__ void sweep_mma_items(const float* pts, int N, const float* smp, const float* ptab, float* cst,
-                                                float* lw, int m0, int S, const Cam& cam, float delta, float radius) {
-    constexpr int PD = Dim<DOF>::POSE;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    const int npair = (N + 1) >> 1, npts = 2 * npair;    // even-padded point count (the pad carries zero weights)
-    const int ntile = (npts + 7) >> 3, tmid = (ntile + 1) >> 1, T = S >> 4;
-    for (int item = warp; item < 2 * T; item += NW) {
-        const int ti = item >> 1, h = item & 1;
-        const int s0 = ti * 16 + g, s1 = s0 + 8;
-        float ah[3][2], al[3][2], c0v[3], c1v[3];
-        if (ptab != nullptr) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r) { c0v[r] = ptab[s0 * 12 + 4 * r + t]; c1v[r] = ptab[s1 * 12 + 4 * r + t]; }
-        } else {
-            float pose[PD];
-#pragma unroll
-            for (int c = 0; c < PD; ++c) pose[c] = smp[(m0 + s0) * PD + c];
-            proj_column<DOF>(pose, cam.k, t, c0v);
-#pragma unroll
-            for (int c = 0; c < PD; ++c) pose[c] = smp[(m0 + s1) * PD + c];
-            proj_column<DOF>(pose, cam.k, t, c1v);
-        }
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            ah[r][0] = tf32_hi_bits(c0v[r]); al[r][0] = c0v[r] - ah[r][0];
-            ah[r][1] = tf32_hi_bits(c1v[r]); al[r][1] = c1v[r] - ah[r][1];
-        }
-        // ONE A quad per projection row, [P_hi | P_lo]: the second MMA multiplies it by [X_lo ; 0], so the unwanted
-        // P_lo X_lo term drops out without a second set of fragments
-        float a1[3][4];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) { a1[r][0] = ah[r][0]; a1[r][1] = ah[r][1]; a1[r][2] = al[r][0]; a1[r][3] = al[r][1]; }
-        V2 acc0 = v2splat(0.f), acc1 = v2splat(0.f);
-        const int t0 = h ? tmid : 0, t1 = h ? ntile : tmid;
-        const int full1 = min(t1, npts >> 3);            // tiles [t0, full1) hold 8 real points each
-        bool free_z = false;
-#if defined(EPNP_SWEEP_NOCLAMP)
-        if (radius >= 0.f) {
-            // pose_depth_margin of the lane's two samples from the third projection row, whose four entries sit in
-            // the four lanes of the group: |P[8..10]| and P[11] by two exchanges
-            float q0 = (t < 3) ? c0v[2] * c0v[2] : 0.f, q1 = (t < 3) ? c1v[2] * c1v[2] : 0.f;
-            q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
-            q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
-            const float tz0 = __shfl_sync(0xffffffffu, c0v[2], (lane & ~3) | 3), tz1 = __shfl_sync(0xffffffffu, c1v[2], (lane & ~3) | 3);
-            const float r0 = sqrtf(q0) * radius, r1 = sqrtf(q1) * radius;
-            const float m0z = (tz0 - r0) - cam.z_min - 1e-5f * (fabsf(tz0) + r0 + cam.z_min);
-            const float m1z = (tz1 - r1) - cam.z_min - 1e-5f * (fabsf(tz1) + r1 + cam.z_min);
-            free_z = __all_sync(0xffffffffu, fminf(m0z, m1z) >= 0.f);
-        }
-#endif
-        // lane-private cursors: coordinate t (pad slot 14 holds the homogeneous 1) of point 8 tl + g, record of pair 4 tl + t
-        const float* bp = pts + (g >> 1) * 16 + (t < 3 ? 2 * t : 14) + (g & 1) + t0 * 64;
-        const float* up = pts + t * 16 + t0 * 64;
-        if (free_z) {
-            for (int tl = t0; tl < full1; ++tl, bp += 64, up += 64) {
-                const float c = *bp;
-                const float bh = tf32_hi_bits(c), bl = c - bh;
-                float d[3][4];
-    #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.f;
-                    mma_tf32_16x8x8(d[r], a1[r], bh, bh);
-                    mma_tf32_16x8x8(d[r], a1[r], bl, 0.f);
-                }
-                const float2 nu2 = *reinterpret_cast<const float2*>(up + 6);
-                const float4 mid = *reinterpret_cast<const float4*>(up + 8);
-                const float2 wv2 = *reinterpret_cast<const float2*>(up + 12);
-                const V2 nu = v2(nu2.x, nu2.y), nv = v2(mid.x, mid.y), wu = v2(mid.z, mid.w), wv = v2(wv2.x, wv2.y);
-                acc0 = pair_cost_tail<BOUNDED, false>(v2(d[0][0], d[0][1]), v2(d[1][0], d[1][1]), v2(d[2][0], d[2][1]), cam, delta, nu, nv, wu, wv, acc0, SweepRsqrt());
-                acc1 = pair_cost_tail<BOUNDED, false>(v2(d[0][2], d[0][3]), v2(d[1][2], d[1][3]), v2(d[2][2], d[2][3]), cam, delta, nu, nv, wu, wv, acc1, SweepRsqrt());
-            }
-        } else {
-            for (int tl = t0; tl < full1; ++tl, bp += 64, up += 64) {
-                const float c = *bp;
-                const float bh = tf32_hi_bits(c), bl = c - bh;
-                float d[3][4];
-    #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.f;
-                    mma_tf32_16x8x8(d[r], a1[r], bh, bh);
-                    mma_tf32_16x8x8(d[r], a1[r], bl, 0.f);
-                }
-                const float2 nu2 = *reinterpret_cast<const float2*>(up + 6);
-                const float4 mid = *reinterpret_cast<const float4*>(up + 8);
-                const float2 wv2 = *reinterpret_cast<const float2*>(up + 12);
-                const V2 nu = v2(nu2.x, nu2.y), nv = v2(mid.x, mid.y), wu = v2(mid.z, mid.w), wv = v2(wv2.x, wv2.y);
-                acc0 = pair_cost_tail<BOUNDED>(v2(d[0][0], d[0][1]), v2(d[1][0], d[1][1]), v2(d[2][0], d[2][1]), cam, delta, nu, nv, wu, wv, acc0, SweepRsqrt());
-                acc1 = pair_cost_tail<BOUNDED>(v2(d[0][2], d[0][3]), v2(d[1][2], d[1][3]), v2(d[2][2], d[2][3]), cam, delta, nu, nv, wu, wv, acc1, SweepRsqrt());
-            }
-        }
-        for (int tl = max(t0, full1); tl < t1; ++tl) {   // the (at most one) partial tile: clamped loads, masked weights
-            const int pt = min(tl * 8 + g, npts - 1);
-            const float c = (t < 3) ? pts[(pt >> 1) * 16 + 2 * t + (pt & 1)] : 1.0f;
-            const float bh = tf32_hi_bits(c), bl = c - bh;
-            float d[3][4];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                d[r][0] = d[r][1] = d[r][2] = d[r][3] = 0.f;
-                mma_tf32_16x8x8(d[r], a1[r], bh, bh);
-                mma_tf32_16x8x8(d[r], a1[r], bl, 0.f);
-            }
-            const int pair = tl * 4 + t;
-            const bool valid = pair < npair;
-            const float* rec = pts + min(pair, npair - 1) * 16;
-            const V2 nu = v2(rec[6], rec[7]), nv = v2(rec[8], rec[9]);
-            const V2 wu = valid ? v2(rec[10], rec[11]) : v2splat(0.f), wv = valid ? v2(rec[12], rec[13]) : v2splat(0.f);
-            acc0 = pair_cost_tail<BOUNDED>(v2(d[0][0], d[0][1]), v2(d[1][0], d[1][1]), v2(d[2][0], d[2][1]), cam, delta, nu, nv, wu, wv, acc0, SweepRsqrt());
-            acc1 = pair_cost_tail<BOUNDED>(v2(d[0][2], d[0][3]), v2(d[1][2], d[1][3]), v2(d[2][2], d[2][3]), cam, delta, nu, nv, wu, wv, acc1, SweepRsqrt());
-        }
-        float c0 = acc0.x + acc0.y, c1 = acc1.x + acc1.y;
-        c0 += __shfl_xor_sync(0xffffffffu, c0, 1); c0 += __shfl_xor_sync(0xffffffffu, c0, 2);
-        c1 += __shfl_xor_sync(0xffffffffu, c1, 1); c1 += __shfl_xor_sync(0xffffffffu, c1, 2);
-        if (t == 0) {
-            float* dst = h ? lw : cst;
-            dst[m0 + s0] = c0; dst[m0 + s1] = c1;
-        }
-    }
-}
-#endif
-
-#if defined(EPNP_AMIS_LSE)
-// experiment (off by default): the mixture density of a sample is kept as ONE running log-sum-exp over the proposals
-// seen so far instead of one log-density per (proposal, sample) -- (I - 1) * M floats less shared memory.
-struct RunningLse {
-    float top, acc;
-    __device__ __forceinline__ void start(float lp) { top = lp; acc = 1.f; }
-    __device__ __forceinline__ void add(float lp) {
-        if (lp > top) { acc = fmaf(acc, expf(top - lp), 1.f); top = lp; }
-        else acc += expf(lp - top);
-    }
-    __device__ __forceinline__ float value() const { return top + logf(acc); }
-};
-__device__ __forceinline__ float log_add_exp(float a, float b) {
-    const float hi = fmaxf(a, b), lo = fminf(a, b);
-    return (lo == -CUDART_INF_F) ? hi : hi + log1pf(expf(lo - hi));
-}
-#endif
-
-// ------------------------------------------------------------------------------------------------
-// AMIS loop for the resident object (6DoF).  sh.prop[0] must not be set yet; pose / cov are read from
-// pose_opt[7] / cov[36] (shared or registers of thread 0 -- passed as shared pointers).
-__device__ void amis_phase6(const KArgs& a, SmemHead<6>& sh, const float* pts4, float* smp, float* cst,
-                            float* logp, float* lw, const Cam& cam, float delta, int obj,
-                            const float* pose_opt, const float* cov EPNP_PTAB_PARAM) {
-    const Params& p = a.p;
-    const int tid = threadIdx.x;
-    const int M = p.mc_samples, I = p.mc_iter, S = M / I;
-    const bool injected = a.noise_n3 != nullptr;
-    const int st = serial_thread(a);
-    PH_DECL;
-
-    if (tid == st) initial_fit6(pose_opt, cov, p.acg_dispersion, sh.prop[0]);
-    PH_MARK(a, PH_INIT_FIT);
-#if defined(EPNP_SWEEP_NOCLAMP)
-    const float radius = object_radius(pts4, a.N, sh.red, 0);
-#elif defined(EPNP_SWEEP_SPLIT)
-    const float radius = -1.f;
-#endif
-    __syncthreads();
-
-    for (int i = 0; i < I; ++i) {
-        // ---- draw, cost, densities of the new samples (one sample per thread and pass)
-        for (int s = tid; s < S; s += NT) {
-            const int m = i * S + s;
-            float n3[3], n4[4], chi2;
-            if (injected) {
-                const size_t g = (size_t)obj * M + m;
-                n3[0] = __ldg(a.noise_n3 + g * 3); n3[1] = __ldg(a.noise_n3 + g * 3 + 1); n3[2] = __ldg(a.noise_n3 + g * 3 + 2);
-                chi2 = __ldg(a.noise_chi2 + g);
-                n4[0] = __ldg(a.noise_rot + g * 4); n4[1] = __ldg(a.noise_rot + g * 4 + 1);
-                n4[2] = __ldg(a.noise_rot + g * 4 + 2); n4[3] = __ldg(a.noise_rot + g * 4 + 3);
-            } else {
-                draw_base_noise(a.seed, a.obj_offset + (uint32_t)obj, (uint32_t)m, n3, chi2, n4);
-            }
-            float q[7];
-            proposal_draw6(sh.prop[i], n3, chi2, n4, q);
-#pragma unroll
-            for (int k = 0; k < 7; ++k) smp[m * 7 + k] = q[k];
-            float* out = a.pose_samples + ((size_t)obj * M + m) * 7;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) out[k] = q[k];
-#if defined(EPNP_SWEEP_SPLIT)
-            // cost: sweep_new_samples below, once every new sample of the iteration is in shared memory
-#elif defined(EPNP_SWEEP_NOCLAMP)
-            cst[m] = pose_cost<6>(pts4, a.N, q, cam, delta, radius);
-#else
-            cst[m] = pose_cost<6>(pts4, a.N, q, cam, delta);
-#endif
-#if defined(EPNP_AMIS_LSE)
-            {
-                RunningLse l;
-                l.start(proposal_logpdf6(sh.prop[0], q));
-                for (int j = 1; j <= i; ++j) l.add(proposal_logpdf6(sh.prop[j], q));
-                logp[m] = l.value();
-            }
-#else
-            for (int j = 0; j <= i; ++j) logp[j * M + m] = proposal_logpdf6(sh.prop[j], q);
-#endif
-        }
-#if defined(EPNP_SWEEP_SPLIT)
-        __syncthreads();
-#if defined(EPNP_NO_LW)
-        float* const half1 = a.logw + (size_t)obj * M;
-#else
-        float* const half1 = lw;
-#endif
-#if defined(EPNP_SWEEP_MMA)
-        if (!sweep_new_samples_mma<6>(pts4, a.N, smp, ptab, cst, half1, i * S, S, cam, delta, radius))
-#endif
-        sweep_new_samples<6>(pts4, a.N, smp, cst, half1, i * S, S, cam, delta, radius);
-#endif
-        PH_MARK(a, PH_DRAW_SWEEP);
-        // ---- the new proposal on all earlier samples
-        for (int m = tid; m < i * S; m += NT) {
-            float q[7];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) q[k] = smp[m * 7 + k];
-#if defined(EPNP_AMIS_LSE)
-            logp[m] = log_add_exp(logp[m], proposal_logpdf6(sh.prop[i], q));
-#else
-            logp[i * M + m] = proposal_logpdf6(sh.prop[i], q);
-#endif
-        }
-        __syncthreads();
-        PH_MARK(a, PH_LOGP_OLD);
-        // ---- mixture density and log-weights of all samples so far
-        const int n = (i + 1) * S;
-        const float log_cnt = logf((float)(i + 1));
-        float mx = -CUDART_INF_F;
-        for (int m = tid; m < n; m += NT) {
-#if defined(EPNP_AMIS_LSE)
-            const float top = logp[m], acc = 1.f;               // logp[m] already is the log-sum-exp
-#else
-            float top = logp[m];
-            for (int j = 1; j <= i; ++j) top = fmaxf(top, logp[j * M + m]);
-            float acc = 0.f;
-            for (int j = 0; j <= i; ++j) acc += expf(logp[j * M + m] - top);
-#endif
-#if defined(EPNP_SWEEP_SPLIT)
-            float cm = cst[m];
-#if defined(EPNP_NO_LW)
-            if (m >= i * S) { cm += a.logw[(size_t)obj * M + m]; cst[m] = cm; }   // second half parked in the output slot
-#else
-            if (m >= i * S) { cm += lw[m]; cst[m] = cm; }       // fold the second point half of a new sample in
-#endif
-            const float v = -cm - ((top + logf(acc)) - log_cnt);
-#else
-            const float v = -cst[m] - ((top + logf(acc)) - log_cnt);
-#endif
-#if defined(EPNP_NO_LW)
-            if (i == I - 1) a.logw[(size_t)obj * M + m] = v;    // n == M on the last iteration: every slot gets its value
-#else
-            lw[m] = v;
-#endif
-            mx = fmaxf(mx, v);
-        }
-        PH_MARK(a, PH_WEIGHTS);
-        if (i == I - 1) {
-#if !defined(EPNP_NO_LW)
-            for (int m = tid; m < M; m += NT) a.logw[(size_t)obj * M + m] = lw[m];
-#endif
-            PH_MARK(a, PH_OUTPUT);
-            break;
-        }
-        // ---- refit proposal i+1 to the weighted samples (estimate_params, epropnp.py:317-342).
-        // Four block reductions, one barrier each:
-        //   A  max of the log-weights
-        //   B  e = exp(lw - max): sum e, sum e t, and ACG fixed-point iteration 1 (Lambda_0 = I, so
-        //      M = q.q) -- the normalisation of the weights cancels in Lambda
-        //   C  translation covariance about the mean (+ ACG iteration 2)
-        //   D+ remaining ACG iterations
-        mx = block_max(mx, sh.red, 0);
-        float lam10[10];
-        float mean[3], inv_sum;
-        {
-            float acc[15];
-#pragma unroll
-            for (int r = 0; r < 15; ++r) acc[r] = 0.f;
-            for (int m = tid; m < n; m += NT) {
-                const float e = LW_E(m);
-                LW_E_STORE(m, e);
-                const float* s7 = smp + m * 7;
-                acc[0] += e;
-                acc[1] = fmaf(e, s7[0], acc[1]); acc[2] = fmaf(e, s7[1], acc[2]); acc[3] = fmaf(e, s7[2], acc[3]);
-                const float* q = s7 + 3;
-                const float mq = fmaxf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3], p.amis_eps);
-                const float wm = e / mq;
-                acc[4] += wm;
-                int idx = 5;
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
-            }
-            block_sum<15>(acc, sh.red, 1);
-            inv_sum = 1.0f / acc[0];
-            mean[0] = acc[1] * inv_sum; mean[1] = acc[2] * inv_sum; mean[2] = acc[3] * inv_sum;
-            const float inv0 = 1.0f / acc[4];
-#pragma unroll
-            for (int r = 0; r < 10; ++r) lam10[r] = acc[5 + r] * inv0;
-            lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
-        }
-        if (p.acg_mle_iter == 0) {          // degenerate configuration: Lambda stays the identity
-#pragma unroll
-            for (int r = 0; r < 10; ++r) lam10[r] = 0.f;
-            lam10[0] = lam10[4] = lam10[7] = lam10[9] = 1.f;
-        }
-        float tc[6];
-        {
-            const bool more = p.acg_mle_iter >= 2;
-            float lam_inv[16];
-            if (more) acg_scatter_inverse(lam10, lam_inv);
-            float acc[17];
-#pragma unroll
-            for (int r = 0; r < 17; ++r) acc[r] = 0.f;
-            for (int m = tid; m < n; m += NT) {
-                const float w = LW_W(m);                                 // normalised softmax weight
-                LW_W_STORE(m, w);
-                const float* s7 = smp + m * 7;
-                const float d0 = s7[0] - mean[0], d1 = s7[1] - mean[1], d2 = s7[2] - mean[2];
-                acc[11] = fmaf(w * d0, d0, acc[11]); acc[12] = fmaf(w * d0, d1, acc[12]); acc[13] = fmaf(w * d0, d2, acc[13]);
-                acc[14] = fmaf(w * d1, d1, acc[14]); acc[15] = fmaf(w * d1, d2, acc[15]); acc[16] = fmaf(w * d2, d2, acc[16]);
-                if (more) {
-                    const float* q = s7 + 3;
-                    const float wm = w / fmaxf(quad4(lam_inv, q), p.amis_eps);
-                    acc[0] += wm;
-                    int idx = 1;
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
-                }
-            }
-            block_sum<17>(acc, sh.red, 0);
-#pragma unroll
-            for (int r = 0; r < 6; ++r) tc[r] = acc[11 + r];
-            if (more) {
-                const float inv0 = 1.0f / acc[0];
-#pragma unroll
-                for (int r = 0; r < 10; ++r) lam10[r] = acc[1 + r] * inv0;
-                lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
-            }
-        }
-        for (int itr = 2; itr < p.acg_mle_iter; ++itr) {
-            float lam_inv[16];
-            acg_scatter_inverse(lam10, lam_inv);
-            float acc[11];
-#pragma unroll
-            for (int r = 0; r < 11; ++r) acc[r] = 0.f;
-            for (int m = tid; m < n; m += NT) {
-                const float* q = smp + m * 7 + 3;
-#if defined(EPNP_NO_LW)
-                const float wm = LW_W(m) / fmaxf(quad4(lam_inv, q), p.amis_eps);
-#else
-                const float wm = lw[m] / fmaxf(quad4(lam_inv, q), p.amis_eps);
-#endif
-                acc[0] += wm;
-                int idx = 1;
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
-            }
-            block_sum<11>(acc, sh.red, (itr + 1) & 1);
-            const float inv0 = 1.0f / acc[0];
-#pragma unroll
-            for (int r = 0; r < 10; ++r) lam10[r] = acc[1 + r] * inv0;
-            lam10[0] += p.amis_eps; lam10[4] += p.amis_eps; lam10[7] += p.amis_eps; lam10[9] += p.amis_eps;
-        }
-        PH_MARK(a, PH_REFIT_SUMS);
-        if (tid == st) {
-            refit_finish6(mean, tc, lam10, p.acg_dispersion, sh.prop[i + 1]);
-        }
-        PH_MARK(a, PH_REFIT_FINISH);
-        __syncthreads();
-    }
-    if (a.proposals && tid < I) {
-        float* o = a.proposals + ((size_t)obj * I + tid) * PROP_FLOATS;
-        const Proposal6& pr = sh.prop[tid];
-        o[0] = pr.mu[0]; o[1] = pr.mu[1]; o[2] = pr.mu[2];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) o[3 + r] = pr.lt[r];
-#pragma unroll
-        for (int r = 0; r < 10; ++r) o[9 + r] = pr.lr[r];
-    }
-    __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------------
-// AMIS loop for the resident object, 4DoF (EProPnP4DoF, epropnp.py:199-260): same skeleton as amis_phase6
-// with the yaw proposal 0.75 von Mises + 0.25 uniform.  Injected noise: noise_rot (B, M) holds the yaw
-// draws themselves (the reference samples them with numpy on the host, distributions.py:61-72, so there
-// is no base noise to replay).
-__device__ void amis_phase4(const KArgs& a, SmemHead<4>& sh, const float* pts4, float* smp, float* cst,
-                            float* logp, float* lw, const Cam& cam, float delta, int obj,
-                            const float* pose_opt, const float* cov EPNP_PTAB_PARAM) {
-    const Params& p = a.p;
-    const int tid = threadIdx.x;
-    const int M = p.mc_samples, I = p.mc_iter, S = M / I;
-    const bool injected = a.noise_n3 != nullptr;
-    const int st = serial_thread(a);
-    PH_DECL;
-
-    if (tid == st) initial_fit4(pose_opt, cov, p.amis_eps, sh.prop4[0]);
-    PH_MARK(a, PH_INIT_FIT);
-#if defined(EPNP_SWEEP_NOCLAMP)
-    const float radius = object_radius(pts4, a.N, sh.red, 0);
-#elif defined(EPNP_SWEEP_SPLIT)
-    const float radius = -1.f;
-#endif
-    __syncthreads();
-
-    for (int i = 0; i < I; ++i) {
-        for (int s = tid; s < S; s += NT) {
-            const int m = i * S + s;
-            float n3[3], chi2, q[4];
-            if (injected) {
-                const size_t g = (size_t)obj * M + m;
-                n3[0] = __ldg(a.noise_n3 + g * 3); n3[1] = __ldg(a.noise_n3 + g * 3 + 1); n3[2] = __ldg(a.noise_n3 + g * 3 + 2);
-                chi2 = __ldg(a.noise_chi2 + g);
-                q[3] = __ldg(a.noise_rot + g);
-            } else {
-                draw_base_noise_t(a.seed, a.obj_offset + (uint32_t)obj, (uint32_t)m, n3, chi2);
-                q[3] = draw_yaw(a.seed, a.obj_offset + (uint32_t)obj, (uint32_t)m, s, S, sh.prop4[i].mode, sh.prop4[i].kappa);
-            }
-            draw_translation(sh.prop4[i].mu, sh.prop4[i].lt, n3, chi2, q);
-            float* out = a.pose_samples + ((size_t)obj * M + m) * 4;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { smp[m * 4 + k] = q[k]; out[k] = q[k]; }
-#if defined(EPNP_SWEEP_SPLIT)
-            // cost: sweep_new_samples below, once every new sample of the iteration is in shared memory
-#elif defined(EPNP_SWEEP_NOCLAMP)
-            cst[m] = pose_cost<4>(pts4, a.N, q, cam, delta, radius);
-#else
-            cst[m] = pose_cost<4>(pts4, a.N, q, cam, delta);
-#endif
-#if defined(EPNP_AMIS_LSE)
-            {
-                RunningLse l;
-                l.start(proposal_logpdf4(sh.prop4[0], q));
-                for (int j = 1; j <= i; ++j) l.add(proposal_logpdf4(sh.prop4[j], q));
-                logp[m] = l.value();
-            }
-#else
-            for (int j = 0; j <= i; ++j) logp[j * M + m] = proposal_logpdf4(sh.prop4[j], q);
-#endif
-        }
-#if defined(EPNP_SWEEP_SPLIT)
-        __syncthreads();
-#if defined(EPNP_NO_LW)
-        float* const half1 = a.logw + (size_t)obj * M;
-#else
-        float* const half1 = lw;
-#endif
-#if defined(EPNP_SWEEP_MMA)
-        if (!sweep_new_samples_mma<4>(pts4, a.N, smp, ptab, cst, half1, i * S, S, cam, delta, radius))
-#endif
-        sweep_new_samples<4>(pts4, a.N, smp, cst, half1, i * S, S, cam, delta, radius);
-#endif
-        PH_MARK(a, PH_DRAW_SWEEP);
-#if defined(EPNP_AMIS_LSE)
-        for (int m = tid; m < i * S; m += NT) logp[m] = log_add_exp(logp[m], proposal_logpdf4(sh.prop4[i], smp + m * 4));
-#else
-        for (int m = tid; m < i * S; m += NT) logp[i * M + m] = proposal_logpdf4(sh.prop4[i], smp + m * 4);
-#endif
-        __syncthreads();
-        PH_MARK(a, PH_LOGP_OLD);
-        const int n = (i + 1) * S;
-        const float log_cnt = logf((float)(i + 1));
-        float mx = -CUDART_INF_F;
-        for (int m = tid; m < n; m += NT) {
-#if defined(EPNP_AMIS_LSE)
-            const float top = logp[m], acc = 1.f;               // logp[m] already is the log-sum-exp
-#else
-            float top = logp[m];
-            for (int j = 1; j <= i; ++j) top = fmaxf(top, logp[j * M + m]);
-            float acc = 0.f;
-            for (int j = 0; j <= i; ++j) acc += expf(logp[j * M + m] - top);
-#endif
-#if defined(EPNP_SWEEP_SPLIT)
-            float cm = cst[m];
-#if defined(EPNP_NO_LW)
-            if (m >= i * S) { cm += a.logw[(size_t)obj * M + m]; cst[m] = cm; }   // second half parked in the output slot
-#else
-            if (m >= i * S) { cm += lw[m]; cst[m] = cm; }       // fold the second point half of a new sample in
-#endif
-            const float v = -cm - ((top + logf(acc)) - log_cnt);
-#else
-            const float v = -cst[m] - ((top + logf(acc)) - log_cnt);
-#endif
-#if defined(EPNP_NO_LW)
-            if (i == I - 1) a.logw[(size_t)obj * M + m] = v;    // n == M on the last iteration: every slot gets its value
-#else
-            lw[m] = v;
-#endif
-            mx = fmaxf(mx, v);
-        }
-        PH_MARK(a, PH_WEIGHTS);
-        if (i == I - 1) {
-#if !defined(EPNP_NO_LW)
-            for (int m = tid; m < M; m += NT) a.logw[(size_t)obj * M + m] = lw[m];
-#endif
-            PH_MARK(a, PH_OUTPUT);
-            break;
-        }
-        // ---- refit (estimate_params, epropnp.py:232-260): A max, B sums of e, e t, e sin, e cos, C covariance
-        mx = block_max(mx, sh.red, 0);
-        float accB[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int m = tid; m < n; m += NT) {
-            const float e = LW_E(m);
-            LW_E_STORE(m, e);
-            const float* s4 = smp + m * 4;
-            float sn, cs;
-            sincosf(s4[3], &sn, &cs);
-            accB[0] += e;
-            accB[1] = fmaf(e, s4[0], accB[1]); accB[2] = fmaf(e, s4[1], accB[2]); accB[3] = fmaf(e, s4[2], accB[3]);
-            accB[4] = fmaf(e, sn, accB[4]); accB[5] = fmaf(e, cs, accB[5]);
-        }
-        block_sum<6>(accB, sh.red, 1);
-        const float inv_sum = 1.0f / accB[0];
-        const float mean[3] = {accB[1] * inv_sum, accB[2] * inv_sum, accB[3] * inv_sum};
-        float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int m = tid; m < n; m += NT) {
-            const float w = LW_W(m);
-            const float* s4 = smp + m * 4;
-            const float d0 = s4[0] - mean[0], d1 = s4[1] - mean[1], d2 = s4[2] - mean[2];
-            tc[0] = fmaf(w * d0, d0, tc[0]); tc[1] = fmaf(w * d0, d1, tc[1]); tc[2] = fmaf(w * d0, d2, tc[2]);
-            tc[3] = fmaf(w * d1, d1, tc[3]); tc[4] = fmaf(w * d1, d2, tc[4]); tc[5] = fmaf(w * d2, d2, tc[5]);
-        }
-        block_sum<6>(tc, sh.red, 0);
-        PH_MARK(a, PH_REFIT_SUMS);
-        if (tid == st) refit_finish4(mean, tc, accB[4] * inv_sum, accB[5] * inv_sum, p.amis_eps, sh.prop4[i + 1]);
-        PH_MARK(a, PH_REFIT_FINISH);
-        __syncthreads();
-    }
-    if (a.proposals && tid < I) {       // (B, I, 19): mu3, Lt6, mode, kappa, 0...
-        float* o = a.proposals + ((size_t)obj * I + tid) * PROP_FLOATS;
-        const Proposal4& pr = sh.prop4[tid];
-        o[0] = pr.mu[0]; o[1] = pr.mu[1]; o[2] = pr.mu[2];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) o[3 + r] = pr.lt[r];
-        o[9] = pr.mode; o[10] = pr.kappa;
-#pragma unroll
-        for (int r = 11; r < PROP_FLOATS; ++r) o[r] = 0.f;
-    }
-    __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------------
-// Kernels
-#if !defined(EPNP_CTAS_PER_SM)
-#define EPNP_CTAS_PER_SM 4              // build option: 5 needs <= 96 registers and <= 44 KB of shared memory per CTA
-#endif
-template <int DOF, bool DO_LM, bool DO_AMIS>
-__global__ void __launch_bounds__(NT, EPNP_CTAS_PER_SM) solve_kernel(const KArgs a) {
-    EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
-    SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
-    float* dyn = reinterpret_cast<float*>(smem_raw);
-#if defined(EPNP_ALIAS_STAGE)
-    // one object per CTA (grid == B): nothing is prefetched during the solve, the ring may live in the sample buffer
-    const SmemPlan pl = plan_smem<DOF>(a.N, a.p.mc_samples, a.p.mc_iter, DO_AMIS, gridDim.x >= (unsigned)a.B);
-#else
-    const SmemPlan pl = plan_smem<DOF>(a.N, a.p.mc_samples, a.p.mc_iter, DO_AMIS);
-#endif
-    float* pts4 = dyn + pl.pts;
-
-    Loader ld(a, sh.bar, dyn + pl.stage);
-    ld.prologue();
-    for (int it = 0; it < ld.n_my; ++it) {
-        const int obj = (int)blockIdx.x + it * (int)gridDim.x;
-        PH_DECL;
-        ld.load_object(it, obj, pts4);
-        const Cam cam = load_cam(a, obj);
-        const float delta = __ldg(a.delta + obj);
-        PH_MARK(a, PH_LOAD);
-        if constexpr (DO_LM) {
-            lm_phase<DOF>(a, sh, pts4, cam, delta, obj, DO_AMIS || a.pose_cov != nullptr);
-        }
-        if constexpr (DO_AMIS) {
-            if constexpr (!DO_LM) {
-                if (threadIdx.x < Dim<DOF>::POSE) sh.lm.pose[threadIdx.x] = __ldg(a.pose_opt_in + (size_t)obj * Dim<DOF>::POSE + threadIdx.x);
-                if (threadIdx.x < DOF * DOF) sh.cov[threadIdx.x] = __ldg(a.pose_cov_in + (size_t)obj * DOF * DOF + threadIdx.x);
-                __syncthreads();
-            }
-#if defined(EPNP_SWEEP_MMA)
-            // table of the current iteration's K[R|t] (12 floats per new sample): the staging ring, which is idle once
-            // the object is packed -- unless this CTA prefetches its next object (persistent grid) or the ring is
-            // aliased into the sample buffer, in which case the tensor-pipe sweep is not used
-            float* ptab = nullptr;
-            if (gridDim.x >= (unsigned)a.B && pl.stage != pl.smp && 12 * (a.p.mc_samples / a.p.mc_iter) <= 2 * STAGE_FLOATS)
-                ptab = dyn + pl.stage;
-#endif
-            if constexpr (DOF == 6)
-                amis_phase6(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.lw, cam, delta, obj,
-                            sh.lm.pose, sh.cov EPNP_PTAB_ARG(ptab));
-            else
-                amis_phase4(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.lw, cam, delta, obj,
-                            sh.lm.pose, sh.cov EPNP_PTAB_ARG(ptab));
-        }
-    }
-}
-
-// Fused solve + all-gather over peer memory (multi-GPU, one node).  Same solve as solve_kernel<DOF, true, true>; when an
-// object is finished, its CTA also stores the object's pose and its M log-weights into row (obj_offset + obj) of the
-// full-batch result buffers of up to EPNP_MAX_PEERS other GPUs (pointers into their memory, mapped through CUDA IPC):
-// plain st.global over NVLink, 2 KB + 28 B per object and peer, issued object by object underneath the other CTAs'
-// math.  No gather kernel and no copy afterwards; the caller only needs a rendezvous before reading (sharded.PushGather).
-// The local outputs (a.pose_opt, a.logw) are normally the local slice of this rank's own full-batch buffers.
-constexpr int EPNP_MAX_PEERS = 8;
-struct PushArgs {
-    float* logw[EPNP_MAX_PEERS];            // (B_total, M) on each peer
-    float* pose[EPNP_MAX_PEERS];            // (B_total, D) on each peer
-    int n;
-};
-
-template <int DOF>
-__global__ void __launch_bounds__(NT, EPNP_CTAS_PER_SM) solve_push_kernel(const KArgs a, const PushArgs push) {
-    EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
-    SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
-    float* dyn = reinterpret_cast<float*>(smem_raw);
-    constexpr int PD = Dim<DOF>::POSE;
-#if defined(EPNP_ALIAS_STAGE)
-    const SmemPlan pl = plan_smem<DOF>(a.N, a.p.mc_samples, a.p.mc_iter, true, gridDim.x >= (unsigned)a.B);
-#else
-    const SmemPlan pl = plan_smem<DOF>(a.N, a.p.mc_samples, a.p.mc_iter, true);
-#endif
-    float* pts4 = dyn + pl.pts;
-    const int M = a.p.mc_samples;
-    Loader ld(a, sh.bar, dyn + pl.stage);
-    ld.prologue();
-    for (int it = 0; it < ld.n_my; ++it) {
-        const int obj = (int)blockIdx.x + it * (int)gridDim.x;
-        ld.load_object(it, obj, pts4);
-        const Cam cam = load_cam(a, obj);
-        const float delta = __ldg(a.delta + obj);
-        lm_phase<DOF>(a, sh, pts4, cam, delta, obj, true);
-#if defined(EPNP_SWEEP_MMA)
-        float* ptab = nullptr;
-        if (gridDim.x >= (unsigned)a.B && pl.stage != pl.smp && 12 * (a.p.mc_samples / a.p.mc_iter) <= 2 * STAGE_FLOATS)
-            ptab = dyn + pl.stage;
-#endif
-        if constexpr (DOF == 6)
-            amis_phase6(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.lw, cam, delta, obj,
-                        sh.lm.pose, sh.cov EPNP_PTAB_ARG(ptab));
-        else
-            amis_phase4(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.lw, cam, delta, obj,
-                        sh.lm.pose, sh.cov EPNP_PTAB_ARG(ptab));
-        // ---- push: the object's outputs, as this CTA wrote them, to the same global row on every peer
-        __syncthreads();                                        // the CTA's own global stores are visible to all its threads
-        const size_t row = (size_t)a.obj_offset + (size_t)obj;
-        const float* src = a.logw + (size_t)obj * M;
-        if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-            for (int q = threadIdx.x; q < M / 4; q += NT) {
-                const float4 v = reinterpret_cast<const float4*>(src)[q];
-                for (int r = 0; r < push.n; ++r) {
-                    float* dst = push.logw[r] + row * M;
-                    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) reinterpret_cast<float4*>(dst)[q] = v;
-                    else { dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w; }
-                }
-            }
-        } else {
-            for (int m = threadIdx.x; m < M; m += NT) {
-                const float v = src[m];
-                for (int r = 0; r < push.n; ++r) push.logw[r][row * M + m] = v;
-            }
-        }
-        if (threadIdx.x < PD) {
-            const float v = a.pose_opt[(size_t)obj * PD + threadIdx.x];
-            for (int r = 0; r < push.n; ++r) push.pose[r][row * PD + threadIdx.x] = v;
-        }
-    }
 }
 
 // cost of S poses per object: poses (S, B, D) -> cost (S, B)
 template <int DOF>
 __global__ void __launch_bounds__(NT, 4) cost_kernel(const KArgs a) {
     EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
-    SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
+    ObjHead<DOF>& sh = *reinterpret_cast<ObjHead<DOF>*>(smem_raw);
     float* dyn = reinterpret_cast<float*>(smem_raw);
-    const SmemPlan pl = plan_smem<DOF>(a.N, 0, 0, false);
+    const ObjPlan pl = plan_obj<DOF>(a.N);
     float* pts4 = dyn + pl.pts;
     constexpr int PD = Dim<DOF>::POSE;
+    const int obj = blockIdx.x;
     Loader ld(a, sh.bar, dyn + pl.stage);
-    ld.prologue();
-    for (int it = 0; it < ld.n_my; ++it) {
-        const int obj = (int)blockIdx.x + it * (int)gridDim.x;
-        ld.load_object(it, obj, pts4);
-        const Cam cam = load_cam(a, obj);
-        const float delta = __ldg(a.delta + obj);
-        for (int s = threadIdx.x; s < a.S_eval; s += NT) {
-            float pose[PD];
+    ld.load_object(obj, pts4);
+    const Cam cam = load_cam(a, obj);
+    const float delta = __ldg(a.delta + obj);
+    for (int s = threadIdx.x; s < a.S_eval; s += NT) {
+        float pose[PD];
 #pragma unroll
-            for (int k = 0; k < PD; ++k) pose[k] = __ldg(a.poses + ((size_t)s * a.B + obj) * PD + k);
-            a.cost_out[(size_t)s * a.B + obj] = pose_cost<DOF>(pts4, a.N, pose, cam, delta);
-        }
-        __syncthreads();        // pts4 is overwritten by the next object
+        for (int k = 0; k < PD; ++k) pose[k] = __ldg(a.poses + ((size_t)s * a.B + obj) * PD + k);
+        a.cost_out[(size_t)s * a.B + obj] = pose_cost<DOF>(pts4, a.N, pose, cam, delta);
     }
 }
 
@@ -1695,77 +110,72 @@ template <int DOF>
 __global__ void __launch_bounds__(NT, 2) rslm_kernel(const RslmArgs r) {
     const KArgs& a = r.k;
     EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
-    SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
+    ObjHead<DOF>& sh = *reinterpret_cast<ObjHead<DOF>*>(smem_raw);
     float* dyn = reinterpret_cast<float*>(smem_raw);
-    const SmemPlan pl = plan_smem<DOF>(a.N, 0, 0, false);
+    const ObjPlan pl = plan_obj<DOF>(a.N);
     float* pts = dyn + pl.pts;
     constexpr int PD = Dim<DOF>::POSE;
     const Params& p = a.p;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, obj = blockIdx.x;
     float* best_cost = sh.red;                                  // [NT]
     int* best_hyp = reinterpret_cast<int*>(sh.red + NT);        // [NT]
     Loader ld(a, sh.bar, dyn + pl.stage);
-    ld.prologue();
-    for (int it = 0; it < ld.n_my; ++it) {
-        const int obj = (int)blockIdx.x + it * (int)gridDim.x;
-        ld.load_object(it, obj, pts);
-        const Cam cam = load_cam(a, obj);
-        const float delta = __ldg(a.delta + obj);
-        float my_cost = CUDART_INF_F, my_pose[PD];
-        int my_hyp = -1;
-        for (int h = tid; h < r.P; h += NT) {
-            const int* idx = r.inds + ((size_t)h * a.B + obj) * r.n;
-            LMState<DOF> s;
+    ld.load_object(obj, pts);
+    const Cam cam = load_cam(a, obj);
+    const float delta = __ldg(a.delta + obj);
+    float my_cost = CUDART_INF_F, my_pose[PD];
+    int my_hyp = -1;
+    for (int h = tid; h < r.P; h += NT) {
+        const int* idx = r.inds + ((size_t)h * a.B + obj) * r.n;
+        LMState<DOF> s;
 #pragma unroll
-            for (int i = 0; i < PD; ++i) s.pose[i] = __ldg(r.start + ((size_t)h * a.B + obj) * PD + i);
-            s.radius = p.initial_radius;
-            s.shrink = 2.0f;
-            float acc[Dim<DOF>::NV];
-            if (!p.fast_mode) {
-                eval_subset<DOF, true>(pts, idx, r.n, s.pose, cam, delta, p.huber_eps, acc);
-                lm_adopt<DOF>(s, acc);
-                if (p.lm_iter > 0) lm_propose<DOF>(s, p);
-                for (int k = 0; k < p.lm_iter; ++k) {
-                    eval_subset<DOF, true>(pts, idx, r.n, s.pose_new, cam, delta, p.huber_eps, acc);
-                    lm_update<DOF>(s, acc, p);
-                    if (k + 1 < p.lm_iter) lm_propose<DOF>(s, p);
-                }
-            } else {
-                for (int k = 0; k < p.lm_iter; ++k) {
-                    eval_subset<DOF, false>(pts, idx, r.n, s.pose, cam, delta, p.huber_eps, acc);
-                    gn_advance<DOF>(s.pose, acc, p.eps, s.pose);
-                }
+        for (int i = 0; i < PD; ++i) s.pose[i] = __ldg(r.start + ((size_t)h * a.B + obj) * PD + i);
+        s.radius = p.initial_radius;
+        s.shrink = 2.0f;
+        float acc[Dim<DOF>::NV];
+        if (!p.fast_mode) {
+            eval_subset<DOF, true>(pts, idx, r.n, s.pose, cam, delta, p.huber_eps, acc);
+            lm_adopt<DOF>(s, acc);
+            if (p.lm_iter > 0) lm_propose<DOF>(s, p);
+            for (int k = 0; k < p.lm_iter; ++k) {
+                eval_subset<DOF, true>(pts, idx, r.n, s.pose_new, cam, delta, p.huber_eps, acc);
+                lm_update<DOF>(s, acc, p);
+                if (k + 1 < p.lm_iter) lm_propose<DOF>(s, p);
             }
-            const float c = pose_cost<DOF>(pts, a.N, s.pose, cam, delta);       // score on the full set
-            if (r.pose_all) {
-#pragma unroll
-                for (int i = 0; i < PD; ++i) r.pose_all[((size_t)h * a.B + obj) * PD + i] = s.pose[i];
-            }
-            if (r.cost_all) r.cost_all[(size_t)h * a.B + obj] = c;
-            if (my_hyp < 0 || cheaper_hypothesis(c, h, my_cost, my_hyp)) {
-                my_cost = c; my_hyp = h;
-#pragma unroll
-                for (int i = 0; i < PD; ++i) my_pose[i] = s.pose[i];
+        } else {
+            for (int k = 0; k < p.lm_iter; ++k) {
+                eval_subset<DOF, false>(pts, idx, r.n, s.pose, cam, delta, p.huber_eps, acc);
+                gn_advance<DOF>(s.pose, acc, p.eps, s.pose);
             }
         }
-        best_cost[tid] = my_cost;
-        best_hyp[tid] = my_hyp;
-        __syncthreads();
-        if (tid == 0) {
-            int w = -1;
-            for (int t = 0; t < NT; ++t) {
-                if (best_hyp[t] < 0) continue;
-                if (w < 0 || cheaper_hypothesis(best_cost[t], best_hyp[t], best_cost[w], best_hyp[w])) w = t;
-            }
-            best_hyp[0] = w;                                    // the winning THREAD (it still holds the pose)
-        }
-        __syncthreads();
-        if (tid == best_hyp[0]) {
+        const float c = pose_cost<DOF>(pts, a.N, s.pose, cam, delta);       // score on the full set
+        if (r.pose_all) {
 #pragma unroll
-            for (int i = 0; i < PD; ++i) r.pose_best[(size_t)obj * PD + i] = my_pose[i];
-            r.cost_best[obj] = my_cost;
+            for (int i = 0; i < PD; ++i) r.pose_all[((size_t)h * a.B + obj) * PD + i] = s.pose[i];
         }
-        __syncthreads();            // pts and the reduction arrays are reused by the next object
+        if (r.cost_all) r.cost_all[(size_t)h * a.B + obj] = c;
+        if (my_hyp < 0 || cheaper_hypothesis(c, h, my_cost, my_hyp)) {
+            my_cost = c; my_hyp = h;
+#pragma unroll
+            for (int i = 0; i < PD; ++i) my_pose[i] = s.pose[i];
+        }
+    }
+    best_cost[tid] = my_cost;
+    best_hyp[tid] = my_hyp;
+    __syncthreads();
+    if (tid == 0) {
+        int w = -1;
+        for (int t = 0; t < NT; ++t) {
+            if (best_hyp[t] < 0) continue;
+            if (w < 0 || cheaper_hypothesis(best_cost[t], best_hyp[t], best_cost[w], best_hyp[w])) w = t;
+        }
+        best_hyp[0] = w;                                    // the winning THREAD (it still holds the pose)
+    }
+    __syncthreads();
+    if (tid == best_hyp[0]) {
+#pragma unroll
+        for (int i = 0; i < PD; ++i) r.pose_best[(size_t)obj * PD + i] = my_pose[i];
+        r.cost_best[obj] = my_cost;
     }
 }
 
@@ -1785,62 +195,57 @@ template <int DOF>
 __global__ void __launch_bounds__(NT, 2) gn_plus_backward_kernel(const GnBwArgs g) {
     const KArgs& a = g.k;
     EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
-    SmemHead<DOF>& sh = *reinterpret_cast<SmemHead<DOF>*>(smem_raw);
+    ObjHead<DOF>& sh = *reinterpret_cast<ObjHead<DOF>*>(smem_raw);
     float* dyn = reinterpret_cast<float*>(smem_raw);
-    const SmemPlan pl = plan_smem<DOF>(a.N, 0, 0, false);
+    const ObjPlan pl = plan_obj<DOF>(a.N);
     float* pts = dyn + pl.pts;
     constexpr int PD = Dim<DOF>::POSE, NA = Dim<DOF>::NA;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, obj = blockIdx.x;
     Loader ld(a, sh.bar, dyn + pl.stage);
-    ld.prologue();
-    for (int it = 0; it < ld.n_my; ++it) {
-        const int obj = (int)blockIdx.x + it * (int)gridDim.x;
-        ld.load_object(it, obj, pts);
-        const Cam cam = load_cam(a, obj);
-        const float delta = __ldg(a.delta + obj);
-        if (tid < PD) sh.lm.pose[tid] = __ldg(a.poses + (size_t)obj * PD + tid);
-        __syncthreads();
-        eval_normal_eq<DOF, true>(pts, a.N, sh.lm.pose, cam, delta, a.p.huber_eps, sh.red, sh.ev);
-        float* step = sh.cov;               // [DOF]
-        float* vvec = sh.cov + DOF;         // [DOF]
-        if (tid == 0) {
-            float add[DOF], st[DOF], sbar[DOF], vv[DOF], gout[PD], pose[PD];
+    ld.load_object(obj, pts);
+    const Cam cam = load_cam(a, obj);
+    const float delta = __ldg(a.delta + obj);
+    if (tid < PD) sh.pose[tid] = __ldg(a.poses + (size_t)obj * PD + tid);
+    __syncthreads();
+    eval_normal_eq<DOF, true>(pts, a.N, sh.pose, cam, delta, a.p.huber_eps, sh.red, sh.ev);
+    float* step = sh.step;              // [DOF]
+    float* vvec = sh.step + DOF;        // [DOF]
+    if (tid == 0) {
+        float add[DOF], st[DOF], sbar[DOF], vv[DOF], gout[PD], pose[PD];
 #pragma unroll
-            for (int i = 0; i < DOF; ++i) add[i] = a.p.eps;
+        for (int i = 0; i < DOF; ++i) add[i] = a.p.eps;
 #pragma unroll
-            for (int i = 0; i < PD; ++i) { pose[i] = sh.lm.pose[i]; gout[i] = __ldg(g.gplus + (size_t)obj * PD + i); }
-            damped_step_refined<DOF>(sh.ev, sh.ev + NA, add, st);
-            pose_add_backward<DOF>(pose, st, gout, sbar);
-            damped_step_refined<DOF>(sh.ev, sbar, add, vv);
+        for (int i = 0; i < PD; ++i) { pose[i] = sh.pose[i]; gout[i] = __ldg(g.gplus + (size_t)obj * PD + i); }
+        damped_step_refined<DOF>(sh.ev, sh.ev + NA, add, st);
+        pose_add_backward<DOF>(pose, st, gout, sbar);
+        damped_step_refined<DOF>(sh.ev, sbar, add, vv);
 #pragma unroll
-            for (int i = 0; i < DOF; ++i) { step[i] = st[i]; vvec[i] = vv[i]; }
-        }
-        __syncthreads();
-        float R[9], t[3], sv[DOF], vv[DOF];
-        {
-            float ps[PD];
-#pragma unroll
-            for (int i = 0; i < PD; ++i) ps[i] = sh.lm.pose[i];
-            pose_to_rot<DOF>(ps, R);
-            t[0] = ps[0]; t[1] = ps[1]; t[2] = ps[2];
-#pragma unroll
-            for (int i = 0; i < DOF; ++i) { sv[i] = step[i]; vv[i] = vvec[i]; }
-        }
-        float gd[1] = {0.f};
-        for (int n = tid; n < a.N; n += NT) {
-            const float* q = pts + (n >> 1) * 16 + (n & 1);
-            float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            gn_step_point_backward<DOF>(R, t, cam, delta, a.p.huber_eps, q[0], q[2], q[4], -q[6], -q[8], q[10], q[12], vv, sv, gr);
-            const size_t o = (size_t)obj * a.N + n;
-            if (g.gx3d) { g.gx3d[o * 3] = gr[0]; g.gx3d[o * 3 + 1] = gr[1]; g.gx3d[o * 3 + 2] = gr[2]; }
-            if (g.gx2d) { g.gx2d[o * 2] = gr[3]; g.gx2d[o * 2 + 1] = gr[4]; }
-            if (g.gw2d) { g.gw2d[o * 2] = gr[5]; g.gw2d[o * 2 + 1] = gr[6]; }
-            gd[0] += gr[7];
-        }
-        block_sum<1>(gd, sh.red, 0);
-        if (tid == 0 && g.gdelta) g.gdelta[obj] = gd[0];
-        __syncthreads();            // pts, pose and the step vectors are reused by the next object
+        for (int i = 0; i < DOF; ++i) { step[i] = st[i]; vvec[i] = vv[i]; }
     }
+    __syncthreads();
+    float R[9], t[3], sv[DOF], vv[DOF];
+    {
+        float ps[PD];
+#pragma unroll
+        for (int i = 0; i < PD; ++i) ps[i] = sh.pose[i];
+        pose_to_rot<DOF>(ps, R);
+        t[0] = ps[0]; t[1] = ps[1]; t[2] = ps[2];
+#pragma unroll
+        for (int i = 0; i < DOF; ++i) { sv[i] = step[i]; vv[i] = vvec[i]; }
+    }
+    float gd[1] = {0.f};
+    for (int n = tid; n < a.N; n += NT) {
+        const float* q = pts + (n >> 1) * 16 + (n & 1);
+        float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        gn_step_point_backward<DOF>(R, t, cam, delta, a.p.huber_eps, q[0], q[2], q[4], -q[6], -q[8], q[10], q[12], vv, sv, gr);
+        const size_t o = (size_t)obj * a.N + n;
+        if (g.gx3d) { g.gx3d[o * 3] = gr[0]; g.gx3d[o * 3 + 1] = gr[1]; g.gx3d[o * 3 + 2] = gr[2]; }
+        if (g.gx2d) { g.gx2d[o * 2] = gr[3]; g.gx2d[o * 2 + 1] = gr[4]; }
+        if (g.gw2d) { g.gw2d[o * 2] = gr[5]; g.gw2d[o * 2 + 1] = gr[6]; }
+        gd[0] += gr[7];
+    }
+    block_sum<1>(gd, sh.red, 0);
+    if (tid == 0 && g.gdelta) g.gdelta[obj] = gd[0];
 }
 
 // residual / Jacobian / cost written out per point (API parity with evaluate_pnp's out_* tensors)
@@ -1886,14 +291,6 @@ __global__ void __launch_bounds__(NT) evaluate_full_kernel(const KArgs a, float*
 // as broadcasts, so the (pose, point) loop touches no global memory.
 constexpr int BW_PPT = 4;               // correspondences per thread and tile
 constexpr int BW_POSE_TILE = 1024;      // poses staged per tile (13 floats each)
-
-#if defined(EPNP_SIMT_EMUL)
-struct FastRsqrt { float operator()(float x) const { return 1.0f / sqrtf(x); } };
-#else
-struct FastRsqrt {
-    __device__ __forceinline__ float operator()(float x) const { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-};
-#endif
 
 // Reverse mode of the cost for TWO correspondences at once (packed fp32x2; same math per half as
 // pnp::point_cost_backward, with s = s2 * rsqrt(s2) and delta / s = delta * rsqrt(s2) from one MUFU.RSQ).
@@ -2128,7 +525,6 @@ __global__ void __launch_bounds__(NT) mc_lse_backward_kernel(const float* logw, 
     float* o = grad_logw + (size_t)obj * M;
     for (int m = threadIdx.x; m < M; m += NT) o[m] = (gb == 0.f) ? 0.f : gb * expf(__ldg(l + m) - ls);
 }
-
 // ------------------------------------------------------------------------------------------------
 // Host side
 int cuda_fail(cudaError_t e) { g_last_cuda_error = (int)e; return EPNP_ERR_CUDA; }
@@ -2143,63 +539,77 @@ int check_common(const KArgs& a) {
     return EPNP_OK;
 }
 
-template <class Kern, class... Extra>
-int launch_persistent(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream, int smem_bytes_single = 0, Extra... extra) {
-    (void)smem_bytes_single;            // EPNP_ALIAS_STAGE: dynamic shared memory when every CTA solves one object
-    if (a.B == 0) return EPNP_OK;
-    if ((size_t)smem_bytes > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
-    a.use_tma = (a.N % 4 == 0) && aligned16(a.x3d) && aligned16(a.x2d) && aligned16(a.w2d);
-    int dev = 0, sms = 0, occ = 0;
+int device_sms(int* sms) {
+    int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return cuda_fail(e);
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
+    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
+}
+
+bool tma_ok(const KArgs& a) { return (a.N % 4 == 0) && aligned16(a.x3d) && aligned16(a.x2d) && aligned16(a.w2d); }
+
+// One CTA of NT threads per object (grid = B): the hardware scheduler hands CTAs to SMs as slots free up, the CTAs'
+// serial and parallel phases de-synchronise and there is no lock-step tail (measured 5 % faster than a persistent grid).
+template <class Kern, class... Extra>
+int launch_cta_per_object(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream, Extra... extra) {
+    if (a.B == 0) return EPNP_OK;
+    if ((size_t)smem_bytes > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
+    a.use_tma = tma_ok(a);
+    int rc = device_sms(&a.num_sms);
+    if (rc != EPNP_OK) return rc;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return cuda_fail(e);
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return cuda_fail(e);
-#if defined(EPNP_CTAS_PER_SM) && EPNP_CTAS_PER_SM > 4
-    // five / six resident CTAs need (nearly) the whole 228 KB of the SM as shared memory: ask for the full carve-out
+    // several resident CTAs need (nearly) the whole 228 KB of the SM as shared memory: ask for the full carve-out
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return cuda_fail(e);
-#endif
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem_bytes);
-    if (e != cudaSuccess) return cuda_fail(e);
-    if (occ < 1) return EPNP_ERR_TOO_MANY_POINTS;
-    a.num_sms = sms;
-    // Work distribution.  Default: ONE object per CTA (grid = B) and the hardware scheduler hands CTAs to SMs as
-    // slots free up -- measured 5 % faster than a persistent grid at B = 4096 (2.93 vs 2.79 M objects/s): the CTAs'
-    // serial and parallel phases de-synchronise and there is no lock-step tail, which outweighs losing the
-    // cross-object TMA prefetch (~1.5 %); it also lets a concurrently enqueued kernel of another stream (the NCCL
-    // gather of the previous batch in the multi-GPU pipeline) start at once instead of waiting for a resident grid
-    // to drain.  EPNP_MAX_OBJECTS_PER_CTA = k (environment, read per call) sets the cap; 0 = fully persistent
-    // (grid = resident slots, objects strided over CTAs, next object's chunks prefetched during the current solve).
-    const int slots = sms * occ;
-    int rounds = 1;
-    if (const char* env = std::getenv("EPNP_MAX_OBJECTS_PER_CTA")) {
-        const int k = std::atoi(env);
-        const int persistent_rounds = (a.B + slots - 1) / slots;
-        rounds = (k <= 0) ? persistent_rounds : (k < persistent_rounds ? k : persistent_rounds);
-    }
-    const int grid = (a.B + rounds - 1) / rounds;
-#if defined(EPNP_ALIAS_STAGE)
-    if (rounds == 1 && smem_bytes_single > 0) smem_bytes = smem_bytes_single;      // the kernel sees grid == B too
-#endif
-    EPNP_LAUNCH(kern, grid, NT, smem_bytes, stream, a, extra...);
+    EPNP_LAUNCH(kern, a.B, NT, smem_bytes, stream, a, extra...);
     e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e);
-    return EPNP_OK;
+    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
+}
+
+// LM / GN solve: one warp (one 32-thread CTA) per object.  Outputs: a.pose_opt, a.pose_cov [opt] (stride a.cov_stride),
+// a.cost [opt], a.pose_plus [opt], a.cost_init [opt].
+template <int DOF>
+int launch_lm(KArgs& a, cudaStream_t stream) {
+    if (a.B == 0) return EPNP_OK;
+    a.use_tma = tma_ok(a);
+    int rc = device_sms(&a.num_sms);
+    if (rc != EPNP_OK) return rc;
+    const bool staged = a.N <= LM_STAGE_MAX_N;
+    const int smem_bytes = lm_smem_bytes<DOF>(a.N, staged);
+    cudaError_t e;
+    if (staged) {
+        e = cudaFuncSetAttribute(lm_warp_kernel<DOF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        e = cudaFuncSetAttribute(lm_warp_kernel<DOF, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return cuda_fail(e);
+        EPNP_LAUNCH((lm_warp_kernel<DOF, true>), a.B, 32, smem_bytes, stream, a);
+    } else {
+        EPNP_LAUNCH((lm_warp_kernel<DOF, false>), a.B, 32, smem_bytes, stream, a);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
+}
+
+template <int DOF>
+int launch_amis(KArgs& a, const PushArgs* push, cudaStream_t stream) {
+    const int smem_bytes = plan_amis<DOF>(a.N, a.p.mc_samples).total_bytes;
+    if (push) return launch_cta_per_object(amis_kernel<DOF, true>, a, smem_bytes, stream, *push);
+    return launch_cta_per_object(amis_kernel<DOF, false>, a, smem_bytes, stream, PushArgs{});
 }
 
 unsigned long long* g_prof_buffer = nullptr;     // set by epnp_debug_set_phase_buffer (profiling build)
 
-// Objects the device solves at once with the fused kernel: SMs x resident CTAs per SM (one CTA per object).  Used by
-// the host-buffer entry point to cut the batch at whole waves.  0 when it cannot be determined.
+// Objects the device works on at once in the AMIS kernel: SMs x resident CTAs per SM.  Used by the host-buffer entry
+// point to cut the batch at whole waves.  0 when it cannot be determined.
 template <class Kern>
 int resident_objects(Kern kern, int smem_bytes) {
-    int dev = 0, sms = 0, occ = 0;
+    int sms = 0, occ = 0;
     if ((size_t)smem_bytes > SMEM_LIMIT) return 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (device_sms(&sms) != EPNP_OK) return 0;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem_bytes) != cudaSuccess) return 0;
     return sms * occ;
 }
@@ -2208,6 +618,25 @@ int check_amis_params(const Params& p) {
     if (p.mc_iter <= 0 || p.mc_iter > MAX_ITER || p.mc_samples <= 0 || p.mc_samples % p.mc_iter != 0) return EPNP_ERR_BAD_ARG;
     if (p.acg_mle_iter < 0) return EPNP_ERR_BAD_ARG;
     return EPNP_OK;
+}
+
+// LM kernel, then AMIS kernel, on `stream`.  The covariance travels through a.pose_cov (caller's buffer) or, when the
+// caller did not ask for it, through the first dof^2 floats of each object's -- not yet written -- sample rows.
+int run_lm_amis(KArgs& a, const PushArgs* push, cudaStream_t stream) {
+    const int dof = a.p.dof, D = dof == 6 ? 7 : 4;
+    if (a.pose_cov) a.cov_stride = dof * dof;
+    else {
+        if (a.p.mc_samples * D < dof * dof) return EPNP_ERR_BAD_ARG;
+        a.pose_cov = a.pose_samples;
+        a.cov_stride = a.p.mc_samples * D;
+    }
+    if ((size_t)(dof == 6 ? plan_amis<6>(a.N, a.p.mc_samples).total_bytes : plan_amis<4>(a.N, a.p.mc_samples).total_bytes) > SMEM_LIMIT)
+        return EPNP_ERR_TOO_MANY_POINTS;        // before anything is launched
+    int rc = dof == 6 ? launch_lm<6>(a, stream) : launch_lm<4>(a, stream);
+    if (rc != EPNP_OK) return rc;
+    a.pose_opt_in = a.pose_opt;
+    a.pose_cov_in = a.pose_cov;
+    return dof == 6 ? launch_amis<6>(a, push, stream) : launch_amis<4>(a, push, stream);
 }
 
 }  // namespace
@@ -2244,13 +673,15 @@ void epnp_default_params(EpnpParams* p, int dof) {
 }
 
 int epnp_max_points(int dof, int mc_samples, int mc_iter) {
+    (void)mc_iter;
     const bool amis = mc_samples > 0;
     int lo = 0, hi = 1 << 16;
     while (lo + 4 <= hi) {                   // largest multiple of 4 that fits
         const int mid = ((lo + hi) / 2) / 4 * 4;
         if (mid == lo) break;
-        const int bytes = (dof == 6) ? plan_smem<6>(mid, mc_samples, mc_iter, amis).total_bytes
-                                     : plan_smem<4>(mid, mc_samples, mc_iter, amis).total_bytes;
+        int bytes;
+        if (amis) bytes = (dof == 6) ? plan_amis<6>(mid, mc_samples).total_bytes : plan_amis<4>(mid, mc_samples).total_bytes;
+        else bytes = (dof == 6) ? plan_obj<6>(mid).total_bytes : plan_obj<4>(mid).total_bytes;
         if ((size_t)bytes <= SMEM_LIMIT) lo = mid; else hi = mid;
     }
     return lo;
@@ -2302,8 +733,8 @@ int epnp_evaluate_cost_f32(const float* x3d, const float* x2d, const float* w2d,
     if (rc != EPNP_OK) return rc;
     if (!poses || !cost || S < 0) return EPNP_ERR_BAD_ARG;
     if (S == 0) return EPNP_OK;
-    if (dof == 6) return launch_persistent(cost_kernel<6>, a, plan_smem<6>(N, 0, 0, false).total_bytes, (cudaStream_t)stream);
-    return launch_persistent(cost_kernel<4>, a, plan_smem<4>(N, 0, 0, false).total_bytes, (cudaStream_t)stream);
+    if (dof == 6) return launch_cta_per_object(cost_kernel<6>, a, plan_obj<6>(N).total_bytes, (cudaStream_t)stream);
+    return launch_cta_per_object(cost_kernel<4>, a, plan_obj<4>(N).total_bytes, (cudaStream_t)stream);
 }
 
 int epnp_evaluate_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
@@ -2337,8 +768,8 @@ int epnp_lm_solve_f32(const float* x3d, const float* x2d, const float* w2d, cons
     int rc = check_common(a);
     if (rc != EPNP_OK) return rc;
     if (!pose_init || !pose_opt || p->lm_iter < 0) return EPNP_ERR_BAD_ARG;
-    if (p->dof == 6) return launch_persistent(solve_kernel<6, true, false>, a, plan_smem<6>(N, 0, 0, false).total_bytes, (cudaStream_t)stream);
-    return launch_persistent(solve_kernel<4, true, false>, a, plan_smem<4>(N, 0, 0, false).total_bytes, (cudaStream_t)stream);
+    a.cov_stride = p->dof * p->dof;
+    return p->dof == 6 ? launch_lm<6>(a, (cudaStream_t)stream) : launch_lm<4>(a, (cudaStream_t)stream);
 }
 
 int epnp_gn_plus_backward_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
@@ -2357,15 +788,12 @@ int epnp_gn_plus_backward_f32(const float* x3d, const float* x2d, const float* w
     if (rc != EPNP_OK) return rc;
     if (!pose || !grad_pose_plus) return EPNP_ERR_BAD_ARG;
     if (B == 0) return EPNP_OK;
-    const int smem_bytes = (dof == 6) ? plan_smem<6>(N, 0, 0, false).total_bytes : plan_smem<4>(N, 0, 0, false).total_bytes;
+    const int smem_bytes = (dof == 6) ? plan_obj<6>(N).total_bytes : plan_obj<4>(N).total_bytes;
     if ((size_t)smem_bytes > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
-    a.use_tma = (N % 4 == 0) && aligned16(x3d) && aligned16(x2d) && aligned16(w2d);
-    int dev = 0, sms = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return cuda_fail(e);
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return cuda_fail(e);
-    a.num_sms = sms;
+    a.use_tma = tma_ok(a);
+    rc = device_sms(&a.num_sms);
+    if (rc != EPNP_OK) return rc;
+    cudaError_t e;
     if (dof == 6) {
         e = cudaFuncSetAttribute(gn_plus_backward_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return cuda_fail(e);
@@ -2394,15 +822,12 @@ int epnp_rslm_f32(const float* x3d, const float* x2d, const float* w2d, const fl
     if (rc != EPNP_OK) return rc;
     if (!inds || !start || !pose_best || !cost_best || P <= 0 || n <= 0 || p->lm_iter < 0) return EPNP_ERR_BAD_ARG;
     if (B == 0) return EPNP_OK;
-    const int smem_bytes = (p->dof == 6) ? plan_smem<6>(N, 0, 0, false).total_bytes : plan_smem<4>(N, 0, 0, false).total_bytes;
+    const int smem_bytes = (p->dof == 6) ? plan_obj<6>(N).total_bytes : plan_obj<4>(N).total_bytes;
     if ((size_t)smem_bytes > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
-    a.use_tma = (N % 4 == 0) && aligned16(x3d) && aligned16(x2d) && aligned16(w2d);
-    int dev = 0, sms = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return cuda_fail(e);
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return cuda_fail(e);
-    a.num_sms = sms;
+    a.use_tma = tma_ok(a);
+    rc = device_sms(&a.num_sms);
+    if (rc != EPNP_OK) return rc;
+    cudaError_t e;
     if (p->dof == 6) {
         e = cudaFuncSetAttribute(rslm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return cuda_fail(e);
@@ -2428,6 +853,7 @@ int epnp_amis_f32(const float* x3d, const float* x2d, const float* w2d, const fl
     a.noise_n3 = noise_normal; a.noise_chi2 = noise_chi2; a.noise_rot = noise_rot;
     a.seed = seed; a.obj_offset = obj_offset;
     a.pose_samples = pose_samples; a.logw = logw; a.proposals = proposals; a.B = B; a.N = N; a.p = *p;
+    a.prof = g_prof_buffer;
     int rc = check_common(a);
     if (rc != EPNP_OK) return rc;
     rc = check_amis_params(*p);
@@ -2435,11 +861,8 @@ int epnp_amis_f32(const float* x3d, const float* x2d, const float* w2d, const fl
     if (!pose_opt || !pose_cov || !pose_samples || !logw) return EPNP_ERR_BAD_ARG;
     const bool any = noise_normal || noise_chi2 || noise_rot, all = noise_normal && noise_chi2 && noise_rot;
     if (any && !all) return EPNP_ERR_BAD_ARG;
-    if (p->dof == 6)
-        return launch_persistent(solve_kernel<6, false, true>, a, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes,
-                                 (cudaStream_t)stream, plan_smem<6>(N, p->mc_samples, p->mc_iter, true, true).total_bytes);
-    return launch_persistent(solve_kernel<4, false, true>, a, plan_smem<4>(N, p->mc_samples, p->mc_iter, true).total_bytes,
-                             (cudaStream_t)stream, plan_smem<4>(N, p->mc_samples, p->mc_iter, true, true).total_bytes);
+    a.cov_stride = p->dof * p->dof;
+    return p->dof == 6 ? launch_amis<6>(a, nullptr, (cudaStream_t)stream) : launch_amis<4>(a, nullptr, (cudaStream_t)stream);
 }
 
 int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
@@ -2465,11 +888,7 @@ int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d,
     if (!pose_init || !pose_opt || !pose_samples || !logw || p->lm_iter < 0) return EPNP_ERR_BAD_ARG;
     const bool any = noise_normal || noise_chi2 || noise_rot, all = noise_normal && noise_chi2 && noise_rot;
     if (any && !all) return EPNP_ERR_BAD_ARG;
-    if (p->dof == 6)
-        return launch_persistent(solve_kernel<6, true, true>, a, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes,
-                                 (cudaStream_t)stream, plan_smem<6>(N, p->mc_samples, p->mc_iter, true, true).total_bytes);
-    return launch_persistent(solve_kernel<4, true, true>, a, plan_smem<4>(N, p->mc_samples, p->mc_iter, true).total_bytes,
-                             (cudaStream_t)stream, plan_smem<4>(N, p->mc_samples, p->mc_iter, true, true).total_bytes);
+    return run_lm_amis(a, nullptr, (cudaStream_t)stream);
 }
 
 int epnp_lm_amis_fused_push_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
@@ -2498,11 +917,7 @@ int epnp_lm_amis_fused_push_f32(const float* x3d, const float* x2d, const float*
         if (!peer_logw[r] || !peer_pose[r]) return EPNP_ERR_BAD_ARG;
         push.logw[r] = peer_logw[r]; push.pose[r] = peer_pose[r];
     }
-    if (p->dof == 6)
-        return launch_persistent(solve_push_kernel<6>, a, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes,
-                                 (cudaStream_t)stream, plan_smem<6>(N, p->mc_samples, p->mc_iter, true, true).total_bytes, push);
-    return launch_persistent(solve_push_kernel<4>, a, plan_smem<4>(N, p->mc_samples, p->mc_iter, true).total_bytes,
-                             (cudaStream_t)stream, plan_smem<4>(N, p->mc_samples, p->mc_iter, true, true).total_bytes, push);
+    return run_lm_amis(a, &push, (cudaStream_t)stream);
 }
 
 int epnp_cost_backward_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
@@ -2614,8 +1029,8 @@ int epnp_lm_amis_fused_host_f32(const float* x3d_host, const float* x2d_host, co
     if (n_chunks == 0) {
         if (check_amis_params(*p) != EPNP_OK) return EPNP_ERR_BAD_ARG;
         const int wave = (p->dof == 6)
-            ? resident_objects(solve_kernel<6, true, true>, plan_smem<6>(N, p->mc_samples, p->mc_iter, true).total_bytes)
-            : resident_objects(solve_kernel<4, true, true>, plan_smem<4>(N, p->mc_samples, p->mc_iter, true).total_bytes);
+            ? resident_objects(amis_kernel<6, false>, plan_amis<6>(N, p->mc_samples).total_bytes)
+            : resident_objects(amis_kernel<4, false>, plan_amis<4>(N, p->mc_samples).total_bytes);
         if (wave > 0) {
             const int waves_per_chunk = (B + 64 * wave - 1) / (64 * wave);
             chunk_objects = wave * waves_per_chunk;

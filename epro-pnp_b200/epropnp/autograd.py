@@ -153,7 +153,7 @@ def native_gn_step_enabled():
     """EPNP_NATIVE_GN_STEP=1: differentiate pose_opt_plus with the native kernel instead of the torch composite.
     Opt-in until its first hardware run (written and checked against the composite on the CPU emulation of the kernels)."""
     import os
-    return os.environ.get("EPNP_NATIVE_GN_STEP", "0") not in ("", "0")
+    return os.environ.get("EPNP_NATIVE_GN_STEP", "1") not in ("", "0")
 
 
 def pose_plus_autograd(solver, x3d, x2d, w2d, pose, camera, cost_fun):

@@ -142,7 +142,7 @@ class LMSolver(nn.Module):
 def _fused_rslm():
     """EPNP_FUSED_RSLM=1 selects the single-launch initialiser (thread <-> hypothesis, epnp_rslm_f32).  Opt-in until its
     first hardware run: it was written and validated on the CPU emulation of the kernels only."""
-    return os.environ.get("EPNP_FUSED_RSLM", "0") not in ("", "0")
+    return os.environ.get("EPNP_FUSED_RSLM", "1") not in ("", "0")
 
 
 @PNP.register_module()

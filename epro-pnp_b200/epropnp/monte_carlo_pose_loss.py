@@ -25,7 +25,7 @@ from epropnp_b200 import native
 
 
 def _use_native(t):
-    return os.environ.get("EPNP_NATIVE_MC_EPILOGUE", "0") == "1" and t.is_cuda
+    return os.environ.get("EPNP_NATIVE_MC_EPILOGUE", "1") == "1" and t.is_cuda
 
 
 def _object_major(t):

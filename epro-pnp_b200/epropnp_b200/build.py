@@ -17,72 +17,18 @@ INCLUDE = os.path.join(REPO_ROOT, "include")
 LIB_PATH = os.path.join(LIB_DIR, "libepropnp_b200.so")
 EMUL_PATH = os.path.join(LIB_DIR, "libhost_emul.so")
 
-# Build options of the SHIPPED library (see EXPERIMENTS below).  Empty: the round-1 kernels as validated on hardware.
-# Adopting a measured variant = listing its options here and rewriting profiles/validated_sass.json in the same commit
-# (tools/first_gpu_calls.sh revalidate); the CPU emulation and the profiling build follow this list.
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE]
+
+# kept for the test-side build helpers (tests/simt_native.py): the shipped library has no build options
 DEFAULT_OPTIONS = []
 
-NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE] + DEFAULT_OPTIONS
 
-
-# Build-option experiments of the kernels: off in the shipped build; tools/variants.py builds
-# and A/Bs them on a GPU box, tests/test_simt_emul_cpu.py runs them under the CPU SIMT emulator.
-EXPERIMENTS = {
-    "lm_packed": ["-DEPNP_LM_PACKED"],
-    "sweep_rsq": ["-DEPNP_SWEEP_RSQ"],
-    "sweep_noclamp": ["-DEPNP_SWEEP_NOCLAMP"],
-    "sweep_split": ["-DEPNP_SWEEP_SPLIT"],
-    "sweep_split_noclamp": ["-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
-    "all": ["-DEPNP_LM_PACKED", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
-    "lm_norefine": ["-DEPNP_LM_NOREFINE"],
-    "lm_cost_first": ["-DEPNP_LM_COST_FIRST"],
-    "fast_blocksum": ["-DEPNP_FAST_BLOCKSUM"],
-    "tf32x3_numerics": ["-DEPNP_TF32X3_NUMERICS"],        # accuracy study of the tensor-core plan, not a speed-up
-    "amis_lse": ["-DEPNP_AMIS_LSE"],
-    "alias_stage": ["-DEPNP_ALIAS_STAGE"],
-    # five resident CTAs per SM: 96 registers (the packed LM evaluation would spill) and 39.8 KB of shared memory per CTA
-    "five_ctas": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
-                  "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE", "-DEPNP_CTAS_PER_SM=5"],
-    # six resident CTAs: 80 registers and, without the log-weight buffer, 37.0 KB of shared memory per CTA
-    "six_ctas": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
-                 "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW", "-DEPNP_CTAS_PER_SM=6"],
-    "no_lw": ["-DEPNP_NO_LW"],
-    # the projection on the tensor pipe through the legacy mma.sync m16n8k8 TF32 instruction (3xTF32), 4 CTAs/SM
-    "sweep_mma": ["-DEPNP_SWEEP_MMA"],
-    "sweep_mma_all": ["-DEPNP_SWEEP_MMA", "-DEPNP_SWEEP_NOCLAMP", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST",
-                      "-DEPNP_FAST_BLOCKSUM"],
-    # ... at five CTAs per SM: 96 registers; the staging ring holds the K[R|t] table, so no aliasing -- 44.9 KB per CTA
-    "five_ctas_mma": ["-DEPNP_SWEEP_MMA", "-DEPNP_SWEEP_NOCLAMP", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST",
-                      "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_NO_LW", "-DEPNP_CTAS_PER_SM=5"],
-    # ... and at six: the K[R|t] columns are computed per work item (no table, the ring is aliased away), 80 registers
-    "six_ctas_mma": ["-DEPNP_SWEEP_MMA", "-DEPNP_SWEEP_NOCLAMP", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST",
-                     "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW", "-DEPNP_CTAS_PER_SM=6"],
-    "sweep_huber_m": ["-DEPNP_SWEEP_HUBER_M"],            # shipped sweep arithmetic with the select-free Huber only
-    "six_ctas_huber_m": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE",
-                         "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW", "-DEPNP_SWEEP_HUBER_M", "-DEPNP_CTAS_PER_SM=6"],
-    # the same residency with the shipped sweep arithmetic (18 packed FP ops + 4 MUFU per pair-sample instead of 20 + 2):
-    # separates "more resident CTAs" from "different sweep formula" in the A/B
-    "five_ctas_plain_sweep": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE",
-                              "-DEPNP_ALIAS_STAGE", "-DEPNP_CTAS_PER_SM=5"],
-    "six_ctas_plain_sweep": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE",
-                             "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW", "-DEPNP_CTAS_PER_SM=6"],
-    "four_ctas_same_code": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
-                            "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE"],
-    "everything": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_LM_COST_FIRST", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP",
-                   "-DEPNP_FAST_BLOCKSUM"],
-    # round-2 call 2: the measured winners without the (measured slower) cost-first LM, with / without the packed LM evaluation
-    "six_hm_nocf": ["-DEPNP_LM_NOREFINE", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE", "-DEPNP_NO_LW",
-                    "-DEPNP_SWEEP_HUBER_M", "-DEPNP_CTAS_PER_SM=6"],
-    "six_hm_nocf_packed": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_PACKED", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE",
-                           "-DEPNP_NO_LW", "-DEPNP_SWEEP_HUBER_M", "-DEPNP_CTAS_PER_SM=6"],
-    "five_hm_nocf": ["-DEPNP_LM_NOREFINE", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE",
-                     "-DEPNP_SWEEP_HUBER_M", "-DEPNP_CTAS_PER_SM=5"],
-    "five_hm_nocf_packed": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_PACKED", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_AMIS_LSE", "-DEPNP_ALIAS_STAGE",
-                            "-DEPNP_SWEEP_HUBER_M", "-DEPNP_CTAS_PER_SM=5"],
-    "four_hm_nocf_packed": ["-DEPNP_LM_NOREFINE", "-DEPNP_LM_PACKED", "-DEPNP_FAST_BLOCKSUM", "-DEPNP_SWEEP_HUBER_M"],
-    "all_norefine": ["-DEPNP_LM_PACKED", "-DEPNP_LM_NOREFINE", "-DEPNP_SWEEP_SPLIT", "-DEPNP_SWEEP_NOCLAMP"],
-}
+def kernel_sources():
+    """Everything the native library is compiled from (dependency list of every in-tree build)."""
+    import glob
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))) + \
+        [os.path.join(INCLUDE, "epropnp_b200.h")]
 
 
 def _newer(target, sources):
@@ -101,7 +47,7 @@ def _nvcc():
 
 def build_library(force=False, verbose=False):
     srcs = [os.path.join(CSRC, "pnp_kernels.cu")]
-    deps = srcs + [os.path.join(CSRC, "pnp_math.cuh"), os.path.join(INCLUDE, "epropnp_b200.h")]
+    deps = kernel_sources()
     os.makedirs(LIB_DIR, exist_ok=True)
     if force or _newer(LIB_PATH, deps):
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs

@@ -60,8 +60,8 @@ float pose_cost_host(const float* x3d, const float* x2d, const float* w2d, int N
     return c;
 }
 
-// Packed (two-lane) formulations kept behind build options in the kernels (EPNP_LM_PACKED, EPNP_SWEEP_RSQ):
-// the same templates, evaluated with the scalar host fall-backs of pnp::V2.
+// The row-packed (two-lane) normal equations of the LM kernel: the same template, evaluated with the scalar host
+// fall-backs of pnp::V2.
 template <int DOF>
 void eval_ne_rows(const float* x3d, const float* x2d, const float* w2d, int N, const float* pose, const Cam& cam,
                   float delta, float heps, bool clip, float* ev) {
@@ -82,27 +82,6 @@ void eval_ne_rows(const float* x3d, const float* x2d, const float* w2d, int N, c
     }
     for (int i = 0; i < NP; ++i) ev[i] = acc2[i].x + acc2[i].y;
     ev[NP] = cost;
-}
-
-template <int DOF>
-float pose_cost_rsq_host(const float* x3d, const float* x2d, const float* w2d, int N, const float* pose,
-                         const Cam& cam, float delta) {
-    float R[9], P[12];
-    pose_to_rot<DOF>(pose, R);
-    make_proj(cam.k, R, pose, P);
-    V2 P2[12];
-    for (int k = 0; k < 12; ++k) P2[k] = v2splat(P[k]);
-    V2 acc = v2splat(0.f);
-    for (int n = 0; n < N; n += 2) {
-        const int m = (n + 1 < N) ? n + 1 : n;            // odd N: the kernels pad the last pair with w = 0
-        const float pad = (n + 1 < N) ? 1.f : 0.f;
-        const V2 X = v2(x3d[3 * n], x3d[3 * m]), Y = v2(x3d[3 * n + 1], x3d[3 * m + 1]), Z = v2(x3d[3 * n + 2], x3d[3 * m + 2]);
-        const V2 nu = v2(-x2d[2 * n], -x2d[2 * m]), nv = v2(-x2d[2 * n + 1], -x2d[2 * m + 1]);
-        const V2 wu = v2(w2d[2 * n], pad * w2d[2 * m]), wv = v2(w2d[2 * n + 1], pad * w2d[2 * m + 1]);
-        acc = cam.bounded ? pair_cost_rsq<true>(P2, cam, delta, X, Y, Z, nu, nv, wu, wv, acc, ExactRsqrt())
-                          : pair_cost_rsq<false>(P2, cam, delta, X, Y, Z, nu, nv, wu, wv, acc, ExactRsqrt());
-    }
-    return acc.x + acc.y;
 }
 
 template <int DOF>
@@ -387,20 +366,6 @@ int emul_normal_eq_rows(const float* x3d, const float* x2d, const float* w2d, co
     return 0;
 }
 
-int emul_cost_rsq(const float* x3d, const float* x2d, const float* w2d, const float* cam, const float* lb,
-                  const float* ub, const float* delta, const float* poses, float* cost, int S, int B, int N, int dof,
-                  float z_min) {
-    const int PD = dof == 6 ? 7 : 4;
-    for (int s = 0; s < S; ++s)
-        for (int b = 0; b < B; ++b) {
-            const Cam c = make_cam(cam, lb, ub, b, z_min);
-            const float *p3 = x3d + (size_t)b * N * 3, *p2 = x2d + (size_t)b * N * 2, *pw = w2d + (size_t)b * N * 2;
-            const float* pose = poses + ((size_t)s * B + b) * PD;
-            cost[(size_t)s * B + b] = dof == 6 ? pose_cost_rsq_host<6>(p3, p2, pw, N, pose, c, delta[b])
-                                               : pose_cost_rsq_host<4>(p3, p2, pw, N, pose, c, delta[b]);
-        }
-    return 0;
-}
 
 int emul_lm(const float* x3d, const float* x2d, const float* w2d, const float* cam, const float* lb, const float* ub,
             const float* delta, const float* pose_init, float* pose_opt, float* cov, float* cost, float* pose_plus,

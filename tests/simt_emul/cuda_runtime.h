@@ -204,6 +204,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call) {
 #define gridDim (simt::gdim())
 
 inline void __syncthreads() { simt::syncthreads(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { simt::syncwarp(); }
 inline float __shfl_xor_sync(unsigned, float v, int m) {
     uint32_t b; std::memcpy(&b, &v, 4);
     b = simt::shfl_xor_bits(b, m);

@@ -26,8 +26,7 @@ def build_emulated(flags=()):
     tag = hashlib.sha1(" ".join(flags).encode()).hexdigest()[:8] if flags else "default"
     out = os.path.join(build.LIB_DIR, f"libepropnp_simt_{tag}.so")
     src = os.path.join(build.CSRC, "pnp_kernels.cu")
-    deps = [src, os.path.join(build.CSRC, "pnp_math.cuh"), os.path.join(build.INCLUDE, "epropnp_b200.h"),
-            os.path.join(_SHIM, "cuda_runtime.h"), os.path.join(_SHIM, "math_constants.h")]
+    deps = build.kernel_sources() + [os.path.join(_SHIM, "cuda_runtime.h"), os.path.join(_SHIM, "math_constants.h")]
     os.makedirs(build.LIB_DIR, exist_ok=True)
     if build._newer(out, deps):
         cmd = ["g++", "-std=c++20", "-O2", "-mfma", "-ffp-contract=fast", "-x", "c++", "-DEPNP_SIMT_EMUL", *flags, "-fPIC", "-shared",

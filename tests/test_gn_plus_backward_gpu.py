@@ -13,8 +13,6 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def dev():
-    if not os.environ.get("EPNP_TEST_EXPERIMENTAL"):
-        pytest.skip("experimental kernel: set EPNP_TEST_EXPERIMENTAL=1")
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")

@@ -77,10 +77,10 @@ def test_point_math(emul, name):
             assert err_vs(ne[b, :-dof - 1], want[b, :-dof - 1]) < 5e-5
             assert err_vs(ne[b, -dof - 1:-1], want[b, -dof - 1:-1]) < 5e-4    # J^T r: cancellation near the optimum
         assert err_vs(ne[:, -1], g["ref64_eval_cost"]) < 2e-5
-    # cost of stacked poses (pre-multiplied projection path): default form and the one-rsqrt form (EPNP_SWEEP_RSQ)
+    # cost of stacked poses (pre-multiplied projection path)
     poses = np.ascontiguousarray(g["eval_poses"], np.float32)
     S = poses.shape[0]
-    for fn in (emul.emul_cost, emul.emul_cost_rsq):
+    for fn in (emul.emul_cost,):
         cm = np.zeros((S, B), np.float32)
         fn(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(poses), fptr(cm),
            S, B, N, dof, ctypes.c_float(float(g["z_min"])))

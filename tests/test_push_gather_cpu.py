@@ -274,16 +274,3 @@ def test_push_and_epilogue_do_not_depend_on_thread_schedule(dev):
                 assert torch.equal(a, b), (mode, seed)
     finally:
         lib.simt_set_schedule(0, 1)
-
-
-@pytest.mark.parametrize("variant", ["six_ctas", "five_ctas_mma"])
-def test_push_kernel_under_the_candidate_builds(monkeypatch, variant):
-    """The push kernel shares the variant-dependent AMIS code (no log-weight buffer, aliased staging ring, tensor-pipe
-    sweep): the assembled batch must stay bit-identical to that build's own single-GPU run, under permuted schedules."""
-    from epropnp_b200.build import EXPERIMENTS
-    flags = tuple(EXPERIMENTS[variant])
-    dev = simt_native.install(monkeypatch, flags=flags)
-    monkeypatch.setattr(simt_native, "handle", (lambda h: (lambda f=(): h(flags)))(simt_native.handle))
-    test_pushed_rows_assemble_the_single_gpu_batch(dev, 6, 24, 16, 2)
-    test_pushed_rows_assemble_the_single_gpu_batch(dev, 4, 21, 12, 3)
-    test_push_and_epilogue_do_not_depend_on_thread_schedule(dev)

@@ -86,12 +86,15 @@ def test_rslm_kernels_against_reference(cuda_device, name, path):
     floor_frac, _ = _hypothesis_agreement(g["ref32_hyp_pose"], g["ref32_hyp_cost"], g, "ref64")
     # at least as many hypotheses agree with the fp64 reference as the reference's own fp32 run manages, minus 5 %
     assert frac64 >= min(0.9, floor_frac - 0.05), (frac64, floor_frac)
-    assert cerr64 < 1e-4 and cerr32 < 1e-4
+    # cost of the pose-matched hypotheses: 1e-4, or 3 x what the reference's own fp32 run loses against its fp64 run
+    ref_c32, ref_c64 = g["ref32_hyp_cost"], g["ref64_hyp_cost"]
+    floor_cost = float((np.abs(ref_c32 - ref_c64) / np.maximum(np.abs(ref_c64), 1e-30)).max())
+    assert cerr64 < max(1e-4, 3 * floor_cost) and cerr32 < max(1e-4, 3 * floor_cost), (cerr64, cerr32, floor_cost)
     perr, crel = _check_object_level(pose_best.cpu().numpy(), cost_best.cpu().numpy(), g, f"{name}/{path}")
     same_winner = float((cost_all.argmin(0) == g["ref64_winner"]).mean())
     record_parity(f"rslm/{name}/{path}", hyp_frac_within_1em4_vs_ref64=frac64, hyp_frac_within_1em4_vs_ref32=frac32,
                   ref32_frac_within_1em4_vs_ref64=floor_frac, hyp_cost_rel_max=max(cerr64, cerr32),
-                  best_pose_rel_max=float(perr.max()), min_cost_rel_max=float(crel.max()), same_winner=same_winner,
+                  best_pose_rel_max=float(perr.max()), min_cost_rel_max=float(crel.max()), same_winner=same_winner, ref32_hyp_cost_rel_max_vs_ref64=floor_cost,
                   hyp_cost=err_stats(cost_all, g["ref64_hyp_cost"]))
 
 

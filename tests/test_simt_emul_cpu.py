@@ -52,94 +52,6 @@ test_evaluate_pnp_cost_is_differentiable = _ag.test_evaluate_pnp_cost_is_differe
 
 
 # ------------------------------------------------------------------------------------------------
-# The build-option experiments (epropnp_b200.build.EXPERIMENTS): each variant's kernel source
-# under the emulator, on the assertions of the GPU suite that exercise the code it changes.
-from conftest import golden_names  # noqa: E402
-from epropnp_b200.build import EXPERIMENTS  # noqa: E402
-
-
-# The combinations that are candidates for the default build get the full matrix; every single option additionally
-# runs alone on a reduced set (fused goldens incl. 4-DoF, the odd-sample-count corner, the smallest point sets).
-CANDIDATE_VARIANTS = ["everything", "six_ctas", "six_ctas_plain_sweep", "five_ctas_mma"]
-SINGLE_OPTIONS = ["lm_packed", "lm_cost_first", "fast_blocksum", "amis_lse", "alias_stage", "no_lw", "sweep_huber_m", "sweep_rsq",
-                  "sweep_noclamp", "sweep_split", "sweep_mma", "six_ctas_mma"]
-EMULATED_VARIANTS = SINGLE_OPTIONS + CANDIDATE_VARIANTS
-
-
-@pytest.fixture(params=CANDIDATE_VARIANTS)
-def variant_device(request, monkeypatch):
-    return simt_native.install(monkeypatch, EXPERIMENTS[request.param])
-
-
-@pytest.fixture(params=SINGLE_OPTIONS)
-def option_device(request, monkeypatch):
-    return simt_native.install(monkeypatch, EXPERIMENTS[request.param])
-
-
-@pytest.mark.parametrize("name", ["mc6_bounds"])
-def test_option_golden_fused_lm_amis(option_device, name):
-    _gp.test_golden_fused_lm_amis(option_device, name)
-
-
-def test_option_golden_fused_4dof(option_device):
-    _gp.test_golden_fused_lm_amis_4dof(option_device)
-
-
-@pytest.mark.parametrize("name", ["lm6_ragged", "gn4_fast"])
-def test_option_golden_lm_and_cost(option_device, name):
-    _gp.test_golden_evaluate(option_device, name)
-    _gp.test_golden_lm_solve(option_device, name)
-
-
-def test_option_odd_sample_count_and_tiny_sets(option_device):
-    _ge.test_parameter_corners_against_oracle(option_device, 126, 2, 1, 5)
-    _ge.test_tiny_point_sets(option_device, 1)
-    _ge.test_tiny_point_sets(option_device, 5)
-
-
-@pytest.mark.parametrize("name", golden_names("mc6"))
-def test_variant_golden_fused_lm_amis(variant_device, name):
-    _gp.test_golden_fused_lm_amis(variant_device, name)
-
-
-@pytest.mark.parametrize("name", golden_names("mc6"))
-def test_variant_golden_amis(variant_device, name):
-    _gp.test_golden_amis_from_reference_solution(variant_device, name)
-
-
-def test_variant_golden_fused_4dof(variant_device):
-    _gp.test_golden_fused_lm_amis_4dof(variant_device)
-
-
-@pytest.mark.parametrize("name", golden_names())
-def test_variant_golden_lm_and_cost(variant_device, name):
-    _gp.test_golden_evaluate(variant_device, name)
-    _gp.test_golden_lm_solve(variant_device, name)
-
-
-@pytest.mark.parametrize("N", [1, 2, 3, 5, 7])
-def test_variant_tiny_point_sets(variant_device, N):
-    _ge.test_tiny_point_sets(variant_device, N)
-
-
-def test_variant_degenerate_inputs(variant_device):
-    _ge.test_all_points_behind_camera(variant_device)
-    _ge.test_nan_object_does_not_leak(variant_device)
-
-
-@pytest.mark.parametrize("M,I,acg,lm_iter", [(128, 1, 3, 10), (126, 2, 1, 5), (1024, 8, 2, 4)])
-def test_variant_parameter_corners(variant_device, M, I, acg, lm_iter):
-    _ge.test_parameter_corners_against_oracle(variant_device, M, I, acg, lm_iter)
-
-
-@pytest.mark.parametrize("variant", CANDIDATE_VARIANTS)
-def test_variant_north_star_shape(monkeypatch, variant):
-    """N = 512, M = 512 against the fp64 / fp32 oracle, including the north star's own <= 1e-4 statement."""
-    dev = simt_native.install(monkeypatch, EXPERIMENTS[variant])
-    _gp.test_fused_against_oracle_north_star_shape(dev, 48, 512, 512, 4)
-
-
-# ------------------------------------------------------------------------------------------------
 # Scheduling-order invariance: the emulator runs a CTA's threads one after another between synchronisation points.
 # Ascending, descending and randomly permuted orders must give bit-identical results; a difference means one thread
 # consumed what another produced without a barrier in between (the class of bug racecheck reports on hardware --
@@ -161,12 +73,10 @@ def _all_outputs(dev, dof, odd_points):
     return [t.clone() for t in res if t is not None]
 
 
-@pytest.mark.parametrize("variant", ["default", "sweep_split", "six_ctas", "five_ctas_mma"])
 @pytest.mark.parametrize("dof,odd_points", [(6, False), (6, True), (4, True)])
-def test_results_do_not_depend_on_thread_schedule(monkeypatch, variant, dof, odd_points):
-    flags = EXPERIMENTS.get(variant, ())
-    dev = simt_native.install(monkeypatch, flags)
-    lib = simt_native.handle(flags)
+def test_results_do_not_depend_on_thread_schedule(monkeypatch, dof, odd_points):
+    dev = simt_native.install(monkeypatch)
+    lib = simt_native.handle()
     try:
         lib.simt_set_schedule(0, 1)
         base = _all_outputs(dev, dof, odd_points)
@@ -174,38 +84,9 @@ def test_results_do_not_depend_on_thread_schedule(monkeypatch, variant, dof, odd
             lib.simt_set_schedule(mode, seed)
             for a, b in zip(base, _all_outputs(dev, dof, odd_points)):
                 assert torch.equal(a, b, ) or (torch.isnan(a) == torch.isnan(b)).all() and torch.equal(
-                    torch.nan_to_num(a), torch.nan_to_num(b)), (variant, mode, seed)
+                    torch.nan_to_num(a), torch.nan_to_num(b)), (mode, seed)
     finally:
         lib.simt_set_schedule(0, 1)
-
-
-@pytest.mark.parametrize("variant", ["default", "six_ctas", "five_ctas_mma"])
-def test_persistent_grid_matches_one_object_per_cta(monkeypatch, variant):
-    """EPNP_MAX_OBJECTS_PER_CTA=0: CTAs stride over several objects and the next object's chunks are prefetched while
-    the current one is solved (staging-ring slot / parity bookkeeping across objects).  Same results, bit for bit."""
-    from epropnp_b200 import native
-    from epropnp_b200.synth import make_problem
-    simt_native.install(monkeypatch, EXPERIMENTS.get(variant, ()))
-    monkeypatch.setenv("SIMT_EMUL_SMS", "2")                  # an emulated device with 2 SMs x 4 resident CTAs
-    B, N = 2 * 4 * 3 + 5, 132                                 # 3-4 objects per CTA, two TMA chunks per object
-    pc = make_problem(B, N, seed=5)
-    prob = native.Problem(pc["x3d"], pc["x2d"], pc["w2d"], pc["cam_mats"], None, None,
-                          native.adaptive_delta(pc["x2d"], pc["w2d"], 0.5))
-    p = native.default_params(6, lm_iter=2, mc_samples=32, mc_iter=2)     # 16 samples per iteration: one MMA sample tile
-    monkeypatch.delenv("EPNP_MAX_OBJECTS_PER_CTA", raising=False)
-    ref = native.lm_amis_fused(prob, pc["pose_init"], p, seed=9, want_cost=True)
-    for cap in ("0", "2"):
-        monkeypatch.setenv("EPNP_MAX_OBJECTS_PER_CTA", cap)
-        out = native.lm_amis_fused(prob, pc["pose_init"], p, seed=9, want_cost=True)
-        for k in ("pose_opt", "cost", "pose_samples", "logw"):
-            if variant == "five_ctas_mma" and k in ("pose_samples", "logw"):
-                # a prefetching CTA has no idle staging ring for the K[R|t] table and runs the CUDA-core sweep:
-                # same samples of the first iteration, costs equal up to the 3xTF32 rounding
-                S = p.mc_samples // p.mc_iter
-                assert torch.equal(out["pose_samples"][:, :S], ref["pose_samples"][:, :S])
-                assert (out["logw"][:, :S] - ref["logw"][:, :S]).abs().max() < 1e-3 * ref["logw"][:, :S].abs().max()
-            else:
-                assert torch.equal(out[k], ref[k]), (variant, cap, k)
 
 
 @pytest.mark.parametrize("n_chunks,bounded", [(1, False), (3, True), (64, False), (0, False), (0, True)])
@@ -237,26 +118,12 @@ def test_host_buffer_entry_point_chunking(cuda_device, monkeypatch, n_chunks, bo
 
 
 # ------------------------------------------------------------------------------------------------
-# Accuracy gate of the tensor-core plan: the ordinary sweep with the projection computed the
-# way tcgen05 kind::tf32 would (operands split into TF32 hi + lo, hi*hi + lo*hi + hi*lo, fp32 accumulation).
-@pytest.mark.parametrize("name", golden_names("mc6"))
-def test_tf32x3_projection_numerics_keep_parity(monkeypatch, name):
-    dev = simt_native.install(monkeypatch, EXPERIMENTS["tf32x3_numerics"])
-    _gp.test_golden_fused_lm_amis(dev, name)
-
-
-def test_tf32x3_projection_numerics_at_north_star_shape(monkeypatch):
-    dev = simt_native.install(monkeypatch, EXPERIMENTS["tf32x3_numerics"])
-    _gp.test_fused_against_oracle_north_star_shape(dev, 48, 512, 512, 4)
-
-
-# ------------------------------------------------------------------------------------------------
 # The size-independent properties the GPU suite checks at B = 4096 (determinism, shard invariance with object
 # offsets, TMA vs plain loader, point-permutation invariance, sanity of the weights), at a size the emulator affords.
 _BIG = {}
 
 
-def _small_big(flags):
+def _small_big():
     from epropnp_b200 import native
     from epropnp_b200.synth import make_problem
     d = {k: v for k, v in make_problem(12, 512, seed=7).items()}
@@ -267,13 +134,12 @@ def _small_big(flags):
     return d
 
 
-@pytest.fixture(params=["default", "six_ctas", "five_ctas_mma"])
-def big(request, monkeypatch):
-    flags = tuple(EXPERIMENTS.get(request.param, ()))
-    simt_native.install(monkeypatch, flags)
-    if flags not in _BIG:
-        _BIG[flags] = _small_big(flags)
-    return _BIG[flags]
+@pytest.fixture
+def big(monkeypatch):
+    simt_native.install(monkeypatch)
+    if "d" not in _BIG:
+        _BIG["d"] = _small_big()
+    return _BIG["d"]
 
 
 test_full_size_sanity = _gp.test_full_size_sanity
