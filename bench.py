@@ -1,26 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- EPro-PnP hot path on B200: PnP objects/sec at (B=4096 per GPU, N=512, M=512).
+"""bench.py -- EPro-PnP hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]           # our arm  (N>1: launched by torchrun)
-    python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU arm: the reference's algorithm
-                                                                   # (oracle port) on the host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config fused|lm_only|amis|dense|train]   # our arm
+    python bench.py --impl reference [--gpus N] [--steps K] [--config ...]                          # CPU arm
 
-One "step" = one pass of the hot path over one batch of synthetic correspondence sets: the fused
-LM(10) + covariance + AMIS(4 x 128) kernel on 4096 objects per GPU (BASELINE.json config #3/#5 shape,
-EProPnP6DoF.monte_carlo_forward with pose_init given), followed, for N > 1, by the single NCCL gather
-of poses + log-weights.  Prints ONE JSON line (rank 0).
+Default = the headline metric: PnP objects/sec at (B = 4096 per GPU, N = 512, M = 512), BASELINE.json configs #3 / #5's
+shape.  One "step" = one pass of the hot path over one batch of synthetic correspondence sets through ONE C-ABI call
+(epnp_lm_amis_fused_f32: the warp-per-object LM kernel, then the CTA-per-object AMIS kernel, same stream), followed,
+for N > 1, by the single gather of poses + log-weights.  Prints ONE JSON line (rank 0).  The other configs are
+BASELINE.json's #2 (LM only, B = 1024), #3 (B = 1024), #4 (dense 64 x 64 coordinate map, B = 256) and the training step
+(forward + backward through the drop-in classes); each prints the same line layout.
 
   value      objects/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        the same through the C-ABI call with HOST (pinned) buffers: H2D of all inputs and D2H of
-             pose / covariance / cost / log-weights / samples inside the timed region
-  roofline   algorithmic HBM bytes per launch / launch time vs the measured copy bandwidth
-             (MEASURED_PEAKS.json).  The kernel is FP32-pipe bound, not HBM bound:
-             `issue` reports executed warp-instructions (ncu) per second against 148 SM x 4 schedulers x clock.
-  cpu_baseline   oracle/pnp_oracle.py (same algorithm as the reference's PyTorch layer, batched torch ops,
-             all host threads) on a bounded sample of the same workload; rank 0, N = 1 only.
+  e2e        the same through the host-buffer call (pinned host tensors; H2D of the inputs and D2H of the results inside
+             the timed region), min / median / max over the timed steps as well
+  roofline   the dominant kernel (amis_kernel; lm_warp_kernel for lm_only): algorithmic HBM bytes per launch / its
+             launch time (CUDA events around that kernel alone, measured in this run) against MEASURED_PEAKS.json.
+             The path is FP32-pipe bound, not HBM bound: `issue` reports the kernel's executed
+             warp-instructions (profiles/kernel_stats.json, from the committed ncu capture of the SAME SASS -- refused
+             when the kernel's SASS fingerprint has changed since) per second against 148 SM x 4 schedulers x clock.
+  cpu_baseline   the UNMODIFIED reference layer (oracle/_ref staged by oracle/stage_ref.py + oracle/pyro_shim) -- or the
+             oracle port when it has not been staged -- on all host cores (one worker process per 4 cores, the objects
+             are independent), bounded sample; rank 0, N = 1 only.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -34,17 +39,32 @@ sys.path.insert(0, os.path.join(ROOT, "epro-pnp_b200"))
 
 import torch  # noqa: E402
 
-B_PER_GPU, N_PTS, MC_SAMPLES, MC_ITER, LM_ITER = 4096, 512, 512, 4, 10
-ROTATING_SETS = 4                         # 4 x 58.7 MB of inputs > 126 MB L2
-E2E_CHUNKS = int(os.environ.get("EPNP_E2E_CHUNKS", "4"))   # object chunks of the host-buffer pipeline
-# host-buffer calls in flight: with 2, consecutive steps alternate between two (stream, workspace, pinned result set)
-# triples, so step i+1's upload runs under step i's solve / download (a double-buffered input pipeline).  1 = every
-# step waits for the previous one (the measured round-1 configuration).
-E2E_LANES = max(1, int(os.environ.get("EPNP_E2E_LANES", "1")))
+# name -> workload.  kind: "lm_amis" = epnp_lm_amis_fused_f32, "lm" = epnp_lm_solve_f32, "train" = forward + backward
+CONFIGS = {
+    "fused": dict(B=4096, N=512, M=512, I=4, lm_iter=10, fast=0, z_min=0.1, rel_delta=0.5, grid2d=False, kind="lm_amis",
+                  metric="PnP objects/sec (B=4096,N=512,M=512)",
+                  what="fused EProPnP6DoF.monte_carlo_forward: LM(10) + cov + AMIS(4x128)"),
+    "lm_only": dict(B=1024, N=512, M=0, I=0, lm_iter=10, fast=0, z_min=0.1, rel_delta=0.5, grid2d=False, kind="lm",
+                    metric="PnP objects/sec (B=1024,N=512,LM only)", what="BASELINE #2: LMSolver 10 iterations + covariance, no MC"),
+    "amis": dict(B=1024, N=512, M=512, I=4, lm_iter=10, fast=0, z_min=0.1, rel_delta=0.5, grid2d=False, kind="lm_amis",
+                 metric="PnP objects/sec (B=1024,N=512,M=512)", what="BASELINE #3: LM(10) init + AMIS(4x128)"),
+    "dense": dict(B=256, N=4096, M=512, I=4, lm_iter=3, fast=1, z_min=0.01, rel_delta=0.1, grid2d=True, kind="lm_amis",
+                  metric="PnP objects/sec (B=256,N=4096,M=512)",
+                  what="BASELINE #4: dense 64x64 coordinate map, AdaptiveHuber(0.1), GN(3) + AMIS(4x128) (lib/test.py:148-229)"),
+    "train": dict(B=4096, N=512, M=512, I=4, lm_iter=10, fast=0, z_min=0.1, rel_delta=0.5, grid2d=False, kind="train",
+                  metric="PnP training objects/sec (B=4096,N=512,M=512)",
+                  what="training step through the drop-in classes: set_param, monte_carlo_forward (pose_init given), "
+                       "MonteCarloPoseLoss, backward to x3d / x2d / w2d"),
+}
+E2E_CHUNKS = int(os.environ.get("EPNP_E2E_CHUNKS", "8"))   # object chunks of the host-buffer pipeline (0 = whole waves)
+# host-buffer calls in flight: consecutive steps alternate between this many (stream, workspace, pinned result set)
+# triples, so step i+1's upload runs under step i's solve / download (a double-buffered input pipeline)
+E2E_LANES = max(1, int(os.environ.get("EPNP_E2E_LANES", "2")))
 WARM_SECONDS = 0.5            # minimum duration of back-to-back warm-up launches before the timed region
-# EPNP_E2E_NUMA=1: allocate the pinned host buffers while the thread is bound to the CPUs NVML reports as local to the
-# GPU (first touch puts the pages on the GPU's NUMA node; a remote node costs upload bandwidth).  Off = as measured.
-E2E_NUMA = os.environ.get("EPNP_E2E_NUMA", "0") == "1"
+# allocate the pinned host buffers while the thread is bound to the CPUs NVML reports as local to the GPU (first touch
+# puts the pages on the GPU's NUMA node; a remote node costs upload bandwidth)
+E2E_NUMA = os.environ.get("EPNP_E2E_NUMA", "1") == "1"
+L2_BYTES = 126e6
 
 
 class gpu_local_cpus:
@@ -81,18 +101,15 @@ class gpu_local_cpus:
         return False
 
 
-METRIC = "PnP objects/sec (B=4096,N=512,M=512)"
 
-
-def algorithmic_bytes_per_object(n=N_PTS, m=MC_SAMPLES):
-    """read 28 N + 36 (K) + 4 (delta) + 28 (pose_init); write 28 (pose) + 144 (cov) + 4 (cost)
-    + 28 M (samples) + 4 M (log-weights)."""
-    return 28 * n + 36 + 4 + 28 + 28 + 144 + 4 + 28 * m + 4 * m
-
-
-# Executed warp-instructions per object of the fused kernel at (N, M, K) = (512, 512, 10), from the committed
-# `ncu --set full` capture (profiles/r1_final_fused_ncu_raw_metrics.json: smsp__inst_executed.sum / 4096 objects).
-WARP_INSTR_PER_OBJECT = 954271847 / 4096.0
+def algorithmic_bytes_per_object(cfg, kernel):
+    """SURVEY.md section 8(d).  amis_kernel: read 28 N (correspondences) + 36 (K) + 4 (delta) + 28 (pose) + 144 (cov),
+    write 28 M (samples) + 4 M (log-weights).  lm_warp_kernel: read 28 N + 36 + 4 + 28 (pose_init), write 28 (pose) + 144
+    (cov) + 4 (cost).  The fused call = both (the correspondences are read once by each kernel)."""
+    n, m = cfg["N"], cfg["M"]
+    lm = 28 * n + 36 + 4 + 28 + 28 + 144 + 4
+    amis = 28 * n + 36 + 4 + 28 + 144 + 28 * m + 4 * m
+    return dict(lm_warp_kernel=lm, amis_kernel=amis)[kernel]
 
 
 def load_peaks():
@@ -103,15 +120,26 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
-def measured_traffic():
-    """dram bytes per launch of the fused kernel from the committed ncu --set full capture, if any."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get("fused_dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
+def kernel_stats(kernel, cfg_name):
+    """Per-launch numbers of `kernel` from the committed ncu capture (profiles/kernel_stats.json, written by
+    tools/ncu_summary.py): executed warp-instructions and DRAM bytes -- ONLY if the kernel's SASS in the library that
+    is about to be timed is bit-identical to the SASS that was profiled.  Otherwise (None, why)."""
+    path = os.path.join(ROOT, "profiles", "kernel_stats.json")
+    if not os.path.exists(path):
+        return None, "no profiles/kernel_stats.json"
+    try:
+        rec = json.load(open(path)).get(f"{kernel}@{cfg_name}")
+        if rec is None:
+            return None, f"no capture of {kernel} at config {cfg_name}"
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sass_identity
+        have = sass_identity.fingerprints(sass_identity.DEFAULT_LIB)
+        sha = {k: v["sha1"] for k, v in have.items() if rec["sass_symbol"] in k}
+        if rec["sass_sha1"] not in sha.values():
+            return None, "stale: the kernel's SASS changed since the capture (re-profile, tools/ncu_summary.py)"
+        return rec, "profiles/kernel_stats.json (same SASS fingerprint)"
+    except Exception as ex:                                # noqa: BLE001
+        return None, f"unavailable: {type(ex).__name__}: {ex}"
 
 
 class ClockSampler:
@@ -188,128 +216,100 @@ class ClockSampler:
         return out
 
 
-_CPU_SETUP = {}
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
-def _cpu_problem(n_pts, m, batch):
-    from oracle import pnp_oracle as orc
-    from epropnp_b200.synth import make_noise, make_problem
-    key = (n_pts, m, batch)
-    if key not in _CPU_SETUP:
-        pc = make_problem(batch, n_pts, seed=5)
-        n3, c2, n4 = make_noise(batch, m, seed=6)
-        S = m // MC_ITER
-        noise = (n3.reshape(batch, MC_ITER, S, 3).permute(1, 2, 0, 3).contiguous(),
-                 c2.reshape(batch, MC_ITER, S).permute(1, 2, 0).contiguous(),
-                 n4.reshape(batch, MC_ITER, S, 4).permute(1, 2, 0, 3).contiguous())
-        cam = orc.Camera(pc["cam_mats"], 0.1)
-
-        def run():
-            with torch.no_grad():
-                delta = orc.adaptive_delta(pc["x2d"], pc["w2d"], 0.5)
-                return orc.monte_carlo_forward_6dof(pc["x3d"], pc["x2d"], pc["w2d"], cam, delta, pc["pose_init"], noise,
-                                                    m, MC_ITER, orc.LMParams(num_iter=LM_ITER))
-        _CPU_SETUP[key] = run
-    return _CPU_SETUP[key]
-
-
-def _best_thread_count(run):
-    """The batched torch ops of the CPU path stop scaling (and collapse) long before 128 threads: try a few
-    thread counts on one short run each and keep the fastest -- that is 'all the threads it can use'."""
-    if "threads" in _CPU_SETUP:
-        return _CPU_SETUP["threads"]
-    ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
-    best, best_t = cands[0], float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
-        run()
-        t0 = time.perf_counter()
-        run()
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = c, dt
-        if dt > 4 * best_t:
-            break
-    _CPU_SETUP["threads"] = best
-    return best
+def cpu_reference_rates(cfg, steps, warmup, seconds_per_step, threads_per_worker=4):
+    """objects/s of the reference's own CPU path on ALL host cores, per step.  One worker process per
+    `threads_per_worker` cores (oracle/ref_worker.py; the objects are independent, and the reference's batched torch ops
+    stop scaling long before 128 threads in one process); every worker runs `warmup + steps` slices of `seconds_per_step`
+    on its own bounded sample and reports objects / seconds per slice; a step's rate is the sum over the workers."""
+    cores = host_cores()
+    nproc = max(1, cores // threads_per_worker)
+    per = 16 if cfg["N"] <= 1024 else 2          # objects per pass and worker
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_worker.py"), "--objects", str(per), "--threads",
+           str(threads_per_worker), "--points", str(cfg["N"]), "--samples", str(max(cfg["M"], cfg["I"] or 1)),
+           "--mc-iter", str(cfg["I"] or 1), "--lm-iter", str(cfg["lm_iter"]), "--config",
+           "lm_only" if cfg["kind"] == "lm" else "fused", "--slices", str(steps + warmup), "--seconds", str(seconds_per_step)]
+    if cfg["fast"]:
+        cmd += ["--fast-mode", "--z-min", str(cfg["z_min"]), "--rel-delta", str(cfg["rel_delta"]), "--grid2d"]
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads_per_worker), MKL_NUM_THREADS=str(threads_per_worker), CUDA_VISIBLE_DEVICES="")
+    procs = [subprocess.Popen(cmd + ["--seed", str(5 + i)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+             for i in range(nproc)]
+    outs = []
+    for p in procs:
+        so, se = p.communicate()
+        line = [l for l in so.splitlines() if l.startswith("{")]
+        if p.returncode == 0 and line:
+            outs.append(json.loads(line[-1]))
+    if not outs:
+        raise RuntimeError("no CPU worker finished: " + (se or "")[-400:])
+    rates = [sum(o["slices"][s][0] / o["slices"][s][1] for o in outs) for s in range(warmup, warmup + steps)]
+    kind = outs[0]["kind"]
+    sample = (f"{len(outs)} worker processes x {threads_per_worker} threads = {len(outs) * threads_per_worker} of {cores} host cores; "
+              f"each worker: passes of {per} objects (N={cfg['N']}, M={cfg['M']}, LM {cfg['lm_iter']}"
+              f"{' + AMIS ' + str(cfg['I']) + 'x' + str(cfg['M'] // cfg['I']) if cfg['M'] else ''}) for {seconds_per_step:.1f} s per step, fp32; "
+              f"{'EProPnP6DoF.monte_carlo_forward of the unmodified reference (oracle/_ref) + pyro shim' if kind == 'reference+shim' else 'oracle port (reference not staged)'}")
+    return rates, len(outs) * threads_per_worker, kind, sample
 
 
-def cpu_oracle_rate(target_seconds, n_pts=N_PTS, m=MC_SAMPLES, batch=64):
-    """objects/s of the oracle port (LM + AMIS, fp32, best-performing host thread count) on a bounded sample."""
-    run = _cpu_problem(n_pts, m, batch)
-    threads = _best_thread_count(run)
-    torch.set_num_threads(threads)
-    S = m // MC_ITER
-    if ("warmed", n_pts, m, batch) not in _CPU_SETUP:       # one untimed pass per problem shape (allocator, thread pool)
-        run()
-        _CPU_SETUP[("warmed", n_pts, m, batch)] = True
-    t0 = time.perf_counter()
-    runs = 0
-    while True:
-        run()
-        runs += 1
-        el = time.perf_counter() - t0
-        if el >= target_seconds or runs >= 400:
-            break
-    return batch * runs / el, threads, (f"{runs} runs x {batch} objects (N={n_pts}, M={m}, LM {LM_ITER} + AMIS {MC_ITER}x{S}), "
-                                        f"fp32, {threads} threads (best of a sweep up to {os.cpu_count()}), {el:.1f} s")
-
-
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, cfg, rank):
     if rank != 0:
         return
-    # the whole arm is bounded to about 2.5 minutes whatever K and W are: a step is a sample of the workload that fits its
-    # share of that budget (64 objects per pass when a step has half a second or more, else 16, else 4)
-    per_step = min(20.0, 150.0 / max(1, args.steps + args.warmup))
-    batch = 64 if per_step >= 0.5 else (16 if per_step >= 0.12 else 4)
-    for _ in range(args.warmup):
-        cpu_oracle_rate(min(per_step, 3.0), batch=batch)
-    rates, sample, cores = [], "", 1
+    # the whole arm is bounded to about 2.5 minutes whatever K and W are
+    per_step = max(1.0, min(20.0, 140.0 / max(1, args.steps + args.warmup)))
+    steps = args.steps if (args.steps + args.warmup) * per_step <= 150 else max(1, int(150 / per_step) - args.warmup)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r, cores, sample = cpu_oracle_rate(per_step, batch=batch)
-        rates.append(r)
+    rates, cores, kind, sample = cpu_reference_rates(cfg, steps, args.warmup, per_step)
     el = time.perf_counter() - t0
     value = statistics.mean(rates)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(1, args.steps),
+    line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": "objects/s", "n_gpus": args.gpus,
+            "steps": args.steps, "steps_run": steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"EProPnP6DoF LM({LM_ITER})+AMIS({MC_ITER}x{MC_SAMPLES // MC_ITER}), N={N_PTS}, "
-                                   f"M={MC_SAMPLES}; CPU arm on a bounded sample per step"},
-            "cpu_baseline": {"value": value, "unit": "objects/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": f"{cfg['what']}, N={cfg['N']}, M={cfg['M']}; CPU arm on a bounded sample per step",
+                       "name": args.config},
+            "cpu_baseline": {"value": value, "unit": "objects/s", "cores": cores, "kind": kind, "sample": sample,
+                             "per_step_min_max": [min(rates), max(rates)], "wall_s": el},
             "e2e": {"value": value, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="fused", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "nccl-coalesced", "peer", "push"],
-                    help="N > 1: 'nccl' = overlapped all_gather_into_tensor (default, the measured configuration); "
-                         "'peer' = copy-engine pulls from IPC-mapped peer buffers (sharded.PeerGather, experimental)")
+    ap.add_argument("--gather", default="push", choices=["nccl", "nccl-coalesced", "peer", "push"],
+                    help="N > 1: 'push' = the AMIS kernel stores finished rows into every rank's result buffer over "
+                         "NVLink (no gather kernel); 'nccl' = overlapped all_gather_into_tensor; 'peer' = copy-engine pulls")
     ap.add_argument("--nccl-max-ctas", type=int, default=0,
-                    help="N > 1: cap the CTAs NCCL may use per collective (sets NCCL_MAX_CTAS before the communicator is "
-                         "created; 0 = NCCL's default).  The overlapped gather shares the SMs with the next solve.")
+                    help="N > 1, --gather nccl: cap the CTAs NCCL may use per collective (0 = NCCL's default)")
     ap.add_argument("--streams", type=int, default=1,
-                    help="batches in flight: consecutive (independent) batches are issued round-robin on this many CUDA "
-                         "streams, so the next batch's CTAs fill the SMs the previous batch's last wave leaves idle. "
-                         "1 = every batch on one stream (the measured round-1 configuration).")
-    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="objects per GPU (default: the metric's 4096)")
+                    help="batches in flight: consecutive (independent) batches are issued round-robin on this many CUDA streams")
+    ap.add_argument("--batch", type=int, default=0, help="objects per GPU (default: the config's)")
     args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.batch > 0:
+        cfg["B"] = args.batch
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, cfg, rank)
         return
 
     import torch.distributed as dist
@@ -331,22 +331,60 @@ def main():
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
-    Bg = args.batch
+    Bg, N_PTS, M, I = cfg["B"], cfg["N"], cfg["M"], cfg["I"]
     B_total = Bg * world
+    kind = cfg["kind"]
+    gathering = world > 1 and kind == "lm_amis"
 
-    # ---- synthetic inputs of this rank's shard (global object index keys the RNG, rank keys the data seed)
-    pc = make_problem(Bg, N_PTS, seed=1000 + rank)
+    # ---- synthetic inputs of this rank's shard (global object index keys the RNG, rank keys the data seed); enough
+    # rotating input sets that consecutive steps cannot be served from the 126 MB L2
+    set_bytes = 28 * N_PTS * Bg
+    n_sets = max(2, min(16, int(math.ceil(1.15 * L2_BYTES / set_bytes)) + 1))
+    pc = make_problem(Bg, N_PTS, seed=1000 + rank, grid2d=cfg["grid2d"])
     sets = []
-    for r in range(ROTATING_SETS):
-        shift = (r * Bg) // ROTATING_SETS
+    for r in range(n_sets):
+        shift = (r * Bg) // n_sets
         d = {k: torch.roll(v, shifts=shift, dims=0).to(dev).contiguous() for k, v in pc.items()}
-        d["delta"] = native.adaptive_delta(d["x2d"], d["w2d"], 0.5)
+        d["delta"] = native.adaptive_delta(d["x2d"], d["w2d"], cfg["rel_delta"])
         d["prob"] = native.Problem(d["x3d"], d["x2d"], d["w2d"], d["cam_mats"], None, None, d["delta"])
         sets.append(d)
-    params = native.default_params(6, lm_iter=LM_ITER, mc_samples=MC_SAMPLES, mc_iter=MC_ITER)
+    params = native.default_params(6, lm_iter=cfg["lm_iter"], fast_mode=cfg["fast"], z_min=cfg["z_min"],
+                                   **({"mc_samples": M, "mc_iter": I} if M else {}))
+    launches_per_step = {"lm_amis": 2, "lm": 1, "train": 5}[kind]
+
+    train = None
+    if kind == "train":
+        from epropnp.camera import PerspectiveCamera
+        from epropnp.cost_fun import AdaptiveHuberPnPCost
+        from epropnp.epropnp import EProPnP6DoF
+        from epropnp.levenberg_marquardt import LMSolver
+        from epropnp.monte_carlo_pose_loss import MonteCarloPoseLoss
+        layer = EProPnP6DoF(mc_samples=M, num_iter=I, solver=LMSolver(dof=6, num_iter=cfg["lm_iter"]))
+        loss_fn = MonteCarloPoseLoss().to(dev)
+        for d in sets:
+            d["leaf"] = tuple(d[k].clone().requires_grad_(True) for k in ("x3d", "x2d", "w2d"))
+            d["camera"] = PerspectiveCamera(cam_mats=d["cam_mats"], z_min=cfg["z_min"])
+
+        def train(i):
+            """One training step of the 6DoF flavour (EPro-PnP-6DoF/lib/train.py:170-200): adaptive delta from the
+            weights, Monte-Carlo forward with the ground-truth pose as pose_init, MC pose loss, backward."""
+            d = sets[i % n_sets]
+            x3d, x2d, w2d = d["leaf"]
+            x3d.grad = x2d.grad = w2d.grad = None
+            cost_fun = AdaptiveHuberPnPCost(relative_delta=cfg["rel_delta"])
+            cost_fun.set_param(x2d.detach(), w2d)
+            _, _, _, _, logw, cost_tgt = layer.monte_carlo_forward(x3d, x2d, w2d, d["camera"], cost_fun,
+                                                                   pose_init=d["pose_gt"], force_init_solve=False)
+            loss = loss_fn(logw, cost_tgt, 1.0)
+            loss.backward()
+            return {"loss": loss.detach(), "gx3d": x3d.grad}
 
     def solve(i):
-        s = sets[i % ROTATING_SETS]
+        s = sets[i % n_sets]
+        if kind == "lm":
+            return native.lm_solve(s["prob"], s["pose_init"], params, want_cov=True, want_cost=True)
+        if kind == "train":
+            return train(i)
         return native.lm_amis_fused(s["prob"], s["pose_init"], params, seed=1234 + i, obj_offset=rank * Bg,
                                     want_cost=True, want_cost_init=False)
 
@@ -372,22 +410,22 @@ def main():
                 torch.cuda.current_stream(dev).wait_stream(s)
 
     def step_on_current_stream(i):
-        """One batch: fused solve, then the gather of (pose_opt, logw).  For N > 1 the gather is asynchronous and the
-        previous batch's gather is awaited only after this batch's solve is enqueued, so exchange i overlaps solve
-        i+1 (batches are independent); every gather completes inside the timed region (drain() before t_end)."""
+        """One batch: the solve, then (N > 1) the gather of (pose_opt, logw).  The gather is asynchronous and the previous
+        batch's is awaited only after this batch's solve is enqueued, so exchange i overlaps solve i+1 (batches are
+        independent); every gather completes inside the timed region (drain() before t_end)."""
         nonlocal pending, peer_gather
-        if world > 1 and args.gather == "push":
-            # fused solve + gather: the kernel stores every finished object's rows into all ranks' result buffers
+        if gathering and args.gather == "push":
+            # solve + gather in one: the AMIS kernel stores every finished object's rows into all ranks' result buffers
             if peer_gather is None:
-                peer_gather = PushGather(B_total, MC_SAMPLES, 7, dev)
-            s = sets[i % ROTATING_SETS]
+                peer_gather = PushGather(B_total, M, 7, dev)
+            s = sets[i % n_sets]
             out, nxt = peer_gather.solve(s["prob"], s["pose_init"], params, seed=1234 + i, want_cost=True, want_cov=True)
             if pending is not None:
                 pending.wait()
             pending = nxt
             return out
         out = solve(i)
-        if world > 1:
+        if gathering:
             if pending is not None:
                 pending.wait()
             if args.gather == "peer":
@@ -418,7 +456,7 @@ def main():
         sampler.start()
         sampler.wait_ready()
     # warm-up: at least W steps AND at least ~0.5 s of back-to-back launches -- the first ~100 ms after an idle
-    # period run measurably slower (power-state ramp), which W = 3 steps of 1.5 ms do not cover
+    # period run measurably slower (power-state ramp), which W = 3 steps of 1 ms do not cover
     t_warm = None                # the 0.5 s start counting after the first chunk: it holds the one-off costs (module load,
     n_warm = 0                   # NCCL communicator / IPC set-up -- seconds at N > 1), which are not back-to-back launches
     out = None
@@ -442,116 +480,175 @@ def main():
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         os.close(saved_stdout)
-    # ---- timed region: exactly K steps, one event pair around all of them + one pair per kernel launch
-    n_ev = min(args.steps, 64)      # per-launch event pairs on the first launches (roofline's kernel time)
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_ev)]
+    # ---- timed region: exactly K steps, one event pair around all of them
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
     wall0 = time.time()
     t_begin.record()
     fork_lanes()                   # lanes start after t_begin ...
     for i in range(args.steps):
-        lane = lanes[i % len(lanes)] if lanes is not None else torch.cuda.current_stream(dev)
-        if i < n_ev:
-            k_ev[i][0].record(lane)
         out = step(i)
-        if i < n_ev:
-            k_ev[i][1].record(lane)
     drain()
     join_lanes()                   # ... and t_end waits for every lane: all K batches complete inside the region
     t_end.record()
     fence()
     wall1 = time.time()
     total_ms = t_begin.elapsed_time(t_end)
-    kern_ms = statistics.mean(a.elapsed_time(b) for a, b in k_ev)
-    if lanes is not None:          # launches of different lanes overlap: a launch's own event pair also times its neighbours
-        kern_ms = total_ms / args.steps
-    if os.environ.get("EPNP_BENCH_DEBUG") and rank == 0:
-        print("per-launch ms:", [round(a.elapsed_time(b), 2) for a, b in k_ev][:24], "gaps:",
-              [round(k_ev[j][1].elapsed_time(k_ev[j + 1][0]), 2) for j in range(min(len(k_ev) - 1, 23))], file=sys.stderr)
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    t = torch.tensor([total_ms, kern_ms], device=dev, dtype=torch.float64)
+
+    # ---- the kernels on their own (roofline): CUDA events around each kernel's launch, same rotating inputs
+    def kernel_time(fn, iters):
+        for j in range(3):
+            fn(j)
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for j, (a, b) in enumerate(ev):
+            a.record()
+            fn(j)
+            b.record()
+        torch.cuda.synchronize()
+        return statistics.mean(a.elapsed_time(b) for a, b in ev)
+
+    n_k = max(3, min(args.steps, 50))
+    lm_ms = kernel_time(lambda j: native.lm_solve(sets[j % n_sets]["prob"], sets[j % n_sets]["pose_init"], params,
+                                                  want_cov=True, want_cost=True), n_k)
+    amis_ms = None
+    if M:
+        lm0 = native.lm_solve(sets[0]["prob"], sets[0]["pose_init"], params, want_cov=True)
+        amis_ms = kernel_time(lambda j: native.amis(sets[j % n_sets]["prob"], lm0["pose_opt"], lm0["pose_cov"], params, seed=j), n_k)
+    t = torch.tensor([total_ms, lm_ms, amis_ms or 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms = t.tolist()
+    total_ms, lm_ms, amis_ms = t.tolist()
 
-    # ---- end to end: HOST (pinned) buffers through the C ABI, copies inside the timed region
+    # ---- end to end: HOST (pinned) buffers, copies inside the timed region
     e2e = None
     if not args.no_e2e:
         with gpu_local_cpus(local_rank, E2E_NUMA) as numa:
             host = {k: pc[k].contiguous().pin_memory() for k in ("x3d", "x2d", "w2d", "cam_mats", "pose_init")}
             host["delta"] = sets[0]["delta"].cpu().pin_memory()
-        shift0 = {k: v for k, v in host.items()}
-        wss = [torch.empty(native.fused_workspace_bytes(Bg, N_PTS, params), dtype=torch.uint8, device=dev)
-               for _ in range(E2E_LANES)]
-        ress = [None] * E2E_LANES
-        e_lanes = [torch.cuda.Stream(dev) for _ in range(E2E_LANES)] if E2E_LANES > 1 else [torch.cuda.current_stream(dev)]
-        e_steps = max(3, min(args.steps, 50))
+        e_steps = max(3, min(args.steps, 60))
+        n_lanes = E2E_LANES
+        e_lanes = [torch.cuda.Stream(dev) for _ in range(n_lanes)]
+        ress = [None] * n_lanes
+        if kind == "lm_amis":
+            # the C ABI's host-buffer entry point: chunked copy-in / LM + AMIS / copy-out pipeline on helper streams
+            wss = [torch.empty(native.fused_workspace_bytes(Bg, N_PTS, params), dtype=torch.uint8, device=dev) for _ in range(n_lanes)]
+            path = "epnp_lm_amis_fused_host_f32 (pinned host buffers, chunked copy / solve overlap)"
 
-        def e2e_step(i, seed):
-            k = i % E2E_LANES
-            with torch.cuda.stream(e_lanes[k]):
-                ress[k] = native.lm_amis_fused_host(shift0, params, wss[k], n_chunks=E2E_CHUNKS, seed=seed + i,
-                                                    obj_offset=rank * Bg, out=ress[k])
-            return ress[k]
-        for i in range(2 * E2E_LANES):
+            def e2e_step(i, seed):
+                k = i % n_lanes
+                with torch.cuda.stream(e_lanes[k]):
+                    ress[k] = native.lm_amis_fused_host(host, params, wss[k], n_chunks=E2E_CHUNKS, seed=seed + i,
+                                                        obj_offset=rank * Bg, out=ress[k])
+                return ress[k]
+        else:
+            # the call a user of the drop-in makes with host tensors: upload, solve, download
+            path = ("pinned host tensors -> .to(device) -> " + ("epnp_lm_solve_f32" if kind == "lm" else "training step (drop-in classes)")
+                    + " -> pinned host results")
+            pins = [None] * n_lanes
+
+            def e2e_step(i, seed):
+                k = i % n_lanes
+                with torch.cuda.stream(e_lanes[k]):
+                    dv = {n: t.to(dev, non_blocking=True) for n, t in host.items()}
+                    if kind == "lm":
+                        prob = native.Problem(dv["x3d"], dv["x2d"], dv["w2d"], dv["cam_mats"], None, None, dv["delta"])
+                        r = native.lm_solve(prob, dv["pose_init"], params, want_cov=True, want_cost=True)
+                        r = {n: v for n, v in r.items() if v is not None}
+                    else:
+                        sets[0]["leaf"][0].data.copy_(dv["x3d"]); sets[0]["leaf"][1].data.copy_(dv["x2d"]); sets[0]["leaf"][2].data.copy_(dv["w2d"])
+                        r = train(0)
+                    if pins[k] is None:
+                        pins[k] = {n: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for n, v in r.items()}
+                    for n, v in r.items():
+                        pins[k][n].copy_(v, non_blocking=True)
+                    ress[k] = pins[k]
+                return ress[k]
+        for i in range(2 * n_lanes):
             res = e2e_step(i, 77)
         fence()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e_steps)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        if E2E_LANES > 1:
-            for s in e_lanes:
-                s.wait_stream(torch.cuda.current_stream(dev))
+        for s in e_lanes:
+            s.wait_stream(torch.cuda.current_stream(dev))
         for i in range(e_steps):
+            ev[i][0].record(e_lanes[i % n_lanes])
             res = e2e_step(i, 99)
-        if E2E_LANES > 1:
-            for s in e_lanes:
-                torch.cuda.current_stream(dev).wait_stream(s)
+            ev[i][1].record(e_lanes[i % n_lanes])
+        for s in e_lanes:
+            torch.cuda.current_stream(dev).wait_stream(s)
         e1.record()
         fence()
         te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        # per-step completion intervals (end of step i-1 -> end of step i on the host clock of the events): their spread
+        # is the run-to-run stability of the pipeline
+        ends = [e0.elapsed_time(b) for _, b in ev]
+        gaps = sorted(b - a for a, b in zip([0.0] + ends[:-1], ends))[1:] if len(ends) > 2 else [te.item() / e_steps]
         h2d = sum(host[k].numel() * 4 for k in host)
-        d2h = sum(v.numel() * 4 for v in res.values() if v is not None)
+        d2h = sum(v.numel() * v.element_size() for v in res.values() if v is not None)
         e2e = {"value": B_total * e_steps / (te.item() * 1e-3), "unit": "objects/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": e_steps, "chunks": E2E_CHUNKS, "calls_in_flight": E2E_LANES, "host_buffers_on_gpu_numa_node": numa.applied,
-               "path": "epnp_lm_amis_fused_host_f32 (pinned host buffers, chunked copy/solve overlap)"}
+               "d2h_bytes_per_step": d2h, "steps": e_steps, "chunks": E2E_CHUNKS if kind == "lm_amis" else None,
+               "calls_in_flight": n_lanes, "host_buffers_on_gpu_numa_node": numa.applied,
+               "ms_per_step": te.item() / e_steps,
+               "step_interval_ms": {"min": gaps[0], "median": statistics.median(gaps), "max": gaps[-1]},
+               "path": path}
 
     if rank == 0:
         peak, peak_src, sm_max = load_peaks()
         value = B_total * args.steps / (total_ms * 1e-3)
-        per_launch_bytes = algorithmic_bytes_per_object() * Bg
-        achieved = per_launch_bytes / (kern_ms * 1e-3) / 1e9
+        dom = "amis_kernel" if M else "lm_warp_kernel"
+        dom_ms = amis_ms if M else lm_ms
+        per_launch_bytes = algorithmic_bytes_per_object(cfg, dom) * Bg
+        achieved = per_launch_bytes / (dom_ms * 1e-3) / 1e9
         clk = (clocks or {}).get("sm_mhz") or sm_max
-        issue_peak = 148 * 4 * clk * 1e6                      # one warp-instruction per SM sub-partition per cycle
-        issue_rate = WARP_INSTR_PER_OBJECT * Bg / (kern_ms * 1e-3)
+        stats, stats_src = kernel_stats(dom, args.config)
+        issue = None
+        if stats is not None:
+            scale = Bg / float(stats["objects_per_launch"])
+            issue_peak = 148 * 4 * clk * 1e6                      # one warp-instruction per SM sub-partition per cycle
+            issue_rate = stats["warp_instr_per_launch"] * scale / (dom_ms * 1e-3)
+            issue = {"bound": "warp-instruction issue / FP32 pipe (the binding resource, DESIGN.md section 4)",
+                     "kernel": dom, "warp_instr_per_object": stats["warp_instr_per_launch"] / stats["objects_per_launch"],
+                     "achieved_warp_instr_per_s": issue_rate, "peak_warp_instr_per_s": issue_peak, "frac": issue_rate / issue_peak,
+                     "sm_mhz_used": clk, "ncu": {k: stats.get(k) for k in ("issue_active_pct", "fma_pipe_pct", "xu_pipe_pct", "duration_ms")}}
+        gather = ""
+        if world > 1:
+            gather = (f", gather(pose,logw) only ({args.gather}"
+                      + (f", NCCL_MAX_CTAS={args.nccl_max_ctas}" if args.nccl_max_ctas else "") + ")"
+                      + ("" if args.gather == "push" else ", gather of batch i overlapped with solve of batch i+1"))
         line = {
-            "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "warmup_steps_run": n_warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"fused EProPnP6DoF.monte_carlo_forward: LM({LM_ITER}) + cov + AMIS({MC_ITER}x"
-                                   f"{MC_SAMPLES // MC_ITER}), B={Bg}/GPU, N={N_PTS}, M={MC_SAMPLES}, in-kernel Philox",
-                       "global_batch": B_total, "parallelism": f"batch-split x{world}, gather(pose,logw) only ({args.gather}{", NCCL_MAX_CTAS=" + str(args.nccl_max_ctas) if args.nccl_max_ctas else ""}), gather of batch i overlapped with solve of batch i+1",
+            "metric": cfg["metric"], "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "warmup_steps_run": n_warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{cfg['what']}, B={Bg}/GPU, N={N_PTS}, M={M}" + (", in-kernel Philox" if M else ""),
+                       "name": args.config, "global_batch": B_total, "parallelism": f"batch-split x{world}{gather}",
                        "batches_in_flight": args.streams,
-                       "l2": f"rotating {ROTATING_SETS} input sets ({ROTATING_SETS * 28 * N_PTS * Bg / 1e6:.0f} MB > 126 MB L2)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(), "peak_source": peak_src,
-                         "bytes_per_object": algorithmic_bytes_per_object(), "kernel_ms": kern_ms,
+                       "l2": f"rotating {n_sets} input sets ({n_sets * set_bytes / 1e6:.0f} MB > 126 MB L2)"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (stats["dram_bytes_per_launch"] * Bg / float(stats["objects_per_launch"])) if stats else None,
+                         "traffic_source": stats_src, "peak_source": peak_src,
+                         "bytes_per_object": algorithmic_bytes_per_object(cfg, dom), "kernel_ms": dom_ms,
                          "note": "issue / FP32-pipe bound, not HBM bound: see the issue block"},
-            "issue": {"bound": "warp-instruction issue / FP32 pipe (the binding resource, see DESIGN.md section 4)",
-                      "warp_instr_per_object": WARP_INSTR_PER_OBJECT, "achieved_warp_instr_per_s": issue_rate,
-                      "peak_warp_instr_per_s": issue_peak, "frac": issue_rate / issue_peak, "sm_mhz_used": clk,
-                      "source": "instruction count from the committed ncu capture, time from this run"},
-            "clocks": clocks, "gpu_launches": args.steps * world,
-            "kernel": ("solve_push_kernel<6>" if (world > 1 and args.gather == "push") else "solve_kernel<6,true,true>")
-                      + " (libepropnp_b200.so)",
+            "kernels_ms": {"lm_warp_kernel": lm_ms, "amis_kernel": amis_ms if M else None,
+                           "note": "each kernel launched alone, CUDA events on its stream, mean over the rotating input sets"},
+            "clocks": clocks, "gpu_launches": args.steps * world * launches_per_step,
+            "kernel": ("lm_warp_kernel<6,staged> + amis_kernel<6," + ("push" if (gathering and args.gather == "push") else "local") + ">"
+                       if kind != "lm" else "lm_warp_kernel<6,staged>") + " (libepropnp_b200.so)",
         }
+        if issue is not None:
+            line["issue"] = issue
         if e2e is not None:
             line["e2e"] = e2e
-        if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample = cpu_oracle_rate(12.0)
-            line["cpu_baseline"] = {"value": v, "unit": "objects/s", "cores": cores, "kind": "port", "sample": sample}
+        if world == 1 and not args.no_cpu_baseline and kind != "train":
+            try:
+                rates, cores, ckind, sample = cpu_reference_rates(cfg, 1, 0, 12.0)
+                line["cpu_baseline"] = {"value": rates[0], "unit": "objects/s", "cores": cores, "kind": ckind, "sample": sample}
+            except Exception as ex:                            # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "error": repr(ex)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -944,14 +944,37 @@ PNP_HD_COLD void initial_fit6(const float* pose, const float* cov /*6x6 full*/, 
 typedef float Refit;
 typedef double RefitInv;
 
-// Lambda^-1 (fp32 out) of the ACG scatter matrix given as packed fp32 upper triangle
+// Lambda^-1 (fp32 out) of the ACG scatter matrix given as packed fp32 upper triangle (a00 a01 a02 a03 a11 a12 a13 a22
+// a23 a33).  The reference calls rot_cov.inverse() (epropnp.py:336).  Closed form through the twelve 2x2 minors of the
+// row pairs (0,1) and (2,3), in fp64: ~80 multiply-adds of depth 4 and ONE reciprocal, instead of the ~300-instruction
+// dependent chain of a Cholesky factorisation + triangular inverse + product (every thread of the CTA evaluates this
+// twice per refit, on the critical path between two AMIS iterations).  Lambda = sum w q q^T + eps I is positive
+// definite; the minors' cancellation costs cond(Lambda) * 1e-16 of relative accuracy, far below the fp32 output.
 PNP_HD void acg_scatter_inverse(const float* lam10, float* inv16) {
-    RefitInv a[10], inv[16];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) a[i] = (RefitInv)lam10[i];
-    spd_inverse<4, RefitInv>(a, inv);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) inv16[i] = (float)inv[i];
+    typedef RefitInv T;
+    const T a00 = lam10[0], a01 = lam10[1], a02 = lam10[2], a03 = lam10[3], a11 = lam10[4], a12 = lam10[5], a13 = lam10[6],
+            a22 = lam10[7], a23 = lam10[8], a33 = lam10[9];
+    // minors of rows 0, 1 (columns i < j) and of rows 2, 3; symmetric input: a10 = a01, a20 = a02, ...
+    const T s0 = a00 * a11 - a01 * a01, s1 = a00 * a12 - a01 * a02, s2 = a00 * a13 - a01 * a03;
+    const T s3 = a01 * a12 - a11 * a02, s4 = a01 * a13 - a11 * a03, s5 = a02 * a13 - a12 * a03;
+    const T c5 = a22 * a33 - a23 * a23, c4 = a12 * a33 - a13 * a23, c3 = a12 * a23 - a13 * a22;
+    const T c2 = a02 * a33 - a03 * a23, c1 = a02 * a23 - a03 * a22, c0 = a02 * a13 - a03 * a12;
+    const T det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+    const T id = fast_recip(det);
+    const T i00 = (a11 * c5 - a12 * c4 + a13 * c3) * id;
+    const T i01 = (-a01 * c5 + a02 * c4 - a03 * c3) * id;
+    const T i02 = (a13 * s5 - a23 * s4 + a33 * s3) * id;
+    const T i03 = (-a12 * s5 + a22 * s4 - a23 * s3) * id;
+    const T i11 = (a00 * c5 - a02 * c2 + a03 * c1) * id;
+    const T i12 = (-a03 * s5 + a23 * s2 - a33 * s1) * id;
+    const T i13 = (a02 * s5 - a22 * s2 + a23 * s1) * id;
+    const T i22 = (a03 * s4 - a13 * s2 + a33 * s0) * id;
+    const T i23 = (-a02 * s4 + a12 * s2 - a23 * s0) * id;
+    const T i33 = (a02 * s3 - a12 * s1 + a22 * s0) * id;
+    inv16[0] = (float)i00; inv16[1] = (float)i01; inv16[2] = (float)i02; inv16[3] = (float)i03;
+    inv16[4] = (float)i01; inv16[5] = (float)i11; inv16[6] = (float)i12; inv16[7] = (float)i13;
+    inv16[8] = (float)i02; inv16[9] = (float)i12; inv16[10] = (float)i22; inv16[11] = (float)i23;
+    inv16[12] = (float)i03; inv16[13] = (float)i13; inv16[14] = (float)i23; inv16[15] = (float)i33;
 }
 
 // Next proposal from the refit statistics (EProPnP6DoF.estimate_params tail, epropnp.py:325, 341-342)

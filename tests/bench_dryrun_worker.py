@@ -15,7 +15,7 @@ import torch.distributed as dist  # noqa: E402
 
 import simt_native  # noqa: E402
 from epropnp_b200 import capi, native, sharded  # noqa: E402
-from test_bench_dryrun_cpu import _Event, _Stream  # noqa: E402
+from test_bench_dryrun_cpu import _Event, _Stream, toy_configs  # noqa: E402
 from test_push_gather_cpu import _host_class  # noqa: E402
 
 
@@ -39,8 +39,8 @@ def main():
     sharded.PushGather = _host_class(sharded.PushGather)
     os.environ.update(EPNP_BENCH_DEVICE="cpu", EPNP_NO_SAMPLER="1", LOCAL_RANK="0")
     import bench
-    for k, v in dict(N_PTS=16, MC_SAMPLES=8, MC_ITER=2, LM_ITER=2, ROTATING_SETS=2, WARM_SECONDS=0.05).items():
-        setattr(bench, k, v)
+    toy_configs(bench, lambda d, k, v: d.__setitem__(k, v))
+    bench.WARM_SECONDS, bench.L2_BYTES = 0.05, 1.0
     sys.argv = ["bench.py", "--batch", "2", "--steps", "5", "--warmup", "3", "--no-cpu-baseline", "--no-e2e"] + sys.argv[1:]
     bench.main()
     if dist.is_initialized():

@@ -32,6 +32,15 @@ class _Event:
         return 1.0
 
 
+def toy_configs(bench, setitem):
+    """every bench config at a size the emulator affords"""
+    for name, cfg in list(bench.CONFIGS.items()):
+        toy = dict(cfg, N=16, lm_iter=2)
+        if cfg["M"]:
+            toy.update(M=8, I=2)
+        setitem(bench.CONFIGS, name, toy)
+
+
 def run_bench(monkeypatch, capsys, argv, **module_overrides):
     import bench
     simt_native.install(monkeypatch)
@@ -44,7 +53,8 @@ def run_bench(monkeypatch, capsys, argv, **module_overrides):
     monkeypatch.setattr(torch, "empty", (lambda f: (lambda *a, pin_memory=False, **k: f(*a, **k)))(torch.empty))
     monkeypatch.setenv("EPNP_BENCH_DEVICE", "cpu")
     monkeypatch.setenv("EPNP_NO_SAMPLER", "1")
-    for k, v in dict(N_PTS=16, MC_SAMPLES=8, MC_ITER=2, LM_ITER=2, ROTATING_SETS=2, WARM_SECONDS=0.05, **module_overrides).items():
+    toy_configs(bench, monkeypatch.setitem)
+    for k, v in dict(WARM_SECONDS=0.05, L2_BYTES=1.0, **module_overrides).items():
         monkeypatch.setattr(bench, k, v)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--batch", "2", "--steps", "3", "--warmup", "3", "--no-cpu-baseline"] + argv)
     bench.main()
@@ -57,21 +67,25 @@ CONTRACT = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
             "vs_baseline", "dtype", "data", "config", "roofline", "clocks", "gpu_launches", "e2e")
 
 
-@pytest.mark.parametrize("argv,overrides", [([], {}), (["--streams", "2"], {}), ([], {"E2E_LANES": 2, "E2E_CHUNKS": 0}),
-                                            (["--no-e2e"], {})])
+@pytest.mark.parametrize("argv,overrides", [([], {}), (["--streams", "2"], {}), ([], {"E2E_LANES": 1, "E2E_CHUNKS": 0}),
+                                            (["--no-e2e"], {}), (["--config", "lm_only"], {}), (["--config", "dense"], {}),
+                                            (["--config", "train"], {})])
 def test_bench_loop_runs_and_prints_the_contract_line(monkeypatch, capsys, argv, overrides):
     line = run_bench(monkeypatch, capsys, argv, **overrides)
     for k in CONTRACT:
         if k == "e2e" and "--no-e2e" in argv:
             continue
         assert k in line, k
-    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["gpu_launches"] == 3 and line["value"] > 0
+    per_step = {"lm_only": 1, "train": 5}.get(argv[1] if "--config" in argv else "", 2)
+    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["gpu_launches"] == 3 * per_step and line["value"] > 0
+    assert line["config"]["name"] == (argv[1] if "--config" in argv else "fused")
     assert line["config"]["batches_in_flight"] == (2 if "--streams" in argv else 1)
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     if "--no-e2e" not in argv:
         e = line["e2e"]
         assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] > 0
-        assert e["calls_in_flight"] == overrides.get("E2E_LANES", 1)
+        assert e["calls_in_flight"] == overrides.get("E2E_LANES", 2)
+        assert set(e["step_interval_ms"]) == {"min", "median", "max"}
 
 
 @pytest.mark.parametrize("flags", [["--gather", "nccl"], ["--gather", "nccl-coalesced"], ["--gather", "peer"],
@@ -99,7 +113,7 @@ def test_two_rank_bench_loop_over_gloo(flags):
     lines = [l for l in outs[0][0].splitlines() if l.startswith("{")]
     assert len(lines) == 1 and not [l for l in outs[1][0].splitlines() if l.startswith("{")]
     line = json.loads(lines[0])
-    assert line["n_gpus"] == 2 and line["config"]["global_batch"] == 4 and line["gpu_launches"] == 10
+    assert line["n_gpus"] == 2 and line["config"]["global_batch"] == 4 and line["gpu_launches"] == 20
     assert flags[1] in line["config"]["parallelism"]
 
 

@@ -2,11 +2,14 @@
 """Turn an `ncu --set full` report into the small JSON summaries kept under profiles/ (runs in the build container:
 ncu reads reports without a GPU).
 
-    python tools/ncu_summary.py gpurun_out/fused_full.ncu-rep --tag r2 [--kernel solve_kernel] [--write-traffic]
+    python tools/ncu_summary.py gpurun_out/r2_amis_full.ncu-rep --tag r2 --kernel amis_kernel --stats-key amis_kernel@fused --objects 4096
 
-writes profiles/<tag>_fused_ncu_raw_metrics.json = {metric: [value, unit]} for the metrics the design discussion uses
-(duration, DRAM bytes, instruction count, issue / pipe utilisation, occupancy limits, bank conflicts) and, with
---write-traffic, refreshes profiles/traffic.json (read by bench.py for `roofline.traffic`).  `ncu -i REP --page raw
+writes profiles/<tag>_<kernel>_ncu_raw_metrics.json = {metric: [value, unit]} for the metrics the design discussion uses
+(duration, DRAM bytes, instruction count, issue / pipe utilisation, occupancy limits, bank conflicts, stall reasons) and,
+with --stats-key, the kernel's record in profiles/kernel_stats.json (read by bench.py for `roofline.traffic` and the
+`issue` block): per-launch warp-instructions and DRAM bytes TOGETHER WITH the SASS fingerprint of that kernel in the
+in-tree library -- run it right after the capture, before the library is rebuilt; bench.py refuses the record once the
+kernel's SASS has changed.  `ncu -i REP --page raw
 --csv` prints either one row per kernel with one column per metric (plus a units row) or one row per (kernel, metric);
 both layouts are understood.
 """
@@ -31,7 +34,7 @@ KEEP = [
     "gpc__cycles_elapsed.avg.per_second", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "smsp__thread_inst_executed_per_inst_executed.ratio", "lts__t_sector_hit_rate.pct",
 ]
-STALLS = "smsp__average_warp_latency_issue_stalled_"      # ..._<reason>.ratio (warp-state section of --set full)
+STALLS = "smsp__average_warps_issue_stalled_"            # ..._<reason>_per_issue_active.ratio (warp-state section of --set full)
 UNIT_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
@@ -80,7 +83,9 @@ def main():
     ap.add_argument("report")
     ap.add_argument("--tag", required=True, help="file prefix under profiles/, e.g. r2")
     ap.add_argument("--kernel", default="solve_kernel", help="substring of the kernel name to summarise (first match)")
-    ap.add_argument("--write-traffic", action="store_true")
+    ap.add_argument("--stats-key", default=None, help="record name in profiles/kernel_stats.json, '<kernel>@<bench config>'")
+    ap.add_argument("--objects", type=int, default=4096, help="objects the profiled launch processed")
+    ap.add_argument("--sass-symbol", default=None, help="substring of the mangled kernel name (default: derived from --kernel: 6DoF, non-push)")
     a = ap.parse_args()
     kernels = per_kernel(raw_rows(a.report))
     hit = [(n, m) for n, m in kernels if a.kernel in n]
@@ -90,16 +95,32 @@ def main():
     keep = {k: metrics[k] for k in KEEP if k in metrics}
     keep.update({k: v for k, v in metrics.items() if k.startswith(STALLS)})
     missing = [k for k in KEEP if k not in metrics]
-    out = os.path.join(ROOT, "profiles", f"{a.tag}_fused_ncu_raw_metrics.json")
+    out = os.path.join(ROOT, "profiles", f"{a.tag}_{a.kernel}_ncu_raw_metrics.json")
     with open(out, "w") as f:
         json.dump(dict(kernel=name, **keep), f, indent=1)
     print("wrote", out, f"({len(keep)} metrics; not in the report: {missing})")
-    if a.write_traffic:
-        traffic = to_bytes(metrics["dram__bytes_read.sum"]) + to_bytes(metrics["dram__bytes_write.sum"])
-        with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
-            json.dump({"fused_dram_bytes_per_launch": traffic,
-                       "source": f"profiles/{a.tag}_fused_ncu_raw_metrics.json (ncu --set full, one launch of {name[:60]})"}, f)
-        print("traffic.json:", traffic, "bytes per launch")
+    if a.stats_key:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sass_identity
+        symbol = a.sass_symbol or {"amis_kernel": "amis_kernelILi6ELb0EE", "lm_warp_kernel": "lm_warp_kernelILi6ELb1EE"}.get(a.kernel, a.kernel)
+        fp = {k: v for k, v in sass_identity.fingerprints(sass_identity.DEFAULT_LIB).items() if symbol in k}
+        if len(fp) != 1:
+            sys.exit(f"--sass-symbol {symbol!r} matches {sorted(fp)}")
+        num = lambda k: float(metrics[k][0].replace(",", ""))
+        dur = num("gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "nsecond": 1e-6, "s": 1e3, "second": 1e3}.get(metrics["gpu__time_duration.sum"][1], 1.0)
+        rec = dict(kernel=name, sass_symbol=symbol, sass_sha1=list(fp.values())[0]["sha1"], objects_per_launch=a.objects,
+                   warp_instr_per_launch=num("smsp__inst_executed.sum"),
+                   dram_bytes_per_launch=to_bytes(metrics["dram__bytes_read.sum"]) + to_bytes(metrics["dram__bytes_write.sum"]),
+                   duration_ms=dur, issue_active_pct=num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                   fma_pipe_pct=num("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                   xu_pipe_pct=num("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                   source=f"profiles/{a.tag}_{a.kernel}_ncu_raw_metrics.json (ncu --set full --clock-control none, one launch)")
+        path = os.path.join(ROOT, "profiles", "kernel_stats.json")
+        allrec = json.load(open(path)) if os.path.exists(path) else {}
+        allrec[a.stats_key] = rec
+        with open(path, "w") as f:
+            json.dump(allrec, f, indent=1, sort_keys=True)
+        print("kernel_stats.json:", a.stats_key, {k: rec[k] for k in ("warp_instr_per_launch", "dram_bytes_per_launch", "duration_ms")})
 
 
 if __name__ == "__main__":

@@ -23,7 +23,7 @@ def fingerprints(lib):
     txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
     out = {}
     for part in re.split(r"\n\s*Function : ", txt)[1:]:
-        name = re.sub(r"_GLOBAL__N__[0-9a-f]+_\d+_pnp_kernels_cu_[0-9a-f]+", "", part.split("\n")[0].strip())
+        name = re.sub(r"_GLOBAL__N__[0-9a-f]+_\d+_pnp_kernels_cu_[0-9a-f]{8}", "", part.split("\n")[0].strip())
         body = [re.sub(r"/\*[0-9a-fx ]+\*/", "", l).strip() for l in part.split("\n")[1:]
                 if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l)]
         out[name] = dict(instructions=len(body), sha1=hashlib.sha1("\n".join(body).encode()).hexdigest())
@@ -40,8 +40,8 @@ def compare(lib=DEFAULT_LIB):
 
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--write":
-        json.dump(dict(note="SASS fingerprints of the kernels validated on a B200 in round 1 (parity suite, "
-                            "compute-sanitizer, ncu; see profiles/README.md)", kernels=fingerprints(sys.argv[2])),
+        json.dump(dict(note="SASS fingerprints of the kernels validated on a B200 (GPU parity suite green on exactly this "
+                            "build; see profiles/README.md)", kernels=fingerprints(sys.argv[2])),
                   open(MANIFEST, "w"), indent=1, sort_keys=True)
         print("wrote", MANIFEST)
     else:
