@@ -391,6 +391,14 @@ def main():
     pending = None
     peer_gather = None
     lanes = [torch.cuda.Stream(dev) for _ in range(args.streams)] if args.streams > 1 else None
+    k_ev = {}                       # step -> (event before, event after) around the solve's launches, timed region only
+    timing = [False]
+
+    def mark(i, which):
+        if timing[0] and lanes is None and i < 64:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            k_ev.setdefault(i, [None, None])[which] = e
 
     def step(i):
         """One batch on its lane (stream i mod S) -- or on the current stream when S = 1."""
@@ -419,12 +427,16 @@ def main():
             if peer_gather is None:
                 peer_gather = PushGather(B_total, M, 7, dev)
             s = sets[i % n_sets]
+            mark(i, 0)
             out, nxt = peer_gather.solve(s["prob"], s["pose_init"], params, seed=1234 + i, want_cost=True, want_cov=True)
+            mark(i, 1)
             if pending is not None:
                 pending.wait()
             pending = nxt
             return out
+        mark(i, 0)
         out = solve(i)
+        mark(i, 1)
         if gathering:
             if pending is not None:
                 pending.wait()
@@ -484,6 +496,7 @@ def main():
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
     wall0 = time.time()
+    timing[0] = True
     t_begin.record()
     fork_lanes()                   # lanes start after t_begin ...
     for i in range(args.steps):
@@ -493,8 +506,16 @@ def main():
     t_end.record()
     fence()
     wall1 = time.time()
+    timing[0] = False
     total_ms = t_begin.elapsed_time(t_end)
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    # the solve's launches inside the loop (first 64 steps): their own duration, and the gap to the next step's launches
+    in_loop = None
+    if k_ev:
+        ks = sorted(k for k, v in k_ev.items() if v[0] is not None and v[1] is not None)
+        dur = [k_ev[k][0].elapsed_time(k_ev[k][1]) for k in ks]
+        gap = [k_ev[a][1].elapsed_time(k_ev[b][0]) for a, b in zip(ks[:-1], ks[1:]) if b == a + 1]
+        in_loop = {"solve_ms": statistics.mean(dur), "gap_ms": statistics.mean(gap) if gap else 0.0, "steps": len(ks)}
 
     # ---- the kernels on their own (roofline): CUDA events around each kernel's launch, same rotating inputs
     def kernel_time(fn, iters):
@@ -635,6 +656,7 @@ def main():
                          "note": "issue / FP32-pipe bound, not HBM bound: see the issue block"},
             "kernels_ms": {"lm_warp_kernel": lm_ms, "amis_kernel": amis_ms if M else None,
                            "note": "each kernel launched alone, CUDA events on its stream, mean over the rotating input sets"},
+            "in_loop": in_loop,
             "clocks": clocks, "gpu_launches": args.steps * world * launches_per_step,
             "kernel": ("lm_warp_kernel<6,staged> + amis_kernel<6," + ("push" if (gathering and args.gather == "push") else "local") + ">"
                        if kind != "lm" else "lm_warp_kernel<6,staged>") + " (libepropnp_b200.so)",

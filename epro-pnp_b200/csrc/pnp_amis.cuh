@@ -9,6 +9,10 @@
 //     lives inside the (not yet written) sample buffer, so a CTA needs 36.1 KB at N = M = 512 and SIX CTAs share an SM;
 //   * the proposal refit is four block reductions (transposed butterflies) + a short chain on one lane.
 // The LM solution (pose, covariance) comes from global memory: lm_warp_kernel wrote it just before (same stream).
+//
+// Long point sets (N >= 2048, the dense 64 x 64 coordinate maps) leave room for one CTA per SM only; there the CTA has
+// T = 512 threads: the cost sweep of a sample is cut into T / 128 = 4 point ranges swept by four threads (their partial
+// costs meet in shared memory, summed in range order), every other pass simply strides over the samples with 512 threads.
 #pragma once
 #include "pnp_device.cuh"
 
@@ -22,24 +26,27 @@ template <int DOF> struct ProposalOf;
 template <> struct ProposalOf<6> { typedef Proposal6 type; };
 template <> struct ProposalOf<4> { typedef Proposal4 type; };
 
-template <int DOF> struct AmisHead {
+constexpr int AMIS_T_DENSE = 512;          // threads per CTA for long point sets
+constexpr int AMIS_DENSE_MIN_N = 2048;     // a function of N only: an object's result must not depend on its batch
+
+template <int DOF, int T> struct AmisHead {
     uint64_t bar[2];
-    float red[2 * NW * 32];                 // two halves: consecutive reductions alternate, one barrier each
+    float red[2 * (T / 32) * 32];           // two halves: consecutive reductions alternate, one barrier each
     float pose[8];                          // the LM solution ...
     float cov[DOF * DOF];                   // ... and its covariance
     typename ProposalOf<DOF>::type prop[MAX_ITER];
 };
 
 struct AmisPlan {        // offsets in floats from the start of dynamic smem
-    int stage, pts, smp, cost, logp, total_bytes;
+    int stage, pts, smp, cost, logp, cpart, total_bytes;
 };
 
 // The staging ring is dead once the object is packed and the sample buffer is not written before the AMIS loop, so the
 // ring lives inside it whenever it fits.
-template <int DOF>
+template <int DOF, int T>
 __host__ __device__ inline AmisPlan plan_amis(int N, int M) {
     AmisPlan s;
-    int off = (int)((sizeof(AmisHead<DOF>) + 127) / 128 * 128 / 4);
+    int off = (int)((sizeof(AmisHead<DOF, T>) + 127) / 128 * 128 / 4);
     const bool alias = Dim<DOF>::POSE * M >= 2 * STAGE_FLOATS;
     s.stage = off; if (!alias) off += 2 * STAGE_FLOATS;
     s.pts = off; off += 16 * ((N + 1) / 2);        // 64 B per pair of points
@@ -47,6 +54,7 @@ __host__ __device__ inline AmisPlan plan_amis(int N, int M) {
     if (alias) s.stage = s.smp;
     s.cost = off; off += M;
     s.logp = off; off += M;                         // running log-sum-exp of the proposal densities, one per sample
+    s.cpart = off; if (T > NT) off += (T / NT) * M; // partial costs of the point ranges (T / 128 sweeping threads per sample)
     s.total_bytes = off * 4;
     return s;
 }
@@ -68,13 +76,15 @@ __device__ __forceinline__ float log_add_exp(float a, float b) {
 
 // ------------------------------------------------------------------------------------------------
 // AMIS loop for the resident object, 6DoF.  sh.pose / sh.cov hold the LM solution.
-__device__ void amis_phase6(const KArgs& a, AmisHead<6>& sh, const float* pts4, float* smp, float* cst, float* logp,
-                            const Cam& cam, float delta, int obj) {
+template <int T>
+__device__ void amis_phase6(const KArgs& a, AmisHead<6, T>& sh, const float* pts4, float* smp, float* cst, float* logp,
+                            float* cpart, const Cam& cam, float delta, int obj) {
+    constexpr int PARTS = T / NT;           // threads sweeping one sample (1: the thread that drew it)
     const Params& p = a.p;
     const int tid = threadIdx.x;
     const int M = p.mc_samples, I = p.mc_iter, S = M / I;
     const bool injected = a.noise_n3 != nullptr;
-    const int st = serial_thread(a);
+    const int st = serial_thread<T>(a);
     float* const logw_out = a.logw + (size_t)obj * M;
     PH_DECL;
 
@@ -83,8 +93,10 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6>& sh, const float* pts4, 
     __syncthreads();
 
     for (int i = 0; i < I; ++i) {
-        // ---- draw, cost, densities of the new samples (one sample per thread and pass)
+        // ---- draw, cost, densities of the new samples (one sample per thread and pass; T > 128: the first 128 threads
+        // draw, then T / 128 threads sweep one point range each of every sample)
         for (int s = tid; s < S; s += NT) {
+            if (PARTS > 1 && tid >= NT) break;
             const int m = i * S + s;
             float n3[3], n4[4], chi2;
             if (injected) {
@@ -103,15 +115,35 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6>& sh, const float* pts4, 
             float* out = a.pose_samples + ((size_t)obj * M + m) * 7;
 #pragma unroll
             for (int k = 0; k < 7; ++k) out[k] = q[k];
-            cst[m] = pose_cost<6>(pts4, a.N, q, cam, delta);
+            if constexpr (PARTS == 1) cst[m] = pose_cost<6>(pts4, a.N, q, cam, delta);
             RunningLse l;
             l.start(proposal_logpdf6(sh.prop[0], q));
             for (int j = 1; j <= i; ++j) l.add(proposal_logpdf6(sh.prop[j], q));
             logp[m] = l.value();
         }
+        if constexpr (PARTS > 1) {
+            __syncthreads();
+            const int part = tid / NT, npair = (a.N + 1) >> 1;
+            const int j0 = (int)((long long)npair * part / PARTS) & ~3, j1 = part + 1 == PARTS ? npair : ((int)((long long)npair * (part + 1) / PARTS) & ~3);
+            for (int s = tid % NT; s < S; s += NT) {
+                const int m = i * S + s;
+                float q[7];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) q[k] = smp[m * 7 + k];
+                cpart[part * M + m] = pose_cost_pairs<6>(pts4, j0, j1, q, cam, delta);
+            }
+            __syncthreads();
+            for (int s = tid; s < S; s += T) {
+                const int m = i * S + s;
+                float c = cpart[m];
+#pragma unroll
+                for (int r = 1; r < PARTS; ++r) c += cpart[r * M + m];
+                cst[m] = c;
+            }
+        }
         PH_MARK(a, PH_DRAW_SWEEP);
         // ---- the new proposal on all earlier samples
-        for (int m = tid; m < i * S; m += NT) {
+        for (int m = tid; m < i * S; m += T) {
             float q[7];
 #pragma unroll
             for (int k = 0; k < 7; ++k) q[k] = smp[m * 7 + k];
@@ -124,12 +156,12 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6>& sh, const float* pts4, 
         const float log_cnt = logf((float)(i + 1));
         auto logweight = [&](int m) { return -cst[m] - (logp[m] - log_cnt); };
         if (i == I - 1) {
-            for (int m = tid; m < M; m += NT) logw_out[m] = logweight(m);
+            for (int m = tid; m < M; m += T) logw_out[m] = logweight(m);
             PH_MARK(a, PH_OUTPUT);
             break;
         }
         float mx = -CUDART_INF_F;
-        for (int m = tid; m < n; m += NT) mx = fmaxf(mx, logweight(m));
+        for (int m = tid; m < n; m += T) mx = fmaxf(mx, logweight(m));
         PH_MARK(a, PH_WEIGHTS);
         // ---- refit proposal i+1 to the weighted samples (estimate_params, epropnp.py:317-342).
         // Four block reductions, one barrier each:
@@ -138,14 +170,14 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6>& sh, const float* pts4, 
         //      M = q.q) -- the normalisation of the weights cancels in Lambda
         //   C  translation covariance about the mean (+ ACG iteration 2)
         //   D+ remaining ACG iterations
-        mx = block_max(mx, sh.red, 0);
+        mx = block_max<T>(mx, sh.red, 0);
         float lam10[10];
         float mean[3], inv_sum;
         {
             float acc[15];
 #pragma unroll
             for (int r = 0; r < 15; ++r) acc[r] = 0.f;
-            for (int m = tid; m < n; m += NT) {
+            for (int m = tid; m < n; m += T) {
                 const float e = expf(logweight(m) - mx);
                 const float* s7 = smp + m * 7;
                 acc[0] += e;
@@ -160,7 +192,7 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6>& sh, const float* pts4, 
 #pragma unroll
                     for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
             }
-            block_sum<15>(acc, sh.red, 1);
+            block_sum<15, T>(acc, sh.red, 1);
             inv_sum = 1.0f / acc[0];
             mean[0] = acc[1] * inv_sum; mean[1] = acc[2] * inv_sum; mean[2] = acc[3] * inv_sum;
             const float inv0 = 1.0f / acc[4];
@@ -181,7 +213,7 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6>& sh, const float* pts4, 
             float acc[17];
 #pragma unroll
             for (int r = 0; r < 17; ++r) acc[r] = 0.f;
-            for (int m = tid; m < n; m += NT) {
+            for (int m = tid; m < n; m += T) {
                 const float w = expf(logweight(m) - mx) * inv_sum;       // normalised softmax weight
                 const float* s7 = smp + m * 7;
                 const float d0 = s7[0] - mean[0], d1 = s7[1] - mean[1], d2 = s7[2] - mean[2];
@@ -198,7 +230,7 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6>& sh, const float* pts4, 
                         for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
                 }
             }
-            block_sum<17>(acc, sh.red, 0);
+            block_sum<17, T>(acc, sh.red, 0);
 #pragma unroll
             for (int r = 0; r < 6; ++r) tc[r] = acc[11 + r];
             if (more) {
@@ -214,7 +246,7 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6>& sh, const float* pts4, 
             float acc[11];
 #pragma unroll
             for (int r = 0; r < 11; ++r) acc[r] = 0.f;
-            for (int m = tid; m < n; m += NT) {
+            for (int m = tid; m < n; m += T) {
                 const float* q = smp + m * 7 + 3;
                 const float wm = expf(logweight(m) - mx) * inv_sum / fmaxf(quad4(lam_inv, q), p.amis_eps);
                 acc[0] += wm;
@@ -224,7 +256,7 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6>& sh, const float* pts4, 
 #pragma unroll
                     for (int c = r; c < 4; ++c) { acc[idx] = fmaf(wm * q[r], q[c], acc[idx]); ++idx; }
             }
-            block_sum<11>(acc, sh.red, (itr + 1) & 1);
+            block_sum<11, T>(acc, sh.red, (itr + 1) & 1);
             const float inv0 = 1.0f / acc[0];
 #pragma unroll
             for (int r = 0; r < 10; ++r) lam10[r] = acc[1 + r] * inv0;
@@ -251,13 +283,15 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6>& sh, const float* pts4, 
 // with the yaw proposal 0.75 von Mises + 0.25 uniform.  Injected noise: noise_rot (B, M) holds the yaw
 // draws themselves (the reference samples them with numpy on the host, distributions.py:61-72, so there
 // is no base noise to replay).
-__device__ void amis_phase4(const KArgs& a, AmisHead<4>& sh, const float* pts4, float* smp, float* cst, float* logp,
-                            const Cam& cam, float delta, int obj) {
+template <int T>
+__device__ void amis_phase4(const KArgs& a, AmisHead<4, T>& sh, const float* pts4, float* smp, float* cst, float* logp,
+                            float* cpart, const Cam& cam, float delta, int obj) {
+    constexpr int PARTS = T / NT;
     const Params& p = a.p;
     const int tid = threadIdx.x;
     const int M = p.mc_samples, I = p.mc_iter, S = M / I;
     const bool injected = a.noise_n3 != nullptr;
-    const int st = serial_thread(a);
+    const int st = serial_thread<T>(a);
     float* const logw_out = a.logw + (size_t)obj * M;
     PH_DECL;
 
@@ -267,6 +301,7 @@ __device__ void amis_phase4(const KArgs& a, AmisHead<4>& sh, const float* pts4, 
 
     for (int i = 0; i < I; ++i) {
         for (int s = tid; s < S; s += NT) {
+            if (PARTS > 1 && tid >= NT) break;
             const int m = i * S + s;
             float n3[3], chi2, q[4];
             if (injected) {
@@ -282,31 +317,48 @@ __device__ void amis_phase4(const KArgs& a, AmisHead<4>& sh, const float* pts4, 
             float* out = a.pose_samples + ((size_t)obj * M + m) * 4;
 #pragma unroll
             for (int k = 0; k < 4; ++k) { smp[m * 4 + k] = q[k]; out[k] = q[k]; }
-            cst[m] = pose_cost<4>(pts4, a.N, q, cam, delta);
+            if constexpr (PARTS == 1) cst[m] = pose_cost<4>(pts4, a.N, q, cam, delta);
             RunningLse l;
             l.start(proposal_logpdf4(sh.prop[0], q));
             for (int j = 1; j <= i; ++j) l.add(proposal_logpdf4(sh.prop[j], q));
             logp[m] = l.value();
         }
+        if constexpr (PARTS > 1) {
+            __syncthreads();
+            const int part = tid / NT, npair = (a.N + 1) >> 1;
+            const int j0 = (int)((long long)npair * part / PARTS) & ~3, j1 = part + 1 == PARTS ? npair : ((int)((long long)npair * (part + 1) / PARTS) & ~3);
+            for (int s = tid % NT; s < S; s += NT) {
+                const int m = i * S + s;
+                cpart[part * M + m] = pose_cost_pairs<4>(pts4, j0, j1, smp + m * 4, cam, delta);
+            }
+            __syncthreads();
+            for (int s = tid; s < S; s += T) {
+                const int m = i * S + s;
+                float c = cpart[m];
+#pragma unroll
+                for (int r = 1; r < PARTS; ++r) c += cpart[r * M + m];
+                cst[m] = c;
+            }
+        }
         PH_MARK(a, PH_DRAW_SWEEP);
-        for (int m = tid; m < i * S; m += NT) logp[m] = log_add_exp(logp[m], proposal_logpdf4(sh.prop[i], smp + m * 4));
+        for (int m = tid; m < i * S; m += T) logp[m] = log_add_exp(logp[m], proposal_logpdf4(sh.prop[i], smp + m * 4));
         __syncthreads();
         PH_MARK(a, PH_LOGP_OLD);
         const int n = (i + 1) * S;
         const float log_cnt = logf((float)(i + 1));
         auto logweight = [&](int m) { return -cst[m] - (logp[m] - log_cnt); };
         if (i == I - 1) {
-            for (int m = tid; m < M; m += NT) logw_out[m] = logweight(m);
+            for (int m = tid; m < M; m += T) logw_out[m] = logweight(m);
             PH_MARK(a, PH_OUTPUT);
             break;
         }
         float mx = -CUDART_INF_F;
-        for (int m = tid; m < n; m += NT) mx = fmaxf(mx, logweight(m));
+        for (int m = tid; m < n; m += T) mx = fmaxf(mx, logweight(m));
         PH_MARK(a, PH_WEIGHTS);
         // ---- refit (estimate_params, epropnp.py:232-260): A max, B sums of e, e t, e sin, e cos, C covariance
-        mx = block_max(mx, sh.red, 0);
+        mx = block_max<T>(mx, sh.red, 0);
         float accB[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int m = tid; m < n; m += NT) {
+        for (int m = tid; m < n; m += T) {
             const float e = expf(logweight(m) - mx);
             const float* s4 = smp + m * 4;
             float sn, cs;
@@ -315,18 +367,18 @@ __device__ void amis_phase4(const KArgs& a, AmisHead<4>& sh, const float* pts4, 
             accB[1] = fmaf(e, s4[0], accB[1]); accB[2] = fmaf(e, s4[1], accB[2]); accB[3] = fmaf(e, s4[2], accB[3]);
             accB[4] = fmaf(e, sn, accB[4]); accB[5] = fmaf(e, cs, accB[5]);
         }
-        block_sum<6>(accB, sh.red, 1);
+        block_sum<6, T>(accB, sh.red, 1);
         const float inv_sum = 1.0f / accB[0];
         const float mean[3] = {accB[1] * inv_sum, accB[2] * inv_sum, accB[3] * inv_sum};
         float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int m = tid; m < n; m += NT) {
+        for (int m = tid; m < n; m += T) {
             const float w = expf(logweight(m) - mx) * inv_sum;
             const float* s4 = smp + m * 4;
             const float d0 = s4[0] - mean[0], d1 = s4[1] - mean[1], d2 = s4[2] - mean[2];
             tc[0] = fmaf(w * d0, d0, tc[0]); tc[1] = fmaf(w * d0, d1, tc[1]); tc[2] = fmaf(w * d0, d2, tc[2]);
             tc[3] = fmaf(w * d1, d1, tc[3]); tc[4] = fmaf(w * d1, d2, tc[4]); tc[5] = fmaf(w * d2, d2, tc[5]);
         }
-        block_sum<6>(tc, sh.red, 0);
+        block_sum<6, T>(tc, sh.red, 0);
         PH_MARK(a, PH_REFIT_SUMS);
         if (tid == st) refit_finish4(mean, tc, accB[4] * inv_sum, accB[5] * inv_sum, p.amis_eps, sh.prop[i + 1]);
         PH_MARK(a, PH_REFIT_FINISH);
@@ -357,15 +409,17 @@ struct PushArgs {
     int n;
 };
 
-// One object per CTA (blockIdx.x = object).
-template <int DOF, bool PUSH>
-__global__ void __launch_bounds__(NT, EPNP_AMIS_CTAS_PER_SM) amis_kernel(const KArgs a, const PushArgs push) {
+// One object per CTA of T threads (blockIdx.x = object).
+template <int DOF, bool PUSH, int T>
+__global__ void __launch_bounds__(T, T == NT ? EPNP_AMIS_CTAS_PER_SM : 1) amis_kernel(const KArgs a, const PushArgs push) {
     EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
-    AmisHead<DOF>& sh = *reinterpret_cast<AmisHead<DOF>*>(smem_raw);
+    AmisHead<DOF, T>& sh = *reinterpret_cast<AmisHead<DOF, T>*>(smem_raw);
     float* dyn = reinterpret_cast<float*>(smem_raw);
     constexpr int PD = Dim<DOF>::POSE;
     const int M = a.p.mc_samples;
-    const AmisPlan pl = plan_amis<DOF>(a.N, M);
+    const AmisPlan pl = plan_amis<DOF, T>(a.N, M);
+    const int st = serial_thread<T>(a);
+    (void)st;
     float* pts4 = dyn + pl.pts;
     const int obj = blockIdx.x, tid = threadIdx.x;
     PH_DECL;
@@ -374,19 +428,19 @@ __global__ void __launch_bounds__(NT, EPNP_AMIS_CTAS_PER_SM) amis_kernel(const K
     if (tid < PD) sh.pose[tid] = a.pose_opt_in[(size_t)obj * PD + tid];
     if (tid < DOF * DOF) sh.cov[tid] = a.pose_cov_in[(size_t)obj * a.cov_stride + tid];
     Loader ld(a, sh.bar, dyn + pl.stage);
-    ld.load_object(obj, pts4);              // ends with a __syncthreads
+    ld.template load_object<T>(obj, pts4);  // ends with a __syncthreads
     const Cam cam = load_cam(a, obj);
     const float delta = __ldg(a.delta + obj);
     PH_MARK(a, PH_LOAD);
-    if constexpr (DOF == 6) amis_phase6(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, cam, delta, obj);
-    else amis_phase4(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, cam, delta, obj);
+    if constexpr (DOF == 6) amis_phase6<T>(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.cpart, cam, delta, obj);
+    else amis_phase4<T>(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.cpart, cam, delta, obj);
     if constexpr (PUSH) {
         // the object's log-weights, as this CTA wrote them, and its pose to the same global row on every peer
         __syncthreads();                                        // the CTA's own global stores are visible to all its threads
         const size_t row = (size_t)a.obj_offset + (size_t)obj;
         const float* src = a.logw + (size_t)obj * M;
         if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-            for (int q = tid; q < M / 4; q += NT) {
+            for (int q = tid; q < M / 4; q += T) {
                 const float4 v = reinterpret_cast<const float4*>(src)[q];
                 for (int r = 0; r < push.n; ++r) {
                     float* dst = push.logw[r] + row * M;
@@ -395,7 +449,7 @@ __global__ void __launch_bounds__(NT, EPNP_AMIS_CTAS_PER_SM) amis_kernel(const K
                 }
             }
         } else {
-            for (int m = tid; m < M; m += NT) {
+            for (int m = tid; m < M; m += T) {
                 const float v = src[m];
                 for (int r = 0; r < push.n; ++r) push.logw[r][row * M + m] = v;
             }

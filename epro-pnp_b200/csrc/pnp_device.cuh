@@ -30,14 +30,14 @@ constexpr int MAX_ITER = 8;             // AMIS iterations supported (reference 
 constexpr int PROP_FLOATS = 19;         // proposals dump: mu3, Lt6, Lr10
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
-// Phase timers (profiling build: -DEPNP_PHASE_TIMERS; tools/phase_profile.py).  The serial thread of every AMIS CTA
+// Phase timers (profiling build: -DEPNP_PHASE_TIMERS; tools/phase_profile.py).  The serial thread `st` of every AMIS CTA
 // adds the clock64() cycles it spent in each phase; the production build compiles them away.
 enum Phase { PH_LOAD = 0, PH_INIT_FIT, PH_DRAW_SWEEP, PH_LOGP_OLD, PH_WEIGHTS, PH_REFIT_SUMS, PH_REFIT_FINISH, PH_OUTPUT, PH_COUNT };
 #ifdef EPNP_PHASE_TIMERS
 #define PH_DECL long long ph_t = clock64()
 #define PH_MARK(a_, which)                                                                     \
     do {                                                                                       \
-        if ((int)threadIdx.x == serial_thread(a_) && (a_).prof) {                              \
+        if ((int)threadIdx.x == st && (a_).prof) {                              \
             const long long now_ = clock64();                                                  \
             atomicAdd((a_).prof + (which), (unsigned long long)(now_ - ph_t));                 \
             ph_t = now_;                                                                       \
@@ -164,8 +164,8 @@ struct Loader {
         tma_load_1d(dst + CH * 3, a.x2d + first * 2, (uint32_t)npts * 8u, b);
         tma_load_1d(dst + CH * 5, a.w2d + first * 2, (uint32_t)npts * 8u, b);
     }
-    // Bring object `obj` into the packed point array.  Ends with a __syncthreads.
-    __device__ void load_object(int obj, float* pts) {
+    // Bring object `obj` into the packed point array (T = threads of the CTA).  Ends with a __syncthreads.
+    template <int T = NT> __device__ void load_object(int obj, float* pts) {
         const int tid = threadIdx.x;
         if (a.use_tma) {
             if (tid == 0) {
@@ -180,7 +180,7 @@ struct Loader {
                 const float* st = stage + (k & 1) * STAGE_FLOATS;
                 mbar_wait(bar + (k & 1), (uint32_t)((k >> 1) & 1));
                 const int npts = min(CH, a.N - k * CH);
-                for (int n = tid; n < npts; n += NT) {
+                for (int n = tid; n < npts; n += T) {
                     const float2 uv = reinterpret_cast<const float2*>(st + CH * 3)[n];
                     const float2 w = reinterpret_cast<const float2*>(st + CH * 5)[n];
                     store_point_padded(pts, k * CH + n, a.N, st[3 * n], st[3 * n + 1], st[3 * n + 2], uv.x, uv.y, w.x, w.y);
@@ -192,7 +192,7 @@ struct Loader {
             const float* g3 = a.x3d + (size_t)obj * a.N * 3;
             const float* g2 = a.x2d + (size_t)obj * a.N * 2;
             const float* gw = a.w2d + (size_t)obj * a.N * 2;
-            for (int n = tid; n < a.N; n += NT)
+            for (int n = tid; n < a.N; n += T)
                 store_point_padded(pts, n, a.N, __ldg(g3 + 3 * n), __ldg(g3 + 3 * n + 1), __ldg(g3 + 3 * n + 2),
                                    __ldg(g2 + 2 * n), __ldg(g2 + 2 * n + 1), __ldg(gw + 2 * n), __ldg(gw + 2 * n + 1));
             __syncthreads();
@@ -218,8 +218,8 @@ __device__ __forceinline__ Cam load_cam(const KArgs& a, int obj) {
 // The once-per-iteration serial work of an AMIS CTA (first proposal, refit finish) runs on lane 0 of ONE warp.
 // Co-resident CTAs of an SM are typically blockIdx, blockIdx + #SM, ...; rotating the serial warp with
 // blockIdx / #SM puts their serial chains on different SM sub-partitions (warp w -> SMSP w % 4).
-__device__ __forceinline__ int serial_thread(const KArgs& a) {
-    return 32 * (int)((blockIdx.x / (unsigned)max(a.num_sms, 1)) & (NW - 1));
+template <int T = NT> __device__ __forceinline__ int serial_thread(const KArgs& a) {
+    return 32 * (int)((blockIdx.x / (unsigned)max(a.num_sms, 1)) & (T / 32 - 1));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -262,13 +262,20 @@ template <int W> __device__ __forceinline__ float warp_transpose_sum_w(float (&v
     return r;
 }
 
-// Block-wide sums of K values per thread; every thread gets the totals.  `red` holds two halves of
-// NW*32 floats: call sites alternate `half` so one __syncthreads per reduction is enough (a thread can be
-// at most one reduction ahead of the slowest reader, and then it writes the other half).
-template <int K> __device__ __forceinline__ void block_sum(float (&v)[K], float* red, int half) {
+// Block-wide sums of K values per thread (T threads, a multiple of 128); every thread gets the totals.  `red` holds two
+// halves of (T / 32) * 32 floats: call sites alternate `half` so one __syncthreads per reduction is enough (a thread
+// can be at most one reduction ahead of the slowest reader, and then it writes the other half).  The per-warp totals
+// are added in warp order, four at a time -- the same association for every T.
+template <int T> __device__ __forceinline__ float sum_warp_partials(const float* r, int k) {
+    float tot = (r[k] + r[32 + k]) + (r[64 + k] + r[96 + k]);
+#pragma unroll
+    for (int w = 4; w < T / 32; w += 4) tot += (r[w * 32 + k] + r[(w + 1) * 32 + k]) + (r[(w + 2) * 32 + k] + r[(w + 3) * 32 + k]);
+    return tot;
+}
+template <int K, int T = NT> __device__ __forceinline__ void block_sum(float (&v)[K], float* red, int half) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* r = red + half * (NW * 32);
-    static_assert(K <= 32, "block_sum: at most 32 values");
+    float* r = red + half * (T / 32 * 32);
+    static_assert(K <= 32 && T % 128 == 0, "block_sum: at most 32 values, whole groups of four warps");
     if constexpr (K > 2) {
         constexpr int W = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
         float w[W];
@@ -290,17 +297,20 @@ template <int K> __device__ __forceinline__ void block_sum(float (&v)[K], float*
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = (r[k] + r[32 + k]) + (r[64 + k] + r[96 + k]);
+    for (int k = 0; k < K; ++k) v[k] = sum_warp_partials<T>(r, k);
 }
 
-__device__ __forceinline__ float block_max(float v, float* red, int half) {
+template <int T = NT> __device__ __forceinline__ float block_max(float v, float* red, int half) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* r = red + half * (NW * 32);
+    float* r = red + half * (T / 32 * 32);
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     if (lane == 0) r[warp * 32] = v;
     __syncthreads();
-    return fmaxf(fmaxf(r[0], r[32]), fmaxf(r[64], r[96]));
+    float m = fmaxf(fmaxf(r[0], r[32]), fmaxf(r[64], r[96]));
+#pragma unroll
+    for (int w = 4; w < T / 32; ++w) m = fmaxf(m, r[w * 32]);
+    return m;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -337,14 +347,15 @@ __device__ __forceinline__ float2 pair_cost(const float2 (&P2)[12], const Cam& c
     return __ffma2_rn(m, __ffma2_rn(m, splat(-0.5f), s), acc);
 }
 
+// pair records [j0, j1)
 template <bool BOUNDED>
-__device__ __forceinline__ float sweep_cost(const float4* pts4, int N, const float* P, const Cam& cam, float delta) {
+__device__ __forceinline__ float sweep_cost(const float4* pts4, int j0, int j1, const float* P, const Cam& cam, float delta) {
     float2 P2[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) P2[k] = splat(P[k]);
     float2 c0 = splat(0.f), c1 = splat(0.f), c2 = splat(0.f), c3 = splat(0.f);
-    const int npair = (N + 1) >> 1;
-    int j = 0;
+    const int npair = j1;
+    int j = j0;
     for (; j + 4 <= npair; j += 4) {            // 8 points in flight per thread
         const float4* q = pts4 + 4 * j;
         c0 = pair_cost<BOUNDED>(P2, cam, delta, c0, q[0], q[1], q[2], q[3]);
@@ -360,13 +371,18 @@ __device__ __forceinline__ float sweep_cost(const float4* pts4, int N, const flo
     return (c0.x + c0.y) + (c1.x + c1.y);
 }
 
+// cost of `pose` over the pair records [j0, j1)
 template <int DOF>
-__device__ __forceinline__ float pose_cost(const float* pts, int N, const float* pose, const Cam& cam, float delta) {
+__device__ __forceinline__ float pose_cost_pairs(const float* pts, int j0, int j1, const float* pose, const Cam& cam, float delta) {
     float R[9], P[12];
     pose_to_rot<DOF>(pose, R);
     make_proj(cam.k, R, pose, P);
     const float4* pts4 = reinterpret_cast<const float4*>(pts);
-    return cam.bounded ? sweep_cost<true>(pts4, N, P, cam, delta) : sweep_cost<false>(pts4, N, P, cam, delta);
+    return cam.bounded ? sweep_cost<true>(pts4, j0, j1, P, cam, delta) : sweep_cost<false>(pts4, j0, j1, P, cam, delta);
+}
+template <int DOF>
+__device__ __forceinline__ float pose_cost(const float* pts, int N, const float* pose, const Cam& cam, float delta) {
+    return pose_cost_pairs<DOF>(pts, 0, (N + 1) >> 1, pose, cam, delta);
 }
 
 }  // namespace

@@ -551,7 +551,7 @@ bool tma_ok(const KArgs& a) { return (a.N % 4 == 0) && aligned16(a.x3d) && align
 
 // One CTA of NT threads per object (grid = B): the hardware scheduler hands CTAs to SMs as slots free up, the CTAs'
 // serial and parallel phases de-synchronise and there is no lock-step tail (measured 5 % faster than a persistent grid).
-template <class Kern, class... Extra>
+template <int T = NT, class Kern, class... Extra>
 int launch_cta_per_object(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stream, Extra... extra) {
     if (a.B == 0) return EPNP_OK;
     if ((size_t)smem_bytes > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
@@ -563,13 +563,32 @@ int launch_cta_per_object(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stre
     // several resident CTAs need (nearly) the whole 228 KB of the SM as shared memory: ask for the full carve-out
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return cuda_fail(e);
-    EPNP_LAUNCH(kern, a.B, NT, smem_bytes, stream, a, extra...);
+    EPNP_LAUNCH(kern, a.B, T, smem_bytes, stream, a, extra...);
     e = cudaGetLastError();
     return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
 }
 
-// LM / GN solve: one warp (one 32-thread CTA) per object.  Outputs: a.pose_opt, a.pose_cov [opt] (stride a.cov_stride),
-// a.cost [opt], a.pose_plus [opt], a.cost_init [opt].
+// LM / GN solve: one CTA of WARPS warps per object (one warp unless the point set is long).  Outputs: a.pose_opt,
+// a.pose_cov [opt] (stride a.cov_stride), a.cost [opt], a.pose_plus [opt], a.cost_init [opt].
+template <int DOF, bool STAGED, int WARPS>
+int launch_lm_as(KArgs& a, int smem_bytes, cudaStream_t stream) {
+    cudaError_t e;
+    if (STAGED) {
+        e = cudaFuncSetAttribute(lm_warp_kernel<DOF, STAGED, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        e = cudaFuncSetAttribute(lm_warp_kernel<DOF, STAGED, WARPS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return cuda_fail(e);
+    }
+    EPNP_LAUNCH((lm_warp_kernel<DOF, STAGED, WARPS>), a.B, 32 * WARPS, smem_bytes, stream, a);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
+}
+
+// Warps per object: a function of N ONLY, so that an object's result does not depend on how large a batch (or which
+// shard of it) it is solved in -- the summation order of the 28 sums changes with the warp count.  Dense coordinate maps
+// (N >= 2048: 16+ points per lane even with 8 warps) get 8 warps, everything else one.
+int lm_warps_per_object(int N) { return N >= 2048 ? 8 : 1; }
+
 template <int DOF>
 int launch_lm(KArgs& a, cudaStream_t stream) {
     if (a.B == 0) return EPNP_OK;
@@ -578,39 +597,48 @@ int launch_lm(KArgs& a, cudaStream_t stream) {
     if (rc != EPNP_OK) return rc;
     const bool staged = a.N <= LM_STAGE_MAX_N;
     const int smem_bytes = lm_smem_bytes<DOF>(a.N, staged);
-    cudaError_t e;
+    const int w = lm_warps_per_object(a.N);
     if (staged) {
-        e = cudaFuncSetAttribute(lm_warp_kernel<DOF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-        if (e != cudaSuccess) return cuda_fail(e);
-        e = cudaFuncSetAttribute(lm_warp_kernel<DOF, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e != cudaSuccess) return cuda_fail(e);
-        EPNP_LAUNCH((lm_warp_kernel<DOF, true>), a.B, 32, smem_bytes, stream, a);
-    } else {
-        EPNP_LAUNCH((lm_warp_kernel<DOF, false>), a.B, 32, smem_bytes, stream, a);
+        switch (w) {
+            case 1: return launch_lm_as<DOF, true, 1>(a, smem_bytes, stream);
+            default: return launch_lm_as<DOF, true, 8>(a, smem_bytes, stream);
+        }
     }
-    e = cudaGetLastError();
-    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
+    switch (w) {
+        case 1: return launch_lm_as<DOF, false, 1>(a, smem_bytes, stream);
+        default: return launch_lm_as<DOF, false, 8>(a, smem_bytes, stream);
+    }
+}
+
+inline bool amis_dense(int N) { return N >= AMIS_DENSE_MIN_N; }
+template <int DOF> int amis_smem_bytes(int N, int M) {
+    return amis_dense(N) ? plan_amis<DOF, AMIS_T_DENSE>(N, M).total_bytes : plan_amis<DOF, NT>(N, M).total_bytes;
 }
 
 template <int DOF>
 int launch_amis(KArgs& a, const PushArgs* push, cudaStream_t stream) {
-    const int smem_bytes = plan_amis<DOF>(a.N, a.p.mc_samples).total_bytes;
-    if (push) return launch_cta_per_object(amis_kernel<DOF, true>, a, smem_bytes, stream, *push);
-    return launch_cta_per_object(amis_kernel<DOF, false>, a, smem_bytes, stream, PushArgs{});
+    const int smem_bytes = amis_smem_bytes<DOF>(a.N, a.p.mc_samples);
+    const PushArgs none{};
+    if (amis_dense(a.N)) {
+        if (push) return launch_cta_per_object<AMIS_T_DENSE>(amis_kernel<DOF, true, AMIS_T_DENSE>, a, smem_bytes, stream, *push);
+        return launch_cta_per_object<AMIS_T_DENSE>(amis_kernel<DOF, false, AMIS_T_DENSE>, a, smem_bytes, stream, none);
+    }
+    if (push) return launch_cta_per_object<NT>(amis_kernel<DOF, true, NT>, a, smem_bytes, stream, *push);
+    return launch_cta_per_object<NT>(amis_kernel<DOF, false, NT>, a, smem_bytes, stream, none);
 }
 
 unsigned long long* g_prof_buffer = nullptr;     // set by epnp_debug_set_phase_buffer (profiling build)
 
 // Objects the device works on at once in the AMIS kernel: SMs x resident CTAs per SM.  Used by the host-buffer entry
 // point to cut the batch at whole waves.  0 when it cannot be determined.
-template <class Kern>
+template <int T, class Kern>
 int resident_objects(Kern kern, int smem_bytes) {
     int sms = 0, occ = 0;
     if ((size_t)smem_bytes > SMEM_LIMIT) return 0;
     if (device_sms(&sms) != EPNP_OK) return 0;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return 0;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem_bytes) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem_bytes) != cudaSuccess) return 0;
     return sms * occ;
 }
 
@@ -630,7 +658,7 @@ int run_lm_amis(KArgs& a, const PushArgs* push, cudaStream_t stream) {
         a.pose_cov = a.pose_samples;
         a.cov_stride = a.p.mc_samples * D;
     }
-    if ((size_t)(dof == 6 ? plan_amis<6>(a.N, a.p.mc_samples).total_bytes : plan_amis<4>(a.N, a.p.mc_samples).total_bytes) > SMEM_LIMIT)
+    if ((size_t)(dof == 6 ? amis_smem_bytes<6>(a.N, a.p.mc_samples) : amis_smem_bytes<4>(a.N, a.p.mc_samples)) > SMEM_LIMIT)
         return EPNP_ERR_TOO_MANY_POINTS;        // before anything is launched
     int rc = dof == 6 ? launch_lm<6>(a, stream) : launch_lm<4>(a, stream);
     if (rc != EPNP_OK) return rc;
@@ -680,7 +708,7 @@ int epnp_max_points(int dof, int mc_samples, int mc_iter) {
         const int mid = ((lo + hi) / 2) / 4 * 4;
         if (mid == lo) break;
         int bytes;
-        if (amis) bytes = (dof == 6) ? plan_amis<6>(mid, mc_samples).total_bytes : plan_amis<4>(mid, mc_samples).total_bytes;
+        if (amis) bytes = (dof == 6) ? amis_smem_bytes<6>(mid, mc_samples) : amis_smem_bytes<4>(mid, mc_samples);
         else bytes = (dof == 6) ? plan_obj<6>(mid).total_bytes : plan_obj<4>(mid).total_bytes;
         if ((size_t)bytes <= SMEM_LIMIT) lo = mid; else hi = mid;
     }
@@ -1029,8 +1057,10 @@ int epnp_lm_amis_fused_host_f32(const float* x3d_host, const float* x2d_host, co
     if (n_chunks == 0) {
         if (check_amis_params(*p) != EPNP_OK) return EPNP_ERR_BAD_ARG;
         const int wave = (p->dof == 6)
-            ? resident_objects(amis_kernel<6, false>, plan_amis<6>(N, p->mc_samples).total_bytes)
-            : resident_objects(amis_kernel<4, false>, plan_amis<4>(N, p->mc_samples).total_bytes);
+            ? (amis_dense(N) ? resident_objects<AMIS_T_DENSE>(amis_kernel<6, false, AMIS_T_DENSE>, amis_smem_bytes<6>(N, p->mc_samples))
+                             : resident_objects<NT>(amis_kernel<6, false, NT>, amis_smem_bytes<6>(N, p->mc_samples)))
+            : (amis_dense(N) ? resident_objects<AMIS_T_DENSE>(amis_kernel<4, false, AMIS_T_DENSE>, amis_smem_bytes<4>(N, p->mc_samples))
+                             : resident_objects<NT>(amis_kernel<4, false, NT>, amis_smem_bytes<4>(N, p->mc_samples)));
         if (wave > 0) {
             const int waves_per_chunk = (B + 64 * wave - 1) / (64 * wave);
             chunk_objects = wave * waves_per_chunk;

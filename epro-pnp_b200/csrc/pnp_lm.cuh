@@ -13,6 +13,11 @@
 // into the warp's shared memory (lane l reads x3d[3 (l + 32 k) + c]: stride 3 floats, conflict-free; x2d / w2d as
 // float2) and re-read from there by the K + 1 evaluations; for N above LM_STAGE_MAX_N (dense coordinate maps) the
 // evaluations read global memory instead (L1 / L2 resident after the first pass).
+//
+// Long point sets: WARPS = 8 warps share one object -- warp w takes points 32 w + lane, 32 (w + 8) + lane, ... -- and their
+// 28 partial sums meet in shared memory (one extra block barrier pair per evaluation): the dense 64 x 64 coordinate maps
+// (N = 4096, typically a few hundred objects) would otherwise run one latency-bound warp per SM.  The warp count is a
+// function of N only, so an object's result never depends on the batch it is solved in.
 #pragma once
 #include "pnp_device.cuh"
 
@@ -20,12 +25,18 @@ namespace {
 
 constexpr int LM_STAGE_MAX_N = 640;     // 28 N bytes of shared memory per warp: 17.9 KB -> 12 resident warps per SM
 
+constexpr int LM_MAX_WARPS = 8;
 template <int DOF> struct LmHead {
     uint64_t bar;
     float ev[32];                       // reduced evaluation: NV floats
     LMState<DOF> lm;
     float cov[DOF * DOF];
+    float part[LM_MAX_WARPS * 32];      // per-warp partial sums (WARPS > 1)
 };
+
+template <int WARPS> __device__ __forceinline__ void lm_group_sync() {
+    if constexpr (WARPS == 1) __syncwarp(); else __syncthreads();
+}
 
 __host__ __device__ inline int lm_padded_points(int N) { return (N + 3) / 4 * 4; }
 template <int DOF> __host__ __device__ inline int lm_head_bytes() { return (int)((sizeof(LmHead<DOF>) + 127) / 128 * 128); }
@@ -33,11 +44,12 @@ template <int DOF> __host__ __device__ inline int lm_smem_bytes(int N, bool stag
     return lm_head_bytes<DOF>() + (staged ? 28 * lm_padded_points(N) : 0);
 }
 
-// Normal equations at `pose` over the object's N points, one warp: result in ev[0..NV) (visible to every lane).
-// Jacobian rows u / v in the two lanes of fp32x2 registers (27 FFMA2 per point instead of 54 FFMA).
-template <int DOF, bool CLIP>
+// Normal equations at `pose` over the object's N points by the object's WARPS warps: result in ev[0..NV) (visible to
+// every thread of the group on return).  Jacobian rows u / v in the two lanes of fp32x2 registers (27 FFMA2 per point
+// instead of 54 FFMA).
+template <int DOF, bool CLIP, int WARPS>
 __device__ __forceinline__ void warp_normal_eq(const float* p3, const float* p2, const float* pw, int N, const float* pose,
-                                               const Cam& cam, float delta, float huber_eps, float* ev) {
+                                               const Cam& cam, float delta, float huber_eps, float* ev, float* part) {
     constexpr int NP = Dim<DOF>::NA + DOF;
     const int lane = threadIdx.x & 31;
     float R[9], t[3];
@@ -55,7 +67,7 @@ __device__ __forceinline__ void warp_normal_eq(const float* p3, const float* p2,
     float cost = 0.f;
     const float2* uv2 = reinterpret_cast<const float2*>(p2);
     const float2* w2 = reinterpret_cast<const float2*>(pw);
-    for (int n = lane; n < N; n += 32) {
+    for (int n = threadIdx.x; n < N; n += 32 * WARPS) {
         const float X = p3[3 * n], Y = p3[3 * n + 1], Z = p3[3 * n + 2];
         const float2 uv = uv2[n], w = w2[n];
         point_normal_eq_rows<DOF, CLIP>(R, t, cam, kuv, delta, huber_eps, X, Y, Z, -uv.x, -uv.y, w.x, w.y, acc2, cost);
@@ -67,18 +79,30 @@ __device__ __forceinline__ void warp_normal_eq(const float* p3, const float* p2,
 #pragma unroll
     for (int i = NP + 1; i < 32; ++i) acc[i] = 0.f;
     const float tot = warp_transpose_sum(acc);
-    ev[lane] = tot;
-    __syncwarp();
+    if constexpr (WARPS == 1) {
+        ev[lane] = tot;
+        __syncwarp();
+    } else {
+        part[(threadIdx.x >> 5) * 32 + lane] = tot;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = part[lane];
+#pragma unroll
+            for (int w = 1; w < WARPS; ++w) v += part[w * 32 + lane];
+            ev[lane] = v;
+        }
+        __syncthreads();
+    }
 }
 
-// One object per warp (blockDim.x = 32, blockIdx.x = object).
-template <int DOF, bool STAGED>
-__global__ void __launch_bounds__(32) lm_warp_kernel(const KArgs a) {
+// One object per CTA of WARPS warps (blockDim.x = 32 WARPS, blockIdx.x = object).
+template <int DOF, bool STAGED, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) lm_warp_kernel(const KArgs a) {
     EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
     LmHead<DOF>& sh = *reinterpret_cast<LmHead<DOF>*>(smem_raw);
     constexpr int PD = Dim<DOF>::POSE;
     const Params& p = a.p;
-    const int lane = threadIdx.x, obj = blockIdx.x, N = a.N;
+    const int lane = threadIdx.x, obj = blockIdx.x, N = a.N;     // `lane`: index within the object's group of 32 WARPS threads
     const float *p3, *p2, *pw;
     if constexpr (STAGED) {
         float* st = reinterpret_cast<float*>(smem_raw + lm_head_bytes<DOF>());
@@ -96,12 +120,12 @@ __global__ void __launch_bounds__(32) lm_warp_kernel(const KArgs a) {
                 tma_load_1d(s2, g2, (uint32_t)N * 8u, &sh.bar);
                 tma_load_1d(sw, gw, (uint32_t)N * 8u, &sh.bar);
             }
-            __syncwarp();
+            lm_group_sync<WARPS>();
             mbar_wait(&sh.bar, 0u);
         } else {
-            for (int i = lane; i < 3 * N; i += 32) s3[i] = __ldg(g3 + i);
-            for (int i = lane; i < 2 * N; i += 32) { s2[i] = __ldg(g2 + i); sw[i] = __ldg(gw + i); }
-            __syncwarp();
+            for (int i = lane; i < 3 * N; i += 32 * WARPS) s3[i] = __ldg(g3 + i);
+            for (int i = lane; i < 2 * N; i += 32 * WARPS) { s2[i] = __ldg(g2 + i); sw[i] = __ldg(gw + i); }
+            lm_group_sync<WARPS>();
         }
         p3 = s3; p2 = s2; pw = sw;
     } else {
@@ -117,32 +141,32 @@ __global__ void __launch_bounds__(32) lm_warp_kernel(const KArgs a) {
         sh.lm.radius = p.initial_radius;
         sh.lm.shrink = 2.0f;
     }
-    __syncwarp();
+    lm_group_sync<WARPS>();
     if (!p.fast_mode) {
-        warp_normal_eq<DOF, true>(p3, p2, pw, N, sh.lm.pose, cam, delta, p.huber_eps, sh.ev);
+        warp_normal_eq<DOF, true, WARPS>(p3, p2, pw, N, sh.lm.pose, cam, delta, p.huber_eps, sh.ev, sh.part);
         if (lane == 0) {
             lm_adopt<DOF>(sh.lm, sh.ev);
             if (a.cost_init) a.cost_init[obj] = sh.lm.cost;
             if (p.lm_iter > 0) lm_propose<DOF>(sh.lm, p);
         }
-        __syncwarp();
+        lm_group_sync<WARPS>();
         for (int it = 0; it < p.lm_iter; ++it) {
-            warp_normal_eq<DOF, true>(p3, p2, pw, N, sh.lm.pose_new, cam, delta, p.huber_eps, sh.ev);
+            warp_normal_eq<DOF, true, WARPS>(p3, p2, pw, N, sh.lm.pose_new, cam, delta, p.huber_eps, sh.ev, sh.part);
             if (lane == 0) {
                 lm_update<DOF>(sh.lm, sh.ev, p);
                 if (it + 1 < p.lm_iter) lm_propose<DOF>(sh.lm, p);
             }
-            __syncwarp();
+            lm_group_sync<WARPS>();
         }
     } else {
         for (int it = 0; it < p.lm_iter; ++it) {
-            warp_normal_eq<DOF, false>(p3, p2, pw, N, sh.lm.pose, cam, delta, p.huber_eps, sh.ev);
+            warp_normal_eq<DOF, false, WARPS>(p3, p2, pw, N, sh.lm.pose, cam, delta, p.huber_eps, sh.ev, sh.part);
             if (lane == 0) {
                 lm_adopt<DOF>(sh.lm, sh.ev);                 // kept for covariance / cost (pre-step)
                 if (it == 0 && a.cost_init) a.cost_init[obj] = sh.lm.cost;
                 gn_advance<DOF>(sh.lm.pose, sh.ev, p.eps, sh.lm.pose);
             }
-            __syncwarp();
+            lm_group_sync<WARPS>();
         }
     }
     if (lane < PD) a.pose_opt[(size_t)obj * PD + lane] = sh.lm.pose[lane];
@@ -154,12 +178,12 @@ __global__ void __launch_bounds__(32) lm_warp_kernel(const KArgs a) {
 #pragma unroll
             for (int i = 0; i < DOF; ++i) sh.cov[i * DOF + lane] = col[i];
         }
-        __syncwarp();
-        for (int i = lane; i < DOF * DOF; i += 32) a.pose_cov[(size_t)obj * a.cov_stride + i] = sh.cov[i];
+        lm_group_sync<WARPS>();
+        for (int i = lane; i < DOF * DOF; i += 32 * WARPS) a.pose_cov[(size_t)obj * a.cov_stride + i] = sh.cov[i];
     }
     if (a.pose_plus) {      // y* (+) one undamped GN step, clip_jac always on (gn_step default)
-        __syncwarp();
-        warp_normal_eq<DOF, true>(p3, p2, pw, N, sh.lm.pose, cam, delta, p.huber_eps, sh.ev);
+        lm_group_sync<WARPS>();
+        warp_normal_eq<DOF, true, WARPS>(p3, p2, pw, N, sh.lm.pose, cam, delta, p.huber_eps, sh.ev, sh.part);
         if (lane == 0) {
             float plus[PD];
             gn_advance<DOF>(sh.lm.pose, sh.ev, p.eps, plus);

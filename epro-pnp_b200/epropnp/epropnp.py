@@ -131,6 +131,17 @@ class EProPnPBase(torch.nn.Module, metaclass=ABCMeta):
                     pose_samples = cast(out["pose_samples"]).transpose(0, 1)      # (M, B, D) view
                     logw = cast(out["logw"]).transpose(0, 1)                      # (M, B) view
 
+        if num_obj == 0 and torch.is_grad_enabled():
+            # an empty batch must still be part of the graph (reference epropnp.py:184-187 and its differentiable
+            # cost_init / pose_opt_plus): a loss built from these outputs has a grad_fn, backward() gives zero gradients
+            # instead of raising, and under DDP the heads of a rank without objects still take part in the all-reduce
+            tie = x3d.sum(dim=(1, 2)) + x2d.sum(dim=(1, 2)) + w2d.sum(dim=(1, 2))             # (0,), connected
+            logw = x3d.reshape(self.mc_samples, 0) + x2d.reshape(self.mc_samples, 0) + w2d.reshape(self.mc_samples, 0)
+            if cost_init is not None:
+                cost_init = cost_init + tie
+            if pose_opt_plus is not None:
+                pose_opt_plus = pose_opt_plus + tie[:, None]
+
         if num_obj > 0 and differentiable:
             # training path: forward = the same fused kernel, backward = native Monte-Carlo cost gradient
             from .autograd import monte_carlo_autograd, pose_plus_autograd

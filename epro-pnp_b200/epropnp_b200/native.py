@@ -214,6 +214,8 @@ def lm_amis_fused_push(prob: Problem, pose_init, params, pose_opt_out, logw_out,
         if tuple(t.shape) != shape or t.dtype != torch.float32 or not t.is_contiguous():
             raise ValueError(f"local output must be contiguous float32 {shape}")
     for lw, ps in zip(peer_logw, peer_pose):
+        if isinstance(lw, int) and isinstance(ps, int):      # raw device pointers of IPC-mapped peer buffers (sharded.raw_ipc_open)
+            continue
         if lw.dtype != torch.float32 or ps.dtype != torch.float32 or not lw.is_contiguous() or not ps.is_contiguous() \
                 or lw.dim() != 2 or lw.shape[1] != M or ps.dim() != 2 or ps.shape[1] != D \
                 or lw.shape[0] < obj_offset + B or ps.shape[0] < obj_offset + B:
@@ -224,8 +226,8 @@ def lm_amis_fused_push(prob: Problem, pose_init, params, pose_opt_out, logw_out,
                cost=prob.empty(B) if want_cost else None,
                pose_cov=prob.empty(B, params.dof, params.dof) if want_cov else None)
     n = len(peer_logw)
-    arr_lw = (ctypes.c_void_p * max(n, 1))(*[t.data_ptr() for t in peer_logw])
-    arr_ps = (ctypes.c_void_p * max(n, 1))(*[t.data_ptr() for t in peer_pose])
+    arr_lw = (ctypes.c_void_p * max(n, 1))(*[t if isinstance(t, int) else t.data_ptr() for t in peer_logw])
+    arr_ps = (ctypes.c_void_p * max(n, 1))(*[t if isinstance(t, int) else t.data_ptr() for t in peer_pose])
     with torch.cuda.device(prob.device):
         check(lib().epnp_lm_amis_fused_push_f32(*prob.common_ptrs(), ptr(pose_init), ctypes.c_uint64(seed),
                                                 ctypes.c_uint32(obj_offset), ptr(out["pose_opt"]), ptr(out["pose_cov"]),

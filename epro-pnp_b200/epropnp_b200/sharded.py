@@ -88,6 +88,65 @@ def gather_results_async(result, num_obj, keys=("pose_opt", "logw"), group=None,
     return PendingGather(outs, works)
 
 
+# ---- raw CUDA IPC: a peer's buffer mapped while THIS process's own device is current.  torch's tensor IPC
+# (reduce_tensor / rebuild_cuda_tensor) opens the handle under the EXPORTER's device index and relies on torch's lazy
+# peer-access switch, which is enough for cross-device copies (PeerGather) but not a documented contract for kernels of
+# another device dereferencing the pointer; the in-kernel push (PushGather) therefore maps its peers the way NCCL does:
+# cudaIpcOpenMemHandle(handle, cudaIpcMemLazyEnablePeerAccess) on the importing device.
+_cudart = None
+
+
+def _runtime():
+    global _cudart
+    if _cudart is None:
+        import ctypes
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                _cudart = ctypes.CDLL(name)
+                break
+            except OSError:
+                continue
+        if _cudart is None:
+            raise RuntimeError("libcudart not found")
+    return _cudart
+
+
+def raw_ipc_export(t):
+    """Picklable description of a CUDA tensor's memory: IPC handle of its allocation + byte offset of its first element."""
+    st = t.untyped_storage()
+    shared = st._share_cuda_()
+    device, handle, _size, offset = shared[0], shared[1], shared[2], shared[3]
+    handle = bytes(handle)
+    # torch >= 2.5 prefixes the 64-byte cudaIpcMemHandle_t with one type byte ('c' = plain cudaMalloc segment; expandable
+    # segments, which have no classic IPC handle, are not supported here)
+    if len(handle) == 65:
+        if handle[:1] != b"c":
+            raise RuntimeError("PushGather needs cudaMalloc-backed allocations (PYTORCH_CUDA_ALLOC_CONF expandable_segments off)")
+        handle = handle[1:]
+    if len(handle) != 64:
+        raise RuntimeError(f"unexpected CUDA IPC handle of {len(handle)} bytes")
+    return dict(device=int(device), handle=handle, offset=int(offset) + t.storage_offset() * t.element_size(),
+                nbytes=t.numel() * t.element_size())
+
+
+def raw_ipc_open(desc, device):
+    """Map the exported allocation into this process with `device` current; returns the device pointer (int) of the tensor's
+    first element, usable by kernels running on `device`."""
+    import ctypes
+
+    class _Handle(ctypes.Structure):
+        _fields_ = [("reserved", ctypes.c_char * 64)]
+    rt = _runtime()
+    rt.cudaIpcOpenMemHandle.argtypes = [ctypes.POINTER(ctypes.c_void_p), _Handle, ctypes.c_uint]
+    rt.cudaIpcOpenMemHandle.restype = ctypes.c_int
+    base = ctypes.c_void_p()
+    with torch.cuda.device(device):
+        rc = rt.cudaIpcOpenMemHandle(ctypes.byref(base), _Handle.from_buffer_copy(desc["handle"]), 1)   # 1 = lazy peer access
+    if rc != 0:
+        raise RuntimeError(f"cudaIpcOpenMemHandle failed with cudaError {rc}")
+    return int(base.value) + int(desc["offset"])
+
+
 class _DeviceHooks:
     """The device-specific pieces of the peer-memory gathers (CUDA streams / events, CUDA IPC).  The CPU test-suite
     substitutes host equivalents (inert streams, shared-memory tensors) to exercise the bookkeeping over gloo."""
@@ -117,6 +176,12 @@ class _DeviceHooks:
     def _import(self, handle):
         fn, args = handle
         return fn(*args)
+
+    def _export_raw(self, t):
+        return raw_ipc_export(t)
+
+    def _import_raw(self, desc):
+        return raw_ipc_open(desc, self.device)     # a raw device pointer (int)
 
 
 class PeerGather(_DeviceHooks):
@@ -244,23 +309,15 @@ class PushGather(_DeviceHooks):
         new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.device)
         self.ring = [dict(pose_opt=new(self.num_obj, pose_dim), logw=new(self.num_obj, mc_samples))
                      for _ in range(self.depth)]
-        self.probe = torch.zeros(4, dtype=torch.float32, device=self.device)
-        mine = dict(ring=[{k: self._export(t) for k, t in slot.items()} for slot in self.ring],
-                    probe=self._export(self.probe))
+        mine = dict(ring=[{k: self._export_raw(t) for k, t in slot.items()} for slot in self.ring])
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=group)
-        self.peers = []                       # peers[r][slot][key] -> full-batch tensor in rank r's memory (None = me)
-        scratch = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self.peers = []                       # peers[r][slot][key] -> rank r's full-batch buffer, mapped for THIS device's kernels (None = me)
         for r, theirs in enumerate(everyone):
             if r == self.rank:
                 self.peers.append(None)
                 continue
-            self.peers.append([{k: self._import(h) for k, h in slot.items()} for slot in theirs["ring"]])
-            # the kernel dereferences these pointers directly: make torch enable peer access in both directions now
-            # (it does so lazily inside cross-device copies) instead of faulting in the first launch
-            remote = self._import(theirs["probe"])
-            scratch.copy_(remote)
-            remote.copy_(scratch)
+            self.peers.append([{k: self._import_raw(h) for k, h in slot.items()} for slot in theirs["ring"]])
         self._device_synchronize()
         self.met = {}                         # batch index -> event of its rendezvous (last `depth` kept)
         self.step = 0

@@ -98,6 +98,13 @@ def lm_amis_fused(prob, pose_init, params, noise=None, seed=0, obj_offset=0, wan
                 proposals=None)
 
 
+def rslm(prob, inds, start, params, want_all=False):
+    r = orc.rslm_solve(prob.x3d, prob.x2d, prob.w2d, prob.camera(params.z_min), prob.delta, inds, start.detach().to(prob.x3d.dtype),
+                       _lm_params(params), fast_mode=bool(params.fast_mode))
+    return dict(pose=r["pose"], cost=r["cost"], pose_all=r["hyp_pose"] if want_all else None,
+                cost_all=r["hyp_cost"] if want_all else None)
+
+
 def cost_backward(prob, dof, z_min, poses_a, grad_a, poses_b=None, grad_b=None, want=(True, True, True, True)):
     """Reference semantics by construction: torch autograd through the oracle's evaluate."""
     with torch.enable_grad():            # we are called from inside Function.backward, where grad mode is off
@@ -113,7 +120,9 @@ def cost_backward(prob, dof, z_min, poses_a, grad_a, poses_b=None, grad_b=None, 
 
 
 def install(monkeypatch):
+    # the derivative-regularisation branch: the torch composite (exact in float64) instead of the fp32 native kernel
+    monkeypatch.setenv("EPNP_NATIVE_GN_STEP", "0")
     for name, fn in (("Problem", FakeProblem), ("adaptive_delta", adaptive_delta), ("evaluate_cost", evaluate_cost),
-                     ("evaluate_full", evaluate_full), ("lm_solve", lm_solve), ("lm_amis_fused", lm_amis_fused),
+                     ("evaluate_full", evaluate_full), ("lm_solve", lm_solve), ("lm_amis_fused", lm_amis_fused), ("rslm", rslm),
                      ("cost_backward", cost_backward)):
         monkeypatch.setattr(native, name, fn)

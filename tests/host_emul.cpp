@@ -448,6 +448,25 @@ int emul_cost_backward(const float* x3d, const float* x2d, const float* w2d, con
 }
 
 // yaw draws of the production sampler, for statistical tests
+// Tail of a proposal refit from given statistics (refit_finish6 / refit_finish4): out[0..3) mu, [3..9) L_t, then
+// dof 6: [9..19) L_r; dof 4: [9] mode, [10] kappa.  Exercises the not-positive-definite fallbacks of the device code.
+int emul_refit_finish(int dof, const float* mean, const float* tc6, const float* lam10_or_sincos, float* out) {
+    if (dof == 6) {
+        Proposal6 p;
+        refit_finish6(mean, tc6, lam10_or_sincos, 1e-3f, p);
+        for (int i = 0; i < 3; ++i) out[i] = p.mu[i];
+        for (int i = 0; i < 6; ++i) out[3 + i] = p.lt[i];
+        for (int i = 0; i < 10; ++i) out[9 + i] = p.lr[i];
+    } else {
+        Proposal4 p;
+        refit_finish4(mean, tc6, lam10_or_sincos[0], lam10_or_sincos[1], 1e-5f, p);
+        for (int i = 0; i < 3; ++i) out[i] = p.mu[i];
+        for (int i = 0; i < 6; ++i) out[3 + i] = p.lt[i];
+        out[9] = p.mode; out[10] = p.kappa;
+    }
+    return 0;
+}
+
 int emul_yaw(uint64_t seed, uint32_t obj, int count, int S, float mode, float kappa, float* out) {
     for (int m = 0; m < count; ++m) out[m] = draw_yaw(seed, obj, (uint32_t)m, m % S, S, mode, kappa);
     return 0;

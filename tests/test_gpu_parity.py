@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_lm_parity, err_vs, golden_bounds, golden_names, load_golden
+from conftest import assert_lm_parity, err_stats, err_vs, golden_bounds, golden_names, load_golden, record_parity
 from epropnp_b200 import native
 from epropnp_b200.synth import make_noise, make_problem
 
@@ -74,9 +74,12 @@ def test_golden_lm_solve(cuda_device, name):
     assert err_vs(out["cost"].cpu().numpy(), g["ref64_lm_cost"]) < max(1e-4, 3 * err_vs(g["ref32_lm_cost"], g["ref64_lm_cost"]))
     assert err_vs(out["pose_cov"].cpu().numpy(), g["ref64_lm_cov"]) < max(2e-3, 3 * err_vs(g["ref32_lm_cov"], g["ref64_lm_cov"]))
     assert err_vs(out["cost_init"].cpu().numpy(), g["ref64_eval_cost"]) < 2e-5
+    record_parity(f"lm/{name}", pose_vs_ref64=err_stats(pose, g["ref64_lm_pose"]), pose_vs_ref32=err_stats(pose, g["ref32_lm_pose"]),
+                  cost_vs_ref64=err_stats(cst, g["ref64_lm_cost"]), cov_vs_ref64=err_stats(out["pose_cov"].cpu().numpy(), g["ref64_lm_cov"]),
+                  ref32_vs_ref64_pose_rel=floor)
 
 
-def _check_amis(samples, logw, props, g):
+def _check_amis(samples, logw, props, g, record=None):
     smp = samples.transpose(0, 1).cpu().numpy()
     lw = logw.transpose(0, 1).cpu().numpy()
     assert np.isfinite(lw).all()
@@ -90,6 +93,10 @@ def _check_amis(samples, logw, props, g):
     ref = np.abs(g["ref32_mc_logw"] - g["ref64_mc_logw"])
     for q in (50, 99):
         assert np.percentile(mine, q) < 3 * np.percentile(ref, q) + 1e-5
+    if record:
+        record_parity(record, samples_vs_ref64=err_stats(smp, g["ref64_mc_samples"]), logw_vs_ref64=err_stats(lw, g["ref64_mc_logw"]),
+                      logw_vs_ref32=err_stats(lw, g["ref32_mc_logw"]), ref32_vs_ref64_logw=err_stats(g["ref32_mc_logw"], g["ref64_mc_logw"]),
+                      ref32_vs_ref64_samples_rel=floor_s)
     if props is not None:
         p = props.cpu().numpy()
         assert err_vs(np.transpose(p[:, :, :3], (1, 0, 2)), g["ref64_mc_trans_mode"]) < 1e-4
@@ -122,7 +129,8 @@ def test_golden_fused_lm_amis(cuda_device, name):
     assert err_vs(out["pose_opt"].cpu().numpy(), g["ref64_mc_pose"]) < max(1e-4, 3 * floor)
     assert err_vs(out["cost_init"].cpu().numpy(), g["ref64_mc_cost_init"]) < 2e-5
     assert err_vs(out["cost"].cpu().numpy(), g["ref64_mc_cost"]) < 1e-4
-    _check_amis(out["pose_samples"], out["logw"], out["proposals"], g)
+    _check_amis(out["pose_samples"], out["logw"], out["proposals"], g, record=f"fused/{name}")
+    record_parity(f"fused/{name}", pose_vs_ref64=err_stats(out["pose_opt"].cpu().numpy(), g["ref64_mc_pose"]))
     # fused == LM kernel followed by AMIS kernel, bit for bit
     lm = native.lm_solve(prob, pose0, p, want_cov=True)
     assert torch.equal(lm["pose_opt"], out["pose_opt"]) and torch.equal(lm["pose_cov"], out["pose_cov"])
@@ -209,6 +217,9 @@ def test_fused_against_oracle_north_star_shape(cuda_device, B, N, M, I):
     mine = np.abs(lw - r64["logw"].numpy())
     ref = np.abs(r32["logw"].numpy() - r64["logw"].numpy())
     assert np.median(mine) < 3 * np.median(ref) + 1e-5
+    record_parity(f"oracle/B{B}_N{N}_M{M}", pose_vs_f64=err_stats(pose, r64["pose_opt"]), pose_vs_f32=err_stats(pose, r32["pose_opt"]),
+                  logw_vs_f64=err_stats(lw, r64["logw"]), logw_vs_f32=err_stats(lw, r32["logw"]), samples_vs_f64=err_stats(smp, r64["samples"]),
+                  f32_vs_f64_logw=err_stats(r32["logw"], r64["logw"]), f32_vs_f64_pose_rel=floor_p, lm_flip_rate=flips)
 
 
 # ------------------------------------------------------------------------------------------------ properties
@@ -323,28 +334,90 @@ def test_philox_draws_are_statistically_equivalent(big):
     assert abs(ess(a).median().item() - ess(b).median().item()) < 0.15 * M
 
 
-def test_dense_config_and_capacity(cuda_device):
-    """N = 4096 (64x64 coordinate map, config #4) stays resident in shared memory; GN fast mode."""
-    B, N = 8, 4096
+def _oracle_amis_from(prob_cpu, noise_cpu, pose, cov, M, I, dtype, z_min, rel_delta):
+    """AMIS of the oracle started from a GIVEN LM solution (so that an LM accept / reject flip cannot leak into the
+    comparison of the sampling loop)."""
+    from oracle import pnp_oracle as orc
+    t = lambda k: prob_cpu[k].to(dtype)
+    cam = orc.Camera(t("cam_mats"), z_min)
+    delta = orc.adaptive_delta(t("x2d"), t("w2d"), rel_delta)
+    B, S = prob_cpu["x3d"].shape[0], M // I
+    n3, c2, n4 = noise_cpu
+    nz = (n3.reshape(B, I, S, 3).permute(1, 2, 0, 3).to(dtype), c2.reshape(B, I, S).permute(1, 2, 0).to(dtype),
+          n4.reshape(B, I, S, 4).permute(1, 2, 0, 3).to(dtype))
+    return orc.amis_6dof(t("x3d"), t("x2d"), t("w2d"), cam, delta, pose.to(dtype), cov.to(dtype), nz, M, I)
+
+
+def test_dense_config_against_oracle_and_capacity(cuda_device):
+    """BASELINE config #4 (EPro-PnP-6DoF/lib/test.py:148-229): N = 4096 (64 x 64 coordinate map), AdaptiveHuber(0.1), GN fast
+    mode + AMIS -- the 8-warps-per-object LM kernel and the 512-thread AMIS kernel (both chosen by N) against the oracle:
+    pose / cost of the solve, then samples and log-weights of the sampling loop started from the kernel's own solution."""
+    B, N, M, I = 8, 4096, 512, 4
     pc = make_problem(B, N, seed=3, grid2d=True)
+    noise = make_noise(B, M, seed=33)
     dev = cuda_device
     delta = native.adaptive_delta(pc["x2d"].to(dev), pc["w2d"].to(dev), 0.1)
     prob = native.Problem(pc["x3d"].to(dev), pc["x2d"].to(dev), pc["w2d"].to(dev), pc["cam_mats"].to(dev), None, None, delta)
-    p = native.default_params(6, lm_iter=3, fast_mode=1, z_min=0.01, mc_samples=512, mc_iter=4)
-    out = native.lm_amis_fused(prob, pc["pose_init"].to(dev), p, seed=1, want_cost=True)
+    p = native.default_params(6, lm_iter=3, fast_mode=1, z_min=0.01, mc_samples=M, mc_iter=I)
+    out = native.lm_amis_fused(prob, pc["pose_init"].to(dev), p, noise=tuple(t.to(dev) for t in noise), want_cost=True)
     from oracle import pnp_oracle as orc
     cam = orc.Camera(pc["cam_mats"].double(), 0.01)
     d64 = orc.adaptive_delta(pc["x2d"].double(), pc["w2d"].double(), 0.1)
-    pose64, _, cost64 = orc.lm_solve(pc["x3d"].double(), pc["x2d"].double(), pc["w2d"].double(), cam, d64,
-                                     pc["pose_init"].double(), orc.LMParams(num_iter=3), fast_mode=True)
+    pose64, cov64, cost64 = orc.lm_solve(pc["x3d"].double(), pc["x2d"].double(), pc["w2d"].double(), cam, d64,
+                                         pc["pose_init"].double(), orc.LMParams(num_iter=3), fast_mode=True)
     assert err_vs(out["pose_opt"].cpu().numpy(), pose64.numpy()) < 1e-4
     assert err_vs(out["cost"].cpu().numpy(), cost64.numpy()) < 1e-4
-    assert torch.isfinite(out["logw"]).all()
+    assert err_vs(out["pose_cov"].cpu().numpy(), cov64.numpy()) < 2e-3
+    pose_k, cov_k = out["pose_opt"].cpu(), out["pose_cov"].cpu()
+    r64 = _oracle_amis_from(pc, noise, pose_k, cov_k, M, I, torch.float64, 0.01, 0.1)
+    r32 = _oracle_amis_from(pc, noise, pose_k, cov_k, M, I, torch.float32, 0.01, 0.1)
+    lw = out["logw"].transpose(0, 1).cpu().numpy()
+    smp = out["pose_samples"].transpose(0, 1).cpu().numpy()
+    floor_w, floor_s = err_vs(r32["logw"], r64["logw"]), err_vs(r32["samples"], r64["samples"])
+    assert np.isfinite(lw).all()
+    assert err_vs(smp, r64["samples"]) < max(1e-4, 5 * floor_s)
+    assert err_vs(lw, r64["logw"]) < max(1e-4, 5 * floor_w)
+    mine, ref = np.abs(lw - r64["logw"].numpy()), np.abs(r32["logw"].numpy() - r64["logw"].numpy())
+    assert np.median(mine) < 3 * np.median(ref) + 1e-5
+    record_parity("oracle/dense_B8_N4096_M512", pose_vs_f64=err_stats(out["pose_opt"].cpu().numpy(), pose64.numpy()),
+                  logw_vs_f64=err_stats(lw, r64["logw"]), samples_vs_f64=err_stats(smp, r64["samples"]),
+                  f32_vs_f64_logw=err_stats(r32["logw"], r64["logw"]))
     too_many = native.capi.lib().epnp_max_points(6, 512, 4) + 4
     big_prob = native.Problem(torch.zeros(1, too_many, 3, device=dev), torch.zeros(1, too_many, 2, device=dev),
                               torch.zeros(1, too_many, 2, device=dev), pc["cam_mats"][:1].to(dev), None, None, 1.0)
     with pytest.raises(native.NativeError, match="shared memory"):
         native.lm_amis_fused(big_prob, pc["pose_init"][:1].to(dev), p)
+
+
+def test_full_batch_strided_subset_against_oracle(cuda_device):
+    """The metric's own shape, B = 4096 / N = 512 / M = 512, with injected noise: every 64th object of the full-size launch
+    (first and last CTAs of the grid included) against the fp64 oracle -- pose, samples and log-weights."""
+    B, N, M, I, stride = 4096, 512, 512, 4, 64
+    pc = make_problem(B, N, seed=17)
+    noise = make_noise(B, M, seed=18)
+    dev = cuda_device
+    delta = native.adaptive_delta(pc["x2d"].to(dev), pc["w2d"].to(dev), 0.5)
+    prob = native.Problem(pc["x3d"].to(dev), pc["x2d"].to(dev), pc["w2d"].to(dev), pc["cam_mats"].to(dev), None, None, delta)
+    p = native.default_params(6, mc_samples=M, mc_iter=I)
+    out = native.lm_amis_fused(prob, pc["pose_init"].to(dev), p, noise=tuple(t.to(dev) for t in noise), want_cost=True)
+    idx = torch.cat((torch.arange(0, B, stride), torch.tensor([B - 1])))
+    sub = {k: v[idx] for k, v in pc.items()}
+    nz = tuple(t[idx] for t in noise)
+    r64 = _oracle_run(sub, nz, M, I, torch.float64)
+    r32 = _oracle_run(sub, nz, M, I, torch.float32)
+    pose = out["pose_opt"][idx.to(dev)].cpu().numpy()
+    lw = out["logw"][idx.to(dev)].transpose(0, 1).cpu().numpy()
+    smp = out["pose_samples"][idx.to(dev)].transpose(0, 1).cpu().numpy()
+    floor_p, floor_w, floor_s = (err_vs(r32[k], r64[k]) for k in ("pose_opt", "logw", "samples"))
+    flips = assert_lm_parity(pose, out["cost"][idx.to(dev)].cpu().numpy(), r64["pose_opt"].numpy(), r64["lm_cost"].numpy(),
+                             max(1e-4, 3 * floor_p), max_flip_frac=0.05, what="strided subset")
+    assert err_vs(smp, r64["samples"]) < max(1e-4, 5 * floor_s)
+    assert err_vs(lw, r64["logw"]) < max(1e-4, 5 * floor_w)
+    if flips == 0.0:
+        assert err_vs(pose, r32["pose_opt"]) < 1e-4 and err_vs(lw, r32["logw"]) < 1e-4 + 2 * floor_w
+    record_parity("oracle/full_batch_B4096_every64th", objects=int(idx.numel()), pose_vs_f64=err_stats(pose, r64["pose_opt"]),
+                  logw_vs_f64=err_stats(lw, r64["logw"]), logw_vs_f32=err_stats(lw, r32["logw"]), samples_vs_f64=err_stats(smp, r64["samples"]),
+                  f32_vs_f64_logw=err_stats(r32["logw"], r64["logw"]), lm_flip_rate=flips)
 
 
 def test_host_buffer_entry_point(big):

@@ -259,3 +259,54 @@ def test_production_rng_statistics(emul):
     out3 = np.zeros((1000, 8), np.float32)
     emul.emul_base_noise(ctypes.c_uint64(1234), ctypes.c_uint32(7), 1000, fptr(out3))
     assert np.array_equal(out3, out[:1000])
+
+
+def test_refit_fallbacks_and_regular_factors(emul):
+    """refit_finish6 / refit_finish4 (the tail of estimate_params, epropnp.py:232-260, 317-342): a translation covariance
+    that is not positive definite gets the identity (6DoF) / diag(1, 1, 4) (4DoF) like cholesky_wrapper (:16-33), a
+    scatter matrix that is not positive definite gets the identity; regular inputs give the Cholesky factors."""
+    mean = np.array([0.1, -0.2, 5.0], np.float32)
+    bad_tc = np.array([1.0, 0.0, 0.0, -1.0, 0.0, 1.0], np.float32)              # diag(1, -1, 1), packed upper
+    A = np.array([[2.0, 0.3, -0.1], [0.3, 1.5, 0.2], [-0.1, 0.2, 0.7]])
+    good_tc = np.array([A[0, 0], A[0, 1], A[0, 2], A[1, 1], A[1, 2], A[2, 2]], np.float32)
+    S = np.array([[0.4, 0.05, 0.0, 0.02], [0.05, 0.3, 0.01, 0.0], [0.0, 0.01, 0.2, 0.03], [0.02, 0.0, 0.03, 0.1]])
+    good_lam = np.array([S[i, j] for i in range(4) for j in range(i, 4)], np.float32)
+    bad_lam = good_lam.copy()
+    bad_lam[4] = -0.3                                                         # a negative diagonal entry
+    out = np.zeros(19, np.float32)
+    tril3 = lambda L: np.array([L[0, 0], L[1, 0], L[1, 1], L[2, 0], L[2, 1], L[2, 2]])
+    # 6DoF
+    emul.emul_refit_finish(6, fptr(mean), fptr(bad_tc), fptr(good_lam), fptr(out))
+    assert np.array_equal(out[3:9], np.array([1, 0, 1, 0, 0, 1], np.float32)) and np.array_equal(out[:3], mean)
+    emul.emul_refit_finish(6, fptr(mean), fptr(good_tc), fptr(bad_lam), fptr(out))
+    assert np.array_equal(out[9:19], np.array([1, 0, 1, 0, 0, 1, 0, 0, 0, 1], np.float32))
+    assert np.abs(out[3:9] - tril3(np.linalg.cholesky(A))).max() < 1e-6
+    emul.emul_refit_finish(6, fptr(mean), fptr(good_tc), fptr(good_lam), fptr(out))
+    Sd = S + np.linalg.det(S) ** 0.25 * 1e-3 * np.eye(4)
+    L4 = np.linalg.cholesky(Sd)
+    assert np.abs(out[9:19] - np.array([L4[i, j] for i in range(4) for j in range(i + 1)])).max() < 1e-6
+    # 4DoF
+    sc = np.array([0.3, 0.4], np.float32)
+    emul.emul_refit_finish(4, fptr(mean), fptr(bad_tc), fptr(sc), fptr(out))
+    assert np.array_equal(out[3:9], np.array([1, 0, 1, 0, 0, 4], np.float32))
+    assert abs(out[9] - np.arctan2(0.3, 0.4)) < 1e-6 and abs(out[10] - 0.33 * 0.5 * (2 - 0.25) / 0.75) < 1e-5
+    emul.emul_refit_finish(4, fptr(mean), fptr(good_tc), fptr(sc), fptr(out))
+    assert np.abs(out[3:9] - tril3(np.linalg.cholesky(A))).max() < 1e-6
+
+
+@pytest.mark.parametrize("kappa", [1e-7, 1e-5, 1e-4, 1e-3, 3e-2, 0.5, 4.0])
+def test_von_mises_sampler_statistics(emul, kappa):
+    """draw_yaw (production 4DoF sampler, Best-Fisher rejection): below kappa ~ 1e-3 the textbook constants cancel in
+    fp32 (rho = 0, rr = inf: every draw collapsed onto the mode before the fix); the cancellation-free form must give a
+    von Mises sample at every concentration -- mean resultant length A(kappa) = I1 / I0, direction = mode."""
+    from scipy.special import i0e, i1e
+    n, S, mode = 40000, 40000, 0.7
+    out = np.zeros(n, np.float32)
+    emul.emul_yaw(ctypes.c_uint64(11), ctypes.c_uint32(3), n, S, ctypes.c_float(mode), ctypes.c_float(kappa), fptr(out))
+    vm = out[int(np.floor(0.25 * S + 0.5)):].astype(np.float64)   # the first quarter of an iteration is uniform
+    assert np.isfinite(vm).all() and np.abs(vm).max() <= np.pi + 1e-5
+    assert np.unique(vm).size > 0.9 * vm.size                      # not collapsed onto the mode
+    C, Sn = np.cos(vm - mode).mean(), np.sin(vm - mode).mean()
+    want = i1e(kappa) / i0e(kappa)
+    tol = 4.0 / np.sqrt(vm.size)
+    assert abs(C - want) < tol and abs(Sn) < tol, (kappa, C, want, Sn)

@@ -203,3 +203,30 @@ def test_builders_construct_nested_configs():
         build_pnp(dict(dof=4))
     with pytest.raises(KeyError):
         PNP.register_module(module=LMSolver)          # duplicate registration
+
+
+def test_empty_batch_stays_in_the_autograd_graph():
+    """B = 0 (a detection rank without objects): the layer's differentiable outputs must carry a grad_fn like the
+    reference's (epropnp.py:184-187), so that a loss made only of them can be back-propagated (zero gradients)."""
+    import torch
+    from epropnp.camera import PerspectiveCamera
+    from epropnp.cost_fun import AdaptiveHuberPnPCost
+    from epropnp.epropnp import EProPnP4DoF, EProPnP6DoF
+    from epropnp.levenberg_marquardt import LMSolver
+    from epropnp.monte_carlo_pose_loss import MonteCarloPoseLoss
+    for cls, dof, pd in ((EProPnP6DoF, 6, 7), (EProPnP4DoF, 4, 4)):
+        x3d = torch.zeros(0, 16, 3, requires_grad=True)
+        x2d = torch.zeros(0, 16, 2, requires_grad=True)
+        w2d = torch.zeros(0, 16, 2, requires_grad=True)
+        camera = PerspectiveCamera(cam_mats=torch.zeros(0, 3, 3))
+        cost_fun = AdaptiveHuberPnPCost(relative_delta=0.5)
+        cost_fun.set_param(x2d.detach(), w2d)
+        layer = cls(mc_samples=8, num_iter=2, solver=LMSolver(dof=dof, num_iter=2))
+        pose_opt, cost, plus, samples, logw, cost_init = layer.monte_carlo_forward(
+            x3d, x2d, w2d, camera, cost_fun, pose_init=torch.zeros(0, pd), force_init_solve=False, with_pose_opt_plus=True)
+        assert pose_opt.shape == (0, pd) and samples.shape == (8, 0, pd) and logw.shape == (8, 0)
+        assert logw.grad_fn is not None and cost_init.grad_fn is not None and plus.grad_fn is not None
+        loss = MonteCarloPoseLoss()(logw, cost_init, 1.0) + plus.sum()
+        loss.backward()
+        for t in (x3d, x2d, w2d):
+            assert t.grad is not None and t.grad.shape == t.shape

@@ -58,8 +58,6 @@ def _worker(rank, world, port, q):
 
 
 def test_peer_gather_matches_nccl():
-    if not os.environ.get("EPNP_TEST_PEER_GATHER"):
-        pytest.skip("experimental path: set EPNP_TEST_PEER_GATHER=1 on a box with two GPUs")
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     world = 2

@@ -128,6 +128,10 @@ def _host_class(base):
             fn, args, shape, dtype = handle
             return torch.empty(0, dtype=dtype).set_(fn(*args), 0, shape)
 
+        # PushGather maps its peers through raw CUDA IPC on the GPU; on the host the shared-memory tensors stand in
+        _export_raw = _export
+        _import_raw = _import
+
     return HostGather
 
 

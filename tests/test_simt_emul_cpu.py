@@ -147,3 +147,39 @@ test_full_size_deterministic_and_shard_invariant = _gp.test_full_size_determinis
 test_lm_flip_rate_at_north_star_shape = _gp.test_lm_flip_rate_at_north_star_shape
 test_tma_and_plain_loader_agree = _gp.test_tma_and_plain_loader_agree
 test_point_permutation_invariance = _gp.test_point_permutation_invariance
+
+
+def test_long_point_sets_take_the_multi_warp_kernels(cuda_device):
+    """N >= 2048 selects the 8-warps-per-object LM kernel and the 512-thread AMIS kernel (split cost sweep): both against
+    the fp64 oracle at a size the emulator affords, LM / GN and bounded / unbounded."""
+    from oracle import pnp_oracle as orc
+    from epropnp_b200 import native
+    from epropnp_b200.synth import make_noise, make_problem
+    from conftest import err_vs
+    B, N, M, I = 2, 2050, 16, 2
+    for fast, bounded in ((1, False), (0, True)):
+        pc = make_problem(B, N, seed=21 + fast)
+        noise = make_noise(B, M, seed=22)
+        lb, ub = ((pc["x2d"].amin(1) + 4.0, pc["x2d"].amax(1) - 4.0) if bounded else (None, None))
+        delta = native.adaptive_delta(pc["x2d"], pc["w2d"], 0.5)
+        prob = native.Problem(pc["x3d"], pc["x2d"], pc["w2d"], pc["cam_mats"], lb, ub, delta)
+        p = native.default_params(6, lm_iter=3, fast_mode=fast, mc_samples=M, mc_iter=I)
+        out = native.lm_amis_fused(prob, pc["pose_init"], p, noise=noise, want_cost=True)
+        d = torch.float64
+        cam = orc.Camera(pc["cam_mats"].to(d), 0.1, None if lb is None else lb.to(d), None if ub is None else ub.to(d))
+        d64 = orc.adaptive_delta(pc["x2d"].to(d), pc["w2d"].to(d), 0.5)
+        pose64, cov64, cost64 = orc.lm_solve(pc["x3d"].to(d), pc["x2d"].to(d), pc["w2d"].to(d), cam, d64, pc["pose_init"].to(d),
+                                             orc.LMParams(num_iter=3), fast_mode=bool(fast))
+        assert err_vs(out["pose_opt"].numpy(), pose64.numpy()) < 1e-4
+        assert err_vs(out["cost"].numpy(), cost64.numpy()) < 1e-4
+        S = M // I
+        nz = (noise[0].reshape(B, I, S, 3).permute(1, 2, 0, 3).to(d), noise[1].reshape(B, I, S).permute(1, 2, 0).to(d),
+              noise[2].reshape(B, I, S, 4).permute(1, 2, 0, 3).to(d))
+        r = orc.amis_6dof(pc["x3d"].to(d), pc["x2d"].to(d), pc["w2d"].to(d), cam, d64, out["pose_opt"].to(d), out["pose_cov"].to(d), nz, M, I)
+        f = torch.float32                                       # the same loop in fp32: what rounding alone moves
+        cam32 = orc.Camera(pc["cam_mats"], 0.1, lb, ub)
+        r32 = orc.amis_6dof(pc["x3d"], pc["x2d"], pc["w2d"], cam32, orc.adaptive_delta(pc["x2d"], pc["w2d"], 0.5), out["pose_opt"],
+                            out["pose_cov"], tuple(t.to(f) for t in nz), M, I)
+        floor_w = err_vs(r32["logw"].numpy(), r["logw"].numpy())
+        assert err_vs(out["pose_samples"].transpose(0, 1).numpy(), r["samples"].numpy()) < 2e-4
+        assert err_vs(out["logw"].transpose(0, 1).numpy(), r["logw"].numpy()) < max(2e-4, 5 * floor_w)
