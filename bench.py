@@ -296,8 +296,10 @@ def main():
                          "NVLink (no gather kernel); 'nccl' = overlapped all_gather_into_tensor; 'peer' = copy-engine pulls")
     ap.add_argument("--nccl-max-ctas", type=int, default=0,
                     help="N > 1, --gather nccl: cap the CTAs NCCL may use per collective (0 = NCCL's default)")
-    ap.add_argument("--streams", type=int, default=1,
-                    help="batches in flight: consecutive (independent) batches are issued round-robin on this many CUDA streams")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="batches in flight: consecutive (independent) batches are issued round-robin on this many CUDA streams, "
+                         "so the next batch's LM kernel and first AMIS CTAs fill the SMs the previous batch's last, partial wave "
+                         "of CTAs leaves idle (measured +4.4 %% at one GPU); 1 = strictly one batch at a time")
     ap.add_argument("--batch", type=int, default=0, help="objects per GPU (default: the config's)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])

@@ -28,6 +28,7 @@ template <> struct ProposalOf<4> { typedef Proposal4 type; };
 
 constexpr int AMIS_T_DENSE = 512;          // threads per CTA for long point sets
 constexpr int AMIS_DENSE_MIN_N = 2048;     // a function of N only: an object's result must not depend on its batch
+constexpr int AMIS_CHUNK_DENSE = 512;      // points per TMA chunk there (one per thread and chunk)
 
 template <int DOF, int T> struct AmisHead {
     uint64_t bar[2];
@@ -47,8 +48,9 @@ template <int DOF, int T>
 __host__ __device__ inline AmisPlan plan_amis(int N, int M) {
     AmisPlan s;
     int off = (int)((sizeof(AmisHead<DOF, T>) + 127) / 128 * 128 / 4);
-    const bool alias = Dim<DOF>::POSE * M >= 2 * STAGE_FLOATS;
-    s.stage = off; if (!alias) off += 2 * STAGE_FLOATS;
+    constexpr int ring = 2 * 7 * (T > NT ? AMIS_CHUNK_DENSE : CH);
+    const bool alias = Dim<DOF>::POSE * M >= ring;
+    s.stage = off; if (!alias) off += ring;
     s.pts = off; off += 16 * ((N + 1) / 2);        // 64 B per pair of points
     s.smp = off; off += Dim<DOF>::POSE * M;
     if (alias) s.stage = s.smp;
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(T, T == NT ? EPNP_AMIS_CTAS_PER_SM : 1) amis_k
     // parked the covariance there (cov_stride = M * D).  Plain loads: that memory is written later in this launch.
     if (tid < PD) sh.pose[tid] = a.pose_opt_in[(size_t)obj * PD + tid];
     if (tid < DOF * DOF) sh.cov[tid] = a.pose_cov_in[(size_t)obj * a.cov_stride + tid];
-    Loader ld(a, sh.bar, dyn + pl.stage);
+    LoaderT<(T > NT ? AMIS_CHUNK_DENSE : CH)> ld(a, sh.bar, dyn + pl.stage);
     ld.template load_object<T>(obj, pts4);  // ends with a __syncthreads
     const Cam cam = load_cam(a, obj);
     const float delta = __ldg(a.delta + obj);

@@ -143,26 +143,29 @@ __device__ __forceinline__ void store_point_padded(float* pts, int n, int N, flo
 }
 
 // Correspondence loader of the CTA-per-object kernels (one object per CTA, blockIdx.x = object): the object's
-// {x3d, x2d, w2d} come from HBM exactly once, in 128-point chunks through a 2-slot TMA ring (cp.async.bulk completing on an
-// mbarrier), and are re-packed into the pair records; plain loads when the pointers / N break the 16-byte rules.
-struct Loader {
+// {x3d, x2d, w2d} come from HBM exactly once, in CHUNK-point chunks through a 2-slot TMA ring (cp.async.bulk completing on
+// an mbarrier), and are re-packed into the pair records; plain loads when the pointers / N break the 16-byte rules.
+// CHUNK = 128 (2 x 3.5 KB of ring, hidden inside the sample buffer); 512 for the 512-thread CTAs of long point sets.
+template <int CHUNK = CH>
+struct LoaderT {
+    static constexpr int SLOT_FLOATS = CHUNK * 7;
     const KArgs& a;
     uint64_t* bar;
     float* stage;
     int nch;
 
-    __device__ Loader(const KArgs& a_, uint64_t* bar_, float* stage_) : a(a_), bar(bar_), stage(stage_) {
-        nch = (a.N + CH - 1) / CH;
+    __device__ LoaderT(const KArgs& a_, uint64_t* bar_, float* stage_) : a(a_), bar(bar_), stage(stage_) {
+        nch = (a.N + CHUNK - 1) / CHUNK;
     }
     __device__ void issue(int obj, int k) {          // one thread
-        const int npts = min(CH, a.N - k * CH);
-        const size_t first = (size_t)obj * a.N + (size_t)k * CH;
-        float* dst = stage + (k & 1) * STAGE_FLOATS;
+        const int npts = min(CHUNK, a.N - k * CHUNK);
+        const size_t first = (size_t)obj * a.N + (size_t)k * CHUNK;
+        float* dst = stage + (k & 1) * SLOT_FLOATS;
         uint64_t* b = bar + (k & 1);
         mbar_expect_tx(b, (uint32_t)npts * 28u);
         tma_load_1d(dst, a.x3d + first * 3, (uint32_t)npts * 12u, b);
-        tma_load_1d(dst + CH * 3, a.x2d + first * 2, (uint32_t)npts * 8u, b);
-        tma_load_1d(dst + CH * 5, a.w2d + first * 2, (uint32_t)npts * 8u, b);
+        tma_load_1d(dst + CHUNK * 3, a.x2d + first * 2, (uint32_t)npts * 8u, b);
+        tma_load_1d(dst + CHUNK * 5, a.w2d + first * 2, (uint32_t)npts * 8u, b);
     }
     // Bring object `obj` into the packed point array (T = threads of the CTA).  Ends with a __syncthreads.
     template <int T = NT> __device__ void load_object(int obj, float* pts) {
@@ -177,13 +180,13 @@ struct Loader {
             }
             __syncthreads();
             for (int k = 0; k < nch; ++k) {
-                const float* st = stage + (k & 1) * STAGE_FLOATS;
+                const float* st = stage + (k & 1) * SLOT_FLOATS;
                 mbar_wait(bar + (k & 1), (uint32_t)((k >> 1) & 1));
-                const int npts = min(CH, a.N - k * CH);
+                const int npts = min(CHUNK, a.N - k * CHUNK);
                 for (int n = tid; n < npts; n += T) {
-                    const float2 uv = reinterpret_cast<const float2*>(st + CH * 3)[n];
-                    const float2 w = reinterpret_cast<const float2*>(st + CH * 5)[n];
-                    store_point_padded(pts, k * CH + n, a.N, st[3 * n], st[3 * n + 1], st[3 * n + 2], uv.x, uv.y, w.x, w.y);
+                    const float2 uv = reinterpret_cast<const float2*>(st + CHUNK * 3)[n];
+                    const float2 w = reinterpret_cast<const float2*>(st + CHUNK * 5)[n];
+                    store_point_padded(pts, k * CHUNK + n, a.N, st[3 * n], st[3 * n + 1], st[3 * n + 2], uv.x, uv.y, w.x, w.y);
                 }
                 __syncthreads();            // slot drained (and, after the last chunk, pts complete)
                 if (tid == 0 && k + 2 < nch) { fence_proxy_async(); issue(obj, k + 2); }
@@ -199,6 +202,7 @@ struct Loader {
         }
     }
 };
+typedef LoaderT<CH> Loader;
 
 __device__ __forceinline__ Cam load_cam(const KArgs& a, int obj) {
     Cam c;

@@ -571,7 +571,8 @@ int launch_cta_per_object(Kern kern, KArgs& a, int smem_bytes, cudaStream_t stre
 // LM / GN solve: one CTA of WARPS warps per object (one warp unless the point set is long).  Outputs: a.pose_opt,
 // a.pose_cov [opt] (stride a.cov_stride), a.cost [opt], a.pose_plus [opt], a.cost_init [opt].
 template <int DOF, bool STAGED, int WARPS>
-int launch_lm_as(KArgs& a, int smem_bytes, cudaStream_t stream) {
+int launch_lm_as(KArgs& a, cudaStream_t stream) {
+    const int smem_bytes = lm_smem_bytes<DOF, WARPS>(a.N, STAGED);
     cudaError_t e;
     if (STAGED) {
         e = cudaFuncSetAttribute(lm_warp_kernel<DOF, STAGED, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -596,17 +597,16 @@ int launch_lm(KArgs& a, cudaStream_t stream) {
     int rc = device_sms(&a.num_sms);
     if (rc != EPNP_OK) return rc;
     const bool staged = a.N <= LM_STAGE_MAX_N;
-    const int smem_bytes = lm_smem_bytes<DOF>(a.N, staged);
     const int w = lm_warps_per_object(a.N);
     if (staged) {
         switch (w) {
-            case 1: return launch_lm_as<DOF, true, 1>(a, smem_bytes, stream);
-            default: return launch_lm_as<DOF, true, 8>(a, smem_bytes, stream);
+            case 1: return launch_lm_as<DOF, true, 1>(a, stream);
+            default: return launch_lm_as<DOF, true, 8>(a, stream);
         }
     }
     switch (w) {
-        case 1: return launch_lm_as<DOF, false, 1>(a, smem_bytes, stream);
-        default: return launch_lm_as<DOF, false, 8>(a, smem_bytes, stream);
+        case 1: return launch_lm_as<DOF, false, 1>(a, stream);
+        default: return launch_lm_as<DOF, false, 8>(a, stream);
     }
 }
 

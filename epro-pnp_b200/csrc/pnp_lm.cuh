@@ -26,12 +26,12 @@ namespace {
 constexpr int LM_STAGE_MAX_N = 640;     // 28 N bytes of shared memory per warp: 17.9 KB -> 12 resident warps per SM
 
 constexpr int LM_MAX_WARPS = 8;
-template <int DOF> struct LmHead {
+template <int DOF, int WARPS> struct LmHead {
     uint64_t bar;
     float ev[32];                       // reduced evaluation: NV floats
     LMState<DOF> lm;
     float cov[DOF * DOF];
-    float part[LM_MAX_WARPS * 32];      // per-warp partial sums (WARPS > 1)
+    float part[WARPS > 1 ? WARPS * 32 : 1];     // per-warp partial sums (WARPS > 1)
 };
 
 template <int WARPS> __device__ __forceinline__ void lm_group_sync() {
@@ -39,9 +39,9 @@ template <int WARPS> __device__ __forceinline__ void lm_group_sync() {
 }
 
 __host__ __device__ inline int lm_padded_points(int N) { return (N + 3) / 4 * 4; }
-template <int DOF> __host__ __device__ inline int lm_head_bytes() { return (int)((sizeof(LmHead<DOF>) + 127) / 128 * 128); }
-template <int DOF> __host__ __device__ inline int lm_smem_bytes(int N, bool staged) {
-    return lm_head_bytes<DOF>() + (staged ? 28 * lm_padded_points(N) : 0);
+template <int DOF, int WARPS> __host__ __device__ inline int lm_head_bytes() { return (int)((sizeof(LmHead<DOF, WARPS>) + 127) / 128 * 128); }
+template <int DOF, int WARPS> __host__ __device__ inline int lm_smem_bytes(int N, bool staged) {
+    return lm_head_bytes<DOF, WARPS>() + (staged ? 28 * lm_padded_points(N) : 0);
 }
 
 // Normal equations at `pose` over the object's N points by the object's WARPS warps: result in ev[0..NV) (visible to
@@ -99,13 +99,13 @@ __device__ __forceinline__ void warp_normal_eq(const float* p3, const float* p2,
 template <int DOF, bool STAGED, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS) lm_warp_kernel(const KArgs a) {
     EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
-    LmHead<DOF>& sh = *reinterpret_cast<LmHead<DOF>*>(smem_raw);
+    LmHead<DOF, WARPS>& sh = *reinterpret_cast<LmHead<DOF, WARPS>*>(smem_raw);
     constexpr int PD = Dim<DOF>::POSE;
     const Params& p = a.p;
     const int lane = threadIdx.x, obj = blockIdx.x, N = a.N;     // `lane`: index within the object's group of 32 WARPS threads
     const float *p3, *p2, *pw;
     if constexpr (STAGED) {
-        float* st = reinterpret_cast<float*>(smem_raw + lm_head_bytes<DOF>());
+        float* st = reinterpret_cast<float*>(smem_raw + lm_head_bytes<DOF, WARPS>());
         const int np = lm_padded_points(N);
         float *s3 = st, *s2 = st + 3 * np, *sw = st + 5 * np;
         const float* g3 = a.x3d + (size_t)obj * N * 3;

@@ -112,20 +112,31 @@ def _runtime():
 
 
 def raw_ipc_export(t):
-    """Picklable description of a CUDA tensor's memory: IPC handle of its allocation + byte offset of its first element."""
-    st = t.untyped_storage()
-    shared = st._share_cuda_()
-    device, handle, _size, offset = shared[0], shared[1], shared[2], shared[3]
-    handle = bytes(handle)
-    # torch >= 2.5 prefixes the 64-byte cudaIpcMemHandle_t with one type byte ('c' = plain cudaMalloc segment; expandable
-    # segments, which have no classic IPC handle, are not supported here)
-    if len(handle) == 65:
-        if handle[:1] != b"c":
-            raise RuntimeError("PushGather needs cudaMalloc-backed allocations (PYTORCH_CUDA_ALLOC_CONF expandable_segments off)")
-        handle = handle[1:]
-    if len(handle) != 64:
-        raise RuntimeError(f"unexpected CUDA IPC handle of {len(handle)} bytes")
-    return dict(device=int(device), handle=handle, offset=int(offset) + t.storage_offset() * t.element_size(),
+    """Picklable description of a CUDA tensor's memory: the cudaIpcMemHandle_t of the cudaMalloc allocation it lives in
+    (cuMemGetAddressRange finds its base; torch's caching allocator sub-allocates segments) + the byte offset of the
+    tensor's first element.  The exporter must keep the tensor alive while peers use the mapping."""
+    import ctypes
+
+    class _Handle(ctypes.Structure):
+        _fields_ = [("reserved", ctypes.c_char * 64)]
+    rt = _runtime()
+    drv = ctypes.CDLL("libcuda.so.1")
+    base, size = ctypes.c_uint64(0), ctypes.c_size_t(0)
+    with torch.cuda.device(t.device):
+        fn = getattr(drv, "cuMemGetAddressRange_v2", None) or drv.cuMemGetAddressRange
+        fn.argtypes = [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_size_t), ctypes.c_uint64]
+        fn.restype = ctypes.c_int
+        rc = fn(ctypes.byref(base), ctypes.byref(size), ctypes.c_uint64(t.data_ptr()))
+        if rc != 0:
+            raise RuntimeError(f"cuMemGetAddressRange failed with CUresult {rc}")
+        h = _Handle()
+        rt.cudaIpcGetMemHandle.argtypes = [ctypes.POINTER(_Handle), ctypes.c_void_p]
+        rt.cudaIpcGetMemHandle.restype = ctypes.c_int
+        rc = rt.cudaIpcGetMemHandle(ctypes.byref(h), ctypes.c_void_p(base.value))
+        if rc != 0:
+            raise RuntimeError(f"cudaIpcGetMemHandle failed with cudaError {rc} (expandable segments have no classic IPC "
+                               "handle: PushGather needs PYTORCH_CUDA_ALLOC_CONF without expandable_segments)")
+    return dict(device=int(t.device.index), handle=bytes(h), offset=int(t.data_ptr() - base.value),
                 nbytes=t.numel() * t.element_size())
 
 

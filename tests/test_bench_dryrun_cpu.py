@@ -67,7 +67,7 @@ CONTRACT = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
             "vs_baseline", "dtype", "data", "config", "roofline", "clocks", "gpu_launches", "e2e")
 
 
-@pytest.mark.parametrize("argv,overrides", [([], {}), (["--streams", "2"], {}), ([], {"E2E_LANES": 1, "E2E_CHUNKS": 0}),
+@pytest.mark.parametrize("argv,overrides", [([], {}), (["--streams", "1"], {}), ([], {"E2E_LANES": 1, "E2E_CHUNKS": 0}),
                                             (["--no-e2e"], {}), (["--config", "lm_only"], {}), (["--config", "dense"], {}),
                                             (["--config", "train"], {})])
 def test_bench_loop_runs_and_prints_the_contract_line(monkeypatch, capsys, argv, overrides):
@@ -79,7 +79,7 @@ def test_bench_loop_runs_and_prints_the_contract_line(monkeypatch, capsys, argv,
     per_step = {"lm_only": 1, "train": 5}.get(argv[1] if "--config" in argv else "", 2)
     assert line["n_gpus"] == 1 and line["steps"] == 3 and line["gpu_launches"] == 3 * per_step and line["value"] > 0
     assert line["config"]["name"] == (argv[1] if "--config" in argv else "fused")
-    assert line["config"]["batches_in_flight"] == (2 if "--streams" in argv else 1)
+    assert line["config"]["batches_in_flight"] == (1 if "--streams" in argv else 2)
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     if "--no-e2e" not in argv:
         e = line["e2e"]
