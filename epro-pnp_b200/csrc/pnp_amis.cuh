@@ -66,18 +66,18 @@ struct RunningLse {
     float top, acc;
     __device__ __forceinline__ void start(float lp) { top = lp; acc = 1.f; }
     __device__ __forceinline__ void add(float lp) {
-        if (lp > top) { acc = fmaf(acc, expf(top - lp), 1.f); top = lp; }
-        else acc += expf(lp - top);
+        if (lp > top) { acc = fmaf(acc, fast_exp(top - lp), 1.f); top = lp; }
+        else acc += fast_exp(lp - top);
     }
-    __device__ __forceinline__ float value() const { return top + logf(acc); }
+    __device__ __forceinline__ float value() const { return top + fast_log(acc); }
 };
 __device__ __forceinline__ float log_add_exp(float a, float b) {
     const float hi = fmaxf(a, b), lo = fminf(a, b);
-    return (lo == -CUDART_INF_F) ? hi : hi + log1pf(expf(lo - hi));
+    return (lo == -CUDART_INF_F) ? hi : hi + fast_log1p(fast_exp(lo - hi));
 }
 
 // ------------------------------------------------------------------------------------------------
-// AMIS loop for the resident object, 6DoF.  sh.pose / sh.cov hold the LM solution.
+// AMIS loop for the resident object, 6DoF.  sh.prop[0] holds the first proposal (the kernel fitted it to the LM solution).
 template <int T>
 __device__ void amis_phase6(const KArgs& a, AmisHead<6, T>& sh, const float* pts4, float* smp, float* cst, float* logp,
                             float* cpart, const Cam& cam, float delta, int obj) {
@@ -89,10 +89,6 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6, T>& sh, const float* pts
     const int st = serial_thread<T>(a);
     float* const logw_out = a.logw + (size_t)obj * M;
     PH_DECL;
-
-    if (tid == st) initial_fit6(sh.pose, sh.cov, p.acg_dispersion, sh.prop[0]);
-    PH_MARK(a, PH_INIT_FIT);
-    __syncthreads();
 
     for (int i = 0; i < I; ++i) {
         // ---- draw, cost, densities of the new samples (one sample per thread and pass; T > 128: the first 128 threads
@@ -180,7 +176,7 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6, T>& sh, const float* pts
 #pragma unroll
             for (int r = 0; r < 15; ++r) acc[r] = 0.f;
             for (int m = tid; m < n; m += T) {
-                const float e = expf(logweight(m) - mx);
+                const float e = fast_exp(logweight(m) - mx);
                 const float* s7 = smp + m * 7;
                 acc[0] += e;
                 acc[1] = fmaf(e, s7[0], acc[1]); acc[2] = fmaf(e, s7[1], acc[2]); acc[3] = fmaf(e, s7[2], acc[3]);
@@ -216,7 +212,7 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6, T>& sh, const float* pts
 #pragma unroll
             for (int r = 0; r < 17; ++r) acc[r] = 0.f;
             for (int m = tid; m < n; m += T) {
-                const float w = expf(logweight(m) - mx) * inv_sum;       // normalised softmax weight
+                const float w = fast_exp(logweight(m) - mx) * inv_sum;       // normalised softmax weight
                 const float* s7 = smp + m * 7;
                 const float d0 = s7[0] - mean[0], d1 = s7[1] - mean[1], d2 = s7[2] - mean[2];
                 acc[11] = fmaf(w * d0, d0, acc[11]); acc[12] = fmaf(w * d0, d1, acc[12]); acc[13] = fmaf(w * d0, d2, acc[13]);
@@ -250,7 +246,7 @@ __device__ void amis_phase6(const KArgs& a, AmisHead<6, T>& sh, const float* pts
             for (int r = 0; r < 11; ++r) acc[r] = 0.f;
             for (int m = tid; m < n; m += T) {
                 const float* q = smp + m * 7 + 3;
-                const float wm = expf(logweight(m) - mx) * inv_sum / fmaxf(quad4(lam_inv, q), p.amis_eps);
+                const float wm = fast_exp(logweight(m) - mx) * inv_sum / fmaxf(quad4(lam_inv, q), p.amis_eps);
                 acc[0] += wm;
                 int idx = 1;
 #pragma unroll
@@ -296,10 +292,6 @@ __device__ void amis_phase4(const KArgs& a, AmisHead<4, T>& sh, const float* pts
     const int st = serial_thread<T>(a);
     float* const logw_out = a.logw + (size_t)obj * M;
     PH_DECL;
-
-    if (tid == st) initial_fit4(sh.pose, sh.cov, p.amis_eps, sh.prop[0]);
-    PH_MARK(a, PH_INIT_FIT);
-    __syncthreads();
 
     for (int i = 0; i < I; ++i) {
         for (int s = tid; s < S; s += NT) {
@@ -361,7 +353,7 @@ __device__ void amis_phase4(const KArgs& a, AmisHead<4, T>& sh, const float* pts
         mx = block_max<T>(mx, sh.red, 0);
         float accB[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int m = tid; m < n; m += T) {
-            const float e = expf(logweight(m) - mx);
+            const float e = fast_exp(logweight(m) - mx);
             const float* s4 = smp + m * 4;
             float sn, cs;
             sincosf(s4[3], &sn, &cs);
@@ -374,7 +366,7 @@ __device__ void amis_phase4(const KArgs& a, AmisHead<4, T>& sh, const float* pts
         const float mean[3] = {accB[1] * inv_sum, accB[2] * inv_sum, accB[3] * inv_sum};
         float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int m = tid; m < n; m += T) {
-            const float w = expf(logweight(m) - mx) * inv_sum;
+            const float w = fast_exp(logweight(m) - mx) * inv_sum;
             const float* s4 = smp + m * 4;
             const float d0 = s4[0] - mean[0], d1 = s4[1] - mean[1], d2 = s4[2] - mean[2];
             tc[0] = fmaf(w * d0, d0, tc[0]); tc[1] = fmaf(w * d0, d1, tc[1]); tc[2] = fmaf(w * d0, d2, tc[2]);
@@ -425,12 +417,26 @@ __global__ void __launch_bounds__(T, T == NT ? EPNP_AMIS_CTAS_PER_SM : 1) amis_k
     float* pts4 = dyn + pl.pts;
     const int obj = blockIdx.x, tid = threadIdx.x;
     PH_DECL;
-    // The LM solution -> shared memory BEFORE this object's sample rows are written: the fused entry point may have
-    // parked the covariance there (cov_stride = M * D).  Plain loads: that memory is written later in this launch.
-    if (tid < PD) sh.pose[tid] = a.pose_opt_in[(size_t)obj * PD + tid];
-    if (tid < DOF * DOF) sh.cov[tid] = a.pose_cov_in[(size_t)obj * a.cov_stride + tid];
-    LoaderT<(T > NT ? AMIS_CHUNK_DENSE : CH)> ld(a, sh.bar, dyn + pl.stage);
-    ld.template load_object<T>(obj, pts4);  // ends with a __syncthreads
+    // Set-up, two things at once.  The serial warp's lane 0 fetches the LM solution and fits the first proposal to it
+    // (EProPnP*.initial_fit: fp64 factorizations, ~12 k cycles on one lane); the other warps meanwhile pull the object's
+    // correspondences through the TMA ring and pack them (named barrier 1 among themselves).  The covariance is read
+    // BEFORE this object's sample rows are written: the fused entry point may have parked it there (cov_stride = M * D);
+    // plain loads, that memory is written later in this launch.
+    const int serial_warp = st >> 5;
+    if ((tid >> 5) == serial_warp) {
+        if (tid == st) {
+#pragma unroll
+            for (int i = 0; i < PD; ++i) sh.pose[i] = a.pose_opt_in[(size_t)obj * PD + i];
+#pragma unroll
+            for (int i = 0; i < DOF * DOF; ++i) sh.cov[i] = a.pose_cov_in[(size_t)obj * a.cov_stride + i];
+            if constexpr (DOF == 6) initial_fit6(sh.pose, sh.cov, a.p.acg_dispersion, sh.prop[0]);
+            else initial_fit4(sh.pose, sh.cov, a.p.amis_eps, sh.prop[0]);
+        }
+    } else {
+        LoaderT<(T > NT ? AMIS_CHUNK_DENSE : CH)> ld(a, sh.bar, dyn + pl.stage);
+        ld.template load_object<T>(obj, pts4, serial_warp);
+    }
+    __syncthreads();
     const Cam cam = load_cam(a, obj);
     const float delta = __ldg(a.delta + obj);
     PH_MARK(a, PH_LOAD);

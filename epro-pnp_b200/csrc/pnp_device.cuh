@@ -64,6 +64,7 @@ inline void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_
     *bar -= (uint64_t)bytes << 32;
     if ((*bar >> 32) == 0) *bar = (uint32_t)*bar + 1u;
 }
+inline void named_barrier(int id, int count) { simt::named_barrier(id, count); }
 struct FastRcp { float operator()(float x) const { return 1.0f / x; } };
 struct FastSqrt { float operator()(float x) const { return sqrtf(x); } };
 struct FastRsqrt { float operator()(float x) const { return 1.0f / sqrtf(x); } };
@@ -94,6 +95,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// barrier `id` (1..15; 0 is __syncthreads) among `count` threads (a multiple of 32) of the CTA
+__device__ __forceinline__ void named_barrier(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 struct FastRcp {
@@ -167,38 +173,45 @@ struct LoaderT {
         tma_load_1d(dst + CHUNK * 3, a.x2d + first * 2, (uint32_t)npts * 8u, b);
         tma_load_1d(dst + CHUNK * 5, a.w2d + first * 2, (uint32_t)npts * 8u, b);
     }
-    // Bring object `obj` into the packed point array (T = threads of the CTA).  Ends with a __syncthreads.
-    template <int T = NT> __device__ void load_object(int obj, float* pts) {
+    // Bring object `obj` into the packed point array (T = threads of the CTA).  Ends with a barrier of the threads that
+    // took part.  skip_warp < 0: all T threads take part (barriers = __syncthreads).  skip_warp = w: warp w does NOT call
+    // this function (it is busy with the object's serial set-up); the other T - 32 threads synchronise on named barrier
+    // 1, and the caller joins everybody with a __syncthreads afterwards.
+    template <int T = NT> __device__ void load_object(int obj, float* pts, int skip_warp = -1) {
         const int tid = threadIdx.x;
+        const bool partial = skip_warp >= 0;
+        const int nthr = partial ? T - 32 : T;
+        const int rank = (partial && tid >= 32 * (skip_warp + 1)) ? tid - 32 : tid;      // index among the participants
+        auto sync = [&]() { if (partial) named_barrier(1, T - 32); else __syncthreads(); };
         if (a.use_tma) {
-            if (tid == 0) {
+            if (rank == 0) {
                 mbar_init(bar + 0, 1);
                 mbar_init(bar + 1, 1);
                 fence_barrier_init();
                 issue(obj, 0);
                 if (nch > 1) issue(obj, 1);
             }
-            __syncthreads();
+            sync();
             for (int k = 0; k < nch; ++k) {
                 const float* st = stage + (k & 1) * SLOT_FLOATS;
                 mbar_wait(bar + (k & 1), (uint32_t)((k >> 1) & 1));
                 const int npts = min(CHUNK, a.N - k * CHUNK);
-                for (int n = tid; n < npts; n += T) {
+                for (int n = rank; n < npts; n += nthr) {
                     const float2 uv = reinterpret_cast<const float2*>(st + CHUNK * 3)[n];
                     const float2 w = reinterpret_cast<const float2*>(st + CHUNK * 5)[n];
                     store_point_padded(pts, k * CHUNK + n, a.N, st[3 * n], st[3 * n + 1], st[3 * n + 2], uv.x, uv.y, w.x, w.y);
                 }
-                __syncthreads();            // slot drained (and, after the last chunk, pts complete)
-                if (tid == 0 && k + 2 < nch) { fence_proxy_async(); issue(obj, k + 2); }
+                sync();                     // slot drained (and, after the last chunk, pts complete)
+                if (rank == 0 && k + 2 < nch) { fence_proxy_async(); issue(obj, k + 2); }
             }
         } else {
             const float* g3 = a.x3d + (size_t)obj * a.N * 3;
             const float* g2 = a.x2d + (size_t)obj * a.N * 2;
             const float* gw = a.w2d + (size_t)obj * a.N * 2;
-            for (int n = tid; n < a.N; n += T)
+            for (int n = rank; n < a.N; n += nthr)
                 store_point_padded(pts, n, a.N, __ldg(g3 + 3 * n), __ldg(g3 + 3 * n + 1), __ldg(g3 + 3 * n + 2),
                                    __ldg(g2 + 2 * n), __ldg(g2 + 2 * n + 1), __ldg(gw + 2 * n), __ldg(gw + 2 * n + 1));
-            __syncthreads();
+            sync();
         }
     }
 };
@@ -300,8 +313,16 @@ template <int K, int T = NT> __device__ __forceinline__ void block_sum(float (&v
         }
     }
     __syncthreads();
+    if constexpr (K > 4) {
+        // lane k of every warp adds the per-warp totals of value k (T / 32 loads); K shuffles hand every lane all K
+        // totals -- instead of K * T / 32 loads per thread
+        const float mine = lane < K ? sum_warp_partials<T>(r, lane) : 0.f;
 #pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = sum_warp_partials<T>(r, k);
+        for (int k = 0; k < K; ++k) v[k] = __shfl_sync(0xffffffffu, mine, k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = sum_warp_partials<T>(r, k);
+    }
 }
 
 template <int T = NT> __device__ __forceinline__ float block_max(float v, float* red, int half) {

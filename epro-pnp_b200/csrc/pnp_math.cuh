@@ -599,29 +599,34 @@ PNP_HD double fast_recip(double x) {
 }
 PNP_HD float fast_recip(float x) { return 1.0f / x; }
 
-// a: packed upper triangle (row-major).  L: full n*n row-major lower factor with the RECIPROCAL of the
-// diagonal stored in Dinv (so the substitutions below multiply instead of divide).  Returns false when
-// a pivot is not positive (LAPACK potrf's failure test: pivot <= 0 or NaN).
+// a: packed upper triangle (row-major).  L: n*n row-major storage of which the LOWER triangle is written (the strict
+// upper part is never read by any caller and stays unset), with the RECIPROCAL of the diagonal stored in Dinv (so the
+// substitutions below multiply instead of divide).  Returns false when a pivot is not positive (LAPACK potrf's
+// failure test: pivot <= 0 or NaN).
 template <int N, class T> PNP_HD bool chol_packed(const T* a, T* L, T* Dinv) {
+    // every loop has the constant trip count N with a compile-time-resolvable guard: loops whose bounds depend on an
+    // outer index are not reliably unrolled, and then L / Dinv are indexed dynamically and live in local memory
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         T d = a[tri(j, j, N)];
 #pragma unroll
-        for (int k = 0; k < j; ++k) d -= L[j * N + k] * L[j * N + k];
+        for (int k = 0; k < N; ++k)
+            if (k < j) d -= L[j * N + k] * L[j * N + k];
         ok = ok && (d > T(0));
         const T inv = inv_sqrt(d);
         Dinv[j] = inv;
         L[j * N + j] = d * inv;
 #pragma unroll
-        for (int i = j + 1; i < N; ++i) {
-            T v = a[tri(j, i, N)];
+        for (int i = 0; i < N; ++i) {
+            if (i > j) {
+                T v = a[tri(j, i, N)];
 #pragma unroll
-            for (int k = 0; k < j; ++k) v -= L[i * N + k] * L[j * N + k];
-            L[i * N + j] = v * inv;
+                for (int k = 0; k < N; ++k)
+                    if (k < j) v -= L[i * N + k] * L[j * N + k];
+                L[i * N + j] = v * inv;
+            }
         }
-#pragma unroll
-        for (int i = 0; i < j; ++i) L[i * N + j] = T(0);
     }
     return ok;
 }
@@ -633,51 +638,19 @@ template <int N, class T> PNP_HD void chol_solve(const T* L, const T* Dinv, cons
     for (int i = 0; i < N; ++i) {
         T v = b[i];
 #pragma unroll
-        for (int k = 0; k < i; ++k) v -= L[i * N + k] * y[k];
+        for (int k = 0; k < N; ++k)
+            if (k < i) v -= L[i * N + k] * y[k];
         y[i] = v * Dinv[i];
     }
 #pragma unroll
-    for (int i = N - 1; i >= 0; --i) {
+    for (int ii = 0; ii < N; ++ii) {
+        const int i = N - 1 - ii;
         T v = y[i];
 #pragma unroll
-        for (int k = i + 1; k < N; ++k) v -= L[k * N + i] * x[k];
+        for (int k = 0; k < N; ++k)
+            if (k > i) v -= L[k * N + i] * x[k];
         x[i] = v * Dinv[i];
     }
-}
-
-// inverse of the lower factor (lower triangular, full storage)
-template <int N, class T> PNP_HD void tri_inverse(const T* L, const T* Dinv, T* Li) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            if (i < j) { Li[i * N + j] = T(0); continue; }
-            if (i == j) { Li[i * N + j] = Dinv[i]; continue; }
-            T v = T(0);
-#pragma unroll
-            for (int k = j; k < i; ++k) v -= L[i * N + k] * Li[k * N + j];
-            Li[i * N + j] = v * Dinv[i];
-        }
-    }
-}
-
-// A^-1 (full, symmetric) = Li^T Li.  Replaces torch.inverse on the SPD matrices of the path.
-template <int N, class T> PNP_HD bool spd_inverse(const T* a_packed, T* inv_full) {
-    T L[N * N], Li[N * N], Dinv[N];
-    const bool ok = chol_packed<N, T>(a_packed, L, Dinv);
-    tri_inverse<N, T>(L, Dinv, Li);
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-#pragma unroll
-        for (int j = i; j < N; ++j) {
-            T v = T(0);
-#pragma unroll
-            for (int k = j; k < N; ++k) v += Li[k * N + i] * Li[k * N + j];
-            inv_full[i * N + j] = v;
-            inv_full[j * N + i] = v;
-        }
-    }
-    return ok;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1007,6 +980,31 @@ PNP_HD void proposal_draw6(const Proposal6& p, const float* n3, float chi2, cons
     else { smp[3] = g0 / n; smp[4] = g1 / n; smp[5] = g2 / n; smp[6] = g3 / n; }
 }
 
+// log / exp of the proposal densities and of the weight bookkeeping: the special-function unit on the device (lg2.approx /
+// ex2.approx: absolute error ~4e-7 of the logarithm, <= ~30 ulp of an exponential of |x| < 20 -- the log-weights these
+// feed are compared at 1e-4 of a scale of several hundred), libm in the host build.
+PNP_HD float fast_log(float x) {
+#if defined(__CUDA_ARCH__)
+    return __logf(x);
+#else
+    return logf(x);
+#endif
+}
+PNP_HD float fast_log1p(float x) {
+#if defined(__CUDA_ARCH__)
+    return __logf(1.0f + x);
+#else
+    return log1pf(x);
+#endif
+}
+PNP_HD float fast_exp(float x) {
+#if defined(__CUDA_ARCH__)
+    return __expf(x);
+#else
+    return expf(x);
+#endif
+}
+
 // log q(sample) under one proposal  (pyro MultivariateStudentT.log_prob + distributions.py:32-40)
 PNP_HD float proposal_logpdf6(const Proposal6& p, const float* smp) {
     const float d0 = smp[0] - p.mu[0], d1 = smp[1] - p.mu[1], d2 = smp[2] - p.mu[2];
@@ -1019,7 +1017,7 @@ PNP_HD float proposal_logpdf6(const Proposal6& p, const float* smp) {
     const float z2 = (smp[5] - p.lr[3] * z0 - p.lr[4] * z1) * p.ilr[2];
     const float z3 = (smp[6] - p.lr[6] * z0 - p.lr[7] * z1 - p.lr[8] * z2) * p.ilr[3];
     const float mr = z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3;
-    return (-3.0f * log1pf(mt * (1.0f / 3.0f)) + p.ct) + (-2.0f * logf(mr) + p.cr);
+    return (-3.0f * fast_log1p(mt * (1.0f / 3.0f)) + p.ct) + (-2.0f * fast_log(mr) + p.cr);
 }
 
 // q^T Lambda^-1 q for the ACG fixed-point iteration (epropnp.py:335-337)
@@ -1130,8 +1128,8 @@ PNP_HD float proposal_logpdf4(const Proposal4& p, const float* smp) {
     const float mt = y0 * y0 + y1 * y1 + y2 * y2;
     const float vm = p.kappa * cosf(smp[3] - p.mode) + p.cvm;
     const float hi = fmaxf(vm, PNP_LOG_UNIFORM_MIX), lo = fminf(vm, PNP_LOG_UNIFORM_MIX);
-    const float rot = hi + log1pf(expf(lo - hi));
-    return (-3.0f * log1pf(mt * (1.0f / 3.0f)) + p.ct) + rot;
+    const float rot = hi + fast_log1p(fast_exp(lo - hi));
+    return (-3.0f * fast_log1p(mt * (1.0f / 3.0f)) + p.ct) + rot;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -94,6 +94,15 @@ inline void syncthreads() {
     while (s.bar_gen == gen) yield();
 }
 
+// bar.sync id, count: `count` threads of the CTA meet on barrier `id` (the kernels only use it with fixed sets)
+inline void named_barrier(int id, int count) {
+    static int cnt[16];
+    static unsigned gen[16];
+    const unsigned g = gen[id];
+    if (++cnt[id] >= count) { cnt[id] = 0; ++gen[id]; return; }
+    while (gen[id] == g) yield();
+}
+
 inline void syncwarp() {
     BlockState& s = state();
     const int w = s.cur >> 5;
