@@ -32,7 +32,7 @@ constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 // Phase timers (profiling build: -DEPNP_PHASE_TIMERS; tools/phase_profile.py).  The serial thread `st` of every AMIS CTA
 // adds the clock64() cycles it spent in each phase; the production build compiles them away.
-enum Phase { PH_LOAD = 0, PH_INIT_FIT, PH_DRAW_SWEEP, PH_LOGP_OLD, PH_WEIGHTS, PH_REFIT_SUMS, PH_REFIT_FINISH, PH_OUTPUT, PH_COUNT };
+enum Phase { PH_LOAD = 0, PH_DRAW_SWEEP, PH_LOGP_OLD, PH_WEIGHTS, PH_REFIT_SUMS, PH_REFIT_FINISH, PH_OUTPUT, PH_COUNT };
 #ifdef EPNP_PHASE_TIMERS
 #define PH_DECL long long ph_t = clock64()
 #define PH_MARK(a_, which)                                                                     \

@@ -9,8 +9,10 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer to contiguous row-major fp32 unless the name ends in _host;
- *   - the caller owns and allocates every buffer; the library keeps no state, allocates nothing,
- *     is re-entrant, and only enqueues work on `stream` (a cudaStream_t passed as void*);
+ *   - the caller owns and allocates every buffer; the library allocates no memory, is re-entrant, and only enqueues work
+ *     on `stream` (a cudaStream_t passed as void*).  Per-host-thread state, exactly two items: the cudaError_t of the
+ *     last failed call (epnp_last_cuda_error) and the four helper streams of epnp_lm_amis_fused_host_f32, created on that
+ *     thread's first host-buffer call and kept for its lifetime;
  *   - return value: EPNP_OK or a negative EPNP_ERR_* code (never throws, never aborts);
  *     CUDA launch errors come back as EPNP_ERR_CUDA (epnp_last_cuda_error() has the cudaError_t);
  *   - B = objects, N = correspondences per object, D = 7 (dof 6: x y z w i j k) or 4 (dof 4:
@@ -144,9 +146,12 @@ int epnp_amis_f32(const float* x3d, const float* x2d, const float* w2d, const fl
                   float* pose_samples /*(B,M,D)*/, float* logw /*(B,M)*/, float* proposals,
                   int B, int N, const EpnpParams* p, void* stream);
 
-/* monte_carlo_forward with pose_init given and no init solver (epropnp.py:87-196 with
- * force_init_solve=False): LM solve + covariance + AMIS in ONE launch, one CTA per object, the
- * correspondence set staged once into shared memory (TMA bulk copies) and never re-read from HBM. */
+/* monte_carlo_forward with pose_init given and no init solver (epropnp.py:87-196 with force_init_solve=False):
+ * LM solve + covariance + AMIS in ONE call = two launches on `stream`, no host round trip -- the warp-per-object LM
+ * kernel (epnp_lm_solve_f32's), then the CTA-per-object AMIS kernel (epnp_amis_f32's); each stages the object's
+ * correspondence set once into shared memory by TMA bulk copies.  (As a single kernel the LM half ran latency-bound:
+ * DESIGN.md section 0.)  pose_cov [opt]: when NULL, the covariance travels between the two kernels through the first
+ * dof^2 floats of each object's -- not yet written -- pose_samples rows (needs M * D >= dof^2).                      */
 int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
                            const float* lb, const float* ub, const float* delta, const float* pose_init,
                            const float* noise_normal, const float* noise_chi2, const float* noise_rot,
@@ -156,10 +161,12 @@ int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d,
                            int B, int N, const EpnpParams* p, void* stream);
 
 /* Multi-GPU form of epnp_lm_amis_fused_f32 (one process per GPU, one NVLink / NVSwitch node): the solve AND the gather
- * of its small results in one kernel.  Every CTA, when its object is finished, additionally stores the object's
+ * of its small results in one kernel (the AMIS kernel).  Every CTA, when its object is finished, additionally stores the object's
  * pose_opt row and its M log-weights into row (obj_offset + b) of `n_peers` (<= 8) full-batch buffers that live in
- * OTHER GPUs' memory -- peer_logw[r] (B_total, M), peer_pose[r] (B_total, D), device pointers obtained by the caller
- * through CUDA IPC / peer access -- with plain stores over NVLink, object by object underneath the remaining math.
+ * OTHER GPUs' memory -- peer_logw[r] (B_total, M), peer_pose[r] (B_total, D), device pointers the caller obtained with
+ * cudaIpcOpenMemHandle(..., cudaIpcMemLazyEnablePeerAccess) WHILE THIS DEVICE WAS CURRENT (a mapping opened under the
+ * exporting device's index is not dereferenceable by this device's kernels) -- with plain stores over NVLink, object
+ * by object underneath the remaining math.
  * There is no gather kernel and no copy afterwards (what replaces the NCCL all-gather of SURVEY.md section 8e); the
  * caller needs one rendezvous of the ranks before it reads its own full-batch buffer.  pose_opt / logw are the LOCAL
  * outputs as before -- typically the local slice [obj_offset, obj_offset + B) of this rank's own full-batch buffers.
@@ -209,7 +216,8 @@ int epnp_mc_lse_backward_f32(const float* logw, const float* lse, const float* g
  * `stream`, in `n_chunks` object chunks through a copy-in / solve / copy-out pipeline (helper streams owned by
  * the calling host thread, created on first use -- the only resource the library keeps).  n_chunks = 0 cuts the
  * batch at whole waves of resident CTAs (SMs x CTAs per SM objects per chunk, as few waves per chunk as the limit of
- * 64 chunks allows); n_chunks >= 1 asks for that many equal chunks (4 for B = 4096 is the measured configuration).
+ * 64 chunks allows); n_chunks >= 1 asks for that many equal chunks (8 for B = 4096, two calls in flight, is the measured
+ * configuration).
  * workspace: device memory of at least epnp_fused_workspace_bytes(B, N, p) bytes.
  * Outputs [opt] as above (pose_samples_host may be NULL to skip the largest copy).              */
 size_t epnp_fused_workspace_bytes(int B, int N, const EpnpParams* p);

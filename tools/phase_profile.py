@@ -1,7 +1,6 @@
 #!/usr/bin/env python
-"""Per-phase cycle breakdown of the fused kernel (profiling build with clock64() timers on thread 0 of
-every CTA).  Usage on a GPU box:  python tools/phase_profile.py [B] [N] [M] [variant]
-`variant` = a name from epropnp_b200.build.EXPERIMENTS (e.g. six_ctas): profile that build instead of the shipped one."""
+"""Per-phase cycle breakdown of the AMIS kernel (profiling build with clock64() timers on the serial thread of every
+CTA).  Usage on a GPU box:  python tools/phase_profile.py [B] [N] [M]"""
 import ctypes
 import os
 import subprocess
@@ -13,16 +12,14 @@ import torch  # noqa: E402
 from epropnp_b200 import build, capi, native  # noqa: E402
 from epropnp_b200.synth import make_problem  # noqa: E402
 
-PHASES = ["load", "lm_eval", "lm_serial", "cov", "init_fit", "draw+sweep", "logp_old", "weights", "refit_sums",
-          "refit_finish", "output"]
+PHASES = ["load + first fit", "draw+sweep", "logp_old", "weights", "refit_sums", "refit_finish", "output"]
 
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     N = int(sys.argv[2]) if len(sys.argv) > 2 else 512
     M = int(sys.argv[3]) if len(sys.argv) > 3 else 512
-    variant = sys.argv[4] if len(sys.argv) > 4 else None
-    extra = build.EXPERIMENTS[variant] if variant else []
+    extra = []
     prof_lib = os.path.join(build.LIB_DIR, "libepropnp_b200_prof.so")
     cmd = [build._nvcc()] + build.NVCC_FLAGS + extra + ["-DEPNP_PHASE_TIMERS", "-o", prof_lib, os.path.join(build.CSRC, "pnp_kernels.cu")]
     subprocess.run(cmd, check=True)
@@ -44,7 +41,7 @@ def main():
     lib.epnp_debug_set_phase_buffer(None)
     c = buf.cpu().tolist()[:len(PHASES)]
     tot = sum(c)
-    print(f"B={B} N={N} M={M} build={variant or 'shipped'}: serial-lane cycles per object, by phase (sum over CTAs / B)")
+    print(f"B={B} N={N} M={M}: cycles of the AMIS kernel's serial thread per object, by phase (sum over CTAs / B)")
     for name, v in zip(PHASES, c):
         print(f"  {name:14s} {v / B:10.0f} cycles  {100.0 * v / tot:5.1f} %")
     print(f"  {'total':14s} {tot / B:10.0f} cycles")
