@@ -57,9 +57,11 @@ CONFIGS = {
                        "MonteCarloPoseLoss, backward to x3d / x2d / w2d"),
 }
 E2E_CHUNKS = int(os.environ.get("EPNP_E2E_CHUNKS", "8"))   # object chunks of the host-buffer pipeline (0 = whole waves)
-# host-buffer calls in flight: consecutive steps alternate between this many (stream, workspace, pinned result set)
-# triples, so step i+1's upload runs under step i's solve / download (a double-buffered input pipeline)
-E2E_LANES = max(1, int(os.environ.get("EPNP_E2E_LANES", "2")))
+# host-buffer calls in flight: consecutive steps rotate over this many (stream, workspace, pinned result set) triples, so
+# step i+1's upload runs under step i's solve and step i-1's download.  3 calls x 8 chunks was the configuration with the
+# smallest box-to-box spread (2.0 M objects/s on both boxes measured; profiles/r2_e2e_sweep*.txt -- the upload bandwidth
+# of pinned memory varies between 20 and 55 GB/s from box to box and size to size, which is what e2e mostly measures)
+E2E_LANES = max(1, int(os.environ.get("EPNP_E2E_LANES", "3")))
 WARM_SECONDS = 0.5            # minimum duration of back-to-back warm-up launches before the timed region
 # allocate the pinned host buffers while the thread is bound to the CPUs NVML reports as local to the GPU (first touch
 # puts the pages on the GPU's NUMA node; a remote node costs upload bandwidth)

@@ -6,7 +6,8 @@
 //     pre-multiplied projection K[R|t] (points are shared-memory broadcasts, packed fp32x2 arithmetic), evaluates the
 //     proposal densities it needs; the mixture density of a sample is kept as ONE running log-sum-exp;
 //   * a log-weight is -cost - (lse - log count): it is recomputed where needed instead of stored, and the staging ring
-//     lives inside the (not yet written) sample buffer, so a CTA needs 36.1 KB at N = M = 512 and SIX CTAs share an SM;
+//     lives inside the (not yet written) sample buffer, so a CTA needs 36.1 KB at N = M = 512; five CTAs share an SM
+//     (96 registers per thread, no spills);
 //   * the proposal refit is four block reductions (transposed butterflies) + a short chain on one lane.
 // The LM solution (pose, covariance) comes from global memory: lm_warp_kernel wrote it just before (same stream).
 //
@@ -18,9 +19,10 @@
 
 namespace {
 
-#if !defined(EPNP_AMIS_CTAS_PER_SM)
-#define EPNP_AMIS_CTAS_PER_SM 6         // 80 registers; 6 x (36.1 KB + 1 KB reserved) of the SM's 228 KB at N = M = 512
-#endif
+// Resident CTAs per SM the 128-thread kernel is compiled for.  Shared memory (36.1 KB at N = M = 512) would allow six at 80
+// registers, but then the sweep spills; measured on B200 after the serial phases had been trimmed: five CTAs at 96
+// registers (no spill) 0.933 ms per 4096 objects, six at 80 registers 0.951 ms (profiles/r2_split_probe.jsonl).
+constexpr int AMIS_CTAS_PER_SM = 5;
 
 template <int DOF> struct ProposalOf;
 template <> struct ProposalOf<6> { typedef Proposal6 type; };
@@ -405,7 +407,7 @@ struct PushArgs {
 
 // One object per CTA of T threads (blockIdx.x = object).
 template <int DOF, bool PUSH, int T>
-__global__ void __launch_bounds__(T, T == NT ? EPNP_AMIS_CTAS_PER_SM : 1) amis_kernel(const KArgs a, const PushArgs push) {
+__global__ void __launch_bounds__(T, T == NT ? AMIS_CTAS_PER_SM : 1) amis_kernel(const KArgs a, const PushArgs push) {
     EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
     AmisHead<DOF, T>& sh = *reinterpret_cast<AmisHead<DOF, T>*>(smem_raw);
     float* dyn = reinterpret_cast<float*>(smem_raw);

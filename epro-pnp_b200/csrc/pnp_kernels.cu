@@ -4,7 +4,7 @@
 //                                    TMA-staged into the warp's shared memory, 16 points per lane, shuffle-only reduction,
 //                                    6x6 damped Cholesky + SE(3) retraction + trust region on lane 0, no block barrier.
 //   amis_kernel (pnp_amis.cuh)       the AMIS Monte-Carlo loop, ONE CTA per object: TMA ring -> packed pair records, one
-//                                    thread per sample, packed fp32x2 cost sweep, refits as block reductions; six CTAs per SM.
+//                                    thread per sample, packed fp32x2 cost sweep, refits as block reductions; five CTAs per SM.
 //   epnp_lm_amis_fused_f32           = lm_warp_kernel, then amis_kernel, on the caller's stream (no host round trip); the
 //                                    split is what a measurement asked for: as one kernel the LM half ran latency-bound at
 //                                    4 points per thread between block barriers.

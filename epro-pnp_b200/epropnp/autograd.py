@@ -59,8 +59,10 @@ class _MonteCarloForward(torch.autograd.Function):
         cost = out["cost"] if want_cost else x3d.new_zeros(0)
         ci = cost_init if cost_init is not None else x3d.new_zeros(0)
         dt = x3d.dtype
-        ctx.mark_non_differentiable(out["pose_opt"], cost, out["pose_samples"])
-        return out["pose_opt"].to(dt), cost.to(dt), out["pose_samples"].to(dt), out["logw"].to(dt), ci.to(dt)
+        # cast FIRST, then mark the tensors that are actually returned (for non-fp32 inputs .to() makes new tensors)
+        pose_opt, cost, samples = out["pose_opt"].to(dt), cost.to(dt), out["pose_samples"].to(dt)
+        ctx.mark_non_differentiable(pose_opt, cost, samples)
+        return pose_opt, cost, samples, out["logw"].to(dt), ci.to(dt)
 
     @staticmethod
     def backward(ctx, g_pose, g_cost, g_samples, g_logw, g_cost_init):

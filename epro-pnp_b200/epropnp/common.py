@@ -61,12 +61,18 @@ def evaluate_pnp(x3d, x2d, w2d, pose, camera, cost_fun,
     clip_jac = kwargs.pop("clip_jac", True)
     if kwargs:
         raise TypeError(f"unexpected arguments {sorted(kwargs)}")
-    if _needs_grad(x3d, x2d, w2d, pose):
+    if _needs_grad(x3d, x2d, w2d, pose, getattr(cost_fun, "delta", None)):
+        if out_jacobian is not False or out_residual is not False or pose.requires_grad:
+            # differentiable residual / Jacobian, or gradients w.r.t. the pose (LMSolver.gn_step under autograd,
+            # reference common.py:67-100): the torch composite of the same two methods the reference calls
+            x2d_proj, jac_cam = camera.project(x3d, pose, out_jac=(out_jacobian is not False), clip_jac=clip_jac)
+            residual, cost, jac = cost_fun.compute(x2d_proj, x2d, w2d, jac_cam=jac_cam, out_residual=(out_residual is not False),
+                                                   out_cost=(out_cost is not False), out_jacobian=(out_jacobian is not False))
+            return ((_store(out_residual, residual) if out_residual is not False else None),
+                    (_store(out_cost, cost) if out_cost is not False else None),
+                    (_store(out_jacobian, jac) if out_jacobian is not False else None))
         from .autograd import evaluate_cost_autograd
-        if out_jacobian is not False or out_residual is not False:
-            raise NotImplementedError("differentiable residual/Jacobian outputs are not provided; "
-                                      "only the cost is differentiable (as used by the reference's losses)")
-        cost = evaluate_cost_autograd(x3d, x2d, w2d, pose, camera, cost_fun)
+        cost = evaluate_cost_autograd(x3d, x2d, w2d, pose, camera, cost_fun)       # native forward + native backward
         return None, (_store(out_cost, cost) if out_cost is not False else None), None
 
     dof = 4 if pose.size(-1) == 4 else 6

@@ -53,6 +53,15 @@ class Problem:
             raise ValueError("x3d/x2d/w2d must be (num_obj, num_pts, 3|2|2)")
         self.B, self.N = x3d.shape[0], x3d.shape[1]
         self.device = x3d.device
+        # the kernels read B*N*{3,2,2} floats through raw pointers: anything else must be caught here
+        if x3d.shape[2] != 3 or tuple(x2d.shape) != (self.B, self.N, 2):
+            raise ValueError(f"x3d must be (B, N, 3) and x2d (B, N, 2); got {tuple(x3d.shape)}, {tuple(x2d.shape)}")
+        if w2d.shape[:2] != x2d.shape[:2] or w2d.shape[2] not in (1, 2):
+            raise ValueError(f"w2d must be (B, N, 2) (or (B, N, 1), broadcast); got {tuple(w2d.shape)}")
+        if x2d.device != self.device or w2d.device != self.device:
+            raise ValueError("x3d, x2d and w2d must live on one device")
+        if w2d.shape[2] == 1:
+            w2d = w2d.expand(self.B, self.N, 2)          # the reference's arithmetic accepts a broadcast weight
         self.x3d, self.x2d, self.w2d = _f32c(x3d), _f32c(x2d), _f32c(w2d)
         self.cam = _cam(cam_mats, self.B, self.device)
         self.lb, self.ub = _bounds(lb, ub, self.B, self.device)
@@ -80,6 +89,7 @@ def adaptive_delta(x2d, w2d, relative_delta):
 def evaluate_cost(prob: Problem, poses, dof, z_min):
     """poses (S, B, D) -> cost (S, B)."""
     S = poses.shape[0]
+    _check_pose(poses, (S, prob.B), 7 if dof == 6 else 4, "poses")
     poses = _f32c(poses)
     out = prob.empty(S, prob.B)
     with torch.cuda.device(prob.device):
@@ -101,10 +111,16 @@ def evaluate_full(prob: Problem, pose, dof, z_min, huber_eps, clip_jac, want_res
     return res, cost, jac
 
 
+def _check_pose(pose, lead, D, what):
+    if tuple(pose.shape) != tuple(lead) + (D,):
+        raise ValueError(f"{what} must be {tuple(lead) + (D,)}; got {tuple(pose.shape)}")
+
+
 def lm_solve(prob: Problem, pose_init, params, want_cov=False, want_cost=False, want_plus=False,
              want_cost_init=False):
     D = 7 if params.dof == 6 else 4
     B = prob.B
+    _check_pose(pose_init, (B,), D, "pose_init")
     pose_init = _f32c(pose_init)
     out = dict(pose_opt=prob.empty(B, D),
                pose_cov=prob.empty(B, params.dof, params.dof) if want_cov else None,
@@ -179,6 +195,7 @@ def lm_amis_fused(prob: Problem, pose_init, params, noise=None, seed=0, obj_offs
                   want_plus=False, want_cost_init=True, want_proposals=False, want_cov=True):
     D = 7 if params.dof == 6 else 4
     B, M, I = prob.B, params.mc_samples, params.mc_iter
+    _check_pose(pose_init, (B,), D, "pose_init")
     pose_init = _f32c(pose_init)
     out = dict(pose_opt=prob.empty(B, D), pose_cov=prob.empty(B, params.dof, params.dof) if want_cov else None,
                cost=prob.empty(B) if want_cost else None,

@@ -103,5 +103,9 @@ def test_evaluate_pnp_cost_is_differentiable(cuda_device):
     fd = (cp - cm) / (2 * eps)
     an = (x3d.grad.double() * v.double()).sum()
     assert abs(fd - an) / abs(an) < 3e-2
-    with pytest.raises(NotImplementedError):
-        evaluate_pnp(x3d, t("x2d"), t("w2d"), poses.requires_grad_(True), camera, cost_fun, out_cost=True)
+    # gradients with respect to the POSE: the torch composite (reference common.py:67-100 is differentiable there too)
+    pg = poses.clone().requires_grad_(True)
+    c2 = evaluate_pnp(x3d.detach(), t("x2d"), t("w2d"), pg, camera, cost_fun, out_cost=True)[1]
+    assert torch.allclose(c2.detach(), cost.detach(), rtol=2e-4, atol=1e-3)
+    c2.sum().backward()
+    assert pg.grad is not None and torch.isfinite(pg.grad).all() and pg.grad.abs().sum() > 0

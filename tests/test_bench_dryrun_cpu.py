@@ -84,7 +84,7 @@ def test_bench_loop_runs_and_prints_the_contract_line(monkeypatch, capsys, argv,
     if "--no-e2e" not in argv:
         e = line["e2e"]
         assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] > 0
-        assert e["calls_in_flight"] == overrides.get("E2E_LANES", 2)
+        assert e["calls_in_flight"] == overrides.get("E2E_LANES", 3)
         assert set(e["step_interval_ms"]) == {"min", "median", "max"}
 
 

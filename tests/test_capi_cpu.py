@@ -192,3 +192,28 @@ def test_validated_kernels_are_bit_identical():
     spec.loader.exec_module(mod)
     changed, _ = mod.compare(build.build_library())
     assert changed == []
+
+
+def test_problem_rejects_wrong_shapes():
+    import torch
+    from epropnp_b200 import native
+
+    class _T(torch.Tensor):
+        pass
+    x3d, x2d, w2d = torch.zeros(2, 8, 3), torch.zeros(2, 8, 2), torch.zeros(2, 8, 2)
+    orig = native._need_cuda
+    native._need_cuda = lambda t, what: None
+    try:
+        cam = torch.eye(3).expand(2, 3, 3)
+        with pytest.raises(ValueError):
+            native.Problem(x3d, torch.zeros(2, 7, 2), w2d, cam, None, None, 1.0)          # N mismatch
+        with pytest.raises(ValueError):
+            native.Problem(torch.zeros(2, 8, 2), x2d, w2d, cam, None, None, 1.0)          # x3d last dim
+        with pytest.raises(ValueError):
+            native.Problem(x3d, x2d, torch.zeros(2, 8, 3), cam, None, None, 1.0)          # w2d last dim
+        p = native.Problem(x3d, x2d, torch.ones(2, 8, 1), cam, None, None, 1.0)           # broadcast weight is expanded
+        assert tuple(p.w2d.shape) == (2, 8, 2) and p.w2d.is_contiguous()
+        with pytest.raises(ValueError):
+            native.lm_solve(p, torch.zeros(2, 4), native.default_params(6))                # pose of the wrong width
+    finally:
+        native._need_cuda = orig

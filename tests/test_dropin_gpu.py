@@ -72,8 +72,12 @@ def test_evaluate_pnp_semantics(cuda_device):
     # clip_jac=False keeps gradients of clamped points
     j_noclip = evaluate_pnp(x3d, x2d, w2d, pose_init, camera, cost_fun, out_jacobian=True, clip_jac=False)[2]
     assert (j_noclip != 0).sum() > (jac != 0).sum()
-    with pytest.raises(NotImplementedError):      # only the cost is differentiable, like the reference's losses use it
-        evaluate_pnp(x3d.clone().requires_grad_(True), x2d, w2d, pose_init, camera, cost_fun, out_jacobian=True)
+    # grad-requiring inputs + a Jacobian request: the torch composite (what LMSolver.gn_step needs under autograd)
+    xg = x3d.clone().requires_grad_(True)
+    rg, _, jg = evaluate_pnp(xg, x2d, w2d, pose_init, camera, cost_fun, out_jacobian=True, out_residual=True)
+    assert jg.grad_fn is not None and err_vs(jg.detach().cpu().numpy(), jac.cpu().numpy()) < 1e-5
+    rg.square().sum().backward()
+    assert xg.grad is not None and xg.grad.abs().sum() > 0
 
 
 @pytest.mark.parametrize("name", golden_names("mc6"))

@@ -230,3 +230,24 @@ def test_empty_batch_stays_in_the_autograd_graph():
         loss.backward()
         for t in (x3d, x2d, w2d):
             assert t.grad is not None and t.grad.shape == t.shape
+
+
+def test_evaluate_pnp_differentiable_outputs_go_through_the_composite(monkeypatch):
+    """evaluate_pnp with grad-requiring inputs and a residual / Jacobian request (or a grad-requiring pose): the torch
+    composite of camera.project + cost_fun.compute, as LMSolver.gn_step needs under autograd (reference common.py:67-100)
+    -- values equal the oracle's, and gradients flow to x3d and to the pose."""
+    import torch
+    pc = make_problem(3, 24, seed=9)
+    x3d = pc["x3d"].to(D).requires_grad_(True)
+    x2d, w2d = pc["x2d"].to(D), pc["w2d"].to(D)
+    pose = pc["pose_init"].to(D).requires_grad_(True)
+    camera = PerspectiveCamera(cam_mats=pc["cam_mats"].to(D))
+    cost_fun = AdaptiveHuberPnPCost(relative_delta=0.5)
+    cost_fun.set_param(x2d, w2d)
+    res, cost, jac = evaluate_pnp(x3d, x2d, w2d, pose, camera, cost_fun, out_jacobian=True, out_residual=True, out_cost=True)
+    from oracle import pnp_oracle as orc
+    e = orc.evaluate(x3d.detach(), x2d, w2d, pose.detach(), orc.Camera(pc["cam_mats"].to(D), 0.1), cost_fun.delta.detach(), want_jac=True)
+    assert torch.allclose(res, e["residual"], atol=1e-9) and torch.allclose(jac, e["jac"], atol=1e-9)
+    assert torch.allclose(cost, e["cost"], atol=1e-9)
+    (cost.sum() + res.square().sum()).backward()
+    assert x3d.grad is not None and pose.grad is not None and x3d.grad.abs().sum() > 0 and pose.grad.abs().sum() > 0
