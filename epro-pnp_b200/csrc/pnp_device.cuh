@@ -375,25 +375,30 @@ __device__ __forceinline__ float2 pair_cost(const float2 (&P2)[12], const Cam& c
 // pair records [j0, j1)
 template <bool BOUNDED>
 __device__ __forceinline__ float sweep_cost(const float4* pts4, int j0, int j1, const float* P, const Cam& cam, float delta) {
+    // point pairs in flight per thread.  Measured with the resident CTAs per SM (AMIS kernel, ms per 4096 objects,
+    // profiles/r2_split_probe.jsonl): U=4 / 5 CTAs 0.933, U=6 / 5 0.943, U=3 / 6 0.955, U=4 / 4 0.990, U=8 / 4 1.003, U=2 / 5 1.023
+    constexpr int U = 4;
     float2 P2[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) P2[k] = splat(P[k]);
-    float2 c0 = splat(0.f), c1 = splat(0.f), c2 = splat(0.f), c3 = splat(0.f);
+    float2 c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = splat(0.f);
     const int npair = j1;
     int j = j0;
-    for (; j + 4 <= npair; j += 4) {            // 8 points in flight per thread
+    for (; j + U <= npair; j += U) {
         const float4* q = pts4 + 4 * j;
-        c0 = pair_cost<BOUNDED>(P2, cam, delta, c0, q[0], q[1], q[2], q[3]);
-        c1 = pair_cost<BOUNDED>(P2, cam, delta, c1, q[4], q[5], q[6], q[7]);
-        c2 = pair_cost<BOUNDED>(P2, cam, delta, c2, q[8], q[9], q[10], q[11]);
-        c3 = pair_cost<BOUNDED>(P2, cam, delta, c3, q[12], q[13], q[14], q[15]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) c[u] = pair_cost<BOUNDED>(P2, cam, delta, c[u], q[4 * u], q[4 * u + 1], q[4 * u + 2], q[4 * u + 3]);
     }
     for (; j < npair; ++j) {
         const float4* q = pts4 + 4 * j;
-        c0 = pair_cost<BOUNDED>(P2, cam, delta, c0, q[0], q[1], q[2], q[3]);
+        c[0] = pair_cost<BOUNDED>(P2, cam, delta, c[0], q[0], q[1], q[2], q[3]);
     }
-    c0 = __fadd2_rn(c0, c2); c1 = __fadd2_rn(c1, c3);
-    return (c0.x + c0.y) + (c1.x + c1.y);
+    float2 t = c[0];
+#pragma unroll
+    for (int u = 1; u < U; ++u) t = __fadd2_rn(t, c[u]);
+    return t.x + t.y;
 }
 
 // cost of `pose` over the pair records [j0, j1)
