@@ -113,7 +113,8 @@ def main():
         from epropnp.camera import PerspectiveCamera
         from epropnp.cost_fun import AdaptiveHuberPnPCost
         from epropnp.levenberg_marquardt import RSLMSolver
-        for dof, B, N, npts, P, K in ((6, b(256), 64, 8, 128, 5), (4, b(512), 64, 16, 64, 3)):
+        for dof, B, N, npts, P, K in ((6, b(256), 64, 8, 128, 5), (4, b(512), 64, 16, 64, 3), (6, b(4096), n(512), 16, 64, 3),
+                                      (6, b(4096), n(512), 8, 128, 3)):
             P = max(2, P // 32) if TOY else P
             pc = {k: v.to(dev) for k, v in make_problem(B, N, seed=3, dof=dof).items()}
             camera = PerspectiveCamera(cam_mats=pc["cam_mats"])
@@ -124,7 +125,7 @@ def main():
             for flag, key in (("0", "ms_unfused"), ("1", "ms_fused")):
                 os.environ["EPNP_FUSED_RSLM"] = flag
                 row[key] = timed(lambda: solver.solve(pc["x3d"], pc["x2d"], pc["w2d"], camera, cost_fun), iters=10)
-            os.environ["EPNP_FUSED_RSLM"] = "0"
+            os.environ["EPNP_FUSED_RSLM"] = "1"
             out.append(row)
     # derivative-regularisation branch: pose_opt_plus forward + backward, torch composite vs native kernel
     if os.environ.get("EPNP_BENCH_GN_PLUS"):
@@ -148,7 +149,7 @@ def main():
             for flag, key in (("0", "ms_composite"), ("1", "ms_native")):
                 os.environ["EPNP_NATIVE_GN_STEP"] = flag
                 row[key] = timed(step, iters=10)
-            os.environ["EPNP_NATIVE_GN_STEP"] = "0"
+            os.environ["EPNP_NATIVE_GN_STEP"] = "1"
             out.append(row)
     # the step after the path: Monte-Carlo pose loss forward + backward and the Det MC score, torch composite on the
     # layer's (M, B) views vs the native one-pass epilogue
@@ -170,7 +171,7 @@ def main():
             for flag, key in (("0", "ms_composite"), ("1", "ms_native")):
                 os.environ["EPNP_NATIVE_MC_EPILOGUE"] = flag
                 row[key] = timed(step, iters=20)
-            os.environ["EPNP_NATIVE_MC_EPILOGUE"] = "0"
+            os.environ["EPNP_NATIVE_MC_EPILOGUE"] = "1"
             out.append(row)
     for r in out:
         print(json.dumps(r))

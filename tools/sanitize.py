@@ -29,7 +29,7 @@ for dof, N, B, bounded in ((6, 64, 5, False), (6, 130, 3, True), (6, 51, 4, Fals
     native.evaluate_full(prob, d["pose_init"], dof, 0.1, 1e-10, True, True, True, True)
     g = native.cost_backward(prob, dof, 0.1, out["pose_samples"], torch.randn(B, 128, device=dev),
                              d["pose_init"].reshape(B, 1, D), torch.randn(B, 1, device=dev))
-    if os.environ.get("EPNP_SANITIZE_EXPERIMENTAL"):       # the kernels that have not had a hardware run yet
+    if True:
         ep = native.mc_epilogue(out["logw"], out["pose_samples"], out["pose_opt"], cost_target=torch.rand(B, device=dev),
                                 want_lse=True, want_loss=True, want_weights=True, want_score=True)
         native.mc_lse_backward(out["logw"], ep["lse"], torch.randn(B, device=dev))
@@ -41,6 +41,17 @@ for dof, N, B, bounded in ((6, 64, 5, False), (6, 130, 3, True), (6, 51, 4, Fals
         torch.cuda.synchronize()
         assert torch.equal(full_lw[1][2:2 + B], full_lw[0][2:2 + B]) and torch.equal(full_ps[2][2:2 + B], full_ps[0][2:2 + B])
         assert torch.equal(full_lw[0][2:2 + B], out["logw"]) and not full_lw[1][:2].any() and not full_lw[1][2 + B:].any()
+        P, n = 5, 6
+        inds = torch.stack([torch.stack([torch.randperm(N, device=dev)[:n] for _ in range(B)]) for _ in range(P)])
+        native.rslm(prob, inds, d["pose_init"][None].repeat(P, 1, 1), native.default_params(dof, lm_iter=2), want_all=True)
+        native.gn_plus_backward(prob, out["pose_opt"], torch.randn(B, D, device=dev), dof, 0.1, 1e-5, 1e-10)
     torch.cuda.synchronize()
     assert torch.isfinite(out["logw"]).all() and all(torch.isfinite(t).all() for t in g)
+# long point set: the 8-warp LM kernel and the 512-thread AMIS kernel
+pc = make_problem(2, 2052, seed=3)
+d = {k: v.to(dev) for k, v in pc.items()}
+prob = native.Problem(d["x3d"], d["x2d"], d["w2d"], d["cam_mats"], None, None, native.adaptive_delta(d["x2d"], d["w2d"], 0.5))
+out = native.lm_amis_fused(prob, d["pose_init"], native.default_params(6, lm_iter=3, mc_samples=64, mc_iter=2), seed=1, want_cost=True)
+torch.cuda.synchronize()
+assert torch.isfinite(out["logw"]).all()
 print("sanitize driver finished")
