@@ -5,11 +5,10 @@ What runs where:
   * the K-iteration Levenberg-Marquardt (or Gauss-Newton `fast_mode`) loop, the pose covariance and
     the optional extra GN step are ONE kernel launch (epnp_lm_solve_f32): no per-iteration launches,
     no host round trips, no materialised (B, 2N, 6) Jacobian;
-  * RSLMSolver draws its random subsets / start rotations with torch (index bookkeeping), then solves
-    all P*B mini-problems in one launch and scores the P hypotheses per object in one more.
+  * RSLMSolver draws its random subsets / start rotations with torch (index bookkeeping); refining and scoring all P
+    hypotheses of every object is one launch (epnp_rslm_f32).
 """
 import math
-import os
 
 import torch
 import torch.nn as nn
@@ -139,12 +138,6 @@ class LMSolver(nn.Module):
         return torch.cat((pose_opt[..., :3] + step[..., :3], F.normalize(q + dq, dim=-1)), dim=-1)
 
 
-def _fused_rslm():
-    """EPNP_FUSED_RSLM=1 selects the single-launch initialiser (thread <-> hypothesis, epnp_rslm_f32).  Opt-in until its
-    first hardware run: it was written and validated on the CPU emulation of the kernels only."""
-    return os.environ.get("EPNP_FUSED_RSLM", "1") not in ("", "0")
-
-
 @PNP.register_module()
 class RSLMSolver(LMSolver):
     """Random-sample LM: a RANSAC-like initialiser for ambiguous problems (levenberg_marquardt.py:268-353)."""
@@ -182,16 +175,16 @@ class RSLMSolver(LMSolver):
             start[..., 3:] = torch.where(qn < self.eps, unit, q / qn)
         return start
 
-    def _solve_fused(self, x3d, x2d, w2d, camera, cost_fun, inds, fast_mode):
-        """One launch for all hypotheses of all objects (epnp_rslm_f32): nothing is gathered or repeated."""
-        start = self._starting_hypotheses(x3d, x2d, camera)
-        prob = native.Problem(x3d, x2d, w2d, camera.cam_mats, camera.lb, camera.ub, cost_fun.delta)
-        out = native.rslm(prob, inds, start, self.native_params(camera, cost_fun, fast_mode))
-        return out["pose"].to(x2d.dtype), None, out["cost"].to(x2d.dtype)
-
     @torch.no_grad()
     def solve(self, x3d, x2d, w2d, camera, cost_fun, **kwargs):
-        """-> pose (B, 4|7), None, min_cost (B)."""
+        """-> pose (B, 4|7), None, min_cost (B).
+
+        The random draws (weighted subsets without replacement, start orientations) are torch calls like the reference's
+        (:306-324); everything after them is ONE kernel launch (epnp_rslm_f32: one CTA per object, thread <-> hypothesis,
+        LM / GN on the n sampled correspondences read from the object's resident pair records, scored on all N points,
+        cheapest kept).  The reference's gather of (P*B, n, .) mini-problems, its P-fold repeated camera / cost objects and
+        its P*B tiny solves do not exist; measured on B200 the single launch beat that formulation on the same kernels
+        (0.60 vs 0.83 ms at B = 256, P = 128; profiles/r2_rslm_ab.jsonl, all four configurations) and the formulation was removed."""
         bs, pn, _ = x2d.size()
         pd = self._pose_dim()
         if bs == 0:
@@ -201,22 +194,7 @@ class RSLMSolver(LMSolver):
         # weighted subsets without replacement, one row per (proposal, object)
         prob_rows = w2d.mean(dim=-1).unsqueeze(0).expand(P, bs, pn).reshape(P * bs, pn)
         inds = torch.multinomial(prob_rows, n).reshape(P, bs, n)
-        if _fused_rslm():
-            return self._solve_fused(x3d, x2d, w2d, camera, cost_fun, inds, kwargs.get("fast_mode", False))
-        inds = inds + (torch.arange(bs, device=inds.device) * pn)[:, None]
-        sub3 = x3d.reshape(-1, 3)[inds].reshape(P * bs, n, 3)
-        sub2 = x2d.reshape(-1, 2)[inds].reshape(P * bs, n, 2)
-        subw = w2d.reshape(-1, 2)[inds].reshape(P * bs, n, 2)
         start = self._starting_hypotheses(x3d, x2d, camera)
-        cam_p = camera.shallow_copy().repeat_(P)
-        cost_p = cost_fun.shallow_copy().repeat_(P)
-        fast_mode = kwargs.get("fast_mode", False)
-        mini = native.Problem(sub3, sub2, subw, cam_p.cam_mats, cam_p.lb, cam_p.ub,
-                              cost_p.delta if not torch.is_tensor(cost_p.delta) or cost_p.delta.numel() == P * bs
-                              else cost_p.delta.reshape(-1))
-        sol = native.lm_solve(mini, start.reshape(P * bs, pd), self.native_params(camera, cost_fun, fast_mode))
-        pose = sol["pose_opt"].reshape(P, bs, pd).to(x2d.dtype)
-        # score every hypothesis on the full correspondence set, keep the best per object
-        cost = evaluate_pnp(x3d, x2d, w2d, pose, camera, cost_fun, out_cost=True)[1]
-        min_cost, best = cost.min(dim=0)
-        return pose[best, torch.arange(bs, device=pose.device)], None, min_cost
+        prob = native.Problem(x3d, x2d, w2d, camera.cam_mats, camera.lb, camera.ub, cost_fun.delta)
+        out = native.rslm(prob, inds, start, self.native_params(camera, cost_fun, kwargs.get("fast_mode", False)))
+        return out["pose"].to(x2d.dtype), None, out["cost"].to(x2d.dtype)

@@ -27,9 +27,7 @@ def _layer():
                                       init_solver=dict(type="RSLMSolver", num_points=16, num_proposals=16, num_iter=3))))
 
 
-@pytest.mark.parametrize("fused_rslm", ["0", "1"])
-def test_inference_sequence(dev, monkeypatch, fused_rslm):
-    monkeypatch.setenv("EPNP_FUSED_RSLM", fused_rslm)         # "1": the single-launch initialiser (epnp_rslm_f32)
+def test_inference_sequence(dev, monkeypatch):
     B, N = 3, 48
     pc = make_problem(B, N, seed=21, dof=4)
     x3d, x2d, w2d, gt = pc["x3d"], pc["x2d"], pc["w2d"], pc["pose_gt"]

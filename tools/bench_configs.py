@@ -106,8 +106,9 @@ def main():
     ms = timed(lambda: native.evaluate_cost(prob, poses, 6, 0.1))
     out.append(dict(config="evaluate_pnp cost, 128 poses x 4096 objects x 512 pts", B=4096, ms=ms,
                     pose_point_pairs_per_s=S * 4096 * 512 / ms * 1e3))
-    # random-sample LM initialiser (RSLMSolver.solve): the unfused path (gather + P*B tiny solves + stacked evaluate_pnp)
-    # against the single-launch kernel (EPNP_FUSED_RSLM=1), demo-notebook and detection configurations
+    # random-sample LM initialiser (RSLMSolver.solve = torch draws + ONE launch of epnp_rslm_f32), demo-notebook and
+    # detection configurations.  (An earlier run, profiles/r2_rslm_ab.jsonl, also timed the reference's own
+    # formulation -- gather + P*B tiny solves + stacked evaluate_pnp -- on the same kernels; it lost everywhere and is gone.)
     if os.environ.get("EPNP_BENCH_RSLM"):
         sys.path.insert(0, os.path.join(ROOT, "epro-pnp_b200"))
         from epropnp.camera import PerspectiveCamera
@@ -122,10 +123,17 @@ def main():
             cost_fun.set_param(pc["x2d"], pc["w2d"])
             solver = RSLMSolver(dof=dof, num_points=npts, num_proposals=P, num_iter=K)
             row = dict(config=f"RSLM init, dof={dof}, N={N}, {P} proposals x {npts} points x LM({K})", B=B)
-            for flag, key in (("0", "ms_unfused"), ("1", "ms_fused")):
-                os.environ["EPNP_FUSED_RSLM"] = flag
-                row[key] = timed(lambda: solver.solve(pc["x3d"], pc["x2d"], pc["w2d"], camera, cost_fun), iters=10)
-            os.environ["EPNP_FUSED_RSLM"] = "1"
+            # the draws alone (torch.multinomial on P*B rows of N weights + the start orientations): torch work of the
+            # reference's own algorithm (levenberg_marquardt.py:306-324) that both paths share
+            rows = pc["w2d"].mean(dim=-1).unsqueeze(0).expand(P, B, N).reshape(P * B, N)
+            row["ms_draws_torch"] = timed(lambda: (torch.multinomial(rows, npts), solver._starting_hypotheses(pc["x3d"], pc["x2d"], camera)), iters=10)
+            row["ms_solve"] = timed(lambda: solver.solve(pc["x3d"], pc["x2d"], pc["w2d"], camera, cost_fun), iters=10)
+            inds = torch.multinomial(rows, npts).reshape(P, B, npts)
+            start = solver._starting_hypotheses(pc["x3d"], pc["x2d"], camera)
+            prob_r = native.Problem(pc["x3d"], pc["x2d"], pc["w2d"], camera.cam_mats, camera.lb, camera.ub, cost_fun.delta)
+            par_r = solver.native_params(camera, cost_fun, False)
+            row["ms_kernel"] = timed(lambda: native.rslm(prob_r, inds, start, par_r), iters=10)
+            row["hypotheses_per_s"] = P * B / row["ms_kernel"] * 1e3
             out.append(row)
     # derivative-regularisation branch: pose_opt_plus forward + backward, torch composite vs native kernel
     if os.environ.get("EPNP_BENCH_GN_PLUS"):

@@ -40,7 +40,8 @@ for dof, N, B, bounded in ((6, 64, 5, False), (6, 130, 3, True), (6, 51, 4, Fals
                                   seed=1, obj_offset=2, want_cost=True, want_cov=True)
         torch.cuda.synchronize()
         assert torch.equal(full_lw[1][2:2 + B], full_lw[0][2:2 + B]) and torch.equal(full_ps[2][2:2 + B], full_ps[0][2:2 + B])
-        assert torch.equal(full_lw[0][2:2 + B], out["logw"]) and not full_lw[1][:2].any() and not full_lw[1][2 + B:].any()
+        same = native.lm_amis_fused(prob, d["pose_init"], p, seed=1, obj_offset=2)          # the Philox stream is keyed by the GLOBAL index
+        assert torch.equal(full_lw[0][2:2 + B], same["logw"]) and not full_lw[1][:2].any() and not full_lw[1][2 + B:].any()
         P, n = 5, 6
         inds = torch.stack([torch.stack([torch.randperm(N, device=dev)[:n] for _ in range(B)]) for _ in range(P)])
         native.rslm(prob, inds, d["pose_init"][None].repeat(P, 1, 1), native.default_params(dof, lm_iter=2), want_all=True)
