@@ -1,6 +1,5 @@
 """The native backward of pose_opt_plus on a real GPU: the assertions of tests/test_gn_plus_backward_cpu.py (which runs
-them on the CPU emulation of the kernels).  Gated until the kernel has had its first hardware run:
-    gpurun -- 'EPNP_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gn_plus_backward_gpu.py -q'"""
+them on the CPU emulation of the kernels)."""
 import os
 
 import pytest

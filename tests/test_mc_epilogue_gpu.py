@@ -1,7 +1,5 @@
 """The native Monte-Carlo epilogue (epnp_mc_epilogue_f32 / epnp_mc_lse_backward_f32) on a real GPU: the assertions of
-tests/test_mc_epilogue_cpu.py that exercise the kernels.  The kernels have not had their first hardware run yet, so the
-file is gated by the environment until they have:
-    gpurun -- 'EPNP_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_mc_epilogue_gpu.py -q'"""
+tests/test_mc_epilogue_cpu.py that exercise the kernels."""
 import os
 
 import pytest

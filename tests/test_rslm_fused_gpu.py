@@ -1,7 +1,5 @@
 """The fused random-sample LM initialiser on a real GPU: the same assertions as tests/test_rslm_fused_cpu.py (which
-runs them on the CPU emulation of the kernels).  The kernel has not had its first hardware run yet, so this file is
-gated by the environment until it has:
-    gpurun -- 'EPNP_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_rslm_fused_gpu.py -q'"""
+runs them on the CPU emulation of the kernels)."""
 import os
 
 import pytest
@@ -20,5 +18,5 @@ def dev():
 
 
 test_every_hypothesis_matches_the_unfused_path = _cpu.test_every_hypothesis_matches_the_unfused_path
-test_solver_class_uses_it_when_asked = _cpu.test_solver_class_uses_it_when_asked
+test_solver_class_returns_the_cheapest_hypothesis = _cpu.test_solver_class_returns_the_cheapest_hypothesis
 test_nan_hypothesis_wins_like_torch_min = _cpu.test_nan_hypothesis_wins_like_torch_min

@@ -5,7 +5,20 @@
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+run_tests() {
+  timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/gpu_tests.log
+}
+run_sanitizer() {
+  : > gpurun_out/r2_sanitizer.txt
+  for tool in memcheck racecheck synccheck; do
+    echo "== $tool" >> gpurun_out/r2_sanitizer.txt
+    timeout 500 compute-sanitizer --tool $tool python tools/sanitize.py 2>&1 \
+        | grep -E "sanitize driver finished|CHECK FAILED|SUMMARY|Error|error|hazard" | head -30 >> gpurun_out/r2_sanitizer.txt
+  done
+  cut -c1-200 gpurun_out/r2_sanitizer.txt
+}
 if [ "${1:-bench}" = "ncu" ]; then
+  [ "${2:-}" = "with-tests" ] && { rm -f gpurun_out/parity_r2.json; run_tests; run_sanitizer; }
   # one `--set full` capture per kernel; the two hot kernels keep their report (source page), the others leave CSVs
   for k in amis_kernel lm_warp_kernel; do
     timeout 200 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -o gpurun_out/r2_$k \
@@ -26,7 +39,7 @@ if [ "${1:-bench}" = "ncu" ]; then
   exit 0
 fi
 rm -f gpurun_out/parity_r2.json gpurun_out/*.ncu-rep
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/gpu_tests.log
+run_tests
 timeout 400 python bench.py --steps 400 --warmup 5 2>gpurun_out/bench.err | tail -1 > gpurun_out/r2_bench_1gpu.json; cut -c1-300 gpurun_out/r2_bench_1gpu.json
 timeout 200 python bench.py --steps 400 --warmup 5 --streams 1 --no-cpu-baseline 2>>gpurun_out/bench.err | tail -1 > gpurun_out/r2_bench_1gpu_one_batch_in_flight.json
 : > gpurun_out/r2_configs.jsonl
@@ -47,10 +60,4 @@ grep -E "RSLM|pose_opt_plus|MC pose loss|training step|evaluate_pnp" gpurun_out/
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 200 python tools/phase_profile.py 4096 512 512 > gpurun_out/r2_phase_cycles_amis.txt 2>&1; tail -9 gpurun_out/r2_phase_cycles_amis.txt
-: > gpurun_out/r2_sanitizer.txt
-for tool in memcheck racecheck synccheck; do
-  echo "== $tool" >> gpurun_out/r2_sanitizer.txt
-  EPNP_SANITIZE_EXPERIMENTAL=1 timeout 500 compute-sanitizer --tool $tool python tools/sanitize.py 2>&1 \
-      | grep -E "sanitize driver finished|SUMMARY|Error|error|hazard" | head -30 >> gpurun_out/r2_sanitizer.txt
-done
-cat gpurun_out/r2_sanitizer.txt | cut -c1-200
+run_sanitizer
