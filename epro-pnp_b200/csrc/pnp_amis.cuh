@@ -406,7 +406,7 @@ struct PushArgs {
 };
 
 // One object per CTA of T threads (blockIdx.x = object).
-template <int DOF, bool PUSH, int T>
+template <int DOF, int T>
 __global__ void __launch_bounds__(T, T == NT ? AMIS_CTAS_PER_SM : 1) amis_kernel(const KArgs a, const PushArgs push) {
     EPNP_DYN_SMEM(unsigned char, smem_raw, 128);
     AmisHead<DOF, T>& sh = *reinterpret_cast<AmisHead<DOF, T>*>(smem_raw);
@@ -444,8 +444,12 @@ __global__ void __launch_bounds__(T, T == NT ? AMIS_CTAS_PER_SM : 1) amis_kernel
     PH_MARK(a, PH_LOAD);
     if constexpr (DOF == 6) amis_phase6<T>(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.cpart, cam, delta, obj);
     else amis_phase4<T>(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.cpart, cam, delta, obj);
-    if constexpr (PUSH) {
-        // the object's log-weights, as this CTA wrote them, and its pose to the same global row on every peer
+    // In-kernel gather (push.n > 0, uniform for the launch): the object's log-weights, as this CTA wrote them, and its
+    // pose go to the same global row on every peer.  A run-time branch of ONE kernel, not a second instantiation: a
+    // sharded run must be bit-identical to the single-GPU run, and two instantiations are two compilations -- as
+    // template variants the push / plain pair agreed bit for bit at N = 64, 512, 2052 but not on two small problems
+    // (N = 51, 130: log-weights 4e-6 apart after one step, profiles/r2_sanitizer_two_instantiations.txt).
+    if (push.n > 0) {
         __syncthreads();                                        // the CTA's own global stores are visible to all its threads
         const size_t row = (size_t)a.obj_offset + (size_t)obj;
         const float* src = a.logw + (size_t)obj * M;

@@ -8,7 +8,7 @@
 //   epnp_lm_amis_fused_f32           = lm_warp_kernel, then amis_kernel, on the caller's stream (no host round trip); the
 //                                    split is what a measurement asked for: as one kernel the LM half ran latency-bound at
 //                                    4 points per thread between block barriers.
-//   cost_kernel, evaluate_full_kernel, rslm_kernel, cost_backward_kernel, gn_plus_backward_kernel, adaptive_delta_kernel,
+//   cost_kernel, evaluate_full_kernel, rslm_draw_kernel, rslm_kernel, cost_backward_kernel, gn_plus_backward_kernel, adaptive_delta_kernel,
 //   mc_epilogue_kernel, mc_lse_backward_kernel      the steps either side of the path (CTA per object).
 // No tensor cores: the only contraction is 6-deep, the work is FP32-pipe + MUFU bound.
 // Build options: EPNP_PHASE_TIMERS (profiling), EPNP_SIMT_EMUL (g++ build for the test-only CPU emulator).
@@ -176,6 +176,98 @@ __global__ void __launch_bounds__(NT, 2) rslm_kernel(const RslmArgs r) {
 #pragma unroll
         for (int i = 0; i < PD; ++i) r.pose_best[(size_t)obj * PD + i] = my_pose[i];
         r.cost_best[obj] = my_cost;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The random draws of RSLMSolver.solve (levenberg_marquardt.py:306-324), one CTA per object, thread <-> hypothesis:
+//   * n DISTINCT correspondence indices, drawn without replacement with probabilities proportional to
+//     wbar_i = mean(w2d[i, :]) -- torch.multinomial(wbar, n) (:306-312).  Same algorithm as torch's: an exponential
+//     race, the n smallest of E_i / wbar_i with E_i ~ Exp(1) (Efraimidis-Spirakis); a weight that is not positive is
+//     never drawn.  The race keeps its n current winners in shared memory ([slot][thread]: conflict-free) together with
+//     the position of the worst of them, so an element costs one compare unless it enters the list
+//     (~ n (1 + ln(N / n)) times per hypothesis).
+//   * the starting pose: the object's centre-based translation with a uniformly random orientation -- a normalised
+//     Gaussian quaternion, (1,0,0,0) when its norm is below eps (:318-324), or a yaw uniform on [0, 2 pi) (:316-317).
+// Philox-4x32-10 keyed by (seed; global object index, hypothesis, block): independent of B, P tiling and launch shape.
+struct RslmDrawArgs {
+    const float* w2d;           // (B, N, 2)
+    const float* t_init;        // (B, 3)
+    int* inds;                  // (P, B, n)
+    float* start;               // (P, B, D)
+    uint64_t seed;
+    uint32_t obj_offset;
+    int P, n, B, N;
+    float eps;
+};
+
+constexpr uint32_t RSLM_TAG_SUBSET = 0x52534c4du, RSLM_TAG_START = 0x52534c53u;
+
+template <int DOF>
+__global__ void __launch_bounds__(NT) rslm_draw_kernel(const RslmDrawArgs r) {
+    EPNP_DYN_SMEM(unsigned char, smem_raw, 16);
+    float* wbar = reinterpret_cast<float*>(smem_raw);                       // [N]
+    float* keys = wbar + ((r.N + 3) & ~3);                                  // [n][NT]
+    int* slots = reinterpret_cast<int*>(keys + (size_t)r.n * NT);           // [n][NT]
+    constexpr int PD = Dim<DOF>::POSE;
+    const int tid = threadIdx.x, obj = blockIdx.x;
+    const uint32_t gobj = r.obj_offset + (uint32_t)obj;
+    for (int i = tid; i < r.N; i += NT) {
+        const float2 w = *reinterpret_cast<const float2*>(r.w2d + ((size_t)obj * r.N + i) * 2);
+        wbar[i] = 0.5f * (w.x + w.y);
+    }
+    __syncthreads();
+    const Philox ph{(uint32_t)r.seed, (uint32_t)(r.seed >> 32)};
+    for (int h = tid; h < r.P; h += NT) {
+        int cnt = 0, worst = 0;
+        float thr = -1.0f;                                                  // the largest key in the list
+        for (int i0 = 0; i0 < r.N; i0 += 4) {
+            uint32_t u[4];
+            ph(gobj, (uint32_t)h, (uint32_t)(i0 >> 2), RSLM_TAG_SUBSET, u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = i0 + j;
+                if (i >= r.N) break;
+                const float w = wbar[i];
+                if (!(w > 0.0f)) continue;
+                const float key = -fast_log(u01(u[j])) / w;
+                if (cnt < r.n) {
+                    keys[cnt * NT + tid] = key; slots[cnt * NT + tid] = i;
+                    if (key > thr) { thr = key; worst = cnt; }
+                    ++cnt;
+                } else if (key < thr) {
+                    keys[worst * NT + tid] = key; slots[worst * NT + tid] = i;
+                    thr = -1.0f;
+                    for (int s = 0; s < r.n; ++s) {
+                        const float k = keys[s * NT + tid];
+                        if (k > thr) { thr = k; worst = s; }
+                    }
+                }
+            }
+        }
+        // fewer than n positive weights (torch.multinomial raises): complete the subset with the first unused indices
+        for (int i = 0; cnt < r.n && i < r.N; ++i) {
+            if (wbar[i] > 0.0f) continue;
+            slots[cnt * NT + tid] = i; ++cnt;
+        }
+        int* out = r.inds + ((size_t)h * r.B + obj) * r.n;
+        for (int s = 0; s < r.n; ++s) out[s] = slots[s * NT + tid];
+        float* st = r.start + ((size_t)h * r.B + obj) * PD;
+        st[0] = __ldg(r.t_init + (size_t)obj * 3); st[1] = __ldg(r.t_init + (size_t)obj * 3 + 1); st[2] = __ldg(r.t_init + (size_t)obj * 3 + 2);
+        uint32_t v[4];
+        ph(gobj, (uint32_t)h, 0u, RSLM_TAG_START, v);
+        if (DOF == 4) {
+            st[3] = u01(v[0]) * 6.283185307179586f;
+        } else {
+            float q[4];
+            box_muller(v[0], v[1], q[0], q[1]);
+            box_muller(v[2], v[3], q[2], q[3]);
+            const float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+            const bool tiny = nrm < r.eps;
+            const float inv = 1.0f / nrm;
+            st[3] = tiny ? 1.0f : q[0] * inv; st[4] = tiny ? 0.0f : q[1] * inv;
+            st[5] = tiny ? 0.0f : q[2] * inv; st[6] = tiny ? 0.0f : q[3] * inv;
+        }
     }
 }
 
@@ -619,12 +711,9 @@ template <int DOF>
 int launch_amis(KArgs& a, const PushArgs* push, cudaStream_t stream) {
     const int smem_bytes = amis_smem_bytes<DOF>(a.N, a.p.mc_samples);
     const PushArgs none{};
-    if (amis_dense(a.N)) {
-        if (push) return launch_cta_per_object<AMIS_T_DENSE>(amis_kernel<DOF, true, AMIS_T_DENSE>, a, smem_bytes, stream, *push);
-        return launch_cta_per_object<AMIS_T_DENSE>(amis_kernel<DOF, false, AMIS_T_DENSE>, a, smem_bytes, stream, none);
-    }
-    if (push) return launch_cta_per_object<NT>(amis_kernel<DOF, true, NT>, a, smem_bytes, stream, *push);
-    return launch_cta_per_object<NT>(amis_kernel<DOF, false, NT>, a, smem_bytes, stream, none);
+    if (amis_dense(a.N))
+        return launch_cta_per_object<AMIS_T_DENSE>(amis_kernel<DOF, AMIS_T_DENSE>, a, smem_bytes, stream, push ? *push : none);
+    return launch_cta_per_object<NT>(amis_kernel<DOF, NT>, a, smem_bytes, stream, push ? *push : none);
 }
 
 unsigned long long* g_prof_buffer = nullptr;     // set by epnp_debug_set_phase_buffer (profiling build)
@@ -869,6 +958,28 @@ int epnp_rslm_f32(const float* x3d, const float* x2d, const float* w2d, const fl
     return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
 }
 
+int epnp_rslm_draw_f32(const float* w2d, const float* t_init, uint64_t seed, uint32_t obj_offset, int* inds, float* start,
+                       int P, int n, int B, int N, int dof, float eps, void* stream) {
+    if (!w2d || !t_init || !inds || !start || (dof != 4 && dof != 6) || P <= 0 || n <= 0 || B < 0 || N <= 0 || n > N)
+        return EPNP_ERR_BAD_ARG;
+    if (B == 0) return EPNP_OK;
+    const size_t smem = (size_t)((N + 3) & ~3) * sizeof(float) + (size_t)n * NT * (sizeof(float) + sizeof(int));
+    if (smem > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
+    RslmDrawArgs r{w2d, t_init, inds, start, seed, obj_offset, P, n, B, N, eps};
+    cudaError_t e;
+    if (dof == 6) {
+        e = cudaFuncSetAttribute(rslm_draw_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e);
+        EPNP_LAUNCH(rslm_draw_kernel<6>, B, NT, smem, (cudaStream_t)stream, r);
+    } else {
+        e = cudaFuncSetAttribute(rslm_draw_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e);
+        EPNP_LAUNCH(rslm_draw_kernel<4>, B, NT, smem, (cudaStream_t)stream, r);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
+}
+
 int epnp_amis_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
                   const float* lb, const float* ub, const float* delta, const float* pose_opt, const float* pose_cov,
                   const float* noise_normal, const float* noise_chi2, const float* noise_rot,
@@ -1057,10 +1168,10 @@ int epnp_lm_amis_fused_host_f32(const float* x3d_host, const float* x2d_host, co
     if (n_chunks == 0) {
         if (check_amis_params(*p) != EPNP_OK) return EPNP_ERR_BAD_ARG;
         const int wave = (p->dof == 6)
-            ? (amis_dense(N) ? resident_objects<AMIS_T_DENSE>(amis_kernel<6, false, AMIS_T_DENSE>, amis_smem_bytes<6>(N, p->mc_samples))
-                             : resident_objects<NT>(amis_kernel<6, false, NT>, amis_smem_bytes<6>(N, p->mc_samples)))
-            : (amis_dense(N) ? resident_objects<AMIS_T_DENSE>(amis_kernel<4, false, AMIS_T_DENSE>, amis_smem_bytes<4>(N, p->mc_samples))
-                             : resident_objects<NT>(amis_kernel<4, false, NT>, amis_smem_bytes<4>(N, p->mc_samples)));
+            ? (amis_dense(N) ? resident_objects<AMIS_T_DENSE>(amis_kernel<6, AMIS_T_DENSE>, amis_smem_bytes<6>(N, p->mc_samples))
+                             : resident_objects<NT>(amis_kernel<6, NT>, amis_smem_bytes<6>(N, p->mc_samples)))
+            : (amis_dense(N) ? resident_objects<AMIS_T_DENSE>(amis_kernel<4, AMIS_T_DENSE>, amis_smem_bytes<4>(N, p->mc_samples))
+                             : resident_objects<NT>(amis_kernel<4, NT>, amis_smem_bytes<4>(N, p->mc_samples)));
         if (wave > 0) {
             const int waves_per_chunk = (B + 64 * wave - 1) / (64 * wave);
             chunk_objects = wave * waves_per_chunk;

@@ -5,8 +5,8 @@ What runs where:
   * the K-iteration Levenberg-Marquardt (or Gauss-Newton `fast_mode`) loop, the pose covariance and
     the optional extra GN step are ONE kernel launch (epnp_lm_solve_f32): no per-iteration launches,
     no host round trips, no materialised (B, 2N, 6) Jacobian;
-  * RSLMSolver draws its random subsets / start rotations with torch (index bookkeeping); refining and scoring all P
-    hypotheses of every object is one launch (epnp_rslm_f32).
+  * RSLMSolver: two launches -- the random subsets / start orientations (epnp_rslm_draw_f32), then refining and
+    scoring all P hypotheses of every object (epnp_rslm_f32).
 """
 import math
 
@@ -142,10 +142,17 @@ class LMSolver(nn.Module):
 class RSLMSolver(LMSolver):
     """Random-sample LM: a RANSAC-like initialiser for ambiguous problems (levenberg_marquardt.py:268-353)."""
 
-    def __init__(self, num_points=16, num_proposals=64, num_iter=3, **kwargs):
+    def __init__(self, num_points=16, num_proposals=64, num_iter=3, draws='native', **kwargs):
+        """draws='native' (default): the weighted subsets and start orientations come from one kernel launch
+        (epnp_rslm_draw_f32, Philox keyed by a seed taken from torch's default generator, so torch.manual_seed governs
+        it); draws='torch': torch.multinomial / randn / rand exactly as the reference calls them (:306-324) -- the same
+        distribution from torch's own streams, for code that replays or compares them (the parity tests do)."""
         super(RSLMSolver, self).__init__(num_iter=num_iter, **kwargs)
         self.num_points = num_points
         self.num_proposals = num_proposals
+        if draws not in ('native', 'torch'):
+            raise ValueError(f"draws must be 'native' or 'torch', got {draws!r}")
+        self.draws = draws
 
     def center_based_init(self, x2d, x3d, camera, eps=1e-6):
         """Translation guess from the spread of the 2D points vs the 3D points (:283-298)."""
@@ -179,22 +186,30 @@ class RSLMSolver(LMSolver):
     def solve(self, x3d, x2d, w2d, camera, cost_fun, **kwargs):
         """-> pose (B, 4|7), None, min_cost (B).
 
-        The random draws (weighted subsets without replacement, start orientations) are torch calls like the reference's
-        (:306-324); everything after them is ONE kernel launch (epnp_rslm_f32: one CTA per object, thread <-> hypothesis,
-        LM / GN on the n sampled correspondences read from the object's resident pair records, scored on all N points,
-        cheapest kept).  The reference's gather of (P*B, n, .) mini-problems, its P-fold repeated camera / cost objects and
-        its P*B tiny solves do not exist; measured on B200 the single launch beat that formulation on the same kernels
-        (0.60 vs 0.83 ms at B = 256, P = 128; profiles/r2_rslm_ab.jsonl, all four configurations) and the formulation was removed."""
+        Two launches after the centre-based translation guess: the random draws (epnp_rslm_draw_f32: per (proposal,
+        object) a weighted subset without replacement and a random start orientation; 0.1 ms where torch.multinomial on
+        the (P*B, N) weight rows took 8 ms at B = 4096, profiles/r2_side_kernels.jsonl) and the solve (epnp_rslm_f32: one
+        CTA per object, thread <-> hypothesis, LM / GN on the n sampled correspondences read from the object's resident
+        pair records, scored on all N points, cheapest kept).  The reference's gather of (P*B, n, .) mini-problems, its
+        P-fold repeated camera / cost objects and its P*B tiny solves do not exist; run on the same kernels that
+        formulation lost in all four measured configurations (profiles/r2_rslm_ab.jsonl) and was removed.
+        `rslm_seed=` fixes the Philox stream of the native draws."""
         bs, pn, _ = x2d.size()
         pd = self._pose_dim()
         if bs == 0:
             return x2d.new_empty((0, pd)), None, x2d.new_empty((0,))
         P, n = self.num_proposals, self.num_points
         x3d, x2d, w2d = x3d.detach(), x2d.detach(), w2d.detach()
-        # weighted subsets without replacement, one row per (proposal, object)
-        prob_rows = w2d.mean(dim=-1).unsqueeze(0).expand(P, bs, pn).reshape(P * bs, pn)
-        inds = torch.multinomial(prob_rows, n).reshape(P, bs, n)
-        start = self._starting_hypotheses(x3d, x2d, camera)
+        if self.draws == 'torch':
+            # weighted subsets without replacement, one row per (proposal, object)
+            prob_rows = w2d.mean(dim=-1).unsqueeze(0).expand(P, bs, pn).reshape(P * bs, pn)
+            inds = torch.multinomial(prob_rows, n).reshape(P, bs, n)
+            start = self._starting_hypotheses(x3d, x2d, camera)
+        else:
+            seed = kwargs.get("rslm_seed")
+            seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+            inds, start = native.rslm_draw(w2d, self.center_based_init(x2d, x3d, camera), P, n, self.dof, eps=self.eps,
+                                           seed=seed)
         prob = native.Problem(x3d, x2d, w2d, camera.cam_mats, camera.lb, camera.ub, cost_fun.delta)
         out = native.rslm(prob, inds, start, self.native_params(camera, cost_fun, kwargs.get("fast_mode", False)))
         return out["pose"].to(x2d.dtype), None, out["cost"].to(x2d.dtype)

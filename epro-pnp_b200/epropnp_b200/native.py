@@ -134,6 +134,27 @@ def lm_solve(prob: Problem, pose_init, params, want_cov=False, want_cost=False, 
     return out
 
 
+def rslm_draw(w2d, t_init, P, n, dof, eps=1e-5, seed=0, obj_offset=0):
+    """The initialiser's random draws in one launch (epnp_rslm_draw_f32): w2d (B, N, 2), t_init (B, 3) ->
+    inds (P, B, n) int32 (weighted, without replacement, per proposal and object), start (P, B, D) (t_init + a
+    uniformly random orientation)."""
+    _need_cuda(w2d, "w2d")
+    if w2d.dim() != 3 or w2d.shape[-1] != 2:
+        raise ValueError(f"w2d must be (B, N, 2), got {tuple(w2d.shape)}")
+    B, N = w2d.shape[0], w2d.shape[1]
+    if tuple(t_init.shape) != (B, 3):
+        raise ValueError(f"t_init must be ({B}, 3), got {tuple(t_init.shape)}")
+    D = 7 if dof == 6 else 4
+    w2d, t_init = _f32c(w2d), _f32c(t_init.to(w2d.device))
+    inds = torch.empty(P, B, n, dtype=torch.int32, device=w2d.device)
+    start = torch.empty(P, B, D, dtype=torch.float32, device=w2d.device)
+    with torch.cuda.device(w2d.device):
+        check(lib().epnp_rslm_draw_f32(ptr(w2d), ptr(t_init), ctypes.c_uint64(seed), ctypes.c_uint32(obj_offset),
+                                       capi.iptr(inds), ptr(start), P, n, B, N, dof, ctypes.c_float(eps),
+                                       stream_ptr(w2d.device)), "epnp_rslm_draw_f32")
+    return inds, start
+
+
 def rslm(prob: Problem, inds, start, params, want_all=False):
     """Fused random-sample LM initialiser (epnp_rslm_f32): inds (P, B, n) integer indices within each object, start
     (P, B, D) -> dict(pose (B, D), cost (B), pose_all (P, B, D) | None, cost_all (P, B) | None)."""

@@ -105,6 +105,23 @@ def rslm(prob, inds, start, params, want_all=False):
                 cost_all=r["hyp_cost"] if want_all else None)
 
 
+def rslm_draw(w2d, t_init, P, n, dof, eps=1e-5, seed=0, obj_offset=0):
+    """The reference's own draws (levenberg_marquardt.py:306-324) from a torch generator seeded with `seed`."""
+    g = torch.Generator().manual_seed(int(seed) % (2 ** 63))
+    B, N = w2d.shape[0], w2d.shape[1]
+    rows = w2d.detach().mean(dim=-1).unsqueeze(0).expand(P, B, N).reshape(P * B, N)
+    inds = torch.multinomial(rows.double(), n, generator=g).reshape(P, B, n).to(torch.int32)
+    start = t_init.new_empty((P, B, 7 if dof == 6 else 4))
+    start[..., :3] = t_init
+    if dof == 4:
+        start[..., 3] = torch.rand((P, B), generator=g, dtype=t_init.dtype) * (2 * math.pi)
+    else:
+        q = torch.randn((P, B, 4), generator=g, dtype=t_init.dtype)
+        qn = q.norm(dim=-1, keepdim=True)
+        start[..., 3:] = torch.where(qn < eps, q.new_tensor([1., 0., 0., 0.]), q / qn)
+    return inds, start
+
+
 def cost_backward(prob, dof, z_min, poses_a, grad_a, poses_b=None, grad_b=None, want=(True, True, True, True)):
     """Reference semantics by construction: torch autograd through the oracle's evaluate."""
     with torch.enable_grad():            # we are called from inside Function.backward, where grad mode is off
@@ -123,6 +140,6 @@ def install(monkeypatch):
     # the derivative-regularisation branch: the torch composite (exact in float64) instead of the fp32 native kernel
     monkeypatch.setenv("EPNP_NATIVE_GN_STEP", "0")
     for name, fn in (("Problem", FakeProblem), ("adaptive_delta", adaptive_delta), ("evaluate_cost", evaluate_cost),
-                     ("evaluate_full", evaluate_full), ("lm_solve", lm_solve), ("lm_amis_fused", lm_amis_fused), ("rslm", rslm),
+                     ("evaluate_full", evaluate_full), ("lm_solve", lm_solve), ("lm_amis_fused", lm_amis_fused), ("rslm", rslm), ("rslm_draw", rslm_draw),
                      ("cost_backward", cost_backward)):
         monkeypatch.setattr(native, name, fn)

@@ -122,7 +122,7 @@ def test_rslm_classes_with_reference_draws(cuda_device, name, monkeypatch):
     cost_fun = AdaptiveHuberPnPCost(relative_delta=float(g["relative_delta"]))
     cost_fun.set_param(t("x2d"), t("w2d"))
     fast = bool(g["fast_mode"])
-    rs = RSLMSolver(dof=dof, num_points=n, num_proposals=P, num_iter=int(g["rs_iter"]))
+    rs = RSLMSolver(dof=dof, num_points=n, num_proposals=P, num_iter=int(g["rs_iter"]), draws="torch")
     _Playback(monkeypatch, dev, [g["inds"], g["force_inds"]], [g["rot_draw"], g["force_rot_draw"]], dof)
     pose, none, cost = rs.solve(t("x3d"), t("x2d"), t("w2d"), camera, cost_fun, fast_mode=fast)
     assert none is None

@@ -106,8 +106,8 @@ def main():
     ms = timed(lambda: native.evaluate_cost(prob, poses, 6, 0.1))
     out.append(dict(config="evaluate_pnp cost, 128 poses x 4096 objects x 512 pts", B=4096, ms=ms,
                     pose_point_pairs_per_s=S * 4096 * 512 / ms * 1e3))
-    # random-sample LM initialiser (RSLMSolver.solve = torch draws + ONE launch of epnp_rslm_f32), demo-notebook and
-    # detection configurations.  (An earlier run, profiles/r2_rslm_ab.jsonl, also timed the reference's own
+    # random-sample LM initialiser (RSLMSolver.solve = centre-based translation in torch + epnp_rslm_draw_f32 +
+    # epnp_rslm_f32), demo-notebook and detection configurations; draws='torch' = the reference's torch.multinomial / randn.  (An earlier run, profiles/r2_rslm_ab.jsonl, also timed the reference's own
     # formulation -- gather + P*B tiny solves + stacked evaluate_pnp -- on the same kernels; it lost everywhere and is gone.)
     if os.environ.get("EPNP_BENCH_RSLM"):
         sys.path.insert(0, os.path.join(ROOT, "epro-pnp_b200"))
@@ -127,7 +127,11 @@ def main():
             # reference's own algorithm (levenberg_marquardt.py:306-324) that both paths share
             rows = pc["w2d"].mean(dim=-1).unsqueeze(0).expand(P, B, N).reshape(P * B, N)
             row["ms_draws_torch"] = timed(lambda: (torch.multinomial(rows, npts), solver._starting_hypotheses(pc["x3d"], pc["x2d"], camera)), iters=10)
+            t0 = solver.center_based_init(pc["x2d"], pc["x3d"], camera)
+            row["ms_draws_native"] = timed(lambda: native.rslm_draw(pc["w2d"], t0, P, npts, dof, seed=1), iters=10)
             row["ms_solve"] = timed(lambda: solver.solve(pc["x3d"], pc["x2d"], pc["w2d"], camera, cost_fun), iters=10)
+            solver_t = RSLMSolver(dof=dof, num_points=npts, num_proposals=P, num_iter=K, draws="torch")
+            row["ms_solve_torch_draws"] = timed(lambda: solver_t.solve(pc["x3d"], pc["x2d"], pc["w2d"], camera, cost_fun), iters=10)
             inds = torch.multinomial(rows, npts).reshape(P, B, npts)
             start = solver._starting_hypotheses(pc["x3d"], pc["x2d"], camera)
             prob_r = native.Problem(pc["x3d"], pc["x2d"], pc["w2d"], camera.cam_mats, camera.lb, camera.ub, cost_fun.delta)

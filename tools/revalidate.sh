@@ -24,7 +24,7 @@ if [ "${1:-bench}" = "ncu" ]; then
     timeout 200 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -o gpurun_out/r2_$k \
         python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --streams 1 > /dev/null 2>&1
   done
-  for k in cost_backward_kernel cost_kernel rslm_kernel gn_plus_backward_kernel adaptive_delta_kernel mc_epilogue_kernel evaluate_full_kernel; do
+  for k in cost_backward_kernel cost_kernel rslm_draw_kernel rslm_kernel gn_plus_backward_kernel adaptive_delta_kernel mc_epilogue_kernel evaluate_full_kernel; do
     timeout 200 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -o /tmp/r2_$k python tools/kernel_tour.py > /dev/null 2>&1
     ncu -i /tmp/r2_$k.ncu-rep --page raw --csv > gpurun_out/r2_${k}_raw.csv 2>/dev/null
     ncu -i /tmp/r2_$k.ncu-rep --page source --csv > gpurun_out/r2_${k}_source.csv 2>/dev/null

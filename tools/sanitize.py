@@ -62,6 +62,10 @@ for dof, N, B, bounded in ((6, 64, 5, False), (6, 130, 3, True), (6, 51, 4, Fals
         P, n = 5, 6
         inds = torch.stack([torch.stack([torch.randperm(N, device=dev)[:n] for _ in range(B)]) for _ in range(P)])
         native.rslm(prob, inds, d["pose_init"][None].repeat(P, 1, 1), native.default_params(dof, lm_iter=2), want_all=True)
+        di, ds = native.rslm_draw(d["w2d"], d["pose_init"][:, :3], 9, n, dof, seed=3)
+        check(f"{tag}: drawn subsets in range and distinct",
+              di.min() >= 0 and di.max() < N and (di.sort(-1).values[..., 1:] != di.sort(-1).values[..., :-1]).all())
+        native.rslm(prob, di, ds, native.default_params(dof, lm_iter=2))
         native.gn_plus_backward(prob, out["pose_opt"], torch.randn(B, D, device=dev), dof, 0.1, 1e-5, 1e-10)
     torch.cuda.synchronize()
     check(f"dof={dof} N={N}: finite log-weights", torch.isfinite(out["logw"]).all())
