@@ -293,9 +293,9 @@ def main():
     ap.add_argument("--config", default="fused", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--gather", default="push", choices=["nccl", "nccl-coalesced", "peer", "push"],
+    ap.add_argument("--gather", default="push", choices=["nccl", "push"],
                     help="N > 1: 'push' = the AMIS kernel stores finished rows into every rank's result buffer over "
-                         "NVLink (no gather kernel); 'nccl' = overlapped all_gather_into_tensor; 'peer' = copy-engine pulls")
+                         "NVLink (no gather kernel); 'nccl' = overlapped all_gather_into_tensor (the baseline it is measured against)")
     ap.add_argument("--nccl-max-ctas", type=int, default=0,
                     help="N > 1, --gather nccl: cap the CTAs NCCL may use per collective (0 = NCCL's default)")
     ap.add_argument("--streams", type=int, default=2,
@@ -318,7 +318,7 @@ def main():
 
     import torch.distributed as dist
     from epropnp_b200 import native
-    from epropnp_b200.sharded import PeerGather, PushGather, gather_results_async
+    from epropnp_b200.sharded import PushGather, gather_results_async
     from epropnp_b200.synth import make_problem
 
     torch.cuda.set_device(local_rank)
@@ -393,7 +393,7 @@ def main():
                                     want_cost=True, want_cost_init=False)
 
     pending = None
-    peer_gather = None
+    push_gather = None
     lanes = [torch.cuda.Stream(dev) for _ in range(args.streams)] if args.streams > 1 else None
     k_ev = {}                       # step -> (event before, event after) around the solve's launches, timed region only
     timing = [False]
@@ -425,14 +425,14 @@ def main():
         """One batch: the solve, then (N > 1) the gather of (pose_opt, logw).  The gather is asynchronous and the previous
         batch's is awaited only after this batch's solve is enqueued, so exchange i overlaps solve i+1 (batches are
         independent); every gather completes inside the timed region (drain() before t_end)."""
-        nonlocal pending, peer_gather
+        nonlocal pending, push_gather
         if gathering and args.gather == "push":
             # solve + gather in one: the AMIS kernel stores every finished object's rows into all ranks' result buffers
-            if peer_gather is None:
-                peer_gather = PushGather(B_total, M, 7, dev)
+            if push_gather is None:
+                push_gather = PushGather(B_total, M, 7, dev)
             s = sets[i % n_sets]
             mark(i, 0)
-            out, nxt = peer_gather.solve(s["prob"], s["pose_init"], params, seed=1234 + i, want_cost=True, want_cov=True)
+            out, nxt = push_gather.solve(s["prob"], s["pose_init"], params, seed=1234 + i, want_cost=True, want_cov=True)
             mark(i, 1)
             if pending is not None:
                 pending.wait()
@@ -444,13 +444,7 @@ def main():
         if gathering:
             if pending is not None:
                 pending.wait()
-            if args.gather == "peer":
-                if peer_gather is None:
-                    peer_gather = PeerGather(out, B_total, keys=("pose_opt", "logw"), depth=3)
-                pending = peer_gather.start(out)
-            else:
-                pending = gather_results_async(out, B_total, keys=("pose_opt", "logw"),
-                                               coalesce=(args.gather == "nccl-coalesced"))
+            pending = gather_results_async(out, B_total, keys=("pose_opt", "logw"))
         return out
 
     def drain():

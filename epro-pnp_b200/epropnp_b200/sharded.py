@@ -62,12 +62,10 @@ class PendingGather:
         return self.tensors
 
 
-def gather_results_async(result, num_obj, keys=("pose_opt", "logw"), group=None, coalesce=False):
+def gather_results_async(result, num_obj, keys=("pose_opt", "logw"), group=None):
     """Same gather, issued asynchronously (equal shards only): NCCL runs it on its own stream after the work
     already enqueued on the current stream, so the NEXT batch's solve overlaps this batch's exchange.  Objects of
-    different batches are independent; nothing inside a solve ever waits for a collective.
-    coalesce=True hands all keys to the backend as ONE grouped all-gather (one NCCL kernel instead of one per key:
-    fewer CTAs parked on the SMs the next solve wants)."""
+    different batches are independent; nothing inside a solve ever waits for a collective."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return PendingGather({k: result[k] for k in keys if result.get(k) is not None}, [])
     world = dist.get_world_size(group)
@@ -77,20 +75,14 @@ def gather_results_async(result, num_obj, keys=("pose_opt", "logw"), group=None,
     present = [k for k in keys if result.get(k) is not None]
     for k in present:
         outs[k] = result[k].new_empty((num_obj,) + tuple(result[k].shape[1:]))
-    if coalesce and len(present) > 1:
-        with dist._coalescing_manager(group=group, async_ops=True) as cm:
-            for k in present:
-                dist.all_gather_into_tensor(outs[k], result[k].contiguous(), group=group)
-        works.append(cm)
-    else:
-        for k in present:
-            works.append(dist.all_gather_into_tensor(outs[k], result[k].contiguous(), group=group, async_op=True))
+    for k in present:
+        works.append(dist.all_gather_into_tensor(outs[k], result[k].contiguous(), group=group, async_op=True))
     return PendingGather(outs, works)
 
 
 # ---- raw CUDA IPC: a peer's buffer mapped while THIS process's own device is current.  torch's tensor IPC
 # (reduce_tensor / rebuild_cuda_tensor) opens the handle under the EXPORTER's device index and relies on torch's lazy
-# peer-access switch, which is enough for cross-device copies (PeerGather) but not a documented contract for kernels of
+# peer-access switch, which is enough for cross-device copies but not a documented contract for kernels of
 # another device dereferencing the pointer; the in-kernel push (PushGather) therefore maps its peers the way NCCL does:
 # cudaIpcOpenMemHandle(handle, cudaIpcMemLazyEnablePeerAccess) on the importing device.
 _cudart = None
@@ -180,96 +172,11 @@ class _DeviceHooks:
     def _record_stream(self, tensor, stream):
         tensor.record_stream(stream)
 
-    def _export(self, t):
-        from torch.multiprocessing.reductions import reduce_tensor
-        return reduce_tensor(t)                 # CUDA IPC handle (+ offset) of a device tensor
-
-    def _import(self, handle):
-        fn, args = handle
-        return fn(*args)
-
     def _export_raw(self, t):
         return raw_ipc_export(t)
 
     def _import_raw(self, desc):
         return raw_ipc_open(desc, self.device)     # a raw device pointer (int)
-
-
-class PeerGather(_DeviceHooks):
-    """Gather WITHOUT streaming multiprocessors (opt-in; equal shards, one node).
-
-    NCCL's all-gather is a kernel: while it moves the (B, M) log-weights it holds SM slots the next batch's solve
-    could use (~0.12 ms of a 1.4 ms step at 8 GPUs).  Here every rank instead exposes a small ring of export buffers
-    through CUDA IPC once; per batch it
-        1. copies its local results into the ring slot of this batch (device-to-device, its own stream),
-        2. meets the other ranks in a 4-byte NCCL all-reduce (the only collective: "slot t is complete everywhere"),
-        3. PULLS every peer's slot into its full-size result with `Tensor.copy_` across devices, i.e.
-           cudaMemcpyPeerAsync: copy-engine DMA over NVLink, no SM involved,
-    all on a side stream, so exchange t overlaps solve t+1 exactly like gather_results_async.  A slot is rewritten
-    `depth` batches later; the rendezvous of batch t+1 (stream-ordered after the pulls of batch t on every rank)
-    proves that all pulls from it are finished, and the export copy of batch t+depth waits for that rendezvous.
-
-    Requires every process to see all GPUs of the node (torchrun's default) with peer access between them.
-    """
-
-    def __init__(self, like, num_obj, keys=("pose_opt", "logw"), depth=2, group=None):
-        """like: dict of local result tensors (shapes / dtypes of one batch), e.g. one native.lm_amis_fused result."""
-        if not (dist.is_available() and dist.is_initialized()):
-            raise RuntimeError("PeerGather needs an initialised process group")
-        self.group, self.keys, self.depth = group, tuple(k for k in keys if like.get(k) is not None), int(depth)
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        if len(set(shard_sizes(num_obj, self.world))) != 1:
-            raise ValueError("PeerGather handles equal shards only (use gather_results for ragged batches)")
-        if self.depth < 2:
-            raise ValueError("depth >= 2: a slot must survive until the next batch's rendezvous")
-        self.num_obj, self.per_rank = int(num_obj), int(num_obj) // self.world
-        self.device = like[self.keys[0]].device
-        self.comm = self._new_stream()
-        self.flag = torch.zeros(1, device=self.device)
-        # ring of export buffers, IPC handles exchanged once
-        self.export = [{k: torch.empty_like(like[k]).contiguous() for k in self.keys} for _ in range(self.depth)]
-        mine = [{k: self._export(slot[k]) for k in self.keys} for slot in self.export]
-        everyone = [None] * self.world
-        dist.all_gather_object(everyone, mine, group=group)
-        self.peers = []                       # peers[r][slot][key] -> tensor mapped from rank r (None for myself)
-        for r, slots in enumerate(everyone):
-            if r == self.rank:
-                self.peers.append(None)
-                continue
-            self.peers.append([{k: self._import(h) for k, h in slot.items()} for slot in slots])
-        self.met = [None] * self.depth        # event: rendezvous that retired the previous use of slot s
-        self.step = 0
-        dist.barrier(group=group)
-
-    def start(self, result):
-        """Enqueue the exchange of one batch's local `result`; returns a PendingGather."""
-        s = self.step % self.depth
-        cur = self._current_stream()
-        if self.met[s] is not None:
-            cur.wait_event(self.met[s])       # every peer has finished pulling the previous content of slot s
-        for k in self.keys:
-            self.export[s][k].copy_(result[k], non_blocking=True)
-        ready = self._new_event()
-        ready.record(cur)
-        outs = {k: result[k].new_empty((self.num_obj,) + tuple(result[k].shape[1:])) for k in self.keys}
-        with self._on_stream(self.comm):
-            self.comm.wait_event(ready)
-            dist.all_reduce(self.flag, group=self.group)          # rendezvous: slot s is complete on every rank
-            met = self._new_event()
-            met.record(self.comm)
-            for r in range(self.world):
-                lo, hi = r * self.per_rank, (r + 1) * self.per_rank
-                for k in self.keys:
-                    src = self.export[s][k] if r == self.rank else self.peers[r][s][k]
-                    outs[k][lo:hi].copy_(src, non_blocking=True)
-            done = self._new_event()
-            done.record(self.comm)
-        for k in self.keys:                   # the side stream uses these until `done`
-            self._record_stream(outs[k], self.comm)
-        # this rendezvous is stream-ordered after the pulls of the PREVIOUS batch on every rank: it retires that slot
-        self.met[(self.step - 1) % self.depth] = met
-        self.step += 1
-        return PendingGather(outs, [_EventWork(done, cur_stream=self._current_stream)])
 
 
 class _EventWork:

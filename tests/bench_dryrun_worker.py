@@ -35,7 +35,6 @@ def main():
     torch.empty = (lambda f: (lambda *a, pin_memory=False, **k: f(*a, **k)))(torch.empty)
     real_init = dist.init_process_group
     dist.init_process_group = lambda backend=None, **kw: real_init("gloo", **{k: v for k, v in kw.items() if k != "device_id"})
-    sharded.PeerGather = _host_class(sharded.PeerGather)
     sharded.PushGather = _host_class(sharded.PushGather)
     os.environ.update(EPNP_BENCH_DEVICE="cpu", EPNP_NO_SAMPLER="1", LOCAL_RANK="0")
     import bench

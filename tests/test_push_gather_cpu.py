@@ -117,20 +117,17 @@ def _host_class(base):
         def _record_stream(self, tensor, stream):
             pass
 
+        # PushGather maps its peers through raw CUDA IPC on the GPU; on the host shared-memory tensors stand in.
         # reduce_tensor() of a HOST tensor embeds the storage object (only ForkingPickler shares it); export the
         # shared-memory file of the storage itself so that all_gather_object's plain pickle carries a real handle
-        def _export(self, t):
+        def _export_raw(self, t):
             t.share_memory_()
             fn, args = reduce_storage(t.untyped_storage())
             return (fn, args, tuple(t.shape), t.dtype)
 
-        def _import(self, handle):
+        def _import_raw(self, handle):
             fn, args, shape, dtype = handle
             return torch.empty(0, dtype=dtype).set_(fn(*args), 0, shape)
-
-        # PushGather maps its peers through raw CUDA IPC on the GPU; on the host the shared-memory tensors stand in
-        _export_raw = _export
-        _import_raw = _import
 
     return HostGather
 
@@ -198,58 +195,6 @@ def test_push_gather_protocol_two_processes_gloo():
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(results) == [(r, True) for r in range(world)]
-
-
-def _peer_worker(rank, world, port, q):
-    """sharded.PeerGather (pull from the peers' export rings) with the same host substitutes: 7 batches through a ring
-    of depth 2, overlapped use (start batch t, then read batch t-1), against the plain all-gather."""
-    import os
-    import torch.distributed as dist
-    from epropnp_b200.sharded import PeerGather, gather_results
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    torch.multiprocessing.set_sharing_strategy("file_system")
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        per, M = 5, 12
-        num_obj = per * world
-        g = torch.Generator().manual_seed(100 + rank)
-        pg, ok, pending, expected = None, True, None, None
-        for step in range(7):
-            local = dict(pose_opt=torch.randn(per, 7, generator=g), logw=torch.randn(per, M, generator=g))
-            want = gather_results(local, num_obj, keys=("pose_opt", "logw"))
-            if pg is None:
-                pg = _host_class(PeerGather)(local, num_obj, keys=("pose_opt", "logw"), depth=2)
-            nxt = pg.start(local)
-            if pending is not None:
-                got = pending.wait()
-                ok = ok and all(torch.equal(got[k], expected[k]) for k in expected)
-            pending, expected = nxt, want
-        got = pending.wait()
-        ok = ok and all(torch.equal(got[k], expected[k]) for k in expected)
-        dist.barrier()
-        q.put((rank, bool(ok)))
-    finally:
-        dist.destroy_process_group()
-
-
-def test_peer_gather_protocol_two_processes_gloo():
-    import socket
-    import torch.multiprocessing as mp
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    world = 2
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
-    for pr in procs:
-        pr.start()
-    results = [q.get(timeout=240) for _ in range(world)]
-    for pr in procs:
-        pr.join(timeout=60)
-    assert sorted(results) == [(r, True) for r in range(world)]
-
 
 def test_push_and_epilogue_do_not_depend_on_thread_schedule(dev):
     """Missing-barrier probe (as tests/test_simt_emul_cpu.py does for the validated kernels): the fibers of a CTA run in
