@@ -397,13 +397,32 @@ __device__ void amis_phase4(const KArgs& a, AmisHead<4, T>& sh, const float* pts
 // log-weights into row (obj_offset + obj) of the full-batch result buffers of up to EPNP_MAX_PEERS other GPUs (pointers
 // into their memory, mapped through CUDA IPC): plain st.global over NVLink, 2 KB + 28 B per object and peer, issued
 // object by object underneath the other CTAs' math.  No gather kernel and no copy afterwards; the caller only needs a
-// rendezvous before reading (sharded.PushGather).
+// rendezvous before reading (sharded.PushGather).  The peers' buffer addresses come as two DEVICE arrays of pointers
+// (like a batched-BLAS pointer array): the kernel takes 20 bytes of parameters for the feature, not a 136-byte table.
 constexpr int EPNP_MAX_PEERS = 8;
 struct PushArgs {
-    float* logw[EPNP_MAX_PEERS];            // (B_total, M) on each peer
-    float* pose[EPNP_MAX_PEERS];            // (B_total, D) on each peer
+    float* const* logw;                     // device array [n]: (B_total, M) buffer of each peer
+    float* const* pose;                     // device array [n]: (B_total, D) buffer of each peer
     int n;
 };
+
+// The push epilogue of one object: its M log-weights (as this CTA wrote them to global memory) and its pose go to row
+// `row` of every peer's buffers.  Not inlined: it must not take part in the main body's register allocation (inlined,
+// the kernel ran 4 % slower for every caller, pushing or not: 0.972 vs 0.934 ms per 4096 objects).
+template <int T>
+__device__ __noinline__ void push_rows(const float* src, const float* pose, size_t row, int M, int PD,
+                                       float* const* peer_logw, float* const* peer_pose, int n) {
+    const int tid = threadIdx.x;
+    for (int r = 0; r < n; ++r) {
+        float* dst = peer_logw[r] + row * M;
+        if ((M & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0) {
+            for (int q = tid; q < M / 4; q += T) reinterpret_cast<float4*>(dst)[q] = reinterpret_cast<const float4*>(src)[q];
+        } else {
+            for (int m = tid; m < M; m += T) dst[m] = src[m];
+        }
+        if (tid < PD) peer_pose[r][row * PD + tid] = pose[tid];
+    }
+}
 
 // One object per CTA of T threads (blockIdx.x = object).
 template <int DOF, int T>
@@ -444,34 +463,13 @@ __global__ void __launch_bounds__(T, T == NT ? AMIS_CTAS_PER_SM : 1) amis_kernel
     PH_MARK(a, PH_LOAD);
     if constexpr (DOF == 6) amis_phase6<T>(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.cpart, cam, delta, obj);
     else amis_phase4<T>(a, sh, pts4, dyn + pl.smp, dyn + pl.cost, dyn + pl.logp, dyn + pl.cpart, cam, delta, obj);
-    // In-kernel gather (push.n > 0, uniform for the launch): the object's log-weights, as this CTA wrote them, and its
-    // pose go to the same global row on every peer.  A run-time branch of ONE kernel, not a second instantiation: a
-    // sharded run must be bit-identical to the single-GPU run, and two instantiations are two compilations -- as
+    // In-kernel gather (push.n > 0, uniform for the launch).  A run-time branch of ONE kernel, not a second instantiation:
+    // a sharded run must be bit-identical to the single-GPU run, and two instantiations are two compilations -- as
     // template variants the push / plain pair agreed bit for bit at N = 64, 512, 2052 but not on two small problems
     // (N = 51, 130: log-weights 4e-6 apart after one step, profiles/r2_sanitizer_two_instantiations.txt).
     if (push.n > 0) {
         __syncthreads();                                        // the CTA's own global stores are visible to all its threads
-        const size_t row = (size_t)a.obj_offset + (size_t)obj;
-        const float* src = a.logw + (size_t)obj * M;
-        if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-            for (int q = tid; q < M / 4; q += T) {
-                const float4 v = reinterpret_cast<const float4*>(src)[q];
-                for (int r = 0; r < push.n; ++r) {
-                    float* dst = push.logw[r] + row * M;
-                    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) reinterpret_cast<float4*>(dst)[q] = v;
-                    else { dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w; }
-                }
-            }
-        } else {
-            for (int m = tid; m < M; m += T) {
-                const float v = src[m];
-                for (int r = 0; r < push.n; ++r) push.logw[r][row * M + m] = v;
-            }
-        }
-        if (tid < PD) {
-            const float v = sh.pose[tid];
-            for (int r = 0; r < push.n; ++r) push.pose[r][row * PD + tid] = v;
-        }
+        push_rows<T>(a.logw + (size_t)obj * M, sh.pose, (size_t)a.obj_offset + (size_t)obj, M, PD, push.logw, push.pose, push.n);
     }
 }
 

@@ -1050,12 +1050,7 @@ int epnp_lm_amis_fused_push_f32(const float* x3d, const float* x2d, const float*
     rc = check_amis_params(*p);
     if (rc != EPNP_OK) return rc;
     if (!pose_init || !pose_opt || !pose_samples || !logw || p->lm_iter < 0) return EPNP_ERR_BAD_ARG;
-    PushArgs push{};
-    push.n = n_peers;
-    for (int r = 0; r < n_peers; ++r) {
-        if (!peer_logw[r] || !peer_pose[r]) return EPNP_ERR_BAD_ARG;
-        push.logw[r] = peer_logw[r]; push.pose[r] = peer_pose[r];
-    }
+    PushArgs push{peer_logw, peer_pose, n_peers};
     return run_lm_amis(a, &push, (cudaStream_t)stream);
 }
 

@@ -237,42 +237,63 @@ def lm_amis_fused(prob: Problem, pose_init, params, noise=None, seed=0, obj_offs
     return out
 
 
+def peer_table(buffers, device):
+    """Device array of pointers (int64 tensor) to the peers' buffers: tensors in other GPUs' memory or raw device
+    pointers (ints) of IPC-mapped buffers (sharded.raw_ipc_open).  Build it ONCE per set of buffers: creating a device
+    tensor from host data is a synchronous copy on the current stream."""
+    return torch.tensor([t if isinstance(t, int) else t.data_ptr() for t in buffers] or [0], dtype=torch.int64, device=device)
+
+
 def lm_amis_fused_push(prob: Problem, pose_init, params, pose_opt_out, logw_out, peer_logw, peer_pose, seed=0,
-                       obj_offset=0, want_cost=False, want_cov=False):
+                       obj_offset=0, want_cost=False, want_cov=False, n_peers=None):
     """Fused solve + in-kernel gather (epnp_lm_amis_fused_push_f32).  pose_opt_out (B, D) / logw_out (B, M): where the
     LOCAL results go (contiguous; normally rows [obj_offset, obj_offset + B) of this rank's own full-batch buffers);
-    peer_logw / peer_pose: lists (<= 8) of full-batch (B_total, M) / (B_total, D) float32 tensors in OTHER GPUs'
-    memory; the kernel writes this rank's rows into each of them.  Returns dict(pose_opt, logw, pose_samples, cost,
-    pose_cov) of local tensors."""
+    peer_logw / peer_pose: the full-batch (B_total, M) / (B_total, D) float32 buffers in OTHER GPUs' memory the kernel
+    also writes this rank's rows into -- lists (<= 8) of tensors / raw pointers, or, for a steady-state loop, the
+    peer_table() of each list built once (then `n_peers` = how many entries are in use).  Returns dict(pose_opt, logw,
+    pose_samples, cost, pose_cov) of local tensors."""
     D = 7 if params.dof == 6 else 4
     B, M = prob.B, params.mc_samples
-    if len(peer_logw) != len(peer_pose) or len(peer_logw) > 8:
-        raise ValueError("peer_logw / peer_pose: equally long lists of at most 8 tensors")
     for t, shape in ((pose_opt_out, (B, D)), (logw_out, (B, M))):
         if tuple(t.shape) != shape or t.dtype != torch.float32 or not t.is_contiguous():
             raise ValueError(f"local output must be contiguous float32 {shape}")
-    for lw, ps in zip(peer_logw, peer_pose):
-        if isinstance(lw, int) and isinstance(ps, int):      # raw device pointers of IPC-mapped peer buffers (sharded.raw_ipc_open)
-            continue
-        if lw.dtype != torch.float32 or ps.dtype != torch.float32 or not lw.is_contiguous() or not ps.is_contiguous() \
-                or lw.dim() != 2 or lw.shape[1] != M or ps.dim() != 2 or ps.shape[1] != D \
-                or lw.shape[0] < obj_offset + B or ps.shape[0] < obj_offset + B:
-            raise ValueError("peer buffers must be contiguous float32 (B_total, M) / (B_total, D) with "
-                             "B_total >= obj_offset + B")
+    if torch.is_tensor(peer_logw) != torch.is_tensor(peer_pose):
+        raise ValueError("peer_logw / peer_pose: both lists or both peer_table() tensors")
+    if torch.is_tensor(peer_logw):
+        n = int(n_peers if n_peers is not None else peer_logw.numel())
+        for t in (peer_logw, peer_pose):
+            if t.dtype != torch.int64 or not t.is_contiguous() or t.numel() < max(n, 1) or t.device != prob.device:
+                raise ValueError("peer tables: contiguous int64 tensors on the solving device (native.peer_table)")
+        tab_lw, tab_ps = peer_logw, peer_pose
+    else:
+        if len(peer_logw) != len(peer_pose) or len(peer_logw) > 8:
+            raise ValueError("peer_logw / peer_pose: equally long lists of at most 8 buffers")
+        for lw, ps in zip(peer_logw, peer_pose):
+            if isinstance(lw, int) and isinstance(ps, int):      # raw device pointers of IPC-mapped peer buffers
+                continue
+            if lw.dtype != torch.float32 or ps.dtype != torch.float32 or not lw.is_contiguous() or not ps.is_contiguous() \
+                    or lw.dim() != 2 or lw.shape[1] != M or ps.dim() != 2 or ps.shape[1] != D \
+                    or lw.shape[0] < obj_offset + B or ps.shape[0] < obj_offset + B:
+                raise ValueError("peer buffers must be contiguous float32 (B_total, M) / (B_total, D) with "
+                                 "B_total >= obj_offset + B")
+        n = len(peer_logw)
+        tab_lw, tab_ps = peer_table(peer_logw, prob.device), peer_table(peer_pose, prob.device)
+    if n > 8:
+        raise ValueError("the kernel pushes to at most 8 peers")
     pose_init = _f32c(pose_init)
     out = dict(pose_opt=pose_opt_out, logw=logw_out, pose_samples=prob.empty(B, M, D),
                cost=prob.empty(B) if want_cost else None,
                pose_cov=prob.empty(B, params.dof, params.dof) if want_cov else None)
-    n = len(peer_logw)
-    arr_lw = (ctypes.c_void_p * max(n, 1))(*[t if isinstance(t, int) else t.data_ptr() for t in peer_logw])
-    arr_ps = (ctypes.c_void_p * max(n, 1))(*[t if isinstance(t, int) else t.data_ptr() for t in peer_pose])
     with torch.cuda.device(prob.device):
         check(lib().epnp_lm_amis_fused_push_f32(*prob.common_ptrs(), ptr(pose_init), ctypes.c_uint64(seed),
                                                 ctypes.c_uint32(obj_offset), ptr(out["pose_opt"]), ptr(out["pose_cov"]),
                                                 ptr(out["cost"]), ptr(out["pose_samples"]), ptr(out["logw"]),
-                                                ctypes.cast(arr_lw, ctypes.c_void_p), ctypes.cast(arr_ps, ctypes.c_void_p), n,
+                                                ctypes.c_void_p(tab_lw.data_ptr()), ctypes.c_void_p(tab_ps.data_ptr()), n,
                                                 B, prob.N, ctypes.byref(params), stream_ptr(prob.device)),
               "epnp_lm_amis_fused_push_f32")
+    if not torch.is_tensor(peer_logw) and tab_lw.is_cuda:
+        tab_lw.record_stream(torch.cuda.current_stream(prob.device))       # the kernel reads the tables after we return
+        tab_ps.record_stream(torch.cuda.current_stream(prob.device))
     return out
 
 

@@ -236,6 +236,13 @@ class PushGather(_DeviceHooks):
                 self.peers.append(None)
                 continue
             self.peers.append([{k: self._import_raw(h) for k, h in slot.items()} for slot in theirs["ring"]])
+        # per ring slot: the device arrays of pointers the kernel reads its peers' buffer addresses from (built once)
+        from . import native
+        others = [r for r in range(self.world) if r != self.rank]
+        self.n_peers = len(others)
+        self.tables = [(native.peer_table([self.peers[r][s]["logw"] for r in others], self.device),
+                        native.peer_table([self.peers[r][s]["pose_opt"] for r in others], self.device))
+                       for s in range(self.depth)]
         self._device_synchronize()
         self.met = {}                         # batch index -> event of its rendezvous (last `depth` kept)
         self.step = 0
@@ -252,12 +259,9 @@ class PushGather(_DeviceHooks):
         gate = self.met.get(t - (self.depth - self.valid_for))
         if gate is not None:
             cur.wait_event(gate)              # every rank is past its reads of the slot this batch overwrites
-        others = [r for r in range(self.world) if r != self.rank]
         out = native.lm_amis_fused_push(prob, pose_init, params, self.ring[s]["pose_opt"][lo:hi],
-                                        self.ring[s]["logw"][lo:hi],
-                                        [self.peers[r][s]["logw"] for r in others],
-                                        [self.peers[r][s]["pose_opt"] for r in others],
-                                        seed=seed, obj_offset=lo, want_cost=want_cost, want_cov=want_cov)
+                                        self.ring[s]["logw"][lo:hi], self.tables[s][0], self.tables[s][1],
+                                        seed=seed, obj_offset=lo, want_cost=want_cost, want_cov=want_cov, n_peers=self.n_peers)
         ready = self._new_event()
         ready.record(cur)
         with self._on_stream(self.comm):

@@ -177,7 +177,9 @@ int epnp_lm_amis_fused_f32(const float* x3d, const float* x2d, const float* w2d,
  * OTHER GPUs' memory -- peer_logw[r] (B_total, M), peer_pose[r] (B_total, D), device pointers the caller obtained with
  * cudaIpcOpenMemHandle(..., cudaIpcMemLazyEnablePeerAccess) WHILE THIS DEVICE WAS CURRENT (a mapping opened under the
  * exporting device's index is not dereferenceable by this device's kernels) -- with plain stores over NVLink, object
- * by object underneath the remaining math.
+ * by object underneath the remaining math.  peer_logw / peer_pose themselves are DEVICE arrays of n_peers pointers (in
+ * this device's memory, like a batched-BLAS pointer array; the kernel reads them when an object finishes): built once
+ * per set of buffers, they must stay valid until the launch has completed.
  * There is no gather kernel and no copy afterwards (what replaces the NCCL all-gather of SURVEY.md section 8e); the
  * caller needs one rendezvous of the ranks before it reads its own full-batch buffer.  pose_opt / logw are the LOCAL
  * outputs as before -- typically the local slice [obj_offset, obj_offset + B) of this rank's own full-batch buffers.
