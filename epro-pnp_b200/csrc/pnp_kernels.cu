@@ -180,21 +180,27 @@ __global__ void __launch_bounds__(NT, 2) rslm_kernel(const RslmArgs r) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// The random draws of RSLMSolver.solve (levenberg_marquardt.py:306-324), one CTA per object, thread <-> hypothesis:
-//   * n DISTINCT correspondence indices, drawn without replacement with probabilities proportional to
-//     wbar_i = mean(w2d[i, :]) -- torch.multinomial(wbar, n) (:306-312).  Same algorithm as torch's: an exponential
-//     race, the n smallest of E_i / wbar_i with E_i ~ Exp(1) (Efraimidis-Spirakis); a weight that is not positive is
-//     never drawn.  The race keeps its n current winners in shared memory ([slot][thread]: conflict-free) together with
-//     the position of the worst of them, so an element costs one compare unless it enters the list
-//     (~ n (1 + ln(N / n)) times per hypothesis).
-//   * the starting pose: the object's centre-based translation with a uniformly random orientation -- a normalised
-//     Gaussian quaternion, (1,0,0,0) when its norm is below eps (:318-324), or a yaw uniform on [0, 2 pi) (:316-317).
+// Everything RSLMSolver.solve does before its solves (levenberg_marquardt.py:283-324), one CTA per object:
+//   * the centre-based translation guess (center_based_init, :283-298): rays = K^-1 [u v 1] dehomogenised, direction =
+//     (mean ray, 1), depth = spread of the 3D points over spread of the rays (unbiased standard deviations: y-extent
+//     for 4DoF, sqrt(2/3) |std3d| / |std ray| for 6DoF) -- two block reductions over the N points; skipped when the
+//     caller passes its own t_init;
+//   * per hypothesis (thread <-> hypothesis) n DISTINCT correspondence indices, drawn without replacement with
+//     probabilities proportional to wbar_i = mean(w2d[i, :]) -- torch.multinomial(wbar, n) (:306-312).  Same algorithm
+//     as torch's: an exponential race, the n smallest of E_i / wbar_i with E_i ~ Exp(1) (Efraimidis-Spirakis); a weight
+//     that is not positive is never drawn.  The race keeps its n current winners in shared memory ([slot][thread]:
+//     conflict-free) with the position of the worst of them; once the list is full an element is rejected by one
+//     multiply and compare (E >= 1 - u), and pays for a logarithm only when it might enter
+//     (~ n (1 + ln(N / n)) times per hypothesis);
+//   * the starting pose: that translation with a uniformly random orientation -- a normalised Gaussian quaternion,
+//     (1,0,0,0) when its norm is below eps (:318-324), or a yaw uniform on [0, 2 pi) (:316-317).
 // Philox-4x32-10 keyed by (seed; global object index, hypothesis, block): independent of B, P tiling and launch shape.
 struct RslmDrawArgs {
-    const float* w2d;           // (B, N, 2)
-    const float* t_init;        // (B, 3)
-    int* inds;                  // (P, B, n)
-    float* start;               // (P, B, D)
+    const float *x3d, *x2d, *w2d, *cam;     // (B, N, 3), (B, N, 2), (B, N, 2), (B, 3, 3)
+    const float* t_init;                    // [opt] (B, 3): overrides the centre-based guess
+    int* inds;                              // (P, B, n)
+    float* start;                           // (P, B, D)
+    float* t_out;                           // [opt] (B, 3): the translation guess that was used
     uint64_t seed;
     uint32_t obj_offset;
     int P, n, B, N;
@@ -206,6 +212,8 @@ constexpr uint32_t RSLM_TAG_SUBSET = 0x52534c4du, RSLM_TAG_START = 0x52534c53u;
 template <int DOF>
 __global__ void __launch_bounds__(NT) rslm_draw_kernel(const RslmDrawArgs r) {
     EPNP_DYN_SMEM(unsigned char, smem_raw, 16);
+    __shared__ float red[2 * NT];
+    __shared__ float t0[3];
     float* wbar = reinterpret_cast<float*>(smem_raw);                       // [N]
     float* keys = wbar + ((r.N + 3) & ~3);                                  // [n][NT]
     int* slots = reinterpret_cast<int*>(keys + (size_t)r.n * NT);           // [n][NT]
@@ -216,7 +224,56 @@ __global__ void __launch_bounds__(NT) rslm_draw_kernel(const RslmDrawArgs r) {
         const float2 w = *reinterpret_cast<const float2*>(r.w2d + ((size_t)obj * r.N + i) * 2);
         wbar[i] = 0.5f * (w.x + w.y);
     }
+    if (r.t_init) {
+        if (tid < 3) t0[tid] = __ldg(r.t_init + (size_t)obj * 3 + tid);
+    } else {
+        // K^-1 by the adjugate (general 3x3), then mean / unbiased variance of the two ray coordinates and of x3d
+        float k[9], inv[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) k[i] = __ldg(r.cam + (size_t)obj * 9 + i);
+        inv[0] = k[4] * k[8] - k[5] * k[7]; inv[1] = k[2] * k[7] - k[1] * k[8]; inv[2] = k[1] * k[5] - k[2] * k[4];
+        inv[3] = k[5] * k[6] - k[3] * k[8]; inv[4] = k[0] * k[8] - k[2] * k[6]; inv[5] = k[2] * k[3] - k[0] * k[5];
+        inv[6] = k[3] * k[7] - k[4] * k[6]; inv[7] = k[1] * k[6] - k[0] * k[7]; inv[8] = k[0] * k[4] - k[1] * k[3];
+        const float idet = 1.0f / (k[0] * inv[0] + k[1] * inv[3] + k[2] * inv[6]);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) inv[i] *= idet;
+        const float* g2 = r.x2d + (size_t)obj * r.N * 2;
+        const float* g3 = r.x3d + (size_t)obj * r.N * 3;
+        auto ray = [&](int i, float& rx, float& ry) {
+            const float u = __ldg(g2 + 2 * i), v = __ldg(g2 + 2 * i + 1);
+            const float z = fmaxf(inv[6] * u + inv[7] * v + inv[8], 1e-6f);
+            rx = (inv[0] * u + inv[1] * v + inv[2]) / z;
+            ry = (inv[3] * u + inv[4] * v + inv[5]) / z;
+        };
+        float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = tid; i < r.N; i += NT) {
+            float rx, ry;
+            ray(i, rx, ry);
+            m[0] += rx; m[1] += ry; m[2] += __ldg(g3 + 3 * i); m[3] += __ldg(g3 + 3 * i + 1); m[4] += __ldg(g3 + 3 * i + 2);
+        }
+        block_sum<5>(m, red, 0);
+        const float in = 1.0f / (float)r.N;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) m[c] *= in;
+        float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = tid; i < r.N; i += NT) {
+            float rx, ry;
+            ray(i, rx, ry);
+            const float d0 = rx - m[0], d1 = ry - m[1], d2 = __ldg(g3 + 3 * i) - m[2], d3 = __ldg(g3 + 3 * i + 1) - m[3],
+                        d4 = __ldg(g3 + 3 * i + 2) - m[4];
+            v[0] += d0 * d0; v[1] += d1 * d1; v[2] += d2 * d2; v[3] += d3 * d3; v[4] += d4 * d4;
+        }
+        block_sum<5>(v, red, 1);
+        if (tid == 0) {
+            const float iv = 1.0f / (float)max(r.N - 1, 1);             // unbiased (torch.std's default)
+            float depth;
+            if (DOF == 4) depth = sqrtf(v[3] * iv) / fmaxf(sqrtf(v[1] * iv), 1e-6f);
+            else depth = 0.816496580927726f * sqrtf((v[2] + v[3] + v[4]) * iv) / fmaxf(sqrtf((v[0] + v[1]) * iv), 1e-6f);
+            t0[0] = m[0] * depth; t0[1] = m[1] * depth; t0[2] = depth;
+        }
+    }
     __syncthreads();
+    if (r.t_out && tid < 3) r.t_out[(size_t)obj * 3 + tid] = t0[tid];
     const Philox ph{(uint32_t)r.seed, (uint32_t)(r.seed >> 32)};
     for (int h = tid; h < r.P; h += NT) {
         int cnt = 0, worst = 0;
@@ -230,7 +287,9 @@ __global__ void __launch_bounds__(NT) rslm_draw_kernel(const RslmDrawArgs r) {
                 if (i >= r.N) break;
                 const float w = wbar[i];
                 if (!(w > 0.0f)) continue;
-                const float key = -fast_log(u01(u[j])) / w;
+                const float uu = u01(u[j]);
+                if (cnt == r.n && (1.0f - uu) >= thr * w) continue;        // E = -log u >= 1 - u: cannot beat the worst winner
+                const float key = -fast_log(uu) / w;
                 if (cnt < r.n) {
                     keys[cnt * NT + tid] = key; slots[cnt * NT + tid] = i;
                     if (key > thr) { thr = key; worst = cnt; }
@@ -253,7 +312,7 @@ __global__ void __launch_bounds__(NT) rslm_draw_kernel(const RslmDrawArgs r) {
         int* out = r.inds + ((size_t)h * r.B + obj) * r.n;
         for (int s = 0; s < r.n; ++s) out[s] = slots[s * NT + tid];
         float* st = r.start + ((size_t)h * r.B + obj) * PD;
-        st[0] = __ldg(r.t_init + (size_t)obj * 3); st[1] = __ldg(r.t_init + (size_t)obj * 3 + 1); st[2] = __ldg(r.t_init + (size_t)obj * 3 + 2);
+        st[0] = t0[0]; st[1] = t0[1]; st[2] = t0[2];
         uint32_t v[4];
         ph(gobj, (uint32_t)h, 0u, RSLM_TAG_START, v);
         if (DOF == 4) {
@@ -958,14 +1017,16 @@ int epnp_rslm_f32(const float* x3d, const float* x2d, const float* w2d, const fl
     return e == cudaSuccess ? EPNP_OK : cuda_fail(e);
 }
 
-int epnp_rslm_draw_f32(const float* w2d, const float* t_init, uint64_t seed, uint32_t obj_offset, int* inds, float* start,
+int epnp_rslm_draw_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats, const float* t_init,
+                       uint64_t seed, uint32_t obj_offset, int* inds, float* start, float* t_out,
                        int P, int n, int B, int N, int dof, float eps, void* stream) {
-    if (!w2d || !t_init || !inds || !start || (dof != 4 && dof != 6) || P <= 0 || n <= 0 || B < 0 || N <= 0 || n > N)
+    if (!w2d || !inds || !start || (dof != 4 && dof != 6) || P <= 0 || n <= 0 || B < 0 || N <= 0 || n > N)
         return EPNP_ERR_BAD_ARG;
+    if (!t_init && (!x3d || !x2d || !cam_mats)) return EPNP_ERR_BAD_ARG;
     if (B == 0) return EPNP_OK;
     const size_t smem = (size_t)((N + 3) & ~3) * sizeof(float) + (size_t)n * NT * (sizeof(float) + sizeof(int));
-    if (smem > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
-    RslmDrawArgs r{w2d, t_init, inds, start, seed, obj_offset, P, n, B, N, eps};
+    if (smem + 2048 > SMEM_LIMIT) return EPNP_ERR_TOO_MANY_POINTS;
+    RslmDrawArgs r{x3d, x2d, w2d, cam_mats, t_init, inds, start, t_out, seed, obj_offset, P, n, B, N, eps};
     cudaError_t e;
     if (dof == 6) {
         e = cudaFuncSetAttribute(rslm_draw_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

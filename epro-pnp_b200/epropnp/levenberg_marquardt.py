@@ -186,9 +186,9 @@ class RSLMSolver(LMSolver):
     def solve(self, x3d, x2d, w2d, camera, cost_fun, **kwargs):
         """-> pose (B, 4|7), None, min_cost (B).
 
-        Two launches after the centre-based translation guess: the random draws (epnp_rslm_draw_f32: per (proposal,
-        object) a weighted subset without replacement and a random start orientation; 0.1 ms where torch.multinomial on
-        the (P*B, N) weight rows took 8 ms at B = 4096, profiles/r2_side_kernels.jsonl) and the solve (epnp_rslm_f32: one
+        Two launches: the set-up (epnp_rslm_draw_f32: the centre-based translation guess and, per (proposal, object), a
+        weighted subset without replacement and a random start orientation -- torch.multinomial on the (P*B, N) weight
+        rows alone took 8 ms at B = 4096, profiles/r2_side_kernels.jsonl) and the solve (epnp_rslm_f32: one
         CTA per object, thread <-> hypothesis, LM / GN on the n sampled correspondences read from the object's resident
         pair records, scored on all N points, cheapest kept).  The reference's gather of (P*B, n, .) mini-problems, its
         P-fold repeated camera / cost objects and its P*B tiny solves do not exist; run on the same kernels that
@@ -208,8 +208,11 @@ class RSLMSolver(LMSolver):
         else:
             seed = kwargs.get("rslm_seed")
             seed = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
-            inds, start = native.rslm_draw(w2d, self.center_based_init(x2d, x3d, camera), P, n, self.dof, eps=self.eps,
-                                           seed=seed)
+            # a subclass that overrides center_based_init keeps its say; otherwise the kernel computes the guess itself
+            own_guess = type(self).center_based_init is not RSLMSolver.center_based_init
+            t_init = self.center_based_init(x2d, x3d, camera) if own_guess else None
+            inds, start = native.rslm_draw(x3d, x2d, w2d, camera.cam_mats, P, n, self.dof, eps=self.eps, seed=seed,
+                                           t_init=t_init)
         prob = native.Problem(x3d, x2d, w2d, camera.cam_mats, camera.lb, camera.ub, cost_fun.delta)
         out = native.rslm(prob, inds, start, self.native_params(camera, cost_fun, kwargs.get("fast_mode", False)))
         return out["pose"].to(x2d.dtype), None, out["cost"].to(x2d.dtype)

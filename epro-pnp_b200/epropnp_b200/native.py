@@ -134,25 +134,36 @@ def lm_solve(prob: Problem, pose_init, params, want_cov=False, want_cost=False, 
     return out
 
 
-def rslm_draw(w2d, t_init, P, n, dof, eps=1e-5, seed=0, obj_offset=0):
-    """The initialiser's random draws in one launch (epnp_rslm_draw_f32): w2d (B, N, 2), t_init (B, 3) ->
-    inds (P, B, n) int32 (weighted, without replacement, per proposal and object), start (P, B, D) (t_init + a
-    uniformly random orientation)."""
+def rslm_draw(x3d, x2d, w2d, cam_mats, P, n, dof, eps=1e-5, seed=0, obj_offset=0, t_init=None, want_t=False):
+    """Everything before the solves of the random-sample initialiser in one launch (epnp_rslm_draw_f32): the
+    centre-based translation guess (unless t_init (B, 3) is given -- then x3d / x2d / cam_mats may be None), inds
+    (P, B, n) int32 (weighted subsets without replacement, per proposal and object) and start (P, B, D) (that translation
+    + a uniformly random orientation).  -> inds, start [, t (B, 3) with want_t]."""
     _need_cuda(w2d, "w2d")
     if w2d.dim() != 3 or w2d.shape[-1] != 2:
         raise ValueError(f"w2d must be (B, N, 2), got {tuple(w2d.shape)}")
     B, N = w2d.shape[0], w2d.shape[1]
-    if tuple(t_init.shape) != (B, 3):
-        raise ValueError(f"t_init must be ({B}, 3), got {tuple(t_init.shape)}")
+    dev = w2d.device
+    if t_init is not None:
+        if tuple(t_init.shape) != (B, 3):
+            raise ValueError(f"t_init must be ({B}, 3), got {tuple(t_init.shape)}")
+        t_init = _f32c(t_init.to(dev))
+        x3d = x2d = cam_mats = None
+    else:
+        for t, shape, what in ((x3d, (B, N, 3), "x3d"), (x2d, (B, N, 2), "x2d"), (cam_mats, (B, 3, 3), "cam_mats")):
+            if t is None or tuple(t.shape) != shape or t.device != dev:
+                raise ValueError(f"{what} must be {shape} on {dev}")
+        x3d, x2d, cam_mats = _f32c(x3d), _f32c(x2d), _f32c(cam_mats)
     D = 7 if dof == 6 else 4
-    w2d, t_init = _f32c(w2d), _f32c(t_init.to(w2d.device))
-    inds = torch.empty(P, B, n, dtype=torch.int32, device=w2d.device)
-    start = torch.empty(P, B, D, dtype=torch.float32, device=w2d.device)
-    with torch.cuda.device(w2d.device):
-        check(lib().epnp_rslm_draw_f32(ptr(w2d), ptr(t_init), ctypes.c_uint64(seed), ctypes.c_uint32(obj_offset),
-                                       capi.iptr(inds), ptr(start), P, n, B, N, dof, ctypes.c_float(eps),
-                                       stream_ptr(w2d.device)), "epnp_rslm_draw_f32")
-    return inds, start
+    w2d = _f32c(w2d)
+    inds = torch.empty(P, B, n, dtype=torch.int32, device=dev)
+    start = torch.empty(P, B, D, dtype=torch.float32, device=dev)
+    t_out = torch.empty(B, 3, dtype=torch.float32, device=dev) if want_t else None
+    with torch.cuda.device(dev):
+        check(lib().epnp_rslm_draw_f32(ptr(x3d), ptr(x2d), ptr(w2d), ptr(cam_mats), ptr(t_init), ctypes.c_uint64(seed),
+                                       ctypes.c_uint32(obj_offset), capi.iptr(inds), ptr(start), ptr(t_out), P, n, B, N, dof,
+                                       ctypes.c_float(eps), stream_ptr(dev)), "epnp_rslm_draw_f32")
+    return (inds, start, t_out) if want_t else (inds, start)
 
 
 def rslm(prob: Problem, inds, start, params, want_all=False):

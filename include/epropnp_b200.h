@@ -105,16 +105,21 @@ int epnp_gn_plus_backward_f32(const float* x3d, const float* x2d, const float* w
                               float* grad_delta, int B, int N, int dof, float z_min, float eps, float huber_eps,
                               void* stream);
 
-/* The random draws of RSLMSolver.solve (levenberg_marquardt.py:306-324) in one launch:
+/* Everything RSLMSolver.solve does before its solves (levenberg_marquardt.py:283-324) in one launch:
+ *   the centre-based translation guess (center_based_init, :283-298: mean ray direction times the ratio of the 3D spread
+ *     to the ray spread), computed per object unless t_init (B, 3) is given; written to t_out [opt] (B, 3);
  *   inds (P, B, n) int32: per (proposal, object) n distinct correspondence indices drawn WITHOUT replacement with
  *     probabilities proportional to mean(w2d, -1) -- torch.multinomial(mean_weight, num_points) (:306-309), by the
  *     same exponential race (the n smallest E_i / w_i, E_i ~ Exp(1)); a weight <= 0 is never drawn while a positive
  *     one is left (the reference raises when fewer than n are positive; here the subset is completed in index order);
- *   start (P, B, D): t_init (B, 3) (center_based_init, :314) + a uniformly random orientation: normalised Gaussian
- *     quaternion, (1,0,0,0) when its norm < eps (:319-324), or a yaw uniform on [0, 2 pi) (:316-317).
+ *   start (P, B, D): that translation (:314) + a uniformly random orientation: normalised Gaussian quaternion,
+ *     (1,0,0,0) when its norm < eps (:319-324), or a yaw uniform on [0, 2 pi) (:316-317).
+ * x3d / x2d / cam_mats may be NULL when t_init is given.
  * Philox-4x32-10 keyed by (seed; obj_offset + object, proposal): a batch shard draws what the whole batch would.   */
-int epnp_rslm_draw_f32(const float* w2d, const float* t_init, uint64_t seed, uint32_t obj_offset,
-                       int* inds, float* start, int P, int n, int B, int N, int dof, float eps, void* stream);
+int epnp_rslm_draw_f32(const float* x3d, const float* x2d, const float* w2d, const float* cam_mats,
+                       const float* t_init, uint64_t seed, uint32_t obj_offset,
+                       int* inds, float* start, float* t_out,
+                       int P, int n, int B, int N, int dof, float eps, void* stream);
 
 /* RSLMSolver.solve after the hypotheses are drawn (levenberg_marquardt.py:300-353): for every object, P starting
  * poses, each refined by LM / GN on its own n sampled correspondences, scored on all N correspondences, cheapest

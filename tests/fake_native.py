@@ -105,10 +105,12 @@ def rslm(prob, inds, start, params, want_all=False):
                 cost_all=r["hyp_cost"] if want_all else None)
 
 
-def rslm_draw(w2d, t_init, P, n, dof, eps=1e-5, seed=0, obj_offset=0):
+def rslm_draw(x3d, x2d, w2d, cam_mats, P, n, dof, eps=1e-5, seed=0, obj_offset=0, t_init=None, want_t=False):
     """The reference's own draws (levenberg_marquardt.py:306-324) from a torch generator seeded with `seed`."""
     g = torch.Generator().manual_seed(int(seed) % (2 ** 63))
     B, N = w2d.shape[0], w2d.shape[1]
+    if t_init is None:
+        t_init = orc.center_based_init(x2d.detach(), x3d.detach(), orc.Camera(cam_mats), dof)
     rows = w2d.detach().mean(dim=-1).unsqueeze(0).expand(P, B, N).reshape(P * B, N)
     inds = torch.multinomial(rows.double(), n, generator=g).reshape(P, B, n).to(torch.int32)
     start = t_init.new_empty((P, B, 7 if dof == 6 else 4))
@@ -119,7 +121,7 @@ def rslm_draw(w2d, t_init, P, n, dof, eps=1e-5, seed=0, obj_offset=0):
         q = torch.randn((P, B, 4), generator=g, dtype=t_init.dtype)
         qn = q.norm(dim=-1, keepdim=True)
         start[..., 3:] = torch.where(qn < eps, q.new_tensor([1., 0., 0., 0.]), q / qn)
-    return inds, start
+    return (inds, start, t_init) if want_t else (inds, start)
 
 
 def cost_backward(prob, dof, z_min, poses_a, grad_a, poses_b=None, grad_b=None, want=(True, True, True, True)):

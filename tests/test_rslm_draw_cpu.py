@@ -36,21 +36,21 @@ def test_subsets_are_distinct_in_range_reproducible_and_tiling_invariant(dev):
     B, N, P, n = 3, 37, 200, 6
     w2d = _weights(B, N, 1, zero_every=5).to(dev)
     t0 = torch.arange(3 * B, dtype=torch.float32).reshape(B, 3).to(dev)
-    inds, start = native.rslm_draw(w2d, t0, P, n, 6, seed=11)
+    inds, start = native.rslm_draw(None, None, w2d, None, P, n, 6, seed=11, t_init=t0)
     assert inds.shape == (P, B, n) and inds.dtype == torch.int32 and start.shape == (P, B, 7)
     i = inds.cpu().numpy()
     assert i.min() >= 0 and i.max() < N
     assert all(len(set(row)) == n for row in i.reshape(-1, n))               # without replacement
     assert (i % 5 != 0).all()                                                 # zero-weight correspondences are never drawn
-    inds2, start2 = native.rslm_draw(w2d, t0, P, n, 6, seed=11)
+    inds2, start2 = native.rslm_draw(None, None, w2d, None, P, n, 6, seed=11, t_init=t0)
     assert torch.equal(inds, inds2) and torch.equal(start, start2)            # counter-based: same seed, same draws
-    inds3, _ = native.rslm_draw(w2d, t0, P, n, 6, seed=12)
+    inds3, _ = native.rslm_draw(None, None, w2d, None, P, n, 6, seed=12, t_init=t0)
     assert not torch.equal(inds, inds3)
     # object 1 drawn alone with its global index == object 1 drawn inside the batch (shards draw what the batch would)
-    alone_i, alone_s = native.rslm_draw(w2d[1:2], t0[1:2], P, n, 6, seed=11, obj_offset=1)
+    alone_i, alone_s = native.rslm_draw(None, None, w2d[1:2], None, P, n, 6, seed=11, obj_offset=1, t_init=t0[1:2])
     assert torch.equal(alone_i[:, 0], inds[:, 1]) and torch.equal(alone_s[:, 0], start[:, 1])
     # fewer proposals: a prefix of the same streams
-    few_i, few_s = native.rslm_draw(w2d, t0, 7, n, 6, seed=11)
+    few_i, few_s = native.rslm_draw(None, None, w2d, None, 7, n, 6, seed=11, t_init=t0)
     assert torch.equal(few_i, inds[:7]) and torch.equal(few_s, start[:7])
 
 
@@ -58,7 +58,7 @@ def test_first_pick_follows_the_weights(dev):
     """n = 1: P(i) = w_i / sum(w) exactly (the minimum of independent exponentials with rates w_i)."""
     N, P = 9, 8192
     w2d = _weights(1, N, 2).to(dev)
-    inds, _ = native.rslm_draw(w2d, torch.zeros(1, 3, device=dev), P, 1, 6, seed=5)
+    inds, _ = native.rslm_draw(None, None, w2d, None, P, 1, 6, seed=5, t_init=torch.zeros(1, 3, device=dev))
     wbar = w2d[0].mean(-1).double().cpu().numpy()
     expect = wbar / wbar.sum()
     freq = np.bincount(inds.cpu().numpy().reshape(-1), minlength=N) / P
@@ -70,7 +70,7 @@ def test_inclusion_frequencies_match_torch_multinomial(dev):
     """n of N without replacement: per-index inclusion frequency against torch.multinomial's on the same weights."""
     N, P, n = 12, 6000, 4
     w2d = _weights(1, N, 3).to(dev)
-    inds, _ = native.rslm_draw(w2d, torch.zeros(1, 3, device=dev), P, n, 6, seed=9)
+    inds, _ = native.rslm_draw(None, None, w2d, None, P, n, 6, seed=9, t_init=torch.zeros(1, 3, device=dev))
     ours = np.bincount(inds.cpu().numpy().reshape(-1), minlength=N) / P
     g = torch.Generator().manual_seed(0)
     ref_n = 60000
@@ -86,7 +86,7 @@ def test_too_few_positive_weights_completes_the_subset_in_index_order(dev):
     N, n = 10, 5
     w2d = torch.zeros(1, N, 2)
     w2d[0, [3, 7]] = 1.0
-    inds, _ = native.rslm_draw(w2d.to(dev), torch.zeros(1, 3, device=dev), 16, n, 4, seed=1)
+    inds, _ = native.rslm_draw(None, None, w2d.to(dev), None, 16, n, 4, seed=1, t_init=torch.zeros(1, 3, device=dev))
     for row in inds.cpu().numpy().reshape(-1, n):
         assert set(row) == {3, 7, 0, 1, 2}
 
@@ -95,7 +95,7 @@ def test_too_few_positive_weights_completes_the_subset_in_index_order(dev):
 def test_start_poses(dev, dof):
     B, P = 2, 4096
     t0 = torch.tensor([[0.1, -0.2, 3.0], [1.0, 2.0, 8.0]]).to(dev)
-    _, start = native.rslm_draw(_weights(B, 8, 4).to(dev), t0, P, 2, dof, seed=3)
+    _, start = native.rslm_draw(None, None, _weights(B, 8, 4).to(dev), None, P, 2, dof, seed=3, t_init=t0)
     s = start.cpu().double()
     assert torch.equal(start[..., :3], t0.expand(P, B, 3))
     if dof == 4:
@@ -112,12 +112,58 @@ def test_start_poses(dev, dof):
         assert (second - torch.eye(4, dtype=torch.float64) / 4).abs().max() < 0.02
 
 
+@pytest.mark.parametrize("dof,N", [(6, 64), (4, 51), (6, 700)])
+def test_centre_based_translation_guess_matches_the_class(dev, dof, N):
+    """The in-kernel guess (two block reductions) against RSLMSolver.center_based_init, the torch restatement of
+    levenberg_marquardt.py:283-298 (itself pinned to the reference by tests/test_host_logic_cpu.py)."""
+    B = 5
+    pc = {k: v.to(dev) for k, v in make_problem(B, N, seed=70 + N, dof=dof).items()}
+    camera = PerspectiveCamera(cam_mats=pc["cam_mats"])
+    want = RSLMSolver(dof=dof).center_based_init(pc["x2d"].double().cpu(), pc["x3d"].double().cpu(),
+                                                 PerspectiveCamera(cam_mats=pc["cam_mats"].double().cpu()))
+    inds, start, t = native.rslm_draw(pc["x3d"], pc["x2d"], pc["w2d"], pc["cam_mats"], 3, 4, dof, seed=1, want_t=True)
+    assert t.shape == (B, 3)
+    assert torch.allclose(t.double().cpu(), want, rtol=2e-5, atol=1e-6), (t, want)
+    assert torch.equal(start[..., :3], t.expand(3, B, 3))
+    # a given t_init overrides it, draw for draw the same subsets and orientations
+    inds2, start2 = native.rslm_draw(None, None, pc["w2d"], None, 3, 4, dof, seed=1, t_init=t + 1.0)
+    assert torch.equal(inds, inds2) and torch.equal(start2[..., 3:], start[..., 3:]) and torch.equal(start2[..., :3], (t + 1.0).expand(3, B, 3))
+
+
+def test_subclass_translation_guess_is_respected(dev):
+    class Fixed(RSLMSolver):
+        def center_based_init(self, x2d, x3d, camera, eps=1e-6):
+            return x2d.new_tensor([0.0, 0.0, 5.0]).expand(x2d.shape[0], 3)
+
+    seen = {}
+    real = native.rslm_draw
+
+    def spy(*a, **k):
+        seen["t_init"] = k.get("t_init")
+        return real(*a, **k)
+
+    pc = {k: v.to(dev) for k, v in make_problem(2, 32, seed=8).items()}
+    camera = PerspectiveCamera(cam_mats=pc["cam_mats"])
+    cost_fun = AdaptiveHuberPnPCost(relative_delta=0.5)
+    cost_fun.set_param(pc["x2d"], pc["w2d"])
+    native.rslm_draw = spy
+    try:
+        Fixed(dof=6, num_points=6, num_proposals=4, num_iter=2).solve(pc["x3d"], pc["x2d"], pc["w2d"], camera, cost_fun)
+        assert seen["t_init"] is not None and torch.equal(seen["t_init"].cpu(), torch.tensor([[0.0, 0.0, 5.0]] * 2))
+        RSLMSolver(dof=6, num_points=6, num_proposals=4, num_iter=2).solve(pc["x3d"], pc["x2d"], pc["w2d"], camera, cost_fun)
+        assert seen["t_init"] is None
+    finally:
+        native.rslm_draw = real
+
+
 def test_bad_arguments_are_refused(dev):
     w2d = _weights(2, 8, 5).to(dev)
     with pytest.raises(native.NativeError):
-        native.rslm_draw(w2d, torch.zeros(2, 3, device=dev), 4, 9, 6)              # n > N
+        native.rslm_draw(None, None, w2d, None, 4, 9, 6, t_init=torch.zeros(2, 3, device=dev))      # n > N
     with pytest.raises(ValueError):
-        native.rslm_draw(w2d, torch.zeros(3, 3, device=dev), 4, 2, 6)              # t_init of another batch
+        native.rslm_draw(None, None, w2d, None, 4, 2, 6, t_init=torch.zeros(3, 3, device=dev))      # t_init of another batch
+    with pytest.raises(ValueError):
+        native.rslm_draw(None, None, w2d, None, 4, 2, 6)                                            # neither t_init nor the points
     with pytest.raises(ValueError):
         RSLMSolver(dof=6, draws="numpy")
 

@@ -1,5 +1,5 @@
 """epnp_rslm_draw_f32 on a real GPU: the assertions of tests/test_rslm_draw_cpu.py (which runs them on the CPU emulation
-of the kernel), plus the emulated and the hardware kernel drawing the very same subsets."""
+of the kernel), plus a detection-sized launch."""
 import pytest
 import torch
 
@@ -20,6 +20,8 @@ test_first_pick_follows_the_weights = _cpu.test_first_pick_follows_the_weights
 test_inclusion_frequencies_match_torch_multinomial = _cpu.test_inclusion_frequencies_match_torch_multinomial
 test_too_few_positive_weights_completes_the_subset_in_index_order = _cpu.test_too_few_positive_weights_completes_the_subset_in_index_order
 test_start_poses = _cpu.test_start_poses
+test_centre_based_translation_guess_matches_the_class = _cpu.test_centre_based_translation_guess_matches_the_class
+test_subclass_translation_guess_is_respected = _cpu.test_subclass_translation_guess_is_respected
 test_bad_arguments_are_refused = _cpu.test_bad_arguments_are_refused
 test_solver_with_native_draws = _cpu.test_solver_with_native_draws
 
@@ -29,7 +31,7 @@ def test_large_batch_shapes(dev):
     B, N, P, n = 4096, 512, 64, 16
     w2d = torch.rand(B, N, 2, device=dev) + 0.01
     from epropnp_b200 import native
-    inds, start = native.rslm_draw(w2d, torch.zeros(B, 3, device=dev), P, n, 6, seed=2)
+    inds, start = native.rslm_draw(None, None, w2d, None, P, n, 6, seed=2, t_init=torch.zeros(B, 3, device=dev))
     assert inds.min() >= 0 and inds.max() < N
     s = inds.sort(dim=-1).values
     assert (s[..., 1:] != s[..., :-1]).all()

@@ -126,9 +126,8 @@ def main():
             # the draws alone (torch.multinomial on P*B rows of N weights + the start orientations): torch work of the
             # reference's own algorithm (levenberg_marquardt.py:306-324) that both paths share
             rows = pc["w2d"].mean(dim=-1).unsqueeze(0).expand(P, B, N).reshape(P * B, N)
-            row["ms_draws_torch"] = timed(lambda: (torch.multinomial(rows, npts), solver._starting_hypotheses(pc["x3d"], pc["x2d"], camera)), iters=10)
-            t0 = solver.center_based_init(pc["x2d"], pc["x3d"], camera)
-            row["ms_draws_native"] = timed(lambda: native.rslm_draw(pc["w2d"], t0, P, npts, dof, seed=1), iters=10)
+            row["ms_setup_torch"] = timed(lambda: (torch.multinomial(rows, npts), solver._starting_hypotheses(pc["x3d"], pc["x2d"], camera)), iters=10)
+            row["ms_setup_native"] = timed(lambda: native.rslm_draw(pc["x3d"], pc["x2d"], pc["w2d"], pc["cam_mats"], P, npts, dof, seed=1), iters=10)
             row["ms_solve"] = timed(lambda: solver.solve(pc["x3d"], pc["x2d"], pc["w2d"], camera, cost_fun), iters=10)
             solver_t = RSLMSolver(dof=dof, num_points=npts, num_proposals=P, num_iter=K, draws="torch")
             row["ms_solve_torch_draws"] = timed(lambda: solver_t.solve(pc["x3d"], pc["x2d"], pc["w2d"], camera, cost_fun), iters=10)

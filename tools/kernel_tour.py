@@ -32,7 +32,7 @@ def main():
                                 want_lse=True, want_loss=True, want_weights=True, want_score=True)      # mc_epilogue_kernel
         native.mc_lse_backward(out["logw"], ep["lse"], torch.randn(B, device=dev))                     # mc_lse_backward_kernel
         P, n = 64, 16
-        inds, start = native.rslm_draw(d["w2d"], d["pose_init"][:, :3], P, n, 6, seed=1)               # rslm_draw_kernel
+        inds, start = native.rslm_draw(d["x3d"], d["x2d"], d["w2d"], d["cam_mats"], P, n, 6, seed=1)               # rslm_draw_kernel
         native.rslm(prob, inds, start, native.default_params(6, lm_iter=3))                            # rslm_kernel
     torch.cuda.synchronize()
     print("kernel tour finished")

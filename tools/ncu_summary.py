@@ -39,10 +39,16 @@ UNIT_BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e
 
 
 def raw_rows(rep):
-    r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.exit("ncu failed: " + (r.stderr or r.stdout)[-800:])
-    text = r.stdout[r.stdout.index('"ID"'):] if '"ID"' in r.stdout else r.stdout
+    """`rep`: an .ncu-rep, or the saved output of `ncu -i REP --page raw --csv` (tools/revalidate.sh keeps only that for the
+    kernels off the hot path)."""
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.exit("ncu failed: " + (r.stderr or r.stdout)[-800:])
+        out = r.stdout
+    text = out[out.index('"ID"'):] if '"ID"' in out else out
     return list(csv.reader(io.StringIO(text)))
 
 
@@ -85,7 +91,7 @@ def main():
     ap.add_argument("--kernel", default="solve_kernel", help="substring of the kernel name to summarise (first match)")
     ap.add_argument("--stats-key", default=None, help="record name in profiles/kernel_stats.json, '<kernel>@<bench config>'")
     ap.add_argument("--objects", type=int, default=4096, help="objects the profiled launch processed")
-    ap.add_argument("--sass-symbol", default=None, help="substring of the mangled kernel name (default: derived from --kernel: 6DoF, non-push)")
+    ap.add_argument("--sass-symbol", default=None, help="substring of the mangled kernel name (default: derived from --kernel: the 6DoF kernels of the N = 512 bench)")
     a = ap.parse_args()
     kernels = per_kernel(raw_rows(a.report))
     hit = [(n, m) for n, m in kernels if a.kernel in n]
@@ -96,13 +102,14 @@ def main():
     keep.update({k: v for k, v in metrics.items() if k.startswith(STALLS)})
     missing = [k for k in KEEP if k not in metrics]
     out = os.path.join(ROOT, "profiles", f"{a.tag}_{a.kernel}_ncu_raw_metrics.json")
+    rel = os.path.relpath(out, ROOT)
     with open(out, "w") as f:
         json.dump(dict(kernel=name, **keep), f, indent=1)
     print("wrote", out, f"({len(keep)} metrics; not in the report: {missing})")
     if a.stats_key:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import sass_identity
-        symbol = a.sass_symbol or {"amis_kernel": "amis_kernelILi6ELb0EE", "lm_warp_kernel": "lm_warp_kernelILi6ELb1EE"}.get(a.kernel, a.kernel)
+        symbol = a.sass_symbol or {"amis_kernel": "amis_kernelILi6ELi128EE", "lm_warp_kernel": "lm_warp_kernelILi6ELb1ELi1EE"}.get(a.kernel, a.kernel)
         fp = {k: v for k, v in sass_identity.fingerprints(sass_identity.DEFAULT_LIB).items() if symbol in k}
         if len(fp) != 1:
             sys.exit(f"--sass-symbol {symbol!r} matches {sorted(fp)}")
@@ -114,10 +121,11 @@ def main():
                    duration_ms=dur, issue_active_pct=num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                    fma_pipe_pct=num("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
                    xu_pipe_pct=num("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
-                   source=f"profiles/{a.tag}_{a.kernel}_ncu_raw_metrics.json (ncu --set full --clock-control none, one launch)")
+                   source=f"{rel} (ncu --set full --clock-control none, one launch)")
         path = os.path.join(ROOT, "profiles", "kernel_stats.json")
         allrec = json.load(open(path)) if os.path.exists(path) else {}
-        allrec[a.stats_key] = rec
+        for key in a.stats_key.split(","):                  # the same kernel serves several bench configs (per-object scaling)
+            allrec[key] = rec
         with open(path, "w") as f:
             json.dump(allrec, f, indent=1, sort_keys=True)
         print("kernel_stats.json:", a.stats_key, {k: rec[k] for k in ("warp_instr_per_launch", "dram_bytes_per_launch", "duration_ms")})

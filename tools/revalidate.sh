@@ -1,7 +1,8 @@
 #!/usr/bin/env bash
 # The evidence set of a build, one GPU (everything lands in gpurun_out/):
 #   gpurun --timeout 1700 -- 'bash tools/revalidate.sh'
-#   gpurun --timeout 1200 -- 'bash tools/revalidate.sh ncu'     (second call: the ncu captures; gpurun_out is capped at 64 MiB)
+#   gpurun --timeout 1200 -- 'bash tools/revalidate.sh ncu'     (the ncu captures; gpurun_out is capped at 64 MiB)
+#   gpurun --timeout 900 -- 'bash tools/revalidate.sh side'     (only the kernels off the hot path changed)
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -17,6 +18,22 @@ run_sanitizer() {
   done
   cut -c1-200 gpurun_out/r2_sanitizer.txt
 }
+run_side_kernels() {
+  # the steps either side of the path, native against what they replaced (RSLM set-up and solve, GN-step backward, MC epilogue)
+  EPNP_BENCH_RSLM=1 EPNP_BENCH_GN_PLUS=1 EPNP_BENCH_MC_EPILOGUE=1 timeout 400 python tools/bench_configs.py > gpurun_out/r2_side_kernels.jsonl 2> gpurun_out/configs.err
+  grep -E "RSLM|pose_opt_plus|MC pose loss|training step|evaluate_pnp" gpurun_out/r2_side_kernels.jsonl | cut -c1-330
+}
+if [ "${1:-bench}" = "side" ]; then
+  # after a change that touches only the kernels off the hot path: tests, their timings, sanitizer, their ncu captures
+  rm -f gpurun_out/parity_r2.json
+  run_tests; run_side_kernels; run_sanitizer
+  for k in ${2:-rslm_draw_kernel}; do
+    timeout 200 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -o /tmp/r2_$k python tools/kernel_tour.py > /dev/null 2>&1
+    ncu -i /tmp/r2_$k.ncu-rep --page raw --csv > gpurun_out/r2_${k}_raw.csv 2>/dev/null
+    ncu -i /tmp/r2_$k.ncu-rep --page source --csv > gpurun_out/r2_${k}_source.csv 2>/dev/null
+  done
+  exit 0
+fi
 if [ "${1:-bench}" = "ncu" ]; then
   [ "${2:-}" = "with-tests" ] && { rm -f gpurun_out/parity_r2.json; run_tests; run_sanitizer; }
   # one `--set full` capture per kernel; the two hot kernels keep their report (source page), the others leave CSVs
@@ -53,9 +70,7 @@ for f in ("gpurun_out/r2_bench_1gpu.json", "gpurun_out/r2_bench_1gpu_one_batch_i
 for l in open("gpurun_out/r2_configs.jsonl"):
     j = json.loads(l); print(j["config"]["name"], round(j["value"]), "obj/s", round(j["ms_per_step"], 4), "ms; kernels", j["kernels_ms"]["lm_warp_kernel"], j["kernels_ms"]["amis_kernel"], " e2e", round(j["e2e"]["value"]), " cpu", (j.get("cpu_baseline") or {}).get("value"))
 PY
-# the steps either side of the path, native against the path they replaced (RSLM initialiser, GN-step backward, MC epilogue)
-EPNP_BENCH_RSLM=1 EPNP_BENCH_GN_PLUS=1 EPNP_BENCH_MC_EPILOGUE=1 timeout 400 python tools/bench_configs.py > gpurun_out/r2_side_kernels.jsonl 2> gpurun_out/configs.err
-grep -E "RSLM|pose_opt_plus|MC pose loss|training step|evaluate_pnp" gpurun_out/r2_side_kernels.jsonl | cut -c1-260
+run_side_kernels
 # launch list of the bench command (cold-cache, serialised: shares only)
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1

@@ -62,7 +62,7 @@ for dof, N, B, bounded in ((6, 64, 5, False), (6, 130, 3, True), (6, 51, 4, Fals
         P, n = 5, 6
         inds = torch.stack([torch.stack([torch.randperm(N, device=dev)[:n] for _ in range(B)]) for _ in range(P)])
         native.rslm(prob, inds, d["pose_init"][None].repeat(P, 1, 1), native.default_params(dof, lm_iter=2), want_all=True)
-        di, ds = native.rslm_draw(d["w2d"], d["pose_init"][:, :3], 9, n, dof, seed=3)
+        di, ds = native.rslm_draw(d["x3d"], d["x2d"], d["w2d"], d["cam_mats"], 9, n, dof, seed=3)
         check(f"{tag}: drawn subsets in range and distinct",
               di.min() >= 0 and di.max() < N and (di.sort(-1).values[..., 1:] != di.sort(-1).values[..., :-1]).all())
         native.rslm(prob, di, ds, native.default_params(dof, lm_iter=2))
