@@ -656,7 +656,7 @@ def main():
                            "note": "each kernel launched alone, CUDA events on its stream, mean over the rotating input sets"},
             "in_loop": in_loop,
             "clocks": clocks, "gpu_launches": args.steps * world * launches_per_step,
-            "kernel": ("lm_warp_kernel<6,staged> + amis_kernel<6," + ("push" if (gathering and args.gather == "push") else "local") + ">"
+            "kernel": ("lm_warp_kernel<6,staged> + amis_kernel<6>" + (", in-kernel push to the peers" if (gathering and args.gather == "push") else "")
                        if kind != "lm" else "lm_warp_kernel<6,staged>") + " (libepropnp_b200.so)",
         }
         if issue is not None:
