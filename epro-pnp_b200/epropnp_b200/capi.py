@@ -32,6 +32,8 @@ def lib_path():
 _P = ctypes.c_void_p
 _I = ctypes.c_int
 _F = ctypes.c_float
+ABI_VERSION = 2            # EPNP_ABI_VERSION of include/epropnp_b200.h
+
 _SIGNATURES = {
     "epnp_abi_version": (ctypes.c_int, []),
     "epnp_error_string": (ctypes.c_char_p, [_I]),
@@ -77,8 +79,9 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.epnp_abi_version() != 1:
-            raise NativeError("libepropnp_b200.so ABI version mismatch")
+        if handle.epnp_abi_version() != ABI_VERSION:
+            raise NativeError(f"libepropnp_b200.so ABI version {handle.epnp_abi_version()}, this package binds version "
+                              f"{ABI_VERSION}: rebuild it (python -c 'import __graft_entry__ as g; g.build()')")
         _lib = handle
     return _lib
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define EPNP_ABI_VERSION 1
+#define EPNP_ABI_VERSION 2   /* 2: epnp_rslm_draw_f32 added; the push entry point takes DEVICE arrays of peer pointers */
 
 enum {
     EPNP_OK = 0,

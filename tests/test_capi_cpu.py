@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(handle):
 
 
 def test_abi_basics(handle):
-    assert handle.epnp_abi_version() == 1
+    assert handle.epnp_abi_version() == capi.ABI_VERSION == 2
     assert handle.epnp_error_string(0) == b"ok"
     assert b"shared memory" in handle.epnp_error_string(-2)
     p = capi.default_params(6)
