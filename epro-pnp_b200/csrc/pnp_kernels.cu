@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(NT, 2) rslm_kernel(const RslmArgs r) {
 //     that is not positive is never drawn.  The race keeps its n current winners in shared memory ([slot][thread]:
 //     conflict-free) with the position of the worst of them; once the list is full an element is rejected by one
 //     multiply and compare (E >= 1 - u), and pays for a logarithm only when it might enter
-//     (~ n (1 + ln(N / n)) times per hypothesis);
+//     (~ n (1 + ln(N / n)) times per hypothesis).  With fewer hypotheses than threads several lanes share one race;
+//     the subset comes out in ascending key order (= the order of the draw);
 //   * the starting pose: that translation with a uniformly random orientation -- a normalised Gaussian quaternion,
 //     (1,0,0,0) when its norm is below eps (:318-324), or a yaw uniform on [0, 2 pi) (:316-317).
 // Philox-4x32-10 keyed by (seed; global object index, hypothesis, block): independent of B, P tiling and launch shape.
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(NT) rslm_draw_kernel(const RslmDrawArgs r) {
     EPNP_DYN_SMEM(unsigned char, smem_raw, 16);
     __shared__ float red[2 * NT];
     __shared__ float t0[3];
+    __shared__ int counts[NT];
     float* wbar = reinterpret_cast<float*>(smem_raw);                       // [N]
     float* keys = wbar + ((r.N + 3) & ~3);                                  // [n][NT]
     int* slots = reinterpret_cast<int*>(keys + (size_t)r.n * NT);           // [n][NT]
@@ -275,58 +277,95 @@ __global__ void __launch_bounds__(NT) rslm_draw_kernel(const RslmDrawArgs r) {
     __syncthreads();
     if (r.t_out && tid < 3) r.t_out[(size_t)obj * 3 + tid] = t0[tid];
     const Philox ph{(uint32_t)r.seed, (uint32_t)(r.seed >> 32)};
-    for (int h = tid; h < r.P; h += NT) {
+    // Fewer hypotheses than threads: G = 2, 4 or 8 lanes (of one warp) share a hypothesis.  Lane g races the Philox blocks
+    // g, g + G, ... into its own list, then lane 0 folds the other lanes' winners into its list.  The n smallest keys of a
+    // hypothesis do not depend on how the race was split, and the subset is written in ascending key order -- the order
+    // in which a draw without replacement produces it -- so the output does not depend on G (or P, or the batch) either.
+    int G = 1;
+    while (G < 8 && r.P * (2 * G) <= NT) G *= 2;
+    const int per_pass = NT / G, g = tid & (G - 1), nblk = (r.N + 3) >> 2;
+    for (int h0 = 0; h0 < r.P; h0 += per_pass) {
+        const int h = h0 + tid / G;
+        const bool live = h < r.P;
         int cnt = 0, worst = 0;
         float thr = -1.0f;                                                  // the largest key in the list
-        for (int i0 = 0; i0 < r.N; i0 += 4) {
-            uint32_t u[4];
-            ph(gobj, (uint32_t)h, (uint32_t)(i0 >> 2), RSLM_TAG_SUBSET, u);
+        auto offer = [&](float key, int i) {
+            if (cnt < r.n) {
+                keys[cnt * NT + tid] = key; slots[cnt * NT + tid] = i;
+                if (key > thr) { thr = key; worst = cnt; }
+                ++cnt;
+            } else if (key < thr) {
+                keys[worst * NT + tid] = key; slots[worst * NT + tid] = i;
+                thr = -1.0f;
+                for (int s = 0; s < r.n; ++s) {
+                    const float k = keys[s * NT + tid];
+                    if (k > thr) { thr = k; worst = s; }
+                }
+            }
+        };
+        if (live) {
+            for (int blk = g; blk < nblk; blk += G) {
+                uint32_t u[4];
+                ph(gobj, (uint32_t)h, (uint32_t)blk, RSLM_TAG_SUBSET, u);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int i = i0 + j;
-                if (i >= r.N) break;
-                const float w = wbar[i];
-                if (!(w > 0.0f)) continue;
-                const float uu = u01(u[j]);
-                if (cnt == r.n && (1.0f - uu) >= thr * w) continue;        // E = -log u >= 1 - u: cannot beat the worst winner
-                const float key = -fast_log(uu) / w;
-                if (cnt < r.n) {
-                    keys[cnt * NT + tid] = key; slots[cnt * NT + tid] = i;
-                    if (key > thr) { thr = key; worst = cnt; }
-                    ++cnt;
-                } else if (key < thr) {
-                    keys[worst * NT + tid] = key; slots[worst * NT + tid] = i;
-                    thr = -1.0f;
-                    for (int s = 0; s < r.n; ++s) {
-                        const float k = keys[s * NT + tid];
-                        if (k > thr) { thr = k; worst = s; }
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    const int i = 4 * blk + j;
+                    if (i >= r.N) break;
+                    const float w = wbar[i];
+                    if (!(w > 0.0f)) continue;
+                    const float uu = u01(u[j]);
+                    if (cnt == r.n && (1.0f - uu) >= thr * w) continue;    // E = -log u >= 1 - u: cannot beat the worst winner
+                    offer(-fast_log(uu) / w, i);
                 }
             }
         }
-        // fewer than n positive weights (torch.multinomial raises): complete the subset with the first unused indices
-        for (int i = 0; cnt < r.n && i < r.N; ++i) {
-            if (wbar[i] > 0.0f) continue;
-            slots[cnt * NT + tid] = i; ++cnt;
+        if (G > 1) {
+            counts[tid] = cnt;
+            __syncwarp();
+            if (live && g == 0) {
+                for (int o = 1; o < G; ++o) {
+                    const int c = counts[tid + o];
+                    for (int s = 0; s < c; ++s) offer(keys[s * NT + tid + o], slots[s * NT + tid + o]);
+                }
+            }
         }
-        int* out = r.inds + ((size_t)h * r.B + obj) * r.n;
-        for (int s = 0; s < r.n; ++s) out[s] = slots[s * NT + tid];
-        float* st = r.start + ((size_t)h * r.B + obj) * PD;
-        st[0] = t0[0]; st[1] = t0[1]; st[2] = t0[2];
-        uint32_t v[4];
-        ph(gobj, (uint32_t)h, 0u, RSLM_TAG_START, v);
-        if (DOF == 4) {
-            st[3] = u01(v[0]) * 6.283185307179586f;
-        } else {
-            float q[4];
-            box_muller(v[0], v[1], q[0], q[1]);
-            box_muller(v[2], v[3], q[2], q[3]);
-            const float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-            const bool tiny = nrm < r.eps;
-            const float inv = 1.0f / nrm;
-            st[3] = tiny ? 1.0f : q[0] * inv; st[4] = tiny ? 0.0f : q[1] * inv;
-            st[5] = tiny ? 0.0f : q[2] * inv; st[6] = tiny ? 0.0f : q[3] * inv;
+        if (live && g == 0) {
+            // ascending (key, index): insertion sort of at most n entries
+            for (int a = 1; a < cnt; ++a) {
+                const float k = keys[a * NT + tid];
+                const int i = slots[a * NT + tid];
+                int bpos = a - 1;
+                while (bpos >= 0 && (keys[bpos * NT + tid] > k || (keys[bpos * NT + tid] == k && slots[bpos * NT + tid] > i))) {
+                    keys[(bpos + 1) * NT + tid] = keys[bpos * NT + tid]; slots[(bpos + 1) * NT + tid] = slots[bpos * NT + tid];
+                    --bpos;
+                }
+                keys[(bpos + 1) * NT + tid] = k; slots[(bpos + 1) * NT + tid] = i;
+            }
+            // fewer than n positive weights (torch.multinomial raises): complete the subset with the first unused indices
+            for (int i = 0; cnt < r.n && i < r.N; ++i) {
+                if (wbar[i] > 0.0f) continue;
+                slots[cnt * NT + tid] = i; ++cnt;
+            }
+            int* out = r.inds + ((size_t)h * r.B + obj) * r.n;
+            for (int s = 0; s < r.n; ++s) out[s] = slots[s * NT + tid];
+            float* st = r.start + ((size_t)h * r.B + obj) * PD;
+            st[0] = t0[0]; st[1] = t0[1]; st[2] = t0[2];
+            uint32_t v[4];
+            ph(gobj, (uint32_t)h, 0u, RSLM_TAG_START, v);
+            if (DOF == 4) {
+                st[3] = u01(v[0]) * 6.283185307179586f;
+            } else {
+                float q[4];
+                box_muller(v[0], v[1], q[0], q[1]);
+                box_muller(v[2], v[3], q[2], q[3]);
+                const float nrm = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+                const bool tiny = nrm < r.eps;
+                const float inv = 1.0f / nrm;
+                st[3] = tiny ? 1.0f : q[0] * inv; st[4] = tiny ? 0.0f : q[1] * inv;
+                st[5] = tiny ? 0.0f : q[2] * inv; st[6] = tiny ? 0.0f : q[3] * inv;
+            }
         }
+        __syncwarp();                       // lane 0 has finished reading the other lanes' lists before they are reused
     }
 }
 

@@ -8,6 +8,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 run_tests() {
   timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/gpu_tests.log
+  timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1 | tee -a gpurun_out/gpu_tests.log
 }
 run_sanitizer() {
   : > gpurun_out/r2_sanitizer.txt
