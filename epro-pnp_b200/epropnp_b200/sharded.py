@@ -192,7 +192,7 @@ class PushGather(_DeviceHooks):
 
     There is no gather step at all: every rank keeps a ring of `depth` FULL-batch result buffers (pose_opt
     (num_obj, D), logw (num_obj, M)), exposed to the other ranks through CUDA IPC once, and the solve kernel itself
-    (native.lm_amis_fused_push -> solve_push_kernel) stores each finished object's rows into slot t mod depth of EVERY
+    (native.lm_amis_fused_push -> the AMIS kernel's push epilogue) stores each finished object's rows into slot t mod depth of EVERY
     rank's ring -- its own slice directly as the kernel's normal output, the peers' with plain stores over NVLink,
     object by object underneath the remaining CTAs' math.  What is left per batch is one 4-byte all-reduce on a side
     stream ("all ranks' kernels for batch t have finished, so every row of my slot t is in place").

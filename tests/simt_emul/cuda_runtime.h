@@ -5,8 +5,7 @@
 //
 // What this buys the CPU suite (-m "not gpu"): the REAL kernel source -- staging and pair-record packing, the
 // block reductions, the LM state machine, the AMIS loop and its shared-memory bookkeeping, the C ABI's argument
-// handling -- runs against the golden vectors without a GPU, including the build-option experiments
-// (tools/variants.py).  Missing barriers are probed by re-running with the fibers scheduled in descending and in
+// handling -- runs against the golden vectors without a GPU.  Missing barriers are probed by re-running with the fibers scheduled in descending and in
 // randomly permuted order (simt_set_schedule): results must be bit-identical.  What it cannot show: memory-model /
 // async-proxy ordering, real TMA latency (bulk copies complete synchronously here), the approximate
 // special-function units (exact libm here), performance.

@@ -68,7 +68,7 @@ def test_point_math(emul, name):
     JtJ = np.einsum("bnd,bne->bde", J, J)
     iu = np.triu_indices(dof)
     want = np.concatenate([JtJ[:, iu[0], iu[1]], np.einsum("bnd,bn->bd", J, r), g["ref64_eval_cost"][:, None]], 1)
-    # scalar form (default build) and the row-packed form kept behind EPNP_LM_PACKED: same bounds
+    # scalar form (the CTA-per-object kernels) and the row-packed form (the warp-per-object LM kernel): same bounds
     for fn in (emul.emul_normal_eq, emul.emul_normal_eq_rows):
         ne = np.zeros((B, NV), np.float32)
         fn(fptr(x3d), fptr(x2d), fptr(w2d), fptr(cam), fptr(lb), fptr(ub), fptr(delta), fptr(pose),

@@ -1,4 +1,4 @@
-"""Fused solve + in-kernel gather (epnp_lm_amis_fused_push_f32 / solve_push_kernel) under the CPU SIMT emulator: two
+"""Fused solve + in-kernel gather (epnp_lm_amis_fused_push_f32: the AMIS kernel's push epilogue) under the CPU SIMT emulator: two
 "ranks" solve the two halves of a batch, each pushing its rows into the other's full-batch buffers (plain host memory
 standing in for IPC-mapped peer memory).  Every rank's assembled buffer must equal the single-"GPU" run bit for bit,
 and rows the rank does not own must not be touched by its own launch."""

@@ -1,9 +1,8 @@
-"""2-GPU test of the fused solve + gather (sharded.PushGather -> solve_push_kernel): every rank's full-batch buffers,
+"""2-GPU test of the fused solve + gather (sharded.PushGather -> the AMIS kernel's push epilogue): every rank's full-batch buffers,
 filled by all ranks' kernels through IPC-mapped peer memory, must equal the single-GPU solve of the whole batch bit for
 bit, over more batches than the ring is deep (slot reuse) and in the overlapped use pattern (start batch t+1, then
-read batch t).  Needs two GPUs on one node.  The path has not had its first hardware run yet, so the test is also
-gated by the environment:
-    gpurun --gpus 2 -- 'EPNP_TEST_PEER_GATHER=1 timeout 300 python -m pytest tests/test_push_gather_gpu.py -q'
+read batch t).  Needs two GPUs on one node:
+    gpurun --gpus 2 -- 'timeout 300 python -m pytest tests/test_push_gather_gpu.py -q'
 """
 import os
 import socket

@@ -88,7 +88,7 @@ def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("report")
     ap.add_argument("--tag", required=True, help="file prefix under profiles/, e.g. r2")
-    ap.add_argument("--kernel", default="solve_kernel", help="substring of the kernel name to summarise (first match)")
+    ap.add_argument("--kernel", default="amis_kernel", help="substring of the kernel name to summarise (first match)")
     ap.add_argument("--stats-key", default=None, help="record name in profiles/kernel_stats.json, '<kernel>@<bench config>'")
     ap.add_argument("--objects", type=int, default=4096, help="objects the profiled launch processed")
     ap.add_argument("--sass-symbol", default=None, help="substring of the mangled kernel name (default: derived from --kernel: the 6DoF kernels of the N = 512 bench)")
