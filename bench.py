@@ -261,6 +261,28 @@ def cpu_reference_rates(cfg, steps, warmup, seconds_per_step, threads_per_worker
     return rates, len(outs) * threads_per_worker, kind, sample
 
 
+def rotating_sets(cfg):
+    """(number of rotating input sets, bytes of one set): enough that consecutive steps cannot be served from the L2."""
+    set_bytes = 28 * cfg["N"] * cfg["B"]
+    return max(2, min(16, int(math.ceil(1.15 * L2_BYTES / set_bytes)) + 1)), set_bytes
+
+
+def config_block(args, cfg, world):
+    """The `config` object of the JSON line -- the SAME for both arms (`--impl ours` / `--impl reference`): it names the
+    workload; what is specific to how the CPU arm samples it goes into that arm's `cpu_baseline.sample`."""
+    n_sets, set_bytes = rotating_sets(cfg)
+    Bg, M = cfg["B"], cfg["M"]
+    gather = ""
+    if world > 1 and cfg["kind"] == "lm_amis":
+        gather = (f", gather(pose,logw) only ({args.gather}"
+                  + (f", NCCL_MAX_CTAS={args.nccl_max_ctas}" if args.nccl_max_ctas else "") + ")"
+                  + ("" if args.gather == "push" else ", gather of batch i overlapped with solve of batch i+1"))
+    return {"workload": f"{cfg['what']}, B={Bg}/GPU, N={cfg['N']}, M={M}" + (", in-kernel Philox" if M else ""),
+            "name": args.config, "global_batch": Bg * world, "parallelism": f"batch-split x{world}{gather}",
+            "batches_in_flight": args.streams,
+            "l2": f"rotating {n_sets} input sets ({n_sets * set_bytes / 1e6:.0f} MB > 126 MB L2)"}
+
+
 def run_reference_arm(args, cfg, rank):
     if rank != 0:
         return
@@ -274,8 +296,7 @@ def run_reference_arm(args, cfg, rank):
     line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": "objects/s", "n_gpus": args.gpus,
             "steps": args.steps, "steps_run": steps, "warmup": args.warmup, "ms_per_step": 1e3 * per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{cfg['what']}, N={cfg['N']}, M={cfg['M']}; CPU arm on a bounded sample per step",
-                       "name": args.config},
+            "config": config_block(args, cfg, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": value, "unit": "objects/s", "cores": cores, "kind": kind, "sample": sample,
                              "per_step_min_max": [min(rates), max(rates)], "wall_s": el},
             "e2e": {"value": value, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -342,8 +363,7 @@ def main():
 
     # ---- synthetic inputs of this rank's shard (global object index keys the RNG, rank keys the data seed); enough
     # rotating input sets that consecutive steps cannot be served from the 126 MB L2
-    set_bytes = 28 * N_PTS * Bg
-    n_sets = max(2, min(16, int(math.ceil(1.15 * L2_BYTES / set_bytes)) + 1))
+    n_sets, set_bytes = rotating_sets(cfg)
     pc = make_problem(Bg, N_PTS, seed=1000 + rank, grid2d=cfg["grid2d"])
     sets = []
     for r in range(n_sets):
@@ -634,19 +654,11 @@ def main():
                      "kernel": dom, "warp_instr_per_object": stats["warp_instr_per_launch"] / stats["objects_per_launch"],
                      "achieved_warp_instr_per_s": issue_rate, "peak_warp_instr_per_s": issue_peak, "frac": issue_rate / issue_peak,
                      "sm_mhz_used": clk, "ncu": {k: stats.get(k) for k in ("issue_active_pct", "fma_pipe_pct", "xu_pipe_pct", "duration_ms")}}
-        gather = ""
-        if world > 1:
-            gather = (f", gather(pose,logw) only ({args.gather}"
-                      + (f", NCCL_MAX_CTAS={args.nccl_max_ctas}" if args.nccl_max_ctas else "") + ")"
-                      + ("" if args.gather == "push" else ", gather of batch i overlapped with solve of batch i+1"))
         line = {
             "metric": cfg["metric"], "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "warmup_steps_run": n_warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{cfg['what']}, B={Bg}/GPU, N={N_PTS}, M={M}" + (", in-kernel Philox" if M else ""),
-                       "name": args.config, "global_batch": B_total, "parallelism": f"batch-split x{world}{gather}",
-                       "batches_in_flight": args.streams,
-                       "l2": f"rotating {n_sets} input sets ({n_sets * set_bytes / 1e6:.0f} MB > 126 MB L2)"},
+            "config": config_block(args, cfg, world),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (stats["dram_bytes_per_launch"] * Bg / float(stats["objects_per_launch"])) if stats else None,
                          "traffic_source": stats_src, "peak_source": peak_src,
