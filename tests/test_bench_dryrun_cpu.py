@@ -88,6 +88,22 @@ def test_bench_loop_runs_and_prints_the_contract_line(monkeypatch, capsys, argv,
         assert set(e["step_interval_ms"]) == {"min", "median", "max"}
 
 
+@pytest.mark.parametrize("argv", [[], ["--config", "dense"], ["--streams", "1"]])
+def test_both_arms_name_the_same_config(monkeypatch, capsys, argv):
+    """`--impl reference` must report the workload of `--impl ours` word for word (the driver pairs the two lines by
+    metric / unit / config); what is specific to the CPU arm's sampling lives in its cpu_baseline block."""
+    import bench
+    ours = run_bench(monkeypatch, capsys, ["--no-e2e"] + argv)
+    monkeypatch.setattr(bench, "cpu_reference_rates", lambda cfg, steps, warmup, per_step: ([10.0] * steps, 8, "reference+shim", "stub"))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--batch", "2", "--steps", "3", "--warmup", "3"] + argv)
+    bench.main()
+    ref = json.loads([l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1])
+    assert ref["impl"] == "reference" and ref["gpu_launches"] == 0
+    for k in ("metric", "unit", "higher_is_better", "config", "scaling", "dtype", "data"):
+        assert ref[k] == ours[k], k
+    assert ref["cpu_baseline"]["kind"] == "reference+shim" and ref["e2e"]["value"] == ref["value"]
+
+
 @pytest.mark.parametrize("flags", [["--gather", "nccl"], ["--gather", "push"], ["--gather", "push", "--streams", "1"]])
 def test_two_rank_bench_loop_over_gloo(flags):
     """bench.py --gpus 2 as torchrun would start it, on the CPU: gloo instead of NCCL, shared-memory host tensors instead
