@@ -17,6 +17,7 @@ from epropnp.cost_fun import AdaptiveHuberPnPCost
 from epropnp.levenberg_marquardt import LMSolver, RSLMSolver
 from epropnp_b200 import native
 from epropnp_b200.synth import make_problem
+from test_oracle_rslm_cpu import RSLM_CASES, load_rslm
 
 
 @pytest.fixture
@@ -128,6 +129,24 @@ def test_centre_based_translation_guess_matches_the_class(dev, dof, N):
     # a given t_init overrides it, draw for draw the same subsets and orientations
     inds2, start2 = native.rslm_draw(None, None, pc["w2d"], None, 3, 4, dof, seed=1, t_init=t + 1.0)
     assert torch.equal(inds, inds2) and torch.equal(start2[..., 3:], start[..., 3:]) and torch.equal(start2[..., :3], (t + 1.0).expand(3, B, 3))
+
+
+@pytest.mark.parametrize("name", RSLM_CASES)
+def test_translation_guess_against_the_unmodified_reference(dev, name):
+    """tests/golden/rslm/*.npz hold the start poses the UNMODIFIED reference built (center_based_init,
+    levenberg_marquardt.py:283-298, fp64 and fp32 runs).  The class's torch restatement must reproduce the fp64 values
+    exactly, the kernel's fp32 guess to fp32 rounding -- no further from them than the reference's own fp32 run."""
+    g = load_rslm(name)
+    dof = int(g["dof"])
+    want = torch.from_numpy(g["ref64_start"][0, :, :3])
+    t64 = lambda k: torch.from_numpy(g[k]).double()
+    got64 = RSLMSolver(dof=dof).center_based_init(t64("x2d"), t64("x3d"), PerspectiveCamera(cam_mats=t64("cam_mats")))
+    assert (got64 - want).abs().max() < 1e-12 * want.abs().max()
+    t32 = lambda k: torch.from_numpy(g[k]).float().to(dev)
+    _, _, t = native.rslm_draw(t32("x3d"), t32("x2d"), t32("w2d"), t32("cam_mats"), 2, 2, dof, seed=1, want_t=True)
+    err = (t.double().cpu() - want).abs().max() / want.abs().max()
+    floor = (torch.from_numpy(g["ref32_start"][0, :, :3]).double() - want).abs().max() / want.abs().max()
+    assert err < max(2e-6, 4 * floor), (float(err), float(floor))
 
 
 def test_subclass_translation_guess_is_respected(dev):
