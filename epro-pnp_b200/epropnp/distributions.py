@@ -1,8 +1,10 @@
-"""Stand-alone versions of the two orientation proposals of the AMIS loop (reference epropnp/distributions.py).
+"""Stand-alone versions of the proposal families of the AMIS loop (reference epropnp/distributions.py, and the one
+distribution the reference takes from pyro).
 
 The kernels carry their own fused sampler / density for these (pnp_math.cuh: proposal_draw6 / proposal_logpdf6,
 draw_yaw / proposal_logpdf4); the classes here keep the public names importable and let callers and tests use the
-densities on their own.  Plain torch.distributions subclasses -- pyro is not needed.
+densities on their own (e.g. through the layer's initial_fit / gen_new_distr / estimate_params methods).  Plain
+torch.distributions subclasses -- pyro is not needed.
 """
 import math
 
@@ -48,6 +50,39 @@ class AngularCentralGaussian(Distribution):
         north_pole = torch.zeros_like(direction)
         north_pole[..., 0] = 1
         return torch.where(length < self.eps, north_pole, direction / length.clamp(min=1e-38))
+
+
+class MultivariateStudentT(Distribution):
+    """Multivariate Student-t: x = loc + L z sqrt(df / c), z ~ N(0, I_n), c ~ chi^2(df).  The translation proposal of
+    the AMIS loop with df = 3 -- the reference imports it from pyro (epropnp.py:10, call sites :224, :306); same
+    constructor arguments (df, loc, scale_tril), batch shapes broadcast.
+        log p(x) = lgamma((df+n)/2) - lgamma(df/2) - (n/2) log(df pi) - log det L - ((df+n)/2) log(1 + |L^-1 (x - loc)|^2 / df)"""
+    arg_constraints = {'df': constraints.positive, 'loc': constraints.real_vector, 'scale_tril': constraints.lower_cholesky}
+    support = constraints.real_vector
+    has_rsample = True
+
+    def __init__(self, df, loc, scale_tril, validate_args=None):
+        n = loc.size(-1)
+        if scale_tril.shape[-2:] != (n, n):
+            raise AssertionError("scale_tril must be (..., n, n) for a loc of (..., n)")
+        self.df = torch.as_tensor(df, dtype=loc.dtype, device=loc.device)
+        batch = torch.broadcast_shapes(self.df.shape, loc.shape[:-1], scale_tril.shape[:-2])
+        self.loc, self.scale_tril, self.n = loc, scale_tril, n
+        super().__init__(batch, (n,), validate_args=False)
+
+    def rsample(self, sample_shape=torch.Size()):
+        shape = self._extended_shape(sample_shape)
+        z = torch.randn(shape, dtype=self.loc.dtype, device=self.loc.device)
+        chi2 = torch.distributions.Chi2(self.df.expand(shape[:-1])).rsample()
+        y = z * torch.rsqrt(chi2 / self.df).unsqueeze(-1)
+        return self.loc + torch.einsum('...ij,...j->...i', self.scale_tril, y)
+
+    def log_prob(self, value):
+        whitened = _forward_substitute(self.scale_tril, value - self.loc)
+        n, df = self.n, self.df
+        log_norm = (self.scale_tril.diagonal(dim1=-2, dim2=-1).log().sum(-1) + 0.5 * n * torch.log(df * math.pi)
+                    + torch.lgamma(0.5 * df) - torch.lgamma(0.5 * (df + n)))
+        return -0.5 * (df + n) * torch.log1p(whitened.square().sum(-1) / df) - log_norm
 
 
 class VonMisesUniformMix(VonMises):

@@ -22,6 +22,13 @@ import torch
 from epropnp_b200 import native
 from .builder import PNP, build_pnp
 from .common import evaluate_pnp, pnp_normalize, pnp_denormalize
+from .distributions import AngularCentralGaussian, MultivariateStudentT, VonMisesUniformMix
+
+# The steps of the AMIS loop the reference exposes as methods of the layer (epropnp.py:65-82).  Here the loop runs inside
+# one kernel; the methods exist as stand-alone torch restatements (same signatures, in-place on the buffers of
+# allocate_buffer) for callers that inspect or re-use the proposals, and monte_carlo_forward refuses a subclass that
+# overrides one of them -- the kernel could not honour it.
+_AMIS_STEPS = ("allocate_buffer", "initial_fit", "gen_new_distr", "gen_old_distr", "estimate_params")
 
 
 def cholesky_wrapper(mat, default_diag=None, force_cpu=True):
@@ -71,6 +78,23 @@ class EProPnPBase(torch.nn.Module, metaclass=ABCMeta):
     def _extra_native_params(self):
         return {}
 
+    def _refuse_overridden_steps(self):
+        stock = EProPnP6DoF if self.dof == 6 else EProPnP4DoF
+        changed = [name for name in _AMIS_STEPS if getattr(type(self), name, None) is not getattr(stock, name)]
+        if changed:
+            raise NotImplementedError(
+                f"{type(self).__name__} overrides {', '.join(changed)}: the AMIS loop runs inside one kernel "
+                "(epnp_lm_amis_fused_f32) that implements these steps itself, so a custom proposal family needs its own "
+                "kernel; the methods are stand-alone restatements, not hooks of monte_carlo_forward")
+
+    @staticmethod
+    def _weighted_translation_fit(pose_samples, weights):
+        """Weighted mean (B, 3) and covariance (B, 3, 3) of the sampled translations; weights (cum, B) sum to 1 over dim 0."""
+        trans = pose_samples[..., :3]
+        mean = torch.einsum('sb,sbi->bi', weights, trans)
+        dev = trans - mean
+        return mean, torch.einsum('sb,sbi,sbj->bij', weights, dev, dev)
+
     def forward(self, *args, **kwargs):
         return self.solver(*args, **kwargs)
 
@@ -83,6 +107,7 @@ class EProPnPBase(torch.nn.Module, metaclass=ABCMeta):
             pose_samples (mc_samples, B, 4|7), pose_sample_logweights (mc_samples, B), cost_init (B) | None
         kwargs forwarded to the solver: with_pose_opt_plus, fast_mode, with_cost.
         """
+        self._refuse_overridden_steps()
         with_plus = kwargs.pop("with_pose_opt_plus", False)
         fast_mode = kwargs.pop("fast_mode", False)
         with_cost = kwargs.pop("with_cost", False)
@@ -169,6 +194,40 @@ class EProPnP4DoF(EProPnPBase):
 
     dof = 4
 
+    def allocate_buffer(self, num_obj, dtype=torch.float32, device=None):
+        """-> trans_mode (I, B, 3), trans_cov_tril (I, B, 3, 3), rot_mode (I, B, 1), rot_kappa (I, B, 1)  (:209-214)."""
+        new = lambda *shape: torch.empty((self.num_iter, num_obj) + shape, dtype=dtype, device=device)
+        return new(3), new(3, 3), new(1), new(1)
+
+    def initial_fit(self, pose_opt, pose_cov, camera, trans_mode, trans_cov_tril, rot_mode, rot_kappa):
+        """Proposal 0 from the LM solution and its covariance (:216-220)."""
+        trans_mode[0], rot_mode[0] = pose_opt[:, :3], pose_opt[:, 3:]
+        trans_cov_tril[0] = cholesky_wrapper(pose_cov[:, :3, :3], [1.0, 1.0, 4.0])
+        rot_kappa[0] = 0.33 / pose_cov[:, 3, 3, None].clamp(min=self.eps)
+
+    @staticmethod
+    def gen_new_distr(iter_id, trans_mode, trans_cov_tril, rot_mode, rot_kappa):
+        return (MultivariateStudentT(3, trans_mode[iter_id], trans_cov_tril[iter_id]),
+                VonMisesUniformMix(rot_mode[iter_id], rot_kappa[iter_id]))
+
+    @staticmethod
+    def gen_old_distr(iter_id, trans_mode, trans_cov_tril, rot_mode, rot_kappa):
+        """All earlier proposals, with a broadcast axis for the samples: batch shape (iter_id, 1, B)."""
+        return (MultivariateStudentT(3, trans_mode[:iter_id, None], trans_cov_tril[:iter_id, None]),
+                VonMisesUniformMix(rot_mode[:iter_id, None], rot_kappa[:iter_id, None]))
+
+    def estimate_params(self, iter_id, pose_samples, pose_sample_logweights, trans_mode, trans_cov_tril, rot_mode, rot_kappa):
+        """Proposal iter_id + 1 from all samples so far (cum, B, 4) and their log-weights (cum, B) (:238-260): weighted
+        translation moments; yaw mode = direction of the weighted mean resultant, concentration from its length."""
+        w = torch.softmax(pose_sample_logweights, dim=0)
+        trans_mode[iter_id + 1], cov = self._weighted_translation_fit(pose_samples, w)
+        trans_cov_tril[iter_id + 1] = cholesky_wrapper(cov, [1.0, 1.0, 4.0])
+        yaw = pose_samples[..., 3]
+        s, c = (w * yaw.sin()).sum(dim=0), (w * yaw.cos()).sum(dim=0)
+        rot_mode[iter_id + 1] = torch.atan2(s, c).unsqueeze(-1)
+        r_sq = (s.square() + c.square()).unsqueeze(-1)
+        rot_kappa[iter_id + 1] = 0.33 * r_sq.sqrt().clamp(min=self.eps) * (2 - r_sq) / (1 - r_sq).clamp(min=self.eps)
+
 
 @PNP.register_module()
 class EProPnP6DoF(EProPnPBase):
@@ -184,3 +243,52 @@ class EProPnP6DoF(EProPnPBase):
 
     def _extra_native_params(self):
         return dict(acg_mle_iter=int(self.acg_mle_iter), acg_dispersion=float(self.acg_dispersion))
+
+    def allocate_buffer(self, num_obj, dtype=torch.float32, device=None):
+        """-> trans_mode (I, B, 3), trans_cov_tril (I, B, 3, 3), rot_cov_tril (I, B, 4, 4)  (:282-286)."""
+        new = lambda *shape: torch.empty((self.num_iter, num_obj) + shape, dtype=dtype, device=device)
+        return new(3), new(3, 3), new(4, 4)
+
+    def _dispersed_tril(self, rot_cov):
+        """chol(C + det(C)^(1/4) * dispersion * I): keeps the ACG proposal from collapsing onto one orientation."""
+        eye = torch.eye(4, dtype=rot_cov.dtype, device=rot_cov.device)
+        return cholesky_wrapper(rot_cov + rot_cov.det()[:, None, None] ** 0.25 * (self.acg_dispersion * eye))
+
+    def initial_fit(self, pose_opt, pose_cov, camera, trans_mode, trans_cov_tril, rot_cov_tril):
+        """Proposal 0 from the LM solution and its covariance (:288-302): the 3-dof rotation covariance of the tangent
+        space is lifted to a 4x4 scatter matrix of the quaternion, (T S^-1 T^T + I)^-1 normalised to unit trace."""
+        trans_mode[0] = pose_opt[:, :3]
+        trans_cov_tril[0] = cholesky_wrapper(pose_cov[:, :3, :3])
+        lift = camera.get_quaternion_transfrom_mat(pose_opt[:, 3:])                       # (B, 4, 3)
+        eye = torch.eye(4, dtype=pose_opt.dtype, device=pose_opt.device)
+        scatter = torch.linalg.inv(lift @ torch.linalg.inv(pose_cov[:, 3:, 3:]) @ lift.transpose(-1, -2) + eye)
+        scatter = scatter / scatter.diagonal(dim1=-2, dim2=-1).sum(-1)[:, None, None]
+        rot_cov_tril[0] = self._dispersed_tril(scatter)
+
+    @staticmethod
+    def gen_new_distr(iter_id, trans_mode, trans_cov_tril, rot_cov_tril):
+        return (MultivariateStudentT(3, trans_mode[iter_id], trans_cov_tril[iter_id]),
+                AngularCentralGaussian(rot_cov_tril[iter_id]))
+
+    @staticmethod
+    def gen_old_distr(iter_id, trans_mode, trans_cov_tril, rot_cov_tril):
+        """All earlier proposals, with a broadcast axis for the samples: batch shape (iter_id, 1, B)."""
+        return (MultivariateStudentT(3, trans_mode[:iter_id, None], trans_cov_tril[:iter_id, None]),
+                AngularCentralGaussian(rot_cov_tril[:iter_id, None]))
+
+    def estimate_params(self, iter_id, pose_samples, pose_sample_logweights, trans_mode, trans_cov_tril, rot_cov_tril):
+        """Proposal iter_id + 1 from all samples so far (cum, B, 7) and their log-weights (cum, B) (:317-342): weighted
+        translation moments; orientation scatter by `acg_mle_iter` fixed-point steps of the weighted ACG maximum
+        likelihood, C <- sum_s w_s q_s q_s^T / (q_s^T C^-1 q_s) with the weights renormalised (+ eps I)."""
+        w = torch.softmax(pose_sample_logweights, dim=0)
+        trans_mode[iter_id + 1], cov = self._weighted_translation_fit(pose_samples, w)
+        trans_cov_tril[iter_id + 1] = cholesky_wrapper(cov)
+        q = pose_samples[..., 3:]
+        eye = torch.eye(4, dtype=q.dtype, device=q.device)
+        scatter = eye.expand(q.size(1), 4, 4)
+        for _ in range(self.acg_mle_iter):
+            mahal = torch.einsum('sbi,bij,sbj->sb', q, torch.linalg.inv(scatter), q).clamp(min=self.eps)
+            ratio = w / mahal
+            ratio = ratio / ratio.sum(dim=0)
+            scatter = torch.einsum('sb,sbi,sbj->bij', ratio, q, q) + eye * self.eps
+        rot_cov_tril[iter_id + 1] = self._dispersed_tril(scatter)
