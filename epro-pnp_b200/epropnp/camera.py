@@ -10,6 +10,23 @@ from .builder import CAMERA
 from .common import _pose_rot, skew
 
 
+def project_a(x3d, pose, cam_mats, z_min: float):
+    """Rotate, translate, apply K, clamp the depth: -> x2d_proj (*, n, 2), x3d_rot (*, n, 3), z (*, n, 1)
+    (reference camera.py:10-18; the form that also yields what the Jacobian needs)."""
+    x3d_rot = x3d @ _pose_rot(pose).transpose(-1, -2)
+    xh = (x3d_rot + pose[..., None, :3]) @ cam_mats.transpose(-1, -2)
+    z = xh[..., 2:3].clamp(min=z_min)
+    return xh[..., :2] / z, x3d_rot, z
+
+
+def project_b(x3d, pose, cam_mats, z_min: float):
+    """The same projection with K R and K t multiplied out first (cost-only evaluations): -> x2d_proj, z
+    (reference camera.py:21-30)."""
+    xh = x3d @ (cam_mats @ _pose_rot(pose)).transpose(-1, -2) + (cam_mats @ pose[..., :3, None]).transpose(-1, -2)
+    z = xh[..., 2:3].clamp(min=z_min)
+    return xh[..., :2] / z, z
+
+
 @CAMERA.register_module()
 class PerspectiveCamera(object):
 

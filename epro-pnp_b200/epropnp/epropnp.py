@@ -78,6 +78,26 @@ class EProPnPBase(torch.nn.Module, metaclass=ABCMeta):
     def _extra_native_params(self):
         return {}
 
+    @abstractmethod
+    def allocate_buffer(self, *args, **kwargs):
+        pass
+
+    @abstractmethod
+    def initial_fit(self, *args, **kwargs):
+        pass
+
+    @abstractmethod
+    def gen_new_distr(self, *args, **kwargs):
+        pass
+
+    @abstractmethod
+    def gen_old_distr(self, *args, **kwargs):
+        pass
+
+    @abstractmethod
+    def estimate_params(self, *args, **kwargs):
+        pass
+
     def _refuse_overridden_steps(self):
         stock = EProPnP6DoF if self.dof == 6 else EProPnP4DoF
         changed = [name for name in _AMIS_STEPS if getattr(type(self), name, None) is not getattr(stock, name)]

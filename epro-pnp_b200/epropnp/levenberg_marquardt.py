@@ -129,6 +129,36 @@ class LMSolver(nn.Module):
         jtj = jac_t @ jac + torch.eye(self.dof, device=jac.device, dtype=jac.dtype) * self.eps
         return -solve_wrapper(jac_t @ residual.unsqueeze(-1), jtj).squeeze(-1)
 
+    def _lm_iter(self, pose_opt, jac, residual, cost, jac_new, residual_new, cost_new, step_is_successful, radius,
+                 decrease_factor, evaluate_fun, camera):
+        """One trust-region iteration on caller-owned state, all tensors updated IN PLACE (reference :192-241; same
+        argument list).  `solve` does not call this -- its iterations run inside lm_warp_kernel (pnp_math.cuh lm_adopt /
+        lm_propose / lm_update) -- it is kept as a stand-alone torch restatement for code that drives the solver step by
+        step.  evaluate_fun(pose=, out_jacobian=, out_residual=, out_cost=) fills the given buffers, as
+        functools.partial(evaluate_pnp, ...) does.  Steps: adopt the last accepted evaluation; damped normal equations
+        (J^T J + clamp(diag) / radius + eps) step = -J^T r; evaluate the candidate; accept when the cost falls by at
+        least min_relative_decrease of what the quadratic model promised; grow / shrink the radius (Ceres' rule)."""
+        took = step_is_successful
+        jac.copy_(torch.where(took[:, None, None], jac_new, jac))
+        residual.copy_(torch.where(took[:, None], residual_new, residual))
+        cost.copy_(torch.where(took, cost_new, cost))
+        jac_t = jac.transpose(-1, -2)
+        jtj = jac_t @ jac
+        gradient = jac_t @ residual.unsqueeze(-1)
+        diag = torch.diagonal(jtj, dim1=-2, dim2=-1)
+        damping = diag.clamp(min=self.min_lm_diagonal, max=self.max_lm_diagonal) / radius[:, None] + self.eps
+        step = -solve_wrapper(gradient, jtj + torch.diag_embed(damping))
+        pose_new = self.pose_add(pose_opt, step.squeeze(-1), camera)
+        evaluate_fun(pose=pose_new, out_jacobian=jac_new, out_residual=residual_new, out_cost=cost_new)
+        predicted = -(step.transpose(-1, -2) @ (0.5 * (jtj @ step) + gradient)).flatten()
+        gain = (cost - cost_new) / predicted
+        took.copy_((gain >= self.min_relative_decrease) & (predicted > 0.0))
+        pose_opt.copy_(torch.where(took[:, None], pose_new, pose_opt))
+        grown = radius / (1.0 - (2.0 * gain - 1.0) ** 3).clamp(min=1.0 / 3.0)
+        radius.copy_(torch.where(took, grown, radius).clamp(max=self.max_trust_region_radius, min=self.eps))
+        radius.copy_(torch.where(took, radius, radius / decrease_factor))
+        decrease_factor.copy_(torch.where(took, torch.full_like(decrease_factor, 2.0), decrease_factor * 2.0))
+
     def pose_add(self, pose_opt, step, camera):
         """pose (+) step; rotations are updated on the unit-quaternion manifold (levenberg_marquardt.py:255-265)."""
         if self.dof == 4:
